@@ -1,0 +1,163 @@
+/*
+ * smart_b200 — C-ABI of the B200-native exact-string-matching scan engine.
+ *
+ * This header is the drop-in boundary for SMART's search hot path.  Every entry
+ * point is `extern "C"`, takes plain pointers and sizes, and names the reference
+ * interface it replaces (paths relative to the reference tree):
+ *
+ *   reference                                         replacement here
+ *   ------------------------------------------------  ---------------------------------
+ *   int search(uchar*,int,uchar*,int)                 sb_plugin_search(), and the per-algorithm
+ *     src/algos/include/main.h:39, one per            `search` symbols in smart_b200/host/algo_stub.c
+ *     src/algos/<name>.c (bf.c:25, kmp.c:44, ...)
+ *   double *run_time,*pre_time (main.h:34-37)         pre_ms / run_ms out-parameters (milliseconds)
+ *   OUTPUT(j) count++ (define.h:33)                   64-bit count return + optional sorted positions
+ *   XSIZE/SIGMA/WSIZE/WORD (define.h:25-32)           SB_XSIZE/SB_SIGMA/SB_WSIZE/SB_WORD
+ *   getText() text buffer in shm (smart.c:95-138)     sb_text (device-resident, possibly sharded)
+ *   textgen (textgen.c:34-54)                         sb_text_generate / sb_textgen_host
+ *   preKmp/preMp/Pre_Horspool/preBmBc/preBmGs/        sb_prep_* table builders (bit-identical tables,
+ *     preQsBc/preSo/preSA + inline HASHq/KR/QF tables   built once per pattern, uploaded to the device)
+ *
+ * Counting semantics are those of src/algos/bf.c:33-36: the number of (overlapping)
+ * start positions j in [0, n-m] with x[0..m) == y[j..j+m).  A return of -1 means
+ * "algorithm not applicable for this m" exactly where the reference algorithm
+ * returns -1 (e.g. hash3.c:31, raita.c:38, qf23.c:44).
+ *
+ * The library never reads or writes text bytes at or beyond y[n]
+ * (86 reference algorithms do).
+ */
+#ifndef SMART_B200_H
+#define SMART_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* limits, same values as src/algos/include/define.h:25-32 */
+#define SB_XSIZE 4200 /* maximal pattern length */
+#define SB_WSIZE 256  /* HASHq shift-table size */
+#define SB_SIGMA 256  /* alphabet size */
+#define SB_WORD 32    /* Shift-Or/And word size in bits */
+
+/* error codes returned where a count is expected (all < -1; -1 is "not applicable") */
+#define SB_NOT_APPLICABLE (-1LL)
+#define SB_ERR_ARG (-2LL)
+#define SB_ERR_CUDA (-3LL)
+#define SB_ERR_NOMEM (-4LL)
+
+/* flags for sb_search64 */
+#define SB_FLAG_POSITIONS 0x1u    /* fill `positions` (sorted ascending, global offsets) */
+#define SB_FLAG_NO_SKIP 0x2u      /* force the read-every-byte kernels even for skip-family algorithms */
+#define SB_FLAG_FILTER_SHIFT 0x10u  /* tuning override: force the shifted-window kernel (m <= 14 only) */
+#define SB_FLAG_FILTER_B4 0x20u     /* tuning override: aligned-block fingerprint width 4 */
+#define SB_FLAG_FILTER_B8 0x40u
+#define SB_FLAG_FILTER_B16 0x80u
+#define SB_FLAG_FILTER_B32 0x100u
+
+/* ---- algorithm registry (names are the lower-cased SMART registry names, smart.c:142) ---- */
+int sb_algo_count(void);
+const char *sb_algo_name(int algo);      /* NULL if out of range */
+int sb_algo_id(const char *name);        /* -1 if unknown */
+/* 0 if algorithm `algo` accepts pattern length m, else the reference's -1 */
+int sb_algo_applicable(int algo, int m);
+
+/* ---- device / error plumbing ---- */
+int sb_device_count(void);               /* number of visible CUDA devices, <0 on error */
+const char *sb_last_error(void);         /* thread-local message for the last failing call */
+const char *sb_version(void);
+
+/* ---- device-resident text (replaces the shm text segment of smart.c:553-568) ---- */
+typedef struct sb_text sb_text;
+
+/* Upload n host bytes, sharded over `ndev` devices (devices==NULL: devices 0..ndev-1; ndev<=0: 1 device).
+ * Each shard holds its slice plus an (SB_XSIZE-1)-byte right halo, so any m <= SB_XSIZE can be
+ * searched without re-sharding. Host bytes are only read in [0,n). */
+sb_text *sb_text_upload(const unsigned char *host, size_t n, const int *devices, int ndev);
+/* Generate n bytes ON the device(s) with the counter-based generator (see sb_textgen_host):
+ * byte i depends only on (seed, sigma, i), so shards are generated in place. sigma in [1,256]. */
+sb_text *sb_text_generate(size_t n, int sigma, uint64_t seed, const int *devices, int ndev);
+/* One process per GPU (bench.py under torchrun): this process holds only part `part` of `nparts` of a
+ * global text of n_total bytes, on `device`. Searches on such a handle count only the start positions the
+ * part owns; the caller sums the per-part counts (no collective on the data path). */
+sb_text *sb_text_generate_part(size_t n_total, int sigma, uint64_t seed, int nparts, int part, int device);
+/* host bytes of the whole text are visible to the caller; only the part's slice + halo is uploaded */
+sb_text *sb_text_upload_part(const unsigned char *host, size_t n_total, int nparts, int part, int device);
+/* the partition rule itself: part g of nparts owns global start positions [*base, *base + *own) and needs
+ * bytes [*base, *base + *len). Returns 0, -1 on bad arguments. */
+int sb_shard_range(size_t n_total, int nparts, int part, size_t *base, size_t *own, size_t *len);
+size_t sb_text_length(const sb_text *t);
+int sb_text_shards(const sb_text *t);
+/* copy text bytes [off, off+len) back to the host (tests, pattern extraction) */
+int sb_text_download(const sb_text *t, size_t off, size_t len, unsigned char *host);
+void sb_text_free(sb_text *t);
+
+/* host mirror of the device generator: writes bytes [off, off+len) of stream (seed, sigma) */
+void sb_textgen_host(unsigned char *dst, size_t off, size_t len, int sigma, uint64_t seed);
+
+/* pinned host memory for the end-to-end path (cudaHostAlloc / cudaFreeHost) */
+void *sb_host_alloc(size_t bytes);
+void sb_host_free(void *p);
+
+/* ---- the search hot path ---- */
+/* Extended entry (64-bit n and count; SURVEY.md section 8b "Extended ABI").
+ * Returns the occurrence count (>=0), SB_NOT_APPLICABLE, or an SB_ERR_* code.
+ * positions/cap are used only with SB_FLAG_POSITIONS: at most `cap` positions are written,
+ * ascending; the return value is still the full count.
+ * *pre_ms  = table build + upload (wall, ms)   -> replaces *pre_time (main.h:30)
+ * *run_ms  = scan incl. count read-back (ms)   -> replaces *run_time (main.h:31); never left 0 */
+long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m, unsigned flags,
+                      unsigned long long *positions, size_t cap, double *pre_ms, double *run_ms);
+
+typedef struct sb_timing {
+    double prep_host_ms;   /* host table build */
+    double upload_ms;      /* pattern/table H2D */
+    double kernel_ms;      /* max over shards of the CUDA-event time of the scan kernel(s) */
+    double wall_ms;        /* host wall clock, first launch -> last count on host */
+    int kernels_launched;  /* scan kernels launched by the last search (all shards) */
+    int filter_kind;       /* 0 = shifted window, 4/8/16/32 = aligned-block width, 1xx = skip kernel */
+    unsigned long long verified; /* candidates sent to exact verification (all shards) */
+} sb_timing;
+void sb_last_timing(sb_timing *out);
+
+/* Host-buffer entry: text in host memory (pinned or pageable), streamed to device 0 in chunks with an
+ * m-1 overlap, copy of chunk k+1 overlapped with the scan of chunk k. This is what the legacy
+ * `search()` plugins call, and what bench.py times as `e2e`. */
+long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned char *y, size_t n,
+                         unsigned flags, double *pre_ms, double *run_ms);
+
+/* Legacy plugin body: exact reference signature semantics (main.h:39), int n, int count.
+ * Returns -1 where the reference algorithm does; counts above INT_MAX saturate to INT_MAX. */
+int sb_plugin_search(int algo, unsigned char *x, int m, unsigned char *y, int n, double *pre_ms,
+                     double *run_ms);
+
+/* ---- pattern preprocessing stage (tables bit-identical to the reference's) ---- */
+typedef struct sb_tables {
+    int m;
+    int mpNext[SB_XSIZE + 1];   /* mp.c:26-35 */
+    int kmpNext[SB_XSIZE + 1];  /* kmp.c:27-41 */
+    int hbc[SB_SIGMA];          /* hor.c:26-30 == bm.c:27-33 (bmBc) == raita.c/tunedbm.c preBmBc */
+    int qsBc[SB_SIGMA];         /* qs.c:26-30 */
+    int suff[SB_XSIZE];         /* bm.c:36-52 */
+    int bmGs[SB_XSIZE];         /* bm.c:54-66 */
+    unsigned int soS[SB_SIGMA]; /* so.c:27-38 (first min(m,32) chars, as search_large does so.c:69-80) */
+    unsigned int soLim;
+    unsigned int saS[SB_SIGMA]; /* sa.c:27-34 */
+    unsigned int saF;           /* sa.c:45 */
+    int hashShift[SB_WSIZE];    /* hash3.c:37-55 / hash5.c / hash8.c for the q of the algorithm */
+    int hashSh1;
+    int hashQ;                  /* 0 if the algorithm is not a HASHq */
+    int krD, krHx;              /* kr.c:34-40 */
+    int qfQ, qfS;               /* qf<Q><S>.c:28-29; 0 if not a QF */
+    int qfB[1 << 18];           /* qf23.c:50-56; entries [0, 1<<(Q*S)) */
+} sb_tables;
+/* Build every table the algorithm family of `algo` uses (others are left zeroed).
+ * Returns 0, or -1 when the algorithm is not applicable to m (same rule as sb_search64). */
+int sb_prep_tables(int algo, const unsigned char *x, int m, sb_tables *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMART_B200_H */

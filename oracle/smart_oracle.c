@@ -1,0 +1,532 @@
+/*
+ * ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product.
+ *
+ * A plain-C CPU restatement of the reference's (ostafen/smart) exact-string-matching path:
+ * the brute-force result that defines every algorithm's count, the preprocessing tables of
+ * the north-star algorithm families, and each family's sequential scan.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
+ * file's shared object; nothing under smart_b200/ links or calls it.
+ *
+ * Every function cites the reference file:line it restates (paths relative to the reference
+ * tree, /root/reference in the build container).  Differences from the reference, all
+ * deliberate and result-preserving on inputs where the reference is well defined:
+ *   - lengths are size_t / counts are 64-bit (the reference uses int, main.h:39);
+ *   - nothing here reads or writes at or beyond y[n] (the reference's HASHq/Tuned-BM write
+ *     sentinels at y[n..n+m), hash3.c:61, tunedbm.c:42; QS/KR read y[n], qs.c:48, kr.c:48;
+ *     Shift-Or/And large-pattern verification can read up to m-32 bytes past y[n], so.c:85-93);
+ *     the bounded scans below stop where the sentinel would have stopped them.
+ *
+ * Parity status: PINNED.  tests/test_oracle.py checks this file against (a) the 16
+ * deterministic fixtures of the reference's own harness (src/test.c:252-382), (b) the
+ * known-answer vectors of SURVEY.md Appendix B computed with the reference sources, (c) the
+ * table-level known answers of Appendix B.2, and (d) in the build container, the reference's
+ * own search()/pre*() functions compiled unmodified into oracle/_ref (golden outputs of that
+ * run are committed under tests/golden/).
+ */
+#include <stddef.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORA_SIGMA 256
+#define ORA_WSIZE 256
+#define ORA_XSIZE 4200
+
+/* ------------------------------------------------------------------------------------------
+ * The specification of the result: src/algos/bf.c:33-36 (and the harness oracle test.c:45-56).
+ * Counts overlapping occurrences; start positions ascend. */
+unsigned long long ora_bf_count(const unsigned char *x, size_t m, const unsigned char *y, size_t n)
+{
+    unsigned long long count = 0;
+    if (m == 0 || m > n) return 0;
+    for (size_t j = 0; j + m <= n; j++) {
+        size_t i = 0;
+        while (i < m && x[i] == y[j + i]) i++;
+        if (i >= m) count++;
+    }
+    return count;
+}
+
+/* same loop, with a fast first-byte skip so the 4 GiB-scale property tests finish in seconds;
+ * the result is identical by construction (memchr only skips positions whose first byte differs) */
+unsigned long long ora_bf_count_fast(const unsigned char *x, size_t m, const unsigned char *y, size_t n)
+{
+    unsigned long long count = 0;
+    if (m == 0 || m > n) return 0;
+    const unsigned char *p = y, *end = y + (n - m + 1);
+    while (p < end) {
+        p = memchr(p, x[0], (size_t)(end - p));
+        if (!p) break;
+        if (memcmp(p, x, m) == 0) count++;
+        p++;
+    }
+    return count;
+}
+
+/* positions of bf.c's OUTPUT(j) calls (define.h:33 discards them), ascending; returns the count
+ * and writes at most cap positions */
+unsigned long long ora_bf_positions(const unsigned char *x, size_t m, const unsigned char *y, size_t n,
+                                    unsigned long long *pos, size_t cap)
+{
+    unsigned long long count = 0;
+    if (m == 0 || m > n) return 0;
+    for (size_t j = 0; j + m <= n; j++)
+        if (y[j] == x[0] && memcmp(y + j, x, m) == 0) {
+            if (count < cap) pos[count] = j;
+            count++;
+        }
+    return count;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Preprocessing tables */
+
+/* mp.c:26-35 preMp */
+void ora_pre_mp(const unsigned char *x, int m, int *mpNext)
+{
+    int i = 0, j = -1;
+    mpNext[0] = -1;
+    while (i < m) {
+        while (j > -1 && x[i] != x[j]) j = mpNext[j];
+        i++;
+        j++;
+        mpNext[i] = j;
+    }
+}
+
+/* kmp.c:27-41 preKmp */
+void ora_pre_kmp(const unsigned char *x, int m, int *kmpNext)
+{
+    int i = 0, j = -1;
+    kmpNext[0] = -1;
+    while (i < m) {
+        while (j > -1 && x[i] != x[j]) j = kmpNext[j];
+        i++;
+        j++;
+        if (i < m && x[i] == x[j])
+            kmpNext[i] = kmpNext[j];
+        else
+            kmpNext[i] = j;
+    }
+}
+
+/* hor.c:26-30 Pre_Horspool == bm.c:27-33 preBmBc (also raita.c:26-32, tunedbm.c:26-32) */
+void ora_pre_hbc(const unsigned char *x, int m, int *bc)
+{
+    for (int c = 0; c < ORA_SIGMA; c++) bc[c] = m;
+    for (int i = 0; i < m - 1; i++) bc[x[i]] = m - i - 1;
+}
+
+/* qs.c:26-30 preQsBc */
+void ora_pre_qsbc(const unsigned char *x, int m, int *bc)
+{
+    for (int c = 0; c < ORA_SIGMA; c++) bc[c] = m + 1;
+    for (int i = 0; i < m; i++) bc[x[i]] = m - i;
+}
+
+/* bm.c:36-52 suffixes */
+void ora_suffixes(const unsigned char *x, int m, int *suff)
+{
+    int f = 0, g = m - 1;
+    suff[m - 1] = m;
+    for (int i = m - 2; i >= 0; i--) {
+        if (i > g && suff[i + m - 1 - f] < i - g) {
+            suff[i] = suff[i + m - 1 - f];
+        } else {
+            if (i < g) g = i;
+            f = i;
+            while (g >= 0 && x[g] == x[g + m - 1 - f]) g--;
+            suff[i] = f - g;
+        }
+    }
+}
+
+/* bm.c:54-66 preBmGs */
+void ora_pre_bmgs(const unsigned char *x, int m, int *suff, int *bmGs)
+{
+    ora_suffixes(x, m, suff);
+    for (int i = 0; i < m; i++) bmGs[i] = m;
+    int j = 0;
+    for (int i = m - 1; i >= 0; i--)
+        if (suff[i] == i + 1)
+            for (; j < m - 1 - i; j++)
+                if (bmGs[j] == m) bmGs[j] = m - 1 - i;
+    for (int i = 0; i <= m - 2; i++) bmGs[m - 1 - suff[i]] = m - 1 - i;
+}
+
+/* so.c:27-38 preSo, called with min(m,32) as so.c:51 / so.c:74-80 do; returns lim */
+unsigned int ora_pre_so(const unsigned char *x, int m, unsigned int *S)
+{
+    unsigned int j = 1, lim = 0;
+    if (m > 32) m = 32;
+    for (int c = 0; c < ORA_SIGMA; c++) S[c] = ~0u;
+    for (int i = 0; i < m; i++, j <<= 1) {
+        S[x[i]] &= ~j;
+        lim |= j;
+    }
+    return ~(lim >> 1);
+}
+
+/* sa.c:27-34 preSA with min(m,32); returns F = 1<<(m-1) (sa.c:45) */
+unsigned int ora_pre_sa(const unsigned char *x, int m, unsigned int *S)
+{
+    unsigned int j = 1;
+    if (m > 32) m = 32;
+    for (int c = 0; c < ORA_SIGMA; c++) S[c] = 0;
+    for (int i = 0; i < m; i++, j <<= 1) S[x[i]] |= j;
+    return 1u << (m - 1);
+}
+
+/* q-gram hash of hash3.c:42-44 / hash5.c:41-46 / hash8.c:41-52 ending at s[i] */
+static unsigned ora_hq(const unsigned char *s, long long i, int q)
+{
+    unsigned h = s[i - q + 1];
+    for (int k = q - 2; k >= 0; k--) h = (h << 1) + s[i - k];
+    return h % ORA_WSIZE;
+}
+
+/* hash3.c:37-55, hash5.c:39-65, hash8.c:38-71.  The reference reads x[i-q+1..i] with the loop index
+ * left at max(q, m-1): for m == q that touches x[m], which the SMART driver sets to 0 (smart.c:313);
+ * xz must therefore provide m+1 readable bytes with xz[m] == 0. */
+void ora_pre_hashq(const unsigned char *xz, int m, int q, int *shift, int *sh1)
+{
+    int i;
+    for (i = 0; i < ORA_WSIZE; i++) shift[i] = m - q + 1;
+    shift[ora_hq(xz, q - 1, q)] = m - q;
+    for (i = q; i < m - 1; i++) shift[ora_hq(xz, i, q)] = m - 1 - i;
+    unsigned h = ora_hq(xz, i, q);
+    *sh1 = shift[h];
+    shift[h] = 0;
+    if (*sh1 == 0) *sh1 = 1;
+}
+
+/* kr.c:34-40: d = 2^(m-1), hx = sum x[i]*2^(m-1-i), int arithmetic that wraps */
+void ora_pre_kr(const unsigned char *x, int m, int *d, int *hx)
+{
+    unsigned dd = 1, h = 0;
+    for (int i = 1; i < m; i++) dd <<= 1;
+    for (int i = 0; i < m; i++) h = (h << 1) + x[i];
+    *d = (int)dd;
+    *hx = (int)h;
+}
+
+/* qf23.c:50-56 (Q,S from qf<Q><S>.c:28-29): B has 1<<(Q*S) entries */
+void ora_pre_qf(const unsigned char *x, int m, int Q, int S, int *B)
+{
+    const int asize = 1 << (Q * S);
+    const unsigned mask = (unsigned)asize - 1;
+    const int mq1 = m - Q + 1;
+    unsigned ch = 0;
+    for (int i = 0; i < asize; i++) B[i] = 0;
+    for (int i = m - 1; i >= 0; i--) {
+        ch = ((ch << S) + x[i]) & mask;
+        if (i < mq1) B[ch] |= (1 << ((m - i) % Q));
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Sequential scans of each family, bounded to y[0..n).  Each returns the count, or -1 where the
+ * reference returns -1. */
+
+/* mp.c:37-61 (table = mpNext) and kmp.c:44-68 (table = kmpNext) share the scan */
+static long long ora_scan_border(const unsigned char *x, int m, const unsigned char *y, size_t n, const int *next)
+{
+    long long count = 0;
+    int i = 0;
+    for (size_t j = 0; j < n;) {
+        while (i > -1 && x[i] != y[j]) i = next[i];
+        i++;
+        j++;
+        if (i >= m) {
+            count++;
+            i = next[i];
+        }
+    }
+    return count;
+}
+
+long long ora_search_mp(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int *next = malloc(sizeof(int) * (size_t)(m + 1));
+    ora_pre_mp(x, m, next);
+    long long c = ora_scan_border(x, m, y, n, next);
+    free(next);
+    return c;
+}
+
+long long ora_search_kmp(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int *next = malloc(sizeof(int) * (size_t)(m + 1));
+    ora_pre_kmp(x, m, next);
+    long long c = ora_scan_border(x, m, y, n, next);
+    free(next);
+    return c;
+}
+
+/* hor.c:33-51 */
+long long ora_search_hor(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int bc[ORA_SIGMA];
+    long long count = 0;
+    ora_pre_hbc(x, m, bc);
+    for (size_t s = 0; s + (size_t)m <= n; s += (size_t)bc[y[s + m - 1]]) {
+        int i = 0;
+        while (i < m && x[i] == y[s + i]) i++;
+        if (i == m) count++;
+    }
+    return count;
+}
+
+/* qs.c:32-52; the reference reads y[s+m] even when s == n-m (that is y[n]); the shift taken there
+ * cannot produce another window, so the bounded version simply stops */
+long long ora_search_qs(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int bc[ORA_SIGMA];
+    long long count = 0;
+    ora_pre_qsbc(x, m, bc);
+    for (size_t s = 0; s + (size_t)m <= n;) {
+        int i = 0;
+        while (i < m && x[i] == y[s + i]) i++;
+        if (i == m) count++;
+        if (s + (size_t)m >= n) break;
+        s += (size_t)bc[y[s + m]];
+    }
+    return count;
+}
+
+/* bm.c:69-93 */
+long long ora_search_bm(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int bc[ORA_SIGMA];
+    int *gs = malloc(sizeof(int) * (size_t)m), *suff = malloc(sizeof(int) * (size_t)m);
+    long long count = 0;
+    ora_pre_bmgs(x, m, suff, gs);
+    ora_pre_hbc(x, m, bc);
+    for (size_t j = 0; j + (size_t)m <= n;) {
+        int i = m - 1;
+        while (i >= 0 && x[i] == y[(size_t)i + j]) i--;
+        if (i < 0) {
+            count++;
+            j += (size_t)gs[0];
+        } else {
+            int a = gs[i], b = bc[y[(size_t)i + j]] - m + 1 + i;
+            j += (size_t)(a > b ? a : b);
+        }
+    }
+    free(gs);
+    free(suff);
+    return count;
+}
+
+/* raita.c:35-63: m<2 -> -1 (:38); last, middle, first character, then the rest */
+long long ora_search_raita(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int bc[ORA_SIGMA];
+    long long count = 0;
+    if (m < 2) return -1;
+    ora_pre_hbc(x, m, bc);
+    const unsigned char first = x[0], middle = x[m / 2], last = x[m - 1];
+    for (size_t j = 0; j + (size_t)m <= n;) {
+        const unsigned char c = y[j + m - 1];
+        if (last == c && middle == y[j + m / 2] && first == y[j] && memcmp(x + 1, y + j + 1, (size_t)m - 2) == 0)
+            count++;
+        j += (size_t)bc[c];
+    }
+    return count;
+}
+
+/* tunedbm.c:34-62: the reference plants m copies of x[m-1] at y[n..n+m) so the unrolled skip loop
+ * stops (:42); here the skip loop is bounded by n instead, which stops at the same window or earlier
+ * past the last valid one.  Note tunedbm.c:55 compares only m-1 bytes: the skip loop already
+ * established y[j+m-1] == x[m-1]. */
+long long ora_search_tunedbm(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int bc[ORA_SIGMA];
+    long long count = 0;
+    ora_pre_hbc(x, m, bc);
+    const int shift = bc[x[m - 1]];
+    bc[x[m - 1]] = 0;
+    for (size_t j = 0; j + (size_t)m <= n;) {
+        int k = bc[y[j + m - 1]];
+        while (k != 0) {
+            j += (size_t)k;
+            if (j + (size_t)m > n) return count;
+            k = bc[y[j + m - 1]];
+        }
+        if (memcmp(x, y + j, (size_t)m - 1) == 0) count++;
+        j += (size_t)shift;
+    }
+    return count;
+}
+
+/* so.c:40-61 for m <= 32; so.c:69-96 search_large for m > 32 (32-char prefix automaton, then the
+ * remaining characters are compared; the bounded version rejects windows that would cross y[n]) */
+long long ora_search_so(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    unsigned int S[ORA_SIGMA], D = ~0u;
+    long long count = 0;
+    const int w = m > 32 ? 32 : m;
+    const unsigned int lim = ora_pre_so(x, m, S);
+    for (size_t j = 0; j < n; j++) {
+        D = (D << 1) | S[y[j]];
+        if (D < lim) {
+            const size_t h = j + 1 - (size_t)w;
+            if (m <= 32) {
+                count++;
+            } else if (h + (size_t)m <= n) {
+                int k = 0;
+                while (k < m && x[k] == y[h + k]) k++;
+                if (k == m) count++;
+            }
+        }
+    }
+    return count;
+}
+
+/* sa.c:36-57 and sa.c:65-93, same structure with the complemented automaton */
+long long ora_search_sa(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    unsigned int S[ORA_SIGMA], D = 0;
+    long long count = 0;
+    const int w = m > 32 ? 32 : m;
+    const unsigned int F = ora_pre_sa(x, m, S);
+    for (size_t j = 0; j < n; j++) {
+        D = ((D << 1) | 1u) & S[y[j]];
+        if (D & F) {
+            const size_t h = j + 1 - (size_t)w;
+            if (m <= 32) {
+                count++;
+            } else if (h + (size_t)m <= n) {
+                int k = 0;
+                while (k < m && x[k] == y[h + k]) k++;
+                if (k == m) count++;
+            }
+        }
+    }
+    return count;
+}
+
+/* kr.c:28-53: rolling hash with REHASH (:26) in wrapping 32-bit arithmetic; the reference's last
+ * REHASH reads y[n], the bounded version skips that final (unused) update */
+long long ora_search_kr(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    long long count = 0;
+    if ((size_t)m > n) return 0;
+    unsigned d = 1, hx = 0, hy = 0;
+    for (int i = 1; i < m; i++) d <<= 1;
+    for (int i = 0; i < m; i++) {
+        hx = (hx << 1) + x[i];
+        hy = (hy << 1) + y[i];
+    }
+    for (size_t j = 0; j + (size_t)m <= n; j++) {
+        if (hx == hy && memcmp(x, y + j, (size_t)m) == 0) count++;
+        if (j + (size_t)m < n) hy = ((hy - y[j] * d) << 1) + y[j + m];
+    }
+    return count;
+}
+
+/* hash3.c:28-84, hash5.c:28-92, hash8.c:28-105: m<q -> -1.  The reference appends a copy of the
+ * pattern at y[n] so the skip loop always stops (hash3.c:61); the bounded version stops the skip
+ * loop at n, which is where the sentinel occurrence would have been found and rejected (i >= n). */
+long long ora_search_hashq(const unsigned char *x, int m, const unsigned char *y, size_t n, int q)
+{
+    int shift[ORA_WSIZE], sh1;
+    long long count = 0;
+    if (m < q) return -1;
+    if ((size_t)m > n) return 0;
+    unsigned char *xz = calloc((size_t)m + 1, 1);
+    memcpy(xz, x, (size_t)m);
+    ora_pre_hashq(xz, m, q, shift, &sh1);
+    free(xz);
+    size_t i = (size_t)m - 1;
+    while (i < n) {
+        int sh = shift[ora_hq(y, (long long)i, q)];
+        if (sh != 0) {
+            i += (size_t)sh;
+            continue;
+        }
+        if (memcmp(x, y + i - (size_t)(m - 1), (size_t)m) == 0) count++;
+        i += (size_t)sh1;
+    }
+    return count;
+}
+
+/* qf23.c:39-85 and siblings (Q,S): m<=Q -> -1 (:44).  Window ends are sampled every m-Q+1 positions,
+ * q-grams are AND-ed backwards through B, surviving alignments verified with memcmp (:61-82). */
+long long ora_search_qf(const unsigned char *x, int m, const unsigned char *y, size_t n, int Q, int S)
+{
+    long long count = 0;
+    if (m <= Q) return -1;
+    if ((size_t)m > n) return 0;
+    const int asize = 1 << (Q * S);
+    const unsigned mask = (unsigned)asize - 1;
+    const long long mq1 = m - Q + 1, nn = (long long)n;
+    int *B = malloc(sizeof(int) * (size_t)asize);
+    ora_pre_qf(x, m, Q, S, B);
+#define ORA_QGRAM(pos)                                                            \
+    ({                                                                            \
+        unsigned g_ = 0;                                                          \
+        for (int k_ = Q - 1; k_ >= 0; k_--) g_ = (g_ << S) + y[(pos) + k_];       \
+        g_ & mask;                                                                \
+    })
+    for (long long i = mq1 - 1; i <= nn - Q; i += mq1) {
+        unsigned D = (unsigned)B[ORA_QGRAM(i)];
+        if (!D) continue;
+        long long j = i - mq1 + Q;
+        int alive = 1;
+        while (1) {
+            i -= Q;
+            if (i < j) break;
+            D &= (unsigned)B[ORA_QGRAM(i)];
+            if (D == 0) {
+                alive = 0;
+                break;
+            }
+        }
+        if (!alive) continue; /* the for-increment resumes from the reduced i, as qf23.c:69 `continue` does */
+        i = j;
+        long long k = j - Q + 1;
+        if (j > nn - m) j = nn - m;
+        for (; k <= j; k++)
+            if (memcmp(y + k, x, (size_t)m) == 0) count++;
+    }
+#undef ORA_QGRAM
+    free(B);
+    return count;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Dispatcher by registry name (lower case, smart.c:142). Returns -2 for an unknown name. */
+long long ora_search(const char *algo, const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if (m < 1) return -2;
+    if (!strcmp(algo, "bf")) return (long long)ora_bf_count(x, (size_t)m, y, n);
+    if (!strcmp(algo, "mp")) return ora_search_mp(x, m, y, n);
+    if (!strcmp(algo, "kmp")) return ora_search_kmp(x, m, y, n);
+    if (!strcmp(algo, "hor")) return (size_t)m > n ? 0 : ora_search_hor(x, m, y, n);
+    if (!strcmp(algo, "qs")) return (size_t)m > n ? 0 : ora_search_qs(x, m, y, n);
+    if (!strcmp(algo, "bm")) return (size_t)m > n ? 0 : ora_search_bm(x, m, y, n);
+    if (!strcmp(algo, "raita")) return m < 2 ? -1 : ((size_t)m > n ? 0 : ora_search_raita(x, m, y, n));
+    if (!strcmp(algo, "tunedbm")) return (size_t)m > n ? 0 : ora_search_tunedbm(x, m, y, n);
+    if (!strcmp(algo, "so")) return ora_search_so(x, m, y, n);
+    if (!strcmp(algo, "sa")) return ora_search_sa(x, m, y, n);
+    if (!strcmp(algo, "kr")) return ora_search_kr(x, m, y, n);
+    if (!strncmp(algo, "hash", 4) && algo[4] && !algo[5]) return ora_search_hashq(x, m, y, n, algo[4] - '0');
+    if (!strncmp(algo, "qf", 2) && algo[2] && algo[3] && !algo[4])
+        return ora_search_qf(x, m, y, n, algo[2] - '0', algo[3] - '0');
+    return -2;
+}
+
+/* glibc rand() stream of textgen.c:34-54: srand is never called => seed 1; the stream continues
+ * across the 8 files (sigma = 2,4,...,128,250), 5 000 000 bytes each.  Writes file `which` (0..7)
+ * truncated to `len` bytes. */
+void ora_textgen(int which, unsigned char *dst, size_t len)
+{
+    static const int sigmas[8] = {2, 4, 8, 16, 32, 64, 128, 250};
+    srand(1);
+    for (int f = 0; f <= which && f < 8; f++)
+        for (size_t i = 0; i < 5000000; i++) {
+            int r = rand() % sigmas[f];
+            if (f == which && i < len) dst[i] = (unsigned char)r;
+        }
+}

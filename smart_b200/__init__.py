@@ -1,0 +1,36 @@
+"""smart_b200 — B200-native exact-string-matching scan engine behind SMART's plugin surface.
+
+The product is the C-ABI shared library ``smart_b200/lib/libsmartb200.so`` (CUDA kernels for
+sm_100a + C host preprocessing, see ``include/smart_b200.h``) and the C host programs under
+``smart_b200/host``.  This Python package is a thin ctypes binding used by the tests and by
+``bench.py``; it adds no compute of its own and has no CPU fallback.
+"""
+from .binding import (  # noqa: F401
+    ALGORITHMS,
+    FLAG_FILTER_B4,
+    FLAG_FILTER_B8,
+    FLAG_FILTER_B16,
+    FLAG_FILTER_B32,
+    FLAG_FILTER_SHIFT,
+    FLAG_NO_SKIP,
+    FLAG_POSITIONS,
+    NOT_APPLICABLE,
+    SmartB200Error,
+    Tables,
+    Text,
+    Timing,
+    algo_id,
+    applicable,
+    build_library,
+    device_count,
+    last_timing,
+    lib,
+    library_path,
+    pinned_buffer,
+    prep_tables,
+    search,
+    search_host,
+    shard_range,
+    plugin_search,
+    textgen_host,
+)

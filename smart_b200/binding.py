@@ -1,0 +1,331 @@
+"""ctypes binding of include/smart_b200.h.
+
+Argument meaning and error behaviour mirror the reference's plugin interface
+(``int search(unsigned char *x, int m, unsigned char *y, int n)``, src/algos/include/main.h:39):
+``search`` returns the occurrence count, ``NOT_APPLICABLE`` (-1) where the reference algorithm
+returns -1, and raises :class:`SmartB200Error` for anything the C layer reports as an error.
+The library is loaded from the tree (never from site-packages) and loading fails loudly if it
+has not been built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libsmartb200.so")
+
+XSIZE = 4200
+NOT_APPLICABLE = -1
+FLAG_POSITIONS = 0x1
+FLAG_NO_SKIP = 0x2
+FLAG_FILTER_SHIFT = 0x10
+FLAG_FILTER_B4 = 0x20
+FLAG_FILTER_B8 = 0x40
+FLAG_FILTER_B16 = 0x80
+FLAG_FILTER_B32 = 0x100
+
+ALGORITHMS = (
+    "bf", "mp", "kmp", "bm", "hor", "qs", "raita", "tunedbm", "so", "sa", "kr",
+    "hash3", "hash5", "hash8",
+    "qf23", "qf24", "qf26", "qf28", "qf33", "qf34", "qf36", "qf42", "qf43", "qf44", "qf62", "qf63",
+)
+
+
+class SmartB200Error(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def build_library(verbose: bool = False) -> str:
+    """Compile the CUDA/C sources in-tree for sm_100a (make in smart_b200/csrc)."""
+    out = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    if verbose or out.returncode:
+        print(out.stdout[-4000:], out.stderr[-4000:])
+    if out.returncode:
+        raise SmartB200Error("building libsmartb200.so failed")
+    return _LIB_PATH
+
+
+class Timing(C.Structure):
+    _fields_ = [
+        ("prep_host_ms", C.c_double),
+        ("upload_ms", C.c_double),
+        ("kernel_ms", C.c_double),
+        ("wall_ms", C.c_double),
+        ("kernels_launched", C.c_int),
+        ("filter_kind", C.c_int),
+        ("verified", C.c_ulonglong),
+    ]
+
+
+class Tables(C.Structure):
+    _fields_ = [
+        ("m", C.c_int),
+        ("mpNext", C.c_int * (XSIZE + 1)),
+        ("kmpNext", C.c_int * (XSIZE + 1)),
+        ("hbc", C.c_int * 256),
+        ("qsBc", C.c_int * 256),
+        ("suff", C.c_int * XSIZE),
+        ("bmGs", C.c_int * XSIZE),
+        ("soS", C.c_uint * 256),
+        ("soLim", C.c_uint),
+        ("saS", C.c_uint * 256),
+        ("saF", C.c_uint),
+        ("hashShift", C.c_int * 256),
+        ("hashSh1", C.c_int),
+        ("hashQ", C.c_int),
+        ("krD", C.c_int),
+        ("krHx", C.c_int),
+        ("qfQ", C.c_int),
+        ("qfS", C.c_int),
+        ("qfB", C.c_int * (1 << 18)),
+    ]
+
+
+_lib = None
+
+# every symbol include/smart_b200.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("sb_algo_count", C.c_int, []),
+    ("sb_algo_name", C.c_char_p, [C.c_int]),
+    ("sb_algo_id", C.c_int, [C.c_char_p]),
+    ("sb_algo_applicable", C.c_int, [C.c_int, C.c_int]),
+    ("sb_device_count", C.c_int, []),
+    ("sb_last_error", C.c_char_p, []),
+    ("sb_version", C.c_char_p, []),
+    ("sb_text_upload", C.c_void_p, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.c_int]),
+    ("sb_text_generate", C.c_void_p, [C.c_size_t, C.c_int, C.c_uint64, C.POINTER(C.c_int), C.c_int]),
+    ("sb_text_generate_part", C.c_void_p, [C.c_size_t, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int]),
+    ("sb_text_upload_part", C.c_void_p, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int]),
+    ("sb_shard_range", C.c_int, [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                 C.POINTER(C.c_size_t)]),
+    ("sb_text_length", C.c_size_t, [C.c_void_p]),
+    ("sb_text_shards", C.c_int, [C.c_void_p]),
+    ("sb_text_download", C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
+    ("sb_text_free", None, [C.c_void_p]),
+    ("sb_textgen_host", None, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_uint64]),
+    ("sb_host_alloc", C.c_void_p, [C.c_size_t]),
+    ("sb_host_free", None, [C.c_void_p]),
+    ("sb_search64", C.c_longlong, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_void_p, C.c_size_t,
+                                   C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    ("sb_last_timing", None, [C.POINTER(Timing)]),
+    ("sb_search_host", C.c_longlong, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_uint,
+                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    ("sb_plugin_search", C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                   C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    ("sb_prep_tables", C.c_int, [C.c_int, C.c_void_p, C.c_int, C.POINTER(Tables)]),
+]
+
+
+def lib() -> C.CDLL:
+    """Load the in-tree shared library (fails loudly when it is missing)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise SmartB200Error(
+                f"{_LIB_PATH} is missing: build it with `make -C smart_b200/csrc` "
+                "(or __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(_LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _err() -> str:
+    return (lib().sb_last_error() or b"").decode(errors="replace")
+
+
+def _as_bytes_ptr(buf):
+    """(pointer, length, keepalive) for bytes / bytearray / numpy uint8 arrays"""
+    if isinstance(buf, np.ndarray):
+        if buf.dtype != np.uint8 or not buf.flags["C_CONTIGUOUS"]:
+            buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        return buf.ctypes.data, buf.size, buf
+    if isinstance(buf, (bytes, bytearray, memoryview)):
+        arr = np.frombuffer(buf, dtype=np.uint8)
+        return arr.ctypes.data, arr.size, arr
+    raise TypeError(f"unsupported buffer type {type(buf)!r}")
+
+
+def device_count() -> int:
+    return lib().sb_device_count()
+
+
+def algo_id(name: str) -> int:
+    i = lib().sb_algo_id(name.encode())
+    if i < 0:
+        raise SmartB200Error(f"unknown algorithm {name!r}")
+    return i
+
+
+def applicable(name: str, m: int) -> bool:
+    return lib().sb_algo_applicable(algo_id(name), m) == 0
+
+
+def shard_range(n_total: int, nparts: int, part: int):
+    """(base, own, len) of part `part`: owns starts [base, base+own), needs bytes [base, base+len)."""
+    b, o, l = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+    if lib().sb_shard_range(n_total, nparts, part, C.byref(b), C.byref(o), C.byref(l)) != 0:
+        raise SmartB200Error("sb_shard_range: bad arguments")
+    return b.value, o.value, l.value
+
+
+def _devices(devices):
+    if devices is None:
+        return None, 1
+    arr = (C.c_int * len(devices))(*devices)
+    return arr, len(devices)
+
+
+class Text:
+    """Device-resident text (replaces SMART's shm text segment, smart.c:553-568)."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise SmartB200Error(_err())
+        self._h = C.c_void_p(handle)
+
+    @classmethod
+    def upload(cls, data, devices=None) -> "Text":
+        ptr, n, keep = _as_bytes_ptr(data)
+        dev, nd = _devices(devices)
+        return cls(lib().sb_text_upload(ptr, n, dev, nd))
+
+    @classmethod
+    def generate(cls, n: int, sigma: int, seed: int, devices=None) -> "Text":
+        dev, nd = _devices(devices)
+        return cls(lib().sb_text_generate(n, sigma, seed, dev, nd))
+
+    @classmethod
+    def generate_part(cls, n_total: int, sigma: int, seed: int, nparts: int, part: int, device: int = 0) -> "Text":
+        return cls(lib().sb_text_generate_part(n_total, sigma, seed, nparts, part, device))
+
+    @classmethod
+    def upload_part(cls, data, nparts: int, part: int, device: int = 0) -> "Text":
+        ptr, n, keep = _as_bytes_ptr(data)
+        return cls(lib().sb_text_upload_part(ptr, n, nparts, part, device))
+
+    def __len__(self) -> int:
+        return lib().sb_text_length(self._h)
+
+    @property
+    def shards(self) -> int:
+        return lib().sb_text_shards(self._h)
+
+    def download(self, off: int, length: int) -> np.ndarray:
+        out = np.empty(length, dtype=np.uint8)
+        if lib().sb_text_download(self._h, off, length, out.ctypes.data) != 0:
+            raise SmartB200Error(_err())
+        return out
+
+    def free(self):
+        if self._h:
+            lib().sb_text_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.free()
+
+
+@dataclass
+class SearchResult:
+    count: int
+    pre_ms: float
+    run_ms: float
+    positions: np.ndarray | None = None
+
+
+def last_timing() -> Timing:
+    t = Timing()
+    lib().sb_last_timing(C.byref(t))
+    return t
+
+
+def search(algo: str, text: Text, pattern, flags: int = 0, positions_cap: int = 0) -> SearchResult:
+    """sb_search64: count (and optionally sorted positions) of `pattern` in a resident text."""
+    ptr, m, keep = _as_bytes_ptr(pattern)
+    pre, run = C.c_double(0), C.c_double(0)
+    pos = None
+    pos_ptr = None
+    if flags & FLAG_POSITIONS:
+        pos = np.empty(max(positions_cap, 1), dtype=np.uint64)
+        pos_ptr = pos.ctypes.data
+    r = lib().sb_search64(algo_id(algo), text._h, ptr, m, flags, pos_ptr, positions_cap, C.byref(pre), C.byref(run))
+    if r < -1:
+        raise SmartB200Error(f"sb_search64 failed ({r}): {_err()}")
+    if pos is not None:
+        pos = pos[: max(0, min(int(r), positions_cap))]
+    return SearchResult(int(r), pre.value, run.value, pos)
+
+
+def search_host(algo: str, pattern, text, flags: int = 0) -> SearchResult:
+    """sb_search_host: text in HOST memory, streamed through device 0 (the e2e path)."""
+    pptr, m, k1 = _as_bytes_ptr(pattern)
+    tptr, n, k2 = _as_bytes_ptr(text)
+    pre, run = C.c_double(0), C.c_double(0)
+    r = lib().sb_search_host(algo_id(algo), pptr, m, tptr, n, flags, C.byref(pre), C.byref(run))
+    if r < -1:
+        raise SmartB200Error(f"sb_search_host failed ({r}): {_err()}")
+    return SearchResult(int(r), pre.value, run.value)
+
+
+def plugin_search(algo: str, pattern, text) -> int:
+    """The legacy plugin body: reference signature, int count, -1 when not applicable."""
+    pptr, m, k1 = _as_bytes_ptr(pattern)
+    tptr, n, k2 = _as_bytes_ptr(text)
+    pre, run = C.c_double(0), C.c_double(0)
+    return lib().sb_plugin_search(algo_id(algo), pptr, m, tptr, n, C.byref(pre), C.byref(run))
+
+
+def prep_tables(algo: str, pattern) -> Tables | None:
+    """Build the preprocessing tables of `algo` for `pattern` (None when not applicable)."""
+    ptr, m, keep = _as_bytes_ptr(pattern)
+    t = Tables()
+    r = lib().sb_prep_tables(algo_id(algo), ptr, m, C.byref(t))
+    if r == -1:
+        return None
+    if r != 0:
+        raise SmartB200Error("sb_prep_tables: bad argument")
+    return t
+
+
+def textgen_host(off: int, length: int, sigma: int, seed: int) -> np.ndarray:
+    out = np.empty(length, dtype=np.uint8)
+    lib().sb_textgen_host(out.ctypes.data, off, length, sigma, seed)
+    return out
+
+
+class pinned_buffer:
+    """Pinned host memory (cudaHostAlloc) exposed as a numpy uint8 array."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = lib().sb_host_alloc(nbytes)
+        if not self.ptr:
+            raise SmartB200Error(_err())
+        self.array = np.ctypeslib.as_array((C.c_ubyte * nbytes).from_address(self.ptr))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().sb_host_free(self.ptr)
+            self.ptr = None

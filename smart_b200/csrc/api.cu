@@ -1,0 +1,726 @@
+/*
+ * C-ABI implementation: device-resident (optionally sharded) text handles, the search entry
+ * points, and the host-buffer streaming path.  See include/smart_b200.h for the contract and
+ * the reference interfaces each entry point replaces.
+ *
+ * There is deliberately NO CPU fallback in this file: if CUDA is unavailable every entry point
+ * that would scan returns SB_ERR_CUDA with a message in sb_last_error().
+ */
+#include "sb_internal.h"
+#include "scan_kernels.cuh"
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <mutex>
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local sb_timing g_timing;
+
+void set_err(const char *fmt, const char *a = "", const char *b = "")
+{
+    snprintf(g_err, sizeof g_err, fmt, a, b);
+}
+
+#define CU_TRY(expr, ret)                                                     \
+    do {                                                                      \
+        cudaError_t e_ = (expr);                                              \
+        if (e_ != cudaSuccess) {                                              \
+            set_err("CUDA error in %s: %s", #expr, cudaGetErrorString(e_));   \
+            return ret;                                                       \
+        }                                                                     \
+    } while (0)
+
+double now_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+constexpr size_t kHalo = SB_XSIZE - 1;        // right halo kept with every shard
+constexpr size_t kShardAlign = 4096;          // shard bases are multiples of this
+constexpr int kMaxShards = 16;
+constexpr size_t kPatBytes = 4352;            // device pattern buffer (>= SB_XSIZE + 8, multiple of 256)
+
+struct DevCtx {                               // per-device scratch, created on first use
+    bool ready = false;
+    int dev = -1;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    uint32_t *d_pat = nullptr;                // pattern words
+    unsigned long long *d_counters = nullptr; // 4 x u64
+    unsigned long long *h_counters = nullptr; // pinned mirror
+    uint32_t *h_pat = nullptr;                // pinned staging for the pattern
+    unsigned long long *d_pos = nullptr;      // position sink, grown on demand
+    size_t pos_cap = 0;
+    int blocks_block[4] = {0, 0, 0, 0};       // resident CTAs/SM for scan_block<4,8,16,32>
+    int blocks_shift[4] = {0, 0, 0, 0};       // ... for scan_shift<HI,MASK>
+    // host-buffer streaming path
+    uint8_t *d_chunk[2] = {nullptr, nullptr};
+    size_t chunk_cap = 0;
+    cudaStream_t cstream[2] = {nullptr, nullptr};
+};
+
+DevCtx g_ctx[64];
+std::mutex g_mu;
+
+template <typename K>
+int occupancy(K kernel)
+{
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, sb::kThreads, 0) != cudaSuccess || nb < 1) nb = 1;
+    return nb;
+}
+
+DevCtx *get_ctx(int dev)
+{
+    if (dev < 0 || dev >= 64) {
+        set_err("device index out of range%s%s");
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    DevCtx &c = g_ctx[dev];
+    if (c.ready) {
+        CU_TRY(cudaSetDevice(dev), nullptr);
+        return &c;
+    }
+    CU_TRY(cudaSetDevice(dev), nullptr);
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, dev), nullptr);
+    if (prop.major < 10) {
+        set_err("smart_b200 needs an sm_100a device (B200); found %s%s", prop.name);
+        return nullptr;
+    }
+    c.dev = dev;
+    c.sms = prop.multiProcessorCount;
+    CU_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), nullptr);
+    CU_TRY(cudaStreamCreateWithFlags(&c.cstream[0], cudaStreamNonBlocking), nullptr);
+    CU_TRY(cudaStreamCreateWithFlags(&c.cstream[1], cudaStreamNonBlocking), nullptr);
+    CU_TRY(cudaEventCreate(&c.e0), nullptr);
+    CU_TRY(cudaEventCreate(&c.e1), nullptr);
+    CU_TRY(cudaMalloc(&c.d_pat, kPatBytes), nullptr);
+    CU_TRY(cudaMalloc(&c.d_counters, 4 * sizeof(unsigned long long)), nullptr);
+    CU_TRY(cudaHostAlloc(&c.h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault), nullptr);
+    CU_TRY(cudaHostAlloc(&c.h_pat, kPatBytes, cudaHostAllocDefault), nullptr);
+    c.blocks_block[0] = occupancy(sb::scan_block_kernel<4>);
+    c.blocks_block[1] = occupancy(sb::scan_block_kernel<8>);
+    c.blocks_block[2] = occupancy(sb::scan_block_kernel<16>);
+    c.blocks_block[3] = occupancy(sb::scan_block_kernel<32>);
+    c.blocks_shift[0] = occupancy(sb::scan_shift_kernel<false, false>);
+    c.blocks_shift[1] = occupancy(sb::scan_shift_kernel<false, true>);
+    c.blocks_shift[2] = occupancy(sb::scan_shift_kernel<true, false>);
+    c.blocks_shift[3] = occupancy(sb::scan_shift_kernel<true, true>);
+    c.ready = true;
+    return &c;
+}
+
+size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Shard {
+    int dev = 0;
+    uint8_t *d_text = nullptr;
+    size_t cap = 0;       // allocated bytes (group multiple + one spare group, zero padded)
+    size_t base = 0;      // global offset of local byte 0
+    size_t own = 0;       // start positions [base, base+own) belong to this shard
+    size_t len = 0;       // valid bytes in the buffer (own + halo, clipped to the text end)
+};
+
+uint32_t load_le32(const unsigned char *p, int avail)
+{
+    uint32_t w = 0;
+    for (int i = 0; i < 4 && i < avail; i++) w |= (uint32_t)p[i] << (8 * i);
+    return w;
+}
+
+uint32_t fingerprint(const unsigned char *p, int B)
+{
+    uint32_t w[8];
+    for (int i = 0; i < B / 4; i++) w[i] = load_le32(p + 4 * i, 4);
+    switch (B) {
+    case 4: return w[0];
+    case 8: return sb::fp8(w[0], w[1]);
+    case 16: return sb::fp16(w[0], w[1], w[2], w[3]);
+    default: return sb::fp32(sb::fp16(w[0], w[1], w[2], w[3]), sb::fp16(w[4], w[5], w[6], w[7]));
+    }
+}
+
+/* which kernel scans a pattern of length m: 0 = shifted window, else aligned-block width */
+int choose_filter(int m, unsigned flags)
+{
+    if ((flags & SB_FLAG_FILTER_B32) && m >= 63) return 32;
+    if ((flags & SB_FLAG_FILTER_B16) && m >= 31) return 16;
+    if ((flags & SB_FLAG_FILTER_B8) && m >= 15) return 8;
+    if ((flags & SB_FLAG_FILTER_B4) && m >= 7) return 4;
+    if ((flags & SB_FLAG_FILTER_SHIFT) && m <= 14) return 0;
+    if (m <= 14) return 0;
+    if (m < 31) return 8;
+    if (m < 63) return 16;
+    return 32;
+}
+
+struct Plan {
+    int filter;
+    sb::ScanArgs args;  // text/base/hi/ngroups/counters/pos filled per shard
+};
+
+void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m, unsigned flags)
+{
+    memset(&pl.args, 0, sizeof pl.args);
+    pl.filter = choose_filter(m, flags);
+    sb::ScanArgs &a = pl.args;
+    a.m = m;
+    a.nwords = (m + 3) / 4;
+    a.tailmask = (m & 3) ? ((1u << (8 * (m & 3))) - 1u) : 0xffffffffu;
+    if (pl.filter == 0) {
+        const int k = m < 8 ? m : 8;
+        const int k0 = k < 4 ? k : 4, k1 = k - k0;
+        a.M0 = k0 == 4 ? 0xffffffffu : ((1u << (8 * k0)) - 1u);
+        a.M1 = k1 == 4 ? 0xffffffffu : (k1 ? ((1u << (8 * k1)) - 1u) : 0u);
+        a.X0 = load_le32(x, k0) & a.M0;
+        a.X1 = k1 ? (load_le32(x + 4, k1) & a.M1) : 0u;
+        a.anchor = 0;
+    } else {
+        const int B = pl.filter;
+        a.anchor = desc->anchor == SB_ANCHOR_SUFFIX ? m - (2 * B - 1) : 0;
+        for (int d = 0; d < B; d++) a.H[d] = fingerprint(x + a.anchor + d, B);
+    }
+}
+
+/* launch the scan of one buffer on `stream`; the caller has set the device */
+cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStream_t stream)
+{
+    if (a.hi <= 0) return cudaSuccess;
+    const int m = a.m;
+    int per_sm;
+    if (pl.filter == 0) {
+        a.ngroups = ((unsigned long long)a.hi + sb::kGroupBytes - 1) / sb::kGroupBytes;
+        const bool hi = m > 4, mask = (m > 8) || a.pos != nullptr;
+        per_sm = c.blocks_shift[(hi ? 2 : 0) + (mask ? 1 : 0)];
+    } else {
+        const unsigned long long end = (unsigned long long)a.hi + a.anchor + 2 * pl.filter;
+        a.ngroups = (end + sb::kGroupBytes - 1) / sb::kGroupBytes;
+        per_sm = c.blocks_block[pl.filter == 4 ? 0 : pl.filter == 8 ? 1 : pl.filter == 16 ? 2 : 3];
+    }
+    unsigned long long want = (a.ngroups + (sb::kThreads / 32) - 1) / (sb::kThreads / 32);
+    unsigned long long maxb = (unsigned long long)c.sms * per_sm;
+    unsigned grid = (unsigned)std::max(1ull, std::min(want, maxb));
+    if (pl.filter == 0) {
+        const bool hi = m > 4, mask = (m > 8) || a.pos != nullptr;
+        if (hi && mask) sb::scan_shift_kernel<true, true><<<grid, sb::kThreads, 0, stream>>>(a);
+        else if (hi) sb::scan_shift_kernel<true, false><<<grid, sb::kThreads, 0, stream>>>(a);
+        else if (mask) sb::scan_shift_kernel<false, true><<<grid, sb::kThreads, 0, stream>>>(a);
+        else sb::scan_shift_kernel<false, false><<<grid, sb::kThreads, 0, stream>>>(a);
+    } else if (pl.filter == 4) sb::scan_block_kernel<4><<<grid, sb::kThreads, 0, stream>>>(a);
+    else if (pl.filter == 8) sb::scan_block_kernel<8><<<grid, sb::kThreads, 0, stream>>>(a);
+    else if (pl.filter == 16) sb::scan_block_kernel<16><<<grid, sb::kThreads, 0, stream>>>(a);
+    else sb::scan_block_kernel<32><<<grid, sb::kThreads, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+/* stage the pattern words for upload */
+void stage_pattern(DevCtx &c, const unsigned char *x, int m)
+{
+    memset(c.h_pat, 0, kPatBytes);
+    memcpy(c.h_pat, x, (size_t)m);
+}
+
+sb_tables *tables_scratch()
+{
+    static thread_local sb_tables *t = nullptr;
+    if (!t) t = (sb_tables *)calloc(1, sizeof(sb_tables));
+    return t;
+}
+
+int cmp_u64(const void *a, const void *b)
+{
+    unsigned long long x = *(const unsigned long long *)a, y = *(const unsigned long long *)b;
+    return x < y ? -1 : x > y;
+}
+
+}  // namespace
+
+struct sb_text {
+    size_t n = 0;
+    int nshards = 0;
+    Shard sh[kMaxShards];
+};
+
+extern "C" {
+
+const char *sb_last_error(void) { return g_err; }
+const char *sb_version(void) { return "smart_b200 0.1 (sm_100a)"; }
+
+int sb_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        set_err("cudaGetDeviceCount: %s%s", cudaGetErrorString(e));
+        return -1;
+    }
+    return n;
+}
+
+void sb_last_timing(sb_timing *out)
+{
+    if (out) *out = g_timing;
+}
+
+void *sb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        set_err("cudaHostAlloc failed%s%s");
+        return nullptr;
+    }
+    return p;
+}
+
+void sb_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+void sb_textgen_host(unsigned char *dst, size_t off, size_t len, int sigma, uint64_t seed)
+{
+    size_t i = 0;
+    while (i < len) {
+        const size_t g = off + i;
+        const unsigned long long w = sb::gen_word(seed, g >> 3, sigma);
+        for (size_t k = g & 7; k < 8 && i < len; k++, i++) dst[i] = (unsigned char)(w >> (8 * k));
+    }
+}
+
+int sb_shard_range(size_t n_total, int nparts, int part, size_t *base, size_t *own, size_t *len)
+{
+    if (nparts < 1 || part < 0 || part >= nparts) return -1;
+    const size_t slice = round_up((n_total + nparts - 1) / nparts, kShardAlign);
+    const size_t b = std::min(n_total, (size_t)part * slice);
+    const size_t o = std::min(slice, n_total - b);
+    if (base) *base = b;
+    if (own) *own = o;
+    if (len) *len = std::min(n_total - b, o + kHalo);
+    return 0;
+}
+
+/* allocate the shards [first, first+count) of an nparts-way partition of an n-byte text */
+static sb_text *text_alloc(size_t n, const int *devices, int nparts, int first, int count)
+{
+    if (nparts <= 0) nparts = 1;
+    if (count > kMaxShards || first < 0 || first + count > nparts) {
+        set_err("bad shard selection%s%s");
+        return nullptr;
+    }
+    sb_text *t = new sb_text();
+    t->n = n;
+    t->nshards = count;
+    for (int g = 0; g < count; g++) {
+        Shard &s = t->sh[g];
+        s.dev = devices ? devices[g] : g;
+        sb_shard_range(n, nparts, first + g, &s.base, &s.own, &s.len);
+        s.cap = round_up(s.len, sb::kGroupBytes) + 2 * sb::kGroupBytes;
+        DevCtx *c = get_ctx(s.dev);
+        if (!c) {
+            sb_text_free(t);
+            return nullptr;
+        }
+        if (cudaMalloc(&s.d_text, s.cap) != cudaSuccess) {
+            set_err("cudaMalloc of a text shard failed%s%s");
+            s.d_text = nullptr;
+            sb_text_free(t);
+            return nullptr;
+        }
+    }
+    return t;
+}
+
+static sb_text *text_fill_upload(sb_text *t, const unsigned char *host)
+{
+    if (!t) return nullptr;
+    for (int g = 0; g < t->nshards; g++) {
+        Shard &s = t->sh[g];
+        DevCtx *c = get_ctx(s.dev);
+        bool ok = c != nullptr;
+        ok = ok && cudaMemsetAsync(s.d_text + s.len, 0, s.cap - s.len, c->stream) == cudaSuccess;
+        ok = ok && (s.len == 0 ||
+                    cudaMemcpyAsync(s.d_text, host + s.base, s.len, cudaMemcpyHostToDevice, c->stream) == cudaSuccess);
+        if (!ok) {
+            set_err("text upload failed: %s%s", cudaGetErrorString(cudaGetLastError()));
+            sb_text_free(t);
+            return nullptr;
+        }
+    }
+    for (int g = 0; g < t->nshards; g++) {
+        DevCtx *c = get_ctx(t->sh[g].dev);
+        if (!c || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+            set_err("text upload sync failed%s%s");
+            sb_text_free(t);
+            return nullptr;
+        }
+    }
+    return t;
+}
+
+static sb_text *text_fill_generate(sb_text *t, int sigma, uint64_t seed)
+{
+    if (!t) return nullptr;
+    for (int g = 0; g < t->nshards; g++) {
+        Shard &s = t->sh[g];
+        DevCtx *c = get_ctx(s.dev);
+        if (!c) {
+            sb_text_free(t);
+            return nullptr;
+        }
+        const unsigned long long nvec = s.cap / 16;
+        // bytes past the shard's valid length must read as zero: generate up to base+len only
+        sb::textgen_kernel<<<c->sms * 8, 256, 0, c->stream>>>(reinterpret_cast<uint4 *>(s.d_text), nvec, s.base,
+                                                              s.base + s.len, seed, sigma);
+        if (cudaGetLastError() != cudaSuccess) {
+            set_err("textgen launch failed%s%s");
+            sb_text_free(t);
+            return nullptr;
+        }
+    }
+    for (int g = 0; g < t->nshards; g++) {
+        DevCtx *c = get_ctx(t->sh[g].dev);
+        cudaError_t e = c ? cudaStreamSynchronize(c->stream) : cudaErrorUnknown;
+        if (e != cudaSuccess) {
+            set_err("textgen failed: %s%s", cudaGetErrorString(e));
+            sb_text_free(t);
+            return nullptr;
+        }
+    }
+    return t;
+}
+
+sb_text *sb_text_upload(const unsigned char *host, size_t n, const int *devices, int ndev)
+{
+    if (!host && n) {
+        set_err("null host text%s%s");
+        return nullptr;
+    }
+    if (ndev <= 0) ndev = 1;
+    return text_fill_upload(text_alloc(n, devices, ndev, 0, ndev), host);
+}
+
+sb_text *sb_text_upload_part(const unsigned char *host, size_t n_total, int nparts, int part, int device)
+{
+    if (!host && n_total) {
+        set_err("null host text%s%s");
+        return nullptr;
+    }
+    return text_fill_upload(text_alloc(n_total, &device, nparts, part, 1), host);
+}
+
+sb_text *sb_text_generate(size_t n, int sigma, uint64_t seed, const int *devices, int ndev)
+{
+    if (sigma < 1 || sigma > 256) {
+        set_err("sigma out of range%s%s");
+        return nullptr;
+    }
+    if (ndev <= 0) ndev = 1;
+    return text_fill_generate(text_alloc(n, devices, ndev, 0, ndev), sigma, seed);
+}
+
+sb_text *sb_text_generate_part(size_t n_total, int sigma, uint64_t seed, int nparts, int part, int device)
+{
+    if (sigma < 1 || sigma > 256) {
+        set_err("sigma out of range%s%s");
+        return nullptr;
+    }
+    return text_fill_generate(text_alloc(n_total, &device, nparts, part, 1), sigma, seed);
+}
+
+size_t sb_text_length(const sb_text *t) { return t ? t->n : 0; }
+int sb_text_shards(const sb_text *t) { return t ? t->nshards : 0; }
+
+int sb_text_download(const sb_text *t, size_t off, size_t len, unsigned char *host)
+{
+    if (!t || off > t->n || len > t->n - off || (!host && len)) {
+        set_err("bad range in sb_text_download%s%s");
+        return -1;
+    }
+    size_t done = 0;
+    while (done < len) {
+        const size_t g_off = off + done;
+        int g = 0;
+        while (g + 1 < t->nshards && g_off >= t->sh[g].base + t->sh[g].own) g++;
+        const Shard &s = t->sh[g];
+        if (g_off < s.base || g_off >= s.base + s.len) {
+            set_err("sb_text_download: range not held by this handle%s%s");
+            return -1;
+        }
+        const size_t local = g_off - s.base;
+        const size_t take = std::min(len - done, s.len - local);
+        CU_TRY(cudaSetDevice(s.dev), -1);
+        CU_TRY(cudaMemcpy(host + done, s.d_text + local, take, cudaMemcpyDeviceToHost), -1);
+        done += take;
+    }
+    return 0;
+}
+
+void sb_text_free(sb_text *t)
+{
+    if (!t) return;
+    for (int g = 0; g < t->nshards; g++)
+        if (t->sh[g].d_text) {
+            cudaSetDevice(t->sh[g].dev);
+            cudaFree(t->sh[g].d_text);
+        }
+    delete t;
+}
+
+long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m, unsigned flags,
+                      unsigned long long *positions, size_t cap, double *pre_ms, double *run_ms)
+{
+    const sb_algo_desc *desc = sb_algo_desc_get(algo);
+    if (!desc || !t || !x || m < 1 || m > SB_XSIZE) {
+        set_err("bad argument to sb_search64 (algo/text/pattern/m)%s%s");
+        return SB_ERR_ARG;
+    }
+    const bool want_pos = (flags & SB_FLAG_POSITIONS) != 0;
+    if (want_pos && !positions && cap) {
+        set_err("SB_FLAG_POSITIONS needs a positions buffer%s%s");
+        return SB_ERR_ARG;
+    }
+    memset(&g_timing, 0, sizeof g_timing);
+    if (pre_ms) *pre_ms = 0;
+    if (run_ms) *run_ms = 0;
+    if (m < desc->min_m) return SB_NOT_APPLICABLE;
+
+    /* ---- preprocessing stage: tables + fingerprints on the host, then upload ---- */
+    const double t0 = now_ms();
+    sb_tables *tab = tables_scratch();
+    if (!tab) return SB_ERR_NOMEM;
+    sb_prep_tables(algo, x, m, tab);
+    Plan pl;
+    make_plan(pl, desc, x, m, flags);
+    const double t1 = now_ms();
+
+    DevCtx *ctx[kMaxShards];
+    for (int g = 0; g < t->nshards; g++) {
+        ctx[g] = get_ctx(t->sh[g].dev);
+        if (!ctx[g]) return SB_ERR_CUDA;
+        // one pattern upload per DEVICE (shards may share a device in tests)
+        bool first = true;
+        for (int k = 0; k < g; k++) first = first && (t->sh[k].dev != t->sh[g].dev);
+        if (!first) continue;
+        stage_pattern(*ctx[g], x, m);
+        CU_TRY(cudaMemcpyAsync(ctx[g]->d_pat, ctx[g]->h_pat, round_up((size_t)m + 8, 16), cudaMemcpyHostToDevice,
+                               ctx[g]->stream),
+               SB_ERR_CUDA);
+        CU_TRY(cudaMemsetAsync(ctx[g]->d_counters, 0, 4 * sizeof(unsigned long long), ctx[g]->stream), SB_ERR_CUDA);
+    }
+    for (int g = 0; g < t->nshards; g++) {
+        CU_TRY(cudaSetDevice(t->sh[g].dev), SB_ERR_CUDA);
+        CU_TRY(cudaStreamSynchronize(ctx[g]->stream), SB_ERR_CUDA);
+    }
+    const double t2 = now_ms();
+
+    /* ---- scan: one kernel per shard, all devices concurrently ---- */
+    const long long total_starts = (long long)t->n - m + 1;
+    int launched = 0;
+    bool dev_first[kMaxShards];
+    for (int g = 0; g < t->nshards; g++) {
+        const Shard &s = t->sh[g];
+        DevCtx &c = *ctx[g];
+        dev_first[g] = true;
+        for (int k = 0; k < g; k++) dev_first[g] = dev_first[g] && (t->sh[k].dev != s.dev);
+        CU_TRY(cudaSetDevice(s.dev), SB_ERR_CUDA);
+        sb::ScanArgs a = pl.args;
+        a.text = reinterpret_cast<const uint4 *>(s.d_text);
+        a.pat = c.d_pat;
+        a.counters = c.d_counters;
+        a.base = s.base;
+        long long hi = total_starts - (long long)s.base;
+        if (hi > (long long)s.own) hi = (long long)s.own;
+        a.hi = hi > 0 ? hi : 0;
+        a.pos = nullptr;
+        a.pos_cap = 0;
+        if (want_pos && a.hi > 0) {
+            // a device shared by several shards (tests) appends to one sink
+            size_t need = std::min((size_t)cap, (size_t)total_starts > 0 ? (size_t)total_starts : 0);
+            if (need < 1) need = 1;
+            if (c.pos_cap < need) {
+                CU_TRY(cudaStreamSynchronize(c.stream), SB_ERR_CUDA);
+                if (c.d_pos) cudaFree(c.d_pos);
+                c.d_pos = nullptr;
+                c.pos_cap = 0;
+                if (cudaMalloc(&c.d_pos, need * sizeof(unsigned long long)) != cudaSuccess) {
+                    set_err("cudaMalloc of the position sink failed%s%s");
+                    return SB_ERR_NOMEM;
+                }
+                c.pos_cap = need;
+            }
+            a.pos = c.d_pos;
+            a.pos_cap = need;
+        }
+        if (dev_first[g]) CU_TRY(cudaEventRecord(c.e0, c.stream), SB_ERR_CUDA);
+        if (a.hi > 0) {
+            CU_TRY(launch_scan(c, pl, a, c.stream), SB_ERR_CUDA);
+            launched++;
+        }
+    }
+    for (int g = t->nshards - 1; g >= 0; g--) {
+        // last shard of each device records the end event and the counter read-back
+        bool last = true;
+        for (int k = g + 1; k < t->nshards; k++) last = last && (t->sh[k].dev != t->sh[g].dev);
+        if (!last) continue;
+        DevCtx &c = *ctx[g];
+        CU_TRY(cudaSetDevice(t->sh[g].dev), SB_ERR_CUDA);
+        CU_TRY(cudaEventRecord(c.e1, c.stream), SB_ERR_CUDA);
+        CU_TRY(cudaMemcpyAsync(c.h_counters, c.d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                               c.stream),
+               SB_ERR_CUDA);
+    }
+    unsigned long long total = 0, verified = 0;
+    double kernel_ms = 0;
+    size_t written = 0;
+    for (int g = 0; g < t->nshards; g++) {
+        if (!dev_first[g]) continue;
+        DevCtx &c = *ctx[g];
+        CU_TRY(cudaSetDevice(t->sh[g].dev), SB_ERR_CUDA);
+        CU_TRY(cudaStreamSynchronize(c.stream), SB_ERR_CUDA);
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, c.e0, c.e1), SB_ERR_CUDA);
+        kernel_ms = std::max(kernel_ms, (double)ms);
+        total += c.h_counters[0];
+        verified += c.h_counters[2];
+        if (want_pos && positions) {
+            // all shards on this device appended to one sink; positions are global offsets
+            size_t have = (size_t)std::min<unsigned long long>(c.h_counters[1], c.pos_cap);
+            size_t take = std::min(have, cap - written);
+            if (take) {
+                // sort needs the full device list: fetch `have`, keep the smallest `take`
+                unsigned long long *tmp = (unsigned long long *)malloc(have * sizeof(unsigned long long));
+                if (!tmp) return SB_ERR_NOMEM;
+                CU_TRY(cudaMemcpy(tmp, c.d_pos, have * sizeof(unsigned long long), cudaMemcpyDeviceToHost),
+                       SB_ERR_CUDA);
+                qsort(tmp, have, sizeof(unsigned long long), cmp_u64);
+                memcpy(positions + written, tmp, take * sizeof(unsigned long long));
+                free(tmp);
+                written += take;
+            }
+        }
+    }
+    if (want_pos && positions && t->nshards > 1 && written > 1)
+        qsort(positions, written, sizeof(unsigned long long), cmp_u64);
+    const double t3 = now_ms();
+
+    g_timing.prep_host_ms = t1 - t0;
+    g_timing.upload_ms = t2 - t1;
+    g_timing.kernel_ms = kernel_ms;
+    g_timing.wall_ms = t3 - t2;
+    g_timing.kernels_launched = launched;
+    g_timing.filter_kind = pl.filter;
+    g_timing.verified = verified;
+    if (pre_ms) *pre_ms = t2 - t0;
+    if (run_ms) *run_ms = (t3 - t2) > 0 ? (t3 - t2) : 1e-6;
+    return (long long)total;
+}
+
+long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned char *y, size_t n, unsigned flags,
+                         double *pre_ms, double *run_ms)
+{
+    const sb_algo_desc *desc = sb_algo_desc_get(algo);
+    if (!desc || !x || (!y && n) || m < 1 || m > SB_XSIZE) {
+        set_err("bad argument to sb_search_host%s%s");
+        return SB_ERR_ARG;
+    }
+    memset(&g_timing, 0, sizeof g_timing);
+    if (pre_ms) *pre_ms = 0;
+    if (run_ms) *run_ms = 0;
+    if (m < desc->min_m) return SB_NOT_APPLICABLE;
+    DevCtx *c = get_ctx(0);
+    if (!c) return SB_ERR_CUDA;
+
+    const double t0 = now_ms();
+    sb_tables *tab = tables_scratch();
+    if (!tab) return SB_ERR_NOMEM;
+    sb_prep_tables(algo, x, m, tab);
+    Plan pl;
+    make_plan(pl, desc, x, m, flags & ~SB_FLAG_POSITIONS);
+    const double t1 = now_ms();
+
+    /* chunk buffers: 64 MiB of start positions + halo each, double buffered */
+    const size_t kChunk = (size_t)64 << 20;
+    const size_t chunk = std::min(kChunk, round_up(n ? n : 1, kShardAlign));
+    const size_t need = round_up(chunk + kHalo, sb::kGroupBytes) + 2 * sb::kGroupBytes;
+    if (c->chunk_cap < need) {
+        for (int b = 0; b < 2; b++) {
+            if (c->d_chunk[b]) cudaFree(c->d_chunk[b]);
+            c->d_chunk[b] = nullptr;
+        }
+        c->chunk_cap = 0;
+        for (int b = 0; b < 2; b++) {
+            if (cudaMalloc(&c->d_chunk[b], need) != cudaSuccess) {
+                set_err("cudaMalloc of a streaming chunk failed%s%s");
+                return SB_ERR_NOMEM;
+            }
+            CU_TRY(cudaMemset(c->d_chunk[b], 0, need), SB_ERR_CUDA);
+        }
+        c->chunk_cap = need;
+    }
+    stage_pattern(*c, x, m);
+    CU_TRY(cudaMemcpyAsync(c->d_pat, c->h_pat, round_up((size_t)m + 8, 16), cudaMemcpyHostToDevice, c->stream),
+           SB_ERR_CUDA);
+    CU_TRY(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream), SB_ERR_CUDA);
+    CU_TRY(cudaStreamSynchronize(c->stream), SB_ERR_CUDA);
+    const double t2 = now_ms();
+
+    const long long total_starts = (long long)n - m + 1;
+    int launched = 0;
+    size_t k = 0;
+    for (size_t base = 0; (long long)base < total_starts; base += chunk, k++) {
+        const int b = (int)(k & 1);
+        const size_t len = std::min(n - base, chunk + (size_t)m - 1);
+        long long hi = std::min<long long>(total_starts - (long long)base, (long long)chunk);
+        CU_TRY(cudaMemcpyAsync(c->d_chunk[b], y + base, len, cudaMemcpyHostToDevice, c->cstream[b]), SB_ERR_CUDA);
+        // bytes past `len` may be stale from an earlier chunk: zero what the last group can touch
+        const size_t pad_end = std::min(c->chunk_cap, round_up(len, sb::kGroupBytes) + 2 * sb::kGroupBytes);
+        CU_TRY(cudaMemsetAsync(c->d_chunk[b] + len, 0, pad_end - len, c->cstream[b]), SB_ERR_CUDA);
+        sb::ScanArgs a = pl.args;
+        a.text = reinterpret_cast<const uint4 *>(c->d_chunk[b]);
+        a.pat = c->d_pat;
+        a.counters = c->d_counters;
+        a.base = base;
+        a.hi = hi;
+        CU_TRY(launch_scan(*c, pl, a, c->cstream[b]), SB_ERR_CUDA);
+        launched++;
+    }
+    CU_TRY(cudaStreamSynchronize(c->cstream[0]), SB_ERR_CUDA);
+    CU_TRY(cudaStreamSynchronize(c->cstream[1]), SB_ERR_CUDA);
+    CU_TRY(cudaMemcpy(c->h_counters, c->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost),
+           SB_ERR_CUDA);
+    const double t3 = now_ms();
+    g_timing.prep_host_ms = t1 - t0;
+    g_timing.upload_ms = t2 - t1;
+    g_timing.wall_ms = t3 - t2;
+    g_timing.kernels_launched = launched;
+    g_timing.filter_kind = pl.filter;
+    g_timing.verified = c->h_counters[2];
+    if (pre_ms) *pre_ms = t2 - t0;
+    if (run_ms) *run_ms = (t3 - t2) > 0 ? (t3 - t2) : 1e-6;
+    return (long long)c->h_counters[0];
+}
+
+int sb_plugin_search(int algo, unsigned char *x, int m, unsigned char *y, int n, double *pre_ms, double *run_ms)
+{
+    if (n < 0) return -1;
+    long long r = sb_search_host(algo, x, m, y, (size_t)n, 0, pre_ms, run_ms);
+    if (r == SB_NOT_APPLICABLE) return -1;
+    if (r < 0) {
+        fprintf(stderr, "smart_b200: %s\n", sb_last_error());
+        return -1;
+    }
+    return r > INT_MAX ? INT_MAX : (int)r;
+}
+
+}  // extern "C"

@@ -1,0 +1,302 @@
+/*
+ * Pattern-preprocessing stage (host side, C): the per-algorithm tables of the SMART
+ * algorithm families, built once per pattern and then uploaded to the device.
+ *
+ * Each builder must produce a table bit-identical to the one the reference builds
+ * (tests compare against oracle/ and against the reference's own exported pre*
+ * functions compiled into oracle/_ref).  They are written from the tables' definitions,
+ * not transcribed from the reference loops; the reference function each one mirrors is
+ * cited next to it (paths relative to the reference tree).
+ */
+#include "sb_internal.h"
+
+#include <string.h>
+
+/* ------------------------------------------------------------------ registry */
+
+static const sb_algo_desc g_algos[] = {
+    /* name      family        anchor      q  Q  S  min_m */
+    {"bf", SB_FAM_BF, SB_ANCHOR_PREFIX, 0, 0, 0, 1},           /* src/algos/bf.c:25 */
+    {"mp", SB_FAM_MP, SB_ANCHOR_PREFIX, 0, 0, 0, 1},           /* mp.c:37 */
+    {"kmp", SB_FAM_KMP, SB_ANCHOR_PREFIX, 0, 0, 0, 1},         /* kmp.c:44 */
+    {"bm", SB_FAM_BM, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},           /* bm.c:69 */
+    {"hor", SB_FAM_HOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},         /* hor.c:33 */
+    {"qs", SB_FAM_QS, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},           /* qs.c:32 */
+    {"raita", SB_FAM_RAITA, SB_ANCHOR_SUFFIX, 0, 0, 0, 2},     /* raita.c:35, m<2 -> -1 (:38) */
+    {"tunedbm", SB_FAM_TUNEDBM, SB_ANCHOR_SUFFIX, 0, 0, 0, 1}, /* tunedbm.c:34 */
+    {"so", SB_FAM_SO, SB_ANCHOR_PREFIX, 0, 0, 0, 1},           /* so.c:40, search_large :69 */
+    {"sa", SB_FAM_SA, SB_ANCHOR_PREFIX, 0, 0, 0, 1},           /* sa.c:36, search_large :65 */
+    {"kr", SB_FAM_KR, SB_ANCHOR_PREFIX, 0, 0, 0, 1},           /* kr.c:28 */
+    {"hash3", SB_FAM_HASHQ, SB_ANCHOR_SUFFIX, 3, 0, 0, 3},     /* hash3.c:28, m<3 -> -1 (:31) */
+    {"hash5", SB_FAM_HASHQ, SB_ANCHOR_SUFFIX, 5, 0, 0, 5},     /* hash5.c:28 */
+    {"hash8", SB_FAM_HASHQ, SB_ANCHOR_SUFFIX, 8, 0, 0, 8},     /* hash8.c:28 */
+    {"qf23", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 2, 3, 3},         /* qf23.c:39, m<=Q -> -1 (:44) */
+    {"qf24", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 2, 4, 3},
+    {"qf26", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 2, 6, 3},
+    {"qf28", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 2, 8, 3},
+    {"qf33", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 3, 3, 4},
+    {"qf34", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 3, 4, 4},
+    {"qf36", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 3, 6, 4},
+    {"qf42", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 4, 2, 5},
+    {"qf43", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 4, 3, 5},
+    {"qf44", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 4, 4, 5},
+    {"qf62", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 6, 2, 7},
+    {"qf63", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 6, 3, 7},
+};
+#define SB_NALGOS ((int)(sizeof(g_algos) / sizeof(g_algos[0])))
+
+int sb_algo_count(void) { return SB_NALGOS; }
+
+const sb_algo_desc *sb_algo_desc_get(int algo)
+{
+    return (algo >= 0 && algo < SB_NALGOS) ? &g_algos[algo] : NULL;
+}
+
+const char *sb_algo_name(int algo)
+{
+    const sb_algo_desc *d = sb_algo_desc_get(algo);
+    return d ? d->name : NULL;
+}
+
+int sb_algo_id(const char *name)
+{
+    if (!name) return -1;
+    for (int i = 0; i < SB_NALGOS; i++) {
+        const char *a = g_algos[i].name, *b = name;
+        /* case-insensitive like str2lower() in function.h:79 */
+        while (*a && *b && (*a == *b || (*b >= 'A' && *b <= 'Z' && *b + 32 == *a))) a++, b++;
+        if (!*a && !*b) return i;
+    }
+    return -1;
+}
+
+int sb_algo_applicable(int algo, int m)
+{
+    const sb_algo_desc *d = sb_algo_desc_get(algo);
+    if (!d) return -1;
+    return m >= d->min_m ? 0 : -1;
+}
+
+/* ------------------------------------------------------------------ border tables */
+
+/* mpNext[i] = length of the longest proper border of x[0..i), mpNext[0] = -1  (mp.c:26-35) */
+void sb_prep_mp(const unsigned char *x, int m, int *mpNext)
+{
+    mpNext[0] = -1;
+    int b = -1;
+    for (int len = 1; len <= m; len++) {
+        unsigned char c = x[len - 1];
+        while (b >= 0 && x[b] != c) b = mpNext[b];
+        mpNext[len] = ++b;
+    }
+}
+
+/* kmpNext[i] (i<m) = longest border b of x[0..i) whose continuation differs, x[b] != x[i];
+ * -1 if none. kmpNext[m] = plain border of the whole pattern  (kmp.c:27-41).
+ * Derived from the plain border table: follow it while the continuation is equal. */
+void sb_prep_kmp(const unsigned char *x, int m, const int *mpNext, int *kmpNext)
+{
+    kmpNext[0] = -1;
+    for (int i = 1; i < m; i++) {
+        int b = mpNext[i];
+        kmpNext[i] = (x[b] == x[i]) ? kmpNext[b] : b;
+    }
+    if (m >= 1) kmpNext[m] = mpNext[m];
+}
+
+/* ------------------------------------------------------------------ bad-character tables */
+
+/* hbc[c] = distance from the last occurrence of c in x[0..m-1) to position m-1; m if absent.
+ * (hor.c:26-30, bm.c:27-33, raita.c:26-32, tunedbm.c:26-32) */
+void sb_prep_hbc(const unsigned char *x, int m, int *hbc)
+{
+    for (int c = 0; c < SB_SIGMA; c++) hbc[c] = m;
+    for (int i = m - 2, seen = 0; i >= 0 && seen < SB_SIGMA; i--)
+        if (hbc[x[i]] == m) {
+            hbc[x[i]] = m - 1 - i;
+            seen++;
+        }
+}
+
+/* qsBc[c] = m - (last index of c in x); m+1 if absent  (qs.c:26-30) */
+void sb_prep_qsbc(const unsigned char *x, int m, int *qsBc)
+{
+    for (int c = 0; c < SB_SIGMA; c++) qsBc[c] = m + 1;
+    for (int i = m - 1, seen = 0; i >= 0 && seen < SB_SIGMA; i--)
+        if (qsBc[x[i]] == m + 1) {
+            qsBc[x[i]] = m - i;
+            seen++;
+        }
+}
+
+/* ------------------------------------------------------------------ Boyer-Moore good suffix */
+
+/* suff[i] = length of the longest common suffix of x[0..i] and x  (bm.c:36-52).
+ * Computed as the Z-function of the reversed pattern: suff[i] = Z_rev[m-1-i]. */
+void sb_prep_suffixes(const unsigned char *x, int m, int *suff)
+{
+    if (m <= 0) return;
+    /* z[k] = longest common prefix of r and r[k..), r = reverse(x); r[k] = x[m-1-k] */
+    suff[m - 1] = m;
+    int l = 0, r = 0; /* current Z-box [l, r) in reversed coordinates */
+    for (int k = 1; k < m; k++) {
+        int z = 0;
+        if (k < r) {
+            int zk = suff[m - 1 - (k - l)];
+            z = zk < r - k ? zk : r - k;
+        }
+        while (k + z < m && x[m - 1 - z] == x[m - 1 - (k + z)]) z++;
+        if (k + z > r) {
+            l = k;
+            r = k + z;
+        }
+        suff[m - 1 - k] = z;
+    }
+}
+
+/* bmGs[i] = shift after a mismatch at x[i] with x[i+1..m) matched  (bm.c:54-66).
+ * case 1: a prefix of x of length i+1 that is also a suffix (suff[i]==i+1) bounds the shift
+ *         for every j < m-1-i still unset, scanning i downward;
+ * case 2: a re-occurrence of the suffix of length suff[i] ending at i gives m-1-i for the
+ *         mismatch position m-1-suff[i]; later (larger) i overwrite, giving the smallest shift. */
+void sb_prep_bmgs(const unsigned char *x, int m, int *suff, int *bmGs)
+{
+    sb_prep_suffixes(x, m, suff);
+    for (int j = 0; j < m; j++) bmGs[j] = m;
+    int j = 0;
+    for (int i = m - 1; i >= 0; i--) {
+        if (suff[i] != i + 1) continue;
+        int shift = m - 1 - i;
+        while (j < shift) {
+            if (bmGs[j] == m) bmGs[j] = shift;
+            j++;
+        }
+    }
+    for (int i = 0; i + 1 < m; i++) bmGs[m - 1 - suff[i]] = m - 1 - i;
+}
+
+/* ------------------------------------------------------------------ bit-parallel masks */
+
+/* Shift-Or: bit i of S[c] is 0 iff x[i]==c, over the first min(m,32) characters;
+ * lim has the bits >= w-1 set, w = min(m,32)  (so.c:27-38; search_large keeps 32 chars, so.c:74-80) */
+unsigned int sb_prep_so(const unsigned char *x, int m, unsigned int *S)
+{
+    int w = m < SB_WORD ? m : SB_WORD;
+    for (int c = 0; c < SB_SIGMA; c++) S[c] = ~0u;
+    for (int i = 0; i < w; i++) S[x[i]] &= ~(1u << i);
+    unsigned int used = (w == 32) ? ~0u : ((1u << w) - 1u);
+    return ~(used >> 1);
+}
+
+/* Shift-And: bit i of S[c] is 1 iff x[i]==c; F = bit (w-1)  (sa.c:27-34, :45) */
+unsigned int sb_prep_sa(const unsigned char *x, int m, unsigned int *S)
+{
+    int w = m < SB_WORD ? m : SB_WORD;
+    memset(S, 0, SB_SIGMA * sizeof(unsigned int));
+    for (int i = 0; i < w; i++) S[x[i]] |= 1u << i;
+    return 1u << (w - 1);
+}
+
+/* ------------------------------------------------------------------ q-gram hash shift (HASHq) */
+
+/* h(i) = (sum_{k<q} x[i-k] << k) mod 256: the reference computes it either in an unsigned char
+ * (hash3.c:29,42-44) or in an unsigned int reduced %WSIZE (hash5.c:46, hash8.c:52); both are the
+ * same value because every step is linear mod 256. */
+static unsigned sb_hashq_at(const unsigned char *s, int i, int q)
+{
+    unsigned h = 0;
+    for (int k = q - 1; k >= 0; k--) h = (h << 1) + s[i - k];
+    return h & (SB_WSIZE - 1);
+}
+
+/* shift[h] = m-1-i for the right-most q-gram ending at i < m-1 with hash h, default m-q+1;
+ * the q-gram ending at m-1 gets shift 0 and its previous value becomes sh1 (>=1)
+ * (hash3.c:37-55, hash5.c:39-65, hash8.c:38-71). */
+void sb_prep_hashq(const unsigned char *x, int m, int q, int *shift, int *sh1)
+{
+    for (int h = 0; h < SB_WSIZE; h++) shift[h] = m - q + 1;
+    for (int i = q - 1; i < m - 1; i++) shift[sb_hashq_at(x, i, q)] = m - 1 - i;
+    unsigned last;
+    if (m > q) {
+        last = sb_hashq_at(x, m - 1, q);
+    } else {
+        /* m == q: the reference's loop index is left at q, not m-1, so its "last" q-gram is
+         * x[1..q] and includes the terminator x[m] == 0 the driver stores (smart.c:313);
+         * the first q-gram already has shift m-q == 0. Reproduced here without reading x[m]. */
+        unsigned char tmp[16];
+        shift[sb_hashq_at(x, q - 1, q)] = 0; /* = m - q, hash3.c:45 */
+        memcpy(tmp, x + 1, (size_t)(q - 1));
+        tmp[q - 1] = 0;
+        last = sb_hashq_at(tmp, q - 1, q);
+    }
+    *sh1 = shift[last] ? shift[last] : 1;
+    shift[last] = 0;
+}
+
+/* ------------------------------------------------------------------ Karp-Rabin */
+
+/* d = 2^(m-1), hx = sum x[i] * 2^(m-1-i), both in wrapping 32-bit arithmetic  (kr.c:34-40) */
+void sb_prep_kr(const unsigned char *x, int m, int *d, int *hx)
+{
+    unsigned dd = (m - 1 >= 32) ? 0u : (1u << (m - 1));
+    unsigned h = 0;
+    for (int i = 0; i < m; i++) h = (h << 1) + x[i];
+    *d = (int)dd;
+    *hx = (int)h;
+}
+
+/* ------------------------------------------------------------------ Q-gram filter (QF) */
+
+/* B[g] has bit ((m-i) mod Q) set for every pattern q-gram starting at i (0 <= i <= m-Q) whose
+ * fingerprint g = (sum_{k<Q} x[i+k] << (S*k)) & mask  (qf23.c:50-56). */
+void sb_prep_qf(const unsigned char *x, int m, int Q, int S, int *B)
+{
+    int asize = 1 << (Q * S);
+    unsigned mask = (unsigned)asize - 1u;
+    memset(B, 0, (size_t)asize * sizeof(int));
+    for (int i = 0; i + Q <= m; i++) {
+        unsigned g = 0;
+        for (int k = Q - 1; k >= 0; k--) g = (g << S) + x[i + k];
+        B[g & mask] |= 1 << ((m - i) % Q);
+    }
+}
+
+/* ------------------------------------------------------------------ all tables of a family */
+
+int sb_prep_tables(int algo, const unsigned char *x, int m, sb_tables *out)
+{
+    const sb_algo_desc *d = sb_algo_desc_get(algo);
+    if (!d || !x || !out || m < 1 || m > SB_XSIZE) return -2;
+    memset(out, 0, offsetof(sb_tables, qfB));
+    out->m = m;
+    if (m < d->min_m) return -1;
+    switch (d->family) {
+    case SB_FAM_BF: break;
+    case SB_FAM_MP: sb_prep_mp(x, m, out->mpNext); break;
+    case SB_FAM_KMP:
+        sb_prep_mp(x, m, out->mpNext);
+        sb_prep_kmp(x, m, out->mpNext, out->kmpNext);
+        break;
+    case SB_FAM_BM:
+        sb_prep_bmgs(x, m, out->suff, out->bmGs);
+        sb_prep_hbc(x, m, out->hbc);
+        break;
+    case SB_FAM_HOR:
+    case SB_FAM_RAITA:
+    case SB_FAM_TUNEDBM: sb_prep_hbc(x, m, out->hbc); break;
+    case SB_FAM_QS: sb_prep_qsbc(x, m, out->qsBc); break;
+    case SB_FAM_SO: out->soLim = sb_prep_so(x, m, out->soS); break;
+    case SB_FAM_SA: out->saF = sb_prep_sa(x, m, out->saS); break;
+    case SB_FAM_KR: sb_prep_kr(x, m, &out->krD, &out->krHx); break;
+    case SB_FAM_HASHQ:
+        out->hashQ = d->q;
+        sb_prep_hashq(x, m, d->q, out->hashShift, &out->hashSh1);
+        break;
+    case SB_FAM_QF:
+        out->qfQ = d->Q;
+        out->qfS = d->S;
+        sb_prep_qf(x, m, d->Q, d->S, out->qfB);
+        break;
+    }
+    return 0;
+}

@@ -1,0 +1,58 @@
+/* Internal declarations shared by prep.c (host C) and the CUDA translation units. */
+#ifndef SB_INTERNAL_H
+#define SB_INTERNAL_H
+
+#include "smart_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum sb_family {
+    SB_FAM_BF = 0,
+    SB_FAM_MP,
+    SB_FAM_KMP,
+    SB_FAM_BM,
+    SB_FAM_HOR,
+    SB_FAM_QS,
+    SB_FAM_RAITA,
+    SB_FAM_TUNEDBM,
+    SB_FAM_SO,
+    SB_FAM_SA,
+    SB_FAM_KR,
+    SB_FAM_HASHQ,
+    SB_FAM_QF
+};
+
+/* which end of the pattern the candidate fingerprint is taken from: the left-to-right families
+ * (BF, MP/KMP, Shift-Or/And, KR) anchor on the prefix, the right-to-left / skip families
+ * (BM, Horspool, QS, Raita, Tuned-BM, HASHq, QF) on the suffix, like their CPU scan order. */
+enum sb_anchor { SB_ANCHOR_PREFIX = 0, SB_ANCHOR_SUFFIX = 1 };
+
+typedef struct sb_algo_desc {
+    const char *name;
+    int family;
+    int anchor;
+    int q;     /* HASHq rank */
+    int Q, S;  /* QF parameters */
+    int min_m; /* smaller m -> -1, as the reference */
+} sb_algo_desc;
+
+const sb_algo_desc *sb_algo_desc_get(int algo);
+
+void sb_prep_mp(const unsigned char *x, int m, int *mpNext);
+void sb_prep_kmp(const unsigned char *x, int m, const int *mpNext, int *kmpNext);
+void sb_prep_hbc(const unsigned char *x, int m, int *hbc);
+void sb_prep_qsbc(const unsigned char *x, int m, int *qsBc);
+void sb_prep_suffixes(const unsigned char *x, int m, int *suff);
+void sb_prep_bmgs(const unsigned char *x, int m, int *suff, int *bmGs);
+unsigned int sb_prep_so(const unsigned char *x, int m, unsigned int *S);
+unsigned int sb_prep_sa(const unsigned char *x, int m, unsigned int *S);
+void sb_prep_hashq(const unsigned char *x, int m, int q, int *shift, int *sh1);
+void sb_prep_kr(const unsigned char *x, int m, int *d, int *hx);
+void sb_prep_qf(const unsigned char *x, int m, int Q, int S, int *B);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

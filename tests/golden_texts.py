@@ -1,0 +1,75 @@
+"""Deterministic recipes for the parity-test texts and patterns (shared by tests/golden/make_golden.py,
+which records the reference's answers, and the tests, which replay them).  Nothing here reads
+/root/reference: corpus slices are committed under tests/golden/, everything else is regenerated."""
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+
+ALGOS = (
+    "bf", "mp", "kmp", "bm", "hor", "qs", "raita", "tunedbm", "so", "sa", "kr",
+    "hash3", "hash5", "hash8",
+    "qf23", "qf24", "qf26", "qf28", "qf33", "qf34", "qf36", "qf42", "qf43", "qf44", "qf62", "qf63",
+)
+
+M_SET = (1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 14, 15, 16, 17, 24, 30, 31, 32, 33, 48, 62, 63, 64, 65, 100, 128, 256,
+         512, 1024, 2048, 4096)
+
+TEXT_NAMES = ("bible64k", "hs32k", "rand2", "rand4", "gen256", "gen4", "a16k", "ab16k", "aab16k")
+
+SYN_N = 256 * 1024
+GEN_SEED = 20261018
+
+
+def make_text(name: str, ora) -> np.ndarray:
+    """ora: oracle_lib.Oracle (provides the reference textgen stream)."""
+    if name == "bible64k":
+        return np.fromfile(os.path.join(GOLDEN, "bible64k.bin"), dtype=np.uint8)
+    if name == "hs32k":
+        return np.fromfile(os.path.join(GOLDEN, "hs32k.bin"), dtype=np.uint8)
+    if name == "rand2":
+        return ora.textgen(0, SYN_N)
+    if name == "rand4":
+        return ora.textgen(1, SYN_N)
+    if name in ("gen256", "gen4"):
+        import smart_b200
+
+        return smart_b200.textgen_host(0, SYN_N, 256 if name == "gen256" else 4, GEN_SEED)
+    if name == "a16k":
+        return np.full(16384, ord("a"), dtype=np.uint8)
+    if name == "ab16k":
+        return np.frombuffer(b"ab" * 8192, dtype=np.uint8).copy()
+    if name == "aab16k":
+        return np.frombuffer((b"aab" * 5462)[:16384], dtype=np.uint8).copy()
+    raise KeyError(name)
+
+
+def make_patterns(tname: str, y: np.ndarray, m: int):
+    """Three patterns per (text, m): two cut from the text (>=1 occurrence, as smart.c:148-158 does),
+    one mutated in its last byte (usually absent)."""
+    n = y.size
+    seed = (hash_name(tname) * 1000003 + m) & 0xFFFFFFFF
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(2):
+        k = int(rng.integers(0, n - m + 1))
+        out.append(y[k : k + m].copy())
+    mut = out[0].copy()
+    mut[-1] = (int(mut[-1]) + 1 + int(rng.integers(0, 3))) & 0xFF
+    out.append(mut)
+    if tname in ("a16k", "ab16k", "aab16k"):
+        # the adversarial shapes of SURVEY.md Appendix A: periodic pattern starting at offset 0 and
+        # a near-periodic one with a foreign last byte
+        out[1] = y[:m].copy()
+        out[2] = y[:m].copy()
+        out[2][-1] = ord("c")
+    return out
+
+
+def hash_name(s: str) -> int:
+    h = 2166136261
+    for ch in s.encode():
+        h = ((h ^ ch) * 16777619) & 0xFFFFFFFF
+    return h

@@ -1,0 +1,121 @@
+"""The product's preprocessing stage (smart_b200/csrc/prep.c via sb_prep_tables) must build tables
+bit-identical to the reference's: checked against tables dumped from the reference's own exported pre*()
+functions (tests/golden/tables.json), against SURVEY.md Appendix B.2, and against the oracle restatement on
+random patterns.  Host-only: no GPU needed."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import smart_b200 as sb
+from golden_texts import GOLDEN
+
+
+def arr(ct, k):
+    return np.ctypeslib.as_array(ct)[:k].tolist()
+
+
+@pytest.fixture(scope="module")
+def table_cases():
+    return json.load(open(os.path.join(GOLDEN, "tables.json")))["tables"]
+
+
+def test_tables_vs_reference_dump(table_cases):
+    for ent in table_cases:
+        x = bytes.fromhex(ent["pattern"])
+        m = len(x)
+        t = sb.prep_tables("kmp", x)
+        assert arr(t.kmpNext, m + 1) == ent["kmpNext"]
+        assert arr(t.mpNext, m + 1) == ent["mpNext"]
+        assert arr(sb.prep_tables("mp", x).mpNext, m + 1) == ent["mpNext"]
+        assert arr(sb.prep_tables("hor", x).hbc, 256) == ent["hbc"]
+        t = sb.prep_tables("bm", x)
+        assert arr(t.hbc, 256) == ent["bmBc"]
+        assert arr(t.suff, m) == ent["suff"]
+        assert arr(t.bmGs, m) == ent["bmGs"]
+        assert arr(sb.prep_tables("qs", x).qsBc, 256) == ent["qsBc"]
+        t = sb.prep_tables("so", x)
+        assert arr(t.soS, 256) == ent["soS"] and t.soLim == ent["soLim"]
+        t = sb.prep_tables("sa", x)
+        assert arr(t.saS, 256) == ent["saS"] and t.saF == 1 << (min(m, 32) - 1)
+        if m >= 2:
+            assert arr(sb.prep_tables("raita", x).hbc, 256) == ent["hbc"]
+        assert arr(sb.prep_tables("tunedbm", x).hbc, 256) == ent["hbc"]
+
+
+def test_appendix_b2_known_answers():
+    x = b"GCAGAGAG"
+    A, Cc, G, T = ord("A"), ord("C"), ord("G"), ord("T")
+    t = sb.prep_tables("kmp", x)
+    assert arr(t.kmpNext, 9) == [-1, 0, 0, -1, 1, -1, 1, -1, 1]
+    assert arr(t.mpNext, 9) == [-1, 0, 0, 0, 1, 0, 1, 0, 1]
+    h = sb.prep_tables("hor", x).hbc
+    assert (h[A], h[Cc], h[G], h[T], h[0], h[255]) == (1, 6, 2, 8, 8, 8)
+    t = sb.prep_tables("bm", x)
+    assert arr(t.suff, 8) == [1, 0, 0, 2, 0, 4, 0, 8]
+    assert arr(t.bmGs, 8) == [7, 7, 7, 2, 7, 4, 7, 1]
+    q = sb.prep_tables("qs", x).qsBc
+    assert (q[A], q[Cc], q[G], q[T], q[1]) == (2, 7, 1, 9, 9)
+    t = sb.prep_tables("so", x)
+    assert t.soLim == 0xFFFFFF80
+    assert (t.soS[A], t.soS[Cc], t.soS[G], t.soS[T], t.soS[7]) == (0xFFFFFFAB, 0xFFFFFFFD, 0xFFFFFF56, 0xFFFFFFFF,
+                                                                    0xFFFFFFFF)
+    t = sb.prep_tables("sa", x)
+    assert (t.saF, t.saS[A], t.saS[Cc], t.saS[G], t.saS[T]) == (0x80, 0x54, 0x02, 0xA9, 0)
+    t = sb.prep_tables("hash3", x)
+    sh = arr(t.hashShift, 256)
+    assert (sh[211], sh[213], sh[227], sh[229], t.hashSh1) == (1, 4, 5, 0, 2)
+    assert all(v == 6 for i, v in enumerate(sh) if i not in (211, 213, 227, 229))
+    t = sb.prep_tables("qf23", x)
+    B = arr(t.qfB, 64)
+    assert {i: v for i, v in enumerate(B) if v} == {11: 2, 15: 2, 31: 1, 57: 1}
+
+
+def test_tables_vs_oracle_random(oracle):
+    rng = np.random.default_rng(5)
+    shapes = [(1, 256), (2, 2), (3, 4), (5, 4), (8, 2), (8, 256), (9, 3), (33, 2), (64, 256), (257, 4), (4200, 2)]
+    pats = [rng.integers(0, s, m, dtype=np.uint8) for m, s in shapes]
+    pats += [np.frombuffer(b"ab" * 50, dtype=np.uint8), np.frombuffer(b"a" * 77, dtype=np.uint8),
+             np.frombuffer(b"aab" * 33 + b"c", dtype=np.uint8)]
+    for x in pats:
+        m = x.size
+        t = sb.prep_tables("kmp", x)
+        assert arr(t.kmpNext, m + 1) == oracle.table("kmpNext", x).tolist()
+        assert arr(t.mpNext, m + 1) == oracle.table("mpNext", x).tolist()
+        t = sb.prep_tables("bm", x)
+        assert arr(t.bmGs, m) == oracle.table("bmGs", x).tolist()
+        assert arr(t.suff, m) == oracle.table("suff", x).tolist()
+        assert arr(t.hbc, 256) == oracle.table("hbc", x).tolist()
+        assert arr(sb.prep_tables("qs", x).qsBc, 256) == oracle.table("qsBc", x).tolist()
+        S, lim = oracle.table("so", x)
+        t = sb.prep_tables("so", x)
+        assert arr(t.soS, 256) == S.tolist() and t.soLim == lim
+        S, F = oracle.table("sa", x)
+        t = sb.prep_tables("sa", x)
+        assert arr(t.saS, 256) == S.tolist() and t.saF == F
+        d, hx = oracle.table("kr", x)
+        t = sb.prep_tables("kr", x)
+        assert (t.krD, t.krHx) == (d, hx)
+        for q in (3, 5, 8):
+            t = sb.prep_tables(f"hash{q}", x)
+            if m < q:
+                assert t is None
+                continue
+            sh, sh1 = oracle.table("hashq", x, q=q)
+            assert arr(t.hashShift, 256) == sh.tolist() and t.hashSh1 == sh1 and t.hashQ == q
+        for name in ("qf23", "qf24", "qf26", "qf28", "qf33", "qf34", "qf36", "qf42", "qf43", "qf44", "qf62", "qf63"):
+            Q, S_ = int(name[2]), int(name[3])
+            t = sb.prep_tables(name, x)
+            if m <= Q:
+                assert t is None
+                continue
+            assert arr(t.qfB, 1 << (Q * S_)) == oracle.table("qf", x, Q=Q, S=S_).tolist(), name
+
+
+def test_not_applicable_domains():
+    """-1 domains of the reference."""
+    for name, min_m in [("raita", 2), ("hash3", 3), ("hash5", 5), ("hash8", 8), ("qf23", 3), ("qf33", 4),
+                        ("qf44", 5), ("qf62", 7), ("bf", 1), ("kmp", 1), ("so", 1)]:
+        for m in range(1, 10):
+            assert sb.applicable(name, m) == (m >= min_m), (name, m)
