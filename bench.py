@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""bench.py — text GB/s scanned (HBM-resident) on B200, the metric of BASELINE.json.
+
+Workload (BASELINE.json configs[2], the "1xB200 roofline run"): a synthetic uniform sigma=256 text of
+4 GiB PER GPU, resident in HBM, generated on the device by the counter-based generator (textgen-style raw
+byte values); one STEP = one pass of the search hot path for every (algorithm, m) in
+{bf, kmp, hor, so} x {4, 16, 64, 256} = 16 searches = 64 GiB of text scanned per GPU per step.  Patterns are
+cut out of the text at seeded offsets (so every search must find >= 1 occurrence, smart.c:148-158,330).
+With N GPUs (one process per GPU under torchrun) the global text is N x 4 GiB, sharded with an m-1 halo;
+per-part counts are summed; there is no collective on the data path ("scaling": "weak").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
+  python bench.py --impl reference [...]                          the reference's own CPU search() (oracle/_ref)
+
+Prints ONE JSON line (rank 0).  `value` is timed with the text already in HBM; `e2e` runs the same searches
+through the host-buffer entry the legacy plugins use (sb_search_host), host->device copy of the text inside
+the timed region; `roofline` is the dominant scan kernel against the measured HBM bandwidth;
+`cpu_baseline` is the reference's search() of the same algorithms on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+GIB = 1 << 30
+METRIC = "text GB/s scanned (HBM-resident)"
+UNIT = "GB/s"
+SEED = 20261018
+FILTER_NAMES = {0: "scan_shift_kernel", 4: "scan_block_kernel<4>", 8: "scan_block_kernel<8>",
+                16: "scan_block_kernel<16>", 32: "scan_block_kernel<32>"}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gib-per-gpu", type=float, default=4.0)
+    ap.add_argument("--sigma", type=int, default=256)
+    ap.add_argument("--ms", default="4,16,64,256")
+    ap.add_argument("--algos", default="bf,kmp,hor,so")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-sample-mib", type=int, default=128)
+    ap.add_argument("--flags", type=int, default=0, help="SB_FLAG_* tuning overrides passed to every search")
+    return ap.parse_args()
+
+
+def patterns_for(n_total, sigma, ms):
+    """Same patterns on every rank: cut from the GLOBAL text via the host mirror of the generator."""
+    import smart_b200 as sb
+
+    rng = np.random.default_rng(SEED)
+    pats = {}
+    for m in ms:
+        off = int(rng.integers(0, n_total - m))
+        pats[m] = sb.textgen_host(off, m, sigma, SEED)
+    return pats
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic(kernel_name):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel_name)
+        except Exception:
+            return None
+    return None
+
+
+# --------------------------------------------------------------------------------------------- CPU legs
+
+_CPU = {}
+
+
+def _cpu_worker(job):
+    algo, ci, m = job
+    import oracle_lib
+
+    st = _CPU
+    ref = st["refs"].get(algo)
+    if ref is None:
+        ref = st["refs"][algo] = oracle_lib.RefAlgo(algo)
+    buf, n = st["chunks"][ci]
+    r = ref.search_padded(st["pats"][m], buf, n)
+    return r
+
+
+def cpu_reference_setup(sample_bytes, sigma, ms, cores, n_total):
+    """Text sample = first `sample_bytes` of the workload text, cut into one chunk per core with an
+    (max m)-1 overlap so the chunks can be searched independently."""
+    import oracle_lib
+    import smart_b200 as sb
+
+    y = sb.textgen_host(0, sample_bytes, sigma, SEED)
+    pats = {m: sb.textgen_host(1000 + 7 * m, m, sigma, SEED) for m in ms}  # cut from inside the sample
+    mmax = max(ms)
+    per = (sample_bytes + cores - 1) // cores
+    chunks = []
+    for c in range(cores):
+        lo = c * per
+        hi = min(sample_bytes, lo + per + mmax - 1)
+        if lo >= sample_bytes:
+            break
+        buf = np.zeros(hi - lo + oracle_lib.RefAlgo.SLACK, dtype=np.uint8)
+        buf[: hi - lo] = y[lo:hi]
+        chunks.append((buf, hi - lo))
+    _CPU.update(refs={}, chunks=chunks, pats=pats, kind="reference" if oracle_lib.ref_available() else "port")
+    return len(chunks)
+
+
+def cpu_reference_step(pool, algos, ms, nchunks):
+    """One step of the workload on the CPU sample; returns seconds."""
+    t0 = time.perf_counter()
+    for a in algos:
+        for m in ms:
+            res = pool.map(_cpu_worker, [(a, ci, m) for ci in range(nchunks)])
+            if any(r == 0 for r in res) and sum(res) == 0:
+                raise RuntimeError(f"reference {a} found no occurrence of a text-extracted pattern (m={m})")
+    return time.perf_counter() - t0
+
+
+def run_cpu_reference(args, algos, ms, steps, warmup, n_total):
+    import multiprocessing as mp
+
+    cores = len(os.sched_getaffinity(0))
+    sample = args.cpu_sample_mib << 20
+    nchunks = cpu_reference_setup(sample, args.sigma, ms, cores, n_total)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(processes=nchunks) as pool:
+        for _ in range(warmup):
+            cpu_reference_step(pool, algos, ms, nchunks)
+        t = 0.0
+        for _ in range(steps):
+            t += cpu_reference_step(pool, algos, ms, nchunks)
+    bytes_per_step = sample * len(algos) * len(ms)
+    gbs = bytes_per_step * steps / t / 1e9
+    return {"value": gbs, "unit": UNIT, "cores": nchunks, "kind": _CPU["kind"],
+            "sample": f"first {args.cpu_sample_mib} MiB of the workload text, {len(algos)}x{len(ms)} searches per step "
+                      f"({','.join(algos)} x m={','.join(map(str, ms))}), one chunk per core with m-1 overlap, "
+                      f"reference search() compiled -O3 -msse4 (oracle/_ref), {steps} step(s)",
+            "seconds": t, "ms_per_step": 1e3 * t / steps}
+
+
+# --------------------------------------------------------------------------------------------- main legs
+
+def main_reference(args, algos, ms):
+    info_rank = int(os.environ.get("RANK", "0"))
+    if info_rank != 0:
+        return 0
+    n_total = int(args.gib_per_gpu * GIB) * args.gpus
+    cb = run_cpu_reference(args, algos, ms, args.steps, max(1, min(args.warmup, 2)), n_total)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, algos, ms, n_total),
+        "cpu_baseline": {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"],
+                         "sample": cb["sample"]},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, algos, ms, n_total):
+    return {"workload": f"BASELINE configs[2]: synthetic uniform rand{args.sigma} text, "
+                        f"{args.gib_per_gpu:g} GiB per GPU resident in HBM, m in {{{','.join(map(str, ms))}}}",
+            "algorithms": algos, "m": ms, "sigma": args.sigma, "text_bytes_total": n_total,
+            "searches_per_step": len(algos) * len(ms), "patterns": "cut from the text at seeded offsets",
+            "parallelism": f"text sharded over {args.gpus} GPU(s), m-1 halo, counts summed, no collective",
+            "l2": "inputs (4 GiB per GPU) larger than L2 (126 MB); no flush needed"}
+
+
+def main_ours(args, algos, ms):
+    import torch
+
+    import smart_b200 as sb
+    from smart_b200 import ranks
+
+    info = ranks.rank_info()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the scan path has no CPU fallback")
+    torch.cuda.set_device(info.local_rank)
+    device = f"cuda:{info.local_rank}"
+    dist = ranks.init_process_group("nccl")
+    world = info.world
+    if world != args.gpus and info.rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+
+    n_part = int(args.gib_per_gpu * GIB)
+    n_total = n_part * world
+    text = sb.Text.generate_part(n_total, args.sigma, SEED, world, info.rank, info.local_rank)
+    base, own, ln = sb.shard_range(n_total, world, info.rank)
+    pats = patterns_for(n_total, args.sigma, ms)
+
+    def step():
+        cnt, kms, launches = 0, {}, 0
+        for a in algos:
+            for m in ms:
+                r = sb.search(a, text, pats[m], flags=args.flags)
+                if r.count < 0:
+                    raise RuntimeError(f"{a} not applicable to m={m}")
+                tm = sb.last_timing()
+                cnt += r.count
+                launches += tm.kernels_launched
+                k = kms.setdefault(tm.filter_kind, [0.0, 0])
+                k[0] += tm.kernel_ms
+                k[1] += tm.kernels_launched
+        return cnt, kms, launches
+
+    for _ in range(max(args.warmup, 3)):
+        first_counts, _, _ = step()
+
+    sampler = None
+    if info.rank == 0:
+        sampler = ClockSampler(info.local_rank)
+        sampler.start()
+        time.sleep(0.3)
+    ranks.barrier(dist, device)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    total_cnt, launches, kernel_ms = 0, 0, {}
+    for _ in range(args.steps):
+        c, kms, l = step()
+        total_cnt += c
+        launches += l
+        for f, (ms_, n_) in kms.items():
+            k = kernel_ms.setdefault(f, [0.0, 0])
+            k[0] += ms_
+            k[1] += n_
+    torch.cuda.synchronize()  # every search already synchronised its own stream before returning
+    elapsed_ms = (time.perf_counter() - t0) * 1e3
+    ranks.barrier(dist, device)
+    if sampler:
+        time.sleep(0.2)
+        sampler.stop()
+    kernel_total = sum(v[0] for v in kernel_ms.values())
+    sum_cnt, max_ms, max_kernel_ms = ranks.reduce_step(dist, device, total_cnt, elapsed_ms, kernel_total)
+
+    # sanity outside the timed region: every text-extracted pattern is found at least once globally and
+    # all algorithms agree on the count for the same m
+    per_m = {}
+    for a in algos:
+        for m in ms:
+            c, _, _ = ranks.reduce_step(dist, device, sb.search(a, text, pats[m], flags=args.flags).count, 0, 0)
+            per_m.setdefault(m, set()).add(c)
+    for m, s in per_m.items():
+        if len(s) != 1 or min(s) < 1:
+            raise RuntimeError(f"count mismatch across algorithms or missing occurrence for m={m}: {s}")
+
+    bytes_per_step_rank = own * len(algos) * len(ms)
+    bytes_per_step = n_total * len(algos) * len(ms)
+    value = bytes_per_step * args.steps / (max_ms * 1e-3) / 1e9
+
+    # ---- per-m kernel-only rates (CUDA events on the launching stream), rank 0's part
+    per_m_rates = {}
+    for m in ms:
+        ts = []
+        for _ in range(5):
+            sb.search("bf", text, pats[m], flags=args.flags)
+            ts.append(sb.last_timing().kernel_ms)
+        per_m_rates[str(m)] = {"kernel": FILTER_NAMES.get(sb.last_timing().filter_kind, "?"),
+                               "GBps_kernel_median": own / (float(np.median(ts)) * 1e-3) / 1e9,
+                               "GBps_kernel_best": own / (min(ts) * 1e-3) / 1e9}
+
+    # ---- roofline of the dominant kernel (largest share of device time inside the timed region)
+    peak, peak_src = measured_peak()
+    dom = max(kernel_ms.items(), key=lambda kv: kv[1][0])
+    dom_name = FILTER_NAMES.get(dom[0], str(dom[0]))
+    avg_ms = dom[1][0] / max(1, dom[1][1])
+    achieved = own / (avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "frac_of_nominal_8TBps": achieved / 8000.0,
+                "traffic": recorded_traffic(dom_name), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": own, "avg_launch_ms": avg_ms,
+                "share_of_step_device_time": dom[1][0] / max(kernel_total, 1e-9),
+                "kernels": {FILTER_NAMES.get(f, str(f)): {"launches": v[1], "avg_ms": v[0] / max(1, v[1]),
+                                                          "GBps": own / (v[0] / max(1, v[1]) * 1e-3) / 1e9}
+                            for f, v in kernel_ms.items()}}
+
+    # ---- e2e: the same searches through the host-buffer entry (legacy plugin path), H2D inside the timer
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(sb, ranks, dist, device, text, base, own, n_total, pats, algos, ms, args)
+
+    # ---- CPU baseline (rank 0, N=1 only): reference search() on this box's host cores
+    cpu = None
+    if info.rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            cb = run_cpu_reference(args, algos, ms, 1, 0, n_total)
+            cpu = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
+        except Exception as e:  # the baseline is reported, never required
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+
+    if info.rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": max_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, algos, ms, n_total),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches * world,
+            "clocks": sampler.summary() if sampler else None,
+            "value_device_events": bytes_per_step_rank * args.steps / (max_kernel_ms * 1e-3) / 1e9 * world,
+            "per_m": per_m_rates, "occurrences_per_step": sum_cnt // args.steps,
+            "timing": "host clock between barrier+synchronize pairs around K blocking steps, max over ranks; "
+                      "kernel times from CUDA events on the library's launching stream",
+        }
+        print(json.dumps(line))
+    text.free()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(sb, ranks, dist, device, text, base, own, n_total, pats, algos, ms, args):
+    import torch
+
+    mmax = max(ms)
+    ln = min(n_total - base, own + mmax - 1)
+    pin = sb.pinned_buffer(ln)
+    try:
+        chunk = 256 << 20
+        for off in range(0, ln, chunk):  # fill the pinned buffer with this rank's part of the text
+            k = min(chunk, ln - off)
+            pin.array[off:off + k] = text.download(base + off, k)
+        steps = max(1, min(args.steps, 3))
+
+        def step():
+            c = 0
+            for a in algos:
+                for m in ms:
+                    hi = min(ln, own + m - 1)
+                    c += sb.search_host(a, pats[m], pin.array[:hi], flags=args.flags).count
+            return c
+
+        step()
+        ranks.barrier(dist, device)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+        ms_el = (time.perf_counter() - t0) * 1e3
+        ranks.barrier(dist, device)
+        _, max_ms, _ = ranks.reduce_step(dist, device, 0, ms_el, 0)
+        nsearch = len(algos) * len(ms)
+        world = 1 if dist is None else dist.get_world_size()
+        return {"value": n_total * nsearch * steps / (max_ms * 1e-3) / 1e9, "unit": UNIT,
+                "h2d_bytes_per_step": int(sum(min(ln, own + m - 1) + 4352 for m in ms) * len(algos) * world),
+                "d2h_bytes_per_step": 32 * nsearch * world, "steps": steps,
+                "api": "sb_search_host (the body of the legacy per-algorithm search() plugins): pinned host text, "
+                       "64 MiB chunks, copy of chunk k+1 overlapped with the scan of chunk k"}
+    finally:
+        pin.free()
+
+
+def main():
+    args = parse_args()
+    ms = [int(v) for v in args.ms.split(",")]
+    algos = args.algos.split(",")
+    if args.impl == "reference":
+        return main_reference(args, algos, ms)
+    return main_ours(args, algos, ms)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

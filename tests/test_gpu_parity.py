@@ -1,0 +1,233 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the oracle, the committed golden
+outputs of the unmodified reference, and size-independent properties at BASELINE.json's sizes.
+
+Bar: bit-exact (integer counts, byte-exact sorted positions)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import smart_b200 as sb
+from fixtures import TEST_C_FIXTURES, seeded_random_fixtures
+from golden_texts import ALGOS, GOLDEN, TEXT_NAMES, make_patterns, make_text
+
+pytestmark = pytest.mark.gpu
+
+FILTERS = {0: sb.FLAG_FILTER_SHIFT, 4: sb.FLAG_FILTER_B4, 8: sb.FLAG_FILTER_B8, 16: sb.FLAG_FILTER_B16,
+           32: sb.FLAG_FILTER_B32}
+
+
+def expected(algo, m, bf):
+    min_m = {"raita": 2, "hash3": 3, "hash5": 5, "hash8": 8}.get(algo, 1)
+    if algo.startswith("qf"):
+        min_m = int(algo[2]) + 1
+    return -1 if m < min_m else bf
+
+
+def filters_for(m):
+    out = [0] if m <= 14 else []
+    out += [b for b in (4, 8, 16, 32) if m >= 2 * b - 1]
+    return out
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return json.load(open(os.path.join(GOLDEN, "counts.json")))
+
+
+def test_device_is_b200():
+    assert sb.device_count() >= 1
+
+
+@pytest.mark.parametrize("x,y,count", TEST_C_FIXTURES)
+def test_testc_fixtures_all_algorithms(x, y, count):
+    """The reference harness's fixtures (src/test.c:252-382) through the resident-text entry, the host
+    streaming entry and the legacy plugin entry."""
+    with sb.Text.upload(y) as t:
+        for a in ALGOS:
+            want = expected(a, len(x), count)
+            assert sb.search(a, t, x).count == want, a
+    for a in ("bf", "kmp", "hor", "so", "hash3", "qf23"):
+        want = expected(a, len(x), count)
+        assert sb.search_host(a, x, y).count == want, a
+        assert sb.plugin_search(a, x, y) == want, a
+
+
+def test_testc_random_cases(oracle):
+    for x, y in seeded_random_fixtures():
+        c = oracle.bf_count(x, y)
+        with sb.Text.upload(y) as t:
+            for a in ALGOS:
+                assert sb.search(a, t, x).count == expected(a, len(x), c)
+
+
+@pytest.mark.parametrize("tname", TEXT_NAMES)
+def test_golden_reference_counts(oracle, golden, tname):
+    """All 26 algorithms on every golden case: the count must equal what the UNMODIFIED reference
+    algorithm returned (recorded by tests/golden/make_golden.py), including its -1 domains."""
+    y = make_text(tname, oracle)
+    with sb.Text.upload(y) as t:
+        assert len(t) == y.size
+        for c in (c for c in golden["cases"] if c["text"] == tname):
+            x = make_patterns(tname, y, c["m"])[c["pi"]]
+            ref = dict(zip(ALGOS, c["ref"]))
+            for a in ALGOS:
+                got = sb.search(a, t, x).count
+                assert got == ref[a], (tname, c["m"], c["pi"], a, got, ref[a])
+
+
+@pytest.mark.parametrize("tname", ["bible64k", "rand2", "gen4", "ab16k", "a16k"])
+def test_every_filter_width_gives_the_same_count(oracle, golden, tname):
+    """The candidate filter is a tuning choice, never a semantic one."""
+    y = make_text(tname, oracle)
+    with sb.Text.upload(y) as t:
+        for c in (c for c in golden["cases"] if c["text"] == tname):
+            x = make_patterns(tname, y, c["m"])[c["pi"]]
+            want = c["ref"][0]
+            for f in filters_for(c["m"]):
+                for a in ("bf", "hor"):  # prefix- and suffix-anchored
+                    r = sb.search(a, t, x, flags=FILTERS[f])
+                    assert sb.last_timing().filter_kind == f
+                    assert r.count == want, (tname, c["m"], c["pi"], a, f)
+
+
+@pytest.mark.parametrize("tname", ["bible64k", "rand2", "gen256", "aab16k", "a16k"])
+def test_positions_sorted_and_identical(oracle, tname):
+    y = make_text(tname, oracle)
+    with sb.Text.upload(y) as t, sb.Text.upload(y, devices=[0, 0, 0]) as t3:
+        for m in (1, 2, 3, 4, 5, 8, 9, 14, 15, 16, 31, 33, 63, 64, 100, 1024):
+            for x in make_patterns(tname, y, m)[:2]:
+                want = oracle.bf_positions(x, y)
+                for a in ("bf", "kmp", "bm"):
+                    r = sb.search(a, t, x, flags=sb.FLAG_POSITIONS, positions_cap=y.size)
+                    assert r.count == want.size
+                    assert np.array_equal(r.positions, want), (tname, m, a)
+                r = sb.search("bf", t3, x, flags=sb.FLAG_POSITIONS, positions_cap=y.size)
+                assert np.array_equal(r.positions, want), (tname, m, "sharded")
+
+
+def test_edge_cases(oracle):
+    # pattern longer than text, equal to text, empty text, matches at both ends, all-zero bytes
+    with sb.Text.upload(b"abc") as t:
+        assert sb.search("bf", t, b"abcd").count == 0
+        assert sb.search("bf", t, b"abc").count == 1
+        assert sb.search("kmp", t, b"c").count == 1
+    with sb.Text.upload(b"") as t:
+        assert sb.search("bf", t, b"a").count == 0
+    z = bytes(5000)
+    with sb.Text.upload(z) as t:
+        for m in (1, 2, 7, 8, 9, 15, 16, 31, 63, 64, 1000, 4200):
+            assert sb.search("bf", t, bytes(m)).count == 5000 - m + 1, m
+            assert sb.search("hor", t, bytes(m)).count == 5000 - m + 1, m
+    y = b"xyz" + b"." * 3000 + b"xyz"
+    with sb.Text.upload(y) as t:
+        r = sb.search("bf", t, b"xyz", flags=sb.FLAG_POSITIONS, positions_cap=10)
+        assert r.positions.tolist() == [0, 3003]
+    # maximum pattern length (XSIZE, define.h:25)
+    rng = np.random.default_rng(3)
+    y = rng.integers(0, 2, 20000, dtype=np.uint8)
+    x = y[5000:9200].copy()
+    with sb.Text.upload(y) as t:
+        assert sb.search("bf", t, x).count == oracle.bf_count(x, y) >= 1
+    with pytest.raises(sb.SmartB200Error):
+        with sb.Text.upload(y) as t:
+            sb.search("bf", t, np.zeros(4201, dtype=np.uint8))
+
+
+def test_text_bytes_after_n_are_never_used(oracle):
+    """86 reference algorithms write/read y[n..]; ours must not depend on those bytes: the same n with
+    different trailing garbage gives the same answer through the host entry."""
+    rng = np.random.default_rng(11)
+    base = rng.integers(0, 2, 100000, dtype=np.uint8)
+    n = 70001
+    for m in (3, 8, 16, 40, 64, 300):
+        x = base[n - m : n].copy()  # a match that ends exactly at y[n-1]
+        want = oracle.bf_count(x, base[:n])
+        for tail in (0, 1):
+            buf = base.copy()
+            buf[n:] = tail
+            for a in ("bf", "so", "hash3", "qs", "kr", "tunedbm"):
+                exp = expected(a, m, want)
+                assert sb.lib().sb_search_host(sb.algo_id(a), x.ctypes.data, m, buf.ctypes.data, n, 0, None,
+                                               None) == exp
+
+
+def test_sharded_counts_equal_unsharded(oracle):
+    rng = np.random.default_rng(21)
+    y = rng.integers(0, 4, 3_000_000, dtype=np.uint8)
+    with sb.Text.upload(y) as t1, sb.Text.upload(y, devices=[0, 0]) as t2, \
+            sb.Text.upload(y, devices=[0] * 8) as t8:
+        assert (t1.shards, t2.shards, t8.shards) == (1, 2, 8)
+        for m in (2, 8, 16, 64, 1024, 4200):
+            # a pattern straddling a shard boundary must be found exactly once
+            base, own, _ = sb.shard_range(y.size, 8, 3)
+            x = y[base + own - m // 2 : base + own - m // 2 + m].copy()
+            want = oracle.bf_count(x, y)
+            assert want >= 1
+            for t in (t1, t2, t8):
+                assert sb.search("bf", t, x).count == want, (m, t.shards)
+        # per-part handles (one process per GPU) sum to the whole
+        x = y[12345:12345 + 24].copy()
+        want = oracle.bf_count(x, y)
+        total = 0
+        for g in range(4):
+            with sb.Text.upload_part(y, 4, g) as part:
+                total += sb.search("kmp", part, x).count
+        assert total == want
+
+
+def test_generated_text_matches_host_mirror():
+    n = 5_000_000
+    for sigma in (2, 4, 250, 256):
+        with sb.Text.generate(n, sigma, 777) as t, sb.Text.generate(n, sigma, 777, devices=[0, 0, 0]) as t3:
+            host = sb.textgen_host(0, n, sigma, 777)
+            assert np.array_equal(t.download(0, n), host)
+            assert np.array_equal(t3.download(0, n), host)
+            assert np.array_equal(t.download(n - 100, 100), host[-100:])
+
+
+@pytest.mark.parametrize("sigma,ms", [(256, (4, 16, 64, 256)), (4, (8, 64, 1024)), (2, (1024, 2048, 4096))])
+def test_full_size_properties(oracle, sigma, ms):
+    """BASELINE.json configs 3-5 at 4 GiB: the count of a text-extracted pattern is >= 1 (smart.c:330's own
+    in-band check), equals the oracle's count on a host-regenerated 256 MiB window plus the counts outside it
+    (linearity over a 3-way split), and does not depend on sharding."""
+    n = 4 << 30
+    seed = 4242 + sigma
+    win_lo, win_len = (1 << 30) + 4096 * 7, 256 << 20
+    host_win = sb.textgen_host(win_lo, win_len, sigma, seed)
+    with sb.Text.generate(n, sigma, seed) as t, sb.Text.generate(n, sigma, seed, devices=[0, 0, 0, 0]) as t4:
+        assert np.array_equal(t.download(win_lo, 1 << 20), host_win[: 1 << 20])
+        for m in ms:
+            x = host_win[1000:1000 + m].copy()
+            whole = sb.search("bf", t, x).count
+            assert whole >= 1
+            assert sb.search("hor", t, x).count == whole
+            assert sb.search("bf", t4, x).count == whole
+            # positions inside the window must be exactly the oracle's
+            r = sb.search("bf", t, x, flags=sb.FLAG_POSITIONS, positions_cap=1 << 22)
+            if r.count <= (1 << 22):
+                pos = r.positions
+                inside = pos[(pos >= win_lo) & (pos + m <= win_lo + win_len)] - win_lo
+                want = oracle.bf_positions(x, host_win, cap=1 << 22)
+                assert np.array_equal(inside, want), (sigma, m)
+                assert np.all(pos[1:] > pos[:-1])
+        # an absent pattern (bytes outside the alphabet) counts 0
+        if sigma < 256:
+            assert sb.search("bf", t, bytes([255] * 16)).count == 0
+
+
+def test_host_streaming_entry_large(oracle):
+    """sb_search_host over several 64 MiB chunks equals the resident-text result (chunk seams + halo)."""
+    n = 200 * (1 << 20) + 12345
+    y = sb.textgen_host(0, n, 4, 99)
+    with sb.Text.upload(y) as t:
+        for m in (3, 8, 20, 64, 1000):
+            # one pattern straddling the first chunk seam
+            x = y[(64 << 20) - m // 2 : (64 << 20) - m // 2 + m].copy()
+            want = sb.search("bf", t, x).count
+            assert want >= 1
+            assert sb.search_host("bf", x, y).count == want
+            assert sb.search_host("hor", x, y).count == want
+    x = y[5_000_000:5_000_032].copy()
+    assert sb.search_host("bf", x, y).count == oracle.bf_count(x, y)
