@@ -51,7 +51,7 @@ extern "C" {
 /* flags for sb_search64 */
 #define SB_FLAG_POSITIONS 0x1u    /* fill `positions` (sorted ascending, global offsets) */
 #define SB_FLAG_NO_SKIP 0x2u      /* force the read-every-byte kernels even for skip-family algorithms */
-#define SB_FLAG_FILTER_SHIFT 0x10u  /* tuning override: force the shifted-window kernel (m <= 14 only) */
+#define SB_FLAG_FILTER_SHIFT 0x10u  /* tuning override: force the per-position 8-byte window kernel (m >= 5) */
 #define SB_FLAG_FILTER_B4 0x20u     /* tuning override: aligned-block fingerprint width 4 */
 #define SB_FLAG_FILTER_B8 0x40u
 #define SB_FLAG_FILTER_B16 0x80u
@@ -89,6 +89,9 @@ sb_text *sb_text_upload_part(const unsigned char *host, size_t n_total, int npar
  * bytes [*base, *base + *len). Returns 0, -1 on bad arguments. */
 int sb_shard_range(size_t n_total, int nparts, int part, size_t *base, size_t *own, size_t *len);
 size_t sb_text_length(const sb_text *t);
+/* collision entropy per byte, -log2(sum p_c^2), of a sampled byte histogram taken when the text was
+ * created; drives the choice of candidate filter (a B-byte fingerprint passes ~2^-(B*bits) of positions) */
+double sb_text_entropy_bits(const sb_text *t);
 int sb_text_shards(const sb_text *t);
 /* copy text bytes [off, off+len) back to the host (tests, pattern extraction) */
 int sb_text_download(const sb_text *t, size_t off, size_t len, unsigned char *host);
@@ -117,7 +120,7 @@ typedef struct sb_timing {
     double kernel_ms;      /* max over shards of the CUDA-event time of the scan kernel(s) */
     double wall_ms;        /* host wall clock, first launch -> last count on host */
     int kernels_launched;  /* scan kernels launched by the last search (all shards) */
-    int filter_kind;       /* 0 = shifted window, 4/8/16/32 = aligned-block width, 1xx = skip kernel */
+    int filter_kind;       /* 0 = scan_short, 1 = scan_window8, 4/8/16/32 = scan_block<B> */
     unsigned long long verified; /* candidates sent to exact verification (all shards) */
 } sb_timing;
 void sb_last_timing(sb_timing *out);

@@ -109,6 +109,7 @@ SYMBOLS = [
                                  C.POINTER(C.c_size_t)]),
     ("sb_text_length", C.c_size_t, [C.c_void_p]),
     ("sb_text_shards", C.c_int, [C.c_void_p]),
+    ("sb_text_entropy_bits", C.c_double, [C.c_void_p]),
     ("sb_text_download", C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
     ("sb_text_free", None, [C.c_void_p]),
     ("sb_textgen_host", None, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_uint64]),
@@ -222,6 +223,10 @@ class Text:
     @property
     def shards(self) -> int:
         return lib().sb_text_shards(self._h)
+
+    @property
+    def entropy_bits(self) -> float:
+        return lib().sb_text_entropy_bits(self._h)
 
     def download(self, off: int, length: int) -> np.ndarray:
         out = np.empty(length, dtype=np.uint8)

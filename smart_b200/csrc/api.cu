@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -47,6 +48,10 @@ constexpr size_t kHalo = SB_XSIZE - 1;        // right halo kept with every shar
 constexpr size_t kShardAlign = 4096;          // shard bases are multiples of this
 constexpr int kMaxShards = 16;
 constexpr size_t kPatBytes = 4352;            // device pattern buffer (>= SB_XSIZE + 8, multiple of 256)
+constexpr int kU = 2;                         // 256-bit loads in flight per thread (scan_block / scan_window8)
+constexpr size_t kGroupLong = kU * 1024;      // bytes per warp iteration of those kernels
+constexpr size_t kGroupShort = 4 * 512;       // ... of scan_short
+constexpr int kFilterShort = 0, kFilterWindow8 = 1;
 
 struct DevCtx {                               // per-device scratch, created on first use
     bool ready = false;
@@ -60,8 +65,10 @@ struct DevCtx {                               // per-device scratch, created on 
     uint32_t *h_pat = nullptr;                // pinned staging for the pattern
     unsigned long long *d_pos = nullptr;      // position sink, grown on demand
     size_t pos_cap = 0;
-    int blocks_block[4] = {0, 0, 0, 0};       // resident CTAs/SM for scan_block<4,8,16,32>
-    int blocks_shift[4] = {0, 0, 0, 0};       // ... for scan_shift<HI,MASK>
+    int occ_block[4] = {0, 0, 0, 0};          // resident CTAs/SM for scan_block<4,8,16,32>
+    int occ_window[4] = {0, 0, 0, 0};         // ... for scan_window8<OFF=1..4>
+    int occ_short[2] = {0, 0};                // ... for scan_short<MASK>
+    unsigned long long *d_hist = nullptr;     // 256-bin byte histogram scratch
     // host-buffer streaming path
     uint8_t *d_chunk[2] = {nullptr, nullptr};
     size_t chunk_cap = 0;
@@ -109,14 +116,17 @@ DevCtx *get_ctx(int dev)
     CU_TRY(cudaMalloc(&c.d_counters, 4 * sizeof(unsigned long long)), nullptr);
     CU_TRY(cudaHostAlloc(&c.h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault), nullptr);
     CU_TRY(cudaHostAlloc(&c.h_pat, kPatBytes, cudaHostAllocDefault), nullptr);
-    c.blocks_block[0] = occupancy(sb::scan_block_kernel<4>);
-    c.blocks_block[1] = occupancy(sb::scan_block_kernel<8>);
-    c.blocks_block[2] = occupancy(sb::scan_block_kernel<16>);
-    c.blocks_block[3] = occupancy(sb::scan_block_kernel<32>);
-    c.blocks_shift[0] = occupancy(sb::scan_shift_kernel<false, false>);
-    c.blocks_shift[1] = occupancy(sb::scan_shift_kernel<false, true>);
-    c.blocks_shift[2] = occupancy(sb::scan_shift_kernel<true, false>);
-    c.blocks_shift[3] = occupancy(sb::scan_shift_kernel<true, true>);
+    CU_TRY(cudaMalloc(&c.d_hist, 256 * sizeof(unsigned long long)), nullptr);
+    c.occ_block[0] = occupancy(sb::scan_block_kernel<4, kU>);
+    c.occ_block[1] = occupancy(sb::scan_block_kernel<8, kU>);
+    c.occ_block[2] = occupancy(sb::scan_block_kernel<16, kU>);
+    c.occ_block[3] = occupancy(sb::scan_block_kernel<32, kU>);
+    c.occ_window[0] = occupancy(sb::scan_window8_kernel<1, kU>);
+    c.occ_window[1] = occupancy(sb::scan_window8_kernel<2, kU>);
+    c.occ_window[2] = occupancy(sb::scan_window8_kernel<3, kU>);
+    c.occ_window[3] = occupancy(sb::scan_window8_kernel<4, kU>);
+    c.occ_short[0] = occupancy(sb::scan_short_kernel<false>);
+    c.occ_short[1] = occupancy(sb::scan_short_kernel<true>);
     c.ready = true;
     return &c;
 }
@@ -131,6 +141,22 @@ struct Shard {
     size_t own = 0;       // start positions [base, base+own) belong to this shard
     size_t len = 0;       // valid bytes in the buffer (own + halo, clipped to the text end)
 };
+
+/* collision entropy per byte, -log2(sum p_c^2): the probability that two independent text bytes are
+ * equal is 2^-bits, so a B-byte fingerprint passes a random position with probability ~2^-(B*bits) */
+double collision_bits(const unsigned long long *hist)
+{
+    double tot = 0, s2 = 0;
+    for (int c = 0; c < 256; c++) tot += (double)hist[c];
+    if (tot <= 0) return 8.0;
+    for (int c = 0; c < 256; c++) {
+        const double p = (double)hist[c] / tot;
+        s2 += p * p;
+    }
+    double bits = -log2(s2);
+    if (bits < 0.05) bits = 0.05;
+    return bits > 8.0 ? 8.0 : bits;
+}
 
 uint32_t load_le32(const unsigned char *p, int avail)
 {
@@ -151,18 +177,30 @@ uint32_t fingerprint(const unsigned char *p, int B)
     }
 }
 
-/* which kernel scans a pattern of length m: 0 = shifted window, else aligned-block width */
-int choose_filter(int m, unsigned flags)
+/* Which kernel scans a pattern of length m over a text with `bits` of collision entropy per byte.
+ * 0 = scan_short (exact, m <= 4), 1 = scan_window8 (8-byte window at every position),
+ * 4/8/16/32 = scan_block<B> (aligned-block fingerprints, needs m >= 2B-1).
+ * The block kernels are the fast ones (16 ALU ops per 16 bytes) but a B-byte fingerprint lets a
+ * fraction ~2^-(B*bits) of all start positions through to verification: pick the narrowest B whose
+ * fingerprint carries >= 20 bits, else the widest feasible one if it still carries >= 14 bits, else the
+ * per-position 8-byte window. */
+int choose_filter(int m, unsigned flags, double bits)
 {
     if ((flags & SB_FLAG_FILTER_B32) && m >= 63) return 32;
     if ((flags & SB_FLAG_FILTER_B16) && m >= 31) return 16;
     if ((flags & SB_FLAG_FILTER_B8) && m >= 15) return 8;
     if ((flags & SB_FLAG_FILTER_B4) && m >= 7) return 4;
-    if ((flags & SB_FLAG_FILTER_SHIFT) && m <= 14) return 0;
-    if (m <= 14) return 0;
-    if (m < 31) return 8;
-    if (m < 63) return 16;
-    return 32;
+    if (m <= 4) return kFilterShort;
+    if (flags & SB_FLAG_FILTER_SHIFT) return kFilterWindow8;
+    int widest = 0;
+    for (int B = 4; B <= 32; B *= 2) {
+        if (2 * B - 1 > m) break;
+        widest = B;
+        if (B * bits >= 20.0) return B;
+    }
+    if (widest && widest * bits >= 14.0) return widest;
+    if (widest > 8) return widest;  // more selective than the 8-byte window
+    return kFilterWindow8;
 }
 
 struct Plan {
@@ -170,22 +208,23 @@ struct Plan {
     sb::ScanArgs args;  // text/base/hi/ngroups/counters/pos filled per shard
 };
 
-void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m, unsigned flags)
+void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m, unsigned flags, double bits)
 {
     memset(&pl.args, 0, sizeof pl.args);
-    pl.filter = choose_filter(m, flags);
+    pl.filter = choose_filter(m, flags, bits);
     sb::ScanArgs &a = pl.args;
     a.m = m;
     a.nwords = (m + 3) / 4;
     a.tailmask = (m & 3) ? ((1u << (8 * (m & 3))) - 1u) : 0xffffffffu;
-    if (pl.filter == 0) {
-        const int k = m < 8 ? m : 8;
-        const int k0 = k < 4 ? k : 4, k1 = k - k0;
-        a.M0 = k0 == 4 ? 0xffffffffu : ((1u << (8 * k0)) - 1u);
-        a.M1 = k1 == 4 ? 0xffffffffu : (k1 ? ((1u << (8 * k1)) - 1u) : 0u);
-        a.X0 = load_le32(x, k0) & a.M0;
-        a.X1 = k1 ? (load_le32(x + 4, k1) & a.M1) : 0u;
-        a.anchor = 0;
+    if (pl.filter == kFilterShort) {
+        a.M0 = m == 4 ? 0xffffffffu : ((1u << (8 * m)) - 1u);
+        a.X0 = load_le32(x, m) & a.M0;
+    } else if (pl.filter == kFilterWindow8) {
+        const int off = m >= 8 ? 4 : m - 4;  // second window word; overlaps the first when m < 8
+        a.X0 = load_le32(x, 4);
+        a.X1 = load_le32(x + off, 4);
+        a.G = sb::fp8(a.X0, a.X1);
+        a.anchor = off;  // reused to carry OFF to launch_scan
     } else {
         const int B = pl.filter;
         a.anchor = desc->anchor == SB_ANCHOR_SUFFIX ? m - (2 * B - 1) : 0;
@@ -197,30 +236,40 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
 cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStream_t stream)
 {
     if (a.hi <= 0) return cudaSuccess;
-    const int m = a.m;
     int per_sm;
-    if (pl.filter == 0) {
-        a.ngroups = ((unsigned long long)a.hi + sb::kGroupBytes - 1) / sb::kGroupBytes;
-        const bool hi = m > 4, mask = (m > 8) || a.pos != nullptr;
-        per_sm = c.blocks_shift[(hi ? 2 : 0) + (mask ? 1 : 0)];
+    size_t group;
+    const bool want_pos = a.pos != nullptr;
+    if (pl.filter == kFilterShort) {
+        group = kGroupShort;
+        a.ngroups = ((unsigned long long)a.hi + group - 1) / group;
+        per_sm = c.occ_short[want_pos ? 1 : 0];
+    } else if (pl.filter == kFilterWindow8) {
+        group = kGroupLong;
+        a.ngroups = ((unsigned long long)a.hi + group - 1) / group;
+        per_sm = c.occ_window[a.anchor - 1];
     } else {
+        group = kGroupLong;
         const unsigned long long end = (unsigned long long)a.hi + a.anchor + 2 * pl.filter;
-        a.ngroups = (end + sb::kGroupBytes - 1) / sb::kGroupBytes;
-        per_sm = c.blocks_block[pl.filter == 4 ? 0 : pl.filter == 8 ? 1 : pl.filter == 16 ? 2 : 3];
+        a.ngroups = (end + group - 1) / group;
+        per_sm = c.occ_block[pl.filter == 4 ? 0 : pl.filter == 8 ? 1 : pl.filter == 16 ? 2 : 3];
     }
     unsigned long long want = (a.ngroups + (sb::kThreads / 32) - 1) / (sb::kThreads / 32);
     unsigned long long maxb = (unsigned long long)c.sms * per_sm;
     unsigned grid = (unsigned)std::max(1ull, std::min(want, maxb));
-    if (pl.filter == 0) {
-        const bool hi = m > 4, mask = (m > 8) || a.pos != nullptr;
-        if (hi && mask) sb::scan_shift_kernel<true, true><<<grid, sb::kThreads, 0, stream>>>(a);
-        else if (hi) sb::scan_shift_kernel<true, false><<<grid, sb::kThreads, 0, stream>>>(a);
-        else if (mask) sb::scan_shift_kernel<false, true><<<grid, sb::kThreads, 0, stream>>>(a);
-        else sb::scan_shift_kernel<false, false><<<grid, sb::kThreads, 0, stream>>>(a);
-    } else if (pl.filter == 4) sb::scan_block_kernel<4><<<grid, sb::kThreads, 0, stream>>>(a);
-    else if (pl.filter == 8) sb::scan_block_kernel<8><<<grid, sb::kThreads, 0, stream>>>(a);
-    else if (pl.filter == 16) sb::scan_block_kernel<16><<<grid, sb::kThreads, 0, stream>>>(a);
-    else sb::scan_block_kernel<32><<<grid, sb::kThreads, 0, stream>>>(a);
+    if (pl.filter == kFilterShort) {
+        if (want_pos) sb::scan_short_kernel<true><<<grid, sb::kThreads, 0, stream>>>(a);
+        else sb::scan_short_kernel<false><<<grid, sb::kThreads, 0, stream>>>(a);
+    } else if (pl.filter == kFilterWindow8) {
+        const int off = a.anchor;
+        a.anchor = 0;
+        if (off == 1) sb::scan_window8_kernel<1, kU><<<grid, sb::kThreads, 0, stream>>>(a);
+        else if (off == 2) sb::scan_window8_kernel<2, kU><<<grid, sb::kThreads, 0, stream>>>(a);
+        else if (off == 3) sb::scan_window8_kernel<3, kU><<<grid, sb::kThreads, 0, stream>>>(a);
+        else sb::scan_window8_kernel<4, kU><<<grid, sb::kThreads, 0, stream>>>(a);
+    } else if (pl.filter == 4) sb::scan_block_kernel<4, kU><<<grid, sb::kThreads, 0, stream>>>(a);
+    else if (pl.filter == 8) sb::scan_block_kernel<8, kU><<<grid, sb::kThreads, 0, stream>>>(a);
+    else if (pl.filter == 16) sb::scan_block_kernel<16, kU><<<grid, sb::kThreads, 0, stream>>>(a);
+    else sb::scan_block_kernel<32, kU><<<grid, sb::kThreads, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -249,6 +298,7 @@ int cmp_u64(const void *a, const void *b)
 struct sb_text {
     size_t n = 0;
     int nshards = 0;
+    double bits = 8.0;  // collision entropy per byte (min over shards), from a sampled histogram
     Shard sh[kMaxShards];
 };
 
@@ -325,7 +375,7 @@ static sb_text *text_alloc(size_t n, const int *devices, int nparts, int first, 
         Shard &s = t->sh[g];
         s.dev = devices ? devices[g] : g;
         sb_shard_range(n, nparts, first + g, &s.base, &s.own, &s.len);
-        s.cap = round_up(s.len, sb::kGroupBytes) + 2 * sb::kGroupBytes;
+        s.cap = round_up(s.len, sb::kPadBytes) + sb::kPadBytes;
         DevCtx *c = get_ctx(s.dev);
         if (!c) {
             sb_text_free(t);
@@ -339,6 +389,30 @@ static sb_text *text_alloc(size_t n, const int *devices, int nparts, int first, 
         }
     }
     return t;
+}
+
+/* sampled byte histogram of every shard -> t->bits (min over shards) */
+static bool text_measure_bits(sb_text *t)
+{
+    double bits = 8.0;
+    for (int g = 0; g < t->nshards; g++) {
+        Shard &s = t->sh[g];
+        if (s.len < 4096) continue;
+        DevCtx *c = get_ctx(s.dev);
+        if (!c) return false;
+        const unsigned long long blocks = s.len / 4096;
+        const unsigned long long nsamples = std::min<unsigned long long>(blocks, 4096);
+        const unsigned long long stride = (blocks / nsamples) * 4096;
+        unsigned long long hist[256];
+        if (cudaMemsetAsync(c->d_hist, 0, sizeof hist, c->stream) != cudaSuccess) return false;
+        sb::histogram_kernel<<<(unsigned)std::min<unsigned long long>(nsamples, 2048), 256, 0, c->stream>>>(
+            s.d_text, s.len, nsamples, stride, c->d_hist);
+        if (cudaMemcpyAsync(hist, c->d_hist, sizeof hist, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return false;
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
+        bits = std::min(bits, collision_bits(hist));
+    }
+    t->bits = bits;
+    return true;
 }
 
 static sb_text *text_fill_upload(sb_text *t, const unsigned char *host)
@@ -364,6 +438,11 @@ static sb_text *text_fill_upload(sb_text *t, const unsigned char *host)
             sb_text_free(t);
             return nullptr;
         }
+    }
+    if (!text_measure_bits(t)) {
+        set_err("text statistics kernel failed: %s%s", cudaGetErrorString(cudaGetLastError()));
+        sb_text_free(t);
+        return nullptr;
     }
     return t;
 }
@@ -396,6 +475,11 @@ static sb_text *text_fill_generate(sb_text *t, int sigma, uint64_t seed)
             sb_text_free(t);
             return nullptr;
         }
+    }
+    if (!text_measure_bits(t)) {
+        set_err("text statistics kernel failed: %s%s", cudaGetErrorString(cudaGetLastError()));
+        sb_text_free(t);
+        return nullptr;
     }
     return t;
 }
@@ -440,6 +524,7 @@ sb_text *sb_text_generate_part(size_t n_total, int sigma, uint64_t seed, int npa
 
 size_t sb_text_length(const sb_text *t) { return t ? t->n : 0; }
 int sb_text_shards(const sb_text *t) { return t ? t->nshards : 0; }
+double sb_text_entropy_bits(const sb_text *t) { return t ? t->bits : 0.0; }
 
 int sb_text_download(const sb_text *t, size_t off, size_t len, unsigned char *host)
 {
@@ -501,7 +586,7 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
     if (!tab) return SB_ERR_NOMEM;
     sb_prep_tables(algo, x, m, tab);
     Plan pl;
-    make_plan(pl, desc, x, m, flags);
+    make_plan(pl, desc, x, m, flags, t->bits);
     const double t1 = now_ms();
 
     DevCtx *ctx[kMaxShards];
@@ -535,7 +620,7 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
         for (int k = 0; k < g; k++) dev_first[g] = dev_first[g] && (t->sh[k].dev != s.dev);
         CU_TRY(cudaSetDevice(s.dev), SB_ERR_CUDA);
         sb::ScanArgs a = pl.args;
-        a.text = reinterpret_cast<const uint4 *>(s.d_text);
+        a.text = s.d_text;
         a.pat = c.d_pat;
         a.counters = c.d_counters;
         a.base = s.base;
@@ -646,13 +731,16 @@ long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned
     if (!tab) return SB_ERR_NOMEM;
     sb_prep_tables(algo, x, m, tab);
     Plan pl;
-    make_plan(pl, desc, x, m, flags & ~SB_FLAG_POSITIONS);
+    /* selectivity estimate from a host-side sample of the text (first 64 KiB) */
+    unsigned long long hist[256] = {0};
+    for (size_t i = 0, e = std::min<size_t>(n, 65536); i < e; i++) hist[y[i]]++;
+    make_plan(pl, desc, x, m, flags & ~SB_FLAG_POSITIONS, n >= 4096 ? collision_bits(hist) : 8.0);
     const double t1 = now_ms();
 
     /* chunk buffers: 64 MiB of start positions + halo each, double buffered */
     const size_t kChunk = (size_t)64 << 20;
     const size_t chunk = std::min(kChunk, round_up(n ? n : 1, kShardAlign));
-    const size_t need = round_up(chunk + kHalo, sb::kGroupBytes) + 2 * sb::kGroupBytes;
+    const size_t need = round_up(chunk + kHalo, sb::kPadBytes) + sb::kPadBytes;
     if (c->chunk_cap < need) {
         for (int b = 0; b < 2; b++) {
             if (c->d_chunk[b]) cudaFree(c->d_chunk[b]);
@@ -684,10 +772,10 @@ long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned
         long long hi = std::min<long long>(total_starts - (long long)base, (long long)chunk);
         CU_TRY(cudaMemcpyAsync(c->d_chunk[b], y + base, len, cudaMemcpyHostToDevice, c->cstream[b]), SB_ERR_CUDA);
         // bytes past `len` may be stale from an earlier chunk: zero what the last group can touch
-        const size_t pad_end = std::min(c->chunk_cap, round_up(len, sb::kGroupBytes) + 2 * sb::kGroupBytes);
+        const size_t pad_end = std::min(c->chunk_cap, round_up(len, sb::kPadBytes) + sb::kPadBytes);
         CU_TRY(cudaMemsetAsync(c->d_chunk[b] + len, 0, pad_end - len, c->cstream[b]), SB_ERR_CUDA);
         sb::ScanArgs a = pl.args;
-        a.text = reinterpret_cast<const uint4 *>(c->d_chunk[b]);
+        a.text = c->d_chunk[b];
         a.pat = c->d_pat;
         a.counters = c->d_counters;
         a.base = base;

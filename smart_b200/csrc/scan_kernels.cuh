@@ -5,23 +5,24 @@
  * number of start positions j in the shard's owned range with x[0..m) == y[j..j+m), and,
  * when asked, those positions.  How they get there is B200-first:
  *
- *   - the text is streamed from HBM exactly once with 128-bit coalesced, L1-bypassing loads
- *     (LDG.E.128.NA), 4 independent loads in flight per thread, one warp per 2 KiB group,
- *     groups strided across a persistent grid;
+ *   - the text is streamed from HBM exactly once with coalesced, L1-bypassing 256-bit loads
+ *     (ld.global.nc.L1::no_allocate.v8.u32 -> LDG.E.NA.ENL2.256), U independent loads in flight per
+ *     thread, one warp per U KiB group, groups strided across a grid sized to the resident CTAs;
  *   - a packed candidate filter runs entirely in registers:
- *       * scan_shift  (m <= 14): the first min(m,8) pattern bytes are compared exactly at all
- *         16 start positions of a vector using funnel-shifted words (SHF + LOP3), the 8-byte
+ *       * scan_block<B> (m >= 2B-1): every occurrence covers one B-aligned text block completely,
+ *         so only ALIGNED blocks are fingerprinted (IMAD, FMA pipe) and compared with the B
+ *         fingerprints of the pattern's B-grams at offsets a..a+B-1 (one ISETP.EQ.OR per start
+ *         position, ALU pipe): no shifts, no halo, no shared memory;
+ *       * scan_window8<OFF> (5 <= m, low-entropy texts or m < 2B-1): an 8-byte window fingerprint
+ *         at EVERY start position (SHF funnel shift + IMAD + ISETP.EQ.OR per position); the 8-byte
  *         halo comes from the neighbouring lane by shuffle, not from memory;
- *       * scan_block<B> (m >= 2B-1): every occurrence covers one B-aligned text block
- *         completely, so only ALIGNED blocks are fingerprinted (IMAD on the FMA pipe) and
- *         compared with the B fingerprints of the pattern's B-grams at offsets a..a+B-1
- *         (one ISETP.EQ.OR per start position on the ALU pipe, no shifts, no halo);
- *   - candidates (rare) go to a warp-cooperative exact verification that reads the text
- *     through L2 with unaligned 32-bit windows, 128 bytes per step;
+ *       * scan_short (m <= 4): exact masked-word compare at every position, counted in registers;
+ *   - candidates (rare) go to an exact verification that reads the text through L2 with unaligned
+ *     32-bit windows (warp-cooperative, 128 bytes per step, in scan_block);
  *   - counts are reduced with warp shuffles and ONE atomicAdd per block.
  *
  * Nothing here is a dense contraction: tensor cores / TMEM are deliberately unused; the bound
- * is HBM bandwidth, with integer issue rate as the secondary limit (DESIGN.md section 4).
+ * is HBM bandwidth, with integer issue rate as the secondary limit (DESIGN.md).
  */
 #pragma once
 #include <cstdint>
@@ -29,9 +30,8 @@
 
 namespace sb {
 
-constexpr int kThreads = 256;            // threads per CTA
-constexpr int kUnroll = 4;               // 128-bit loads in flight per thread
-constexpr int kGroupBytes = 32 * 16 * kUnroll;  // bytes one warp consumes per iteration (2 KiB)
+constexpr int kThreads = 256;       // threads per CTA
+constexpr int kPadBytes = 8192;     // every text buffer is zero padded to a multiple of this plus this much
 constexpr unsigned kFull = 0xffffffffu;
 
 // fingerprint multipliers (odd => w -> w*K is a bijection mod 2^32)
@@ -47,23 +47,38 @@ __host__ __device__ __forceinline__ uint32_t fp16(uint32_t w0, uint32_t w1, uint
 __host__ __device__ __forceinline__ uint32_t fp32(uint32_t lo16, uint32_t hi16) { return lo16 * K3 + hi16; }
 
 struct ScanArgs {
-    const uint4 *text;            // shard buffer, 16-B aligned, zero-padded to a group multiple + 1 group
+    const uint8_t *text;          // shard buffer, 32-B aligned, zero padded (kPadBytes rule)
     const uint32_t *pat;          // pattern as little-endian words, zero padded
     unsigned long long *counters; // [0] match count, [1] position cursor, [2] verified candidates
     unsigned long long *pos;      // position sink (unsorted) or nullptr
     unsigned long long pos_cap;
     unsigned long long base;      // global offset of local byte 0
     long long hi;                 // owned local start positions are [0, hi)
-    unsigned long long ngroups;   // 2 KiB groups to scan
+    unsigned long long ngroups;   // groups to scan (group size depends on the kernel)
     int m;
     int anchor;                   // byte offset a of the fingerprinted sub-pattern
     int nwords;                   // ceil(m/4)
     uint32_t tailmask;            // mask for the last pattern word
-    uint32_t H[32];               // block kernel: fingerprints of x[a+d .. a+d+B), d < B
-    uint32_t X0, X1, M0, M1;      // shift kernel: first 8 pattern bytes (pre-masked) and their masks
+    uint32_t H[32];               // scan_block: fingerprints of x[a+d .. a+d+B), d < B
+    uint32_t X0, X1, M0;          // scan_short: masked first word; scan_window8: the two window words
+    uint32_t G;                   // scan_window8: fp8(X0, X1)
 };
 
-__device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
+struct V8 {
+    uint32_t w[8];
+};
+
+__device__ __forceinline__ V8 ldg_stream256(const uint8_t *p)
+{
+    V8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
+                   "=r"(r.w[7])
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint4 ldg_stream128(const uint8_t *p)
 {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -73,7 +88,7 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
 }
 
 /* 32-bit little-endian window at an arbitrary byte offset (two aligned loads + funnel shift) */
-__device__ __forceinline__ uint32_t text_window32(const uint4 *text, long long off)
+__device__ __forceinline__ uint32_t text_window32(const uint8_t *text, long long off)
 {
     const uint32_t *w = reinterpret_cast<const uint32_t *>(text) + (off >> 2);
     uint32_t a = __ldg(w), b = __ldg(w + 1);
@@ -94,6 +109,17 @@ __device__ __forceinline__ bool warp_verify(const ScanArgs &a, long long j, unsi
             ok = (diff == 0);
         }
         if (!__all_sync(kFull, ok)) return false;
+    }
+    return true;
+}
+
+/* the same comparison by a single lane (divergent callers), words [from, nwords) */
+__device__ __forceinline__ bool lane_verify(const ScanArgs &a, long long j, int from)
+{
+    for (int k = from; k < a.nwords; k++) {
+        uint32_t diff = text_window32(a.text, j + 4ll * k) ^ __ldg(a.pat + k);
+        if (k == a.nwords - 1) diff &= a.tailmask;
+        if (diff) return false;
     }
     return true;
 }
@@ -133,53 +159,48 @@ __device__ __forceinline__ void block_reduce_count(const ScanArgs &a, unsigned c
     }
 }
 
-/* ===================================================================== scan_block<B> */
+/* ===================================================================== scan_block<B, U> */
 
-/* Slow path of scan_block: lane `src` of this warp saw a fingerprint hit in its vector.
- * The whole warp re-derives which (block, d) slots hit and verifies each candidate. */
+/* Slow path of scan_block: some lane of this warp saw a fingerprint hit in its 32-byte vector.
+ * For each such lane the whole warp re-derives which of the 32 (block, d) slots hit (one slot per
+ * lane) and verifies each candidate cooperatively. */
 template <int B>
-__device__ __noinline__ void block_candidates(const ScanArgs &a, uint4 v, uint32_t hpair, long long voff,
-                                              bool hit, unsigned lane, unsigned &cnt, unsigned &nver)
+__device__ __noinline__ uint2 block_candidates(const ScanArgs &a, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3,
+                                               uint32_t v4, uint32_t v5, uint32_t v6, uint32_t v7, long long voff,
+                                               bool hit, unsigned lane)
 {
+    // everything by value and the result returned: a by-reference vector would force the caller to
+    // keep a copy of every loaded vector in local memory (an STL per load in the hot loop)
+    const uint32_t vw[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
+    unsigned cnt = 0, nver = 0;
     unsigned pending = __ballot_sync(kFull, hit);
     while (pending) {
         const int src = __ffs(pending) - 1;
         pending &= pending - 1;
-        const uint32_t sx = __shfl_sync(kFull, v.x, src), sy = __shfl_sync(kFull, v.y, src);
-        const uint32_t sz = __shfl_sync(kFull, v.z, src), sw = __shfl_sync(kFull, v.w, src);
-        const uint32_t sh = __shfl_sync(kFull, hpair, src);
+        uint32_t s[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = __shfl_sync(kFull, vw[i], src);
         const long long soff = __shfl_sync(kFull, voff, src);
-        // 16 (block, d) slots per vector; lanes 0..15 each test one
-        const int slot = (int)(lane & 15);
+        const int blk = (int)lane / B, d = (int)lane % B;  // slot of this lane
         uint32_t h;
-        int d;
-        long long t;
         if (B == 4) {
-            const int blk = slot >> 2;
-            d = slot & 3;
-            h = blk == 0 ? sx : blk == 1 ? sy : blk == 2 ? sz : sw;
-            t = soff + 4 * blk;
+            h = s[0];
+#pragma unroll
+            for (int i = 1; i < 8; i++) h = (blk == i) ? s[i] : h;
         } else if (B == 8) {
-            const int blk = slot >> 3;
-            d = slot & 7;
-            h = blk == 0 ? fp8(sx, sy) : fp8(sz, sw);
-            t = soff + 8 * blk;
+            h = fp8(s[0], s[1]);
+#pragma unroll
+            for (int i = 1; i < 4; i++) h = (blk == i) ? fp8(s[2 * i], s[2 * i + 1]) : h;
         } else if (B == 16) {
-            d = slot;
-            h = fp16(sx, sy, sz, sw);
-            t = soff;
+            h = blk ? fp16(s[4], s[5], s[6], s[7]) : fp16(s[0], s[1], s[2], s[3]);
         } else {
-            d = slot + 16 * (src & 1);
-            h = sh;
-            t = soff & ~31ll;
+            h = fp32(fp16(s[0], s[1], s[2], s[3]), fp16(s[4], s[5], s[6], s[7]));
         }
-        unsigned slots = __ballot_sync(kFull, lane < 16 && h == a.H[d]);
+        unsigned slots = __ballot_sync(kFull, h == a.H[d]);
         while (slots) {
-            const int s = __ffs(slots) - 1;
+            const int sl = __ffs(slots) - 1;
             slots &= slots - 1;
-            const long long ts = __shfl_sync(kFull, t, s);
-            const int ds = __shfl_sync(kFull, d, s);
-            const long long j = ts - ds - a.anchor;
+            const long long j = soff + (sl / B) * B - (sl % B) - a.anchor;
             if (j >= 0 && j < a.hi) {
                 nver += (lane == 0);
                 if (warp_verify(a, j, lane) && lane == 0) {
@@ -189,9 +210,42 @@ __device__ __noinline__ void block_candidates(const ScanArgs &a, uint4 v, uint32
             }
         }
     }
+    return make_uint2(cnt, nver);
 }
 
 template <int B>
+__device__ __forceinline__ bool block_hit(const ScanArgs &a, const V8 &v)
+{
+    bool hit = false;
+    if (B == 4) {
+#pragma unroll
+        for (int w = 0; w < 8; w++)
+#pragma unroll
+            for (int d = 0; d < 4; d++) hit |= (v.w[w] == a.H[d]);
+    } else if (B == 8) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t h = fp8(v.w[2 * k], v.w[2 * k + 1]);
+#pragma unroll
+            for (int d = 0; d < 8; d++) hit |= (h == a.H[d]);
+        }
+    } else if (B == 16) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const uint32_t h = fp16(v.w[4 * k], v.w[4 * k + 1], v.w[4 * k + 2], v.w[4 * k + 3]);
+#pragma unroll
+            for (int d = 0; d < 16; d++) hit |= (h == a.H[d]);
+        }
+    } else {
+        const uint32_t h = fp32(fp16(v.w[0], v.w[1], v.w[2], v.w[3]), fp16(v.w[4], v.w[5], v.w[6], v.w[7]));
+#pragma unroll
+        for (int d = 0; d < 32; d++) hit |= (h == a.H[d]);
+    }
+    return hit;
+}
+
+/* group = U x 1 KiB per warp */
+template <int B, int U>
 __global__ void __launch_bounds__(kThreads) scan_block_kernel(const __grid_constant__ ScanArgs a)
 {
     const unsigned lane = threadIdx.x & 31;
@@ -199,127 +253,60 @@ __global__ void __launch_bounds__(kThreads) scan_block_kernel(const __grid_const
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * kThreads) >> 5;
     unsigned cnt = 0, nver = 0;
 
-    // the 16 fingerprints this lane compares against (B==32: even lanes d<16, odd lanes d>=16)
-    uint32_t H[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        if (B == 32)
-            H[i] = (lane & 1) ? a.H[16 + i] : a.H[i];
-        else
-            H[i] = a.H[i % B];
-    }
-
     for (unsigned long long g = warp; g < a.ngroups; g += nwarps) {
-        const uint4 *p = a.text + g * (kGroupBytes / 16) + lane;
-        uint4 v[kUnroll];
+        const uint8_t *p = a.text + g * (U * 1024ull) + lane * 32;
+        V8 v[U];
 #pragma unroll
-        for (int c = 0; c < kUnroll; c++) v[c] = ldg_stream(p + c * 32);
+        for (int c = 0; c < U; c++) v[c] = ldg_stream256(p + c * 1024);
 #pragma unroll
-        for (int c = 0; c < kUnroll; c++) {
-            bool hit = false;
-            uint32_t hp = 0;
-            if (B == 4) {
-#pragma unroll
-                for (int d = 0; d < 4; d++)
-                    hit |= (v[c].x == H[d]) | (v[c].y == H[d]) | (v[c].z == H[d]) | (v[c].w == H[d]);
-            } else if (B == 8) {
-                const uint32_t h0 = fp8(v[c].x, v[c].y), h1 = fp8(v[c].z, v[c].w);
-#pragma unroll
-                for (int d = 0; d < 8; d++) hit |= (h0 == H[d]) | (h1 == H[d]);
-            } else if (B == 16) {
-                const uint32_t h = fp16(v[c].x, v[c].y, v[c].z, v[c].w);
-#pragma unroll
-                for (int d = 0; d < 16; d++) hit |= (h == H[d]);
-            } else {
-                const uint32_t mine = fp16(v[c].x, v[c].y, v[c].z, v[c].w);
-                const uint32_t other = __shfl_xor_sync(kFull, mine, 1);
-                hp = (lane & 1) ? fp32(other, mine) : fp32(mine, other);
-#pragma unroll
-                for (int d = 0; d < 16; d++) hit |= (hp == H[d]);
-            }
+        for (int c = 0; c < U; c++) {
+            const bool hit = block_hit<B>(a, v[c]);
             if (__any_sync(kFull, hit)) {
-                const long long voff = (long long)(g * kGroupBytes) + c * 512 + lane * 16;
-                block_candidates<B>(a, v[c], hp, voff, hit, lane, cnt, nver);
+                const long long voff = (long long)(g * (U * 1024ull)) + c * 1024 + lane * 32;
+                const uint2 r = block_candidates<B>(a, v[c].w[0], v[c].w[1], v[c].w[2], v[c].w[3], v[c].w[4],
+                                                    v[c].w[5], v[c].w[6], v[c].w[7], voff, hit, lane);
+                cnt += r.x;
+                nver += r.y;
             }
         }
     }
     block_reduce_count(a, cnt, nver);
 }
 
-/* ===================================================================== scan_shift */
+/* ===================================================================== scan_window8<OFF, U> */
 
-/* Per-lane tail of scan_shift when m > 8 or positions are wanted: `mm` has bit p set for every
- * start position p of this lane's vector whose first min(m,8) bytes match. */
-__device__ __noinline__ void shift_candidates(const ScanArgs &a, unsigned mm, long long voff, unsigned &cnt,
-                                              unsigned &nver)
+/* Per-lane slow path of scan_window8: W[0..9] are the lane's 32 bytes plus the next 8; re-test every
+ * start position exactly (both window words), then verify the rest of the pattern. */
+template <int OFF>
+__device__ __noinline__ uint2 window8_candidates(const ScanArgs &a, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
+                                                 uint32_t w4, uint32_t w5, uint32_t w6, uint32_t w7, uint32_t w8,
+                                                 uint32_t w9, long long voff)
 {
-    const unsigned char *tb = reinterpret_cast<const unsigned char *>(a.text);
-    const unsigned char *pb = reinterpret_cast<const unsigned char *>(a.pat);
-    while (mm) {
-        const int p = __ffs(mm) - 1;
-        mm &= mm - 1;
+    const uint32_t W[10] = {w0, w1, w2, w3, w4, w5, w6, w7, w8, w9};  // by value, see block_candidates
+    unsigned cnt = 0, nver = 0;
+#pragma unroll 1
+    for (int p = 0; p < 32; p++) {
         const long long j = voff + p;
         if (j >= a.hi) break;
-        bool ok = true;
+        const int q = p >> 2, r = (p & 3) * 8;
+        const int p2 = p + OFF, q2 = p2 >> 2, r2 = (p2 & 3) * 8;
+        const uint32_t lo = __funnelshift_r(W[q], W[q + 1], r);
+        const uint32_t hi = __funnelshift_r(W[q2], q2 + 1 < 10 ? W[q2 + 1] : 0u, r2);
+        if (lo != a.X0 || hi != a.X1) continue;
         if (a.m > 8) {
             nver++;
-            for (int k = 8; k < a.m; k++)
-                if (__ldg(tb + j + k) != __ldg(pb + k)) {
-                    ok = false;
-                    break;
-                }
+            if (!lane_verify(a, j, 2)) continue;
         }
-        if (ok) {
-            cnt++;
-            emit_match(a, j);
-        }
+        cnt++;
+        emit_match(a, j);
     }
+    return make_uint2(cnt, nver);
 }
 
-/* HI: compare a second word (m > 4).  MASK: collect a per-position mask and post-process
- * (needed for m > 8, for position output and for vectors straddling the owned range). */
-template <bool HI>
-__device__ __forceinline__ unsigned shift_match_mask(const ScanArgs &a, const uint32_t (&W)[6])
-{
-    unsigned mm = 0;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const uint32_t lo = r ? __funnelshift_r(W[q], W[q + 1], 8 * r) : W[q];
-            uint32_t t = (lo & a.M0) ^ a.X0;
-            if (HI) {
-                const uint32_t hi = r ? __funnelshift_r(W[q + 1], W[q + 2], 8 * r) : W[q + 1];
-                t |= (hi & a.M1) ^ a.X1;
-            }
-            mm |= (t == 0 ? 1u : 0u) << (4 * q + r);
-        }
-    }
-    return mm;
-}
-
-template <bool HI>
-__device__ __forceinline__ unsigned shift_match_count(const ScanArgs &a, const uint32_t (&W)[6])
-{
-    unsigned c = 0;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const uint32_t lo = r ? __funnelshift_r(W[q], W[q + 1], 8 * r) : W[q];
-            uint32_t t = (lo & a.M0) ^ a.X0;
-            if (HI) {
-                const uint32_t hi = r ? __funnelshift_r(W[q + 1], W[q + 2], 8 * r) : W[q + 1];
-                t |= (hi & a.M1) ^ a.X1;
-            }
-            c += (t == 0);
-        }
-    }
-    return c;
-}
-
-template <bool HI, bool MASK>
-__global__ void __launch_bounds__(kThreads) scan_shift_kernel(const __grid_constant__ ScanArgs a)
+/* 8-byte window fingerprint at every start position: window = bytes [p, p+4) and [p+OFF, p+OFF+4),
+ * OFF = 4 for m >= 8 and m-4 for 5 <= m <= 7 (the two words overlap and cover exactly m bytes). */
+template <int OFF, int U>
+__global__ void __launch_bounds__(kThreads) scan_window8_kernel(const __grid_constant__ ScanArgs a)
 {
     const unsigned lane = threadIdx.x & 31;
     const unsigned long long warp = ((unsigned long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
@@ -327,37 +314,142 @@ __global__ void __launch_bounds__(kThreads) scan_shift_kernel(const __grid_const
     unsigned cnt = 0, nver = 0;
 
     for (unsigned long long g = warp; g < a.ngroups; g += nwarps) {
-        const uint4 *p = a.text + g * (kGroupBytes / 16) + lane;
-        uint4 v[kUnroll];
+        const uint8_t *p = a.text + g * (U * 1024ull) + lane * 32;
+        V8 v[U];
 #pragma unroll
-        for (int c = 0; c < kUnroll; c++) v[c] = ldg_stream(p + c * 32);
-        // halo for the last chunk's lane 31: the first 8 bytes of the next group (lane 0 fetches them)
+        for (int c = 0; c < U; c++) v[c] = ldg_stream256(p + c * 1024);
+        // halo of the last chunk's lane 31: first 8 bytes of the next group, fetched by lane 0 (L2 hit later)
         uint2 gn = make_uint2(0u, 0u);
-        if (lane == 0) gn = __ldg(reinterpret_cast<const uint2 *>(a.text + (g + 1) * (kGroupBytes / 16)));
+        if (lane == 0) gn = __ldg(reinterpret_cast<const uint2 *>(a.text + (g + 1) * (U * 1024ull)));
 #pragma unroll
-        for (int c = 0; c < kUnroll; c++) {
-            // next 8 bytes after this lane's vector: lane+1's (x,y); lane 31 takes lane 0 of the next chunk
+        for (int c = 0; c < U; c++) {
+            // the 8 bytes after this lane's vector: lane+1's first two words; lane 31 takes lane 0 of the next chunk
             uint32_t sx, sy;
-            if (c + 1 < kUnroll) {
-                sx = lane == 0 ? v[c + 1].x : v[c].x;
-                sy = lane == 0 ? v[c + 1].y : v[c].y;
+            if (c + 1 < U) {
+                sx = lane == 0 ? v[c + 1].w[0] : v[c].w[0];
+                sy = lane == 0 ? v[c + 1].w[1] : v[c].w[1];
             } else {
-                sx = lane == 0 ? gn.x : v[c].x;
-                sy = lane == 0 ? gn.y : v[c].y;
+                sx = lane == 0 ? gn.x : v[c].w[0];
+                sy = lane == 0 ? gn.y : v[c].w[1];
             }
-            const uint32_t nx = __shfl_sync(kFull, sx, (lane + 1) & 31);
-            const uint32_t ny = __shfl_sync(kFull, sy, (lane + 1) & 31);
-            const uint32_t W[6] = {v[c].x, v[c].y, v[c].z, v[c].w, nx, ny};
-            const long long voff = (long long)(g * kGroupBytes) + c * 512 + lane * 16;
-            if (!MASK && voff + 16 <= a.hi) {
-                cnt += shift_match_count<HI>(a, W);
-            } else if (voff < a.hi) {
-                const unsigned mm = shift_match_mask<HI>(a, W);
-                if (mm) shift_candidates(a, mm, voff, cnt, nver);
+            uint32_t W[10];
+#pragma unroll
+            for (int i = 0; i < 8; i++) W[i] = v[c].w[i];
+            W[8] = __shfl_sync(kFull, sx, (lane + 1) & 31);
+            W[9] = __shfl_sync(kFull, sy, (lane + 1) & 31);
+            // shifted words for byte offsets 0..31+OFF
+            uint32_t S[32 + OFF];
+#pragma unroll
+            for (int b = 0; b < 32 + OFF; b++)
+                S[b] = (b & 3) ? __funnelshift_r(W[b >> 2], W[(b >> 2) + 1], 8 * (b & 3)) : W[b >> 2];
+            bool hit = false;
+#pragma unroll
+            for (int b = 0; b < 32; b++) hit |= (fp8(S[b], S[b + OFF]) == a.G);
+            if (hit) {
+                const long long voff = (long long)(g * (U * 1024ull)) + c * 1024 + lane * 32;
+                const uint2 r = window8_candidates<OFF>(a, W[0], W[1], W[2], W[3], W[4], W[5], W[6], W[7], W[8], W[9], voff);
+                cnt += r.x;
+                nver += r.y;
             }
         }
     }
     block_reduce_count(a, cnt, nver);
+}
+
+/* ===================================================================== scan_short (m <= 4) */
+
+/* Per-lane tail of scan_short when positions are wanted or the vector straddles the owned range:
+ * `mm` has bit p set for every start position p of this lane's 16-byte vector that matches. */
+__device__ __noinline__ unsigned short_candidates(const ScanArgs &a, unsigned mm, long long voff)
+{
+    unsigned cnt = 0;
+    while (mm) {
+        const int p = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const long long j = voff + p;
+        if (j >= a.hi) break;
+        cnt++;
+        emit_match(a, j);
+    }
+    return cnt;
+}
+
+/* MASK: collect a per-position mask and post-process (position output). 128-bit loads, 4 in flight. */
+template <bool MASK>
+__global__ void __launch_bounds__(kThreads) scan_short_kernel(const __grid_constant__ ScanArgs a)
+{
+    constexpr int U = 4;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long warp = ((unsigned long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * kThreads) >> 5;
+    unsigned cnt = 0;
+
+    for (unsigned long long g = warp; g < a.ngroups; g += nwarps) {
+        const uint8_t *p = a.text + g * (U * 512ull) + lane * 16;
+        uint4 v[U];
+#pragma unroll
+        for (int c = 0; c < U; c++) v[c] = ldg_stream128(p + c * 512);
+        uint32_t gn = 0;
+        if (lane == 0) gn = __ldg(reinterpret_cast<const uint32_t *>(a.text + (g + 1) * (U * 512ull)));
+#pragma unroll
+        for (int c = 0; c < U; c++) {
+            uint32_t sx;
+            if (c + 1 < U)
+                sx = lane == 0 ? v[c + 1].x : v[c].x;
+            else
+                sx = lane == 0 ? gn : v[c].x;
+            const uint32_t nx = __shfl_sync(kFull, sx, (lane + 1) & 31);
+            const uint32_t W[5] = {v[c].x, v[c].y, v[c].z, v[c].w, nx};
+            const long long voff = (long long)(g * (U * 512ull)) + c * 512 + lane * 16;
+            if (!MASK && voff + 16 <= a.hi) {
+#pragma unroll
+                for (int b = 0; b < 16; b++) {
+                    const uint32_t lo = (b & 3) ? __funnelshift_r(W[b >> 2], W[(b >> 2) + 1], 8 * (b & 3)) : W[b >> 2];
+                    cnt += (((lo & a.M0) ^ a.X0) == 0);
+                }
+            } else if (voff < a.hi) {
+                unsigned mm = 0;
+#pragma unroll
+                for (int b = 0; b < 16; b++) {
+                    const uint32_t lo = (b & 3) ? __funnelshift_r(W[b >> 2], W[(b >> 2) + 1], 8 * (b & 3)) : W[b >> 2];
+                    mm |= ((((lo & a.M0) ^ a.X0) == 0) ? 1u : 0u) << b;
+                }
+                if (mm) cnt += short_candidates(a, mm, voff);
+            }
+        }
+    }
+    block_reduce_count(a, cnt, 0u);
+}
+
+/* ===================================================================== text statistics */
+
+/* byte histogram of up to `nsamples` 4 KiB samples spread evenly over the shard: used once per text
+ * to estimate how selective a B-byte fingerprint is (collision entropy), see choose_filter() */
+__global__ void __launch_bounds__(256) histogram_kernel(const uint8_t *text, unsigned long long len,
+                                                        unsigned long long nsamples, unsigned long long stride,
+                                                        unsigned long long *hist)
+{
+    __shared__ unsigned h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    for (unsigned long long s = blockIdx.x; s < nsamples; s += gridDim.x) {
+        const unsigned long long off = s * stride;
+        for (unsigned i = threadIdx.x * 16; i < 4096; i += 256 * 16) {
+            if (off + i + 16 <= len) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(text + off + i);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    atomicAdd(&h[w[k] & 0xff], 1u);
+                    atomicAdd(&h[(w[k] >> 8) & 0xff], 1u);
+                    atomicAdd(&h[(w[k] >> 16) & 0xff], 1u);
+                    atomicAdd(&h[w[k] >> 24], 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(hist + threadIdx.x, (unsigned long long)h[threadIdx.x]);
 }
 
 /* ===================================================================== text generator */

@@ -14,7 +14,8 @@ from golden_texts import ALGOS, GOLDEN, TEXT_NAMES, make_patterns, make_text
 
 pytestmark = pytest.mark.gpu
 
-FILTERS = {0: sb.FLAG_FILTER_SHIFT, 4: sb.FLAG_FILTER_B4, 8: sb.FLAG_FILTER_B8, 16: sb.FLAG_FILTER_B16,
+# filter kinds reported by sb_last_timing: 0 scan_short, 1 scan_window8, 4/8/16/32 scan_block<B>
+FILTERS = {0: 0, 1: sb.FLAG_FILTER_SHIFT, 4: sb.FLAG_FILTER_B4, 8: sb.FLAG_FILTER_B8, 16: sb.FLAG_FILTER_B16,
            32: sb.FLAG_FILTER_B32}
 
 
@@ -26,7 +27,7 @@ def expected(algo, m, bf):
 
 
 def filters_for(m):
-    out = [0] if m <= 14 else []
+    out = [0] if m <= 4 else [1]
     out += [b for b in (4, 8, 16, 32) if m >= 2 * b - 1]
     return out
 

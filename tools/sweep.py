@@ -11,7 +11,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import smart_b200 as sb  # noqa: E402
 
-FILTERS = {0: sb.FLAG_FILTER_SHIFT, 4: sb.FLAG_FILTER_B4, 8: sb.FLAG_FILTER_B8, 16: sb.FLAG_FILTER_B16,
+FILTERS = {0: 0, 1: sb.FLAG_FILTER_SHIFT, 4: sb.FLAG_FILTER_B4, 8: sb.FLAG_FILTER_B8, 16: sb.FLAG_FILTER_B16,
            32: sb.FLAG_FILTER_B32}
 
 
@@ -35,7 +35,7 @@ def main():
                 if a.default_only:
                     fl = [None]
                 else:
-                    fl = ([0] if m <= 14 else []) + [b for b in (4, 8, 16, 32) if m >= 2 * b - 1]
+                    fl = [None] + ([0] if m <= 4 else [1]) + [b for b in (4, 8, 16, 32) if m >= 2 * b - 1]
                 for f in fl:
                     flags = 0 if f is None else FILTERS[f]
                     ts, cnt = [], None
@@ -44,7 +44,7 @@ def main():
                         tm = sb.last_timing()
                         ts.append(tm.kernel_ms)
                         cnt = r.count
-                    rec = {"sigma": sigma, "m": m, "filter": tm.filter_kind, "count": cnt, "verified": tm.verified,
+                    rec = {"sigma": sigma, "m": m, "filter": tm.filter_kind, "default": f is None, "count": cnt, "verified": tm.verified,
                            "kernel_ms_median": float(np.median(ts)), "GBps": n / (float(np.median(ts)) * 1e-3) / 1e9,
                            "GBps_best": n / (min(ts) * 1e-3) / 1e9}
                     out.write(json.dumps(rec) + "\n")
