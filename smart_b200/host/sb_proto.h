@@ -1,0 +1,36 @@
+/* Wire protocol between the thin per-algorithm executables and the resident GPU worker (smartd).
+ * One request / one reply per search over a Unix stream socket.  The text and the pattern never travel
+ * over the socket: they stay in the SysV segments the SMART driver created (smart.c:553-568, :236-250 in
+ * the reference tree) and the worker attaches them by key, exactly as an algorithm executable would
+ * (main.h:60-98). */
+#ifndef SB_PROTO_H
+#define SB_PROTO_H
+#include <stdint.h>
+
+#define SB_PROTO_MAGIC 0x53423230u /* "SB20" */
+enum { SB_REQ_SEARCH = 1, SB_REQ_PING = 2, SB_REQ_QUIT = 3, SB_REQ_STATS = 4 };
+
+typedef struct sb_request {
+    uint32_t magic;
+    int32_t kind;
+    int32_t algo; /* sb_algo_id */
+    int32_t pkey; /* SysV key of the pattern segment */
+    int32_t m;
+    int32_t tkey; /* SysV key of the text segment */
+    int32_t n;
+    int32_t reserved;
+} sb_request;
+
+typedef struct sb_reply {
+    uint32_t magic;
+    int32_t status; /* 0 ok, else errno-like */
+    int64_t count;  /* occurrences, -1 not applicable */
+    double pre_ms, run_ms;
+    double upload_ms;     /* text (re)upload paid by this request, 0 when the resident text was reused */
+    uint64_t searches;    /* STATS: searches served */
+    uint64_t text_uploads; /* STATS: text uploads (cache misses) */
+} sb_reply;
+
+/* default socket path: $SMART_B200_SOCK or /tmp/smart_b200.<uid>.sock */
+const char *sb_socket_path(char *buf, unsigned long len);
+#endif

@@ -1,0 +1,104 @@
+"""GPU-side checks of the C host programs through the real plugin protocol (SysV shm + one process per
+search): the reference's own `test` binary drives OUR per-algorithm executables, our driver runs them with
+the resident worker, and the worker keeps the text in HBM across the whole loop."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "bin")
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+pytestmark = pytest.mark.gpu
+
+
+def run(cmd, **kw):
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600, **kw)
+
+
+@pytest.fixture()
+def worker(tmp_path):
+    sock = str(tmp_path / "w.sock")
+    env = {**os.environ, "SMART_B200_SOCK": sock}
+    r = run([os.path.join(BIN, "smartd")], env=env)
+    assert r.returncode == 0 and r.stdout.startswith("ready"), (r.stdout, r.stderr)
+    yield env
+    run([os.path.join(BIN, "smartd"), "-stop"], env=env)
+
+
+def stats(env):
+    r = run([os.path.join(BIN, "smartd"), "-stats"], env=env)
+    m = re.search(r"searches (\d+) text_uploads (\d+)", r.stdout)
+    return int(m.group(1)), int(m.group(2))
+
+
+def test_standalone_mode_prints_reference_format():
+    # main.h:123-135: "<algo> P m T n" -> "found %d occurrences"
+    for algo, want in (("bf", 4), ("kmp", 4), ("qf23", 4), ("hash5", -1)):
+        r = run([os.path.join(BIN, "algos", algo), "aba", "3", "ababababab", "10"],
+                env={**os.environ, "SMART_B200_NO_WORKER": "1"})
+        assert r.returncode == 0 and r.stdout.strip() == f"found {want} occurrences", (algo, r.stdout, r.stderr)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "test")), reason="oracle/_ref/test not built")
+def test_reference_harness_drives_our_executables(tmp_path, worker):
+    """The UNMODIFIED reference harness (src/test.c) runs its 20 cases against our executables."""
+    (tmp_path / "source").mkdir()
+    os.symlink(os.path.join(BIN, "algos"), tmp_path / "source" / "bin")
+    for a in ("bf", "kmp", "mp", "hor", "bm", "qs", "so", "sa", "kr", "tunedbm", "raita", "hash3", "hash8", "qf23", "qf63"):
+        r = run([os.path.join(REF, "test"), a], cwd=tmp_path, env=worker)
+        assert "Test passed" in r.stdout and r.returncode == 0, (a, r.stdout[-300:], r.stderr[-300:])
+    searches, uploads = stats(worker)
+    assert searches >= 15 * 10  # not-applicable cases never reach the worker
+    # and once without the worker: every search creates its own CUDA context
+    r = run([os.path.join(REF, "test"), "kmp"], cwd=tmp_path, env={**os.environ, "SMART_B200_NO_WORKER": "1"})
+    assert "Test passed" in r.stdout, (r.stdout[-300:], r.stderr[-300:])
+
+
+def test_our_harness_strict_on_our_executables(worker):
+    for a in ("bf", "kmp", "hor", "so"):
+        r = run([os.path.join(BIN, "test"), a, "-strict"], env=worker)
+        assert r.returncode == 0 and "20 cases, 0 skipped" in r.stdout, (a, r.stdout, r.stderr)
+
+
+def test_driver_keeps_text_resident_and_matches_reference(tmp_path):
+    data = tmp_path / "data" / "mini"
+    data.mkdir(parents=True)
+    text = open(os.path.join(ROOT, "tests", "golden", "bible64k.bin"), "rb").read()
+    (data / "a.txt").write_bytes(text)
+    (data / "index.txt").write_text("#a.txt#\n")
+    sock = str(tmp_path / "d.sock")
+    env = {**os.environ, "SMART_B200_SOCK": sock}
+    common = ["-text", "mini", "-data", str(tmp_path / "data"), "-results", str(tmp_path / "results"), "-pset", "6",
+              "-plen", "2", "32", "-short", "-occ", "-seed", "11"]
+    ours = run([os.path.join(BIN, "smart"), *common, "-algo", "bf,kmp,hor,so,hash3,qf23"], cwd=tmp_path, env=env)
+    assert ours.returncode == 0, ours.stderr
+    assert "Resident GPU worker started" in ours.stdout
+    assert ".[ERROR]" not in ours.stdout and ".[OUT]" not in ours.stdout
+    assert ours.stdout.count(".[--]") == 2  # hash3 and qf23 at m=2 (hash3.c:31, qf23.c:44)
+    occ = lambda s: re.findall(r"\] (\w+) \.+.*?occ (\d+)", s)
+    got = occ(ours.stdout)
+    assert len(got) == 16 * 6 - 2
+    if os.path.exists(os.path.join(REF, "bin", "bf")):
+        ref = run([os.path.join(BIN, "smart"), *common, "-algo", "bf,kmp,hor,so,hash3,qf23", "-bin",
+                   os.path.join(REF, "bin"), "-noworker"], cwd=tmp_path, env=env)
+        assert occ(ref.stdout) == got  # same seed, same patterns: identical occurrence columns
+    # the worker is stopped by the driver
+    r = run([os.path.join(BIN, "smartd"), "-stats"], env=env)
+    assert r.returncode != 0
+
+
+def test_worker_uploads_text_once_per_text(tmp_path, worker):
+    data = tmp_path / "data"
+    for name, blob in (("t1", b"abcabcabd" * 5000), ("t2", b"xyzxyzxyw" * 5000)):
+        (data / name).mkdir(parents=True)
+        (data / name / "f.txt").write_bytes(blob)
+        (data / name / "index.txt").write_text("#f.txt#\n")
+    r = run([os.path.join(BIN, "smart"), "-text", "t1-t2", "-data", str(data), "-pset", "5", "-plen", "4", "8",
+             "-algo", "bf,kmp", "-noworker", "-seed", "3"], cwd=tmp_path, env=worker)
+    assert r.returncode == 0 and r.stdout.count(".[OK]") == 2 * 2 * 2, r.stdout
+    searches, uploads = stats(worker)
+    assert searches == 2 * 2 * 2 * 5
+    assert uploads == 2  # one per text, although the shm key and n are identical for t1 and t2

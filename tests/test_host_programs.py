@@ -1,0 +1,135 @@
+"""The C host side (plugin shim, driver, harness, textgen) checked on the CPU by CROSS-DRIVING: our
+driver and our harness speak the reference's shm + argv protocol, so they can run the reference's own
+algorithm executables (oracle/_ref/bin, built from the unmodified sources).  GPU-side cross-driving (the
+reference's `test` binary driving OUR executables) lives in test_gpu_host.py."""
+import hashlib
+import os
+import re
+import subprocess
+
+import pytest
+
+import oracle_lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "bin")
+REFBIN = os.path.join(ROOT, "oracle", "_ref", "bin")
+
+needs_ref = pytest.mark.skipif(not os.path.exists(os.path.join(REFBIN, "bf")), reason="oracle/_ref/bin not built")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "smart_b200", "host")], check=True, capture_output=True)
+
+
+def run(cmd, **kw):
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=300, **kw)
+
+
+def test_all_plugin_executables_exist():
+    import smart_b200 as sb
+
+    for a in sb.ALGORITHMS:
+        assert os.access(os.path.join(BIN, "algos", a), os.X_OK), a
+    for p in ("smart", "test", "textgen", "smartd"):
+        assert os.access(os.path.join(BIN, p), os.X_OK), p
+
+
+def test_shim_argument_errors_match_reference_messages():
+    # main.h:48-51 and :124-127
+    r = run([os.path.join(BIN, "algos", "bf"), "shared", "1", "2"])
+    assert r.returncode == 1 and "five parameters needed when used with shared memory" in r.stdout
+    r = run([os.path.join(BIN, "algos", "bf"), "abc"])
+    assert r.returncode == 1 and "four parameters needed in standard mode" in r.stdout
+    # missing segments: shmget fails, exit 1 (main.h:60-63)
+    r = run([os.path.join(BIN, "algos", "bf"), "shared", "991", "3", "992", "10", "993", "994", "995"])
+    assert r.returncode == 1 and "shmget" in r.stderr
+
+
+def test_plugin_fails_loudly_without_gpu():
+    import smart_b200 as sb
+
+    if sb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    r = run([os.path.join(BIN, "algos", "kmp"), "aba", "3", "ababababab", "10"], env={**os.environ, "SMART_B200_NO_WORKER": "1"})
+    assert r.returncode != 0 and "found" not in r.stdout  # never a made-up count
+    # not-applicable is decided before any CUDA call, exactly like hash3.c:31
+    r = run([os.path.join(BIN, "algos", "hash3"), "ab", "2", "ababababab", "10"])
+    assert r.returncode == 0 and "found -1 occurrences" in r.stdout
+    r = run([os.path.join(BIN, "smartd"), "-fg"])
+    assert r.returncode != 0 and "no CUDA device" in r.stderr
+
+
+@needs_ref
+def test_our_harness_drives_reference_executables():
+    for a in ("bf", "kmp", "hor", "so", "bm", "hash3", "qf23", "raita"):
+        r = run([os.path.join(BIN, "test"), a, "-bin", REFBIN])
+        assert r.returncode == 0 and "Test passed" in r.stdout, (a, r.stdout, r.stderr)
+    # the harness must catch a wrong algorithm: sbndm2 is wrong on a^40 in a^64
+    if not os.path.exists(os.path.join(REFBIN, "sbndm2")):
+        subprocess.run(["gcc", "-O3", "-msse4", "-w", "-o", os.path.join(REFBIN, "sbndm2"),
+                        "/root/reference/src/algos/sbndm2.c", "-lm"], check=False)
+    if os.path.exists(os.path.join(REFBIN, "sbndm2")):
+        r = run([os.path.join(BIN, "test"), "sbndm2", "-bin", REFBIN])
+        assert r.returncode == 1 and "test failed on case n.16" in r.stdout
+    # -strict: raita answers -1 for m=1 (raita.c:38) so it is reported, not hidden
+    r = run([os.path.join(BIN, "test"), "raita", "-bin", REFBIN, "-strict"])
+    assert r.returncode == 1 and "returned -1" in r.stdout
+
+
+@needs_ref
+def test_our_driver_drives_reference_executables(tmp_path):
+    data = tmp_path / "data" / "mini"
+    data.mkdir(parents=True)
+    text = open(os.path.join(ROOT, "tests", "golden", "bible64k.bin"), "rb").read()
+    (data / "part1.txt").write_bytes(text[:30000])
+    (data / "part2.txt").write_bytes(text[30000:])
+    (data / "index.txt").write_text("#part1.txt#\n#part2.txt#\n")
+    r = run([os.path.join(BIN, "smart"), "-text", "mini", "-data", str(tmp_path / "data"), "-results",
+             str(tmp_path / "results"), "-pset", "3", "-plen", "2", "16", "-short", "-algo", "bf,kmp,hash3,raita",
+             "-bin", REFBIN, "-occ", "-pre", "-dif", "-std", "-txt", "-seed", "5", "-noworker"], cwd=tmp_path)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout
+    assert "Text buffer of dimension 65536 byte" in out
+    assert out.count("Searching for a set of 3 patterns with length") == 8  # m = 2,4,...,16
+    assert out.count(".[OK]") == 8 * 4 - 1  # hash3 is not applicable to m=2 -> [--] (hash3.c:31)
+    assert out.count(".[--]") == 1 and ".[ERROR]" not in out
+    # same seed -> same pattern sets -> same occurrence columns
+    r2 = run([os.path.join(BIN, "smart"), "-text", "mini", "-data", str(tmp_path / "data"), "-results",
+              str(tmp_path / "results"), "-pset", "3", "-plen", "2", "16", "-short", "-algo", "bf,kmp", "-bin", REFBIN,
+              "-occ", "-seed", "5", "-noworker"], cwd=tmp_path)
+    occ = lambda s: re.findall(r"\[\d/\d\] (\w+) .*occ (\d+)", s)
+    a, b = occ(out), occ(r2.stdout)
+    assert [v for k, v in a if k in ("BF", "KMP")] == [v for k, v in b]
+    assert all(v == w for (k, v), (k2, w) in zip(a[0::4], a[1::4]))  # BF and KMP agree
+    txt = list((tmp_path / "results").glob("EXP*/mini.txt"))
+    assert len(txt) == 1
+    rows = txt[0].read_text().splitlines()
+    assert [row.split()[0] for row in rows] == ["BF", "KMP", "HASH3", "RAITA"]
+    assert rows[2].split()[1] == "-"  # hash3 @ m=2: no result
+    # -simple mode (smart.c:496-507)
+    r = run([os.path.join(BIN, "smart"), "-simple", "aba", "ababababab", "-algo", "bf", "-bin", REFBIN, "-occ",
+             "-noworker"], cwd=tmp_path)
+    assert "occ 4" in r.stdout
+
+
+def test_driver_argument_errors():
+    r = run([os.path.join(BIN, "smart")])
+    assert "No parameter given" in r.stdout
+    r = run([os.path.join(BIN, "smart"), "-pset", "3"])
+    assert "No filename given" in r.stdout
+    r = run([os.path.join(BIN, "smart"), "-text", "x", "-simple", "a", "b"])
+    assert "Both parameters -simple and -text defined" in r.stdout
+    r = run([os.path.join(BIN, "smart"), "-bogus"])
+    assert "Error in input parameters" in r.stdout
+
+
+def test_textgen_reproduces_reference_files(tmp_path):
+    """md5 of SMART's rand2/rand4; -only keeps the rand() stream position."""
+    r = run([os.path.join(BIN, "textgen"), "-data", str(tmp_path), "-only", "4"])
+    assert r.returncode == 0
+    f = tmp_path / "rand4" / "rand4.txt"
+    assert hashlib.md5(f.read_bytes()).hexdigest() == "c371ad58eda30fa18f35a77b1e775ece"
+    assert (tmp_path / "rand4" / "index.txt").read_text().strip() == "#rand4.txt#"
+    assert not (tmp_path / "rand2").exists()
