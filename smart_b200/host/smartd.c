@@ -16,6 +16,7 @@
 #include "smart_b200.h"
 
 #include <errno.h>
+#include <fcntl.h>
 #include <signal.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -182,39 +183,65 @@ int main(int argc, char **argv)
     }
     char path[108];
     sb_socket_path(path, sizeof path);
-    if (sb_device_count() < 1) {
-        fprintf(stderr, "smartd: no CUDA device: %s\n", sb_last_error());
-        return 3;
-    }
-    int ls = listen_on(path);
-    if (ls < 0) {
-        perror("smartd: bind");
-        return 4;
-    }
+    /* Daemonise BEFORE the first CUDA call: a CUDA context does not survive fork().  The child reports
+     * "ok" or an error line to the parent through a pipe once it is listening. */
+    int report[2] = {-1, -1};
     if (!fg) {
+        if (pipe(report) != 0) return 5;
         pid_t pid = fork();
         if (pid < 0) return 5;
         if (pid > 0) {
-            printf("ready %s pid %d\n", path, (int)pid);
-            return 0;
+            char msg[256];
+            close(report[1]);
+            ssize_t k = read(report[0], msg, sizeof msg - 1);
+            msg[k > 0 ? k : 0] = 0;
+            if (k >= 2 && !strncmp(msg, "ok", 2)) {
+                printf("ready %s pid %d\n", path, (int)pid);
+                return 0;
+            }
+            fprintf(stderr, "smartd: %s\n", k > 0 ? msg : "worker died during start-up");
+            return 3;
         }
+        close(report[0]);
         setsid();
+        /* detach from the caller's stdio so that a capturing parent is not kept waiting */
+        int nul = open("/dev/null", O_RDWR);
+        if (nul >= 0) {
+            dup2(nul, 0);
+            dup2(nul, 1);
+            if (!getenv("SMART_B200_KEEP_STDERR")) dup2(nul, 2);
+            if (nul > 2) close(nul);
+        }
+    }
+#define FAIL_START(code, ...)                                  \
+    do {                                                       \
+        char m_[256];                                          \
+        snprintf(m_, sizeof m_, __VA_ARGS__);                  \
+        if (report[1] >= 0) {                                  \
+            if (write(report[1], m_, strlen(m_)) < 0) {}       \
+            close(report[1]);                                  \
+        } else                                                 \
+            fprintf(stderr, "smartd: %s\n", m_);               \
+        return code;                                           \
+    } while (0)
+    if (sb_device_count() < 1) FAIL_START(3, "no CUDA device: %s", sb_last_error());
+    /* create the CUDA context now, not inside the first timed search */
+    {
+        unsigned char dummy[64] = {0};
+        sb_text *w = sb_text_upload(dummy, sizeof dummy, NULL, 1);
+        if (!w) FAIL_START(6, "CUDA initialisation failed: %s", sb_last_error());
+        sb_text_free(w);
+    }
+    int ls = listen_on(path);
+    if (ls < 0) FAIL_START(4, "cannot bind %s: %s", path, strerror(errno));
+    if (report[1] >= 0) {
+        if (write(report[1], "ok", 2) < 0) {}
+        close(report[1]);
     } else {
         printf("ready %s pid %d\n", path, (int)getpid());
         fflush(stdout);
     }
     signal(SIGPIPE, SIG_IGN);
-    /* create the CUDA context now, not inside the first timed search */
-    {
-        unsigned char dummy[64] = {0};
-        sb_text *w = sb_text_upload(dummy, sizeof dummy, NULL, 1);
-        if (!w) {
-            fprintf(stderr, "smartd: CUDA initialisation failed: %s\n", sb_last_error());
-            unlink(path);
-            return 6;
-        }
-        sb_text_free(w);
-    }
     for (;;) {
         int fd = accept(ls, NULL, NULL);
         if (fd < 0) {

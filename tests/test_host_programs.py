@@ -57,8 +57,9 @@ def test_plugin_fails_loudly_without_gpu():
     # not-applicable is decided before any CUDA call, exactly like hash3.c:31
     r = run([os.path.join(BIN, "algos", "hash3"), "ab", "2", "ababababab", "10"])
     assert r.returncode == 0 and "found -1 occurrences" in r.stdout
-    r = run([os.path.join(BIN, "smartd"), "-fg"])
-    assert r.returncode != 0 and "no CUDA device" in r.stderr
+    for args in (["-fg"], []):
+        r = run([os.path.join(BIN, "smartd"), *args], env={**os.environ, "SMART_B200_SOCK": "/tmp/sb_test_nogpu.sock"})
+        assert r.returncode != 0 and "no CUDA device" in r.stderr
 
 
 @needs_ref
