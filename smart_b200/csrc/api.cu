@@ -67,7 +67,7 @@ struct DevCtx {                               // per-device scratch, created on 
     size_t pos_cap = 0;
     int occ_block[4] = {0, 0, 0, 0};          // resident CTAs/SM for scan_block<4,8,16,32>
     int occ_window[4] = {0, 0, 0, 0};         // ... for scan_window8<OFF=1..4>
-    int occ_short[2] = {0, 0};                // ... for scan_short<MASK>
+    int occ_short[6] = {0, 0, 0, 0, 0, 0};    // ... for scan_short<MODE, FULL>
     unsigned long long *d_hist = nullptr;     // 256-bin byte histogram scratch
     // host-buffer streaming path
     uint8_t *d_chunk[2] = {nullptr, nullptr};
@@ -125,8 +125,12 @@ DevCtx *get_ctx(int dev)
     c.occ_window[1] = occupancy(sb::scan_window8_kernel<2, kU>);
     c.occ_window[2] = occupancy(sb::scan_window8_kernel<3, kU>);
     c.occ_window[3] = occupancy(sb::scan_window8_kernel<4, kU>);
-    c.occ_short[0] = occupancy(sb::scan_short_kernel<false>);
-    c.occ_short[1] = occupancy(sb::scan_short_kernel<true>);
+    c.occ_short[0] = occupancy(sb::scan_short_kernel<0, false>);
+    c.occ_short[1] = occupancy(sb::scan_short_kernel<0, true>);
+    c.occ_short[2] = occupancy(sb::scan_short_kernel<1, false>);
+    c.occ_short[3] = occupancy(sb::scan_short_kernel<1, true>);
+    c.occ_short[4] = occupancy(sb::scan_short_kernel<2, false>);
+    c.occ_short[5] = occupancy(sb::scan_short_kernel<2, true>);
     c.ready = true;
     return &c;
 }
@@ -205,6 +209,7 @@ int choose_filter(int m, unsigned flags, double bits)
 
 struct Plan {
     int filter;
+    bool sparse;        // scan_short: a match of the whole pattern is rare in this text
     sb::ScanArgs args;  // text/base/hi/ngroups/counters/pos filled per shard
 };
 
@@ -212,6 +217,7 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
 {
     memset(&pl.args, 0, sizeof pl.args);
     pl.filter = choose_filter(m, flags, bits);
+    pl.sparse = m * bits >= 18.0 && !(flags & SB_FLAG_DENSE);
     sb::ScanArgs &a = pl.args;
     a.m = m;
     a.nwords = (m + 3) / 4;
@@ -242,7 +248,8 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
     if (pl.filter == kFilterShort) {
         group = kGroupShort;
         a.ngroups = ((unsigned long long)a.hi + group - 1) / group;
-        per_sm = c.occ_short[want_pos ? 1 : 0];
+        const int mode = pl.sparse ? 2 : (want_pos ? 1 : 0);
+        per_sm = c.occ_short[mode * 2 + (a.m == 4 ? 1 : 0)];
     } else if (pl.filter == kFilterWindow8) {
         group = kGroupLong;
         a.ngroups = ((unsigned long long)a.hi + group - 1) / group;
@@ -257,8 +264,14 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
     unsigned long long maxb = (unsigned long long)c.sms * per_sm;
     unsigned grid = (unsigned)std::max(1ull, std::min(want, maxb));
     if (pl.filter == kFilterShort) {
-        if (want_pos) sb::scan_short_kernel<true><<<grid, sb::kThreads, 0, stream>>>(a);
-        else sb::scan_short_kernel<false><<<grid, sb::kThreads, 0, stream>>>(a);
+        const int mode = pl.sparse ? 2 : (want_pos ? 1 : 0);
+        const bool full = a.m == 4;
+        if (mode == 0 && !full) sb::scan_short_kernel<0, false><<<grid, sb::kThreads, 0, stream>>>(a);
+        else if (mode == 0) sb::scan_short_kernel<0, true><<<grid, sb::kThreads, 0, stream>>>(a);
+        else if (mode == 1 && !full) sb::scan_short_kernel<1, false><<<grid, sb::kThreads, 0, stream>>>(a);
+        else if (mode == 1) sb::scan_short_kernel<1, true><<<grid, sb::kThreads, 0, stream>>>(a);
+        else if (!full) sb::scan_short_kernel<2, false><<<grid, sb::kThreads, 0, stream>>>(a);
+        else sb::scan_short_kernel<2, true><<<grid, sb::kThreads, 0, stream>>>(a);
     } else if (pl.filter == kFilterWindow8) {
         const int off = a.anchor;
         a.anchor = 0;

@@ -275,24 +275,16 @@ __global__ void __launch_bounds__(kThreads) scan_block_kernel(const __grid_const
 
 /* ===================================================================== scan_window8<OFF, U> */
 
-/* Per-lane slow path of scan_window8: W[0..9] are the lane's 32 bytes plus the next 8; re-test every
- * start position exactly (both window words), then verify the rest of the pattern. */
-template <int OFF>
-__device__ __noinline__ uint2 window8_candidates(const ScanArgs &a, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
-                                                 uint32_t w4, uint32_t w5, uint32_t w6, uint32_t w7, uint32_t w8,
-                                                 uint32_t w9, long long voff)
+/* Per-lane slow path of scan_window8: `mm` has bit p set for every start position p of this lane's
+ * 32-byte vector whose two window words match exactly; verify the rest of the pattern (m > 8) and count. */
+__device__ __noinline__ uint2 window8_matches(const ScanArgs &a, unsigned mm, long long voff)
 {
-    const uint32_t W[10] = {w0, w1, w2, w3, w4, w5, w6, w7, w8, w9};  // by value, see block_candidates
     unsigned cnt = 0, nver = 0;
-#pragma unroll 1
-    for (int p = 0; p < 32; p++) {
+    while (mm) {
+        const int p = __ffs(mm) - 1;
+        mm &= mm - 1;
         const long long j = voff + p;
         if (j >= a.hi) break;
-        const int q = p >> 2, r = (p & 3) * 8;
-        const int p2 = p + OFF, q2 = p2 >> 2, r2 = (p2 & 3) * 8;
-        const uint32_t lo = __funnelshift_r(W[q], W[q + 1], r);
-        const uint32_t hi = __funnelshift_r(W[q2], q2 + 1 < 10 ? W[q2 + 1] : 0u, r2);
-        if (lo != a.X0 || hi != a.X1) continue;
         if (a.m > 8) {
             nver++;
             if (!lane_verify(a, j, 2)) continue;
@@ -345,11 +337,16 @@ __global__ void __launch_bounds__(kThreads) scan_window8_kernel(const __grid_con
             bool hit = false;
 #pragma unroll
             for (int b = 0; b < 32; b++) hit |= (fp8(S[b], S[b + OFF]) == a.G);
-            if (hit) {
-                const long long voff = (long long)(g * (U * 1024ull)) + c * 1024 + lane * 32;
-                const uint2 r = window8_candidates<OFF>(a, W[0], W[1], W[2], W[3], W[4], W[5], W[6], W[7], W[8], W[9], voff);
-                cnt += r.x;
-                nver += r.y;
+            if (hit) {  // per lane: which positions match both words exactly (the hash can collide)
+                unsigned mm = 0;
+#pragma unroll
+                for (int b = 0; b < 32; b++) mm |= ((S[b] == a.X0 && S[b + OFF] == a.X1) ? 1u : 0u) << b;
+                if (mm) {
+                    const long long voff = (long long)(g * (U * 1024ull)) + c * 1024 + lane * 32;
+                    const uint2 r = window8_matches(a, mm, voff);
+                    cnt += r.x;
+                    nver += r.y;
+                }
             }
         }
     }
@@ -374,8 +371,12 @@ __device__ __noinline__ unsigned short_candidates(const ScanArgs &a, unsigned mm
     return cnt;
 }
 
-/* MASK: collect a per-position mask and post-process (position output). 128-bit loads, 4 in flight. */
-template <bool MASK>
+/* MODE 0: dense  - count every position in registers (no position output);
+ * MODE 1: dense  - collect a per-position mask and post-process (position output);
+ * MODE 2: sparse - OR-reduce the compares (one ISETP.EQ.OR per position) and only build the mask when some
+ *                  position of the vector matched: for texts where a match of m bytes is rare (m*bits >= 18).
+ * FULL: m == 4, the mask M0 is all ones and is dropped.  128-bit loads, 4 in flight. */
+template <int MODE, bool FULL>
 __global__ void __launch_bounds__(kThreads) scan_short_kernel(const __grid_constant__ ScanArgs a)
 {
     constexpr int U = 4;
@@ -400,21 +401,28 @@ __global__ void __launch_bounds__(kThreads) scan_short_kernel(const __grid_const
                 sx = lane == 0 ? gn : v[c].x;
             const uint32_t nx = __shfl_sync(kFull, sx, (lane + 1) & 31);
             const uint32_t W[5] = {v[c].x, v[c].y, v[c].z, v[c].w, nx};
+            uint32_t S[16];
+#pragma unroll
+            for (int b = 0; b < 16; b++) {
+                const uint32_t lo = (b & 3) ? __funnelshift_r(W[b >> 2], W[(b >> 2) + 1], 8 * (b & 3)) : W[b >> 2];
+                S[b] = FULL ? lo : (lo & a.M0);
+            }
             const long long voff = (long long)(g * (U * 512ull)) + c * 512 + lane * 16;
-            if (!MASK && voff + 16 <= a.hi) {
+            if (MODE == 0 && voff + 16 <= a.hi) {
 #pragma unroll
-                for (int b = 0; b < 16; b++) {
-                    const uint32_t lo = (b & 3) ? __funnelshift_r(W[b >> 2], W[(b >> 2) + 1], 8 * (b & 3)) : W[b >> 2];
-                    cnt += (((lo & a.M0) ^ a.X0) == 0);
-                }
+                for (int b = 0; b < 16; b++) cnt += (S[b] == a.X0);
             } else if (voff < a.hi) {
-                unsigned mm = 0;
+                bool any = (MODE != 2);
+                if (MODE == 2) {
 #pragma unroll
-                for (int b = 0; b < 16; b++) {
-                    const uint32_t lo = (b & 3) ? __funnelshift_r(W[b >> 2], W[(b >> 2) + 1], 8 * (b & 3)) : W[b >> 2];
-                    mm |= ((((lo & a.M0) ^ a.X0) == 0) ? 1u : 0u) << b;
+                    for (int b = 0; b < 16; b++) any |= (S[b] == a.X0);
                 }
-                if (mm) cnt += short_candidates(a, mm, voff);
+                if (any) {
+                    unsigned mm = 0;
+#pragma unroll
+                    for (int b = 0; b < 16; b++) mm |= ((S[b] == a.X0) ? 1u : 0u) << b;
+                    if (mm) cnt += short_candidates(a, mm, voff);
+                }
             }
         }
     }

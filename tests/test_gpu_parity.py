@@ -91,6 +91,10 @@ def test_every_filter_width_gives_the_same_count(oracle, golden, tname):
                     r = sb.search(a, t, x, flags=FILTERS[f])
                     assert sb.last_timing().filter_kind == f
                     assert r.count == want, (tname, c["m"], c["pi"], a, f)
+            if c["m"] <= 4:  # scan_short: dense (count every position) and sparse (OR-reduce) modes agree
+                assert sb.search("bf", t, x, flags=sb.FLAG_DENSE).count == want
+                r = sb.search("bf", t, x, flags=sb.FLAG_DENSE | sb.FLAG_POSITIONS, positions_cap=y.size)
+                assert r.count == want and np.array_equal(r.positions, oracle.bf_positions(x, y))
 
 
 @pytest.mark.parametrize("tname", ["bible64k", "rand2", "gen256", "aab16k", "a16k"])
