@@ -17,7 +17,8 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "lib", "libsmartb200.so")
+# SMART_B200_LIB selects an alternative in-tree build (tuning variants made by tools/build_variants.sh)
+_LIB_PATH = os.environ.get("SMART_B200_LIB") or os.path.join(_HERE, "lib", "libsmartb200.so")
 
 XSIZE = 4200
 NOT_APPLICABLE = -1

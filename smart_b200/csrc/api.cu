@@ -48,7 +48,10 @@ constexpr size_t kHalo = SB_XSIZE - 1;        // right halo kept with every shar
 constexpr size_t kShardAlign = 4096;          // shard bases are multiples of this
 constexpr int kMaxShards = 16;
 constexpr size_t kPatBytes = 4352;            // device pattern buffer (>= SB_XSIZE + 8, multiple of 256)
-constexpr int kU = 2;                         // 256-bit loads in flight per thread (scan_block / scan_window8)
+#ifndef SB_U
+#define SB_U 4
+#endif
+constexpr int kU = SB_U;                      // 256-bit loads in flight per thread (scan_block / scan_window8)
 constexpr size_t kGroupLong = kU * 1024;      // bytes per warp iteration of those kernels
 constexpr size_t kGroupShort = 4 * 512;       // ... of scan_short
 constexpr int kFilterShort = 0, kFilterWindow8 = 1;

@@ -31,6 +31,9 @@
 namespace sb {
 
 constexpr int kThreads = 256;       // threads per CTA
+#ifndef SB_MINB
+#define SB_MINB 1                   // __launch_bounds__ min CTAs/SM for the streaming kernels (tuning knob)
+#endif
 constexpr int kPadBytes = 8192;     // every text buffer is zero padded to a multiple of this plus this much
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -246,7 +249,7 @@ __device__ __forceinline__ bool block_hit(const ScanArgs &a, const V8 &v)
 
 /* group = U x 1 KiB per warp */
 template <int B, int U>
-__global__ void __launch_bounds__(kThreads) scan_block_kernel(const __grid_constant__ ScanArgs a)
+__global__ void __launch_bounds__(kThreads, SB_MINB) scan_block_kernel(const __grid_constant__ ScanArgs a)
 {
     const unsigned lane = threadIdx.x & 31;
     const unsigned long long warp = ((unsigned long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
@@ -298,7 +301,7 @@ __device__ __noinline__ uint2 window8_matches(const ScanArgs &a, unsigned mm, lo
 /* 8-byte window fingerprint at every start position: window = bytes [p, p+4) and [p+OFF, p+OFF+4),
  * OFF = 4 for m >= 8 and m-4 for 5 <= m <= 7 (the two words overlap and cover exactly m bytes). */
 template <int OFF, int U>
-__global__ void __launch_bounds__(kThreads) scan_window8_kernel(const __grid_constant__ ScanArgs a)
+__global__ void __launch_bounds__(kThreads, SB_MINB) scan_window8_kernel(const __grid_constant__ ScanArgs a)
 {
     const unsigned lane = threadIdx.x & 31;
     const unsigned long long warp = ((unsigned long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
