@@ -38,7 +38,8 @@ METRIC = "text GB/s scanned (HBM-resident)"
 UNIT = "GB/s"
 SEED = 20261018
 FILTER_NAMES = {0: "scan_short_kernel", 1: "scan_window8_kernel", 4: "scan_block_kernel<4>",
-                8: "scan_block_kernel<8>", 16: "scan_block_kernel<16>", 32: "scan_block_kernel<32>"}
+                8: "scan_block_kernel<8>", 16: "scan_block_kernel<16>", 32: "scan_block_kernel<32>",
+                108: "scan_skip_kernel<8>", 116: "scan_skip_kernel<16>", 132: "scan_skip_kernel<32>"}
 
 
 def parse_args():
@@ -337,7 +338,10 @@ def main_ours(args, algos, ms):
 
     # ---- roofline of the dominant kernel (largest share of device time inside the timed region)
     peak, peak_src = measured_peak()
-    dom = max(kernel_ms.items(), key=lambda kv: kv[1][0])
+    # the sub-linear scan_skip kernels read 32 of every `stride` bytes, so n/t is not bounded by the
+    # read-once roofline; the roofline object describes the dominant READ-EVERY-BYTE kernel
+    linear = {f: v for f, v in kernel_ms.items() if f < 100} or kernel_ms
+    dom = max(linear.items(), key=lambda kv: kv[1][0])
     dom_name = FILTER_NAMES.get(dom[0], str(dom[0]))
     avg_ms = dom[1][0] / max(1, dom[1][1])
     achieved = own / (avg_ms * 1e-3) / 1e9
@@ -347,8 +351,11 @@ def main_ours(args, algos, ms):
                 "algorithmic_bytes_per_launch": own, "avg_launch_ms": avg_ms,
                 "share_of_step_device_time": dom[1][0] / max(kernel_total, 1e-9),
                 "kernels": {FILTER_NAMES.get(f, str(f)): {"launches": v[1], "avg_ms": v[0] / max(1, v[1]),
-                                                          "GBps": own / (v[0] / max(1, v[1]) * 1e-3) / 1e9}
-                            for f, v in kernel_ms.items()}}
+                                                          "GBps": own / (v[0] / max(1, v[1]) * 1e-3) / 1e9,
+                                                          "sublinear": f >= 100}
+                            for f, v in kernel_ms.items()},
+                "note": "scan_skip kernels sample one 32-byte sector per stride (stride ~ m-7): their text GB/s "
+                        "may exceed the read-once peak; see profiles/ for their DRAM traffic"}
 
     # ---- e2e: the same searches through the host-buffer entry (legacy plugin path), H2D inside the timer
     e2e = None

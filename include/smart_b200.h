@@ -50,7 +50,8 @@ extern "C" {
 
 /* flags for sb_search64 */
 #define SB_FLAG_POSITIONS 0x1u    /* fill `positions` (sorted ascending, global offsets) */
-#define SB_FLAG_NO_SKIP 0x2u      /* force the read-every-byte kernels even for skip-family algorithms */
+#define SB_FLAG_NO_SKIP 0x2u      /* force the read-every-byte kernels even for skip-family algorithms (the
+                                     sub-linear scan_skip kernel is their default for m >= 71) */
 #define SB_FLAG_DENSE 0x4u        /* tuning override: m <= 4, count every position even if matches look rare */
 #define SB_FLAG_FILTER_SHIFT 0x10u  /* tuning override: force the per-position 8-byte window kernel (m >= 5) */
 #define SB_FLAG_FILTER_B4 0x20u     /* tuning override: aligned-block fingerprint width 4 */
@@ -121,7 +122,7 @@ typedef struct sb_timing {
     double kernel_ms;      /* max over shards of the CUDA-event time of the scan kernel(s) */
     double wall_ms;        /* host wall clock, first launch -> last count on host */
     int kernels_launched;  /* scan kernels launched by the last search (all shards) */
-    int filter_kind;       /* 0 = scan_short, 1 = scan_window8, 4/8/16/32 = scan_block<B> */
+    int filter_kind;       /* 0 = scan_short, 1 = scan_window8, 4/8/16/32 = scan_block<B>, 108/116/132 = scan_skip<G> */
     unsigned long long verified; /* candidates sent to exact verification (all shards) */
 } sb_timing;
 void sb_last_timing(sb_timing *out);

@@ -55,6 +55,8 @@ constexpr int kU = SB_U;                      // 256-bit loads in flight per thr
 constexpr size_t kGroupLong = kU * 1024;      // bytes per warp iteration of those kernels
 constexpr size_t kGroupShort = 4 * 512;       // ... of scan_short
 constexpr int kFilterShort = 0, kFilterWindow8 = 1;
+constexpr int kFilterSkip = 100;              // + gram bytes (108, 116, 132): scan_skip<G>
+constexpr size_t kAuxWords = sb::kBloomWords + 2 * sb::kSkipTableSize;
 
 struct DevCtx {                               // per-device scratch, created on first use
     bool ready = false;
@@ -72,6 +74,8 @@ struct DevCtx {                               // per-device scratch, created on 
     int occ_window[4] = {0, 0, 0, 0};         // ... for scan_window8<OFF=1..4>
     int occ_short[6] = {0, 0, 0, 0, 0, 0};    // ... for scan_short<MODE, FULL>
     unsigned long long *d_hist = nullptr;     // 256-bin byte histogram scratch
+    uint32_t *d_aux = nullptr, *h_aux = nullptr; // scan_skip: Bloom bitmap + gram fingerprint list
+    int occ_skip[3] = {0, 0, 0};              // resident CTAs/SM for scan_skip<8,16,32>
     // host-buffer streaming path
     uint8_t *d_chunk[2] = {nullptr, nullptr};
     size_t chunk_cap = 0;
@@ -110,6 +114,8 @@ DevCtx *get_ctx(int dev)
     }
     c.dev = dev;
     c.sms = prop.multiProcessorCount;
+    if (const char *e = getenv("SMART_B200_L2_FETCH"))  // tuning: DRAM->L2 fetch granularity hint (32/64/128)
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
     CU_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), nullptr);
     CU_TRY(cudaStreamCreateWithFlags(&c.cstream[0], cudaStreamNonBlocking), nullptr);
     CU_TRY(cudaStreamCreateWithFlags(&c.cstream[1], cudaStreamNonBlocking), nullptr);
@@ -120,6 +126,11 @@ DevCtx *get_ctx(int dev)
     CU_TRY(cudaHostAlloc(&c.h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault), nullptr);
     CU_TRY(cudaHostAlloc(&c.h_pat, kPatBytes, cudaHostAllocDefault), nullptr);
     CU_TRY(cudaMalloc(&c.d_hist, 256 * sizeof(unsigned long long)), nullptr);
+    CU_TRY(cudaMalloc(&c.d_aux, kAuxWords * sizeof(uint32_t)), nullptr);
+    CU_TRY(cudaHostAlloc(&c.h_aux, kAuxWords * sizeof(uint32_t), cudaHostAllocDefault), nullptr);
+    c.occ_skip[0] = occupancy(sb::scan_skip_kernel<8>);
+    c.occ_skip[1] = occupancy(sb::scan_skip_kernel<16>);
+    c.occ_skip[2] = occupancy(sb::scan_skip_kernel<32>);
     c.occ_block[0] = occupancy(sb::scan_block_kernel<4, kU>);
     c.occ_block[1] = occupancy(sb::scan_block_kernel<8, kU>);
     c.occ_block[2] = occupancy(sb::scan_block_kernel<16, kU>);
@@ -210,8 +221,25 @@ int choose_filter(int m, unsigned flags, double bits)
     return kFilterWindow8;
 }
 
+/* Smallest sampling stride for which skipping sectors beats streaming: measured on B200, sampling one
+ * sector in 2 or 4 (stride 64/128) is no faster than reading everything (DRAM delivers 64 bytes per
+ * sampled sector even with the L2::64B hint, 128 without), from stride 160 on it wins (8.5 vs 7.1 TB/s).
+ * SMART_B200_SKIP_MIN_STRIDE overrides (tuning). */
+int skip_min_stride()
+{
+    static int v = 0;
+    if (!v) {
+        const char *e = getenv("SMART_B200_SKIP_MIN_STRIDE");
+        v = e ? atoi(e) : 160;
+        if (v < 32) v = 32;
+    }
+    return v;
+}
+
 struct Plan {
     int filter;
+    int skip_grams;     // scan_skip: entries of the fingerprint list (= stride), 0 otherwise
+    uint32_t list[4224]; // scan_skip: fingerprints of the pattern grams
     bool sparse;        // scan_short: a match of the whole pattern is rare in this text
     sb::ScanArgs args;  // text/base/hi/ngroups/counters/pos filled per shard
 };
@@ -221,10 +249,28 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
     memset(&pl.args, 0, sizeof pl.args);
     pl.filter = choose_filter(m, flags, bits);
     pl.sparse = m * bits >= 18.0 && !(flags & SB_FLAG_DENSE);
+    pl.skip_grams = 0;
     sb::ScanArgs &a = pl.args;
     a.m = m;
     a.nwords = (m + 3) / 4;
     a.tailmask = (m & 3) ? ((1u << (8 * (m & 3))) - 1u) : 0xffffffffu;
+    /* Sub-linear sampling for the skip families: one G-byte gram every `stride` bytes (a multiple of the
+     * 32-byte DRAM sector), G wide enough that a text gram rarely equals one of `stride` pattern grams. */
+    const unsigned forced = SB_FLAG_FILTER_SHIFT | SB_FLAG_FILTER_B4 | SB_FLAG_FILTER_B8 | SB_FLAG_FILTER_B16 |
+                            SB_FLAG_FILTER_B32 | SB_FLAG_NO_SKIP;
+    if (desc->anchor == SB_ANCHOR_SUFFIX && !(flags & forced)) {
+        for (int G = 8; G <= 32; G *= 2) {
+            const int stride = ((m - (G - 1)) / 32) * 32;
+            if (stride < skip_min_stride()) break;
+            if (G * bits < 14.0 + log2((double)stride)) continue;  // P(sampled gram is a pattern gram) <= ~1e-4
+            pl.filter = kFilterSkip + G;
+            pl.skip_grams = stride;
+            a.stride = stride;
+            a.anchor = m - (stride + G - 1);
+            for (int d = 0; d < stride; d++) pl.list[d] = fingerprint(x + a.anchor + d, G);
+            return;
+        }
+    }
     if (pl.filter == kFilterShort) {
         a.M0 = m == 4 ? 0xffffffffu : ((1u << (8 * m)) - 1u);
         a.X0 = load_le32(x, m) & a.M0;
@@ -248,6 +294,19 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
     int per_sm;
     size_t group;
     const bool want_pos = a.pos != nullptr;
+    if (pl.filter >= kFilterSkip) {
+        const int G = pl.filter - kFilterSkip;
+        a.aux = c.d_aux;
+        a.nsamples = ((unsigned long long)a.hi + a.anchor + a.stride - 2) / a.stride + 1;
+        const unsigned long long per_cta = 32ull * 8 * (sb::kThreads / 32);
+        const unsigned long long want_ctas = (a.nsamples + per_cta - 1) / per_cta;
+        const int occ = c.occ_skip[G == 8 ? 0 : G == 16 ? 1 : 2];
+        const unsigned g = (unsigned)std::max(1ull, std::min(want_ctas, (unsigned long long)c.sms * occ));
+        if (G == 8) sb::scan_skip_kernel<8><<<g, sb::kThreads, 0, stream>>>(a);
+        else if (G == 16) sb::scan_skip_kernel<16><<<g, sb::kThreads, 0, stream>>>(a);
+        else sb::scan_skip_kernel<32><<<g, sb::kThreads, 0, stream>>>(a);
+        return cudaGetLastError();
+    }
     if (pl.filter == kFilterShort) {
         group = kGroupShort;
         a.ngroups = ((unsigned long long)a.hi + group - 1) / group;
@@ -294,6 +353,24 @@ void stage_pattern(DevCtx &c, const unsigned char *x, int m)
 {
     memset(c.h_pat, 0, kPatBytes);
     memcpy(c.h_pat, x, (size_t)m);
+}
+
+/* Bloom bitmap + fingerprint list of a skip plan, staged in pinned memory; returns the bytes to upload */
+size_t stage_aux(DevCtx &c, const Plan &pl)
+{
+    if (!pl.skip_grams) return 0;
+    memset(c.h_aux, 0, kAuxWords * sizeof(uint32_t));
+    uint32_t *table = c.h_aux + sb::kBloomWords;
+    for (int d = 0; d < pl.skip_grams; d++) {
+        const uint32_t s1 = sb::bloom_slot(pl.list[d]), s2 = sb::bloom_slot2(pl.list[d]);
+        c.h_aux[s1 >> 5] |= 1u << (s1 & 31);
+        c.h_aux[s2 >> 5] |= 1u << (s2 & 31);
+        uint32_t slot = sb::table_slot(pl.list[d]);
+        while (table[2 * slot + 1]) slot = (slot + 1) & (sb::kSkipTableSize - 1);  // linear probing
+        table[2 * slot] = pl.list[d];
+        table[2 * slot + 1] = (uint32_t)d + 1;
+    }
+    return kAuxWords * sizeof(uint32_t);
 }
 
 sb_tables *tables_scratch()
@@ -617,6 +694,9 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
         CU_TRY(cudaMemcpyAsync(ctx[g]->d_pat, ctx[g]->h_pat, round_up((size_t)m + 8, 16), cudaMemcpyHostToDevice,
                                ctx[g]->stream),
                SB_ERR_CUDA);
+        if (const size_t aux_bytes = stage_aux(*ctx[g], pl))
+            CU_TRY(cudaMemcpyAsync(ctx[g]->d_aux, ctx[g]->h_aux, aux_bytes, cudaMemcpyHostToDevice, ctx[g]->stream),
+                   SB_ERR_CUDA);
         CU_TRY(cudaMemsetAsync(ctx[g]->d_counters, 0, 4 * sizeof(unsigned long long), ctx[g]->stream), SB_ERR_CUDA);
     }
     for (int g = 0; g < t->nshards; g++) {
@@ -775,6 +855,8 @@ long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned
     stage_pattern(*c, x, m);
     CU_TRY(cudaMemcpyAsync(c->d_pat, c->h_pat, round_up((size_t)m + 8, 16), cudaMemcpyHostToDevice, c->stream),
            SB_ERR_CUDA);
+    if (const size_t aux_bytes = stage_aux(*c, pl))
+        CU_TRY(cudaMemcpyAsync(c->d_aux, c->h_aux, aux_bytes, cudaMemcpyHostToDevice, c->stream), SB_ERR_CUDA);
     CU_TRY(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream), SB_ERR_CUDA);
     CU_TRY(cudaStreamSynchronize(c->stream), SB_ERR_CUDA);
     const double t2 = now_ms();

@@ -65,16 +65,33 @@ struct ScanArgs {
     uint32_t H[32];               // scan_block: fingerprints of x[a+d .. a+d+B), d < B
     uint32_t X0, X1, M0;          // scan_short: masked first word; scan_window8: the two window words
     uint32_t G;                   // scan_window8: fp8(X0, X1)
+    // scan_skip: one G-byte gram is sampled every `stride` bytes; aux = Bloom bitmap (kBloomWords words)
+    // followed by an open-addressing table {fingerprint of x[anchor+d .. anchor+d+G), d+1}, d < stride
+    const uint32_t *aux;
+    unsigned long long nsamples;
+    int stride;
 };
+
+constexpr int kBloomBits = 18;                       // 2^18-bit Bloom bitmap = 32 KiB of shared memory, 2 probes
+constexpr int kBloomWords = (1 << kBloomBits) / 32;
+__host__ __device__ __forceinline__ uint32_t bloom_slot(uint32_t h) { return (h * 0x2545F491u) >> (32 - kBloomBits); }
+__host__ __device__ __forceinline__ uint32_t bloom_slot2(uint32_t h) { return (h * 0x9FB21C65u + 0x7F4A7C15u) >> (32 - kBloomBits); }
+// exact second level: open-addressing table {fingerprint, d+1} (linear probing, 0 = empty) after the bitmap
+constexpr int kSkipTableBits = 13;
+constexpr int kSkipTableSize = 1 << kSkipTableBits;   // 8192 entries >= 2 x 4193 grams
+__host__ __device__ __forceinline__ uint32_t table_slot(uint32_t h) { return (h * 0xB5297A4Du) >> (32 - kSkipTableBits); }
 
 struct V8 {
     uint32_t w[8];
 };
 
+#ifndef SB_STREAM_L2
+#define SB_STREAM_L2 "" /* optional L2 prefetch-size hint for the streaming loads (tuning) */
+#endif
 __device__ __forceinline__ V8 ldg_stream256(const uint8_t *p)
 {
     V8 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc.L1::no_allocate" SB_STREAM_L2 ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
                    "=r"(r.w[7])
                  : "l"(p));
@@ -350,6 +367,113 @@ __global__ void __launch_bounds__(kThreads, SB_MINB) scan_window8_kernel(const _
                     cnt += r.x;
                     nver += r.y;
                 }
+            }
+        }
+    }
+    block_reduce_count(a, cnt, nver);
+}
+
+
+/* ===================================================================== scan_skip<G> */
+
+/* Sub-linear scan for the skip families (BM, Horspool, QS, Raita, Tuned-BM, HASHq, QF are sub-linear on the
+ * CPU for the same reason): every occurrence [j, j+m) contains the G-byte gram at the first multiple t of
+ * `stride` with t >= j + anchor, provided stride + G - 1 <= m - anchor.  So only ONE 32-byte sector out of
+ * every stride/32 is read.  The gram's fingerprint is looked up in a Bloom bitmap of the `stride` pattern
+ * grams it could be (shared memory); a hit is resolved against the fingerprint list and verified exactly.
+ * Text GB/s (n / t) can therefore exceed the read-once HBM roofline.  Measured (ncu, profiles/): DRAM
+ * delivers 128 bytes per sampled sector, so the traffic is ~n*128/stride and skipping pays from stride 192. */
+#ifndef SB_SKIP_L2
+#define SB_SKIP_L2 ".L2::64B" /* smallest L2 prefetch-size hint PTX offers: the sampled sectors are isolated */
+#endif
+template <int G>
+__device__ __forceinline__ uint32_t skip_fp(const uint8_t *p)
+{
+    if (G == 8) {
+        uint2 v;
+        asm volatile("ld.global.nc.L1::no_allocate" SB_SKIP_L2 ".v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+        return fp8(v.x, v.y);
+    } else if (G == 16) {
+        uint4 v;
+        asm volatile("ld.global.nc.L1::no_allocate" SB_SKIP_L2 ".v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(p));
+        return fp16(v.x, v.y, v.z, v.w);
+    } else {
+        V8 v;
+        asm volatile("ld.global.nc.L1::no_allocate" SB_SKIP_L2 ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]), "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]),
+                       "=r"(v.w[7])
+                     : "l"(p));
+        return fp32(fp16(v.w[0], v.w[1], v.w[2], v.w[3]), fp16(v.w[4], v.w[5], v.w[6], v.w[7]));
+    }
+}
+
+__device__ __noinline__ uint2 skip_candidates(const ScanArgs &a, uint32_t h, long long t, bool hit, unsigned lane)
+{
+    unsigned cnt = 0, nver = 0;
+    const uint2 *table = reinterpret_cast<const uint2 *>(a.aux + kBloomWords);
+    unsigned pending = __ballot_sync(kFull, hit);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const uint32_t sh = __shfl_sync(kFull, h, src);
+        const long long st = __shfl_sync(kFull, t, src);
+        // 32 consecutive table entries per round; the probe chain ends at the first empty entry
+        const uint32_t base = table_slot(sh);
+        for (int round = 0; round < kSkipTableSize / 32; round++) {
+            const uint2 e = __ldg(table + ((base + round * 32 + lane) & (kSkipTableSize - 1)));
+            const unsigned empty = __ballot_sync(kFull, e.y == 0);
+            unsigned eq = __ballot_sync(kFull, e.y != 0 && e.x == sh);
+            if (empty) eq &= (1u << (__ffs(empty) - 1)) - 1u;
+            while (eq) {
+                const int l = __ffs(eq) - 1;
+                eq &= eq - 1;
+                const int d = (int)__shfl_sync(kFull, e.y, l) - 1;
+                const long long j = st - d - a.anchor;
+                if (j >= 0 && j < a.hi) {
+                    nver += (lane == 0);
+                    if (warp_verify(a, j, lane) && lane == 0) {
+                        cnt++;
+                        emit_match(a, j);
+                    }
+                }
+            }
+            if (empty) break;
+        }
+    }
+    return make_uint2(cnt, nver);
+}
+
+template <int G>
+__global__ void __launch_bounds__(kThreads) scan_skip_kernel(const __grid_constant__ ScanArgs a)
+{
+    constexpr int U = 8;  // independent sector loads in flight per thread
+    __shared__ uint32_t bloom[kBloomWords];
+    for (int i = threadIdx.x; i < kBloomWords; i += kThreads) bloom[i] = __ldg(a.aux + i);
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long warp = ((unsigned long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * kThreads) >> 5;
+    const unsigned long long stride = (unsigned long long)a.stride;
+    unsigned cnt = 0, nver = 0;
+
+    for (unsigned long long k0 = warp * (32 * U); k0 < a.nsamples; k0 += nwarps * (32 * U)) {
+        uint32_t h[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const unsigned long long k = k0 + u * 32 + lane;  // samples past the end read zero padding
+            h[u] = skip_fp<G>(a.text + (k < a.nsamples ? k : a.nsamples - 1) * stride);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const unsigned long long k = k0 + u * 32 + lane;
+            const uint32_t s1 = bloom_slot(h[u]), s2 = bloom_slot2(h[u]);
+            const bool hit = ((bloom[s1 >> 5] >> (s1 & 31)) & (bloom[s2 >> 5] >> (s2 & 31)) & 1u) && k < a.nsamples;
+            if (__any_sync(kFull, hit)) {
+                const uint2 r = skip_candidates(a, h[u], (long long)(k * stride), hit, lane);
+                cnt += r.x;
+                nver += r.y;
             }
         }
     }

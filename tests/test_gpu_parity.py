@@ -172,6 +172,8 @@ def test_sharded_counts_equal_unsharded(oracle):
             assert want >= 1
             for t in (t1, t2, t8):
                 assert sb.search("bf", t, x).count == want, (m, t.shards)
+                assert sb.search("hor", t, x).count == want, (m, t.shards)  # sub-linear kernel for m >= 71
+                assert sb.search("hor", t, x, flags=sb.FLAG_NO_SKIP).count == want
         # per-part handles (one process per GPU) sum to the whole
         x = y[12345:12345 + 24].copy()
         want = oracle.bf_count(x, y)
@@ -180,6 +182,35 @@ def test_sharded_counts_equal_unsharded(oracle):
             with sb.Text.upload_part(y, 4, g) as part:
                 total += sb.search("kmp", part, x).count
         assert total == want
+
+
+def test_skip_kernel_is_selected_and_exact(oracle):
+    """The skip families use the sub-linear sampled-gram kernel for m >= 71 (filter_kind 100+G); the gram
+    width follows the text's entropy; counts and positions equal the oracle's."""
+    for sigma, kinds in ((256, {108}), (4, {116, 132}), (2, {132})):
+        y = sb.textgen_host(0, 6_000_000, sigma, 5)
+        with sb.Text.upload(y) as t:
+            for m in (71, 100, 199, 230, 256, 1000, 4200):
+                x = y[3_000_000 - m : 3_000_000].copy()
+                want = oracle.bf_positions(x, y)
+                for a in ("hor", "bm", "qs", "hash3", "qf23", "tunedbm", "raita"):
+                    r = sb.search(a, t, x, flags=sb.FLAG_POSITIONS, positions_cap=1 << 20)
+                    k = sb.last_timing().filter_kind
+                    G = {256: 8, 4: 16, 2: 32}[sigma]
+                    stride = (m - (G - 1)) // 32 * 32
+                    if stride < 160:
+                        assert k < 100  # stride too short for skipping sectors to win
+                    else:
+                        assert k == 100 + G, (sigma, m, a, k)
+                    assert r.count == want.size and np.array_equal(r.positions, want), (sigma, m, a)
+                assert sb.search("bf", t, x).count == want.size  # prefix family never skips
+                assert sb.last_timing().filter_kind < 100
+    # periodic text: every sample hits, every candidate verifies
+    y = np.frombuffer(b"ab" * 40000, dtype=np.uint8)
+    with sb.Text.upload(y) as t:
+        for m in (80, 200, 1001):
+            x = y[:m].copy()
+            assert sb.search("hor", t, x).count == oracle.bf_count(x, y)
 
 
 def test_generated_text_matches_host_mirror():
