@@ -699,10 +699,8 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
                    SB_ERR_CUDA);
         CU_TRY(cudaMemsetAsync(ctx[g]->d_counters, 0, 4 * sizeof(unsigned long long), ctx[g]->stream), SB_ERR_CUDA);
     }
-    for (int g = 0; g < t->nshards; g++) {
-        CU_TRY(cudaSetDevice(t->sh[g].dev), SB_ERR_CUDA);
-        CU_TRY(cudaStreamSynchronize(ctx[g]->stream), SB_ERR_CUDA);
-    }
+    /* no synchronisation here: the uploads and the scan are ordered by the stream.  pre_ms therefore covers
+     * the table build and the enqueue of the uploads; the (few-KB) copies themselves overlap the launch. */
     const double t2 = now_ms();
 
     /* ---- scan: one kernel per shard, all devices concurrently ---- */

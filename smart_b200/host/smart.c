@@ -70,6 +70,18 @@ typedef struct {
 
 static segment seg_text, seg_pat, seg_count, seg_time, seg_pre;
 
+/* Pattern sampling has its own generator (splitmix64) so that a given -seed always yields the same pattern
+ * sets: glibc's rand() and random() share one state, and the number of rand() calls spent on picking free
+ * shm keys varies from run to run. */
+static unsigned long long pat_rng_state;
+static unsigned long long pat_rng(void)
+{
+    unsigned long long z = (pat_rng_state += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
 static void usage(void)
 {
     printf("\n\tSMART driver (smart_b200)\n\n"
@@ -132,7 +144,7 @@ static void destroy_all(void)
 /* ---- corpus loading: index.txt with #file# markers (smart.c:95-138) ---- */
 static long load_text(unsigned char *T, const char *dir, long tsize, int *nalpha, int *maxcode)
 {
-    char path[1024];
+    char path[2048];
     long n = 0;
     snprintf(path, sizeof path, "%s/index.txt", dir);
     FILE *idx = fopen(path, "r");
@@ -275,7 +287,7 @@ static void run_experiment(const config *cf, const char *label, unsigned char *T
             if (simple) {
                 memcpy(set[i], cf->simple_p, (size_t)m);
             } else {
-                long k = random() % (n - m);
+                long k = (long)(pat_rng() % (unsigned long long)(n - m));
                 memcpy(set[i], T + k, (size_t)m);
             }
             set[i][m] = 0;
@@ -438,8 +450,8 @@ int main(int argc, char **argv)
     if (cf.nalgo == 0 && add_algos_registry(&cf, "source/algorithms.h") != 0) add_algos_csv(&cf, "bf,kmp,hor,so");
     if (cf.nalgo == 0) { printf("No algorithm selected.\n"); return 0; }
 
-    srand(cf.seed);
-    srandom(cf.seed);
+    srand(cf.seed ^ (unsigned)getpid()); /* shm keys only */
+    pat_rng_state = cf.seed;
     snprintf(cf.code, sizeof cf.code, "EXP%ld", (long)time(NULL)); /* smart.c:90-93 */
 
     const segment *none[1] = {NULL};

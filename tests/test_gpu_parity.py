@@ -267,3 +267,28 @@ def test_host_streaming_entry_large(oracle):
             assert sb.search_host("hor", x, y).count == want
     x = y[5_000_000:5_000_032].copy()
     assert sb.search_host("bf", x, y).count == oracle.bf_count(x, y)
+
+
+def test_multi_device_in_process(oracle):
+    """The single-box partitioner with REAL devices (needs >= 2 GPUs; the devices=[0,0,..] tests cover the
+    same logic on one)."""
+    nd = sb.device_count()
+    if nd < 2:
+        pytest.skip("needs at least 2 GPUs")
+    devs = list(range(min(nd, 8)))
+    n = 1 << 30
+    with sb.Text.generate(n, 4, 31337, devices=devs) as t, sb.Text.generate(n, 4, 31337) as t1:
+        assert t.shards == len(devs)
+        host = sb.textgen_host(0, 1 << 20, 4, 31337)
+        assert np.array_equal(t.download(0, 1 << 20), host)
+        for m in (2, 8, 24, 64, 300, 4096):
+            base, own, _ = sb.shard_range(n, len(devs), 1)
+            x = sb.textgen_host(base - m // 2, m, 4, 31337)  # straddles the device 0 / device 1 seam
+            want = sb.search("bf", t1, x).count
+            assert want >= 1
+            for a in ("bf", "kmp", "hor", "so"):
+                assert sb.search(a, t, x).count == want, (a, m)
+            r = sb.search("bm", t, x, flags=sb.FLAG_POSITIONS, positions_cap=1 << 22)
+            r1 = sb.search("bm", t1, x, flags=sb.FLAG_POSITIONS, positions_cap=1 << 22)
+            if want <= (1 << 22):
+                assert np.array_equal(r.positions, r1.positions)
