@@ -127,6 +127,12 @@ typedef struct sb_timing {
 } sb_timing;
 void sb_last_timing(sb_timing *out);
 
+/* CUDA-event stopwatch on the library's launching stream of `device` (bench.py brackets its K timed steps
+ * with it: torch.cuda.Event only sees torch's own stream). begin records an event; end records a second
+ * one, waits for it and returns the elapsed milliseconds (<0 on error). */
+int sb_stream_timer_begin(int device);
+double sb_stream_timer_end_ms(int device);
+
 /* Host-buffer entry: text in host memory (pinned or pageable), streamed to device 0 in chunks with an
  * m-1 overlap, copy of chunk k+1 overlapped with the scan of chunk k. This is what the legacy
  * `search()` plugins call, and what bench.py times as `e2e`. */
@@ -155,6 +161,7 @@ typedef struct sb_tables {
     int hashSh1;
     int hashQ;                  /* 0 if the algorithm is not a HASHq */
     int krD, krHx;              /* kr.c:34-40 */
+    int acEll;                  /* ac.c:52-53 */
     int qfQ, qfS;               /* qf<Q><S>.c:28-29; 0 if not a QF */
     int qfB[1 << 18];           /* qf23.c:50-56; entries [0, 1<<(Q*S)) */
 } sb_tables;

@@ -495,6 +495,141 @@ long long ora_search_qf(const unsigned char *x, int m, const unsigned char *y, s
     return count;
 }
 
+/* smith.c:41-63: shift = max(bmBc[y[j+m-1]], qsBc[y[j+m]]); the reference reads y[n] at the last window,
+ * the bounded version stops there (no further window can start) */
+long long ora_search_smith(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int bc[ORA_SIGMA], qs[ORA_SIGMA];
+    long long count = 0;
+    ora_pre_hbc(x, m, bc);
+    ora_pre_qsbc(x, m, qs);
+    for (size_t j = 0; j + (size_t)m <= n;) {
+        if (memcmp(x, y + j, (size_t)m) == 0) count++;
+        if (j + (size_t)m >= n) break;
+        const int a = bc[y[j + m - 1]], b = qs[y[j + m]];
+        j += (size_t)(a > b ? a : b);
+    }
+    return count;
+}
+
+/* tbm.c:66-111 Turbo-BM: remembers the factor matched during the previous attempt (u) to jump over it */
+long long ora_search_tbm(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int bc[ORA_SIGMA];
+    int *gs = malloc(sizeof(int) * (size_t)m), *suff = malloc(sizeof(int) * (size_t)m);
+    long long count = 0;
+    ora_pre_bmgs(x, m, suff, gs);
+    ora_pre_hbc(x, m, bc);
+    int u = 0, shift = m;
+    for (size_t j = 0; j + (size_t)m <= n; j += (size_t)shift) {
+        int i = m - 1;
+        while (i >= 0 && x[i] == y[(size_t)i + j]) {
+            --i;
+            if (u != 0 && i == m - 1 - shift) i -= u;
+        }
+        if (i < 0) {
+            count++;
+            shift = gs[0];
+            u = m - shift;
+        } else {
+            const int v = m - 1 - i, turbo = u - v, bcs = bc[y[(size_t)i + j]] - m + 1 + i;
+            shift = turbo > bcs ? turbo : bcs;
+            if (gs[i] > shift) shift = gs[i];
+            if (shift == gs[i]) {
+                u = (m - shift < v) ? m - shift : v;
+            } else {
+                if (turbo < bcs && u + 1 > shift) shift = u + 1;
+                u = 0;
+            }
+        }
+    }
+    free(gs);
+    free(suff);
+    return count;
+}
+
+/* ag.c:59-115 Apostolico-Giancarlo: skip[] remembers, per pattern position, how much of the window was matched
+ * by earlier attempts; suff[] lets whole remembered factors be jumped */
+long long ora_search_ag(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int bc[ORA_SIGMA];
+    int *gs = malloc(sizeof(int) * (size_t)m), *suff = malloc(sizeof(int) * (size_t)m);
+    int *skip = calloc((size_t)m, sizeof(int));
+    long long count = 0;
+    ora_pre_bmgs(x, m, suff, gs);
+    ora_pre_hbc(x, m, bc);
+    for (size_t j = 0; j + (size_t)m <= n;) {
+        int i = m - 1, shift;
+        while (i >= 0) {
+            const int k = skip[i], s = suff[i];
+            if (k > 0) {
+                if (k > s) {
+                    i = (i + 1 == s) ? -1 : i - s;
+                    break;
+                }
+                i -= k;
+                if (k < s) break;
+            } else {
+                if (x[i] == y[(size_t)i + j]) --i;
+                else break;
+            }
+        }
+        if (i < 0) {
+            count++;
+            skip[m - 1] = m;
+            shift = gs[0];
+        } else {
+            const int b = bc[y[(size_t)i + j]] - m + 1 + i;
+            skip[m - 1] = m - 1 - i;
+            shift = gs[i] > b ? gs[i] : b;
+        }
+        j += (size_t)shift;
+        memmove(skip, skip + shift, (size_t)(m - shift) * sizeof(int));
+        memset(skip + m - shift, 0, (size_t)shift * sizeof(int));
+    }
+    free(gs);
+    free(suff);
+    free(skip);
+    return count;
+}
+
+/* ac.c:52-53: ell */
+int ora_pre_ac_ell(const unsigned char *x, int m)
+{
+    int ell = 1;
+    while (ell < m && x[ell - 1] == x[ell]) ell++;
+    return ell == m ? 0 : ell;
+}
+
+/* ac.c:44-83 Apostolico-Crochemore */
+long long ora_search_ac(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int *next = malloc(sizeof(int) * (size_t)(m + 1));
+    long long count = 0;
+    ora_pre_kmp(x, m, next);
+    const int ell = ora_pre_ac_ell(x, m);
+    int i = ell, k = 0;
+    for (size_t j = 0; j + (size_t)m <= n;) {
+        while (i < m && x[i] == y[(size_t)i + j]) ++i;
+        if (i >= m) {
+            while (k < ell && x[k] == y[j + (size_t)k]) ++k;
+            if (k >= ell) count++;
+        }
+        j += (size_t)(i - next[i]);
+        if (i == ell) {
+            k = k - 1 > 0 ? k - 1 : 0;
+        } else if (next[i] <= ell) {
+            k = next[i] > 0 ? next[i] : 0;
+            i = ell;
+        } else {
+            k = ell;
+            i = next[i];
+        }
+    }
+    free(next);
+    return count;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Dispatcher by registry name (lower case, smart.c:142). Returns -2 for an unknown name. */
 long long ora_search(const char *algo, const unsigned char *x, int m, const unsigned char *y, size_t n)
@@ -511,6 +646,10 @@ long long ora_search(const char *algo, const unsigned char *x, int m, const unsi
     if (!strcmp(algo, "so")) return ora_search_so(x, m, y, n);
     if (!strcmp(algo, "sa")) return ora_search_sa(x, m, y, n);
     if (!strcmp(algo, "kr")) return ora_search_kr(x, m, y, n);
+    if (!strcmp(algo, "smith")) return (size_t)m > n ? 0 : ora_search_smith(x, m, y, n);
+    if (!strcmp(algo, "tbm")) return (size_t)m > n ? 0 : ora_search_tbm(x, m, y, n);
+    if (!strcmp(algo, "ag")) return (size_t)m > n ? 0 : ora_search_ag(x, m, y, n);
+    if (!strcmp(algo, "ac")) return (size_t)m > n ? 0 : ora_search_ac(x, m, y, n);
     if (!strncmp(algo, "hash", 4) && algo[4] && !algo[5]) return ora_search_hashq(x, m, y, n, algo[4] - '0');
     if (!strncmp(algo, "qf", 2) && algo[2] && algo[3] && !algo[4])
         return ora_search_qf(x, m, y, n, algo[2] - '0', algo[3] - '0');

@@ -32,6 +32,8 @@ from .binding import (  # noqa: F401
     search,
     search_host,
     shard_range,
+    stream_timer_begin,
+    stream_timer_end_ms,
     plugin_search,
     textgen_host,
 )

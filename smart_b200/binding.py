@@ -35,6 +35,7 @@ ALGORITHMS = (
     "bf", "mp", "kmp", "bm", "hor", "qs", "raita", "tunedbm", "so", "sa", "kr",
     "hash3", "hash5", "hash8",
     "qf23", "qf24", "qf26", "qf28", "qf33", "qf34", "qf36", "qf42", "qf43", "qf44", "qf62", "qf63",
+    "smith", "tbm", "ag", "ac",
 )
 
 
@@ -86,6 +87,7 @@ class Tables(C.Structure):
         ("hashQ", C.c_int),
         ("krD", C.c_int),
         ("krHx", C.c_int),
+        ("acEll", C.c_int),
         ("qfQ", C.c_int),
         ("qfS", C.c_int),
         ("qfB", C.c_int * (1 << 18)),
@@ -120,6 +122,8 @@ SYMBOLS = [
     ("sb_search64", C.c_longlong, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_void_p, C.c_size_t,
                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("sb_last_timing", None, [C.POINTER(Timing)]),
+    ("sb_stream_timer_begin", C.c_int, [C.c_int]),
+    ("sb_stream_timer_end_ms", C.c_double, [C.c_int]),
     ("sb_search_host", C.c_longlong, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_uint,
                                       C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("sb_plugin_search", C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
@@ -266,6 +270,18 @@ def last_timing() -> Timing:
     t = Timing()
     lib().sb_last_timing(C.byref(t))
     return t
+
+
+def stream_timer_begin(device: int = 0):
+    if lib().sb_stream_timer_begin(device) != 0:
+        raise SmartB200Error(_err())
+
+
+def stream_timer_end_ms(device: int = 0) -> float:
+    ms = lib().sb_stream_timer_end_ms(device)
+    if ms < 0:
+        raise SmartB200Error(_err())
+    return ms
 
 
 def search(algo: str, text: Text, pattern, flags: int = 0, positions_cap: int = 0) -> SearchResult:

@@ -64,6 +64,7 @@ struct DevCtx {                               // per-device scratch, created on 
     int sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;   // sb_stream_timer_*
     uint32_t *d_pat = nullptr;                // pattern words
     unsigned long long *d_counters = nullptr; // 4 x u64
     unsigned long long *h_counters = nullptr; // pinned mirror
@@ -121,6 +122,8 @@ DevCtx *get_ctx(int dev)
     CU_TRY(cudaStreamCreateWithFlags(&c.cstream[1], cudaStreamNonBlocking), nullptr);
     CU_TRY(cudaEventCreate(&c.e0), nullptr);
     CU_TRY(cudaEventCreate(&c.e1), nullptr);
+    CU_TRY(cudaEventCreate(&c.t0), nullptr);
+    CU_TRY(cudaEventCreate(&c.t1), nullptr);
     CU_TRY(cudaMalloc(&c.d_pat, kPatBytes), nullptr);
     CU_TRY(cudaMalloc(&c.d_counters, 4 * sizeof(unsigned long long)), nullptr);
     CU_TRY(cudaHostAlloc(&c.h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault), nullptr);
@@ -414,6 +417,25 @@ int sb_device_count(void)
 void sb_last_timing(sb_timing *out)
 {
     if (out) *out = g_timing;
+}
+
+int sb_stream_timer_begin(int device)
+{
+    DevCtx *c = get_ctx(device);
+    if (!c) return -1;
+    CU_TRY(cudaEventRecord(c->t0, c->stream), -1);
+    return 0;
+}
+
+double sb_stream_timer_end_ms(int device)
+{
+    DevCtx *c = get_ctx(device);
+    if (!c) return -1.0;
+    float ms = 0;
+    CU_TRY(cudaEventRecord(c->t1, c->stream), -1.0);
+    CU_TRY(cudaEventSynchronize(c->t1), -1.0);
+    CU_TRY(cudaEventElapsedTime(&ms, c->t0, c->t1), -1.0);
+    return (double)ms;
 }
 
 void *sb_host_alloc(size_t bytes)

@@ -42,6 +42,11 @@ static const sb_algo_desc g_algos[] = {
     {"qf44", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 4, 4, 5},
     {"qf62", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 6, 2, 7},
     {"qf63", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 6, 3, 7},
+    /* further clean families whose tables are the ones above */
+    {"smith", SB_FAM_SMITH, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},     /* smith.c:41: max(bmBc, qsBc) shift */
+    {"tbm", SB_FAM_TBM, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},         /* tbm.c:66: Turbo-BM (bmGs, bmBc) */
+    {"ag", SB_FAM_AG, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},           /* ag.c:59: Apostolico-Giancarlo (bmGs, suff, bmBc) */
+    {"ac", SB_FAM_AC, SB_ANCHOR_PREFIX, 0, 0, 0, 1},           /* ac.c:44: Apostolico-Crochemore (kmpNext, ell) */
 };
 #define SB_NALGOS ((int)(sizeof(g_algos) / sizeof(g_algos[0])))
 
@@ -285,6 +290,24 @@ int sb_prep_tables(int algo, const unsigned char *x, int m, sb_tables *out)
     case SB_FAM_RAITA:
     case SB_FAM_TUNEDBM: sb_prep_hbc(x, m, out->hbc); break;
     case SB_FAM_QS: sb_prep_qsbc(x, m, out->qsBc); break;
+    case SB_FAM_SMITH:
+        sb_prep_hbc(x, m, out->hbc);
+        sb_prep_qsbc(x, m, out->qsBc);
+        break;
+    case SB_FAM_TBM:
+    case SB_FAM_AG:
+        sb_prep_bmgs(x, m, out->suff, out->bmGs);
+        sb_prep_hbc(x, m, out->hbc);
+        break;
+    case SB_FAM_AC: {
+        /* ell = length of the leading run of x[0] if the pattern is not a single run, else 0 (ac.c:52-53) */
+        int ell = 1;
+        sb_prep_mp(x, m, out->mpNext);
+        sb_prep_kmp(x, m, out->mpNext, out->kmpNext);
+        while (ell < m && x[ell] == x[0]) ell++;
+        out->acEll = (ell == m) ? 0 : ell;
+        break;
+    }
     case SB_FAM_SO: out->soLim = sb_prep_so(x, m, out->soS); break;
     case SB_FAM_SA: out->saF = sb_prep_sa(x, m, out->saS); break;
     case SB_FAM_KR: sb_prep_kr(x, m, &out->krD, &out->krHx); break;

@@ -21,7 +21,11 @@ enum sb_family {
     SB_FAM_SA,
     SB_FAM_KR,
     SB_FAM_HASHQ,
-    SB_FAM_QF
+    SB_FAM_QF,
+    SB_FAM_SMITH,
+    SB_FAM_TBM,
+    SB_FAM_AG,
+    SB_FAM_AC
 };
 
 /* which end of the pattern the candidate fingerprint is taken from: the left-to-right families

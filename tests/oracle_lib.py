@@ -106,6 +106,8 @@ class Oracle:
         if name == "kr":
             d, hx = C.c_int(0), C.c_int(0)
             L.ora_pre_kr(_ptr(x), m, C.byref(d), C.byref(hx)); return d.value, hx.value
+        if name == "acEll":
+            return int(L.ora_pre_ac_ell(_ptr(x), m))
         if name == "qf":
             Q, S = int(kw["Q"]), int(kw["S"])
             t = ia(1 << (Q * S)); L.ora_pre_qf(_ptr(x), m, Q, S, _ptr(t)); return t

@@ -94,6 +94,13 @@ def test_tables_vs_oracle_random(oracle):
         S, F = oracle.table("sa", x)
         t = sb.prep_tables("sa", x)
         assert arr(t.saS, 256) == S.tolist() and t.saF == F
+        t = sb.prep_tables("ac", x)
+        assert arr(t.kmpNext, m + 1) == oracle.table("kmpNext", x).tolist() and t.acEll == oracle.table("acEll", x)
+        t = sb.prep_tables("smith", x)
+        assert arr(t.hbc, 256) == oracle.table("hbc", x).tolist() and arr(t.qsBc, 256) == oracle.table("qsBc", x).tolist()
+        for name in ("tbm", "ag"):
+            t = sb.prep_tables(name, x)
+            assert arr(t.bmGs, m) == oracle.table("bmGs", x).tolist() and arr(t.suff, m) == oracle.table("suff", x).tolist()
         d, hx = oracle.table("kr", x)
         t = sb.prep_tables("kr", x)
         assert (t.krD, t.krHx) == (d, hx)
