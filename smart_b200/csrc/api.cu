@@ -54,7 +54,7 @@ constexpr size_t kPatBytes = 4352;            // device pattern buffer (>= SB_XS
 constexpr int kU = SB_U;                      // 256-bit loads in flight per thread (scan_block / scan_window8)
 constexpr size_t kGroupLong = kU * 1024;      // bytes per warp iteration of those kernels
 constexpr size_t kGroupShort = 4 * 512;       // ... of scan_short
-constexpr int kFilterShort = 0, kFilterWindow8 = 1;
+constexpr int kFilterShort = 0, kFilterWindow8 = 1, kFilterWindow12 = 2, kFilterWindow16 = 3;
 constexpr int kFilterSkip = 100;              // + gram bytes (108, 116, 132): scan_skip<G>
 constexpr size_t kAuxWords = sb::kBloomWords + 2 * sb::kSkipTableSize;
 
@@ -72,7 +72,7 @@ struct DevCtx {                               // per-device scratch, created on 
     unsigned long long *d_pos = nullptr;      // position sink, grown on demand
     size_t pos_cap = 0;
     int occ_block[4] = {0, 0, 0, 0};          // resident CTAs/SM for scan_block<4,8,16,32>
-    int occ_window[4] = {0, 0, 0, 0};         // ... for scan_window8<OFF=1..4>
+    int occ_window[24] = {0};                 // ... for scan_window<NW,OFF,DENSE>, index window_index()
     int occ_short[6] = {0, 0, 0, 0, 0, 0};    // ... for scan_short<MODE, FULL>
     unsigned long long *d_hist = nullptr;     // 256-bin byte histogram scratch
     uint32_t *d_aux = nullptr, *h_aux = nullptr; // scan_skip: Bloom bitmap + gram fingerprint list
@@ -85,6 +85,8 @@ struct DevCtx {                               // per-device scratch, created on 
 
 DevCtx g_ctx[64];
 std::mutex g_mu;
+
+constexpr int window_index(int nw, int off, bool dense) { return ((nw - 2) * 4 + (off - 1)) * 2 + (dense ? 1 : 0); }
 
 template <typename K>
 int occupancy(K kernel)
@@ -138,10 +140,13 @@ DevCtx *get_ctx(int dev)
     c.occ_block[1] = occupancy(sb::scan_block_kernel<8, kU>);
     c.occ_block[2] = occupancy(sb::scan_block_kernel<16, kU>);
     c.occ_block[3] = occupancy(sb::scan_block_kernel<32, kU>);
-    c.occ_window[0] = occupancy(sb::scan_window8_kernel<1, kU>);
-    c.occ_window[1] = occupancy(sb::scan_window8_kernel<2, kU>);
-    c.occ_window[2] = occupancy(sb::scan_window8_kernel<3, kU>);
-    c.occ_window[3] = occupancy(sb::scan_window8_kernel<4, kU>);
+#define SB_WIN_OCC(NW, OFF)                                                                       \
+    c.occ_window[window_index(NW, OFF, false)] = occupancy(sb::scan_window_kernel<NW, OFF, false, kU>); \
+    c.occ_window[window_index(NW, OFF, true)] = occupancy(sb::scan_window_kernel<NW, OFF, true, kU>);
+    SB_WIN_OCC(2, 1) SB_WIN_OCC(2, 2) SB_WIN_OCC(2, 3) SB_WIN_OCC(2, 4)
+    SB_WIN_OCC(3, 1) SB_WIN_OCC(3, 2) SB_WIN_OCC(3, 3) SB_WIN_OCC(3, 4)
+    SB_WIN_OCC(4, 1) SB_WIN_OCC(4, 2) SB_WIN_OCC(4, 3) SB_WIN_OCC(4, 4)
+#undef SB_WIN_OCC
     c.occ_short[0] = occupancy(sb::scan_short_kernel<0, false>);
     c.occ_short[1] = occupancy(sb::scan_short_kernel<0, true>);
     c.occ_short[2] = occupancy(sb::scan_short_kernel<1, false>);
@@ -199,7 +204,7 @@ uint32_t fingerprint(const unsigned char *p, int B)
 }
 
 /* Which kernel scans a pattern of length m over a text with `bits` of collision entropy per byte.
- * 0 = scan_short (exact, m <= 4), 1 = scan_window8 (8-byte window at every position),
+ * 0 = scan_short (exact, m <= 4), 1/2/3 = scan_window (8/12/16-byte window at every position),
  * 4/8/16/32 = scan_block<B> (aligned-block fingerprints, needs m >= 2B-1).
  * The block kernels are the fast ones (16 ALU ops per 16 bytes) but a B-byte fingerprint lets a
  * fraction ~2^-(B*bits) of all start positions through to verification: pick the narrowest B whose
@@ -212,7 +217,7 @@ int choose_filter(int m, unsigned flags, double bits)
     if ((flags & SB_FLAG_FILTER_B8) && m >= 15) return 8;
     if ((flags & SB_FLAG_FILTER_B4) && m >= 7) return 4;
     if (m <= 4) return kFilterShort;
-    if (flags & SB_FLAG_FILTER_SHIFT) return kFilterWindow8;
+    if (flags & SB_FLAG_FILTER_SHIFT) return kFilterWindow8;  // 8-byte window (exact for m <= 8)
     int widest = 0;
     for (int B = 4; B <= 32; B *= 2) {
         if (2 * B - 1 > m) break;
@@ -220,7 +225,13 @@ int choose_filter(int m, unsigned flags, double bits)
         if (B * bits >= 20.0) return B;
     }
     if (widest && widest * bits >= 14.0) return widest;
-    if (widest > 8) return widest;  // more selective than the 8-byte window
+    if (widest > 16) return widest;  // more selective than any per-position window
+    // per-position window of 2, 3 or 4 words: the narrowest that carries >= 14 bits, else the widest
+    // that fits (a window never exceeds the pattern: min(m, 4*NW) bytes)
+    for (int nw = 2; nw <= 4; nw++) {
+        const int bytes = m < 4 * nw ? m : 4 * nw;
+        if (bytes * bits >= 14.0 || bytes == m || nw == 4) return kFilterWindow8 + (nw - 2);
+    }
     return kFilterWindow8;
 }
 
@@ -239,6 +250,18 @@ int skip_min_stride()
     return v;
 }
 
+/* below this many bits (m * bits) a pattern that fits in the window is counted in registers (dense mode)
+ * instead of OR-reducing the compares; SMART_B200_DENSE_BITS overrides (tuning) */
+double dense_bits()
+{
+    static double v = -1;
+    if (v < 0) {
+        const char *e = getenv("SMART_B200_DENSE_BITS");
+        v = e ? atof(e) : 12.5;  // measured crossover (sigma 2 and 4, m = 5..16): dense wins below ~12.5 bits
+    }
+    return v;
+}
+
 struct Plan {
     int filter;
     int skip_grams;     // scan_skip: entries of the fingerprint list (= stride), 0 otherwise
@@ -251,7 +274,7 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
 {
     memset(&pl.args, 0, sizeof pl.args);
     pl.filter = choose_filter(m, flags, bits);
-    pl.sparse = m * bits >= 18.0 && !(flags & SB_FLAG_DENSE);
+    pl.sparse = m * bits >= 18.0 && !(flags & SB_FLAG_DENSE);  // scan_short; scan_window decides below
     pl.skip_grams = 0;
     sb::ScanArgs &a = pl.args;
     a.m = m;
@@ -277,12 +300,18 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
     if (pl.filter == kFilterShort) {
         a.M0 = m == 4 ? 0xffffffffu : ((1u << (8 * m)) - 1u);
         a.X0 = load_le32(x, m) & a.M0;
-    } else if (pl.filter == kFilterWindow8) {
-        const int off = m >= 8 ? 4 : m - 4;  // second window word; overlaps the first when m < 8
+    } else if (pl.filter <= kFilterWindow16) {
+        const int nw = pl.filter + 1;                         // window words: 2, 3 or 4
+        const int off = m >= 4 * nw ? 4 : m - 4 * (nw - 1);   // last word overlaps when the window is the pattern
         a.X0 = load_le32(x, 4);
-        a.X1 = load_le32(x + off, 4);
-        a.G = sb::fp8(a.X0, a.X1);
+        for (int k = 1; k < nw; k++) a.Xw[k - 1] = load_le32(x + 4 * (k - 1) + (k == nw - 1 ? off : 4), 4);
+        a.X1 = a.Xw[nw - 2];
+        if (nw == 2) a.G = sb::fp8(a.X0, a.X1);
+        else if (nw == 3) a.G = sb::fp8(a.X0, a.Xw[0]) * sb::K2 + a.Xw[1];
+        else a.G = sb::fp8(a.X0, a.Xw[0]) * sb::K2 + sb::fp8(a.Xw[1], a.Xw[2]);
         a.anchor = off;  // reused to carry OFF to launch_scan
+        // when the window is the whole pattern and matches are frequent, count them in registers
+        pl.sparse = !(m <= 4 * nw && (m * bits < dense_bits() || (flags & SB_FLAG_DENSE)));
     } else {
         const int B = pl.filter;
         a.anchor = desc->anchor == SB_ANCHOR_SUFFIX ? m - (2 * B - 1) : 0;
@@ -315,10 +344,11 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
         a.ngroups = ((unsigned long long)a.hi + group - 1) / group;
         const int mode = pl.sparse ? 2 : (want_pos ? 1 : 0);
         per_sm = c.occ_short[mode * 2 + (a.m == 4 ? 1 : 0)];
-    } else if (pl.filter == kFilterWindow8) {
+    } else if (pl.filter <= kFilterWindow16) {
         group = kGroupLong;
         a.ngroups = ((unsigned long long)a.hi + group - 1) / group;
-        per_sm = c.occ_window[a.anchor - 1];
+        const bool dense = !pl.sparse && !want_pos;
+        per_sm = c.occ_window[window_index(pl.filter + 1, a.anchor, dense)];
     } else {
         group = kGroupLong;
         const unsigned long long end = (unsigned long long)a.hi + a.anchor + 2 * pl.filter;
@@ -337,13 +367,20 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
         else if (mode == 1) sb::scan_short_kernel<1, true><<<grid, sb::kThreads, 0, stream>>>(a);
         else if (!full) sb::scan_short_kernel<2, false><<<grid, sb::kThreads, 0, stream>>>(a);
         else sb::scan_short_kernel<2, true><<<grid, sb::kThreads, 0, stream>>>(a);
-    } else if (pl.filter == kFilterWindow8) {
+    } else if (pl.filter <= kFilterWindow16) {
         const int off = a.anchor;
+        const bool dense = !pl.sparse && !want_pos;
         a.anchor = 0;
-        if (off == 1) sb::scan_window8_kernel<1, kU><<<grid, sb::kThreads, 0, stream>>>(a);
-        else if (off == 2) sb::scan_window8_kernel<2, kU><<<grid, sb::kThreads, 0, stream>>>(a);
-        else if (off == 3) sb::scan_window8_kernel<3, kU><<<grid, sb::kThreads, 0, stream>>>(a);
-        else sb::scan_window8_kernel<4, kU><<<grid, sb::kThreads, 0, stream>>>(a);
+        const int nw = pl.filter + 1;
+#define SB_WIN_LAUNCH(NW, OFF)                                                                   \
+    if (nw == NW && off == OFF) {                                                                \
+        if (dense) sb::scan_window_kernel<NW, OFF, true, kU><<<grid, sb::kThreads, 0, stream>>>(a); \
+        else sb::scan_window_kernel<NW, OFF, false, kU><<<grid, sb::kThreads, 0, stream>>>(a);      \
+    }
+        SB_WIN_LAUNCH(2, 1) SB_WIN_LAUNCH(2, 2) SB_WIN_LAUNCH(2, 3) SB_WIN_LAUNCH(2, 4)
+        SB_WIN_LAUNCH(3, 1) SB_WIN_LAUNCH(3, 2) SB_WIN_LAUNCH(3, 3) SB_WIN_LAUNCH(3, 4)
+        SB_WIN_LAUNCH(4, 1) SB_WIN_LAUNCH(4, 2) SB_WIN_LAUNCH(4, 3) SB_WIN_LAUNCH(4, 4)
+#undef SB_WIN_LAUNCH
     } else if (pl.filter == 4) sb::scan_block_kernel<4, kU><<<grid, sb::kThreads, 0, stream>>>(a);
     else if (pl.filter == 8) sb::scan_block_kernel<8, kU><<<grid, sb::kThreads, 0, stream>>>(a);
     else if (pl.filter == 16) sb::scan_block_kernel<16, kU><<<grid, sb::kThreads, 0, stream>>>(a);

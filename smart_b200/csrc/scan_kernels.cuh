@@ -13,9 +13,9 @@
  *         so only ALIGNED blocks are fingerprinted (IMAD, FMA pipe) and compared with the B
  *         fingerprints of the pattern's B-grams at offsets a..a+B-1 (one ISETP.EQ.OR per start
  *         position, ALU pipe): no shifts, no halo, no shared memory;
- *       * scan_window8<OFF> (5 <= m, low-entropy texts or m < 2B-1): an 8-byte window fingerprint
- *         at EVERY start position (SHF funnel shift + IMAD + ISETP.EQ.OR per position); the 8-byte
- *         halo comes from the neighbouring lane by shuffle, not from memory;
+ *       * scan_window<NW,OFF> (5 <= m, low-entropy texts or m < 2B-1): an 8/12/16-byte window
+ *         fingerprint at EVERY start position (SHF funnel shift + IMAD + ISETP.EQ.OR per position);
+ *         the halo comes from the neighbouring lane by shuffle, not from memory;
  *       * scan_short (m <= 4): exact masked-word compare at every position, counted in registers;
  *   - candidates (rare) go to an exact verification that reads the text through L2 with unaligned
  *     32-bit windows (warp-cooperative, 128 bytes per step, in scan_block);
@@ -63,8 +63,9 @@ struct ScanArgs {
     int nwords;                   // ceil(m/4)
     uint32_t tailmask;            // mask for the last pattern word
     uint32_t H[32];               // scan_block: fingerprints of x[a+d .. a+d+B), d < B
-    uint32_t X0, X1, M0;          // scan_short: masked first word; scan_window8: the two window words
-    uint32_t G;                   // scan_window8: fp8(X0, X1)
+    uint32_t X0, X1, M0;          // scan_short: masked first word; scan_window: first and (NW=2) second word
+    uint32_t Xw[3];               // scan_window: window words 1..NW-1 (Xw[NW-2] is the last one)
+    uint32_t G;                   // scan_window: fingerprint of the window words
     // scan_skip: one G-byte gram is sampled every `stride` bytes; aux = Bloom bitmap (kBloomWords words)
     // followed by an open-addressing table {fingerprint of x[anchor+d .. anchor+d+G), d+1}, d < stride
     const uint32_t *aux;
@@ -293,11 +294,11 @@ __global__ void __launch_bounds__(kThreads, SB_MINB) scan_block_kernel(const __g
     block_reduce_count(a, cnt, nver);
 }
 
-/* ===================================================================== scan_window8<OFF, U> */
+/* ===================================================================== scan_window<NW, OFF, DENSE, U> */
 
-/* Per-lane slow path of scan_window8: `mm` has bit p set for every start position p of this lane's
- * 32-byte vector whose two window words match exactly; verify the rest of the pattern (m > 8) and count. */
-__device__ __noinline__ uint2 window8_matches(const ScanArgs &a, unsigned mm, long long voff)
+/* Per-lane slow path of scan_window: `mm` has bit p set for every start position p of this lane's
+ * 32-byte vector whose window words match exactly; verify the pattern words from `from` on and count. */
+__device__ __noinline__ uint2 window_matches(const ScanArgs &a, unsigned mm, long long voff, int from)
 {
     unsigned cnt = 0, nver = 0;
     while (mm) {
@@ -305,9 +306,9 @@ __device__ __noinline__ uint2 window8_matches(const ScanArgs &a, unsigned mm, lo
         mm &= mm - 1;
         const long long j = voff + p;
         if (j >= a.hi) break;
-        if (a.m > 8) {
+        if (a.nwords > from) {
             nver++;
-            if (!lane_verify(a, j, 2)) continue;
+            if (!lane_verify(a, j, from)) continue;
         }
         cnt++;
         emit_match(a, j);
@@ -315,11 +316,19 @@ __device__ __noinline__ uint2 window8_matches(const ScanArgs &a, unsigned mm, lo
     return make_uint2(cnt, nver);
 }
 
-/* 8-byte window fingerprint at every start position: window = bytes [p, p+4) and [p+OFF, p+OFF+4),
- * OFF = 4 for m >= 8 and m-4 for 5 <= m <= 7 (the two words overlap and cover exactly m bytes). */
-template <int OFF, int U>
-__global__ void __launch_bounds__(kThreads, SB_MINB) scan_window8_kernel(const __grid_constant__ ScanArgs a)
+/* Window fingerprint at EVERY start position p: NW 32-bit words at byte offsets p, p+4, .., the last one at
+ * p + 4*(NW-2) + OFF.  OFF = 4: an 8/12/16-byte prefix window (the rest of a longer pattern is verified on
+ * a hit).  OFF < 4: m = 4*(NW-1) + OFF, the last word overlaps the previous one and the window covers the
+ * pattern EXACTLY, so a window match is an occurrence.  Wider windows are for low-entropy texts (sigma=2)
+ * where 8 bytes are not selective.  DENSE (window == pattern, frequent matches): every position is compared
+ * exactly and counted in registers, no branch. */
+template <int NW, int OFF, bool DENSE, int U>
+__global__ void __launch_bounds__(kThreads, SB_MINB) scan_window_kernel(const __grid_constant__ ScanArgs a)
 {
+    constexpr int LAST = 4 * (NW - 2) + OFF;     // byte offset of the last window word
+    constexpr int NS = 32 + LAST;                // shifted words needed: byte offsets 0 .. 31+LAST
+    constexpr int NWORDS = (NS + 2) / 4 + 1;     // 32-bit words feeding them (8 own + halo)
+    constexpr int HALO = NWORDS - 8;
     const unsigned lane = threadIdx.x & 31;
     const unsigned long long warp = ((unsigned long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * kThreads) >> 5;
@@ -330,40 +339,68 @@ __global__ void __launch_bounds__(kThreads, SB_MINB) scan_window8_kernel(const _
         V8 v[U];
 #pragma unroll
         for (int c = 0; c < U; c++) v[c] = ldg_stream256(p + c * 1024);
-        // halo of the last chunk's lane 31: first 8 bytes of the next group, fetched by lane 0 (L2 hit later)
-        uint2 gn = make_uint2(0u, 0u);
-        if (lane == 0) gn = __ldg(reinterpret_cast<const uint2 *>(a.text + (g + 1) * (U * 1024ull)));
+        // halo of the last chunk's lane 31: first 16 bytes of the next group, fetched by lane 0 (L2 hit later)
+        uint4 gn = make_uint4(0u, 0u, 0u, 0u);
+        if (lane == 0) gn = __ldg(reinterpret_cast<const uint4 *>(a.text + (g + 1) * (U * 1024ull)));
+        const uint32_t gnw[4] = {gn.x, gn.y, gn.z, gn.w};
 #pragma unroll
         for (int c = 0; c < U; c++) {
-            // the 8 bytes after this lane's vector: lane+1's first two words; lane 31 takes lane 0 of the next chunk
-            uint32_t sx, sy;
-            if (c + 1 < U) {
-                sx = lane == 0 ? v[c + 1].w[0] : v[c].w[0];
-                sy = lane == 0 ? v[c + 1].w[1] : v[c].w[1];
-            } else {
-                sx = lane == 0 ? gn.x : v[c].w[0];
-                sy = lane == 0 ? gn.y : v[c].w[1];
-            }
-            uint32_t W[10];
+            // the bytes after this lane's vector: lane+1's first words; lane 31 takes lane 0 of the next chunk
+            uint32_t W[NWORDS];
 #pragma unroll
             for (int i = 0; i < 8; i++) W[i] = v[c].w[i];
-            W[8] = __shfl_sync(kFull, sx, (lane + 1) & 31);
-            W[9] = __shfl_sync(kFull, sy, (lane + 1) & 31);
-            // shifted words for byte offsets 0..31+OFF
-            uint32_t S[32 + OFF];
 #pragma unroll
-            for (int b = 0; b < 32 + OFF; b++)
+            for (int i = 0; i < HALO; i++) {
+                const uint32_t nxt = (c + 1 < U) ? v[(c + 1 < U) ? c + 1 : c].w[i] : gnw[i];
+                const uint32_t snd = lane == 0 ? nxt : v[c].w[i];
+                W[8 + i] = __shfl_sync(kFull, snd, (lane + 1) & 31);
+            }
+            uint32_t S[NS];
+#pragma unroll
+            for (int b = 0; b < NS; b++)
                 S[b] = (b & 3) ? __funnelshift_r(W[b >> 2], W[(b >> 2) + 1], 8 * (b & 3)) : W[b >> 2];
-            bool hit = false;
+            const long long voff = (long long)(g * (U * 1024ull)) + c * 1024 + lane * 32;
+            if (DENSE && voff + 32 <= a.hi) {
 #pragma unroll
-            for (int b = 0; b < 32; b++) hit |= (fp8(S[b], S[b + OFF]) == a.G);
-            if (hit) {  // per lane: which positions match both words exactly (the hash can collide)
+                for (int b = 0; b < 32; b++) {
+                    bool eq = (S[b] == a.X0) && (S[b + LAST] == a.Xw[NW - 2]);
+                    if (NW >= 3) eq = eq && (S[b + 4] == a.Xw[0]);
+                    if (NW >= 4) eq = eq && (S[b + 8] == a.Xw[1]);
+                    cnt += eq;
+                }
+                continue;
+            }
+            bool hit = DENSE;
+            if (!DENSE) {
+                if (NW == 2) {
+#pragma unroll
+                    for (int b = 0; b < 32; b++) hit |= (fp8(S[b], S[b + LAST]) == a.G);
+                } else if (NW == 3) {
+#pragma unroll
+                    for (int b = 0; b < 32; b++) hit |= (fp8(S[b], S[b + 4]) * K2 + S[b + LAST] == a.G);
+                } else if (OFF == 4) {
+                    uint32_t g8[40];
+#pragma unroll
+                    for (int b = 0; b < 40; b++) g8[b] = fp8(S[b], S[b + 4]);
+#pragma unroll
+                    for (int b = 0; b < 32; b++) hit |= (g8[b] * K2 + g8[b + 8] == a.G);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 32; b++)
+                        hit |= (fp8(S[b], S[b + 4]) * K2 + fp8(S[b + 8], S[b + LAST]) == a.G);
+                }
+            }
+            if (hit && voff < a.hi) {  // per lane: which positions match all window words exactly
                 unsigned mm = 0;
 #pragma unroll
-                for (int b = 0; b < 32; b++) mm |= ((S[b] == a.X0 && S[b + OFF] == a.X1) ? 1u : 0u) << b;
+                for (int b = 0; b < 32; b++) {
+                    bool eq = (S[b] == a.X0) && (S[b + LAST] == a.Xw[NW - 2]);
+                    if (NW >= 3) eq = eq && (S[b + 4] == a.Xw[0]);
+                    if (NW >= 4) eq = eq && (S[b + 8] == a.Xw[1]);
+                    mm |= (eq ? 1u : 0u) << b;
+                }
                 if (mm) {
-                    const long long voff = (long long)(g * (U * 1024ull)) + c * 1024 + lane * 32;
-                    const uint2 r = window8_matches(a, mm, voff);
+                    const uint2 r = window_matches(a, mm, voff, NW);
                     cnt += r.x;
                     nver += r.y;
                 }

@@ -91,7 +91,7 @@ def test_every_filter_width_gives_the_same_count(oracle, golden, tname):
                     r = sb.search(a, t, x, flags=FILTERS[f])
                     assert sb.last_timing().filter_kind == f
                     assert r.count == want, (tname, c["m"], c["pi"], a, f)
-            if c["m"] <= 4:  # scan_short: dense (count every position) and sparse (OR-reduce) modes agree
+            if c["m"] <= 16:  # scan_short / scan_window: dense (count every position) and sparse modes agree
                 assert sb.search("bf", t, x, flags=sb.FLAG_DENSE).count == want
                 r = sb.search("bf", t, x, flags=sb.FLAG_DENSE | sb.FLAG_POSITIONS, positions_cap=y.size)
                 assert r.count == want and np.array_equal(r.positions, oracle.bf_positions(x, y))
@@ -182,6 +182,24 @@ def test_sharded_counts_equal_unsharded(oracle):
             with sb.Text.upload_part(y, 4, g) as part:
                 total += sb.search("kmp", part, x).count
         assert total == want
+
+
+def test_low_entropy_windows(oracle):
+    """sigma=2: 8 bytes carry 8 bits, so 12 <= m < 31 uses the 12/16-byte per-position windows (kinds 2, 3);
+    frequent short patterns are counted in registers (dense mode).  All against the oracle."""
+    y = sb.textgen_host(0, 3_000_000, 2, 9)
+    with sb.Text.upload(y) as t:
+        kinds = {}
+        for m in (5, 6, 7, 8, 9, 11, 12, 13, 15, 16, 17, 23, 30, 31):
+            x = y[1_000_000 : 1_000_000 + m].copy()
+            want = oracle.bf_positions(x, y)
+            r = sb.search("bf", t, x)
+            kinds[m] = sb.last_timing().filter_kind
+            assert r.count == want.size, m
+            r = sb.search("kmp", t, x, flags=sb.FLAG_POSITIONS, positions_cap=y.size)
+            assert np.array_equal(r.positions, want), m
+        # 5..8: two-word window == pattern; 9..12: three words; 13..30: four words (exact up to 16); 31+: block
+        assert [kinds[m] for m in (5, 8, 9, 12, 13, 15, 16, 30, 31)] == [1, 1, 2, 2, 3, 3, 3, 3, 16]
 
 
 def test_skip_kernel_is_selected_and_exact(oracle):
