@@ -91,8 +91,9 @@ sb_text *sb_text_upload_part(const unsigned char *host, size_t n_total, int npar
  * bytes [*base, *base + *len). Returns 0, -1 on bad arguments. */
 int sb_shard_range(size_t n_total, int nparts, int part, size_t *base, size_t *own, size_t *len);
 size_t sb_text_length(const sb_text *t);
-/* collision entropy per byte, -log2(sum p_c^2), of a sampled byte histogram taken when the text was
- * created; drives the choice of candidate filter (a B-byte fingerprint passes ~2^-(B*bits) of positions) */
+/* selectivity estimate per text byte (mean of the collision entropy and the min-entropy of a sampled byte
+ * histogram taken when the text was created; log2(sigma) for uniform texts); drives the choice of candidate
+ * filter (a B-byte fingerprint passes ~2^-(B*bits) of positions) */
 double sb_text_entropy_bits(const sb_text *t);
 int sb_text_shards(const sb_text *t);
 /* copy text bytes [off, off+len) back to the host (tests, pattern extraction) */
@@ -109,8 +110,9 @@ void sb_host_free(void *p);
 /* ---- the search hot path ---- */
 /* Extended entry (64-bit n and count; SURVEY.md section 8b "Extended ABI").
  * Returns the occurrence count (>=0), SB_NOT_APPLICABLE, or an SB_ERR_* code.
- * positions/cap are used only with SB_FLAG_POSITIONS: at most `cap` positions are written,
- * ascending; the return value is still the full count.
+ * positions/cap are used only with SB_FLAG_POSITIONS: the min(count, cap) SMALLEST occurrence positions
+ * are written, ascending (sorted on the device); the return value is still the full count.  When the
+ * count exceeds `cap` the text is scanned a second time with an exactly sized sink.
  * *pre_ms  = table build + upload (wall, ms)   -> replaces *pre_time (main.h:30)
  * *run_ms  = scan incl. count read-back (ms)   -> replaces *run_time (main.h:31); never left 0 */
 long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m, unsigned flags,

@@ -17,6 +17,9 @@
 #include <cstring>
 #include <ctime>
 #include <mutex>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
 
 namespace {
 
@@ -70,7 +73,10 @@ struct DevCtx {                               // per-device scratch, created on 
     unsigned long long *h_counters = nullptr; // pinned mirror
     uint32_t *h_pat = nullptr;                // pinned staging for the pattern
     unsigned long long *d_pos = nullptr;      // position sink, grown on demand
+    unsigned long long *d_pos_alt = nullptr;  // radix-sort output (same capacity)
     size_t pos_cap = 0;
+    void *d_sort_temp = nullptr;              // cub::DeviceRadixSort scratch
+    size_t sort_temp_bytes = 0;
     int occ_block[4] = {0, 0, 0, 0};          // resident CTAs/SM for scan_block<4,8,16,32>
     int occ_window[24] = {0};                 // ... for scan_window<NW,OFF,DENSE>, index window_index()
     int occ_short[6] = {0, 0, 0, 0, 0, 0};    // ... for scan_short<MODE, FULL>
@@ -168,18 +174,23 @@ struct Shard {
     size_t len = 0;       // valid bytes in the buffer (own + halo, clipped to the text end)
 };
 
-/* collision entropy per byte, -log2(sum p_c^2): the probability that two independent text bytes are
- * equal is 2^-bits, so a B-byte fingerprint passes a random position with probability ~2^-(B*bits) */
+/* Selectivity estimate per text byte from a byte histogram.  For a uniform alphabet both terms are log2(sigma).
+ * The collision entropy H2 = -log2(sum p_c^2) gives the MEAN rate at which a text gram equals a pattern gram
+ * (patterns are cut from the text); the min-entropy -log2(max p_c) bounds the worst pattern (all its bytes the
+ * most frequent symbol) and also stands in for the inter-byte dependence of natural text that a byte
+ * histogram cannot see.  The estimate is their mean: English text gives ~3.3 bits (H2 4.1, Hmin 2.5), so a
+ * 4-byte fingerprint (13 bits) is judged too weak there and the 8-byte window is used instead. */
 double collision_bits(const unsigned long long *hist)
 {
-    double tot = 0, s2 = 0;
+    double tot = 0, s2 = 0, pmax = 0;
     for (int c = 0; c < 256; c++) tot += (double)hist[c];
     if (tot <= 0) return 8.0;
     for (int c = 0; c < 256; c++) {
         const double p = (double)hist[c] / tot;
         s2 += p * p;
+        if (p > pmax) pmax = p;
     }
-    double bits = -log2(s2);
+    double bits = 0.5 * (-log2(s2) - log2(pmax));
     if (bits < 0.05) bits = 0.05;
     return bits > 8.0 ? 8.0 : bits;
 }
@@ -420,10 +431,25 @@ sb_tables *tables_scratch()
     return t;
 }
 
-int cmp_u64(const void *a, const void *b)
+/* grow the position sink (and its sort buffer) of a device to at least `need` entries */
+bool ensure_pos_capacity(DevCtx &c, size_t need)
 {
-    unsigned long long x = *(const unsigned long long *)a, y = *(const unsigned long long *)b;
-    return x < y ? -1 : x > y;
+    if (need < 1) need = 1;
+    if (c.pos_cap >= need) return true;
+    cudaStreamSynchronize(c.stream);
+    if (c.d_pos) cudaFree(c.d_pos);
+    if (c.d_pos_alt) cudaFree(c.d_pos_alt);
+    c.d_pos = c.d_pos_alt = nullptr;
+    c.pos_cap = 0;
+    if (cudaMalloc(&c.d_pos, need * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&c.d_pos_alt, need * sizeof(unsigned long long)) != cudaSuccess) {
+        set_err("cudaMalloc of the position sink failed%s%s");
+        if (c.d_pos) cudaFree(c.d_pos);
+        c.d_pos = nullptr;
+        return false;
+    }
+    c.pos_cap = need;
+    return true;
 }
 
 }  // namespace
@@ -767,11 +793,13 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
     int launched = 0;
     bool dev_first[kMaxShards];
     for (int g = 0; g < t->nshards; g++) {
+        dev_first[g] = true;
+        for (int k = 0; k < g; k++) dev_first[g] = dev_first[g] && (t->sh[k].dev != t->sh[g].dev);
+    }
+    // launch the scan of shard g; positions (global offsets, unsorted) go to the device's sink if asked
+    auto launch_shard = [&](int g, bool with_pos) -> cudaError_t {
         const Shard &s = t->sh[g];
         DevCtx &c = *ctx[g];
-        dev_first[g] = true;
-        for (int k = 0; k < g; k++) dev_first[g] = dev_first[g] && (t->sh[k].dev != s.dev);
-        CU_TRY(cudaSetDevice(s.dev), SB_ERR_CUDA);
         sb::ScanArgs a = pl.args;
         a.text = s.d_text;
         a.pat = c.d_pat;
@@ -780,31 +808,22 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
         long long hi = total_starts - (long long)s.base;
         if (hi > (long long)s.own) hi = (long long)s.own;
         a.hi = hi > 0 ? hi : 0;
-        a.pos = nullptr;
-        a.pos_cap = 0;
-        if (want_pos && a.hi > 0) {
-            // a device shared by several shards (tests) appends to one sink
-            size_t need = std::min((size_t)cap, (size_t)total_starts > 0 ? (size_t)total_starts : 0);
-            if (need < 1) need = 1;
-            if (c.pos_cap < need) {
-                CU_TRY(cudaStreamSynchronize(c.stream), SB_ERR_CUDA);
-                if (c.d_pos) cudaFree(c.d_pos);
-                c.d_pos = nullptr;
-                c.pos_cap = 0;
-                if (cudaMalloc(&c.d_pos, need * sizeof(unsigned long long)) != cudaSuccess) {
-                    set_err("cudaMalloc of the position sink failed%s%s");
-                    return SB_ERR_NOMEM;
-                }
-                c.pos_cap = need;
-            }
-            a.pos = c.d_pos;
-            a.pos_cap = need;
+        a.pos = with_pos ? c.d_pos : nullptr;
+        a.pos_cap = with_pos ? c.pos_cap : 0;
+        if (a.hi <= 0) return cudaSuccess;
+        launched++;
+        return launch_scan(c, pl, a, c.stream);
+    };
+    const bool collect = want_pos && positions && cap > 0 && total_starts > 0;
+    for (int g = 0; g < t->nshards; g++) {
+        DevCtx &c = *ctx[g];
+        CU_TRY(cudaSetDevice(t->sh[g].dev), SB_ERR_CUDA);
+        if (collect && dev_first[g]) {
+            // first guess for the sink: room for `cap` positions (a device may hold several shards)
+            if (!ensure_pos_capacity(c, std::min((size_t)cap, (size_t)total_starts))) return SB_ERR_NOMEM;
         }
         if (dev_first[g]) CU_TRY(cudaEventRecord(c.e0, c.stream), SB_ERR_CUDA);
-        if (a.hi > 0) {
-            CU_TRY(launch_scan(c, pl, a, c.stream), SB_ERR_CUDA);
-            launched++;
-        }
+        CU_TRY(launch_shard(g, collect), SB_ERR_CUDA);
     }
     for (int g = t->nshards - 1; g >= 0; g--) {
         // last shard of each device records the end event and the counter read-back
@@ -820,7 +839,7 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
     }
     unsigned long long total = 0, verified = 0;
     double kernel_ms = 0;
-    size_t written = 0;
+    int ndev_used = 0;
     for (int g = 0; g < t->nshards; g++) {
         if (!dev_first[g]) continue;
         DevCtx &c = *ctx[g];
@@ -831,25 +850,68 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
         kernel_ms = std::max(kernel_ms, (double)ms);
         total += c.h_counters[0];
         verified += c.h_counters[2];
-        if (want_pos && positions) {
-            // all shards on this device appended to one sink; positions are global offsets
-            size_t have = (size_t)std::min<unsigned long long>(c.h_counters[1], c.pos_cap);
-            size_t take = std::min(have, cap - written);
-            if (take) {
-                // sort needs the full device list: fetch `have`, keep the smallest `take`
-                unsigned long long *tmp = (unsigned long long *)malloc(have * sizeof(unsigned long long));
-                if (!tmp) return SB_ERR_NOMEM;
-                CU_TRY(cudaMemcpy(tmp, c.d_pos, have * sizeof(unsigned long long), cudaMemcpyDeviceToHost),
+        ndev_used++;
+    }
+
+    /* ---- positions: complete the sinks, sort on the device, return the smallest `cap` ascending ---- */
+    if (collect) {
+        std::vector<unsigned long long> merged;  // only used when several devices contribute
+        size_t written = 0;
+        int end_bit = 1;
+        while (end_bit < 64 && (t->n >> end_bit)) end_bit++;
+        for (int g = 0; g < t->nshards; g++) {
+            if (!dev_first[g]) continue;
+            DevCtx &c = *ctx[g];
+            CU_TRY(cudaSetDevice(t->sh[g].dev), SB_ERR_CUDA);
+            size_t found = (size_t)c.h_counters[1];
+            if (found > c.pos_cap) {
+                // the sink overflowed (more occurrences than `cap`): the entries it holds are an arbitrary
+                // subset, so grow it to the exact size and scan this device's shards once more
+                if (!ensure_pos_capacity(c, found)) return SB_ERR_NOMEM;
+                CU_TRY(cudaMemsetAsync(c.d_counters, 0, 4 * sizeof(unsigned long long), c.stream), SB_ERR_CUDA);
+                for (int k = g; k < t->nshards; k++)
+                    if (t->sh[k].dev == t->sh[g].dev) CU_TRY(launch_shard(k, true), SB_ERR_CUDA);
+                CU_TRY(cudaStreamSynchronize(c.stream), SB_ERR_CUDA);
+            }
+            if (!found) continue;
+            size_t temp_bytes = 0;
+            cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, c.d_pos, c.d_pos_alt, found, 0, end_bit, c.stream);
+            if (c.sort_temp_bytes < temp_bytes) {
+                if (c.d_sort_temp) cudaFree(c.d_sort_temp);
+                c.d_sort_temp = nullptr;
+                c.sort_temp_bytes = 0;
+                if (cudaMalloc(&c.d_sort_temp, temp_bytes) != cudaSuccess) {
+                    set_err("cudaMalloc of the sort scratch failed%s%s");
+                    return SB_ERR_NOMEM;
+                }
+                c.sort_temp_bytes = temp_bytes;
+            }
+            CU_TRY(cub::DeviceRadixSort::SortKeys(c.d_sort_temp, temp_bytes, c.d_pos, c.d_pos_alt, found, 0, end_bit,
+                                                  c.stream),
+                   SB_ERR_CUDA);
+            const size_t take = std::min(found, (size_t)cap);
+            if (ndev_used == 1) {
+                CU_TRY(cudaMemcpyAsync(positions, c.d_pos_alt, take * sizeof(unsigned long long),
+                                       cudaMemcpyDeviceToHost, c.stream),
                        SB_ERR_CUDA);
-                qsort(tmp, have, sizeof(unsigned long long), cmp_u64);
-                memcpy(positions + written, tmp, take * sizeof(unsigned long long));
-                free(tmp);
-                written += take;
+                CU_TRY(cudaStreamSynchronize(c.stream), SB_ERR_CUDA);
+                written = take;
+            } else {
+                const size_t old = merged.size();
+                merged.resize(old + take);
+                CU_TRY(cudaMemcpyAsync(merged.data() + old, c.d_pos_alt, take * sizeof(unsigned long long),
+                                       cudaMemcpyDeviceToHost, c.stream),
+                       SB_ERR_CUDA);
+                CU_TRY(cudaStreamSynchronize(c.stream), SB_ERR_CUDA);
             }
         }
+        if (ndev_used > 1) {
+            std::sort(merged.begin(), merged.end());  // each device's list is sorted; devices may interleave shards
+            written = std::min(merged.size(), (size_t)cap);
+            memcpy(positions, merged.data(), written * sizeof(unsigned long long));
+        }
+        (void)written;
     }
-    if (want_pos && positions && t->nshards > 1 && written > 1)
-        qsort(positions, written, sizeof(unsigned long long), cmp_u64);
     const double t3 = now_ms();
 
     g_timing.prep_host_ms = t1 - t0;

@@ -110,6 +110,10 @@ def test_positions_sorted_and_identical(oracle, tname):
                     assert np.array_equal(r.positions, want), (tname, m, a)
                 r = sb.search("bf", t3, x, flags=sb.FLAG_POSITIONS, positions_cap=y.size)
                 assert np.array_equal(r.positions, want), (tname, m, "sharded")
+                if want.size > 3:  # a short buffer receives the SMALLEST positions; the count stays complete
+                    for tt in (t, t3):
+                        r = sb.search("hor", tt, x, flags=sb.FLAG_POSITIONS, positions_cap=3)
+                        assert r.count == want.size and np.array_equal(r.positions, want[:3]), (tname, m)
 
 
 def test_edge_cases(oracle):
