@@ -118,13 +118,22 @@ void sb_host_free(void *p);
 long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m, unsigned flags,
                       unsigned long long *positions, size_t cap, double *pre_ms, double *run_ms);
 
+/* Multi-pattern entry: count `npat` patterns of the SAME length m (stored back
+ * to back, npat*m bytes) in ONE pass over the resident text instead of npat passes — the shape of the driver's
+ * inner loop (smart.c:312: 500 patterns per length).  counts[p] receives the occurrence count of pattern p;
+ * returns their sum, SB_NOT_APPLICABLE, or an SB_ERR_* code.  Falls back to one scan per pattern when no
+ * aligned-block width is selective enough for the whole set (m < 7, tiny alphabets). */
+long long sb_search_multi64(int algo, const sb_text *t, const unsigned char *patterns, int npat, int m, unsigned flags,
+                            unsigned long long *counts, double *pre_ms, double *run_ms);
+
 typedef struct sb_timing {
     double prep_host_ms;   /* host table build */
     double upload_ms;      /* pattern/table H2D */
     double kernel_ms;      /* max over shards of the CUDA-event time of the scan kernel(s) */
     double wall_ms;        /* host wall clock, first launch -> last count on host */
     int kernels_launched;  /* scan kernels launched by the last search (all shards) */
-    int filter_kind;       /* 0 = scan_short, 1 = scan_window8, 4/8/16/32 = scan_block<B>, 108/116/132 = scan_skip<G> */
+    int filter_kind;       /* 0 = scan_short, 1/2/3 = scan_window 8/12/16 B, 4/8/16/32 = scan_block<B>,
+                              108/116/132 = scan_skip<G>, 204/208/216 = scan_multi<B>, -1 = per-pattern fallback */
     unsigned long long verified; /* candidates sent to exact verification (all shards) */
 } sb_timing;
 void sb_last_timing(sb_timing *out);

@@ -31,6 +31,7 @@ from .binding import (  # noqa: F401
     prep_tables,
     search,
     search_host,
+    search_multi,
     shard_range,
     stream_timer_begin,
     stream_timer_end_ms,

@@ -121,6 +121,8 @@ SYMBOLS = [
     ("sb_host_free", None, [C.c_void_p]),
     ("sb_search64", C.c_longlong, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_void_p, C.c_size_t,
                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    ("sb_search_multi64", C.c_longlong, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p,
+                                         C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("sb_last_timing", None, [C.POINTER(Timing)]),
     ("sb_stream_timer_begin", C.c_int, [C.c_int]),
     ("sb_stream_timer_end_ms", C.c_double, [C.c_int]),
@@ -299,6 +301,23 @@ def search(algo: str, text: Text, pattern, flags: int = 0, positions_cap: int = 
     if pos is not None:
         pos = pos[: max(0, min(int(r), positions_cap))]
     return SearchResult(int(r), pre.value, run.value, pos)
+
+
+def search_multi(algo: str, text: Text, patterns, flags: int = 0):
+    """sb_search_multi64: `patterns` is a 2-D uint8 array (npat x m). Returns (counts array, pre_ms, run_ms)."""
+    pats = np.ascontiguousarray(patterns, dtype=np.uint8)
+    if pats.ndim != 2:
+        raise ValueError("patterns must be a 2-D array (npat x m)")
+    npat, m = pats.shape
+    counts = np.zeros(npat, dtype=np.uint64)
+    pre, run = C.c_double(0), C.c_double(0)
+    r = lib().sb_search_multi64(algo_id(algo), text._h, pats.ctypes.data, npat, m, flags, counts.ctypes.data,
+                                C.byref(pre), C.byref(run))
+    if r < -1:
+        raise SmartB200Error(f"sb_search_multi64 failed ({r}): {_err()}")
+    if r == -1:
+        return None, pre.value, run.value
+    return counts, pre.value, run.value
 
 
 def search_host(algo: str, pattern, text, flags: int = 0) -> SearchResult:

@@ -71,12 +71,17 @@ struct ScanArgs {
     const uint32_t *aux;
     unsigned long long nsamples;
     int stride;
+    // scan_multi: npat patterns of the same length, pattern p at pat + p*pat_stride_words; per-pattern
+    // counts at multi_counts[p]; aux = Bloom bitmap + table {fingerprint, ((p << 5) | d) + 1}
+    unsigned long long *multi_counts;
+    int npat, pat_stride_words;
 };
 
 constexpr int kBloomBits = 18;                       // 2^18-bit Bloom bitmap = 32 KiB of shared memory, 2 probes
 constexpr int kBloomWords = (1 << kBloomBits) / 32;
 __host__ __device__ __forceinline__ uint32_t bloom_slot(uint32_t h) { return (h * 0x2545F491u) >> (32 - kBloomBits); }
 __host__ __device__ __forceinline__ uint32_t bloom_slot2(uint32_t h) { return (h * 0x9FB21C65u + 0x7F4A7C15u) >> (32 - kBloomBits); }
+__host__ __device__ __forceinline__ uint32_t bloom_slot3(uint32_t h) { return ((h ^ (h >> 15)) * 0x2C1B3C6Du) >> (32 - kBloomBits); }
 // exact second level: open-addressing table {fingerprint, d+1} (linear probing, 0 = empty) after the bitmap
 constexpr int kSkipTableBits = 13;
 constexpr int kSkipTableSize = 1 << kSkipTableBits;   // 8192 entries >= 2 x 4193 grams
@@ -118,14 +123,15 @@ __device__ __forceinline__ uint32_t text_window32(const uint8_t *text, long long
 
 /* Exact comparison of x[0..m) with text[j..j+m), one 32-bit window per lane per step.
  * All 32 lanes must call it with the same j. */
-__device__ __forceinline__ bool warp_verify(const ScanArgs &a, long long j, unsigned lane)
+__device__ __forceinline__ bool warp_verify(const ScanArgs &a, long long j, unsigned lane, const uint32_t *pat = nullptr)
 {
     const int nwords = a.nwords;
+    if (!pat) pat = a.pat;
     for (int base = 0; base < nwords; base += 32) {
         const int k = base + (int)lane;
         bool ok = true;
         if (k < nwords) {
-            uint32_t diff = text_window32(a.text, j + 4ll * k) ^ __ldg(a.pat + k);
+            uint32_t diff = text_window32(a.text, j + 4ll * k) ^ __ldg(pat + k);
             if (k == nwords - 1) diff &= a.tailmask;
             ok = (diff == 0);
         }
@@ -515,6 +521,113 @@ __global__ void __launch_bounds__(kThreads) scan_skip_kernel(const __grid_consta
         }
     }
     block_reduce_count(a, cnt, nver);
+}
+
+
+/* ===================================================================== scan_multi<B> */
+
+/* Multi-pattern scan: ALL `npat` patterns of one length are counted in ONE pass over
+ * the text.  Same aligned-block argument as scan_block, but instead of comparing a block fingerprint with
+ * the B fingerprints of one pattern it is looked up in a 3-probe Bloom bitmap (shared memory) holding the
+ * npat*B fingerprints of all patterns; hits are resolved in the exact table {fingerprint, (pattern, d)} and
+ * verified against that pattern; counts are kept per pattern. */
+template <int B>
+__device__ __noinline__ unsigned multi_candidates(const ScanArgs &a, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3,
+                                                  uint32_t v4, uint32_t v5, uint32_t v6, uint32_t v7, long long voff,
+                                                  unsigned hitmask, unsigned lane)
+{
+    const uint32_t vw[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
+    const uint2 *table = reinterpret_cast<const uint2 *>(a.aux + kBloomWords);
+    unsigned nver = 0;
+    unsigned pending = __ballot_sync(kFull, hitmask != 0);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        uint32_t s[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = __shfl_sync(kFull, vw[i], src);
+        const long long soff = __shfl_sync(kFull, voff, src);
+        unsigned blocks = __shfl_sync(kFull, hitmask, src);  // bit k: block k of the vector hit the bitmap
+        while (blocks) {
+            const int blk = __ffs(blocks) - 1;
+            blocks &= blocks - 1;
+            uint32_t h;
+            if (B == 4) {
+                h = s[0];
+#pragma unroll
+                for (int i = 1; i < 8; i++) h = (blk == i) ? s[i] : h;
+            } else if (B == 8) {
+                h = fp8(s[0], s[1]);
+#pragma unroll
+                for (int i = 1; i < 4; i++) h = (blk == i) ? fp8(s[2 * i], s[2 * i + 1]) : h;
+            } else {
+                h = blk ? fp16(s[4], s[5], s[6], s[7]) : fp16(s[0], s[1], s[2], s[3]);
+            }
+            const long long t = soff + blk * B;
+            const uint32_t base = table_slot(h);
+            for (int round = 0; round < kSkipTableSize / 32; round++) {
+                const uint2 e = __ldg(table + ((base + round * 32 + lane) & (kSkipTableSize - 1)));
+                const unsigned empty = __ballot_sync(kFull, e.y == 0);
+                unsigned eq = __ballot_sync(kFull, e.y != 0 && e.x == h);
+                if (empty) eq &= (1u << (__ffs(empty) - 1)) - 1u;
+                while (eq) {
+                    const int l = __ffs(eq) - 1;
+                    eq &= eq - 1;
+                    const uint32_t code = __shfl_sync(kFull, e.y, l) - 1;
+                    const int d = (int)(code & 31), pid = (int)(code >> 5);
+                    const long long j = t - d - a.anchor;
+                    if (j >= 0 && j < a.hi) {
+                        nver += (lane == 0);
+                        if (warp_verify(a, j, lane, a.pat + (size_t)pid * a.pat_stride_words) && lane == 0)
+                            atomicAdd(a.multi_counts + pid, 1ull);
+                    }
+                }
+                if (empty) break;
+            }
+        }
+    }
+    return nver;
+}
+
+template <int B, int U>
+__global__ void __launch_bounds__(kThreads) scan_multi_kernel(const __grid_constant__ ScanArgs a)
+{
+    __shared__ uint32_t bloom[kBloomWords];
+    for (int i = threadIdx.x; i < kBloomWords; i += kThreads) bloom[i] = __ldg(a.aux + i);
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long warp = ((unsigned long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * kThreads) >> 5;
+    unsigned nver = 0;
+    constexpr int NB = 32 / B;  // blocks per 32-byte vector
+
+    for (unsigned long long g = warp; g < a.ngroups; g += nwarps) {
+        const uint8_t *p = a.text + g * (U * 1024ull) + lane * 32;
+        V8 v[U];
+#pragma unroll
+        for (int c = 0; c < U; c++) v[c] = ldg_stream256(p + c * 1024);
+#pragma unroll
+        for (int c = 0; c < U; c++) {
+            unsigned hitmask = 0;
+#pragma unroll
+            for (int k = 0; k < NB; k++) {
+                uint32_t h;
+                if (B == 4) h = v[c].w[k];
+                else if (B == 8) h = fp8(v[c].w[2 * k], v[c].w[2 * k + 1]);
+                else h = fp16(v[c].w[4 * k], v[c].w[4 * k + 1], v[c].w[4 * k + 2], v[c].w[4 * k + 3]);
+                const uint32_t s1 = bloom_slot(h), s2 = bloom_slot2(h), s3 = bloom_slot3(h);
+                const uint32_t bit = (bloom[s1 >> 5] >> (s1 & 31)) & (bloom[s2 >> 5] >> (s2 & 31)) &
+                                     (bloom[s3 >> 5] >> (s3 & 31)) & 1u;
+                hitmask |= bit << k;
+            }
+            if (__any_sync(kFull, hitmask != 0)) {
+                const long long voff = (long long)(g * (U * 1024ull)) + c * 1024 + lane * 32;
+                nver += multi_candidates<B>(a, v[c].w[0], v[c].w[1], v[c].w[2], v[c].w[3], v[c].w[4], v[c].w[5],
+                                            v[c].w[6], v[c].w[7], voff, hitmask, lane);
+            }
+        }
+    }
+    block_reduce_count(a, 0u, nver);
 }
 
 /* ===================================================================== scan_short (m <= 4) */

@@ -314,3 +314,36 @@ def test_multi_device_in_process(oracle):
             r1 = sb.search("bm", t1, x, flags=sb.FLAG_POSITIONS, positions_cap=1 << 22)
             if want <= (1 << 22):
                 assert np.array_equal(r.positions, r1.positions)
+
+
+def test_multi_pattern_scan_equals_single_scans(oracle):
+    """sb_search_multi64: a whole pattern set of one length in one pass == one search per pattern."""
+    for sigma in (256, 4, 2):
+        y = sb.textgen_host(0, 4_000_000, sigma, 77)
+        with sb.Text.upload(y) as t, sb.Text.upload(y, devices=[0, 0, 0]) as t3:
+            rng = np.random.default_rng(sigma)
+            for m, npat in ((3, 5), (8, 40), (16, 500), (33, 700), (200, 64), (1024, 20)):
+                offs = rng.integers(0, y.size - m, npat)
+                pats = np.stack([y[o:o + m] for o in offs])
+                pats[-1] = pats[0]           # a duplicate pattern gets the same count
+                if m >= 8:
+                    pats[-2, -1] ^= 0x55     # and a (probably) absent one gets 0 or few
+                want = np.array([oracle.bf_count(p, y) for p in pats], dtype=np.uint64)
+                for algo in ("bf", "hor"):
+                    for tt in (t, t3):
+                        counts, pre, run = sb.search_multi(algo, tt, pats)
+                        assert np.array_equal(counts, want), (sigma, m, npat, algo, tt.shards)
+                        assert run > 0
+                k = sb.last_timing().filter_kind
+                assert k == -1 or k in (204, 208, 216)
+            # not applicable: same rule as the single search
+            counts, _, _ = sb.search_multi("hash8", t, np.stack([y[:5], y[5:10]]))
+            assert counts is None
+    # English-like text, the driver's real shape: 500 patterns of length 16
+    y = make_text("bible64k", oracle)
+    with sb.Text.upload(y) as t:
+        rng = np.random.default_rng(5)
+        pats = np.stack([y[o:o + 16] for o in rng.integers(0, y.size - 16, 500)])
+        counts, _, _ = sb.search_multi("kmp", t, pats)
+        assert np.array_equal(counts, np.array([oracle.bf_count(p, y) for p in pats], dtype=np.uint64))
+        assert counts.min() >= 1
