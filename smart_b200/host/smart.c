@@ -33,6 +33,9 @@
 #include <time.h>
 #include <unistd.h>
 
+#include "sb_client.h"
+#include "sb_proto.h"
+
 #define XSIZE 4200 /* define.h:25 */
 #define SIGMA 256
 #define MAX_ALGOS 500 /* NumAlgo, smart.c:21 */
@@ -59,6 +62,7 @@ typedef struct {
     int limit_ms;   /* -tb */
     unsigned seed;
     int use_worker;
+    int batch;      /* -batch: one worker request per (algorithm, length) for the whole pattern set */
     char bindir[512];
     char datadir[512];
     char resdir[512];
@@ -69,6 +73,7 @@ typedef struct {
 } config;
 
 static segment seg_text, seg_pat, seg_count, seg_time, seg_pre;
+static segment seg_mpat, seg_mcounts; /* -batch: pattern set (npat x m) and per-pattern counts (npat x u64) */
 
 /* Pattern sampling has its own generator (splitmix64) so that a given -seed always yields the same pattern
  * sets: glibc's rand() and random() share one state, and the number of rand() calls spent on picking free
@@ -98,7 +103,9 @@ static void usage(void)
            "\t-bin DIR         directory of the algorithm executables (default: bin/algos next to this binary)\n"
            "\t-data DIR        corpus directory (default data)\n"
            "\t-seed S          seed for pattern sampling (default: time)\n"
-           "\t-noworker        do not start the resident GPU worker\n\n");
+           "\t-noworker        do not start the resident GPU worker\n"
+           "\t-batch           scan the text ONCE per (algorithm, length) for the whole pattern set\n"
+           "\t                 (needs the worker; reported time = time of the pass / number of patterns)\n\n");
 }
 
 /* ---- shared memory: keys are small random integers like the reference's rand()%1000 ---- */
@@ -139,6 +146,8 @@ static void destroy_all(void)
     seg_destroy(&seg_count);
     seg_destroy(&seg_time);
     seg_destroy(&seg_pre);
+    seg_destroy(&seg_mpat);
+    seg_destroy(&seg_mcounts);
 }
 
 /* ---- corpus loading: index.txt with #file# markers (smart.c:95-138) ---- */
@@ -261,6 +270,49 @@ static void worker_stop(const char *selfdir)
     worker_started = 0;
 }
 
+/* -batch: the whole pattern set of length m in one request; returns 0 and fills sum/min of the counts and
+ * the pass times, or -1 (worker unreachable / failed) */
+static int run_batch(const config *cf, const char *algo, int m, long n, unsigned char (*set)[XSIZE + 1],
+                     long long *sum, long long *min_occ, double *pre_ms, double *run_ms)
+{
+    unsigned char *dst = seg_mpat.ptr;
+    unsigned long long *counts = seg_mcounts.ptr;
+    for (int i = 0; i < cf->npat; i++) memcpy(dst + (size_t)i * m, set[i], (size_t)m);
+    memset(counts, 0, (size_t)cf->npat * sizeof *counts);
+    sb_request rq;
+    sb_reply rp;
+    memset(&rq, 0, sizeof rq);
+    rq.magic = SB_PROTO_MAGIC;
+    rq.kind = SB_REQ_SEARCH_MULTI;
+    rq.algo = -1;
+    snprintf(rq.algo_name, sizeof rq.algo_name, "%s", algo);
+    rq.pkey = seg_mpat.key;
+    rq.m = m;
+    rq.tkey = seg_text.key;
+    rq.n = (int)n;
+    rq.npat = cf->npat;
+    rq.ckey = seg_mcounts.key;
+    int fd = sb_worker_connect();
+    if (fd < 0) return -1;
+    int rc = sb_worker_call(fd, &rq, &rp);
+    close(fd);
+    if (rc != 0 || rp.status != 0) return -1;
+    if (rp.count == -1) { /* not applicable */
+        *sum = -1;
+        *min_occ = -1;
+        return 0;
+    }
+    *sum = 0;
+    *min_occ = (long long)counts[0];
+    for (int i = 0; i < cf->npat; i++) {
+        *sum += (long long)counts[i];
+        if ((long long)counts[i] < *min_occ) *min_occ = (long long)counts[i];
+    }
+    *pre_ms = rp.pre_ms + rp.upload_ms;
+    *run_ms = rp.run_ms;
+    return 0;
+}
+
 static void rule(void)
 {
     printf("\t");
@@ -309,6 +361,23 @@ static void run_experiment(const config *cf, const char *label, unsigned char *T
             double sum = 0, sum_pre = 0, best = 1e30, worst = 0;
             long long total_occ = 0;
             int done = 0, verdict = 1; /* 1 ok, 0 [ERROR], -1 [--], -2 [OUT] */
+            if (cf->batch && !simple) {
+                long long min_occ = 0;
+                double pre_b = 0, run_b = 0;
+                if (run_batch(cf, cf->algos[a], m, n, set, &total_occ, &min_occ, &pre_b, &run_b) != 0 || min_occ < 0)
+                    verdict = -1;
+                else if (min_occ == 0)
+                    verdict = 0;
+                else {
+                    const double per = (run_b + (cf->pre ? 0 : pre_b)) / cf->npat;
+                    sum = per * cf->npat;
+                    sum_pre = pre_b;
+                    best = worst = per;
+                    for (int k = 0; k < cf->npat; k++) samples[k] = per;
+                    done = cf->npat;
+                    if (per > cf->limit_ms) verdict = -2;
+                }
+            } else
             for (int k = 0; k < cf->npat; k++) {
                 memcpy(P, set[k], (size_t)m);
                 P[m] = 0; /* smart.c:313 */
@@ -438,6 +507,7 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "-results")) { NEED(1); snprintf(cf.resdir, sizeof cf.resdir, "%s", argv[++i]); }
         else if (!strcmp(a, "-seed")) { NEED(1); cf.seed = (unsigned)strtoul(argv[++i], NULL, 10); }
         else if (!strcmp(a, "-noworker")) cf.use_worker = 0;
+        else if (!strcmp(a, "-batch")) cf.batch = 1;
         else { printf("Error in input parameters. Use -h for help.\n\n"); return 0; }
     }
     if (cf.minlen < 1 || cf.minlen > XSIZE || cf.maxlen < cf.minlen) {
@@ -466,7 +536,18 @@ int main(int argc, char **argv)
     if (seg_create(&seg_count, 4, o4, 4)) { destroy_all(); return 1; }
     unsigned char *T = seg_text.ptr;
 
+    if (cf.batch) {
+        const segment *o5[] = {&seg_text, &seg_time, &seg_pre, &seg_pat, &seg_count};
+        if (seg_create(&seg_mpat, (size_t)cf.npat * XSIZE, o5, 5)) { destroy_all(); return 1; }
+        const segment *o6[] = {&seg_text, &seg_time, &seg_pre, &seg_pat, &seg_count, &seg_mpat};
+        if (seg_create(&seg_mcounts, (size_t)cf.npat * 8, o6, 6)) { destroy_all(); return 1; }
+    }
     worker_start(&cf, selfdir);
+    if (cf.batch && !worker_started) {
+        printf("\t-batch needs the resident GPU worker\n");
+        destroy_all();
+        return 1;
+    }
     if (cf.simple_p) {
         static int one[MAX_LENS];
         const long n = (long)strlen(cf.simple_t);

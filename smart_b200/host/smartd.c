@@ -134,6 +134,62 @@ static void serve_search(const sb_request *rq, sb_reply *rp)
     g_searches++;
 }
 
+/* make sure the resident copy of the text segment (tkey, n) is current; returns 0 or an errno */
+static int ensure_text(int tkey, int n, double *upload_ms)
+{
+    const unsigned char *t = attach(tkey, (size_t)n, &g_text.shmid, g_text.host, g_text.tkey);
+    if (!t) return errno ? errno : ENOENT;
+    const double t0 = now_ms();
+    const uint64_t h = text_hash(t, (size_t)n);
+    if (!g_text.dev || t != g_text.host || g_text.tkey != tkey || g_text.n != (size_t)n || g_text.hash != h) {
+        if (g_text.dev) sb_text_free(g_text.dev);
+        g_text.dev = sb_text_upload(t, (size_t)n, NULL, 1);
+        g_text.host = t;
+        g_text.tkey = tkey;
+        g_text.n = (size_t)n;
+        g_text.hash = h;
+        g_uploads++;
+        if (!g_text.dev) {
+            fprintf(stderr, "smartd: text upload failed: %s\n", sb_last_error());
+            return EIO;
+        }
+        *upload_ms = now_ms() - t0;
+    }
+    return 0;
+}
+
+/* SEARCH_MULTI: the whole pattern set of one length in one pass (sb_search_multi64) */
+static void serve_multi(const sb_request *rq, sb_reply *rp)
+{
+    rp->status = 0;
+    if (rq->m < 1 || rq->m > SB_XSIZE || rq->n < 0 || rq->npat < 1) {
+        rp->status = EINVAL;
+        return;
+    }
+    int pid = shmget((key_t)rq->pkey, (size_t)rq->npat * (size_t)rq->m, 0666);
+    int cid = shmget((key_t)rq->ckey, (size_t)rq->npat * sizeof(uint64_t), 0666);
+    const unsigned char *pats = pid >= 0 ? shmat(pid, NULL, SHM_RDONLY) : (void *)-1;
+    unsigned long long *counts = cid >= 0 ? shmat(cid, NULL, 0) : (void *)-1;
+    if (pats == (void *)-1 || counts == (void *)-1) {
+        rp->status = errno ? errno : ENOENT;
+    } else if ((rp->status = ensure_text(rq->tkey, rq->n, &rp->upload_ms)) == 0) {
+        char name[sizeof rq->algo_name + 1];
+        memcpy(name, rq->algo_name, sizeof rq->algo_name);
+        name[sizeof rq->algo_name] = 0;
+        const int algo = rq->algo >= 0 ? rq->algo : sb_algo_id(name);
+        long long c = sb_search_multi64(algo, g_text.dev, pats, rq->npat, rq->m, 0, counts, &rp->pre_ms, &rp->run_ms);
+        if (c < -1) {
+            fprintf(stderr, "smartd: multi search failed: %s\n", sb_last_error());
+            rp->status = EIO;
+        } else {
+            rp->count = c;
+            g_searches += (uint64_t)rq->npat;
+        }
+    }
+    if (pats != (void *)-1) shmdt(pats);
+    if (counts != (void *)-1) shmdt(counts);
+}
+
 static int listen_on(const char *path)
 {
     struct sockaddr_un sa;
@@ -158,7 +214,7 @@ static int simple_request(int kind)
         fprintf(stderr, "smartd: no worker is listening\n");
         return 1;
     }
-    sb_request rq = {SB_PROTO_MAGIC, kind, 0, 0, 0, 0, 0, 0};
+    sb_request rq = {SB_PROTO_MAGIC, kind, 0, 0, 0, 0, 0, 0, 0, 0, ""};
     sb_reply rp;
     int rc = sb_worker_call(fd, &rq, &rp);
     close(fd);
@@ -261,6 +317,7 @@ int main(int argc, char **argv)
         int quit = 0;
         if (got == sizeof rq && rq.magic == SB_PROTO_MAGIC) {
             if (rq.kind == SB_REQ_SEARCH) serve_search(&rq, &rp);
+            else if (rq.kind == SB_REQ_SEARCH_MULTI) serve_multi(&rq, &rp);
             else if (rq.kind == SB_REQ_QUIT) quit = 1;
             rp.searches = g_searches;
             rp.text_uploads = g_uploads;

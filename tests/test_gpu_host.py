@@ -103,3 +103,23 @@ def test_worker_uploads_text_once_per_text(tmp_path, worker):
     searches, uploads = stats(worker)
     assert searches == 2 * 2 * 2 * 5
     assert uploads == 2  # one per text, although the shm key and n are identical for t1 and t2
+
+
+def test_driver_batch_mode_matches_per_pattern_mode(tmp_path):
+    """-batch: one pass of the resident text per (algorithm, length) for the whole pattern set; the
+    occurrence columns must equal the process-per-search run with the same seed."""
+    data = tmp_path / "data" / "mini"
+    data.mkdir(parents=True)
+    text = open(os.path.join(ROOT, "tests", "golden", "bible64k.bin"), "rb").read()
+    (data / "a.txt").write_bytes(text)
+    (data / "index.txt").write_text("#a.txt#\n")
+    env = {**os.environ, "SMART_B200_SOCK": str(tmp_path / "b.sock")}
+    common = ["-text", "mini", "-data", str(tmp_path / "data"), "-pset", "40", "-plen", "2", "32", "-short", "-occ",
+              "-seed", "23", "-algo", "bf,kmp,hor,hash3"]
+    single = run([os.path.join(BIN, "smart"), *common], cwd=tmp_path, env=env)
+    batch = run([os.path.join(BIN, "smart"), *common, "-batch"], cwd=tmp_path, env=env)
+    assert single.returncode == 0 and batch.returncode == 0, (single.stderr, batch.stderr)
+    occ = lambda s: re.findall(r"\] (\w+) \.+\[(\w+|--)\](?:.*?occ (\d+))?", s)
+    a, b = occ(single.stdout), occ(batch.stdout)
+    assert len(a) == 16 * 4 and a == b, [(x, y) for x, y in zip(a, b) if x != y][:5]
+    assert sum(1 for x in b if x[1] == "--") == 1  # hash3 at m=2
