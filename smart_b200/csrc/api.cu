@@ -57,7 +57,7 @@ constexpr size_t kPatBytes = 4352;            // device pattern buffer (>= SB_XS
 constexpr int kU = SB_U;                      // 256-bit loads in flight per thread (scan_block / scan_window8)
 constexpr size_t kGroupLong = kU * 1024;      // bytes per warp iteration of those kernels
 constexpr size_t kGroupShort = 4 * 512;       // ... of scan_short
-constexpr int kFilterShort = 0, kFilterWindow8 = 1, kFilterWindow12 = 2, kFilterWindow16 = 3;
+constexpr int kFilterShort = 0, kFilterWindow8 = 1, kFilterWindow16 = 3;  // 2 = the 12-byte window
 constexpr int kFilterSkip = 100;              // + gram bytes (108, 116, 132): scan_skip<G>
 constexpr size_t kAuxWords = sb::kBloomWords + 2 * sb::kSkipTableSize;
 

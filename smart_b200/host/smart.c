@@ -58,7 +58,7 @@ typedef struct {
     int minlen, maxlen;
     int npat;       /* -pset */
     long tsize;     /* bytes */
-    int occ, pre, dif, std, txt;
+    int occ, pre, dif, std, txt, xml;
     int limit_ms;   /* -tb */
     unsigned seed;
     int use_worker;
@@ -97,6 +97,7 @@ static void usage(void)
            "\t-tsize S         text size in MB (default 1)\n"
            "\t-tb MS           time bound per cell in ms (default 300)\n"
            "\t-occ -pre -dif -std -txt   as in SMART\n"
+           "\t-xml             also write results/<code>/<text>.xml (schema of SMART's outputXML)\n"
            "\t-simple P T      one search of pattern P in text T\n"
            "\t-algo a,b,c      algorithms to run (default bf,kmp,hor,so)\n"
            "\t-alist FILE      read the selection from a SMART registry file (#1 #name lines)\n"
@@ -452,6 +453,40 @@ static void run_experiment(const config *cf, const char *label, unsigned char *T
             fclose(f);
         }
     }
+    if (cf->xml && !simple) { /* output.h:196-245: RESULTS/CODE/TEXT, one ALGO block per algorithm, BEST per length */
+        char path[1024];
+        snprintf(path, sizeof path, "%s/%s", cf->resdir, cf->code);
+        mkdir(cf->resdir, 0775);
+        mkdir(path, 0775);
+        snprintf(path, sizeof path, "%s/%s/%s.xml", cf->resdir, cf->code, label);
+        FILE *f = fopen(path, "w");
+        if (f) {
+            printf("\tSaving data on %s/%s.xml\n", cf->code, label);
+            fprintf(f, "<RESULTS>\n\t<CODE>%s</CODE>\n\t<TEXT>%s</TEXT>\n", cf->code, label);
+            for (int a = 0; a < cf->nalgo; a++) {
+                char up[32];
+                snprintf(up, sizeof up, "%s", cf->algos[a]);
+                for (char *q = up; *q; q++) *q = (char)toupper((unsigned char)*q);
+                fprintf(f, "\t<ALGO>\n\t\t<NAME>%s</NAME>\n", up);
+                for (int il = 0; il < MAX_LENS && cf->lens[il] > 0; il++) {
+                    if (cf->lens[il] < cf->minlen || cf->lens[il] > cf->maxlen) continue;
+                    if (mean[a][il] == 0) fprintf(f, "\t\t<DATA>-</DATA>\n");
+                    else fprintf(f, "\t\t<DATA>\n\t\t\t<SEARCH>%.4f</SEARCH>\n\t\t</DATA>\n", mean[a][il]);
+                }
+                fprintf(f, "\t</ALGO>\n");
+            }
+            fprintf(f, "\t<BEST>\n");
+            for (int il = 0; il < MAX_LENS && cf->lens[il] > 0; il++) {
+                if (cf->lens[il] < cf->minlen || cf->lens[il] > cf->maxlen) continue;
+                double best = 0;
+                for (int a = 0; a < cf->nalgo; a++)
+                    if (mean[a][il] > 0 && (best == 0 || mean[a][il] < best)) best = mean[a][il];
+                fprintf(f, "\t\t<DATA>%.4f</DATA>\n", best);
+            }
+            fprintf(f, "\t</BEST>\n</RESULTS>");
+            fclose(f);
+        }
+    }
     free(set);
     free(samples);
 }
@@ -498,6 +533,7 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "-dif")) cf.dif = 1;
         else if (!strcmp(a, "-std")) cf.std = 1;
         else if (!strcmp(a, "-txt")) cf.txt = 1;
+        else if (!strcmp(a, "-xml")) cf.xml = 1;
         else if (!strcmp(a, "-short")) cf.lens = LEN_SHORT;
         else if (!strcmp(a, "-vshort")) cf.lens = LEN_VERY_SHORT;
         else if (!strcmp(a, "-algo")) { NEED(1); add_algos_csv(&cf, argv[++i]); }

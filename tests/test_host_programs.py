@@ -89,7 +89,7 @@ def test_our_driver_drives_reference_executables(tmp_path):
     (data / "index.txt").write_text("#part1.txt#\n#part2.txt#\n")
     r = run([os.path.join(BIN, "smart"), "-text", "mini", "-data", str(tmp_path / "data"), "-results",
              str(tmp_path / "results"), "-pset", "3", "-plen", "2", "16", "-short", "-algo", "bf,kmp,hash3,raita",
-             "-bin", REFBIN, "-occ", "-pre", "-dif", "-std", "-txt", "-seed", "5", "-noworker"], cwd=tmp_path)
+             "-bin", REFBIN, "-occ", "-pre", "-dif", "-std", "-txt", "-xml", "-seed", "5", "-noworker"], cwd=tmp_path)
     assert r.returncode == 0, r.stderr
     out = r.stdout
     assert "Text buffer of dimension 65536 byte" in out
@@ -109,6 +109,9 @@ def test_our_driver_drives_reference_executables(tmp_path):
     rows = txt[0].read_text().splitlines()
     assert [row.split()[0] for row in rows] == ["BF", "KMP", "HASH3", "RAITA"]
     assert rows[2].split()[1] == "-"  # hash3 @ m=2: no result
+    xml = list((tmp_path / "results").glob("EXP*/mini.xml"))[0].read_text()
+    assert xml.startswith("<RESULTS>") and xml.count("<ALGO>") == 4 and xml.count("<NAME>HASH3</NAME>") == 1
+    assert xml.count("<DATA>-</DATA>") == 1 and xml.count("<SEARCH>") == 8 * 4 - 1 and "<BEST>" in xml
     # -simple mode (smart.c:496-507)
     r = run([os.path.join(BIN, "smart"), "-simple", "aba", "ababababab", "-algo", "bf", "-bin", REFBIN, "-occ",
              "-noworker"], cwd=tmp_path)
