@@ -328,8 +328,11 @@ __device__ __noinline__ uint2 window_matches(const ScanArgs &a, unsigned mm, lon
  * pattern EXACTLY, so a window match is an occurrence.  Wider windows are for low-entropy texts (sigma=2)
  * where 8 bytes are not selective.  DENSE (window == pattern, frequent matches): every position is compared
  * exactly and counted in registers, no branch. */
+/* register caps (measured, sigma=4 m=8 and sigma=2 m=16 on 4 GiB): unconstrained the kernels take 83+
+ * registers = 2 CTAs/SM (5.7 / 5.1 TB/s); two-word windows fit 64 registers = 4 CTAs/SM (6.7 TB/s), the
+ * 12/16-byte windows spill at 64 and are best at 80 registers = 3 CTAs/SM (5.45 TB/s) */
 template <int NW, int OFF, bool DENSE, int U>
-__global__ void __launch_bounds__(kThreads, SB_MINB) scan_window_kernel(const __grid_constant__ ScanArgs a)
+__global__ void __launch_bounds__(kThreads, NW == 2 ? 4 : 3) scan_window_kernel(const __grid_constant__ ScanArgs a)
 {
     constexpr int LAST = 4 * (NW - 2) + OFF;     // byte offset of the last window word
     constexpr int NS = 32 + LAST;                // shifted words needed: byte offsets 0 .. 31+LAST
