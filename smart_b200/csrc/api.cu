@@ -79,7 +79,7 @@ struct DevCtx {                               // per-device scratch, created on 
     size_t sort_temp_bytes = 0;
     int occ_block[4] = {0, 0, 0, 0};          // resident CTAs/SM for scan_block<4,8,16,32>
     int occ_window[24] = {0};                 // ... for scan_window<NW,OFF,DENSE>, index window_index()
-    int occ_short[6] = {0, 0, 0, 0, 0, 0};    // ... for scan_short<MODE, FULL>
+    int occ_short[7] = {0, 0, 0, 0, 0, 0, 0}; // ... for scan_short<MODE, FULL>; [6] = packed m=1
     unsigned long long *d_hist = nullptr;     // 256-bin byte histogram scratch
     uint32_t *d_aux = nullptr, *h_aux = nullptr; // scan_skip / scan_multi: Bloom bitmap + exact fingerprint table
     uint32_t *d_mpat = nullptr;               // scan_multi: pattern set (words), grown on demand
@@ -167,6 +167,7 @@ DevCtx *get_ctx(int dev)
     c.occ_short[3] = occupancy(sb::scan_short_kernel<1, true>);
     c.occ_short[4] = occupancy(sb::scan_short_kernel<2, false>);
     c.occ_short[5] = occupancy(sb::scan_short_kernel<2, true>);
+    c.occ_short[6] = occupancy(sb::scan_short_kernel<3, false>);
     c.ready = true;
     return &c;
 }
@@ -361,8 +362,8 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
     if (pl.filter == kFilterShort) {
         group = kGroupShort;
         a.ngroups = ((unsigned long long)a.hi + group - 1) / group;
-        const int mode = pl.sparse ? 2 : (want_pos ? 1 : 0);
-        per_sm = c.occ_short[mode * 2 + (a.m == 4 ? 1 : 0)];
+        const int mode = pl.sparse ? 2 : (want_pos ? 1 : (a.m == 1 ? 3 : 0));
+        per_sm = mode == 3 ? c.occ_short[6] : c.occ_short[mode * 2 + (a.m == 4 ? 1 : 0)];
     } else if (pl.filter <= kFilterWindow16) {
         group = kGroupLong;
         a.ngroups = ((unsigned long long)a.hi + group - 1) / group;
@@ -378,9 +379,10 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
     unsigned long long maxb = (unsigned long long)c.sms * per_sm;
     unsigned grid = (unsigned)std::max(1ull, std::min(want, maxb));
     if (pl.filter == kFilterShort) {
-        const int mode = pl.sparse ? 2 : (want_pos ? 1 : 0);
+        const int mode = pl.sparse ? 2 : (want_pos ? 1 : (a.m == 1 ? 3 : 0));
         const bool full = a.m == 4;
-        if (mode == 0 && !full) sb::scan_short_kernel<0, false><<<grid, sb::kThreads, 0, stream>>>(a);
+        if (mode == 3) sb::scan_short_kernel<3, false><<<grid, sb::kThreads, 0, stream>>>(a);
+        else if (mode == 0 && !full) sb::scan_short_kernel<0, false><<<grid, sb::kThreads, 0, stream>>>(a);
         else if (mode == 0) sb::scan_short_kernel<0, true><<<grid, sb::kThreads, 0, stream>>>(a);
         else if (mode == 1 && !full) sb::scan_short_kernel<1, false><<<grid, sb::kThreads, 0, stream>>>(a);
         else if (mode == 1) sb::scan_short_kernel<1, true><<<grid, sb::kThreads, 0, stream>>>(a);

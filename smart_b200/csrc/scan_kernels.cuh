@@ -651,7 +651,10 @@ __device__ __noinline__ unsigned short_candidates(const ScanArgs &a, unsigned mm
     return cnt;
 }
 
-/* MODE 0: dense  - count every position in registers (no position output);
+/* MODE 3: packed - m == 1 without position output: the four bytes of a word are compared at once with the
+ *                  exact zero-byte test ~(((t & 0x7f..) + 0x7f..) | t | 0x7f..) and counted with POPC
+ *                  (6 ops per 4 positions, no funnel shifts, no halo);
+ * MODE 0: dense  - count every position in registers (no position output);
  * MODE 1: dense  - collect a per-position mask and post-process (position output);
  * MODE 2: sparse - OR-reduce the compares (one ISETP.EQ.OR per position) and only build the mask when some
  *                  position of the vector matched: for texts where a match of m bytes is rare (m*bits >= 18).
@@ -679,7 +682,19 @@ __global__ void __launch_bounds__(kThreads) scan_short_kernel(const __grid_const
                 sx = lane == 0 ? v[c + 1].x : v[c].x;
             else
                 sx = lane == 0 ? gn : v[c].x;
-            const uint32_t nx = __shfl_sync(kFull, sx, (lane + 1) & 31);
+            const long long voff = (long long)(g * (U * 512ull)) + c * 512 + lane * 16;
+            if (MODE == 3 && voff + 16 <= a.hi) {
+                const uint32_t splat = a.X0 * 0x01010101u;
+                const uint32_t w4[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t t = w4[k] ^ splat;
+                    cnt += __popc(~(((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t | 0x7f7f7f7fu));
+                }
+                continue;
+            }
+            // m == 1 needs no halo, and its straddling lanes must not wait in a full-mask shuffle the others skip
+            const uint32_t nx = MODE == 3 ? 0u : __shfl_sync(kFull, sx, (lane + 1) & 31);
             const uint32_t W[5] = {v[c].x, v[c].y, v[c].z, v[c].w, nx};
             uint32_t S[16];
 #pragma unroll
@@ -687,12 +702,11 @@ __global__ void __launch_bounds__(kThreads) scan_short_kernel(const __grid_const
                 const uint32_t lo = (b & 3) ? __funnelshift_r(W[b >> 2], W[(b >> 2) + 1], 8 * (b & 3)) : W[b >> 2];
                 S[b] = FULL ? lo : (lo & a.M0);
             }
-            const long long voff = (long long)(g * (U * 512ull)) + c * 512 + lane * 16;
             if (MODE == 0 && voff + 16 <= a.hi) {
 #pragma unroll
                 for (int b = 0; b < 16; b++) cnt += (S[b] == a.X0);
             } else if (voff < a.hi) {
-                bool any = (MODE != 2);
+                bool any = (MODE != 2);  // MODE 3 reaches this point only for the vector straddling the range end
                 if (MODE == 2) {
 #pragma unroll
                     for (int b = 0; b < 16; b++) any |= (S[b] == a.X0);
