@@ -231,7 +231,7 @@ def main_reference(args, algos, ms):
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print_json(line)
     return 0
 
 
@@ -409,7 +409,7 @@ def main_ours(args, algos, ms):
                       "barrier+synchronize pairs), max over ranks; value_host_clock = same region by the host clock; "
                       "value_kernels_only = sum of per-kernel event times",
         }
-        print(json.dumps(line))
+        print_json(line)
     text.free()
     if dist is not None:
         dist.destroy_process_group()
@@ -462,9 +462,19 @@ def main():
     args = parse_args()
     ms = [int(v) for v in args.ms.split(",")]
     algos = args.algos.split(",")
+    # stdout must carry exactly ONE JSON line: libraries (e.g. the NCCL version banner) print to fd 1, so
+    # everything else is sent to stderr and the JSON line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global print_json
+    print_json = lambda obj: os.write(real_stdout, (json.dumps(obj) + "\n").encode())
     if args.impl == "reference":
         return main_reference(args, algos, ms)
     return main_ours(args, algos, ms)
+
+
+print_json = lambda obj: print(json.dumps(obj))
 
 
 if __name__ == "__main__":

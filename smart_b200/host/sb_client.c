@@ -19,7 +19,9 @@ int sb_client_search(int algo, unsigned char *x, int m, unsigned char *y, int n,
     if (pkey >= 0 && tkey >= 0 && !getenv("SMART_B200_NO_WORKER")) {
         int fd = sb_worker_connect();
         if (fd >= 0) {
-            sb_request rq = {SB_PROTO_MAGIC, SB_REQ_SEARCH, algo, pkey, m, tkey, n, 0, 0, 0, ""};
+            sb_request rq = {SB_PROTO_MAGIC, SB_REQ_SEARCH, algo, pkey, m, tkey, n, 0, 0, 0, "", 0};
+            const char *gen = getenv("SMART_B200_TEXT_GEN");
+            if (gen) rq.text_gen = strtoull(gen, NULL, 10);
             sb_reply rp;
             int rc = sb_worker_call(fd, &rq, &rp);
             close(fd);

@@ -22,6 +22,9 @@ typedef struct sb_request {
     int32_t ckey; /* SEARCH_MULTI: SysV key of the per-pattern count segment (npat x uint64) */
     int32_t reserved;
     char algo_name[24]; /* used when algo < 0 (the driver does not link the library's registry) */
+    uint64_t text_gen;  /* non-zero: the sender vouches that (tkey, n, text_gen) identifies the text content
+                           (our driver exports SMART_B200_TEXT_GEN after every text load); zero: the worker
+                           hashes the text to detect a change (unmodified SMART driver) */
 } sb_request;
 
 typedef struct sb_reply {

@@ -293,6 +293,10 @@ static int run_batch(const config *cf, const char *algo, int m, long n, unsigned
     rq.n = (int)n;
     rq.npat = cf->npat;
     rq.ckey = seg_mcounts.key;
+    {
+        const char *gen = getenv("SMART_B200_TEXT_GEN");
+        rq.text_gen = gen ? strtoull(gen, NULL, 10) : 0;
+    }
     int fd = sb_worker_connect();
     if (fd < 0) return -1;
     int rc = sb_worker_call(fd, &rq, &rp);
@@ -608,6 +612,12 @@ int main(int argc, char **argv)
                 continue;
             }
             printf("\tText buffer of dimension %ld byte\n", n);
+            {   /* tell the worker (through the algorithm executables' environment) that the text changed */
+                static unsigned long long text_gen;
+                char gen[40];
+                snprintf(gen, sizeof gen, "%llu", ((unsigned long long)getpid() << 24) | ++text_gen);
+                setenv("SMART_B200_TEXT_GEN", gen, 1);
+            }
             run_experiment(&cf, buf, T, n);
         }
     }

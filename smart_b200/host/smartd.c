@@ -69,10 +69,10 @@ static uint64_t text_hash(const unsigned char *t, size_t n)
 static struct {
     int tkey, shmid;
     size_t n;
-    uint64_t hash;
+    uint64_t hash, gen;
     const unsigned char *host; /* attachment */
     sb_text *dev;
-} g_text = {-1, -1, 0, 0, NULL, NULL};
+} g_text = {-1, -1, 0, 0, 0, NULL, NULL};
 
 static struct {
     int pkey, shmid;
@@ -93,6 +93,8 @@ static const unsigned char *attach(int key, size_t size, int *shmid_io, const un
     return p;
 }
 
+static int ensure_text(int tkey, int n, uint64_t gen, double *upload_ms);
+
 static void serve_search(const sb_request *rq, sb_reply *rp)
 {
     rp->status = 0;
@@ -102,28 +104,11 @@ static void serve_search(const sb_request *rq, sb_reply *rp)
     }
     g_pat.host = attach(rq->pkey, (size_t)rq->m, &g_pat.shmid, g_pat.host, g_pat.pkey);
     g_pat.pkey = rq->pkey;
-    const unsigned char *t = attach(rq->tkey, (size_t)rq->n, &g_text.shmid, g_text.host, g_text.tkey);
-    if (!g_pat.host || !t) {
+    if (!g_pat.host) {
         rp->status = errno ? errno : ENOENT;
         return;
     }
-    const double t0 = now_ms();
-    const uint64_t h = text_hash(t, (size_t)rq->n);
-    if (!g_text.dev || t != g_text.host || g_text.tkey != rq->tkey || g_text.n != (size_t)rq->n || g_text.hash != h) {
-        if (g_text.dev) sb_text_free(g_text.dev);
-        g_text.dev = sb_text_upload(t, (size_t)rq->n, NULL, 1);
-        g_text.host = t;
-        g_text.tkey = rq->tkey;
-        g_text.n = (size_t)rq->n;
-        g_text.hash = h;
-        g_uploads++;
-        if (!g_text.dev) {
-            fprintf(stderr, "smartd: text upload failed: %s\n", sb_last_error());
-            rp->status = EIO;
-            return;
-        }
-        rp->upload_ms = now_ms() - t0;
-    }
+    if ((rp->status = ensure_text(rq->tkey, rq->n, rq->text_gen, &rp->upload_ms)) != 0) return;
     long long c = sb_search64(rq->algo, g_text.dev, g_pat.host, rq->m, 0, NULL, 0, &rp->pre_ms, &rp->run_ms);
     if (c < -1) {
         fprintf(stderr, "smartd: search failed: %s\n", sb_last_error());
@@ -135,19 +120,22 @@ static void serve_search(const sb_request *rq, sb_reply *rp)
 }
 
 /* make sure the resident copy of the text segment (tkey, n) is current; returns 0 or an errno */
-static int ensure_text(int tkey, int n, double *upload_ms)
+static int ensure_text(int tkey, int n, uint64_t gen, double *upload_ms)
 {
     const unsigned char *t = attach(tkey, (size_t)n, &g_text.shmid, g_text.host, g_text.tkey);
     if (!t) return errno ? errno : ENOENT;
     const double t0 = now_ms();
-    const uint64_t h = text_hash(t, (size_t)n);
-    if (!g_text.dev || t != g_text.host || g_text.tkey != tkey || g_text.n != (size_t)n || g_text.hash != h) {
+    /* a sender-provided generation number identifies the content; otherwise hash the text */
+    const uint64_t h = gen ? 0 : text_hash(t, (size_t)n);
+    if (!g_text.dev || t != g_text.host || g_text.tkey != tkey || g_text.n != (size_t)n || g_text.gen != gen ||
+        g_text.hash != h) {
         if (g_text.dev) sb_text_free(g_text.dev);
         g_text.dev = sb_text_upload(t, (size_t)n, NULL, 1);
         g_text.host = t;
         g_text.tkey = tkey;
         g_text.n = (size_t)n;
         g_text.hash = h;
+        g_text.gen = gen;
         g_uploads++;
         if (!g_text.dev) {
             fprintf(stderr, "smartd: text upload failed: %s\n", sb_last_error());
@@ -172,7 +160,7 @@ static void serve_multi(const sb_request *rq, sb_reply *rp)
     unsigned long long *counts = cid >= 0 ? shmat(cid, NULL, 0) : (void *)-1;
     if (pats == (void *)-1 || counts == (void *)-1) {
         rp->status = errno ? errno : ENOENT;
-    } else if ((rp->status = ensure_text(rq->tkey, rq->n, &rp->upload_ms)) == 0) {
+    } else if ((rp->status = ensure_text(rq->tkey, rq->n, rq->text_gen, &rp->upload_ms)) == 0) {
         char name[sizeof rq->algo_name + 1];
         memcpy(name, rq->algo_name, sizeof rq->algo_name);
         name[sizeof rq->algo_name] = 0;
@@ -214,7 +202,7 @@ static int simple_request(int kind)
         fprintf(stderr, "smartd: no worker is listening\n");
         return 1;
     }
-    sb_request rq = {SB_PROTO_MAGIC, kind, 0, 0, 0, 0, 0, 0, 0, 0, ""};
+    sb_request rq = {SB_PROTO_MAGIC, kind, 0, 0, 0, 0, 0, 0, 0, 0, "", 0};
     sb_reply rp;
     int rc = sb_worker_call(fd, &rq, &rp);
     close(fd);
