@@ -294,7 +294,7 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
 {
     memset(&pl.args, 0, sizeof pl.args);
     pl.filter = choose_filter(m, flags, bits);
-    pl.sparse = m * bits >= 18.0 && !(flags & SB_FLAG_DENSE);  // scan_short; scan_window decides below
+    pl.sparse = m * bits >= dense_bits() && !(flags & SB_FLAG_DENSE);  // scan_short; scan_window decides below
     pl.skip_grams = 0;
     sb::ScanArgs &a = pl.args;
     a.m = m;

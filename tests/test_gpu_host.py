@@ -123,3 +123,10 @@ def test_driver_batch_mode_matches_per_pattern_mode(tmp_path):
     a, b = occ(single.stdout), occ(batch.stdout)
     assert len(a) == 16 * 4 and a == b, [(x, y) for x, y in zip(a, b) if x != y][:5]
     assert sum(1 for x in b if x[1] == "--") == 1  # hash3 at m=2
+
+
+def test_plain_c_client_of_the_abi():
+    """tests/c/abi_demo.c: a C program against include/smart_b200.h only (no Python in the loop)."""
+    r = run([os.path.join(BIN, "abi_demo")])
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert r.stdout.count(": ok") == 4 and "FAIL" not in r.stdout

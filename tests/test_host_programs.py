@@ -32,7 +32,7 @@ def test_all_plugin_executables_exist():
 
     for a in sb.ALGORITHMS:
         assert os.access(os.path.join(BIN, "algos", a), os.X_OK), a
-    for p in ("smart", "test", "textgen", "smartd"):
+    for p in ("smart", "test", "textgen", "smartd", "abi_demo"):
         assert os.access(os.path.join(BIN, p), os.X_OK), p
 
 
