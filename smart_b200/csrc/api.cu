@@ -309,11 +309,26 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
             const int stride = ((m - (G - 1)) / 32) * 32;
             if (stride < skip_min_stride()) break;
             if (G * bits < 14.0 + log2((double)stride)) continue;  // P(sampled gram is a pattern gram) <= ~1e-4
+            const int anchor = m - (stride + G - 1);
+            for (int d = 0; d < stride; d++) pl.list[d] = fingerprint(x + anchor + d, G);
+            /* A (nearly) periodic pattern has few DISTINCT grams: every sampled hit would then fan out into
+             * hundreds of candidate alignments resolved by one warp (measured: (ab)^n, m=4096 -> 0.03 GB/s).
+             * Such patterns stay on the read-every-byte kernels, whose candidates spread over all warps. */
+            {
+                uint32_t sorted[4224];
+                memcpy(sorted, pl.list, (size_t)stride * sizeof(uint32_t));
+                std::sort(sorted, sorted + stride);
+                int run = 1, worst = 1;
+                for (int d = 1; d < stride; d++) {
+                    run = sorted[d] == sorted[d - 1] ? run + 1 : 1;
+                    worst = std::max(worst, run);
+                }
+                if (worst > 8) break;
+            }
             pl.filter = kFilterSkip + G;
             pl.skip_grams = stride;
             a.stride = stride;
-            a.anchor = m - (stride + G - 1);
-            for (int d = 0; d < stride; d++) pl.list[d] = fingerprint(x + a.anchor + d, G);
+            a.anchor = anchor;
             return;
         }
     }

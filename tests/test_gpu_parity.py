@@ -227,12 +227,18 @@ def test_skip_kernel_is_selected_and_exact(oracle):
                     assert r.count == want.size and np.array_equal(r.positions, want), (sigma, m, a)
                 assert sb.search("bf", t, x).count == want.size  # prefix family never skips
                 assert sb.last_timing().filter_kind < 100
-    # periodic text: every sample hits, every candidate verifies
+    # periodic pattern: few distinct grams -> stays on the read-every-byte kernels; still exact
     y = np.frombuffer(b"ab" * 40000, dtype=np.uint8)
     with sb.Text.upload(y) as t:
         for m in (80, 200, 1001):
             x = y[:m].copy()
             assert sb.search("hor", t, x).count == oracle.bf_count(x, y)
+            assert sb.last_timing().filter_kind < 100
+    # a pattern with a long period (16 distinct grams per period of 300) may still skip, and is exact
+    y = np.tile(sb.textgen_host(0, 300, 256, 3), 300)
+    with sb.Text.upload(y) as t:
+        x = y[17:17 + 1500].copy()
+        assert sb.search("hor", t, x).count == oracle.bf_count(x, y)
 
 
 def test_generated_text_matches_host_mirror():
