@@ -173,6 +173,8 @@ typedef struct sb_tables {
     int hashQ;                  /* 0 if the algorithm is not a HASHq */
     int krD, krHx;              /* kr.c:34-40 */
     int acEll;                  /* ac.c:52-53 */
+    unsigned int bndmB[SB_SIGMA]; /* bndm.c:33-38 (first min(m,32) chars, reversed) */
+    int brBc[SB_SIGMA * SB_SIGMA]; /* br.c:26-37 == tvsbs.c:26-37, row-major [a][b] */
     int qfQ, qfS;               /* qf<Q><S>.c:28-29; 0 if not a QF */
     int qfB[1 << 18];           /* qf23.c:50-56; entries [0, 1<<(Q*S)) */
 } sb_tables;

@@ -630,6 +630,158 @@ long long ora_search_ac(const unsigned char *x, int m, const unsigned char *y, s
     return count;
 }
 
+/* bndm.c:33-38 / :70-76: masks of the reversed first min(m,32) characters */
+void ora_pre_bndm(const unsigned char *x, int m, unsigned int *B)
+{
+    unsigned int s = 1;
+    if (m > 32) m = 32;
+    for (int c = 0; c < ORA_SIGMA; c++) B[c] = 0;
+    for (int i = m - 1; i >= 0; i--) {
+        B[x[i]] |= s;
+        s <<= 1;
+    }
+}
+
+/* bndm.c:26-60 and search_large :62-110: backward scan of the window with the suffix automaton of the
+ * (32-char prefix of the) pattern; `last` remembers the longest window suffix that is a pattern prefix.
+ * The bounded version rejects prefix matches whose full pattern would cross y[n]. */
+long long ora_search_bndm(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    unsigned int B[ORA_SIGMA];
+    long long count = 0;
+    const int w = m > 32 ? 32 : m;
+    ora_pre_bndm(x, m, B);
+    for (size_t j = 0; j + (size_t)w <= n;) {
+        int i = w - 1, last = w;
+        unsigned int D = ~0u;
+        while (i >= 0 && D != 0) {
+            D &= B[y[j + (size_t)i]];
+            i--;
+            if (D != 0) {
+                if (i >= 0) {
+                    last = i + 1;
+                } else if (j + (size_t)m <= n) {
+                    int k = w;
+                    while (k < m && x[k] == y[j + (size_t)k]) k++;
+                    if (k == m) count++;
+                }
+            }
+            D <<= 1;
+        }
+        j += (size_t)last;
+    }
+    return count;
+}
+
+/* br.c:26-37 preBrBc == tvsbs.c:26-37; brBc is row-major [256][256] */
+void ora_pre_brbc(const unsigned char *x, int m, int *brBc)
+{
+    for (int a = 0; a < ORA_SIGMA; a++)
+        for (int b = 0; b < ORA_SIGMA; b++) brBc[a * ORA_SIGMA + b] = m + 2;
+    for (int a = 0; a < ORA_SIGMA; a++) brBc[a * ORA_SIGMA + x[0]] = m + 1;
+    for (int i = 0; i < m - 1; i++) brBc[x[i] * ORA_SIGMA + x[i + 1]] = m - i;
+    for (int a = 0; a < ORA_SIGMA; a++) brBc[x[m - 1] * ORA_SIGMA + a] = 1;
+}
+
+/* the two characters after the window; the reference reads y[n] (the driver's NUL, smart.c:125) and y[n+1]
+ * (which br.c:51 sets to 0): positions at or past n read as 0 here */
+static unsigned char ora_at(const unsigned char *y, size_t n, size_t i) { return i < n ? y[i] : 0; }
+
+/* br.c:40-63 (whole = 1) and tvsbs.c:40-62 (whole = 0: last and first character, then the inside backwards) */
+long long ora_search_br(const unsigned char *x, int m, const unsigned char *y, size_t n, int whole)
+{
+    int *brBc = malloc(sizeof(int) * ORA_SIGMA * ORA_SIGMA);
+    long long count = 0;
+    ora_pre_brbc(x, m, brBc);
+    for (size_t j = 0; j + (size_t)m <= n;) {
+        if (whole) {
+            int i = 0;
+            while (i < m && x[i] == y[j + (size_t)i]) i++;
+            if (i >= m) count++;
+        } else if (x[m - 1] == y[j + (size_t)m - 1] && x[0] == y[j]) {
+            int i = m - 2;
+            while (i > 0 && x[i] == y[j + (size_t)i]) i--;
+            if (i <= 0) count++;
+        }
+        j += (size_t)brBc[ora_at(y, n, j + (size_t)m) * ORA_SIGMA + ora_at(y, n, j + (size_t)m + 1)];
+    }
+    free(brBc);
+    return count;
+}
+
+/* fjs.c:47-73: Sunday shifts until the last character matches, then a KMP step */
+long long ora_search_fjs(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int qs[ORA_SIGMA];
+    int *kmp = malloc(sizeof(int) * (size_t)(m + 1));
+    long long count = 0;
+    ora_pre_qsbc(x, m, qs);
+    ora_pre_kmp(x, m, kmp);
+    size_t s = 0;
+    while (s + (size_t)m <= n) {
+        while (s + (size_t)m <= n && x[m - 1] != y[s + (size_t)m - 1]) s += (size_t)qs[ora_at(y, n, s + (size_t)m)];
+        if (s + (size_t)m > n) break;
+        int i = 0;
+        while (i < m && x[i] == y[s + (size_t)i]) i++;
+        if (i >= m) count++;
+        s += (size_t)(i - kmp[i]);
+    }
+    free(kmp);
+    return count;
+}
+
+/* ssabs.c:35-55: last and first character, the inside backwards, Sunday shift */
+long long ora_search_ssabs(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int qs[ORA_SIGMA];
+    long long count = 0;
+    ora_pre_qsbc(x, m, qs);
+    for (size_t j = 0; j + (size_t)m <= n; j += (size_t)qs[ora_at(y, n, j + (size_t)m)]) {
+        if (x[m - 1] == y[j + (size_t)m - 1] && x[0] == y[j]) {
+            int i = m - 2;
+            while (i > 0 && x[i] == y[j + (size_t)i]) i--;
+            if (i <= 0) count++;
+        }
+    }
+    return count;
+}
+
+/* ts.c:25-59 Tailed-Substring: phase 1 looks for the pattern position i whose previous equal character is
+ * furthest away (dim), shifting by that distance after every probe hit; phase 2 keeps probing position k */
+long long ora_search_ts(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    long long count = 0;
+    size_t s = 0;
+    int i = m - 1, k = m - 1, dim = 1;
+    while (s + (size_t)m <= n && i - dim >= 0) {
+        if (x[i] != y[s + (size_t)i]) {
+            s++;
+        } else {
+            int j = 0, h;
+            while (j < m && x[j] == y[s + (size_t)j]) j++;
+            if (j == m) count++;
+            for (h = i - 1; h >= 0 && x[h] != x[i]; h--) {}
+            if (dim < i - h) {
+                k = i;
+                dim = i - h;
+            }
+            s += (size_t)(i - h);
+            i--;
+        }
+    }
+    while (s + (size_t)m <= n) {
+        if (x[k] != y[s + (size_t)k]) {
+            s++;
+        } else {
+            int j = 0;
+            while (j < m && x[j] == y[s + (size_t)j]) j++;
+            if (j == m) count++;
+            s += (size_t)dim;
+        }
+    }
+    return count;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Dispatcher by registry name (lower case, smart.c:142). Returns -2 for an unknown name. */
 long long ora_search(const char *algo, const unsigned char *x, int m, const unsigned char *y, size_t n)
@@ -650,6 +802,12 @@ long long ora_search(const char *algo, const unsigned char *x, int m, const unsi
     if (!strcmp(algo, "tbm")) return (size_t)m > n ? 0 : ora_search_tbm(x, m, y, n);
     if (!strcmp(algo, "ag")) return (size_t)m > n ? 0 : ora_search_ag(x, m, y, n);
     if (!strcmp(algo, "ac")) return (size_t)m > n ? 0 : ora_search_ac(x, m, y, n);
+    if (!strcmp(algo, "bndm")) return (size_t)m > n ? 0 : ora_search_bndm(x, m, y, n);
+    if (!strcmp(algo, "br")) return (size_t)m > n ? 0 : ora_search_br(x, m, y, n, 1);
+    if (!strcmp(algo, "tvsbs")) return (size_t)m > n ? 0 : ora_search_br(x, m, y, n, 0);
+    if (!strcmp(algo, "fjs")) return (size_t)m > n ? 0 : ora_search_fjs(x, m, y, n);
+    if (!strcmp(algo, "ssabs")) return (size_t)m > n ? 0 : ora_search_ssabs(x, m, y, n);
+    if (!strcmp(algo, "ts")) return (size_t)m > n ? 0 : ora_search_ts(x, m, y, n);
     if (!strncmp(algo, "hash", 4) && algo[4] && !algo[5]) return ora_search_hashq(x, m, y, n, algo[4] - '0');
     if (!strncmp(algo, "qf", 2) && algo[2] && algo[3] && !algo[4])
         return ora_search_qf(x, m, y, n, algo[2] - '0', algo[3] - '0');

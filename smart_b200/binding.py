@@ -36,6 +36,7 @@ ALGORITHMS = (
     "hash3", "hash5", "hash8",
     "qf23", "qf24", "qf26", "qf28", "qf33", "qf34", "qf36", "qf42", "qf43", "qf44", "qf62", "qf63",
     "smith", "tbm", "ag", "ac",
+    "bndm", "br", "tvsbs", "fjs", "ssabs", "ts",
 )
 
 
@@ -88,6 +89,8 @@ class Tables(C.Structure):
         ("krD", C.c_int),
         ("krHx", C.c_int),
         ("acEll", C.c_int),
+        ("bndmB", C.c_uint * 256),
+        ("brBc", C.c_int * 65536),
         ("qfQ", C.c_int),
         ("qfS", C.c_int),
         ("qfB", C.c_int * (1 << 18)),

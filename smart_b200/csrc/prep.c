@@ -47,6 +47,12 @@ static const sb_algo_desc g_algos[] = {
     {"tbm", SB_FAM_TBM, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},         /* tbm.c:66: Turbo-BM (bmGs, bmBc) */
     {"ag", SB_FAM_AG, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},           /* ag.c:59: Apostolico-Giancarlo (bmGs, suff, bmBc) */
     {"ac", SB_FAM_AC, SB_ANCHOR_PREFIX, 0, 0, 0, 1},           /* ac.c:44: Apostolico-Crochemore (kmpNext, ell) */
+    {"bndm", SB_FAM_BNDM, SB_ANCHOR_PREFIX, 0, 0, 0, 1},       /* bndm.c:26, search_large :62 (32-char prefix) */
+    {"br", SB_FAM_BR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},           /* br.c:40: Berry-Ravindran brBc[256][256] */
+    {"tvsbs", SB_FAM_BR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},        /* tvsbs.c:40: same table, first/last char first */
+    {"fjs", SB_FAM_FJS, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},         /* fjs.c:47: Franek-Jennings-Smyth (qsBc + kmpNext) */
+    {"ssabs", SB_FAM_QS, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},        /* ssabs.c:35: qsBc, first/last char first */
+    {"ts", SB_FAM_BF, SB_ANCHOR_PREFIX, 0, 0, 0, 1},           /* ts.c:25: Tailed-Substring, no tables */
 };
 #define SB_NALGOS ((int)(sizeof(g_algos) / sizeof(g_algos[0])))
 
@@ -202,6 +208,26 @@ unsigned int sb_prep_sa(const unsigned char *x, int m, unsigned int *S)
     return 1u << (w - 1);
 }
 
+/* BNDM: bit k of B[c] is set iff x[w-1-k] == c, over the first w = min(m,32) characters: the masks of the
+ * REVERSED prefix (bndm.c:33-38; search_large keeps 32 characters, bndm.c:70-76) */
+void sb_prep_bndm(const unsigned char *x, int m, unsigned int *B)
+{
+    const int w = m < SB_WORD ? m : SB_WORD;
+    memset(B, 0, SB_SIGMA * sizeof(unsigned int));
+    for (int k = 0; k < w; k++) B[x[w - 1 - k]] |= 1u << k;
+}
+
+/* Berry-Ravindran: brBc[a][b] = shift aligning the two text characters after the window with their
+ * right-most occurrence in the pattern (br.c:26-37, tvsbs.c:26-37).  Filled by decreasing priority:
+ * default m+2; b == x[0] -> m+1; pair x[i]x[i+1] -> m-i (right-most pair wins); a == x[m-1] -> 1. */
+void sb_prep_brbc(const unsigned char *x, int m, int *brBc)
+{
+    for (int i = 0; i < SB_SIGMA * SB_SIGMA; i++) brBc[i] = m + 2;
+    for (int a = 0; a < SB_SIGMA; a++) brBc[a * SB_SIGMA + x[0]] = m + 1;
+    for (int i = 0; i + 1 < m; i++) brBc[x[i] * SB_SIGMA + x[i + 1]] = m - i;
+    for (int b = 0; b < SB_SIGMA; b++) brBc[x[m - 1] * SB_SIGMA + b] = 1;
+}
+
 /* ------------------------------------------------------------------ q-gram hash shift (HASHq) */
 
 /* h(i) = (sum_{k<q} x[i-k] << k) mod 256: the reference computes it either in an unsigned char
@@ -272,7 +298,7 @@ int sb_prep_tables(int algo, const unsigned char *x, int m, sb_tables *out)
 {
     const sb_algo_desc *d = sb_algo_desc_get(algo);
     if (!d || !x || !out || m < 1 || m > SB_XSIZE) return -2;
-    memset(out, 0, offsetof(sb_tables, qfB));
+    memset(out, 0, offsetof(sb_tables, brBc));
     out->m = m;
     if (m < d->min_m) return -1;
     switch (d->family) {
@@ -298,6 +324,13 @@ int sb_prep_tables(int algo, const unsigned char *x, int m, sb_tables *out)
     case SB_FAM_AG:
         sb_prep_bmgs(x, m, out->suff, out->bmGs);
         sb_prep_hbc(x, m, out->hbc);
+        break;
+    case SB_FAM_BNDM: sb_prep_bndm(x, m, out->bndmB); break;
+    case SB_FAM_BR: sb_prep_brbc(x, m, out->brBc); break;
+    case SB_FAM_FJS:
+        sb_prep_qsbc(x, m, out->qsBc);
+        sb_prep_mp(x, m, out->mpNext);
+        sb_prep_kmp(x, m, out->mpNext, out->kmpNext);
         break;
     case SB_FAM_AC: {
         /* ell = length of the leading run of x[0] if the pattern is not a single run, else 0 (ac.c:52-53) */

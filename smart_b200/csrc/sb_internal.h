@@ -25,7 +25,10 @@ enum sb_family {
     SB_FAM_SMITH,
     SB_FAM_TBM,
     SB_FAM_AG,
-    SB_FAM_AC
+    SB_FAM_AC,
+    SB_FAM_BNDM,
+    SB_FAM_BR,
+    SB_FAM_FJS
 };
 
 /* which end of the pattern the candidate fingerprint is taken from: the left-to-right families
@@ -52,6 +55,8 @@ void sb_prep_suffixes(const unsigned char *x, int m, int *suff);
 void sb_prep_bmgs(const unsigned char *x, int m, int *suff, int *bmGs);
 unsigned int sb_prep_so(const unsigned char *x, int m, unsigned int *S);
 unsigned int sb_prep_sa(const unsigned char *x, int m, unsigned int *S);
+void sb_prep_bndm(const unsigned char *x, int m, unsigned int *B);
+void sb_prep_brbc(const unsigned char *x, int m, int *brBc);
 void sb_prep_hashq(const unsigned char *x, int m, int q, int *shift, int *sh1);
 void sb_prep_kr(const unsigned char *x, int m, int *d, int *hx);
 void sb_prep_qf(const unsigned char *x, int m, int Q, int S, int *B);

@@ -106,6 +106,10 @@ class Oracle:
         if name == "kr":
             d, hx = C.c_int(0), C.c_int(0)
             L.ora_pre_kr(_ptr(x), m, C.byref(d), C.byref(hx)); return d.value, hx.value
+        if name == "bndmB":
+            t = np.zeros(256, dtype=np.uint32); L.ora_pre_bndm(_ptr(x), m, _ptr(t)); return t
+        if name == "brBc":
+            t = ia(65536); L.ora_pre_brbc(_ptr(x), m, _ptr(t)); return t
         if name == "acEll":
             return int(L.ora_pre_ac_ell(_ptr(x), m))
         if name == "qf":

@@ -2,6 +2,7 @@
 bit-identical to the reference's: checked against tables dumped from the reference's own exported pre*()
 functions (tests/golden/tables.json), against SURVEY.md Appendix B.2, and against the oracle restatement on
 random patterns.  Host-only: no GPU needed."""
+import hashlib
 import json
 import os
 
@@ -42,6 +43,8 @@ def test_tables_vs_reference_dump(table_cases):
         if m >= 2:
             assert arr(sb.prep_tables("raita", x).hbc, 256) == ent["hbc"]
         assert arr(sb.prep_tables("tunedbm", x).hbc, 256) == ent["hbc"]
+        br = np.ctypeslib.as_array(sb.prep_tables("br", x).brBc).astype(np.int32)
+        assert hashlib.sha1(br.tobytes()).hexdigest() == ent["brBc_sha1"]  # preBrBc dumped from br.c
 
 
 def test_appendix_b2_known_answers():
@@ -101,6 +104,12 @@ def test_tables_vs_oracle_random(oracle):
         for name in ("tbm", "ag"):
             t = sb.prep_tables(name, x)
             assert arr(t.bmGs, m) == oracle.table("bmGs", x).tolist() and arr(t.suff, m) == oracle.table("suff", x).tolist()
+        assert arr(sb.prep_tables("bndm", x).bndmB, 256) == oracle.table("bndmB", x).tolist()
+        for name in ("br", "tvsbs"):
+            assert arr(sb.prep_tables(name, x).brBc, 65536) == oracle.table("brBc", x).tolist()
+        t = sb.prep_tables("fjs", x)
+        assert arr(t.qsBc, 256) == oracle.table("qsBc", x).tolist() and arr(t.kmpNext, m + 1) == oracle.table("kmpNext", x).tolist()
+        assert arr(sb.prep_tables("ssabs", x).qsBc, 256) == oracle.table("qsBc", x).tolist()
         d, hx = oracle.table("kr", x)
         t = sb.prep_tables("kr", x)
         assert (t.krD, t.krHx) == (d, hx)
