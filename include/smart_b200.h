@@ -52,6 +52,7 @@ extern "C" {
 #define SB_FLAG_POSITIONS 0x1u    /* fill `positions` (sorted ascending, global offsets) */
 #define SB_FLAG_NO_SKIP 0x2u      /* force the read-every-byte kernels even for skip-family algorithms (the
                                      sub-linear scan_skip kernel is their default for m >= 71) */
+#define SB_FLAG_NO_PERIOD 0x8u    /* tuning/test override: verify every candidate in full (no period shortcut) */
 #define SB_FLAG_DENSE 0x4u        /* tuning override: m <= 4, count every position even if matches look rare */
 #define SB_FLAG_FILTER_SHIFT 0x10u  /* tuning override: force the per-position 8-byte window kernel (m >= 5) */
 #define SB_FLAG_FILTER_B4 0x20u     /* tuning override: aligned-block fingerprint width 4 */

@@ -14,6 +14,7 @@ from .binding import (  # noqa: F401
     FLAG_FILTER_SHIFT,
     FLAG_NO_SKIP,
     FLAG_DENSE,
+    FLAG_NO_PERIOD,
     FLAG_POSITIONS,
     NOT_APPLICABLE,
     SmartB200Error,

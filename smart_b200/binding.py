@@ -25,6 +25,7 @@ NOT_APPLICABLE = -1
 FLAG_POSITIONS = 0x1
 FLAG_NO_SKIP = 0x2
 FLAG_DENSE = 0x4
+FLAG_NO_PERIOD = 0x8
 FLAG_FILTER_SHIFT = 0x10
 FLAG_FILTER_B4 = 0x20
 FLAG_FILTER_B8 = 0x40

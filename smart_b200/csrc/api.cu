@@ -300,6 +300,13 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
     a.m = m;
     a.nwords = (m + 3) / 4;
     a.tailmask = (m & 3) ? ((1u << (8 * (m & 3))) - 1u) : 0xffffffffu;
+    {   /* the pattern's smallest period, from the border table (mp.c:26-35): used on the device by the
+         * period-aware verification of scan_block when the pattern is at least two periods long */
+        static thread_local int border[SB_XSIZE + 1];
+        sb_prep_mp(x, m, border);
+        const int period = m - border[m];
+        a.period = (period * 2 <= m && !(flags & SB_FLAG_NO_PERIOD)) ? period : 0;
+    }
     /* Sub-linear sampling for the skip families: one G-byte gram every `stride` bytes (a multiple of the
      * 32-byte DRAM sector), G wide enough that a text gram rarely equals one of `stride` pattern grams. */
     const unsigned forced = SB_FLAG_FILTER_SHIFT | SB_FLAG_FILTER_B4 | SB_FLAG_FILTER_B8 | SB_FLAG_FILTER_B16 |

@@ -75,6 +75,10 @@ struct ScanArgs {
     // counts at multi_counts[p]; aux = Bloom bitmap + table {fingerprint, ((p << 5) | d) + 1}
     unsigned long long *multi_counts;
     int npat, pat_stride_words;
+    // smallest period of the pattern, m - mpNext[m] (mp.c:26-35), when it is at most m/2; else 0.
+    // Drives period-aware verification in scan_block: after a verified occurrence at j, a candidate at
+    // j + k*period (< j + m) only needs its last k*period bytes compared.
+    int period;
 };
 
 constexpr int kBloomBits = 18;                       // 2^18-bit Bloom bitmap = 32 KiB of shared memory, 2 probes
@@ -122,20 +126,35 @@ __device__ __forceinline__ uint32_t text_window32(const uint8_t *text, long long
 }
 
 /* Exact comparison of x[0..m) with text[j..j+m), one 32-bit window per lane per step.
- * All 32 lanes must call it with the same j. */
-__device__ __forceinline__ bool warp_verify(const ScanArgs &a, long long j, unsigned lane, const uint32_t *pat = nullptr)
+ * All 32 lanes must call it with the same j.  Words [from_word, nwords) are compared; for long patterns the
+ * first step looks at BOTH ends (16 words each): a candidate that agrees with the pattern around the
+ * fingerprinted block but differs far from it (near-periodic inputs) is then rejected in one step. */
+__device__ __forceinline__ bool warp_compare(const ScanArgs &a, long long j, const uint32_t *pat, int k, bool active)
+{
+    bool ok = true;
+    if (active) {
+        uint32_t diff = text_window32(a.text, j + 4ll * k) ^ __ldg(pat + k);
+        if (k == a.nwords - 1) diff &= a.tailmask;
+        ok = (diff == 0);
+    }
+    return __all_sync(kFull, ok);
+}
+
+__device__ __forceinline__ bool warp_verify(const ScanArgs &a, long long j, unsigned lane, const uint32_t *pat = nullptr,
+                                            int from_word = 0)
 {
     const int nwords = a.nwords;
     if (!pat) pat = a.pat;
-    for (int base = 0; base < nwords; base += 32) {
+    int lo = from_word, hi = nwords;
+    if (hi - lo > 32) {
+        const int k = lane < 16 ? lo + (int)lane : hi - 32 + (int)lane;
+        if (!warp_compare(a, j, pat, k, true)) return false;
+        lo += 16;
+        hi -= 16;
+    }
+    for (int base = lo; base < hi; base += 32) {
         const int k = base + (int)lane;
-        bool ok = true;
-        if (k < nwords) {
-            uint32_t diff = text_window32(a.text, j + 4ll * k) ^ __ldg(pat + k);
-            if (k == nwords - 1) diff &= a.tailmask;
-            ok = (diff == 0);
-        }
-        if (!__all_sync(kFull, ok)) return false;
+        if (!warp_compare(a, j, pat, k, k < hi)) return false;
     }
     return true;
 }
@@ -191,10 +210,15 @@ __device__ __forceinline__ void block_reduce_count(const ScanArgs &a, unsigned c
 /* Slow path of scan_block: some lane of this warp saw a fingerprint hit in its 32-byte vector.
  * For each such lane the whole warp re-derives which of the 32 (block, d) slots hit (one slot per
  * lane) and verifies each candidate cooperatively. */
+struct CandResult {
+    unsigned cnt, nver;
+    long long run_j;  // start of the last verified occurrence seen by this warp (-1: none)
+};
+
 template <int B>
-__device__ __noinline__ uint2 block_candidates(const ScanArgs &a, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3,
-                                               uint32_t v4, uint32_t v5, uint32_t v6, uint32_t v7, long long voff,
-                                               bool hit, unsigned lane)
+__device__ __noinline__ CandResult block_candidates(const ScanArgs &a, uint32_t v0, uint32_t v1, uint32_t v2,
+                                                    uint32_t v3, uint32_t v4, uint32_t v5, uint32_t v6, uint32_t v7,
+                                                    long long voff, bool hit, unsigned lane, long long run_j)
 {
     // everything by value and the result returned: a by-reference vector would force the caller to
     // keep a copy of every loaded vector in local memory (an STL per load in the hot loop)
@@ -208,7 +232,9 @@ __device__ __noinline__ uint2 block_candidates(const ScanArgs &a, uint32_t v0, u
 #pragma unroll
         for (int i = 0; i < 8; i++) s[i] = __shfl_sync(kFull, vw[i], src);
         const long long soff = __shfl_sync(kFull, voff, src);
-        const int blk = (int)lane / B, d = (int)lane % B;  // slot of this lane
+        // slot of this lane; d runs DOWN inside a block so that the candidate positions of a vector are
+        // visited in ascending order (the period-aware shortcut below relies on that)
+        const int blk = (int)lane / B, d = B - 1 - (int)lane % B;
         uint32_t h;
         if (B == 4) {
             h = s[0];
@@ -227,17 +253,31 @@ __device__ __noinline__ uint2 block_candidates(const ScanArgs &a, uint32_t v0, u
         while (slots) {
             const int sl = __ffs(slots) - 1;
             slots &= slots - 1;
-            const long long j = soff + (sl / B) * B - (sl % B) - a.anchor;
+            const long long j = soff + (sl / B) * B - (B - 1 - sl % B) - a.anchor;
             if (j >= 0 && j < a.hi) {
                 nver += (lane == 0);
-                if (warp_verify(a, j, lane) && lane == 0) {
-                    cnt++;
-                    emit_match(a, j);
+                // Period-aware verification: x has period p and text[run_j .. run_j+m) == x.  If j = run_j + k*p
+                // lies inside that occurrence, text[j .. run_j+m) equals x[0 .. m-k*p) by periodicity and only
+                // the last k*p bytes remain to be compared (rounded down to a word).
+                int from_word = 0;
+                const long long delta = j - run_j;
+                if (a.period && run_j >= 0 && delta > 0 && delta < a.m && delta % a.period == 0)
+                    from_word = (a.m - (int)delta) >> 2;
+                if (warp_verify(a, j, lane, nullptr, from_word)) {
+                    run_j = j;
+                    if (lane == 0) {
+                        cnt++;
+                        emit_match(a, j);
+                    }
                 }
             }
         }
     }
-    return make_uint2(cnt, nver);
+    CandResult r;
+    r.cnt = cnt;
+    r.nver = nver;
+    r.run_j = run_j;
+    return r;
 }
 
 template <int B>
@@ -279,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, SB_MINB) scan_block_kernel(const __g
     const unsigned long long warp = ((unsigned long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * kThreads) >> 5;
     unsigned cnt = 0, nver = 0;
+    long long run_j = -1;  // last verified occurrence of this warp, for period-aware verification
 
     for (unsigned long long g = warp; g < a.ngroups; g += nwarps) {
         const uint8_t *p = a.text + g * (U * 1024ull) + lane * 32;
@@ -290,10 +331,11 @@ __global__ void __launch_bounds__(kThreads, SB_MINB) scan_block_kernel(const __g
             const bool hit = block_hit<B>(a, v[c]);
             if (__any_sync(kFull, hit)) {
                 const long long voff = (long long)(g * (U * 1024ull)) + c * 1024 + lane * 32;
-                const uint2 r = block_candidates<B>(a, v[c].w[0], v[c].w[1], v[c].w[2], v[c].w[3], v[c].w[4],
-                                                    v[c].w[5], v[c].w[6], v[c].w[7], voff, hit, lane);
-                cnt += r.x;
-                nver += r.y;
+                const CandResult r = block_candidates<B>(a, v[c].w[0], v[c].w[1], v[c].w[2], v[c].w[3], v[c].w[4],
+                                                         v[c].w[5], v[c].w[6], v[c].w[7], voff, hit, lane, run_j);
+                cnt += r.cnt;
+                nver += r.nver;
+                run_j = r.run_j;
             }
         }
     }

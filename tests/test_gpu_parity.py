@@ -91,6 +91,8 @@ def test_every_filter_width_gives_the_same_count(oracle, golden, tname):
                     r = sb.search(a, t, x, flags=FILTERS[f])
                     assert sb.last_timing().filter_kind == f
                     assert r.count == want, (tname, c["m"], c["pi"], a, f)
+            # the period-aware verification shortcut is an optimisation, never a semantic change
+            assert sb.search("kmp", t, x, flags=sb.FLAG_NO_PERIOD).count == want
             if c["m"] <= 16:  # scan_short / scan_window: dense (count every position) and sparse modes agree
                 assert sb.search("bf", t, x, flags=sb.FLAG_DENSE).count == want
                 r = sb.search("bf", t, x, flags=sb.FLAG_DENSE | sb.FLAG_POSITIONS, positions_cap=y.size)

@@ -40,7 +40,7 @@ def text_and_pattern(draw):
     return y, x
 
 
-@settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=400, deadline=None, suppress_health_check=list(HealthCheck))
 @given(text_and_pattern())
 def test_random_small_cases(oracle, case):
     y, x = case
@@ -50,7 +50,7 @@ def test_random_small_cases(oracle, case):
             assert sb.search(a, t, x).count == expected(a, x.size, want.size), (a, x.size, y.size)
         r = sb.search("kmp", t2, x, flags=sb.FLAG_POSITIONS, positions_cap=max(1, y.size))
         assert np.array_equal(r.positions, want)
-        for flags in (sb.FLAG_DENSE, sb.FLAG_FILTER_SHIFT if x.size >= 5 else 0, sb.FLAG_NO_SKIP):
+        for flags in (sb.FLAG_DENSE, sb.FLAG_FILTER_SHIFT if x.size >= 5 else 0, sb.FLAG_NO_SKIP, sb.FLAG_NO_PERIOD):
             assert sb.search("hor", t, x, flags=flags).count == want.size
     assert sb.search_host("bm", x, y).count == want.size
 
