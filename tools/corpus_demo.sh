@@ -2,7 +2,7 @@
 # BASELINE.json configs[0]: the SMART driver on the bundled corpus (englishTexts first), text-extracted
 # patterns m = 2..32 (-short), BF/KMP/Horspool/Shift-Or (+BM, HASH3, QF23): once with OUR executables and the
 # resident GPU worker, once with the REFERENCE executables on the host CPU, same seed => same pattern sets.
-# Needs data_local/ (a git-ignored copy of the reference's data/ made in the build container).
+# Needs data_local/ = a git-ignored copy of the reference data: mkdir data_local && cp -r /root/reference/data/{englishTexts,italianTexts,frenchTexts,chineseTexts,protein,midimusic} data_local/
 set -e
 cd "$(dirname "$0")/.."
 W=${1:-gpurun_out/corpus_demo}
