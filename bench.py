@@ -458,6 +458,17 @@ def run_e2e(sb, ranks, dist, device, text, base, own, n_total, pats, algos, ms, 
         pin.free()
 
 
+def ensure_built():
+    """Binaries are git-ignored; a fresh checkout builds them (nvcc/gcc are in the image). Not a fallback:
+    a failed build stops the bench."""
+    import smart_b200
+
+    if not os.path.exists(smart_b200.library_path()):
+        smart_b200.build_library()
+    if not os.path.exists(os.path.join(ROOT, "oracle", "libsmart_oracle.so")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle", "ref"], check=True, capture_output=True)
+
+
 def main():
     args = parse_args()
     ms = [int(v) for v in args.ms.split(",")]
@@ -469,6 +480,15 @@ def main():
     os.dup2(2, 1)
     global print_json
     print_json = lambda obj: os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        ensure_built()
+    else:  # the other ranks wait for local rank 0's build (normally the prebuilt library is already there)
+        import smart_b200
+
+        for _ in range(600):
+            if os.path.exists(smart_b200.library_path()):
+                break
+            time.sleep(1.0)
     if args.impl == "reference":
         return main_reference(args, algos, ms)
     return main_ours(args, algos, ms)
