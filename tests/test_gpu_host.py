@@ -130,3 +130,31 @@ def test_plain_c_client_of_the_abi():
     r = run([os.path.join(BIN, "abi_demo")])
     assert r.returncode == 0, (r.stdout, r.stderr)
     assert r.stdout.count(": ok") == 4 and "FAIL" not in r.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "smart")), reason="oracle/_ref/smart not built")
+def test_reference_driver_drives_our_executables(tmp_path, worker):
+    """BASELINE configs[0] end to end with the UNMODIFIED reference driver (src/smart.c): it loads the text,
+    creates the shm segments, samples patterns and launches OUR executables from ./source/bin; every cell must
+    come back [OK] (a count of 0 would print [ERROR], a failure [--], smart.c:376-377)."""
+    (tmp_path / "source").mkdir()
+    os.symlink(os.path.join(BIN, "algos"), tmp_path / "source" / "bin")
+    (tmp_path / "source" / "algorithms.h").write_text("#1 #bf \n#1 #kmp \n#1 #hor \n#1 #so \n#0 #bm \n#1 #hash3 \n")
+    (tmp_path / "results").mkdir()
+    d = tmp_path / "data" / "englishTexts"
+    d.mkdir(parents=True)
+    (d / "bible.txt").write_bytes(open(os.path.join(ROOT, "tests", "golden", "bible64k.bin"), "rb").read())
+    (d / "index.txt").write_text("#bible.txt#\n")
+    r = run([os.path.join(REF, "smart"), "-text", "englishTexts", "-pset", "4", "-plen", "4", "16", "-short", "-occ"],
+            cwd=tmp_path, env=worker)
+    out = r.stdout.replace("\b", "")
+    assert "Text buffer of dimension 65536 byte" in out, (out[-500:], r.stderr[-300:])
+    assert out.count("[OK]") == 5 * 7, out[-1500:]   # 5 enabled algorithms x m = 4,6,...,16
+    assert "[ERROR]" not in out and "[--]" not in out and "[OUT]" not in out
+    occ = [int(v) for v in re.findall(r"occ (\d+)", out)]
+    assert len(occ) == 35 and min(occ) >= 1
+    # all algorithms of one length saw the same pattern set, so they report the same mean occurrence count
+    for k in range(0, 35, 5):
+        assert len(set(occ[k:k + 5])) == 1
+    searches, uploads = stats(worker)
+    assert searches == 35 * 4 and uploads == 1   # 140 searches, the 64 KiB text uploaded once
