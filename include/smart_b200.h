@@ -161,7 +161,8 @@ typedef struct sb_tables {
     int m;
     int mpNext[SB_XSIZE + 1];   /* mp.c:26-35 */
     int kmpNext[SB_XSIZE + 1];  /* kmp.c:27-41 */
-    int hbc[SB_SIGMA];          /* hor.c:26-30 == bm.c:27-33 (bmBc) == raita.c/tunedbm.c preBmBc */
+    int hbc[SB_SIGMA];          /* hor.c:26-30 == bm.c:27-33 (bmBc) == raita.c/tunedbm.c preBmBc;
+                                   fs/graspm: the variant over all m characters (fs.c:50-51) */
     int qsBc[SB_SIGMA];         /* qs.c:26-30 */
     int suff[SB_XSIZE];         /* bm.c:36-52 */
     int bmGs[SB_XSIZE];         /* bm.c:54-66 */
@@ -174,6 +175,9 @@ typedef struct sb_tables {
     int hashQ;                  /* 0 if the algorithm is not a HASHq */
     int krD, krHx;              /* kr.c:34-40 */
     int acEll;                  /* ac.c:52-53 */
+    int bucketHead[SB_SIGMA];   /* skip.c:31-39 / kmpskip.c:71-77 z[]; graspm.c:41-45 lists (see prep.c) */
+    int bucketNext[SB_XSIZE + 1]; /* ... list[] / next pointers, -1 terminated */
+    int fsGs[SB_XSIZE + 1];     /* fs.c:26-41 Pre_GS, entries [0..m] */
     unsigned int bndmB[SB_SIGMA]; /* bndm.c:33-38 (first min(m,32) chars, reversed) */
     int brBc[SB_SIGMA * SB_SIGMA]; /* br.c:26-37 == tvsbs.c:26-37, row-major [a][b] */
     int qfQ, qfS;               /* qf<Q><S>.c:28-29; 0 if not a QF */

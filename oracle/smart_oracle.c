@@ -782,6 +782,180 @@ long long ora_search_ts(const unsigned char *x, int m, const unsigned char *y, s
     return count;
 }
 
+/* skip.c:31-39: z[c] lists the pattern positions holding c, right-most first (each new cell is pushed in
+ * front); kmpskip.c:71-77 builds the same structure as arrays z[] / list[] */
+void ora_pre_buckets(const unsigned char *x, int m, int *z, int *list)
+{
+    for (int c = 0; c < ORA_SIGMA; c++) z[c] = -1;
+    for (int i = 0; i < m; i++) {
+        list[i] = z[x[i]];
+        z[x[i]] = i;
+    }
+}
+
+/* skip.c:26-52 Skip-Search: every m-th text character selects the alignments to try */
+long long ora_search_skip(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int z[ORA_SIGMA];
+    int *list = malloc(sizeof(int) * (size_t)m);
+    long long count = 0;
+    ora_pre_buckets(x, m, z, list);
+    for (size_t j = (size_t)m - 1; j < n; j += (size_t)m)
+        for (int e = z[y[j]]; e >= 0; e = list[e])
+            if (j - (size_t)e + (size_t)m <= n && memcmp(x, y + j - (size_t)e, (size_t)m) == 0) count++;
+    free(list);
+    return count;
+}
+
+/* kmpskip.c:59-146 KMP-Skip-Search */
+long long ora_search_kmpskip(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int z[ORA_SIGMA];
+    int *list = malloc(sizeof(int) * (size_t)m), *mp = malloc(sizeof(int) * (size_t)(m + 1)),
+        *kmp = malloc(sizeof(int) * (size_t)(m + 1));
+    long long count = 0, nn = (long long)n, i, j, k, start, wall = 0, kmpStart;
+    ora_pre_mp(x, m, mp);
+    ora_pre_kmp(x, m, kmp);
+    ora_pre_buckets(x, m, z, list);
+    const int per = m - kmp[m];
+#define ORA_NEXT_BUCKET()                          \
+    do {                                           \
+        j += m;                                    \
+    } while (j < nn && z[y[j]] < 0);               \
+    if (j >= nn) goto done;                        \
+    i = z[y[j]];
+    i = j = -1;
+    ORA_NEXT_BUCKET();
+    start = j - i;
+    while (start <= nn - m) {
+        if (start > wall) wall = start;
+        k = wall - start;
+        while (k < m && x[k] == y[k + start]) ++k;
+        wall = start + k;
+        if (k == m) {
+            count++;
+            i -= per;
+        } else {
+            i = list[i];
+        }
+        if (i < 0) {
+            ORA_NEXT_BUCKET();
+        }
+        kmpStart = start + k - kmp[k];
+        k = kmp[k];
+        start = j - i;
+        while (start < kmpStart || (kmpStart < start && start < wall)) {
+            if (start < kmpStart) {
+                i = list[i];
+                if (i < 0) {
+                    ORA_NEXT_BUCKET();
+                }
+                start = j - i;
+            } else {
+                kmpStart += (k - mp[k]);
+                k = mp[k];
+            }
+        }
+    }
+done:
+#undef ORA_NEXT_BUCKET
+    free(list);
+    free(mp);
+    free(kmp);
+    return count;
+}
+
+/* fs.c:50-51 (also graspm.c:47-48): last-occurrence table over ALL m characters */
+void ora_pre_lastocc(const unsigned char *x, int m, int *bc)
+{
+    for (int a = 0; a < ORA_SIGMA; a++) bc[a] = m;
+    for (int j = 0; j < m; j++) bc[x[j]] = m - j - 1;
+}
+
+/* fs.c:26-41 Pre_GS; gs has m+1 entries */
+void ora_pre_fsgs(const unsigned char *x, int m, int *gs)
+{
+    int *f = malloc(sizeof(int) * (size_t)(m + 2));
+    int i, j, p;
+    for (i = 0; i <= m; i++) gs[i] = 0;
+    f[m] = j = m + 1;
+    for (i = m; i > 0; i--) {
+        while (j <= m && x[i - 1] != x[j - 1]) {
+            if (gs[j] == 0) gs[j] = j - i;
+            j = f[j];
+        }
+        f[i - 1] = --j;
+    }
+    p = f[0];
+    for (j = 0; j <= m; ++j) {
+        if (gs[j] == 0) gs[j] = p;
+        if (j == p) p = f[p];
+    }
+    free(f);
+}
+
+/* fs.c:44-72 Fast-Search; the reference stops its skip loop with m copies of x[m-1] at y[n..] (:53), the
+ * bounded version stops it at n */
+long long ora_search_fs(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int bc[ORA_SIGMA];
+    int *gs = malloc(sizeof(int) * (size_t)(m + 1));
+    long long count = 0;
+    ora_pre_lastocc(x, m, bc);
+    ora_pre_fsgs(x, m, gs);
+    if (memcmp(x, y, (size_t)m) == 0) count++;
+    size_t s = (size_t)m;
+    while (s < n) {
+        int k;
+        while (s < n && (k = bc[y[s]]) != 0) s += (size_t)k;
+        if (s >= n) break;
+        int j = 2;
+        while (j <= m && x[m - j] == y[s - (size_t)j + 1]) j++;
+        if (j > m) count++;
+        s += (size_t)gs[m - j + 1];
+    }
+    free(gs);
+    return count;
+}
+
+/* graspm.c:41-45: lists z[c] as head/next arrays, -1 terminated (0 is the shared tail when x[0]==x[m-1]) */
+void ora_pre_graspm(const unsigned char *x, int m, int *head, int *next)
+{
+    for (int c = 0; c < ORA_SIGMA; c++) head[c] = -1;
+    next[0] = -1;
+    if (x[0] == x[m - 1])
+        for (int c = 0; c < ORA_SIGMA; c++) head[c] = 0;
+    for (int i = 0; i < m - 1; i++)
+        if (x[i + 1] == x[m - 1]) {
+            next[i + 1] = head[x[i]];
+            head[x[i]] = i + 1;
+        }
+}
+
+/* graspm.c:37-73 GRASPm; skip loop bounded by n instead of the sentinel copy of the pattern (:49) */
+long long ora_search_graspm(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int bc[ORA_SIGMA], head[ORA_SIGMA];
+    int *next = malloc(sizeof(int) * (size_t)(m + 1));
+    long long count = 0;
+    ora_pre_lastocc(x, m, bc);
+    ora_pre_graspm(x, m, head, next);
+    size_t j = (size_t)m - 1;
+    while (j < n) {
+        int k;
+        while (j < n && (k = bc[y[j]]) != 0) j += (size_t)k;
+        if (j >= n) break;
+        for (int e = head[j > 0 ? y[j - 1] : 0]; e >= 0; e = next[e]) {
+            if (j < (size_t)e) continue;
+            const size_t first = j - (size_t)e;
+            if (first + (size_t)m <= n && memcmp(x, y + first, (size_t)m) == 0) count++;
+        }
+        j += (size_t)m;
+    }
+    free(next);
+    return count;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Dispatcher by registry name (lower case, smart.c:142). Returns -2 for an unknown name. */
 long long ora_search(const char *algo, const unsigned char *x, int m, const unsigned char *y, size_t n)
@@ -808,6 +982,10 @@ long long ora_search(const char *algo, const unsigned char *x, int m, const unsi
     if (!strcmp(algo, "fjs")) return (size_t)m > n ? 0 : ora_search_fjs(x, m, y, n);
     if (!strcmp(algo, "ssabs")) return (size_t)m > n ? 0 : ora_search_ssabs(x, m, y, n);
     if (!strcmp(algo, "ts")) return (size_t)m > n ? 0 : ora_search_ts(x, m, y, n);
+    if (!strcmp(algo, "skip")) return (size_t)m > n ? 0 : ora_search_skip(x, m, y, n);
+    if (!strcmp(algo, "kmpskip")) return (size_t)m > n ? 0 : ora_search_kmpskip(x, m, y, n);
+    if (!strcmp(algo, "fs")) return (size_t)m > n ? 0 : ora_search_fs(x, m, y, n);
+    if (!strcmp(algo, "graspm")) return (size_t)m > n ? 0 : ora_search_graspm(x, m, y, n);
     if (!strncmp(algo, "hash", 4) && algo[4] && !algo[5]) return ora_search_hashq(x, m, y, n, algo[4] - '0');
     if (!strncmp(algo, "qf", 2) && algo[2] && algo[3] && !algo[4])
         return ora_search_qf(x, m, y, n, algo[2] - '0', algo[3] - '0');

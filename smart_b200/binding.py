@@ -38,6 +38,7 @@ ALGORITHMS = (
     "qf23", "qf24", "qf26", "qf28", "qf33", "qf34", "qf36", "qf42", "qf43", "qf44", "qf62", "qf63",
     "smith", "tbm", "ag", "ac",
     "bndm", "br", "tvsbs", "fjs", "ssabs", "ts",
+    "skip", "kmpskip", "fs", "graspm",
 )
 
 
@@ -90,6 +91,9 @@ class Tables(C.Structure):
         ("krD", C.c_int),
         ("krHx", C.c_int),
         ("acEll", C.c_int),
+        ("bucketHead", C.c_int * 256),
+        ("bucketNext", C.c_int * (XSIZE + 1)),
+        ("fsGs", C.c_int * (XSIZE + 1)),
         ("bndmB", C.c_uint * 256),
         ("brBc", C.c_int * 65536),
         ("qfQ", C.c_int),

@@ -53,6 +53,10 @@ static const sb_algo_desc g_algos[] = {
     {"fjs", SB_FAM_FJS, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},         /* fjs.c:47: Franek-Jennings-Smyth (qsBc + kmpNext) */
     {"ssabs", SB_FAM_QS, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},        /* ssabs.c:35: qsBc, first/last char first */
     {"ts", SB_FAM_BF, SB_ANCHOR_PREFIX, 0, 0, 0, 1},           /* ts.c:25: Tailed-Substring, no tables */
+    {"skip", SB_FAM_SKIP, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},       /* skip.c:26: Skip-Search, bucket lists per character */
+    {"kmpskip", SB_FAM_KMPSKIP, SB_ANCHOR_SUFFIX, 0, 0, 0, 1}, /* kmpskip.c:59: buckets + mpNext + kmpNext */
+    {"fs", SB_FAM_FS, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},           /* fs.c:44: Fast-Search (bc over all m chars, Pre_GS) */
+    {"graspm", SB_FAM_GRASPM, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},   /* graspm.c:37: GRASPm (bc + lists keyed by x[i]) */
 };
 #define SB_NALGOS ((int)(sizeof(g_algos) / sizeof(g_algos[0])))
 
@@ -208,6 +212,64 @@ unsigned int sb_prep_sa(const unsigned char *x, int m, unsigned int *S)
     return 1u << (w - 1);
 }
 
+/* Bucket lists of Skip-Search and KMP-Skip-Search: head[c] = right-most index i with x[i] == c (-1 if none),
+ * next[i] = the next index to the left holding the same character (-1 at the end): the order in which the
+ * reference's linked lists are traversed (skip.c:31-39 pushes front; kmpskip.c:71-77 z[]/list[]). */
+void sb_prep_buckets(const unsigned char *x, int m, int *head, int *next)
+{
+    for (int c = 0; c < SB_SIGMA; c++) head[c] = -1;
+    for (int i = 0; i < m; i++) {
+        next[i] = head[x[i]];
+        head[x[i]] = i;
+    }
+}
+
+/* bc[c] = m-1 - (right-most index of c in the WHOLE pattern), m if absent: unlike hbc the last character
+ * counts, so bc[x[m-1]] == 0 stops the skip loop (fs.c:50-51, graspm.c:47-48, ffs.c:60-61) */
+void sb_prep_lastocc(const unsigned char *x, int m, int *bc)
+{
+    for (int c = 0; c < SB_SIGMA; c++) bc[c] = m;
+    for (int j = 0; j < m; j++) bc[x[j]] = m - 1 - j;
+}
+
+/* Fast-Search good-suffix table gs[0..m] (fs.c:26-41 Pre_GS): the classical Knuth/BM construction through
+ * the border array f of the reversed pattern.  Entries 1..m are used by the scan (gs[m-j+1]). */
+void sb_prep_fsgs(const unsigned char *x, int m, int *gs)
+{
+    static _Thread_local int f[SB_XSIZE + 2];
+    for (int i = 0; i <= m; i++) gs[i] = 0;
+    int j = m + 1;
+    f[m] = j;
+    for (int i = m; i > 0; i--) {
+        while (j <= m && x[i - 1] != x[j - 1]) {
+            if (gs[j] == 0) gs[j] = j - i;
+            j = f[j];
+        }
+        f[i - 1] = --j;
+    }
+    int p = f[0];
+    for (j = 0; j <= m; j++) {
+        if (gs[j] == 0) gs[j] = p;
+        if (j == p) p = f[p];
+    }
+}
+
+/* GRASPm candidate lists (graspm.c:41-45): for a text character c seen just before an occurrence of the
+ * pattern's last character, the alignments k to try: every k = i+1 with x[i] == c and x[i+1] == x[m-1]
+ * (right-most first), followed by k = 0 for EVERY c when x[0] == x[m-1].  Encoded as head[c] / next[k],
+ * -1 terminated; the shared tail element 0 has next[0] == -1. */
+void sb_prep_graspm(const unsigned char *x, int m, int *head, int *next)
+{
+    const int tail = (x[0] == x[m - 1]) ? 0 : -1;
+    for (int c = 0; c < SB_SIGMA; c++) head[c] = tail;
+    next[0] = -1;
+    for (int i = 0; i + 1 < m; i++)
+        if (x[i + 1] == x[m - 1]) {
+            next[i + 1] = head[x[i]];
+            head[x[i]] = i + 1;
+        }
+}
+
 /* BNDM: bit k of B[c] is set iff x[w-1-k] == c, over the first w = min(m,32) characters: the masks of the
  * REVERSED prefix (bndm.c:33-38; search_large keeps 32 characters, bndm.c:70-76) */
 void sb_prep_bndm(const unsigned char *x, int m, unsigned int *B)
@@ -324,6 +386,20 @@ int sb_prep_tables(int algo, const unsigned char *x, int m, sb_tables *out)
     case SB_FAM_AG:
         sb_prep_bmgs(x, m, out->suff, out->bmGs);
         sb_prep_hbc(x, m, out->hbc);
+        break;
+    case SB_FAM_SKIP: sb_prep_buckets(x, m, out->bucketHead, out->bucketNext); break;
+    case SB_FAM_KMPSKIP:
+        sb_prep_buckets(x, m, out->bucketHead, out->bucketNext);
+        sb_prep_mp(x, m, out->mpNext);
+        sb_prep_kmp(x, m, out->mpNext, out->kmpNext);
+        break;
+    case SB_FAM_FS:
+        sb_prep_lastocc(x, m, out->hbc);
+        sb_prep_fsgs(x, m, out->fsGs);
+        break;
+    case SB_FAM_GRASPM:
+        sb_prep_lastocc(x, m, out->hbc);
+        sb_prep_graspm(x, m, out->bucketHead, out->bucketNext);
         break;
     case SB_FAM_BNDM: sb_prep_bndm(x, m, out->bndmB); break;
     case SB_FAM_BR: sb_prep_brbc(x, m, out->brBc); break;

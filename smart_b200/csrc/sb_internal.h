@@ -28,7 +28,11 @@ enum sb_family {
     SB_FAM_AC,
     SB_FAM_BNDM,
     SB_FAM_BR,
-    SB_FAM_FJS
+    SB_FAM_FJS,
+    SB_FAM_SKIP,
+    SB_FAM_KMPSKIP,
+    SB_FAM_FS,
+    SB_FAM_GRASPM
 };
 
 /* which end of the pattern the candidate fingerprint is taken from: the left-to-right families
@@ -55,6 +59,10 @@ void sb_prep_suffixes(const unsigned char *x, int m, int *suff);
 void sb_prep_bmgs(const unsigned char *x, int m, int *suff, int *bmGs);
 unsigned int sb_prep_so(const unsigned char *x, int m, unsigned int *S);
 unsigned int sb_prep_sa(const unsigned char *x, int m, unsigned int *S);
+void sb_prep_buckets(const unsigned char *x, int m, int *head, int *next);
+void sb_prep_lastocc(const unsigned char *x, int m, int *bc);
+void sb_prep_fsgs(const unsigned char *x, int m, int *gs);
+void sb_prep_graspm(const unsigned char *x, int m, int *head, int *next);
 void sb_prep_bndm(const unsigned char *x, int m, unsigned int *B);
 void sb_prep_brbc(const unsigned char *x, int m, int *brBc);
 void sb_prep_hashq(const unsigned char *x, int m, int q, int *shift, int *sh1);

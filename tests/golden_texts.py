@@ -14,6 +14,7 @@ ALGOS = (
     "qf23", "qf24", "qf26", "qf28", "qf33", "qf34", "qf36", "qf42", "qf43", "qf44", "qf62", "qf63",
     "smith", "tbm", "ag", "ac",
     "bndm", "br", "tvsbs", "fjs", "ssabs", "ts",
+    "skip", "kmpskip", "fs", "graspm",
 )
 
 M_SET = (1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 14, 15, 16, 17, 24, 30, 31, 32, 33, 48, 62, 63, 64, 65, 100, 128, 256,

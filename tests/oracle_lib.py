@@ -106,6 +106,14 @@ class Oracle:
         if name == "kr":
             d, hx = C.c_int(0), C.c_int(0)
             L.ora_pre_kr(_ptr(x), m, C.byref(d), C.byref(hx)); return d.value, hx.value
+        if name == "buckets":
+            h, nx = ia(256), ia(m); L.ora_pre_buckets(_ptr(x), m, _ptr(h), _ptr(nx)); return h, nx
+        if name == "lastocc":
+            t = ia(256); L.ora_pre_lastocc(_ptr(x), m, _ptr(t)); return t
+        if name == "fsGs":
+            t = ia(m + 1); L.ora_pre_fsgs(_ptr(x), m, _ptr(t)); return t
+        if name == "graspm":
+            h, nx = ia(256), ia(m + 1); L.ora_pre_graspm(_ptr(x), m, _ptr(h), _ptr(nx)); return h, nx
         if name == "bndmB":
             t = np.zeros(256, dtype=np.uint32); L.ora_pre_bndm(_ptr(x), m, _ptr(t)); return t
         if name == "brBc":

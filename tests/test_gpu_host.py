@@ -50,12 +50,13 @@ def test_reference_harness_drives_our_executables(tmp_path, worker):
     (tmp_path / "source").mkdir()
     os.symlink(os.path.join(BIN, "algos"), tmp_path / "source" / "bin")
     for a in ("bf", "kmp", "mp", "hor", "bm", "qs", "so", "sa", "kr", "tunedbm", "raita", "hash3", "hash8", "qf23", "qf63",
-              "smith", "tbm", "ag", "ac", "bndm", "br", "tvsbs", "fjs", "ssabs", "ts"):
+              "smith", "tbm", "ag", "ac", "bndm", "br", "tvsbs", "fjs", "ssabs", "ts",
+              "skip", "kmpskip", "fs", "graspm"):
         r = run([os.path.join(REF, "test"), a], cwd=tmp_path, env=worker)
         assert "Test passed" in r.stdout and r.returncode == 0, (a, r.stdout[-300:], r.stderr[-300:])
     searches, uploads = stats(worker)
-    assert searches >= 25 * 10  # not-applicable cases never reach the worker
-    assert uploads >= 25  # tiny texts change with every case
+    assert searches >= 29 * 10  # not-applicable cases never reach the worker
+    assert uploads >= 29  # tiny texts change with every case
 
 
 def test_our_harness_strict_on_our_executables(worker):

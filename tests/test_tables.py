@@ -13,6 +13,12 @@ import smart_b200 as sb
 from golden_texts import GOLDEN
 
 
+def iter_list(e, nxt):
+    while e >= 0:
+        yield e
+        e = nxt[e]
+
+
 def arr(ct, k):
     return np.ctypeslib.as_array(ct)[:k].tolist()
 
@@ -43,6 +49,7 @@ def test_tables_vs_reference_dump(table_cases):
         if m >= 2:
             assert arr(sb.prep_tables("raita", x).hbc, 256) == ent["hbc"]
         assert arr(sb.prep_tables("tunedbm", x).hbc, 256) == ent["hbc"]
+        assert arr(sb.prep_tables("fs", x).fsGs, m + 1) == ent["fsGs"]  # Pre_GS dumped from fs.c
         br = np.ctypeslib.as_array(sb.prep_tables("br", x).brBc).astype(np.int32)
         assert hashlib.sha1(br.tobytes()).hexdigest() == ent["brBc_sha1"]  # preBrBc dumped from br.c
 
@@ -104,6 +111,18 @@ def test_tables_vs_oracle_random(oracle):
         for name in ("tbm", "ag"):
             t = sb.prep_tables(name, x)
             assert arr(t.bmGs, m) == oracle.table("bmGs", x).tolist() and arr(t.suff, m) == oracle.table("suff", x).tolist()
+        h, nx = oracle.table("buckets", x)
+        for name in ("skip", "kmpskip"):
+            t = sb.prep_tables(name, x)
+            assert arr(t.bucketHead, 256) == h.tolist() and arr(t.bucketNext, m) == nx.tolist()
+        t = sb.prep_tables("fs", x)
+        assert arr(t.hbc, 256) == oracle.table("lastocc", x).tolist() and arr(t.fsGs, m + 1) == oracle.table("fsGs", x).tolist()
+        t = sb.prep_tables("graspm", x)
+        h, nx = oracle.table("graspm", x)
+        assert arr(t.hbc, 256) == oracle.table("lastocc", x).tolist() and arr(t.bucketHead, 256) == h.tolist()
+        e_list = lambda head, nxt, c: [e for e in iter_list(head[c], nxt)]
+        for c in set(x.tolist()) | {0}:
+            assert e_list(arr(t.bucketHead, 256), arr(t.bucketNext, m + 1), c) == e_list(h.tolist(), nx.tolist(), c)
         assert arr(sb.prep_tables("bndm", x).bndmB, 256) == oracle.table("bndmB", x).tolist()
         for name in ("br", "tvsbs"):
             assert arr(sb.prep_tables(name, x).brBc, 65536) == oracle.table("brBc", x).tolist()
