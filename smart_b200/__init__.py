@@ -11,6 +11,9 @@ from .binding import (  # noqa: F401
     FLAG_FILTER_B8,
     FLAG_FILTER_B16,
     FLAG_FILTER_B32,
+    FLAG_FILTER_B4L8,
+    FLAG_FILTER_B4L16,
+    FLAG_FILTER_B8L16,
     FLAG_FILTER_SHIFT,
     FLAG_NO_SKIP,
     FLAG_DENSE,

@@ -31,6 +31,9 @@ FLAG_FILTER_B4 = 0x20
 FLAG_FILTER_B8 = 0x40
 FLAG_FILTER_B16 = 0x80
 FLAG_FILTER_B32 = 0x100
+FLAG_FILTER_B4L8 = 0x200
+FLAG_FILTER_B4L16 = 0x400
+FLAG_FILTER_B8L16 = 0x800
 
 ALGORITHMS = (
     "bf", "mp", "kmp", "bm", "hor", "qs", "raita", "tunedbm", "so", "sa", "kr",

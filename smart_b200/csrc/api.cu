@@ -77,7 +77,7 @@ struct DevCtx {                               // per-device scratch, created on 
     size_t pos_cap = 0;
     void *d_sort_temp = nullptr;              // cub::DeviceRadixSort scratch
     size_t sort_temp_bytes = 0;
-    int occ_block[4] = {0, 0, 0, 0};          // resident CTAs/SM for scan_block<4,8,16,32>
+    int occ_block[7] = {0};                   // resident CTAs/SM for scan_block<B,L>, index block_index()
     int occ_window[24] = {0};                 // ... for scan_window<NW,OFF,DENSE>, index window_index()
     int occ_short[7] = {0, 0, 0, 0, 0, 0, 0}; // ... for scan_short<MODE, FULL>; [6] = packed m=1
     unsigned long long *d_hist = nullptr;     // 256-bin byte histogram scratch
@@ -96,6 +96,12 @@ struct DevCtx {                               // per-device scratch, created on 
 
 DevCtx g_ctx[64];
 std::mutex g_mu;
+
+/* scan_block<B,L> variants: disjoint blocks (L == B) 4,8,16,32 and overlapping windows <4,8> <4,16> <8,16> */
+constexpr int block_index(int B, int L)
+{
+    return L == B ? (B == 4 ? 0 : B == 8 ? 1 : B == 16 ? 2 : 3) : (B == 4 && L == 8) ? 4 : (B == 4 && L == 16) ? 5 : 6;
+}
 
 constexpr int window_index(int nw, int off, bool dense) { return ((nw - 2) * 4 + (off - 1)) * 2 + (dense ? 1 : 0); }
 
@@ -150,10 +156,13 @@ DevCtx *get_ctx(int dev)
     c.occ_multi[0] = occupancy(sb::scan_multi_kernel<4, kU>);
     c.occ_multi[1] = occupancy(sb::scan_multi_kernel<8, kU>);
     c.occ_multi[2] = occupancy(sb::scan_multi_kernel<16, kU>);
-    c.occ_block[0] = occupancy(sb::scan_block_kernel<4, kU>);
-    c.occ_block[1] = occupancy(sb::scan_block_kernel<8, kU>);
-    c.occ_block[2] = occupancy(sb::scan_block_kernel<16, kU>);
-    c.occ_block[3] = occupancy(sb::scan_block_kernel<32, kU>);
+    c.occ_block[block_index(4, 4)] = occupancy(sb::scan_block_kernel<4, 4, kU>);
+    c.occ_block[block_index(8, 8)] = occupancy(sb::scan_block_kernel<8, 8, kU>);
+    c.occ_block[block_index(16, 16)] = occupancy(sb::scan_block_kernel<16, 16, kU>);
+    c.occ_block[block_index(32, 32)] = occupancy(sb::scan_block_kernel<32, 32, kU>);
+    c.occ_block[block_index(4, 8)] = occupancy(sb::scan_block_kernel<4, 8, kU>);
+    c.occ_block[block_index(4, 16)] = occupancy(sb::scan_block_kernel<4, 16, kU>);
+    c.occ_block[block_index(8, 16)] = occupancy(sb::scan_block_kernel<8, 16, kU>);
 #define SB_WIN_OCC(NW, OFF)                                                                       \
     c.occ_window[window_index(NW, OFF, false)] = occupancy(sb::scan_window_kernel<NW, OFF, false, kU>); \
     c.occ_window[window_index(NW, OFF, true)] = occupancy(sb::scan_window_kernel<NW, OFF, true, kU>);
@@ -223,29 +232,36 @@ uint32_t fingerprint(const unsigned char *p, int B)
     }
 }
 
-/* Which kernel scans a pattern of length m over a text with `bits` of collision entropy per byte.
- * 0 = scan_short (exact, m <= 4), 1/2/3 = scan_window (8/12/16-byte window at every position),
- * 4/8/16/32 = scan_block<B> (aligned-block fingerprints, needs m >= 2B-1).
- * The block kernels are the fast ones (16 ALU ops per 16 bytes) but a B-byte fingerprint lets a
- * fraction ~2^-(B*bits) of all start positions through to verification: pick the narrowest B whose
- * fingerprint carries >= 20 bits, else the widest feasible one if it still carries >= 14 bits, else the
- * per-position 8-byte window. */
-int choose_filter(int m, unsigned flags, double bits)
+/* Which kernel scans a pattern of length m over a text with `bits` of selectivity per byte (see
+ * collision_bits).  Returns the filter kind and, for scan_block, the fingerprint length L in *flen:
+ *   0 = scan_short (exact, m <= 4), 1/2/3 = scan_window (8/12/16-byte window at every position),
+ *   4/8/16/32 = scan_block<B,L>: B-aligned windows of L >= B bytes, needs m >= L+B-1.
+ * The block kernels are the fast ones (one compare per start position, no shifts) but an L-byte fingerprint
+ * lets ~2^-(L*bits) of all start positions through to verification: pick the shortest L that carries
+ * >= 20 bits (with the widest alignment B <= L that still fits the pattern), else the longest feasible L if it
+ * carries >= 14 bits (or is 32), else a per-position window. */
+int choose_filter(int m, unsigned flags, double bits, int *flen)
 {
-    if ((flags & SB_FLAG_FILTER_B32) && m >= 63) return 32;
-    if ((flags & SB_FLAG_FILTER_B16) && m >= 31) return 16;
-    if ((flags & SB_FLAG_FILTER_B8) && m >= 15) return 8;
-    if ((flags & SB_FLAG_FILTER_B4) && m >= 7) return 4;
+    static const int variants[7][2] = {{4, 4}, {8, 8}, {4, 8}, {16, 16}, {8, 16}, {4, 16}, {32, 32}};  // by L, widest B first
+    *flen = 0;
+    if ((flags & SB_FLAG_FILTER_B32) && m >= 63) return *flen = 32;
+    if ((flags & SB_FLAG_FILTER_B8L16) && m >= 23) return *flen = 16, 8;
+    if ((flags & SB_FLAG_FILTER_B4L16) && m >= 19) return *flen = 16, 4;
+    if ((flags & SB_FLAG_FILTER_B4L8) && m >= 11) return *flen = 8, 4;
+    if ((flags & SB_FLAG_FILTER_B16) && m >= 31) return *flen = 16;
+    if ((flags & SB_FLAG_FILTER_B8) && m >= 15) return *flen = 8;
+    if ((flags & SB_FLAG_FILTER_B4) && m >= 7) return *flen = 4;
     if (m <= 4) return kFilterShort;
     if (flags & SB_FLAG_FILTER_SHIFT) return kFilterWindow8;  // 8-byte window (exact for m <= 8)
-    int widest = 0;
-    for (int B = 4; B <= 32; B *= 2) {
-        if (2 * B - 1 > m) break;
-        widest = B;
-        if (B * bits >= 20.0) return B;
+    int bestB = 0, bestL = 0;
+    for (int v = 0; v < 7; v++) {
+        const int B = variants[v][0], L = variants[v][1];
+        if (L + B - 1 > m || L <= bestL) continue;  // infeasible, or a wider alignment of this L was taken
+        bestB = B;
+        bestL = L;
+        if (L * bits >= 20.0) return *flen = L, B;
     }
-    if (widest && widest * bits >= 14.0) return widest;
-    if (widest > 16) return widest;  // more selective than any per-position window
+    if (bestL && (bestL * bits >= 14.0 || bestL > 16)) return *flen = bestL, bestB;
     // per-position window of 2, 3 or 4 words: the narrowest that carries >= 14 bits, else the widest
     // that fits (a window never exceeds the pattern: min(m, 4*NW) bytes)
     for (int nw = 2; nw <= 4; nw++) {
@@ -284,6 +300,7 @@ double dense_bits()
 
 struct Plan {
     int filter;
+    int flen;           // scan_block: fingerprint length L (>= filter = B)
     int skip_grams;     // scan_skip: entries of the fingerprint list (= stride), 0 otherwise
     uint32_t list[4224]; // scan_skip: fingerprints of the pattern grams
     bool sparse;        // scan_short: a match of the whole pattern is rare in this text
@@ -293,7 +310,7 @@ struct Plan {
 void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m, unsigned flags, double bits)
 {
     memset(&pl.args, 0, sizeof pl.args);
-    pl.filter = choose_filter(m, flags, bits);
+    pl.filter = choose_filter(m, flags, bits, &pl.flen);
     pl.sparse = m * bits >= dense_bits() && !(flags & SB_FLAG_DENSE);  // scan_short; scan_window decides below
     pl.skip_grams = 0;
     sb::ScanArgs &a = pl.args;
@@ -310,7 +327,8 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
     /* Sub-linear sampling for the skip families: one G-byte gram every `stride` bytes (a multiple of the
      * 32-byte DRAM sector), G wide enough that a text gram rarely equals one of `stride` pattern grams. */
     const unsigned forced = SB_FLAG_FILTER_SHIFT | SB_FLAG_FILTER_B4 | SB_FLAG_FILTER_B8 | SB_FLAG_FILTER_B16 |
-                            SB_FLAG_FILTER_B32 | SB_FLAG_NO_SKIP;
+                            SB_FLAG_FILTER_B32 | SB_FLAG_FILTER_B4L8 | SB_FLAG_FILTER_B4L16 | SB_FLAG_FILTER_B8L16 |
+                            SB_FLAG_NO_SKIP;
     if (desc->anchor == SB_ANCHOR_SUFFIX && !(flags & forced)) {
         for (int G = 8; G <= 32; G *= 2) {
             const int stride = ((m - (G - 1)) / 32) * 32;
@@ -355,9 +373,9 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
         // when the window is the whole pattern and matches are frequent, count them in registers
         pl.sparse = !(m <= 4 * nw && (m * bits < dense_bits() || (flags & SB_FLAG_DENSE)));
     } else {
-        const int B = pl.filter;
-        a.anchor = desc->anchor == SB_ANCHOR_SUFFIX ? m - (2 * B - 1) : 0;
-        for (int d = 0; d < B; d++) a.H[d] = fingerprint(x + a.anchor + d, B);
+        const int B = pl.filter, L = pl.flen;
+        a.anchor = desc->anchor == SB_ANCHOR_SUFFIX ? m - (L + B - 1) : 0;
+        for (int d = 0; d < B; d++) a.H[d] = fingerprint(x + a.anchor + d, L);
     }
 }
 
@@ -393,9 +411,9 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
         per_sm = c.occ_window[window_index(pl.filter + 1, a.anchor, dense)];
     } else {
         group = kGroupLong;
-        const unsigned long long end = (unsigned long long)a.hi + a.anchor + 2 * pl.filter;
+        const unsigned long long end = (unsigned long long)a.hi + a.anchor + pl.filter + pl.flen;
         a.ngroups = (end + group - 1) / group;
-        per_sm = c.occ_block[pl.filter == 4 ? 0 : pl.filter == 8 ? 1 : pl.filter == 16 ? 2 : 3];
+        per_sm = c.occ_block[block_index(pl.filter, pl.flen)];
     }
     unsigned long long want = (a.ngroups + (sb::kThreads / 32) - 1) / (sb::kThreads / 32);
     unsigned long long maxb = (unsigned long long)c.sms * per_sm;
@@ -424,10 +442,17 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
         SB_WIN_LAUNCH(3, 1) SB_WIN_LAUNCH(3, 2) SB_WIN_LAUNCH(3, 3) SB_WIN_LAUNCH(3, 4)
         SB_WIN_LAUNCH(4, 1) SB_WIN_LAUNCH(4, 2) SB_WIN_LAUNCH(4, 3) SB_WIN_LAUNCH(4, 4)
 #undef SB_WIN_LAUNCH
-    } else if (pl.filter == 4) sb::scan_block_kernel<4, kU><<<grid, sb::kThreads, 0, stream>>>(a);
-    else if (pl.filter == 8) sb::scan_block_kernel<8, kU><<<grid, sb::kThreads, 0, stream>>>(a);
-    else if (pl.filter == 16) sb::scan_block_kernel<16, kU><<<grid, sb::kThreads, 0, stream>>>(a);
-    else sb::scan_block_kernel<32, kU><<<grid, sb::kThreads, 0, stream>>>(a);
+    } else {
+        switch (block_index(pl.filter, pl.flen)) {
+        case 0: sb::scan_block_kernel<4, 4, kU><<<grid, sb::kThreads, 0, stream>>>(a); break;
+        case 1: sb::scan_block_kernel<8, 8, kU><<<grid, sb::kThreads, 0, stream>>>(a); break;
+        case 2: sb::scan_block_kernel<16, 16, kU><<<grid, sb::kThreads, 0, stream>>>(a); break;
+        case 3: sb::scan_block_kernel<32, 32, kU><<<grid, sb::kThreads, 0, stream>>>(a); break;
+        case 4: sb::scan_block_kernel<4, 8, kU><<<grid, sb::kThreads, 0, stream>>>(a); break;
+        case 5: sb::scan_block_kernel<4, 16, kU><<<grid, sb::kThreads, 0, stream>>>(a); break;
+        default: sb::scan_block_kernel<8, 16, kU><<<grid, sb::kThreads, 0, stream>>>(a); break;
+        }
+    }
     return cudaGetLastError();
 }
 
@@ -951,7 +976,7 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
     g_timing.kernel_ms = kernel_ms;
     g_timing.wall_ms = t3 - t2;
     g_timing.kernels_launched = launched;
-    g_timing.filter_kind = pl.filter;
+    g_timing.filter_kind = (pl.filter >= 4 && pl.filter < kFilterSkip && pl.flen != pl.filter) ? pl.filter * 100 + pl.flen : pl.filter;
     g_timing.verified = verified;
     if (pre_ms) *pre_ms = t2 - t0;
     if (run_ms) *run_ms = (t3 - t2) > 0 ? (t3 - t2) : 1e-6;
@@ -1225,7 +1250,7 @@ long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned
     g_timing.upload_ms = t2 - t1;
     g_timing.wall_ms = t3 - t2;
     g_timing.kernels_launched = launched;
-    g_timing.filter_kind = pl.filter;
+    g_timing.filter_kind = (pl.filter >= 4 && pl.filter < kFilterSkip && pl.flen != pl.filter) ? pl.filter * 100 + pl.flen : pl.filter;
     g_timing.verified = c->h_counters[2];
     if (pre_ms) *pre_ms = t2 - t0;
     if (run_ms) *run_ms = (t3 - t2) > 0 ? (t3 - t2) : 1e-6;

@@ -9,10 +9,10 @@
  *     (ld.global.nc.L1::no_allocate.v8.u32 -> LDG.E.NA.ENL2.256), U independent loads in flight per
  *     thread, one warp per U KiB group, groups strided across a grid sized to the resident CTAs;
  *   - a packed candidate filter runs entirely in registers:
- *       * scan_block<B> (m >= 2B-1): every occurrence covers one B-aligned text block completely,
- *         so only ALIGNED blocks are fingerprinted (IMAD, FMA pipe) and compared with the B
- *         fingerprints of the pattern's B-grams at offsets a..a+B-1 (one ISETP.EQ.OR per start
- *         position, ALU pipe): no shifts, no halo, no shared memory;
+ *       * scan_block<B,L> (m >= L+B-1): every occurrence contains the L bytes that start at some
+ *         B-aligned text position, so only ALIGNED windows are fingerprinted (IMAD, FMA pipe) and
+ *         compared with the B fingerprints of the pattern's L-grams at offsets a..a+B-1 (one
+ *         ISETP.EQ.OR per start position, ALU pipe): no shifts, no shared memory, no halo when L == B;
  *       * scan_window<NW,OFF> (5 <= m, low-entropy texts or m < 2B-1): an 8/12/16-byte window
  *         fingerprint at EVERY start position (SHF funnel shift + IMAD + ISETP.EQ.OR per position);
  *         the halo comes from the neighbouring lane by shuffle, not from memory;
@@ -205,50 +205,51 @@ __device__ __forceinline__ void block_reduce_count(const ScanArgs &a, unsigned c
     }
 }
 
-/* ===================================================================== scan_block<B, U> */
+/* ===================================================================== scan_block<B, L, U> */
 
-/* Slow path of scan_block: some lane of this warp saw a fingerprint hit in its 32-byte vector.
- * For each such lane the whole warp re-derives which of the 32 (block, d) slots hit (one slot per
- * lane) and verifies each candidate cooperatively. */
 struct CandResult {
     unsigned cnt, nver;
     long long run_j;  // start of the last verified occurrence seen by this warp (-1: none)
 };
 
-template <int B>
+/* fingerprint of the L bytes starting at word q of W (L = 4, 8, 16 or 32; L == 32 only with q == 0) */
+template <int L>
+__device__ __forceinline__ uint32_t block_fp(const uint32_t *W, int q)
+{
+    if (L == 4) return W[q];
+    if (L == 8) return fp8(W[q], W[q + 1]);
+    if (L == 16) return fp16(W[q], W[q + 1], W[q + 2], W[q + 3]);
+    return fp32(fp16(W[0], W[1], W[2], W[3]), fp16(W[4], W[5], W[6], W[7]));
+}
+
+/* Slow path of scan_block: some lane of this warp saw a fingerprint hit in its 32-byte vector.
+ * For each such lane the whole warp re-derives which of the 32 (block, d) slots hit (one slot per
+ * lane) and verifies each candidate cooperatively.  v0..v10: the lane's 8 words + up to 3 halo words. */
+template <int B, int L>
 __device__ __noinline__ CandResult block_candidates(const ScanArgs &a, uint32_t v0, uint32_t v1, uint32_t v2,
                                                     uint32_t v3, uint32_t v4, uint32_t v5, uint32_t v6, uint32_t v7,
-                                                    long long voff, bool hit, unsigned lane, long long run_j)
+                                                    uint32_t v8, uint32_t v9, uint32_t v10, long long voff, bool hit,
+                                                    unsigned lane, long long run_j)
 {
     // everything by value and the result returned: a by-reference vector would force the caller to
     // keep a copy of every loaded vector in local memory (an STL per load in the hot loop)
-    const uint32_t vw[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
+    const uint32_t vw[11] = {v0, v1, v2, v3, v4, v5, v6, v7, v8, v9, v10};
+    constexpr int NWORDS = 8 + (L - B) / 4;
     unsigned cnt = 0, nver = 0;
     unsigned pending = __ballot_sync(kFull, hit);
     while (pending) {
         const int src = __ffs(pending) - 1;
         pending &= pending - 1;
-        uint32_t s[8];
+        uint32_t s[11];
 #pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = __shfl_sync(kFull, vw[i], src);
+        for (int i = 0; i < NWORDS; i++) s[i] = __shfl_sync(kFull, vw[i], src);
         const long long soff = __shfl_sync(kFull, voff, src);
         // slot of this lane; d runs DOWN inside a block so that the candidate positions of a vector are
         // visited in ascending order (the period-aware shortcut below relies on that)
         const int blk = (int)lane / B, d = B - 1 - (int)lane % B;
-        uint32_t h;
-        if (B == 4) {
-            h = s[0];
+        uint32_t h = block_fp<L>(s, 0);
 #pragma unroll
-            for (int i = 1; i < 8; i++) h = (blk == i) ? s[i] : h;
-        } else if (B == 8) {
-            h = fp8(s[0], s[1]);
-#pragma unroll
-            for (int i = 1; i < 4; i++) h = (blk == i) ? fp8(s[2 * i], s[2 * i + 1]) : h;
-        } else if (B == 16) {
-            h = blk ? fp16(s[4], s[5], s[6], s[7]) : fp16(s[0], s[1], s[2], s[3]);
-        } else {
-            h = fp32(fp16(s[0], s[1], s[2], s[3]), fp16(s[4], s[5], s[6], s[7]));
-        }
+        for (int i = 1; i < 32 / B; i++) h = (blk == i) ? block_fp<L>(s, i * (B / 4)) : h;
         unsigned slots = __ballot_sync(kFull, h == a.H[d]);
         while (slots) {
             const int sl = __ffs(slots) - 1;
@@ -280,41 +281,39 @@ __device__ __noinline__ CandResult block_candidates(const ScanArgs &a, uint32_t 
     return r;
 }
 
-template <int B>
-__device__ __forceinline__ bool block_hit(const ScanArgs &a, const V8 &v)
+/* B = alignment of the fingerprinted blocks = number of pattern alignments compared per block;
+ * L >= B = bytes fingerprinted from each block start.  L == B: disjoint blocks (no halo).  L > B: overlapping
+ * windows — the selectivity of L bytes for patterns as short as L+B-1 (e.g. B=4, L=8 from m = 11). */
+template <int B, int L>
+__device__ __forceinline__ bool block_hit(const ScanArgs &a, const uint32_t *W)
 {
     bool hit = false;
-    if (B == 4) {
+    if (L == 16 && B == 4) {  // share the 8-byte halves between the overlapping 16-byte windows
+        uint32_t g8[10];
 #pragma unroll
-        for (int w = 0; w < 8; w++)
+        for (int q = 0; q < 10; q++) g8[q] = fp8(W[q], W[q + 1]);
 #pragma unroll
-            for (int d = 0; d < 4; d++) hit |= (v.w[w] == a.H[d]);
-    } else if (B == 8) {
+        for (int q = 0; q < 8; q++) {
+            const uint32_t h = g8[q] * K2 + g8[q + 2];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t h = fp8(v.w[2 * k], v.w[2 * k + 1]);
-#pragma unroll
-            for (int d = 0; d < 8; d++) hit |= (h == a.H[d]);
+            for (int d = 0; d < 4; d++) hit |= (h == a.H[d]);
         }
-    } else if (B == 16) {
+        return hit;
+    }
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const uint32_t h = fp16(v.w[4 * k], v.w[4 * k + 1], v.w[4 * k + 2], v.w[4 * k + 3]);
+    for (int k = 0; k < 32 / B; k++) {
+        const uint32_t h = block_fp<L>(W, k * (B / 4));
 #pragma unroll
-            for (int d = 0; d < 16; d++) hit |= (h == a.H[d]);
-        }
-    } else {
-        const uint32_t h = fp32(fp16(v.w[0], v.w[1], v.w[2], v.w[3]), fp16(v.w[4], v.w[5], v.w[6], v.w[7]));
-#pragma unroll
-        for (int d = 0; d < 32; d++) hit |= (h == a.H[d]);
+        for (int d = 0; d < B; d++) hit |= (h == a.H[d]);
     }
     return hit;
 }
 
 /* group = U x 1 KiB per warp */
-template <int B, int U>
-__global__ void __launch_bounds__(kThreads, SB_MINB) scan_block_kernel(const __grid_constant__ ScanArgs a)
+template <int B, int L, int U>
+__global__ void __launch_bounds__(kThreads, L > B ? 3 : SB_MINB) scan_block_kernel(const __grid_constant__ ScanArgs a)
 {
+    constexpr int HALO = (L - B) / 4;  // words needed from the next lane
     const unsigned lane = threadIdx.x & 31;
     const unsigned long long warp = ((unsigned long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * kThreads) >> 5;
@@ -326,13 +325,32 @@ __global__ void __launch_bounds__(kThreads, SB_MINB) scan_block_kernel(const __g
         V8 v[U];
 #pragma unroll
         for (int c = 0; c < U; c++) v[c] = ldg_stream256(p + c * 1024);
+        uint32_t gnw[4] = {0u, 0u, 0u, 0u};
+        if (HALO > 0 && lane == 0) {  // halo of the last chunk's lane 31: first words of the next group
+            const uint4 gn = __ldg(reinterpret_cast<const uint4 *>(a.text + (g + 1) * (U * 1024ull)));
+            gnw[0] = gn.x;
+            gnw[1] = gn.y;
+            gnw[2] = gn.z;
+            gnw[3] = gn.w;
+        }
 #pragma unroll
         for (int c = 0; c < U; c++) {
-            const bool hit = block_hit<B>(a, v[c]);
+            uint32_t W[11];
+#pragma unroll
+            for (int i = 0; i < 8; i++) W[i] = v[c].w[i];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                W[8 + i] = 0u;
+                if (i < HALO) {
+                    const uint32_t nxt = (c + 1 < U) ? v[(c + 1 < U) ? c + 1 : c].w[i] : gnw[i];
+                    W[8 + i] = __shfl_sync(kFull, lane == 0 ? nxt : v[c].w[i], (lane + 1) & 31);
+                }
+            }
+            const bool hit = block_hit<B, L>(a, W);
             if (__any_sync(kFull, hit)) {
                 const long long voff = (long long)(g * (U * 1024ull)) + c * 1024 + lane * 32;
-                const CandResult r = block_candidates<B>(a, v[c].w[0], v[c].w[1], v[c].w[2], v[c].w[3], v[c].w[4],
-                                                         v[c].w[5], v[c].w[6], v[c].w[7], voff, hit, lane, run_j);
+                const CandResult r = block_candidates<B, L>(a, W[0], W[1], W[2], W[3], W[4], W[5], W[6], W[7], W[8],
+                                                            W[9], W[10], voff, hit, lane, run_j);
                 cnt += r.cnt;
                 nver += r.nver;
                 run_j = r.run_j;

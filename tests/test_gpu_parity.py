@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 # filter kinds reported by sb_last_timing: 0 scan_short, 1 scan_window8, 4/8/16/32 scan_block<B>
 FILTERS = {0: 0, 1: sb.FLAG_FILTER_SHIFT, 4: sb.FLAG_FILTER_B4, 8: sb.FLAG_FILTER_B8, 16: sb.FLAG_FILTER_B16,
-           32: sb.FLAG_FILTER_B32}
+           32: sb.FLAG_FILTER_B32, 408: sb.FLAG_FILTER_B4L8, 416: sb.FLAG_FILTER_B4L16, 816: sb.FLAG_FILTER_B8L16}
 
 
 def expected(algo, m, bf):
@@ -29,6 +29,7 @@ def expected(algo, m, bf):
 def filters_for(m):
     out = [0] if m <= 4 else [1]
     out += [b for b in (4, 8, 16, 32) if m >= 2 * b - 1]
+    out += [k for k, need in ((408, 11), (416, 19), (816, 23)) if m >= need]  # overlapping windows <B,L>
     return out
 
 
@@ -196,7 +197,7 @@ def test_low_entropy_windows(oracle):
     y = sb.textgen_host(0, 3_000_000, 2, 9)
     with sb.Text.upload(y) as t:
         kinds = {}
-        for m in (5, 6, 7, 8, 9, 11, 12, 13, 15, 16, 17, 23, 30, 31):
+        for m in (5, 6, 7, 8, 9, 11, 12, 13, 15, 16, 17, 19, 23, 30, 31):
             x = y[1_000_000 : 1_000_000 + m].copy()
             want = oracle.bf_positions(x, y)
             r = sb.search("bf", t, x)
@@ -204,8 +205,10 @@ def test_low_entropy_windows(oracle):
             assert r.count == want.size, m
             r = sb.search("kmp", t, x, flags=sb.FLAG_POSITIONS, positions_cap=y.size)
             assert np.array_equal(r.positions, want), m
-        # 5..8: two-word window == pattern; 9..12: three words; 13..30: four words (exact up to 16); 31+: block
-        assert [kinds[m] for m in (5, 8, 9, 12, 13, 15, 16, 30, 31)] == [1, 1, 2, 2, 3, 3, 3, 3, 16]
+        # 5..8: two-word window == pattern; 9..12: three words; 13..18: four words (exact up to 16);
+        # 19..22: 16-byte fingerprints at 4-byte alignment; 23..30: at 8-byte alignment; 31+: disjoint 16-byte blocks
+        assert [kinds[m] for m in (5, 8, 9, 12, 13, 15, 16, 17, 19, 23, 30, 31)] == \
+            [1, 1, 2, 2, 3, 3, 3, 3, 416, 816, 816, 16]
 
 
 def test_skip_kernel_is_selected_and_exact(oracle):
