@@ -298,13 +298,13 @@ __device__ __forceinline__ bool block_hit(const ScanArgs &a, const uint32_t *W)
 #pragma unroll
             for (int d = 0; d < 4; d++) hit |= (h == a.H[d]);
         }
-        return hit;
-    }
+    } else {
 #pragma unroll
-    for (int k = 0; k < 32 / B; k++) {
-        const uint32_t h = block_fp<L>(W, k * (B / 4));
+        for (int k = 0; k < 32 / B; k++) {
+            const uint32_t h = block_fp<L>(W, k * (B / 4));
 #pragma unroll
-        for (int d = 0; d < B; d++) hit |= (h == a.H[d]);
+            for (int d = 0; d < B; d++) hit |= (h == a.H[d]);
+        }
     }
     return hit;
 }
@@ -424,6 +424,8 @@ __global__ void __launch_bounds__(kThreads, NW == 2 ? 4 : 3) scan_window_kernel(
                 const uint32_t snd = lane == 0 ? nxt : v[c].w[i];
                 W[8 + i] = __shfl_sync(kFull, snd, (lane + 1) & 31);
             }
+            // shifted words for byte offsets 0 .. 31+LAST.  (Forming them on the idle FMA pipe instead, as
+            // hi*2^k + umulhi(lo, 2^k), was measured slower: IMAD.HI is not full rate.)
             uint32_t S[NS];
 #pragma unroll
             for (int b = 0; b < NS; b++)
