@@ -358,3 +358,33 @@ def test_multi_pattern_scan_equals_single_scans(oracle):
         counts, _, _ = sb.search_multi("kmp", t, pats)
         assert np.array_equal(counts, np.array([oracle.bf_count(p, y) for p in pats], dtype=np.uint64))
         assert counts.min() >= 1
+
+
+def test_64GiB_text_on_one_gpu(oracle):
+    """BASELINE configs[3] at full size on ONE B200 (64 GiB of its 180 GB): 64-bit offsets and counts.
+    The count of a text-extracted pattern equals the sum over 8 independently generated parts, and the
+    positions inside a host-regenerated window far beyond 2^32 are exactly the oracle's."""
+    n, sigma, seed = 64 << 30, 4, 640
+    win_lo, win_len = (40 << 30) + 12345 * 4096, 64 << 20
+    host_win = sb.textgen_host(win_lo, win_len, sigma, seed)
+    with sb.Text.generate(n, sigma, seed) as t:
+        assert len(t) == n
+        assert np.array_equal(t.download(win_lo + 4096, 1 << 16), host_win[4096:4096 + (1 << 16)])
+        whole = {}
+        for m in (8, 64, 1024):
+            x = host_win[777:777 + m].copy()
+            whole[m] = (x, sb.search("bf", t, x).count, sb.search("hor", t, x).count)
+            assert whole[m][1] >= 1 and whole[m][1] == whole[m][2]
+        x8 = whole[8][0]
+        r = sb.search("bf", t, x8, flags=sb.FLAG_POSITIONS, positions_cap=1 << 22)
+        assert r.count == whole[8][1] and r.count <= (1 << 22)
+        pos = r.positions
+        assert np.all(pos[1:] > pos[:-1]) and pos[-1] > (1 << 35)
+        inside = pos[(pos >= win_lo) & (pos + 8 <= win_lo + win_len)] - win_lo
+        assert np.array_equal(inside, oracle.bf_positions(x8, host_win, cap=1 << 20))
+    parts = {m: 0 for m in whole}
+    for g in range(8):
+        with sb.Text.generate_part(n, sigma, seed, 8, g) as part:
+            for m, (x, _, _) in whole.items():
+                parts[m] += sb.search("kmp", part, x).count
+    assert {m: v[1] for m, v in whole.items()} == parts
