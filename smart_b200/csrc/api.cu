@@ -298,6 +298,17 @@ double dense_bits()
     return v;
 }
 
+/* SMART_B200_TMA=1 routes the disjoint-block filters through the TMA/shared-memory variant (experiment) */
+bool use_tma()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SMART_B200_TMA");
+        v = (e && atoi(e) > 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+
 struct Plan {
     int filter;
     int flen;           // scan_block: fingerprint length L (>= filter = B)
@@ -442,6 +453,26 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
         SB_WIN_LAUNCH(3, 1) SB_WIN_LAUNCH(3, 2) SB_WIN_LAUNCH(3, 3) SB_WIN_LAUNCH(3, 4)
         SB_WIN_LAUNCH(4, 1) SB_WIN_LAUNCH(4, 2) SB_WIN_LAUNCH(4, 3) SB_WIN_LAUNCH(4, 4)
 #undef SB_WIN_LAUNCH
+    } else if (pl.flen == pl.filter && use_tma()) {
+        // experiment: the same filter fed by TMA bulk copies through shared memory
+        static const int stages = getenv("SMART_B200_TMA_STAGES") ? atoi(getenv("SMART_B200_TMA_STAGES")) : sb::kTmaStages;
+        static const int ctas = getenv("SMART_B200_TMA_CTAS") ? atoi(getenv("SMART_B200_TMA_CTAS")) : 6;
+        a.stride = stages;
+        const size_t smem = (size_t)stages * sb::kTmaTile + 2 * stages * sizeof(uint64_t);
+        const unsigned long long end = (unsigned long long)a.hi + a.anchor + 2 * pl.filter;
+        a.nsamples = round_up(end, 4096);  // within the zero padding of the shard buffer (kPadBytes rule)
+        a.ngroups = (a.nsamples + sb::kTmaTile - 1) / sb::kTmaTile;
+        const unsigned g = (unsigned)std::max(1ull, std::min<unsigned long long>(a.ngroups, (unsigned long long)ctas * c.sms));
+#define SB_TMA_LAUNCH(B)                                                                                         \
+    {                                                                                                            \
+        cudaFuncSetAttribute(sb::scan_block_tma_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        sb::scan_block_tma_kernel<B><<<g, sb::kTmaThreads, smem, stream>>>(a);                                   \
+    }
+        if (pl.filter == 4) SB_TMA_LAUNCH(4)
+        else if (pl.filter == 8) SB_TMA_LAUNCH(8)
+        else if (pl.filter == 16) SB_TMA_LAUNCH(16)
+        else SB_TMA_LAUNCH(32)
+#undef SB_TMA_LAUNCH
     } else {
         switch (block_index(pl.filter, pl.flen)) {
         case 0: sb::scan_block_kernel<4, 4, kU><<<grid, sb::kThreads, 0, stream>>>(a); break;

@@ -360,6 +360,140 @@ __global__ void __launch_bounds__(kThreads, L > B ? 3 : SB_MINB) scan_block_kern
     block_reduce_count(a, cnt, nver);
 }
 
+
+/* ===================================================================== scan_block_tma<B> (experiment) */
+
+/* The same aligned-block filter fed by TMA bulk copies instead of per-thread loads: one elected producer thread
+ * streams 16 KiB tiles global -> shared with cp.async.bulk (UBLKCP) into a ring of kTmaStages buffers,
+ * completion signalled on an mbarrier per stage; 8 consumer warps read their 2 KiB slice of the tile with
+ * LDS.128, run block_hit / block_candidates, and release the stage through a second mbarrier.
+ * Kept to MEASURE the claim of DESIGN.md section 3.3 (no reuse => shared-memory staging cannot beat register
+ * streaming); selected only with SMART_B200_TMA=1. */
+constexpr int kTmaTile = 16384;
+constexpr int kTmaStages = 2;  // default ring depth x 6 CTAs/SM (a.stride overrides): best of the r1 sweep
+constexpr int kTmaThreads = 288;  // 8 consumer warps + 1 producer warp
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_load(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int B>
+__global__ void __launch_bounds__(kTmaThreads, 1) scan_block_tma_kernel(const __grid_constant__ ScanArgs a)
+{
+    extern __shared__ __align__(128) uint8_t tma_smem[];
+    uint8_t *tiles = tma_smem;
+    const int stages = a.stride;                 // ring depth
+    const unsigned long long limit = a.nsamples;  // readable bytes of the shard buffer (multiple of 16)
+    uint64_t *full = reinterpret_cast<uint64_t *>(tma_smem + stages * kTmaTile);
+    uint64_t *empty = full + stages;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long ntiles = a.ngroups;  // here: number of 16 KiB tiles
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned cnt = 0, nver = 0;
+    long long run_j = -1;
+    if (warp == 8) {
+        if (lane == 0) {  // producer
+            unsigned k = 0;
+            for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
+                const int s = k % stages;
+                const unsigned round = k / stages;
+                if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+                const unsigned long long off = tile * kTmaTile;
+                const unsigned bytes = (unsigned)min((unsigned long long)kTmaTile, limit - off);
+                mbar_expect_tx(&full[s], bytes);  // a short last tile leaves stale bytes behind it: they can only
+                tma_bulk_load(tiles + s * kTmaTile, a.text + off, bytes, &full[s]);  // add candidates >= hi
+            }
+        }
+    } else {
+        unsigned k = 0;
+        for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
+            const int s = k % stages;
+            mbar_wait(&full[s], (k / stages) & 1);
+            const uint8_t *slice = tiles + s * kTmaTile + warp * 2048;
+            V8 v[2];
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const uint4 lo = *reinterpret_cast<const uint4 *>(slice + c * 1024 + lane * 32);
+                const uint4 hi = *reinterpret_cast<const uint4 *>(slice + c * 1024 + lane * 32 + 16);
+                v[c].w[0] = lo.x; v[c].w[1] = lo.y; v[c].w[2] = lo.z; v[c].w[3] = lo.w;
+                v[c].w[4] = hi.x; v[c].w[5] = hi.y; v[c].w[6] = hi.z; v[c].w[7] = hi.w;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);  // the slice is in registers: the stage may be refilled
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const bool hit = block_hit<B, B>(a, v[c].w);
+                if (__any_sync(kFull, hit)) {
+                    const long long voff = (long long)(tile * kTmaTile) + warp * 2048 + c * 1024 + lane * 32;
+                    const CandResult r = block_candidates<B, B>(a, v[c].w[0], v[c].w[1], v[c].w[2], v[c].w[3], v[c].w[4],
+                                                                v[c].w[5], v[c].w[6], v[c].w[7], 0u, 0u, 0u, voff, hit,
+                                                                lane, run_j);
+                    cnt += r.cnt;
+                    nver += r.nver;
+                    run_j = r.run_j;
+                }
+            }
+        }
+    }
+    // block_reduce_count expects kThreads; reduce here over the 9 warps
+    __shared__ unsigned t_cnt[9], t_ver[9];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(kFull, cnt, o);
+        nver += __shfl_xor_sync(kFull, nver, o);
+    }
+    if (lane == 0) {
+        t_cnt[warp] = cnt;
+        t_ver[warp] = nver;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long c = 0, v = 0;
+        for (int w = 0; w < 9; w++) {
+            c += t_cnt[w];
+            v += t_ver[w];
+        }
+        if (c) atomicAdd(a.counters + 0, c);
+        if (v) atomicAdd(a.counters + 2, v);
+    }
+}
+
 /* ===================================================================== scan_window<NW, OFF, DENSE, U> */
 
 /* Per-lane slow path of scan_window: `mm` has bit p set for every start position p of this lane's

@@ -388,3 +388,43 @@ def test_64GiB_text_on_one_gpu(oracle):
             for m, (x, _, _) in whole.items():
                 parts[m] += sb.search("kmp", part, x).count
     assert {m: v[1] for m, v in whole.items()} == parts
+
+
+_TMA_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import smart_b200 as sb
+from oracle_lib import Oracle
+ora = Oracle()
+FL = {4: sb.FLAG_FILTER_B4, 8: sb.FLAG_FILTER_B8, 16: sb.FLAG_FILTER_B16, 32: sb.FLAG_FILTER_B32}
+for sigma, n in ((4, 3 * (1 << 20) + 8193), (256, (1 << 20) + 5), (2, 40000), (256, 16384), (4, 70)):
+    y = sb.textgen_host(0, n, sigma, 77 + sigma)
+    with sb.Text.upload(y) as t:
+        for m in (7, 15, 31, 63, 64, 200):
+            if m > n:
+                continue
+            for k in (0, n // 2, n - m):
+                x = y[k:k + m].copy()
+                want = ora.search("bf", x, y)
+                for B, f in FL.items():
+                    if m < 2 * B - 1:
+                        continue
+                    r = sb.search("bf", t, x, flags=f | sb.FLAG_NO_SKIP | sb.FLAG_POSITIONS, positions_cap=want + 4)
+                    assert r.count == want, (sigma, n, m, k, B, r.count, want)
+                    assert n < 4096 or sb.last_timing().filter_kind == B, (sigma, n, m, B, sb.last_timing().filter_kind)
+                    assert np.array_equal(r.positions, ora.bf_positions(x, y)), (sigma, n, m, B)
+print("tma-ok")
+"""
+
+
+def test_tma_fed_block_kernel_matches_oracle():
+    """SMART_B200_TMA=1 feeds the disjoint-block filter through cp.async.bulk + mbarrier rings instead of
+    per-thread 256-bit loads (DESIGN.md section 3.3 experiment); the answers must not change.  Own process:
+    the switch is read once per library load."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SMART_B200_TMA="1")
+    r = subprocess.run([sys.executable, "-c", _TMA_SCRIPT, root], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "tma-ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
