@@ -37,7 +37,7 @@ GIB = 1 << 30
 METRIC = "text GB/s scanned (HBM-resident)"
 UNIT = "GB/s"
 SEED = 20261018
-FILTER_NAMES = {0: "scan_short_kernel", 1: "scan_window8_kernel", 4: "scan_block_kernel<4>",
+FILTER_NAMES = {0: "scan_swar_kernel", 1: "scan_window8_kernel", 4: "scan_block_kernel<4>",
                 8: "scan_block_kernel<8>", 16: "scan_block_kernel<16>", 32: "scan_block_kernel<32>",
                 108: "scan_skip_kernel<8>", 116: "scan_skip_kernel<16>", 132: "scan_skip_kernel<32>"}
 

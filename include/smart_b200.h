@@ -136,7 +136,7 @@ typedef struct sb_timing {
     double kernel_ms;      /* max over shards of the CUDA-event time of the scan kernel(s) */
     double wall_ms;        /* host wall clock, first launch -> last count on host */
     int kernels_launched;  /* scan kernels launched by the last search (all shards) */
-    int filter_kind;       /* 0 = scan_short, 1/2/3 = scan_window 8/12/16 B, 4/8/16/32 = scan_block<B,B>,
+    int filter_kind;       /* 0 = scan_swar (m <= 4), 1/2/3 = scan_window 8/12/16 B, 4/8/16/32 = scan_block<B,B>,
                               408/416/816 = scan_block<B,L> (overlapping windows),
                               108/116/132 = scan_skip<G>, 204/208/216 = scan_multi<B>, -1 = per-pattern fallback */
     unsigned long long verified; /* candidates sent to exact verification (all shards) */

@@ -56,7 +56,6 @@ constexpr size_t kPatBytes = 4352;            // device pattern buffer (>= SB_XS
 #endif
 constexpr int kU = SB_U;                      // 256-bit loads in flight per thread (scan_block / scan_window8)
 constexpr size_t kGroupLong = kU * 1024;      // bytes per warp iteration of those kernels
-constexpr size_t kGroupShort = 4 * 512;       // ... of scan_short
 constexpr int kFilterShort = 0, kFilterWindow8 = 1, kFilterWindow16 = 3;  // 2 = the 12-byte window
 constexpr int kFilterSkip = 100;              // + gram bytes (108, 116, 132): scan_skip<G>
 constexpr size_t kAuxWords = sb::kBloomWords + 2 * sb::kSkipTableSize;
@@ -79,7 +78,7 @@ struct DevCtx {                               // per-device scratch, created on 
     size_t sort_temp_bytes = 0;
     int occ_block[7] = {0};                   // resident CTAs/SM for scan_block<B,L>, index block_index()
     int occ_window[24] = {0};                 // ... for scan_window<NW,OFF,DENSE>, index window_index()
-    int occ_short[7] = {0, 0, 0, 0, 0, 0, 0}; // ... for scan_short<MODE, FULL>; [6] = packed m=1
+    int occ_swar[8] = {0};                    // ... for scan_swar<M, DENSE>, index (M-1)*2 + DENSE
     unsigned long long *d_hist = nullptr;     // 256-bin byte histogram scratch
     uint32_t *d_aux = nullptr, *h_aux = nullptr; // scan_skip / scan_multi: Bloom bitmap + exact fingerprint table
     uint32_t *d_mpat = nullptr;               // scan_multi: pattern set (words), grown on demand
@@ -170,13 +169,11 @@ DevCtx *get_ctx(int dev)
     SB_WIN_OCC(3, 1) SB_WIN_OCC(3, 2) SB_WIN_OCC(3, 3) SB_WIN_OCC(3, 4)
     SB_WIN_OCC(4, 1) SB_WIN_OCC(4, 2) SB_WIN_OCC(4, 3) SB_WIN_OCC(4, 4)
 #undef SB_WIN_OCC
-    c.occ_short[0] = occupancy(sb::scan_short_kernel<0, false>);
-    c.occ_short[1] = occupancy(sb::scan_short_kernel<0, true>);
-    c.occ_short[2] = occupancy(sb::scan_short_kernel<1, false>);
-    c.occ_short[3] = occupancy(sb::scan_short_kernel<1, true>);
-    c.occ_short[4] = occupancy(sb::scan_short_kernel<2, false>);
-    c.occ_short[5] = occupancy(sb::scan_short_kernel<2, true>);
-    c.occ_short[6] = occupancy(sb::scan_short_kernel<3, false>);
+#define SB_OCC_SWAR(M)                                                        \
+    c.occ_swar[(M - 1) * 2] = occupancy(sb::scan_swar_kernel<M, false>); \
+    c.occ_swar[(M - 1) * 2 + 1] = occupancy(sb::scan_swar_kernel<M, true>);
+    SB_OCC_SWAR(1) SB_OCC_SWAR(2) SB_OCC_SWAR(3) SB_OCC_SWAR(4)
+#undef SB_OCC_SWAR
     c.ready = true;
     return &c;
 }
@@ -234,7 +231,7 @@ uint32_t fingerprint(const unsigned char *p, int B)
 
 /* Which kernel scans a pattern of length m over a text with `bits` of selectivity per byte (see
  * collision_bits).  Returns the filter kind and, for scan_block, the fingerprint length L in *flen:
- *   0 = scan_short (exact, m <= 4), 1/2/3 = scan_window (8/12/16-byte window at every position),
+ *   0 = scan_swar (exact, m <= 4), 1/2/3 = scan_window (8/12/16-byte window at every position),
  *   4/8/16/32 = scan_block<B,L>: B-aligned windows of L >= B bytes, needs m >= L+B-1.
  * The block kernels are the fast ones (one compare per start position, no shifts) but an L-byte fingerprint
  * lets ~2^-(L*bits) of all start positions through to verification: pick the shortest L that carries
@@ -314,7 +311,7 @@ struct Plan {
     int flen;           // scan_block: fingerprint length L (>= filter = B)
     int skip_grams;     // scan_skip: entries of the fingerprint list (= stride), 0 otherwise
     uint32_t list[4224]; // scan_skip: fingerprints of the pattern grams
-    bool sparse;        // scan_short: a match of the whole pattern is rare in this text
+    bool sparse;        // scan_swar: a match of the whole pattern is rare in this text
     sb::ScanArgs args;  // text/base/hi/ngroups/counters/pos filled per shard
 };
 
@@ -322,7 +319,7 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
 {
     memset(&pl.args, 0, sizeof pl.args);
     pl.filter = choose_filter(m, flags, bits, &pl.flen);
-    pl.sparse = m * bits >= dense_bits() && !(flags & SB_FLAG_DENSE);  // scan_short; scan_window decides below
+    pl.sparse = m * bits >= dense_bits() && !(flags & SB_FLAG_DENSE);  // scan_swar; scan_window decides below
     pl.skip_grams = 0;
     sb::ScanArgs &a = pl.args;
     a.m = m;
@@ -410,11 +407,13 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
         else sb::scan_skip_kernel<32><<<g, sb::kThreads, 0, stream>>>(a);
         return cudaGetLastError();
     }
-    if (pl.filter == kFilterShort) {
-        group = kGroupShort;
+    const bool swar = pl.filter == kFilterShort;  // m <= 4: the SIMD-within-a-register kernel
+    const bool swar_dense = !pl.sparse && !want_pos;
+    if (swar) {
+        a.period = 1;  // the kernel's multiplier-by-one (see scan_swar_kernel)
+        group = kGroupLong;
         a.ngroups = ((unsigned long long)a.hi + group - 1) / group;
-        const int mode = pl.sparse ? 2 : (want_pos ? 1 : (a.m == 1 ? 3 : 0));
-        per_sm = mode == 3 ? c.occ_short[6] : c.occ_short[mode * 2 + (a.m == 4 ? 1 : 0)];
+        per_sm = c.occ_swar[(a.m - 1) * 2 + (swar_dense ? 1 : 0)];
     } else if (pl.filter <= kFilterWindow16) {
         group = kGroupLong;
         a.ngroups = ((unsigned long long)a.hi + group - 1) / group;
@@ -429,16 +428,14 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
     unsigned long long want = (a.ngroups + (sb::kThreads / 32) - 1) / (sb::kThreads / 32);
     unsigned long long maxb = (unsigned long long)c.sms * per_sm;
     unsigned grid = (unsigned)std::max(1ull, std::min(want, maxb));
-    if (pl.filter == kFilterShort) {
-        const int mode = pl.sparse ? 2 : (want_pos ? 1 : (a.m == 1 ? 3 : 0));
-        const bool full = a.m == 4;
-        if (mode == 3) sb::scan_short_kernel<3, false><<<grid, sb::kThreads, 0, stream>>>(a);
-        else if (mode == 0 && !full) sb::scan_short_kernel<0, false><<<grid, sb::kThreads, 0, stream>>>(a);
-        else if (mode == 0) sb::scan_short_kernel<0, true><<<grid, sb::kThreads, 0, stream>>>(a);
-        else if (mode == 1 && !full) sb::scan_short_kernel<1, false><<<grid, sb::kThreads, 0, stream>>>(a);
-        else if (mode == 1) sb::scan_short_kernel<1, true><<<grid, sb::kThreads, 0, stream>>>(a);
-        else if (!full) sb::scan_short_kernel<2, false><<<grid, sb::kThreads, 0, stream>>>(a);
-        else sb::scan_short_kernel<2, true><<<grid, sb::kThreads, 0, stream>>>(a);
+    if (swar) {
+#define SB_SWAR_LAUNCH(M)                                                                      \
+    if (a.m == M) {                                                                            \
+        if (swar_dense) sb::scan_swar_kernel<M, true><<<grid, sb::kThreads, 0, stream>>>(a);   \
+        else sb::scan_swar_kernel<M, false><<<grid, sb::kThreads, 0, stream>>>(a);             \
+    }
+        SB_SWAR_LAUNCH(1) SB_SWAR_LAUNCH(2) SB_SWAR_LAUNCH(3) SB_SWAR_LAUNCH(4)
+#undef SB_SWAR_LAUNCH
     } else if (pl.filter <= kFilterWindow16) {
         const int off = a.anchor;
         const bool dense = !pl.sparse && !want_pos;

@@ -16,7 +16,8 @@
  *       * scan_window<NW,OFF> (5 <= m, low-entropy texts or m < 2B-1): an 8/12/16-byte window
  *         fingerprint at EVERY start position (SHF funnel shift + IMAD + ISETP.EQ.OR per position);
  *         the halo comes from the neighbouring lane by shuffle, not from memory;
- *       * scan_short (m <= 4): exact masked-word compare at every position, counted in registers;
+ *       * scan_swar<M> (m <= 4): exact byte-parallel compare, four start positions per instruction,
+ *         counted with POPC in registers;
  *   - candidates (rare) go to an exact verification that reads the text through L2 with unaligned
  *     32-bit windows (warp-cooperative, 128 bytes per step, in scan_block);
  *   - counts are reduced with warp shuffles and ONE atomicAdd per block.
@@ -63,7 +64,7 @@ struct ScanArgs {
     int nwords;                   // ceil(m/4)
     uint32_t tailmask;            // mask for the last pattern word
     uint32_t H[32];               // scan_block: fingerprints of x[a+d .. a+d+B), d < B
-    uint32_t X0, X1, M0;          // scan_short: masked first word; scan_window: first and (NW=2) second word
+    uint32_t X0, X1, M0;          // scan_swar: masked first word; scan_window: first and (NW=2) second word
     uint32_t Xw[3];               // scan_window: window words 1..NW-1 (Xw[NW-2] is the last one)
     uint32_t G;                   // scan_window: fingerprint of the window words
     // scan_skip: one G-byte gram is sampled every `stride` bytes; aux = Bloom bitmap (kBloomWords words)
@@ -829,11 +830,25 @@ __global__ void __launch_bounds__(kThreads) scan_multi_kernel(const __grid_const
     block_reduce_count(a, 0u, nver);
 }
 
-/* ===================================================================== scan_short (m <= 4) */
+/* ===================================================================== scan_swar<M, DENSE> */
 
-/* Per-lane tail of scan_short when positions are wanted or the vector straddles the owned range:
- * `mm` has bit p set for every start position p of this lane's 16-byte vector that matches. */
-__device__ __noinline__ unsigned short_candidates(const ScanArgs &a, unsigned mm, long long voff)
+/* Patterns of M <= 4 bytes, four start positions per instruction (SIMD within a register).
+ * For text word w at byte offset o and the words w_i = text[o+i .. o+i+4) (funnel shifts of two loaded words),
+ *     t = (w_0 ^ splat(x[0])) | (w_1 ^ splat(x[1])) | ... | (w_{M-1} ^ splat(x[M-1]))
+ * has byte k equal to zero exactly when x occurs at o + k.  ((t & 0x7f7f7f7f) + 0x7f7f7f7f) | t has bit 7 of
+ * byte k set exactly when byte k of t is non-zero (no carries between bytes), so its complement & 0x80808080
+ * marks the occurrences: exact, no verification.  Cost per 4 positions: (M-1) SHF + M LOP3 + LOP3 + ADD + LOP3, against
+ * one SHF + (LOP3) + ISETP per POSITION for a word compare at every byte offset.
+ * DENSE: occurrences are counted with POPC in registers (no position output).
+ * !DENSE: the nz words of a 32-byte vector are AND-reduced and only a vector that holds an occurrence takes the
+ *         per-position path (count + optional position output).
+ * 256-bit loads, U = 4 in flight, the halo word of the next lane by shuffle (M > 1). */
+__device__ __forceinline__ uint32_t movemask4(uint32_t z)  // bits 7,15,23,31 -> bits 0..3
+{
+    return ((z >> 7) * 0x10204080u) >> 28;
+}
+
+__device__ __noinline__ unsigned swar_candidates(const ScanArgs &a, unsigned mm, long long voff)
 {
     unsigned cnt = 0;
     while (mm) {
@@ -847,71 +862,73 @@ __device__ __noinline__ unsigned short_candidates(const ScanArgs &a, unsigned mm
     return cnt;
 }
 
-/* MODE 3: packed - m == 1 without position output: the four bytes of a word are compared at once with the
- *                  exact zero-byte test ~(((t & 0x7f..) + 0x7f..) | t | 0x7f..) and counted with POPC
- *                  (6 ops per 4 positions, no funnel shifts, no halo);
- * MODE 0: dense  - count every position in registers (no position output);
- * MODE 1: dense  - collect a per-position mask and post-process (position output);
- * MODE 2: sparse - OR-reduce the compares (one ISETP.EQ.OR per position) and only build the mask when some
- *                  position of the vector matched: for texts where a match of m bytes is rare (m*bits >= 18).
- * FULL: m == 4, the mask M0 is all ones and is dropped.  128-bit loads, 4 in flight. */
-template <int MODE, bool FULL>
-__global__ void __launch_bounds__(kThreads) scan_short_kernel(const __grid_constant__ ScanArgs a)
+template <int M, bool DENSE>
+__global__ void __launch_bounds__(kThreads) scan_swar_kernel(const __grid_constant__ ScanArgs a)
 {
     constexpr int U = 4;
+    constexpr uint32_t K7 = 0x7f7f7f7fu, K8 = 0x80808080u;
     const unsigned lane = threadIdx.x & 31;
     const unsigned long long warp = ((unsigned long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * kThreads) >> 5;
+    uint32_t C[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) C[i] = ((a.X0 >> (8 * i)) & 0xffu) * 0x01010101u;
+    const uint32_t one = (uint32_t)a.period;  // set to 1 by launch_scan
     unsigned cnt = 0;
 
     for (unsigned long long g = warp; g < a.ngroups; g += nwarps) {
-        const uint8_t *p = a.text + g * (U * 512ull) + lane * 16;
-        uint4 v[U];
+        const uint8_t *p = a.text + g * (U * 1024ull) + lane * 32;
+        V8 v[U];
 #pragma unroll
-        for (int c = 0; c < U; c++) v[c] = ldg_stream128(p + c * 512);
+        for (int c = 0; c < U; c++) v[c] = ldg_stream256(p + c * 1024);
         uint32_t gn = 0;
-        if (lane == 0) gn = __ldg(reinterpret_cast<const uint32_t *>(a.text + (g + 1) * (U * 512ull)));
+        if (M > 1 && lane == 0) gn = __ldg(reinterpret_cast<const uint32_t *>(a.text + (g + 1) * (U * 1024ull)));
 #pragma unroll
         for (int c = 0; c < U; c++) {
-            uint32_t sx;
-            if (c + 1 < U)
-                sx = lane == 0 ? v[c + 1].x : v[c].x;
-            else
-                sx = lane == 0 ? gn : v[c].x;
-            const long long voff = (long long)(g * (U * 512ull)) + c * 512 + lane * 16;
-            if (MODE == 3 && voff + 16 <= a.hi) {
-                const uint32_t splat = a.X0 * 0x01010101u;
-                const uint32_t w4[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+            uint32_t W[9];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t t = w4[k] ^ splat;
-                    cnt += __popc(~(((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t | 0x7f7f7f7fu));
+            for (int i = 0; i < 8; i++) W[i] = v[c].w[i];
+            W[8] = 0u;
+            if (M > 1) {
+                const uint32_t nxt = (c + 1 < U) ? v[(c + 1 < U) ? c + 1 : c].w[0] : gn;
+                W[8] = __shfl_sync(kFull, lane == 0 ? nxt : v[c].w[0], (lane + 1) & 31);
+            }
+            const long long voff = (long long)(g * (U * 1024ull)) + c * 1024 + lane * 32;
+            if (M == 4 && !DENSE) {
+                // rare 4-byte pattern: one SHF + one ISETP.EQ.OR per position is cheaper than the byte-parallel
+                // test (7 against 9 ALU operations per word); the SIMD test below runs only on a hit
+                bool hit = false;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    hit |= (W[k] == a.X0);
+#pragma unroll
+                    for (int i = 1; i < 4; i++) hit |= (__funnelshift_r(W[k], W[k + 1], 8 * i) == a.X0);
                 }
-                continue;
+                if (!hit) continue;
             }
-            // m == 1 needs no halo, and its straddling lanes must not wait in a full-mask shuffle the others skip
-            const uint32_t nx = MODE == 3 ? 0u : __shfl_sync(kFull, sx, (lane + 1) & 31);
-            const uint32_t W[5] = {v[c].x, v[c].y, v[c].z, v[c].w, nx};
-            uint32_t S[16];
+            uint32_t z[8];  // bit 7 of byte b of z[k] set <=> occurrence at voff + 4k + b
 #pragma unroll
-            for (int b = 0; b < 16; b++) {
-                const uint32_t lo = (b & 3) ? __funnelshift_r(W[b >> 2], W[(b >> 2) + 1], 8 * (b & 3)) : W[b >> 2];
-                S[b] = FULL ? lo : (lo & a.M0);
+            for (int k = 0; k < 8; k++) {
+                uint32_t t = W[k] ^ C[0];
+#pragma unroll
+                for (int i = 1; i < M; i++) t |= __funnelshift_r(W[k], W[k + 1], 8 * i) ^ C[i];
+                // the add as IMAD (FMA pipe) - the ALU pipe is the one that saturates; `one` comes from the
+                // parameter block so that ptxas cannot fold the multiply back into an ALU add
+                const uint32_t s7 = (t & K7) * one + K7;
+                z[k] = ~(s7 | t) & K8;
             }
-            if (MODE == 0 && voff + 16 <= a.hi) {
+            if (DENSE && voff + 32 <= a.hi) {
 #pragma unroll
-                for (int b = 0; b < 16; b++) cnt += (S[b] == a.X0);
+                for (int k = 0; k < 8; k++) cnt += __popc(z[k]);
             } else if (voff < a.hi) {
-                bool any = (MODE != 2);  // MODE 3 reaches this point only for the vector straddling the range end
-                if (MODE == 2) {
+                uint32_t any = z[0];
 #pragma unroll
-                    for (int b = 0; b < 16; b++) any |= (S[b] == a.X0);
-                }
-                if (any) {
+                for (int k = 1; k < 8; k++) any |= z[k];
+                if (any != 0u) {
                     unsigned mm = 0;
 #pragma unroll
-                    for (int b = 0; b < 16; b++) mm |= ((S[b] == a.X0) ? 1u : 0u) << b;
-                    if (mm) cnt += short_candidates(a, mm, voff);
+                    for (int k = 0; k < 8; k++) mm |= movemask4(z[k]) << (4 * k);
+                    cnt += swar_candidates(a, mm, voff);
                 }
             }
         }
