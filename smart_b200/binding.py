@@ -34,6 +34,7 @@ FLAG_FILTER_B32 = 0x100
 FLAG_FILTER_B4L8 = 0x200
 FLAG_FILTER_B4L16 = 0x400
 FLAG_FILTER_B8L16 = 0x800
+FLAG_FILTER_B2 = 0x1000
 
 ALGORITHMS = (
     "bf", "mp", "kmp", "bm", "hor", "qs", "raita", "tunedbm", "so", "sa", "kr",

@@ -57,6 +57,7 @@ constexpr size_t kPatBytes = 4352;            // device pattern buffer (>= SB_XS
 constexpr int kU = SB_U;                      // 256-bit loads in flight per thread (scan_block / scan_window8)
 constexpr size_t kGroupLong = kU * 1024;      // bytes per warp iteration of those kernels
 constexpr int kFilterShort = 0, kFilterWindow8 = 1, kFilterWindow16 = 3;  // 2 = the 12-byte window
+constexpr int kFilterPair = 20;               // scan_block<2,L>: windows at even positions, L = 4..8 in Plan::flen
 constexpr int kFilterSkip = 100;              // + gram bytes (108, 116, 132): scan_skip<G>
 constexpr size_t kAuxWords = sb::kBloomWords + 2 * sb::kSkipTableSize;
 
@@ -76,6 +77,7 @@ struct DevCtx {                               // per-device scratch, created on 
     size_t pos_cap = 0;
     void *d_sort_temp = nullptr;              // cub::DeviceRadixSort scratch
     size_t sort_temp_bytes = 0;
+    int occ_pair[5] = {0};                    // ... for scan_block<2,L>, index L-4
     int occ_block[7] = {0};                   // resident CTAs/SM for scan_block<B,L>, index block_index()
     int occ_window[24] = {0};                 // ... for scan_window<NW,OFF,DENSE>, index window_index()
     int occ_swar[8] = {0};                    // ... for scan_swar<M, DENSE>, index (M-1)*2 + DENSE
@@ -155,6 +157,11 @@ DevCtx *get_ctx(int dev)
     c.occ_multi[0] = occupancy(sb::scan_multi_kernel<4, kU>);
     c.occ_multi[1] = occupancy(sb::scan_multi_kernel<8, kU>);
     c.occ_multi[2] = occupancy(sb::scan_multi_kernel<16, kU>);
+    c.occ_pair[0] = occupancy(sb::scan_block_kernel<2, 4, kU>);
+    c.occ_pair[1] = occupancy(sb::scan_block_kernel<2, 5, kU>);
+    c.occ_pair[2] = occupancy(sb::scan_block_kernel<2, 6, kU>);
+    c.occ_pair[3] = occupancy(sb::scan_block_kernel<2, 7, kU>);
+    c.occ_pair[4] = occupancy(sb::scan_block_kernel<2, 8, kU>);
     c.occ_block[block_index(4, 4)] = occupancy(sb::scan_block_kernel<4, 4, kU>);
     c.occ_block[block_index(8, 8)] = occupancy(sb::scan_block_kernel<8, 8, kU>);
     c.occ_block[block_index(16, 16)] = occupancy(sb::scan_block_kernel<16, 16, kU>);
@@ -229,10 +236,23 @@ uint32_t fingerprint(const unsigned char *p, int B)
     }
 }
 
+uint32_t fingerprint_pair(const unsigned char *p, int L)
+{
+    const uint32_t lo = load_le32(p, 4), hi = L > 4 ? load_le32(p + 4, L - 4) : 0u;
+    switch (L) {
+    case 4: return sb::pair_fp<4>(lo, hi);
+    case 5: return sb::pair_fp<5>(lo, hi);
+    case 6: return sb::pair_fp<6>(lo, hi);
+    case 7: return sb::pair_fp<7>(lo, hi);
+    default: return sb::pair_fp<8>(lo, hi);
+    }
+}
+
 /* Which kernel scans a pattern of length m over a text with `bits` of selectivity per byte (see
  * collision_bits).  Returns the filter kind and, for scan_block, the fingerprint length L in *flen:
  *   0 = scan_swar (exact, m <= 4), 1/2/3 = scan_window (8/12/16-byte window at every position),
- *   4/8/16/32 = scan_block<B,L>: B-aligned windows of L >= B bytes, needs m >= L+B-1.
+ *   4/8/16/32 = scan_block<B,L>: B-aligned windows of L >= B bytes, needs m >= L+B-1;
+ *   20 = scan_block<2,L>: windows of L = 4..8 bytes at every even position, needs m >= L+1.
  * The block kernels are the fast ones (one compare per start position, no shifts) but an L-byte fingerprint
  * lets ~2^-(L*bits) of all start positions through to verification: pick the shortest L that carries
  * >= 20 bits (with the widest alignment B <= L that still fits the pattern), else the longest feasible L if it
@@ -241,6 +261,7 @@ int choose_filter(int m, unsigned flags, double bits, int *flen)
 {
     static const int variants[7][2] = {{4, 4}, {8, 8}, {4, 8}, {16, 16}, {8, 16}, {4, 16}, {32, 32}};  // by L, widest B first
     *flen = 0;
+    if ((flags & SB_FLAG_FILTER_B2) && m >= 5) return *flen = (m - 1 < 8 ? m - 1 : 8), kFilterPair;
     if ((flags & SB_FLAG_FILTER_B32) && m >= 63) return *flen = 32;
     if ((flags & SB_FLAG_FILTER_B8L16) && m >= 23) return *flen = 16, 8;
     if ((flags & SB_FLAG_FILTER_B4L16) && m >= 19) return *flen = 16, 4;
@@ -259,6 +280,11 @@ int choose_filter(int m, unsigned flags, double bits, int *flen)
         if (L * bits >= 20.0) return *flen = L, B;
     }
     if (bestL && (bestL * bits >= 14.0 || bestL > 16)) return *flen = bestL, bestB;
+    // 5 <= m < 11 (or 4 bytes too weak): windows of min(8, m-1) bytes at every even position
+    if (m >= 5) {
+        const int L = m - 1 < 8 ? m - 1 : 8;
+        if (L * bits >= 15.0) return *flen = L, kFilterPair;  // measured: at 14 bits (sigma=4, m=8) the window kernel still wins
+    }
     // per-position window of 2, 3 or 4 words: the narrowest that carries >= 14 bits, else the widest
     // that fits (a window never exceeds the pattern: min(m, 4*NW) bytes)
     for (int nw = 2; nw <= 4; nw++) {
@@ -336,7 +362,7 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
      * 32-byte DRAM sector), G wide enough that a text gram rarely equals one of `stride` pattern grams. */
     const unsigned forced = SB_FLAG_FILTER_SHIFT | SB_FLAG_FILTER_B4 | SB_FLAG_FILTER_B8 | SB_FLAG_FILTER_B16 |
                             SB_FLAG_FILTER_B32 | SB_FLAG_FILTER_B4L8 | SB_FLAG_FILTER_B4L16 | SB_FLAG_FILTER_B8L16 |
-                            SB_FLAG_NO_SKIP;
+                            SB_FLAG_FILTER_B2 | SB_FLAG_NO_SKIP;
     if (desc->anchor == SB_ANCHOR_SUFFIX && !(flags & forced)) {
         for (int G = 8; G <= 32; G *= 2) {
             const int stride = ((m - (G - 1)) / 32) * 32;
@@ -381,10 +407,19 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
         // when the window is the whole pattern and matches are frequent, count them in registers
         pl.sparse = !(m <= 4 * nw && (m * bits < dense_bits() || (flags & SB_FLAG_DENSE)));
     } else {
-        const int B = pl.filter, L = pl.flen;
+        const bool pair = pl.filter == kFilterPair;
+        const int B = pair ? 2 : pl.filter, L = pl.flen;
         a.anchor = desc->anchor == SB_ANCHOR_SUFFIX ? m - (L + B - 1) : 0;
-        for (int d = 0; d < B; d++) a.H[d] = fingerprint(x + a.anchor + d, L);
+        for (int d = 0; d < B; d++) a.H[d] = pair ? fingerprint_pair(x + a.anchor + d, L) : fingerprint(x + a.anchor + d, L);
     }
+}
+
+/* what sb_last_timing reports: see include/smart_b200.h */
+int filter_kind_of(const Plan &pl)
+{
+    if (pl.filter == kFilterPair) return 20 + pl.flen;
+    if (pl.filter >= 4 && pl.filter < kFilterSkip && pl.flen != pl.filter) return pl.filter * 100 + pl.flen;
+    return pl.filter;
 }
 
 /* launch the scan of one buffer on `stream`; the caller has set the device */
@@ -421,9 +456,10 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
         per_sm = c.occ_window[window_index(pl.filter + 1, a.anchor, dense)];
     } else {
         group = kGroupLong;
-        const unsigned long long end = (unsigned long long)a.hi + a.anchor + pl.filter + pl.flen;
+        const bool pair = pl.filter == kFilterPair;
+        const unsigned long long end = (unsigned long long)a.hi + a.anchor + (pair ? 2 : pl.filter) + pl.flen;
         a.ngroups = (end + group - 1) / group;
-        per_sm = c.occ_block[block_index(pl.filter, pl.flen)];
+        per_sm = pair ? c.occ_pair[pl.flen - 4] : c.occ_block[block_index(pl.filter, pl.flen)];
     }
     unsigned long long want = (a.ngroups + (sb::kThreads / 32) - 1) / (sb::kThreads / 32);
     unsigned long long maxb = (unsigned long long)c.sms * per_sm;
@@ -450,6 +486,14 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
         SB_WIN_LAUNCH(3, 1) SB_WIN_LAUNCH(3, 2) SB_WIN_LAUNCH(3, 3) SB_WIN_LAUNCH(3, 4)
         SB_WIN_LAUNCH(4, 1) SB_WIN_LAUNCH(4, 2) SB_WIN_LAUNCH(4, 3) SB_WIN_LAUNCH(4, 4)
 #undef SB_WIN_LAUNCH
+    } else if (pl.filter == kFilterPair) {
+        switch (pl.flen) {
+        case 4: sb::scan_block_kernel<2, 4, kU><<<grid, sb::kThreads, 0, stream>>>(a); break;
+        case 5: sb::scan_block_kernel<2, 5, kU><<<grid, sb::kThreads, 0, stream>>>(a); break;
+        case 6: sb::scan_block_kernel<2, 6, kU><<<grid, sb::kThreads, 0, stream>>>(a); break;
+        case 7: sb::scan_block_kernel<2, 7, kU><<<grid, sb::kThreads, 0, stream>>>(a); break;
+        default: sb::scan_block_kernel<2, 8, kU><<<grid, sb::kThreads, 0, stream>>>(a); break;
+        }
     } else if (pl.flen == pl.filter && use_tma()) {
         // experiment: the same filter fed by TMA bulk copies through shared memory
         static const int stages = getenv("SMART_B200_TMA_STAGES") ? atoi(getenv("SMART_B200_TMA_STAGES")) : sb::kTmaStages;
@@ -1004,7 +1048,7 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
     g_timing.kernel_ms = kernel_ms;
     g_timing.wall_ms = t3 - t2;
     g_timing.kernels_launched = launched;
-    g_timing.filter_kind = (pl.filter >= 4 && pl.filter < kFilterSkip && pl.flen != pl.filter) ? pl.filter * 100 + pl.flen : pl.filter;
+    g_timing.filter_kind = filter_kind_of(pl);
     g_timing.verified = verified;
     if (pre_ms) *pre_ms = t2 - t0;
     if (run_ms) *run_ms = (t3 - t2) > 0 ? (t3 - t2) : 1e-6;
@@ -1278,7 +1322,7 @@ long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned
     g_timing.upload_ms = t2 - t1;
     g_timing.wall_ms = t3 - t2;
     g_timing.kernels_launched = launched;
-    g_timing.filter_kind = (pl.filter >= 4 && pl.filter < kFilterSkip && pl.flen != pl.filter) ? pl.filter * 100 + pl.flen : pl.filter;
+    g_timing.filter_kind = filter_kind_of(pl);
     g_timing.verified = c->h_counters[2];
     if (pre_ms) *pre_ms = t2 - t0;
     if (run_ms) *run_ms = (t3 - t2) > 0 ? (t3 - t2) : 1e-6;

@@ -223,6 +223,35 @@ __device__ __forceinline__ uint32_t block_fp(const uint32_t *W, int q)
     return fp32(fp16(W[0], W[1], W[2], W[3]), fp16(W[4], W[5], W[6], W[7]));
 }
 
+/* B = 2 (windows at every EVEN text position, L = 4..8 bytes): fingerprint of the L bytes lo|hi, the bytes of
+ * hi beyond L multiplied away (hi * 2^(8*(8-L)) keeps its low L-4 bytes): IMADs only, no mask */
+template <int L>
+__host__ __device__ __forceinline__ uint32_t pair_fp(uint32_t lo, uint32_t hi)
+{
+    if (L == 4) return lo;
+    return lo * K3 + hi * (1u << (8 * (8 - L)));
+}
+
+/* words a lane needs for its 32-byte vector: 8 own + halo from the next lane */
+template <int B, int L>
+struct BlockShape {
+    static constexpr int HALO = B == 2 ? (L <= 6 ? 1 : 2) : (L - B) / 4;
+    static constexpr int NWORDS = 8 + HALO;
+};
+
+/* fingerprint of block i (byte offset i*B) of a vector held in s[] */
+template <int B, int L>
+__device__ __forceinline__ uint32_t slot_fp(const uint32_t *s, int i)
+{
+    if (B == 2) {
+        const int q = i >> 1;
+        if (i & 1)
+            return pair_fp<L>(__funnelshift_r(s[q], s[q + 1], 16), L > 4 ? __funnelshift_r(s[q + 1], s[q + 2], 16) : 0u);
+        return pair_fp<L>(s[q], L > 4 ? s[q + 1] : 0u);
+    }
+    return block_fp<L>(s, i * (B / 4));
+}
+
 /* Slow path of scan_block: some lane of this warp saw a fingerprint hit in its 32-byte vector.
  * For each such lane the whole warp re-derives which of the 32 (block, d) slots hit (one slot per
  * lane) and verifies each candidate cooperatively.  v0..v10: the lane's 8 words + up to 3 halo words. */
@@ -235,22 +264,22 @@ __device__ __noinline__ CandResult block_candidates(const ScanArgs &a, uint32_t 
     // everything by value and the result returned: a by-reference vector would force the caller to
     // keep a copy of every loaded vector in local memory (an STL per load in the hot loop)
     const uint32_t vw[11] = {v0, v1, v2, v3, v4, v5, v6, v7, v8, v9, v10};
-    constexpr int NWORDS = 8 + (L - B) / 4;
+    constexpr int NWORDS = BlockShape<B, L>::NWORDS;
     unsigned cnt = 0, nver = 0;
     unsigned pending = __ballot_sync(kFull, hit);
     while (pending) {
         const int src = __ffs(pending) - 1;
         pending &= pending - 1;
-        uint32_t s[11];
+        uint32_t s[11] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
         for (int i = 0; i < NWORDS; i++) s[i] = __shfl_sync(kFull, vw[i], src);
         const long long soff = __shfl_sync(kFull, voff, src);
         // slot of this lane; d runs DOWN inside a block so that the candidate positions of a vector are
         // visited in ascending order (the period-aware shortcut below relies on that)
         const int blk = (int)lane / B, d = B - 1 - (int)lane % B;
-        uint32_t h = block_fp<L>(s, 0);
+        uint32_t h = slot_fp<B, L>(s, 0);
 #pragma unroll
-        for (int i = 1; i < 32 / B; i++) h = (blk == i) ? block_fp<L>(s, i * (B / 4)) : h;
+        for (int i = 1; i < 32 / B; i++) h = (blk == i) ? slot_fp<B, L>(s, i) : h;
         unsigned slots = __ballot_sync(kFull, h == a.H[d]);
         while (slots) {
             const int sl = __ffs(slots) - 1;
@@ -289,7 +318,17 @@ template <int B, int L>
 __device__ __forceinline__ bool block_hit(const ScanArgs &a, const uint32_t *W)
 {
     bool hit = false;
-    if (L == 16 && B == 4) {  // share the 8-byte halves between the overlapping 16-byte windows
+    if (B == 2) {  // windows at even offsets: the odd half-words by one funnel shift per word
+        uint32_t F[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) F[k] = (L > 4 || k < 8) ? __funnelshift_r(W[k], W[k + 1], 16) : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t h0 = pair_fp<L>(W[k], W[k + 1]);
+            const uint32_t h2 = pair_fp<L>(F[k], F[k + 1]);
+            hit |= (h0 == a.H[0]) | (h0 == a.H[1]) | (h2 == a.H[0]) | (h2 == a.H[1]);
+        }
+    } else if (L == 16 && B == 4) {  // share the 8-byte halves between the overlapping 16-byte windows
         uint32_t g8[10];
 #pragma unroll
         for (int q = 0; q < 10; q++) g8[q] = fp8(W[q], W[q + 1]);
@@ -312,9 +351,9 @@ __device__ __forceinline__ bool block_hit(const ScanArgs &a, const uint32_t *W)
 
 /* group = U x 1 KiB per warp */
 template <int B, int L, int U>
-__global__ void __launch_bounds__(kThreads, L > B ? 3 : SB_MINB) scan_block_kernel(const __grid_constant__ ScanArgs a)
+__global__ void __launch_bounds__(kThreads, (L > B || B == 2) ? 3 : SB_MINB) scan_block_kernel(const __grid_constant__ ScanArgs a)
 {
-    constexpr int HALO = (L - B) / 4;  // words needed from the next lane
+    constexpr int HALO = BlockShape<B, L>::HALO;  // words needed from the next lane
     const unsigned lane = threadIdx.x & 31;
     const unsigned long long warp = ((unsigned long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * kThreads) >> 5;

@@ -14,8 +14,8 @@ from golden_texts import ALGOS, GOLDEN, TEXT_NAMES, make_patterns, make_text
 
 pytestmark = pytest.mark.gpu
 
-# filter kinds reported by sb_last_timing: 0 scan_short, 1 scan_window8, 4/8/16/32 scan_block<B>
-FILTERS = {0: 0, 1: sb.FLAG_FILTER_SHIFT, 4: sb.FLAG_FILTER_B4, 8: sb.FLAG_FILTER_B8, 16: sb.FLAG_FILTER_B16,
+# filter kinds reported by sb_last_timing: 0 scan_swar, 1 scan_window8, 4/8/16/32 scan_block<B>, 24..28 scan_block<2,L>
+FILTERS = {0: 0, 1: sb.FLAG_FILTER_SHIFT, 2: sb.FLAG_FILTER_B2, 4: sb.FLAG_FILTER_B4, 8: sb.FLAG_FILTER_B8, 16: sb.FLAG_FILTER_B16,
            32: sb.FLAG_FILTER_B32, 408: sb.FLAG_FILTER_B4L8, 416: sb.FLAG_FILTER_B4L16, 816: sb.FLAG_FILTER_B8L16}
 
 
@@ -27,7 +27,7 @@ def expected(algo, m, bf):
 
 
 def filters_for(m):
-    out = [0] if m <= 4 else [1]
+    out = [0] if m <= 4 else [1, 2]  # 2: windows of min(8, m-1) bytes at every even position (kind 20+L)
     out += [b for b in (4, 8, 16, 32) if m >= 2 * b - 1]
     out += [k for k, need in ((408, 11), (416, 19), (816, 23)) if m >= need]  # overlapping windows <B,L>
     return out
@@ -90,7 +90,7 @@ def test_every_filter_width_gives_the_same_count(oracle, golden, tname):
             for f in filters_for(c["m"]):
                 for a in ("bf", "hor"):  # prefix- and suffix-anchored
                     r = sb.search(a, t, x, flags=FILTERS[f])
-                    assert sb.last_timing().filter_kind == f
+                    assert sb.last_timing().filter_kind == (20 + min(8, c["m"] - 1) if f == 2 else f)
                     assert r.count == want, (tname, c["m"], c["pi"], a, f)
             # the period-aware verification shortcut is an optimisation, never a semantic change
             assert sb.search("kmp", t, x, flags=sb.FLAG_NO_PERIOD).count == want

@@ -11,7 +11,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import smart_b200 as sb  # noqa: E402
 
-FILTERS = {0: 0, 1: sb.FLAG_FILTER_SHIFT, 4: sb.FLAG_FILTER_B4, 8: sb.FLAG_FILTER_B8, 16: sb.FLAG_FILTER_B16,
+FILTERS = {0: 0, 1: sb.FLAG_FILTER_SHIFT, 2: sb.FLAG_FILTER_B2, 4: sb.FLAG_FILTER_B4, 8: sb.FLAG_FILTER_B8, 16: sb.FLAG_FILTER_B16,
            32: sb.FLAG_FILTER_B32, 408: sb.FLAG_FILTER_B4L8, 416: sb.FLAG_FILTER_B4L16, 816: sb.FLAG_FILTER_B8L16}
 
 
@@ -35,7 +35,7 @@ def main():
                 if a.default_only:
                     fl = [None]
                 else:
-                    fl = [None] + ([0] if m <= 4 else [1]) + [b for b in (4, 8, 16, 32) if m >= 2 * b - 1]
+                    fl = [None] + ([0] if m <= 4 else [1, 2]) + [b for b in (4, 8, 16, 32) if m >= 2 * b - 1]
                     fl += [k for k, need in ((408, 11), (416, 19), (816, 23)) if m >= need]
                 for f in fl:
                     flags = 0 if f is None else FILTERS[f]
