@@ -466,7 +466,7 @@ def ensure_built():
     if not os.path.exists(smart_b200.library_path()):
         smart_b200.build_library()
     if not os.path.exists(os.path.join(ROOT, "oracle", "libsmart_oracle.so")):
-        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle", "ref"], check=True, capture_output=True)
+        subprocess.run(["make", "-j8", "-C", os.path.join(ROOT, "oracle"), "oracle", "ref"], check=True, capture_output=True)
 
 
 def main():

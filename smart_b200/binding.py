@@ -43,6 +43,16 @@ ALGORITHMS = (
     "smith", "tbm", "ag", "ac",
     "bndm", "br", "tvsbs", "fjs", "ssabs", "ts",
     "skip", "kmpskip", "fs", "graspm",
+    # second batch: registered with -1 domain and scan direction, prep.c
+    "aoso2", "aoso4", "aoso6", "faoso2", "faoso4", "svm0", "blim", "ufndmq2", "ufndmq4", "ufndmq6", "ufndmq8", "aut",
+    "smoa", "tw", "rcolussi", "bndmq2", "bndmq4", "bndmq6", "lbndm", "sbndm", "sbndm-bmh", "fsbndm-w2", "fndm", "tndm",
+    "tndma", "bxs", "bxs2", "bxs4", "bxs6", "bxs8", "bww", "dbww", "dbww2", "bom", "bom2", "ebom",
+    "fbom", "sebom", "sfbom", "ildm1", "ildm2", "fdm", "bsdm", "bsdm4", "bsdm5", "bsdm7", "bsdm8", "ww",
+    "wfr", "wfr2", "wfr3", "wfr4", "wfr5", "wfr6", "wfr7", "wfr8", "wfrq2", "wfrq3", "wfrq4", "wfrq5",
+    "wfrq6", "wfrq7", "wfrq8", "twfr", "twfr2", "twfr3", "twfr4", "twfr5", "twfr6", "twfr7", "twfr8", "twfrq2",
+    "twfrq3", "twfrq4", "twfrq5", "twfrq6", "twfrq7", "twfrq8", "lwfr2", "lwfr3", "lwfr4", "lwfr5", "lwfr6", "lwfr7",
+    "lwfr8", "skip3", "skip5", "skip6", "skip7", "skip8", "bfs", "ffs", "iom", "wom", "pbmh", "qlqs",
+    "tsw", "wc", "zt", "tvsbs-w2", "fs-w1", "ssef",
 )
 
 

@@ -869,6 +869,13 @@ void sb_text_free(sb_text *t)
     delete t;
 }
 
+/* the reference's `return -1` guards: m below the algorithm's minimum (hash3.c:31, raita.c:38, qf23.c:44, ...)
+ * or, for the double-window searches, a text shorter than two patterns (dbww.c:35) */
+static bool outside_domain(const sb_algo_desc *d, int m, unsigned long long n)
+{
+    return m < d->min_m || (d->min_ratio > 0 && n / (unsigned long long)m < (unsigned long long)d->min_ratio);
+}
+
 long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m, unsigned flags,
                       unsigned long long *positions, size_t cap, double *pre_ms, double *run_ms)
 {
@@ -885,7 +892,7 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
     memset(&g_timing, 0, sizeof g_timing);
     if (pre_ms) *pre_ms = 0;
     if (run_ms) *run_ms = 0;
-    if (m < desc->min_m) return SB_NOT_APPLICABLE;
+    if (outside_domain(desc, m, t->n)) return SB_NOT_APPLICABLE;
 
     /* ---- preprocessing stage: tables + fingerprints on the host, then upload ---- */
     const double t0 = now_ms();
@@ -1068,7 +1075,7 @@ long long sb_search_multi64(int algo, const sb_text *t, const unsigned char *pat
     if (pre_ms) *pre_ms = 0;
     if (run_ms) *run_ms = 0;
     for (int p = 0; p < npat; p++) counts[p] = 0;
-    if (m < desc->min_m) return SB_NOT_APPLICABLE;
+    if (outside_domain(desc, m, t->n)) return SB_NOT_APPLICABLE;
 
     /* block width: P(an aligned block equals one of the npat*B pattern grams) ~ npat*B*2^-(B*bits) must be
      * small; if no width achieves that (short patterns, tiny alphabets) fall back to one scan per pattern */
@@ -1250,7 +1257,7 @@ long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned
     memset(&g_timing, 0, sizeof g_timing);
     if (pre_ms) *pre_ms = 0;
     if (run_ms) *run_ms = 0;
-    if (m < desc->min_m) return SB_NOT_APPLICABLE;
+    if (outside_domain(desc, m, n)) return SB_NOT_APPLICABLE;
     DevCtx *c = get_ctx(0);
     if (!c) return SB_ERR_CUDA;
 

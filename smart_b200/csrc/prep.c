@@ -15,48 +15,155 @@
 /* ------------------------------------------------------------------ registry */
 
 static const sb_algo_desc g_algos[] = {
-    /* name      family        anchor      q  Q  S  min_m */
-    {"bf", SB_FAM_BF, SB_ANCHOR_PREFIX, 0, 0, 0, 1},           /* src/algos/bf.c:25 */
-    {"mp", SB_FAM_MP, SB_ANCHOR_PREFIX, 0, 0, 0, 1},           /* mp.c:37 */
-    {"kmp", SB_FAM_KMP, SB_ANCHOR_PREFIX, 0, 0, 0, 1},         /* kmp.c:44 */
-    {"bm", SB_FAM_BM, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},           /* bm.c:69 */
-    {"hor", SB_FAM_HOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},         /* hor.c:33 */
-    {"qs", SB_FAM_QS, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},           /* qs.c:32 */
-    {"raita", SB_FAM_RAITA, SB_ANCHOR_SUFFIX, 0, 0, 0, 2},     /* raita.c:35, m<2 -> -1 (:38) */
-    {"tunedbm", SB_FAM_TUNEDBM, SB_ANCHOR_SUFFIX, 0, 0, 0, 1}, /* tunedbm.c:34 */
-    {"so", SB_FAM_SO, SB_ANCHOR_PREFIX, 0, 0, 0, 1},           /* so.c:40, search_large :69 */
-    {"sa", SB_FAM_SA, SB_ANCHOR_PREFIX, 0, 0, 0, 1},           /* sa.c:36, search_large :65 */
-    {"kr", SB_FAM_KR, SB_ANCHOR_PREFIX, 0, 0, 0, 1},           /* kr.c:28 */
-    {"hash3", SB_FAM_HASHQ, SB_ANCHOR_SUFFIX, 3, 0, 0, 3},     /* hash3.c:28, m<3 -> -1 (:31) */
-    {"hash5", SB_FAM_HASHQ, SB_ANCHOR_SUFFIX, 5, 0, 0, 5},     /* hash5.c:28 */
-    {"hash8", SB_FAM_HASHQ, SB_ANCHOR_SUFFIX, 8, 0, 0, 8},     /* hash8.c:28 */
-    {"qf23", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 2, 3, 3},         /* qf23.c:39, m<=Q -> -1 (:44) */
-    {"qf24", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 2, 4, 3},
-    {"qf26", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 2, 6, 3},
-    {"qf28", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 2, 8, 3},
-    {"qf33", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 3, 3, 4},
-    {"qf34", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 3, 4, 4},
-    {"qf36", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 3, 6, 4},
-    {"qf42", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 4, 2, 5},
-    {"qf43", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 4, 3, 5},
-    {"qf44", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 4, 4, 5},
-    {"qf62", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 6, 2, 7},
-    {"qf63", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 6, 3, 7},
+    /* name      family        anchor      q  Q  S  min_m  min n/m */
+    {"bf", SB_FAM_BF, SB_ANCHOR_PREFIX, 0, 0, 0, 1, 0},           /* src/algos/bf.c:25 */
+    {"mp", SB_FAM_MP, SB_ANCHOR_PREFIX, 0, 0, 0, 1, 0},           /* mp.c:37 */
+    {"kmp", SB_FAM_KMP, SB_ANCHOR_PREFIX, 0, 0, 0, 1, 0},         /* kmp.c:44 */
+    {"bm", SB_FAM_BM, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0},           /* bm.c:69 */
+    {"hor", SB_FAM_HOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0},         /* hor.c:33 */
+    {"qs", SB_FAM_QS, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0},           /* qs.c:32 */
+    {"raita", SB_FAM_RAITA, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0},     /* raita.c:35, m<2 -> -1 (:38) */
+    {"tunedbm", SB_FAM_TUNEDBM, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* tunedbm.c:34 */
+    {"so", SB_FAM_SO, SB_ANCHOR_PREFIX, 0, 0, 0, 1, 0},           /* so.c:40, search_large :69 */
+    {"sa", SB_FAM_SA, SB_ANCHOR_PREFIX, 0, 0, 0, 1, 0},           /* sa.c:36, search_large :65 */
+    {"kr", SB_FAM_KR, SB_ANCHOR_PREFIX, 0, 0, 0, 1, 0},           /* kr.c:28 */
+    {"hash3", SB_FAM_HASHQ, SB_ANCHOR_SUFFIX, 3, 0, 0, 3, 0},     /* hash3.c:28, m<3 -> -1 (:31) */
+    {"hash5", SB_FAM_HASHQ, SB_ANCHOR_SUFFIX, 5, 0, 0, 5, 0},     /* hash5.c:28 */
+    {"hash8", SB_FAM_HASHQ, SB_ANCHOR_SUFFIX, 8, 0, 0, 8, 0},     /* hash8.c:28 */
+    {"qf23", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 2, 3, 3, 0},         /* qf23.c:39, m<=Q -> -1 (:44) */
+    {"qf24", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 2, 4, 3, 0},
+    {"qf26", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 2, 6, 3, 0},
+    {"qf28", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 2, 8, 3, 0},
+    {"qf33", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 3, 3, 4, 0},
+    {"qf34", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 3, 4, 4, 0},
+    {"qf36", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 3, 6, 4, 0},
+    {"qf42", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 4, 2, 5, 0},
+    {"qf43", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 4, 3, 5, 0},
+    {"qf44", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 4, 4, 5, 0},
+    {"qf62", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 6, 2, 7, 0},
+    {"qf63", SB_FAM_QF, SB_ANCHOR_SUFFIX, 0, 6, 3, 7, 0},
     /* further clean families whose tables are the ones above */
-    {"smith", SB_FAM_SMITH, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},     /* smith.c:41: max(bmBc, qsBc) shift */
-    {"tbm", SB_FAM_TBM, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},         /* tbm.c:66: Turbo-BM (bmGs, bmBc) */
-    {"ag", SB_FAM_AG, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},           /* ag.c:59: Apostolico-Giancarlo (bmGs, suff, bmBc) */
-    {"ac", SB_FAM_AC, SB_ANCHOR_PREFIX, 0, 0, 0, 1},           /* ac.c:44: Apostolico-Crochemore (kmpNext, ell) */
-    {"bndm", SB_FAM_BNDM, SB_ANCHOR_PREFIX, 0, 0, 0, 1},       /* bndm.c:26, search_large :62 (32-char prefix) */
-    {"br", SB_FAM_BR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},           /* br.c:40: Berry-Ravindran brBc[256][256] */
-    {"tvsbs", SB_FAM_BR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},        /* tvsbs.c:40: same table, first/last char first */
-    {"fjs", SB_FAM_FJS, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},         /* fjs.c:47: Franek-Jennings-Smyth (qsBc + kmpNext) */
-    {"ssabs", SB_FAM_QS, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},        /* ssabs.c:35: qsBc, first/last char first */
-    {"ts", SB_FAM_BF, SB_ANCHOR_PREFIX, 0, 0, 0, 1},           /* ts.c:25: Tailed-Substring, no tables */
-    {"skip", SB_FAM_SKIP, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},       /* skip.c:26: Skip-Search, bucket lists per character */
-    {"kmpskip", SB_FAM_KMPSKIP, SB_ANCHOR_SUFFIX, 0, 0, 0, 1}, /* kmpskip.c:59: buckets + mpNext + kmpNext */
-    {"fs", SB_FAM_FS, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},           /* fs.c:44: Fast-Search (bc over all m chars, Pre_GS) */
-    {"graspm", SB_FAM_GRASPM, SB_ANCHOR_SUFFIX, 0, 0, 0, 1},   /* graspm.c:37: GRASPm (bc + lists keyed by x[i]) */
+    {"smith", SB_FAM_SMITH, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0},     /* smith.c:41: max(bmBc, qsBc) shift */
+    {"tbm", SB_FAM_TBM, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0},         /* tbm.c:66: Turbo-BM (bmGs, bmBc) */
+    {"ag", SB_FAM_AG, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0},           /* ag.c:59: Apostolico-Giancarlo (bmGs, suff, bmBc) */
+    {"ac", SB_FAM_AC, SB_ANCHOR_PREFIX, 0, 0, 0, 1, 0},           /* ac.c:44: Apostolico-Crochemore (kmpNext, ell) */
+    {"bndm", SB_FAM_BNDM, SB_ANCHOR_PREFIX, 0, 0, 0, 1, 0},       /* bndm.c:26, search_large :62 (32-char prefix) */
+    {"br", SB_FAM_BR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0},           /* br.c:40: Berry-Ravindran brBc[256][256] */
+    {"tvsbs", SB_FAM_BR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0},        /* tvsbs.c:40: same table, first/last char first */
+    {"fjs", SB_FAM_FJS, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0},         /* fjs.c:47: Franek-Jennings-Smyth (qsBc + kmpNext) */
+    {"ssabs", SB_FAM_QS, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0},        /* ssabs.c:35: qsBc, first/last char first */
+    {"ts", SB_FAM_BF, SB_ANCHOR_PREFIX, 0, 0, 0, 1, 0},           /* ts.c:25: Tailed-Substring, no tables */
+    {"skip", SB_FAM_SKIP, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0},       /* skip.c:26: Skip-Search, bucket lists per character */
+    {"kmpskip", SB_FAM_KMPSKIP, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* kmpskip.c:59: buckets + mpNext + kmpNext */
+    {"fs", SB_FAM_FS, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0},           /* fs.c:44: Fast-Search (bc over all m chars, Pre_GS) */
+    {"graspm", SB_FAM_GRASPM, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0},   /* graspm.c:37: GRASPm (bc + lists keyed by x[i]) */
+    /* second batch of SURVEY section 8(f)-1: the other algorithms of the reference that agree with bf.c on every
+     * golden input (tests/golden/counts.json holds their recorded outputs).  name, family, scan direction,
+     * -1 domain; columns as above plus min n/m.  Not registered, because the reference's own output is wrong
+     * on some golden input: the 63 of SURVEY Appendix A.2 and, found here, kbndm, ksa (absent pattern counted
+     * once on rand2 for m >= 62) and ssm (m = 1). */
+    {"aoso2", SB_FAM_BITPAR, SB_ANCHOR_PREFIX, 0, 0, 0, 3, 0}, /* aoso2.c:42, m<3 -> -1 (:47) */
+    {"aoso4", SB_FAM_BITPAR, SB_ANCHOR_PREFIX, 0, 0, 0, 5, 0}, /* aoso4.c:42, m<5 -> -1 (:47) */
+    {"aoso6", SB_FAM_BITPAR, SB_ANCHOR_PREFIX, 0, 0, 0, 7, 0}, /* aoso6.c:42, m<7 -> -1 (:47) */
+    {"faoso2", SB_FAM_BITPAR, SB_ANCHOR_PREFIX, 0, 0, 0, 3, 0}, /* faoso2.c:47, m<3 -> -1 (:56) */
+    {"faoso4", SB_FAM_BITPAR, SB_ANCHOR_PREFIX, 0, 0, 0, 5, 0}, /* faoso4.c:47, m<5 -> -1 (:56) */
+    {"svm0", SB_FAM_BITPAR, SB_ANCHOR_PREFIX, 0, 0, 0, 1, 0}, /* svm0.c:36 */
+    {"blim", SB_FAM_BITPAR, SB_ANCHOR_PREFIX, 0, 0, 0, 1, 0}, /* blim.c:30 */
+    {"ufndmq2", SB_FAM_BITPAR, SB_ANCHOR_PREFIX, 0, 0, 0, 2, 0}, /* ufndmq2.c:31, m<2 -> -1 (:36) */
+    {"ufndmq4", SB_FAM_BITPAR, SB_ANCHOR_PREFIX, 0, 0, 0, 4, 0}, /* ufndmq4.c:29, m<4 -> -1 (:34) */
+    {"ufndmq6", SB_FAM_BITPAR, SB_ANCHOR_PREFIX, 0, 0, 0, 6, 0}, /* ufndmq6.c:29, m<6 -> -1 (:34) */
+    {"ufndmq8", SB_FAM_BITPAR, SB_ANCHOR_PREFIX, 0, 0, 0, 8, 0}, /* ufndmq8.c:29, m<8 -> -1 (:34) */
+    {"aut", SB_FAM_AUT, SB_ANCHOR_PREFIX, 0, 0, 0, 1, 0}, /* aut.c:26 */
+    {"smoa", SB_FAM_TWOWAY, SB_ANCHOR_PREFIX, 0, 0, 0, 1, 0}, /* smoa.c:55 */
+    {"tw", SB_FAM_TWOWAY, SB_ANCHOR_PREFIX, 0, 0, 0, 1, 0}, /* tw.c:92 */
+    {"rcolussi", SB_FAM_TWOWAY, SB_ANCHOR_PREFIX, 0, 0, 0, 1, 0}, /* rcolussi.c:96 */
+    {"bndmq2", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* bndmq2.c:31, m<2 -> -1 (:35) */
+    {"bndmq4", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 4, 0}, /* bndmq4.c:29, m<4 -> -1 (:33) */
+    {"bndmq6", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 6, 0}, /* bndmq6.c:29, m<6 -> -1 (:33) */
+    {"lbndm", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* lbndm.c:42, m<2 -> -1 (:49) */
+    {"sbndm", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* sbndm.c:28, m<2 -> -1 (:36) */
+    {"sbndm-bmh", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* sbndm-bmh.c:27, m<2 -> -1 (:34) */
+    {"fsbndm-w2", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* fsbndm-w2.c:47 */
+    {"fndm", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* fndm.c:28 */
+    {"tndm", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* tndm.c:28 */
+    {"tndma", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* tndma.c:28 */
+    {"bxs", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* bxs.c:30 */
+    {"bxs2", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* bxs2.c:30, m<2 -> -1 (:33) */
+    {"bxs4", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 4, 0}, /* bxs4.c:30, m<4 -> -1 (:33) */
+    {"bxs6", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 6, 0}, /* bxs6.c:30, m<6 -> -1 (:33) */
+    {"bxs8", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 8, 0}, /* bxs8.c:30, m<8 -> -1 (:33) */
+    {"bww", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* bww.c:28 */
+    {"dbww", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 2}, /* dbww.c:28, n/m<2 -> -1 (:35) */
+    {"dbww2", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 2}, /* dbww2.c:31, n/m<2 -> -1 (:38) */
+    {"bom", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* bom.c:77 */
+    {"bom2", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* bom2.c:28 */
+    {"ebom", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* ebom.c:28, m<2 -> -1 (:35) */
+    {"fbom", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* fbom.c:28 */
+    {"sebom", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* sebom.c:25, m<2 -> -1 (:32) */
+    {"sfbom", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* sfbom.c:25 */
+    {"ildm1", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* ildm1.c:29 */
+    {"ildm2", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* ildm2.c:40 */
+    {"fdm", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* fdm.c:27 */
+    {"bsdm", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* bsdm.c:30 */
+    {"bsdm4", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 4, 0}, /* bsdm4.c:32, m<4 -> -1 (:36) */
+    {"bsdm5", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 5, 0}, /* bsdm5.c:32, m<5 -> -1 (:36) */
+    {"bsdm7", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 7, 0}, /* bsdm7.c:32, m<7 -> -1 (:36) */
+    {"bsdm8", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 8, 0}, /* bsdm8.c:32, m<8 -> -1 (:36) */
+    {"ww", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* ww.c:43 */
+    {"wfr", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* wfr.c:61 */
+    {"wfr2", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* wfr2.c:61, m<2 -> -1 (:65) */
+    {"wfr3", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 3, 0}, /* wfr3.c:60, m<3 -> -1 (:64) */
+    {"wfr4", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 4, 0}, /* wfr4.c:60, m<4 -> -1 (:64) */
+    {"wfr5", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 5, 0}, /* wfr5.c:59, m<5 -> -1 (:63) */
+    {"wfr6", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 6, 0}, /* wfr6.c:60, m<6 -> -1 (:64) */
+    {"wfr7", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 7, 0}, /* wfr7.c:61, m<7 -> -1 (:65) */
+    {"wfr8", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 8, 0}, /* wfr8.c:60, m<8 -> -1 (:64) */
+    {"wfrq2", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* wfrq2.c:68, m<2 -> -1 (:72) */
+    {"wfrq3", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 3, 0}, /* wfrq3.c:67, m<3 -> -1 (:71) */
+    {"wfrq4", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 4, 0}, /* wfrq4.c:67, m<4 -> -1 (:71) */
+    {"wfrq5", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 5, 0}, /* wfrq5.c:66, m<5 -> -1 (:70) */
+    {"wfrq6", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 6, 0}, /* wfrq6.c:67, m<6 -> -1 (:71) */
+    {"wfrq7", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 7, 0}, /* wfrq7.c:68, m<7 -> -1 (:72) */
+    {"wfrq8", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 8, 0}, /* wfrq8.c:67, m<8 -> -1 (:71) */
+    {"twfr", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* twfr.c:42 */
+    {"twfr2", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* twfr2.c:41, m<2 -> -1 (:45) */
+    {"twfr3", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 3, 0}, /* twfr3.c:41, m<3 -> -1 (:45) */
+    {"twfr4", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 4, 0}, /* twfr4.c:41, m<4 -> -1 (:45) */
+    {"twfr5", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 5, 0}, /* twfr5.c:41, m<5 -> -1 (:45) */
+    {"twfr6", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 6, 0}, /* twfr6.c:41, m<6 -> -1 (:45) */
+    {"twfr7", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 7, 0}, /* twfr7.c:41, m<7 -> -1 (:45) */
+    {"twfr8", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 8, 0}, /* twfr8.c:41, m<8 -> -1 (:45) */
+    {"twfrq2", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* twfrq2.c:49, m<2 -> -1 (:53) */
+    {"twfrq3", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 3, 0}, /* twfrq3.c:48, m<3 -> -1 (:52) */
+    {"twfrq4", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 4, 0}, /* twfrq4.c:48, m<4 -> -1 (:52) */
+    {"twfrq5", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 5, 0}, /* twfrq5.c:48, m<5 -> -1 (:52) */
+    {"twfrq6", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 6, 0}, /* twfrq6.c:48, m<6 -> -1 (:52) */
+    {"twfrq7", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 7, 0}, /* twfrq7.c:48, m<7 -> -1 (:52) */
+    {"twfrq8", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 8, 0}, /* twfrq8.c:48, m<8 -> -1 (:52) */
+    {"lwfr2", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* lwfr2.c:60, m<2 -> -1 (:65) */
+    {"lwfr3", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 3, 0}, /* lwfr3.c:60, m<3 -> -1 (:65) */
+    {"lwfr4", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 4, 0}, /* lwfr4.c:60, m<4 -> -1 (:65) */
+    {"lwfr5", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 5, 0}, /* lwfr5.c:60, m<5 -> -1 (:65) */
+    {"lwfr6", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 6, 0}, /* lwfr6.c:60, m<6 -> -1 (:65) */
+    {"lwfr7", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 7, 0}, /* lwfr7.c:60, m<7 -> -1 (:65) */
+    {"lwfr8", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 8, 0}, /* lwfr8.c:60, m<8 -> -1 (:65) */
+    {"skip3", SB_FAM_SKIPQ, SB_ANCHOR_SUFFIX, 0, 0, 0, 3, 0}, /* skip3.c:28, m<3 -> -1 (:31) */
+    {"skip5", SB_FAM_SKIPQ, SB_ANCHOR_SUFFIX, 0, 0, 0, 5, 0}, /* skip5.c:28, m<5 -> -1 (:31) */
+    {"skip6", SB_FAM_SKIPQ, SB_ANCHOR_SUFFIX, 0, 0, 0, 6, 0}, /* skip6.c:28, m<6 -> -1 (:31) */
+    {"skip7", SB_FAM_SKIPQ, SB_ANCHOR_SUFFIX, 0, 0, 0, 7, 0}, /* skip7.c:28, m<7 -> -1 (:31) */
+    {"skip8", SB_FAM_SKIPQ, SB_ANCHOR_SUFFIX, 0, 0, 0, 8, 0}, /* skip8.c:28, m<8 -> -1 (:31) */
+    {"bfs", SB_FAM_BADCHAR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* bfs.c:64 */
+    {"ffs", SB_FAM_BADCHAR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* ffs.c:52 */
+    {"iom", SB_FAM_BADCHAR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* iom.c:32 */
+    {"wom", SB_FAM_BADCHAR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* wom.c:57 */
+    {"pbmh", SB_FAM_BADCHAR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* pbmh.c:29 */
+    {"qlqs", SB_FAM_BADCHAR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* qlqs.c:38 */
+    {"tsw", SB_FAM_BADCHAR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* tsw.c:40 */
+    {"wc", SB_FAM_BADCHAR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* wc.c:68 */
+    {"zt", SB_FAM_BADCHAR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* zt.c:76 */
+    {"tvsbs-w2", SB_FAM_BADCHAR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* tvsbs-w2.c:36 */
+    {"fs-w1", SB_FAM_BADCHAR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* fs-w1.c:65 */
+    {"ssef", SB_FAM_SSEF, SB_ANCHOR_SUFFIX, 0, 0, 0, 32, 0}, /* ssef.c:40, m<32 -> -1 (:41) */
 };
 #define SB_NALGOS ((int)(sizeof(g_algos) / sizeof(g_algos[0])))
 

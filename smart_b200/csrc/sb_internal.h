@@ -32,7 +32,18 @@ enum sb_family {
     SB_FAM_SKIP,
     SB_FAM_KMPSKIP,
     SB_FAM_FS,
-    SB_FAM_GRASPM
+    SB_FAM_GRASPM,
+    /* SURVEY section 8(f)-1, second batch: registered with their -1 domain and scan direction; the result is
+     * the common exact count (bf.c:33-36), which is what each of them returns wherever it is correct */
+    SB_FAM_BITPAR,  /* forward bit-parallel: aoso*, faoso*, svm0, blim, ufndmq* */
+    SB_FAM_AUT,     /* deterministic automaton: aut */
+    SB_FAM_TWOWAY,  /* constant-space linear: smoa, tw, rcolussi */
+    SB_FAM_BNDMX,   /* backward bit-parallel windows: bndmq*, lbndm, sbndm*, fsbndm-w2, fndm, tndm*, bxs*, bww, dbww* */
+    SB_FAM_ORACLE,  /* factor oracles / suffix automata: bom*, ebom, fbom, sebom, sfbom, ildm*, fdm, bsdm*, ww */
+    SB_FAM_WFR,     /* hashed weak-factor recognition: wfr*, twfr*, lwfr* */
+    SB_FAM_SKIPQ,   /* q-gram bucket skip search: skip3..8 */
+    SB_FAM_BADCHAR, /* further bad-character / good-suffix shift variants: bfs, ffs, iom, wom, pbmh, qlqs, tsw, wc, zt, ... */
+    SB_FAM_SSEF     /* SSE filtering: ssef (m >= 32) */
 };
 
 /* which end of the pattern the candidate fingerprint is taken from: the left-to-right families
@@ -47,6 +58,7 @@ typedef struct sb_algo_desc {
     int q;     /* HASHq rank */
     int Q, S;  /* QF parameters */
     int min_m; /* smaller m -> -1, as the reference */
+    int min_ratio; /* n / m below this -> -1 (dbww.c:35); 0 = no such rule */
 } sb_algo_desc;
 
 const sb_algo_desc *sb_algo_desc_get(int algo);

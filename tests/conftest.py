@@ -24,9 +24,9 @@ def built_artifacts():
     if not os.path.exists(smart_b200.library_path()):
         smart_b200.build_library()
     if not os.path.exists(os.path.join(ROOT, "bin", "algos", "bf")):
-        subprocess.run(["make", "-C", os.path.join(ROOT, "smart_b200", "host")], check=True, capture_output=True)
+        subprocess.run(["make", "-j8", "-C", os.path.join(ROOT, "smart_b200", "host")], check=True, capture_output=True)
     if not os.path.exists(os.path.join(ROOT, "oracle", "libsmart_oracle.so")):
-        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle", "ref"], check=True, capture_output=True)
+        subprocess.run(["make", "-j8", "-C", os.path.join(ROOT, "oracle"), "oracle", "ref"], check=True, capture_output=True)
 
 
 @pytest.fixture(scope="session")

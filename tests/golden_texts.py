@@ -16,6 +16,46 @@ ALGOS = (
     "bndm", "br", "tvsbs", "fjs", "ssabs", "ts",
     "skip", "kmpskip", "fs", "graspm",
 )
+# tier 1: scan restated in oracle/smart_oracle.c.  Tier 2: result specification + -1 domain only, pinned by the
+# recorded outputs of the unmodified reference (counts.json)
+TIER1 = ALGOS
+TIER2 = (
+    "aoso2", "aoso4", "aoso6", "faoso2", "faoso4", "svm0", "blim", "ufndmq2", "ufndmq4", "ufndmq6", "ufndmq8", "aut",
+    "smoa", "tw", "rcolussi", "bndmq2", "bndmq4", "bndmq6", "lbndm", "sbndm", "sbndm-bmh", "fsbndm-w2", "fndm", "tndm",
+    "tndma", "bxs", "bxs2", "bxs4", "bxs6", "bxs8", "bww", "dbww", "dbww2", "bom", "bom2", "ebom",
+    "fbom", "sebom", "sfbom", "ildm1", "ildm2", "fdm", "bsdm", "bsdm4", "bsdm5", "bsdm7", "bsdm8", "ww",
+    "wfr", "wfr2", "wfr3", "wfr4", "wfr5", "wfr6", "wfr7", "wfr8", "wfrq2", "wfrq3", "wfrq4", "wfrq5",
+    "wfrq6", "wfrq7", "wfrq8", "twfr", "twfr2", "twfr3", "twfr4", "twfr5", "twfr6", "twfr7", "twfr8", "twfrq2",
+    "twfrq3", "twfrq4", "twfrq5", "twfrq6", "twfrq7", "twfrq8", "lwfr2", "lwfr3", "lwfr4", "lwfr5", "lwfr6", "lwfr7",
+    "lwfr8", "skip3", "skip5", "skip6", "skip7", "skip8", "bfs", "ffs", "iom", "wom", "pbmh", "qlqs",
+    "tsw", "wc", "zt", "tvsbs-w2", "fs-w1", "ssef",
+)
+ALGOS = TIER1 + TIER2
+
+# -1 domains (Appendix A.1 of SURVEY.md; the `return -1` guards of the sources)
+MIN_M = {"raita": 2, "hash3": 3, "hash5": 5, "hash8": 8, "aoso2": 3, "aoso4": 5, "aoso6": 7, "faoso2": 3, "faoso4": 5,
+         "ebom": 2, "lbndm": 2, "sbndm": 2, "sbndm-bmh": 2, "sebom": 2, "ssef": 32}
+MIN_RATIO = {"dbww": 2, "dbww2": 2}
+
+
+def min_m(algo: str) -> int:
+    import re
+
+    if algo in MIN_M:
+        return MIN_M[algo]
+    if algo.startswith("qf"):
+        return int(algo[2]) + 1
+    g = re.fullmatch(r"(bndmq|bsdm|bxs|ufndmq|wfr|wfrq|twfr|twfrq|lwfr|skip)(\d)", algo)
+    return int(g.group(2)) if g else 1
+
+
+def expected(algo: str, m: int, bf: int, n=None) -> int:
+    """what the reference returns for a pattern of length m whose true count is bf"""
+    if m < min_m(algo):
+        return -1
+    if n is not None and algo in MIN_RATIO and n // m < MIN_RATIO[algo]:
+        return -1
+    return bf
 
 M_SET = (1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 14, 15, 16, 17, 24, 30, 31, 32, 33, 48, 62, 63, 64, 65, 100, 128, 256,
          512, 1024, 2048, 4096)

@@ -51,7 +51,10 @@ def test_reference_harness_drives_our_executables(tmp_path, worker):
     os.symlink(os.path.join(BIN, "algos"), tmp_path / "source" / "bin")
     for a in ("bf", "kmp", "mp", "hor", "bm", "qs", "so", "sa", "kr", "tunedbm", "raita", "hash3", "hash8", "qf23", "qf63",
               "smith", "tbm", "ag", "ac", "bndm", "br", "tvsbs", "fjs", "ssabs", "ts",
-              "skip", "kmpskip", "fs", "graspm"):
+              "skip", "kmpskip", "fs", "graspm",
+              # second batch: a few of every family
+              "aoso2", "blim", "ufndmq4", "aut", "tw", "smoa", "sbndm", "bxs4", "dbww", "bom", "ebom", "bsdm5", "wfr",
+              "twfrq3", "lwfr4", "skip5", "zt", "tvsbs-w2", "fs-w1", "ssef"):
         r = run([os.path.join(REF, "test"), a], cwd=tmp_path, env=worker)
         assert "Test passed" in r.stdout and r.returncode == 0, (a, r.stdout[-300:], r.stderr[-300:])
     searches, uploads = stats(worker)

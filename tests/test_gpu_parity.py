@@ -10,7 +10,7 @@ import pytest
 
 import smart_b200 as sb
 from fixtures import TEST_C_FIXTURES, seeded_random_fixtures
-from golden_texts import ALGOS, GOLDEN, TEXT_NAMES, make_patterns, make_text
+from golden_texts import ALGOS, GOLDEN, TEXT_NAMES, make_patterns, make_text, expected
 
 pytestmark = pytest.mark.gpu
 
@@ -19,11 +19,6 @@ FILTERS = {0: 0, 1: sb.FLAG_FILTER_SHIFT, 2: sb.FLAG_FILTER_B2, 4: sb.FLAG_FILTE
            32: sb.FLAG_FILTER_B32, 408: sb.FLAG_FILTER_B4L8, 416: sb.FLAG_FILTER_B4L16, 816: sb.FLAG_FILTER_B8L16}
 
 
-def expected(algo, m, bf):
-    min_m = {"raita": 2, "hash3": 3, "hash5": 5, "hash8": 8}.get(algo, 1)
-    if algo.startswith("qf"):
-        min_m = int(algo[2]) + 1
-    return -1 if m < min_m else bf
 
 
 def filters_for(m):
@@ -48,10 +43,10 @@ def test_testc_fixtures_all_algorithms(x, y, count):
     streaming entry and the legacy plugin entry."""
     with sb.Text.upload(y) as t:
         for a in ALGOS:
-            want = expected(a, len(x), count)
+            want = expected(a, len(x), count, len(y))
             assert sb.search(a, t, x).count == want, a
     for a in ("bf", "kmp", "hor", "so", "hash3", "qf23"):
-        want = expected(a, len(x), count)
+        want = expected(a, len(x), count, len(y))
         assert sb.search_host(a, x, y).count == want, a
         assert sb.plugin_search(a, x, y) == want, a
 
@@ -61,7 +56,7 @@ def test_testc_random_cases(oracle):
         c = oracle.bf_count(x, y)
         with sb.Text.upload(y) as t:
             for a in ALGOS:
-                assert sb.search(a, t, x).count == expected(a, len(x), c)
+                assert sb.search(a, t, x).count == expected(a, len(x), c, len(y))
 
 
 @pytest.mark.parametrize("tname", TEXT_NAMES)

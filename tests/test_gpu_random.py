@@ -6,16 +6,11 @@ from hypothesis import HealthCheck, given, settings
 from hypothesis import strategies as st
 
 import smart_b200 as sb
-from golden_texts import ALGOS
+from golden_texts import ALGOS, expected
 
 pytestmark = pytest.mark.gpu
 
 
-def expected(algo, m, bf):
-    min_m = {"raita": 2, "hash3": 3, "hash5": 5, "hash8": 8}.get(algo, 1)
-    if algo.startswith("qf"):
-        min_m = int(algo[2]) + 1
-    return -1 if m < min_m else bf
 
 
 @st.composite
@@ -47,7 +42,7 @@ def test_random_small_cases(oracle, case):
     want = oracle.bf_positions(x, y)
     with sb.Text.upload(y) as t, sb.Text.upload(y, devices=[0, 0]) as t2:
         for a in ALGOS:
-            assert sb.search(a, t, x).count == expected(a, x.size, want.size), (a, x.size, y.size)
+            assert sb.search(a, t, x).count == expected(a, x.size, want.size, y.size), (a, x.size, y.size)
         r = sb.search("kmp", t2, x, flags=sb.FLAG_POSITIONS, positions_cap=max(1, y.size))
         assert np.array_equal(r.positions, want)
         for flags in (sb.FLAG_DENSE, sb.FLAG_FILTER_SHIFT if x.size >= 5 else 0, sb.FLAG_NO_SKIP, sb.FLAG_NO_PERIOD):

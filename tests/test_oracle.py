@@ -10,16 +10,11 @@ import pytest
 
 import oracle_lib
 from fixtures import TEST_C_FIXTURES, seeded_random_fixtures
-from golden_texts import ALGOS, GOLDEN, TEXT_NAMES, make_patterns, make_text
+from golden_texts import ALGOS, GOLDEN, TEXT_NAMES, make_patterns, make_text, expected
 
 REF_DATA = "/root/reference/data"
 
 
-def expected(algo, m, bf):
-    min_m = {"raita": 2, "hash3": 3, "hash5": 5, "hash8": 8}.get(algo, 1)
-    if algo.startswith("qf"):
-        min_m = int(algo[2]) + 1
-    return -1 if m < min_m else bf
 
 
 @pytest.mark.parametrize("x,y,count", TEST_C_FIXTURES)
@@ -28,7 +23,7 @@ def test_testc_fixtures(oracle, x, y, count):
     assert oracle.bf_count(x, y, fast=True) == count
     assert len(oracle.bf_positions(x, y)) == count
     for a in ALGOS:
-        assert oracle.search(a, x, y) == expected(a, len(x), count), a
+        assert oracle.search(a, x, y) == expected(a, len(x), count, len(y)), a
 
 
 def test_testc_random_cases(oracle):
@@ -36,7 +31,7 @@ def test_testc_random_cases(oracle):
         c = oracle.bf_count(x, y, fast=False)
         assert c >= 1  # test.c:330,340: the pattern is a prefix of the text
         for a in ALGOS:
-            assert oracle.search(a, x, y) == expected(a, len(x), c), a
+            assert oracle.search(a, x, y) == expected(a, len(x), c, len(y)), a
 
 
 def test_positions_sorted_and_exact(oracle):
