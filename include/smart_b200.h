@@ -188,6 +188,8 @@ typedef struct sb_tables {
     int brBc[SB_SIGMA * SB_SIGMA]; /* br.c:26-37 == tvsbs.c:26-37, row-major [a][b] */
     int qfQ, qfS;               /* qf<Q><S>.c:28-29; 0 if not a QF */
     int qfB[1 << 18];           /* qf23.c:50-56; entries [0, 1<<(Q*S)) */
+    int wfrQ;                   /* wfrq<Q>.c / twfrq<Q>.c: q-gram length; 0 for wfr, wfr2..8, twfr*, lwfr* */
+    unsigned char wfrF[65536];  /* wfr.c:41-58, wfrq4.c:50-65: weak-factor table, 1 = some factor hashes here */
 } sb_tables;
 /* Build every table the algorithm family of `algo` uses (others are left zeroed).
  * Returns 0, or -1 when the algorithm is not applicable to m (same rule as sb_search64). */

@@ -113,6 +113,8 @@ class Tables(C.Structure):
         ("qfQ", C.c_int),
         ("qfS", C.c_int),
         ("qfB", C.c_int * (1 << 18)),
+        ("wfrQ", C.c_int),
+        ("wfrF", C.c_ubyte * 65536),
     ]
 
 

@@ -118,13 +118,13 @@ static const sb_algo_desc g_algos[] = {
     {"wfr6", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 6, 0}, /* wfr6.c:60, m<6 -> -1 (:64) */
     {"wfr7", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 7, 0}, /* wfr7.c:61, m<7 -> -1 (:65) */
     {"wfr8", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 8, 0}, /* wfr8.c:60, m<8 -> -1 (:64) */
-    {"wfrq2", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* wfrq2.c:68, m<2 -> -1 (:72) */
-    {"wfrq3", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 3, 0}, /* wfrq3.c:67, m<3 -> -1 (:71) */
-    {"wfrq4", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 4, 0}, /* wfrq4.c:67, m<4 -> -1 (:71) */
-    {"wfrq5", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 5, 0}, /* wfrq5.c:66, m<5 -> -1 (:70) */
-    {"wfrq6", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 6, 0}, /* wfrq6.c:67, m<6 -> -1 (:71) */
-    {"wfrq7", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 7, 0}, /* wfrq7.c:68, m<7 -> -1 (:72) */
-    {"wfrq8", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 8, 0}, /* wfrq8.c:67, m<8 -> -1 (:71) */
+    {"wfrq2", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 2, 0, 2, 0}, /* wfrq2.c:68, m<2 -> -1 (:72) */
+    {"wfrq3", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 3, 0, 3, 0}, /* wfrq3.c:67, m<3 -> -1 (:71) */
+    {"wfrq4", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 4, 0, 4, 0}, /* wfrq4.c:67, m<4 -> -1 (:71) */
+    {"wfrq5", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 5, 0, 5, 0}, /* wfrq5.c:66, m<5 -> -1 (:70) */
+    {"wfrq6", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 6, 0, 6, 0}, /* wfrq6.c:67, m<6 -> -1 (:71) */
+    {"wfrq7", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 7, 0, 7, 0}, /* wfrq7.c:68, m<7 -> -1 (:72) */
+    {"wfrq8", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 8, 0, 8, 0}, /* wfrq8.c:67, m<8 -> -1 (:71) */
     {"twfr", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* twfr.c:42 */
     {"twfr2", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* twfr2.c:41, m<2 -> -1 (:45) */
     {"twfr3", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 3, 0}, /* twfr3.c:41, m<3 -> -1 (:45) */
@@ -133,13 +133,13 @@ static const sb_algo_desc g_algos[] = {
     {"twfr6", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 6, 0}, /* twfr6.c:41, m<6 -> -1 (:45) */
     {"twfr7", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 7, 0}, /* twfr7.c:41, m<7 -> -1 (:45) */
     {"twfr8", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 8, 0}, /* twfr8.c:41, m<8 -> -1 (:45) */
-    {"twfrq2", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* twfrq2.c:49, m<2 -> -1 (:53) */
-    {"twfrq3", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 3, 0}, /* twfrq3.c:48, m<3 -> -1 (:52) */
-    {"twfrq4", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 4, 0}, /* twfrq4.c:48, m<4 -> -1 (:52) */
-    {"twfrq5", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 5, 0}, /* twfrq5.c:48, m<5 -> -1 (:52) */
-    {"twfrq6", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 6, 0}, /* twfrq6.c:48, m<6 -> -1 (:52) */
-    {"twfrq7", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 7, 0}, /* twfrq7.c:48, m<7 -> -1 (:52) */
-    {"twfrq8", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 8, 0}, /* twfrq8.c:48, m<8 -> -1 (:52) */
+    {"twfrq2", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 2, 0, 2, 0}, /* twfrq2.c:49, m<2 -> -1 (:53) */
+    {"twfrq3", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 3, 0, 3, 0}, /* twfrq3.c:48, m<3 -> -1 (:52) */
+    {"twfrq4", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 4, 0, 4, 0}, /* twfrq4.c:48, m<4 -> -1 (:52) */
+    {"twfrq5", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 5, 0, 5, 0}, /* twfrq5.c:48, m<5 -> -1 (:52) */
+    {"twfrq6", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 6, 0, 6, 0}, /* twfrq6.c:48, m<6 -> -1 (:52) */
+    {"twfrq7", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 7, 0, 7, 0}, /* twfrq7.c:48, m<7 -> -1 (:52) */
+    {"twfrq8", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 8, 0, 8, 0}, /* twfrq8.c:48, m<8 -> -1 (:52) */
     {"lwfr2", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* lwfr2.c:60, m<2 -> -1 (:65) */
     {"lwfr3", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 3, 0}, /* lwfr3.c:60, m<3 -> -1 (:65) */
     {"lwfr4", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 4, 0}, /* lwfr4.c:60, m<4 -> -1 (:65) */
@@ -461,6 +461,40 @@ void sb_prep_qf(const unsigned char *x, int m, int Q, int S, int *B)
     }
 }
 
+/* Weak-factor-recognition table (wfr.c:41-58, wfrq4.c:50-65): F[h] = 1 for the 16-bit hash h of every pattern
+ * factor the scan can ask about.  The hash is built right to left, as the scan reads the window.
+ * Q <= 1 (wfr, wfr2..8, twfr*, lwfr*): every factor x[j..i] of at most 16 characters, h <- (h << 2) + x[j].
+ * Q >= 2 (wfrqQ, twfrqQ): factors made of whole q-grams ending at i, i-Q, i-2Q, ... and not reaching further
+ * back than min(m, 8) characters; a q-gram ending at e hashes to g(e) = sum_k x[e-k] << 2(Q-1-k) and
+ * h <- (h << 2Q) + g(e).  All arithmetic modulo 2^16 (the reference keeps h in an unsigned short). */
+void sb_prep_wfr(const unsigned char *x, int m, int Q, unsigned char *F)
+{
+    memset(F, 0, 65536);
+    if (Q <= 1) {
+        const int fact = m < 16 ? m : 16;
+        for (int i = 0; i < m; i++) {
+            const int stop = i - fact + 1 > 0 ? i - fact + 1 : 0;
+            unsigned h = 0;
+            for (int j = i; j >= stop; j--) {
+                h = ((h << 2) + x[j]) & 0xffffu;
+                F[h] = 1;
+            }
+        }
+        return;
+    }
+    const int fact = m < 8 ? m : 8;
+    for (int i = Q - 1; i < m; i++) {
+        const int stop = i - fact + 1 >= Q - 1 ? i - fact + 1 : Q - 1;
+        unsigned h = 0;
+        for (int e = i; e == i || e >= stop; e -= Q) {
+            unsigned g = 0;
+            for (int k = 0; k < Q; k++) g += (unsigned)x[e - k] << (2 * (Q - 1 - k));
+            h = (e == i ? g : (h << (2 * Q)) + g) & 0xffffu;
+            F[h] = 1;
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ all tables of a family */
 
 int sb_prep_tables(int algo, const unsigned char *x, int m, sb_tables *out)
@@ -536,6 +570,24 @@ int sb_prep_tables(int algo, const unsigned char *x, int m, sb_tables *out)
         out->qfS = d->S;
         sb_prep_qf(x, m, d->Q, d->S, out->qfB);
         break;
+    case SB_FAM_WFR:
+        out->wfrQ = d->Q;
+        sb_prep_wfr(x, m, d->Q, out->wfrF);
+        if (!strncmp(d->name, "lwfr", 4)) { /* lwfr4.c:36 preKmp: the linear variant also carries kmpNext */
+            sb_prep_mp(x, m, out->mpNext);
+            sb_prep_kmp(x, m, out->mpNext, out->kmpNext);
+        }
+        break;
+    case SB_FAM_BADCHAR: /* members whose tables are the reference's own copies of builders above */
+        if (!strcmp(d->name, "tsw")) sb_prep_brbc(x, m, out->brBc);          /* tsw.c preBrBc == br.c:26-37 */
+        else if (!strcmp(d->name, "fs-w1")) sb_prep_fsgs(x, m, out->fsGs);   /* fs-w1.c Pre_GS == fs.c Pre_GS */
+        else if (!strcmp(d->name, "qlqs")) sb_prep_qsbc(x, m, out->qsBc);    /* qlqs.c:32-36 == qs.c:26-30 (forward table) */
+        else if (!strcmp(d->name, "zt")) {                                   /* zt.c suffixes/preBmGs == bm.c:36-66 */
+            sb_prep_suffixes(x, m, out->suff);
+            sb_prep_bmgs(x, m, out->suff, out->bmGs);
+        }
+        break;
+    default: break; /* the other second-batch families expose no tables yet */
     }
     return 0;
 }

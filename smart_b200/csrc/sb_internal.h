@@ -56,7 +56,7 @@ typedef struct sb_algo_desc {
     int family;
     int anchor;
     int q;     /* HASHq rank */
-    int Q, S;  /* QF parameters */
+    int Q, S;  /* QF parameters; WFR: Q = q-gram length of the wfrq/twfrq variants */
     int min_m; /* smaller m -> -1, as the reference */
     int min_ratio; /* n / m below this -> -1 (dbww.c:35); 0 = no such rule */
 } sb_algo_desc;
@@ -80,6 +80,7 @@ void sb_prep_brbc(const unsigned char *x, int m, int *brBc);
 void sb_prep_hashq(const unsigned char *x, int m, int q, int *shift, int *sh1);
 void sb_prep_kr(const unsigned char *x, int m, int *d, int *hx);
 void sb_prep_qf(const unsigned char *x, int m, int Q, int S, int *B);
+void sb_prep_wfr(const unsigned char *x, int m, int Q, unsigned char *F);
 
 #ifdef __cplusplus
 }

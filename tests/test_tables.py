@@ -50,6 +50,18 @@ def test_tables_vs_reference_dump(table_cases):
             assert arr(sb.prep_tables("raita", x).hbc, 256) == ent["hbc"]
         assert arr(sb.prep_tables("tunedbm", x).hbc, 256) == ent["hbc"]
         assert arr(sb.prep_tables("fs", x).fsGs, m + 1) == ent["fsGs"]  # Pre_GS dumped from fs.c
+        # second batch: the reference keeps private copies of these builders (checked equal in make_golden.py)
+        assert arr(sb.prep_tables("fs-w1", x).fsGs, m + 1) == ent["fsGs"]
+        assert arr(sb.prep_tables("qlqs", x).qsBc, 256) == ent["qsBc"]
+        t = sb.prep_tables("zt", x)
+        assert arr(t.suff, m) == ent["suff"] and arr(t.bmGs, m) == ent["bmGs"]
+        if m >= 4:
+            assert arr(sb.prep_tables("lwfr4", x).kmpNext, m + 1) == ent["kmpNext"]
+        tsw = np.ctypeslib.as_array(sb.prep_tables("tsw", x).brBc).astype(np.int32)
+        assert hashlib.sha1(tsw.tobytes()).hexdigest() == ent["brBc_sha1"]
+        for a, digest in ent["wfrF_sha1"].items():  # the 37 weak-factor variants share two table builders
+            F = bytes(sb.prep_tables(a, x).wfrF)
+            assert hashlib.sha1(F).hexdigest()[:16] == digest, (a, m)
         br = np.ctypeslib.as_array(sb.prep_tables("br", x).brBc).astype(np.int32)
         assert hashlib.sha1(br.tobytes()).hexdigest() == ent["brBc_sha1"]  # preBrBc dumped from br.c
 
