@@ -58,7 +58,7 @@ typedef struct {
     int minlen, maxlen;
     int npat;       /* -pset */
     long tsize;     /* bytes */
-    int occ, pre, dif, std, txt, xml;
+    int occ, pre, dif, std, txt, xml, tex, html;
     int limit_ms;   /* -tb */
     unsigned seed;
     int use_worker;
@@ -98,6 +98,8 @@ static void usage(void)
            "\t-tb MS           time bound per cell in ms (default 300)\n"
            "\t-occ -pre -dif -std -txt   as in SMART\n"
            "\t-xml             also write results/<code>/<text>.xml (schema of SMART's outputXML)\n"
+           "\t-tex             also write results/<code>/<text>.tex (tabular, as SMART's outputLatex)\n"
+           "\t-html            also write results/<code>/<text>.html and results/<code>/index.html\n"
            "\t-simple P T      one search of pattern P in text T\n"
            "\t-algo a,b,c      algorithms to run (default bf,kmp,hor,so)\n"
            "\t-alist FILE      read the selection from a SMART registry file (#1 #name lines)\n"
@@ -149,6 +151,26 @@ static void destroy_all(void)
     seg_destroy(&seg_pre);
     seg_destroy(&seg_mpat);
     seg_destroy(&seg_mcounts);
+}
+
+/* results/<code>/<label>.<ext>, directories created on the way (output.h:119-128) */
+static FILE *open_report(const config *cf, const char *label, const char *ext)
+{
+    char path[1024];
+    snprintf(path, sizeof path, "%s/%s", cf->resdir, cf->code);
+    mkdir(cf->resdir, 0775);
+    mkdir(path, 0775);
+    snprintf(path, sizeof path, "%s/%s/%s.%s", cf->resdir, cf->code, label, ext);
+    FILE *f = fopen(path, "w");
+    if (f) printf("\tSaving data on %s/%s.%s\n", cf->code, label, ext);
+    else printf("\tError in writing file %s/%s.%s\n", cf->code, label, ext);
+    return f;
+}
+
+static void upper_name(char *dst, size_t cap, const char *name)
+{
+    snprintf(dst, cap, "%s", name);
+    for (char *q = dst; *q; q++) *q = (char)toupper((unsigned char)*q);
 }
 
 /* ---- corpus loading: index.txt with #file# markers (smart.c:95-138) ---- */
@@ -491,6 +513,83 @@ static void run_experiment(const config *cf, const char *label, unsigned char *T
             fclose(f);
         }
     }
+    if (cf->tex && !simple) { /* output.h:153-194: a tabular with one row per algorithm, "-" = no result */
+        FILE *f = open_report(cf, label, "tex");
+        if (f) {
+            fprintf(f, "\\begin{tabular}{|l|");
+            for (int il = 0; il < MAX_LENS && cf->lens[il] > 0; il++)
+                if (cf->lens[il] >= cf->minlen && cf->lens[il] <= cf->maxlen) fputc('l', f);
+            fprintf(f, "|}\n\\hline\n$m$");
+            for (int il = 0; il < MAX_LENS && cf->lens[il] > 0; il++)
+                if (cf->lens[il] >= cf->minlen && cf->lens[il] <= cf->maxlen) fprintf(f, " & $%d$", cf->lens[il]);
+            fprintf(f, "\\\\\n");
+            for (int a = 0; a < cf->nalgo; a++) {
+                char up[32];
+                upper_name(up, sizeof up, cf->algos[a]);
+                fprintf(f, "\\textsc{%s}", up);
+                for (int il = 0; il < MAX_LENS && cf->lens[il] > 0; il++) {
+                    if (cf->lens[il] < cf->minlen || cf->lens[il] > cf->maxlen) continue;
+                    if (mean[a][il] == 0) fprintf(f, " & -");
+                    else fprintf(f, " & %.4f", mean[a][il]);
+                }
+                fprintf(f, "\\\\\n");
+            }
+            fprintf(f, "\\hline\n\\end{tabular}");
+            fclose(f);
+        }
+    }
+    if (cf->html && !simple) {
+        /* output.h:635-704 renders the XML with a script; here the same table (lengths across, one row per
+         * algorithm, best time of a column underlined) is written out statically, next to an index.html in
+         * the layout of output.h:706-745 so that results/<code>/ can be browsed like the reference's */
+        FILE *f = open_report(cf, label, "html");
+        if (f) {
+            fprintf(f, "<html>\n<head>\n\t<title>SMART: experimental results %s on %s</title>\n"
+                       "\t<meta http-equiv=\"Content-Type\" content=\"text/html; charset=utf-8\" />\n"
+                       "\t<link href=\"../style.css\" rel=\"stylesheet\" type=\"text/css\" />\n</head>\n<body>\n"
+                       "\t<h2>SMART: experimental results %s on %s</h2><br>Mean search times in milliseconds "
+                       "(smart_b200, GPU)<br/>\n\t<table align=\"center\">\n\t\t<tr><td></td>",
+                    cf->code, label, cf->code, label);
+            for (int il = 0; il < MAX_LENS && cf->lens[il] > 0; il++)
+                if (cf->lens[il] >= cf->minlen && cf->lens[il] <= cf->maxlen) fprintf(f, "<td><b>%d</b></td>", cf->lens[il]);
+            fprintf(f, "</tr>\n");
+            for (int a = 0; a < cf->nalgo; a++) {
+                char up[32];
+                upper_name(up, sizeof up, cf->algos[a]);
+                fprintf(f, "\t\t<tr><td><b>%s</b></td>", up);
+                for (int il = 0; il < MAX_LENS && cf->lens[il] > 0; il++) {
+                    if (cf->lens[il] < cf->minlen || cf->lens[il] > cf->maxlen) continue;
+                    double best = 0;
+                    for (int b = 0; b < cf->nalgo; b++)
+                        if (mean[b][il] > 0 && (best == 0 || mean[b][il] < best)) best = mean[b][il];
+                    if (mean[a][il] == 0) fprintf(f, "<td>--</td>");
+                    else if (mean[a][il] == best) fprintf(f, "<td><b><u>%.4f</u></b></td>", mean[a][il]);
+                    else fprintf(f, "<td>%.4f</td>", mean[a][il]);
+                }
+                fprintf(f, "</tr>\n");
+            }
+            fprintf(f, "\t</table>\n</body>\n</html>");
+            fclose(f);
+        }
+        char path[1024];
+        snprintf(path, sizeof path, "%s/%s/index.html", cf->resdir, cf->code);
+        const int fresh = access(path, F_OK) != 0;
+        f = fopen(path, fresh ? "w" : "r+");
+        if (f) { /* one row per text buffer; appended before the closing tags on later buffers */
+            static const char tail[] = "\t</table>\n</body>\n</html>";
+            if (fresh)
+                fprintf(f, "<html>\n<head>\n\t<title>SMART: experimental results %s</title>\n"
+                           "\t<meta http-equiv=\"Content-Type\" content=\"text/html; charset=utf-8\" />\n"
+                           "\t<link href=\"../style.css\" rel=\"stylesheet\" type=\"text/css\" />\n</head>\n<body>\n"
+                           "\t<h2>SMART: experimental results %s</h2><br>\n\t<table align=\"center\">\n",
+                        cf->code, cf->code);
+            else
+                fseek(f, -(long)(sizeof tail - 1), SEEK_END);
+            fprintf(f, "\t\t<tr><td><a href=\"%s.html\">Experimental results on %s</a></td></tr>\n%s", label, label, tail);
+            fclose(f);
+            printf("\tWriting %s/index.html\n", cf->code);
+        }
+    }
     free(set);
     free(samples);
 }
@@ -538,6 +637,8 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "-std")) cf.std = 1;
         else if (!strcmp(a, "-txt")) cf.txt = 1;
         else if (!strcmp(a, "-xml")) cf.xml = 1;
+        else if (!strcmp(a, "-tex")) cf.tex = 1;
+        else if (!strcmp(a, "-html")) cf.html = 1;
         else if (!strcmp(a, "-short")) cf.lens = LEN_SHORT;
         else if (!strcmp(a, "-vshort")) cf.lens = LEN_VERY_SHORT;
         else if (!strcmp(a, "-algo")) { NEED(1); add_algos_csv(&cf, argv[++i]); }

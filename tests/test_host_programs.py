@@ -89,7 +89,8 @@ def test_our_driver_drives_reference_executables(tmp_path):
     (data / "index.txt").write_text("#part1.txt#\n#part2.txt#\n")
     r = run([os.path.join(BIN, "smart"), "-text", "mini", "-data", str(tmp_path / "data"), "-results",
              str(tmp_path / "results"), "-pset", "3", "-plen", "2", "16", "-short", "-algo", "bf,kmp,hash3,raita",
-             "-bin", REFBIN, "-occ", "-pre", "-dif", "-std", "-txt", "-xml", "-seed", "5", "-noworker"], cwd=tmp_path)
+             "-bin", REFBIN, "-occ", "-pre", "-dif", "-std", "-txt", "-xml", "-tex", "-html", "-seed", "5", "-noworker"],
+            cwd=tmp_path)
     assert r.returncode == 0, r.stderr
     out = r.stdout
     assert "Text buffer of dimension 65536 byte" in out
@@ -112,10 +113,56 @@ def test_our_driver_drives_reference_executables(tmp_path):
     xml = list((tmp_path / "results").glob("EXP*/mini.xml"))[0].read_text()
     assert xml.startswith("<RESULTS>") and xml.count("<ALGO>") == 4 and xml.count("<NAME>HASH3</NAME>") == 1
     assert xml.count("<DATA>-</DATA>") == 1 and xml.count("<SEARCH>") == 8 * 4 - 1 and "<BEST>" in xml
+    # -tex (output.h:153-194) and -html (+ index.html, output.h:635-745)
+    tex = list((tmp_path / "results").glob("EXP*/mini.tex"))[0].read_text()
+    assert tex.startswith("\\begin{tabular}{|l|llllllll|}") and tex.endswith("\\end{tabular}")
+    assert "$m$ & $2$ & $4$" in tex and tex.count("\\textsc{") == 4 and "\\textsc{HASH3} & - &" in tex
+    html = list((tmp_path / "results").glob("EXP*/mini.html"))[0].read_text()
+    assert html.count("<tr>") == 5 and "<td><b>HASH3</b></td><td>--</td>" in html and html.count("<b><u>") == 8
+    index = list((tmp_path / "results").glob("EXP*/index.html"))[0].read_text()
+    assert index.count('<a href="mini.html">') == 1 and index.rstrip().endswith("</html>")
     # -simple mode (smart.c:496-507)
     r = run([os.path.join(BIN, "smart"), "-simple", "aba", "ababababab", "-algo", "bf", "-bin", REFBIN, "-occ",
              "-noworker"], cwd=tmp_path)
     assert "occ 4" in r.stdout
+
+
+def test_select_edits_a_registry_like_the_reference_tool(tmp_path):
+    """bin/select: the command line of src/select.c on the '#<0|1> #<name>' registry format."""
+    sel = os.path.join(BIN, "select")
+    reg = str(tmp_path / "algorithms.h")
+    common = ["-file", reg, "-bin", os.path.join(BIN, "algos")]
+    r = run([sel, "-init", *common])
+    assert r.returncode == 0 and "142 algorithms registered" in r.stdout
+    lines = open(reg).read().splitlines()
+    assert len(lines) == 142 and lines == sorted(lines) and all(ln.startswith("#0 #") for ln in lines)
+    assert run([sel, "-show", *common]).stdout.count("\n") == 143
+    r = run([sel, "bf", "kmp", *common])
+    assert "The bf algorithm has been selected" in r.stdout and "The kmp algorithm has been selected" in r.stdout
+    assert run([sel, "-which", *common]).stdout.split() == ["The", "list", "of", "selected", "algorithms:", "-bf", "-kmp"]
+    assert "has been deselected" in run([sel, "kmp", *common]).stdout
+    assert "#1 #bf " in open(reg).read() and "#0 #kmp " in open(reg).read()
+    run([sel, "-all", *common])
+    assert open(reg).read().count("#1 #") == 142
+    run([sel, "-none", *common])
+    assert open(reg).read().count("#1 #") == 0
+    assert "no parameter nosuch" in run([sel, "nosuch", *common]).stdout
+    # -add: the executable must exist and pass the harness (select.c:105-126)
+    assert "already in the set" in run([sel, "-add", "bf", *common]).stdout
+    assert "does not exist" in run([sel, "-add", "ghost", *common]).stdout
+    extra = tmp_path / "bin"
+    extra.mkdir()
+    os.symlink(os.path.join(BIN, "algos", "bf"), extra / "mine")
+    ok = run([sel, "-add", "mine", "-file", reg, "-bin", str(extra), "-test", "/bin/true"])
+    assert "added succesfully" in ok.stdout and "#0 #mine " in open(reg).read()
+    os.symlink(os.path.join(BIN, "algos", "bf"), extra / "broken")
+    bad = run([sel, "-add", "broken", "-file", reg, "-bin", str(extra), "-test", "/bin/false"])
+    assert "unable to add the algorithm broken" in bad.stdout and "broken" not in open(reg).read()
+    # our driver reads the file it wrote (function.h:62-77 format)
+    run([sel, "hor", *common])
+    r = run([os.path.join(BIN, "smart"), "-simple", "aba", "ababababab", "-alist", reg, "-bin", REFBIN, "-occ", "-noworker"],
+            cwd=tmp_path)
+    assert "HOR" in r.stdout and "occ 4" in r.stdout
 
 
 def test_driver_argument_errors():
