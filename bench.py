@@ -421,6 +421,7 @@ def run_e2e(sb, ranks, dist, device, text, base, own, n_total, pats, algos, ms, 
 
     mmax = max(ms)
     ln = min(n_total - base, own + mmax - 1)
+    sb.set_device(int(str(device).split(":")[1]) if ":" in str(device) else 0)  # this rank's GPU and PCIe link
     pin = sb.pinned_buffer(ln)
     try:
         chunk = 256 << 20

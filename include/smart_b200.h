@@ -73,6 +73,10 @@ int sb_algo_applicable(int algo, int m);
 
 /* ---- device / error plumbing ---- */
 int sb_device_count(void);               /* number of visible CUDA devices, <0 on error */
+/* CUDA device of the host-buffer entry points (sb_search_host, sb_plugin_search); default: the environment
+ * variable SMART_B200_DEVICE, else 0.  One process per GPU sets its local rank.  0, or SB_ERR_ARG. */
+int sb_set_device(int device);
+int sb_get_device(void);
 const char *sb_last_error(void);         /* thread-local message for the last failing call */
 const char *sb_version(void);
 

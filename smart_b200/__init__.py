@@ -29,6 +29,8 @@ from .binding import (  # noqa: F401
     applicable,
     build_library,
     device_count,
+    get_device,
+    set_device,
     last_timing,
     lib,
     library_path,

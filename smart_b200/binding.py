@@ -127,6 +127,8 @@ SYMBOLS = [
     ("sb_algo_id", C.c_int, [C.c_char_p]),
     ("sb_algo_applicable", C.c_int, [C.c_int, C.c_int]),
     ("sb_device_count", C.c_int, []),
+    ("sb_set_device", C.c_int, [C.c_int]),
+    ("sb_get_device", C.c_int, []),
     ("sb_last_error", C.c_char_p, []),
     ("sb_version", C.c_char_p, []),
     ("sb_text_upload", C.c_void_p, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.c_int]),
@@ -193,6 +195,16 @@ def _as_bytes_ptr(buf):
 
 def device_count() -> int:
     return lib().sb_device_count()
+
+
+def set_device(device: int) -> None:
+    """CUDA device of search_host / plugin_search (one process per GPU: its local rank)."""
+    if lib().sb_set_device(device) != 0:
+        raise SmartB200Error(lib().sb_last_error().decode())
+
+
+def get_device() -> int:
+    return lib().sb_get_device()
 
 
 def algo_id(name: str) -> int:

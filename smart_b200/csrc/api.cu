@@ -869,6 +869,31 @@ void sb_text_free(sb_text *t)
     delete t;
 }
 
+/* device used by the host-buffer entry points (sb_search_host, sb_plugin_search): sb_set_device(), else the
+ * environment variable SMART_B200_DEVICE, else 0.  One process per GPU sets it to its local rank. */
+static int g_host_device = -1;
+static int host_device()
+{
+    if (g_host_device < 0) {
+        const char *e = getenv("SMART_B200_DEVICE");
+        g_host_device = e ? atoi(e) : 0;
+    }
+    return g_host_device;
+}
+
+int sb_set_device(int device)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+        set_err("sb_set_device: no such CUDA device%s%s");
+        return SB_ERR_ARG;
+    }
+    g_host_device = device;
+    return 0;
+}
+
+int sb_get_device(void) { return host_device(); }
+
 /* the reference's `return -1` guards: m below the algorithm's minimum (hash3.c:31, raita.c:38, qf23.c:44, ...)
  * or, for the double-window searches, a text shorter than two patterns (dbww.c:35) */
 static bool outside_domain(const sb_algo_desc *d, int m, unsigned long long n)
@@ -1258,7 +1283,7 @@ long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned
     if (pre_ms) *pre_ms = 0;
     if (run_ms) *run_ms = 0;
     if (outside_domain(desc, m, n)) return SB_NOT_APPLICABLE;
-    DevCtx *c = get_ctx(0);
+    DevCtx *c = get_ctx(host_device());
     if (!c) return SB_ERR_CUDA;
 
     const double t0 = now_ms();

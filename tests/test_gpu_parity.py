@@ -423,3 +423,20 @@ def test_tma_fed_block_kernel_matches_oracle():
     env = dict(os.environ, SMART_B200_TMA="1")
     r = subprocess.run([sys.executable, "-c", _TMA_SCRIPT, root], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "tma-ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_host_buffer_entries_follow_sb_set_device(oracle):
+    """sb_search_host / sb_plugin_search run on the device chosen with sb_set_device (one process per GPU sets
+    its local rank; before this knob every rank of a multi-GPU job streamed through GPU 0's PCIe link)."""
+    y = sb.textgen_host(0, 300_000, 4, 21)
+    x = y[1000:1012].copy()
+    want = oracle.bf_count(x, y)
+    assert sb.get_device() == 0
+    with pytest.raises(sb.SmartB200Error):
+        sb.set_device(sb.device_count())
+    for dev in range(min(sb.device_count(), 2)):
+        sb.set_device(dev)
+        assert sb.get_device() == dev
+        assert sb.search_host("kmp", x, y).count == want
+        assert sb.plugin_search("hor", x, y) == want
+    sb.set_device(0)
