@@ -61,7 +61,7 @@ def test_testc_random_cases(oracle):
 
 @pytest.mark.parametrize("tname", TEXT_NAMES)
 def test_golden_reference_counts(oracle, golden, tname):
-    """All 26 algorithms on every golden case: the count must equal what the UNMODIFIED reference
+    """All registered algorithms (142) on every golden case: the count must equal what the UNMODIFIED reference
     algorithm returned (recorded by tests/golden/make_golden.py), including its -1 domains."""
     y = make_text(tname, oracle)
     with sb.Text.upload(y) as t:
@@ -89,7 +89,7 @@ def test_every_filter_width_gives_the_same_count(oracle, golden, tname):
                     assert r.count == want, (tname, c["m"], c["pi"], a, f)
             # the period-aware verification shortcut is an optimisation, never a semantic change
             assert sb.search("kmp", t, x, flags=sb.FLAG_NO_PERIOD).count == want
-            if c["m"] <= 16:  # scan_short / scan_window: dense (count every position) and sparse modes agree
+            if c["m"] <= 16:  # scan_swar / scan_window: dense (count every position) and sparse modes agree
                 assert sb.search("bf", t, x, flags=sb.FLAG_DENSE).count == want
                 r = sb.search("bf", t, x, flags=sb.FLAG_DENSE | sb.FLAG_POSITIONS, positions_cap=y.size)
                 assert r.count == want and np.array_equal(r.positions, oracle.bf_positions(x, y))
