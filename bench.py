@@ -149,12 +149,16 @@ def _cpu_worker(job):
     import oracle_lib
 
     st = _CPU
+    buf, n = st["chunks"][ci]
+    if st["kind"] == "port":  # oracle/_ref absent (fresh checkout on a box without the reference): the C restatement
+        ora = st["refs"].get("_oracle")
+        if ora is None:
+            ora = st["refs"]["_oracle"] = oracle_lib.Oracle()
+        return ora.search(algo, st["pats"][m], buf[:n])
     ref = st["refs"].get(algo)
     if ref is None:
         ref = st["refs"][algo] = oracle_lib.RefAlgo(algo)
-    buf, n = st["chunks"][ci]
-    r = ref.search_padded(st["pats"][m], buf, n)
-    return r
+    return ref.search_padded(st["pats"][m], buf, n)
 
 
 def cpu_reference_setup(sample_bytes, sigma, ms, cores, n_total):
@@ -209,7 +213,8 @@ def run_cpu_reference(args, algos, ms, steps, warmup, n_total):
     return {"value": gbs, "unit": UNIT, "cores": nchunks, "kind": _CPU["kind"],
             "sample": f"first {args.cpu_sample_mib} MiB of the workload text, {len(algos)}x{len(ms)} searches per step "
                       f"({','.join(algos)} x m={','.join(map(str, ms))}), one chunk per core with m-1 overlap, "
-                      f"reference search() compiled -O3 -msse4 (oracle/_ref), {steps} step(s)",
+                      + ("reference search() compiled -O3 -msse4 (oracle/_ref)" if _CPU["kind"] == "reference"
+                         else "oracle/smart_oracle.c restatement (oracle/_ref not built)") + f", {steps} step(s)",
             "seconds": t, "ms_per_step": 1e3 * t / steps}
 
 
