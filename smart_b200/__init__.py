@@ -15,6 +15,7 @@ from .binding import (  # noqa: F401
     FLAG_FILTER_B4L16,
     FLAG_FILTER_B8L16,
     FLAG_FILTER_B2,
+    FLAG_NO_PACK,
     FLAG_FILTER_SHIFT,
     FLAG_NO_SKIP,
     FLAG_DENSE,

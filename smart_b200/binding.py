@@ -35,6 +35,7 @@ FLAG_FILTER_B4L8 = 0x200
 FLAG_FILTER_B4L16 = 0x400
 FLAG_FILTER_B8L16 = 0x800
 FLAG_FILTER_B2 = 0x1000
+FLAG_NO_PACK = 0x2000
 
 ALGORITHMS = (
     "bf", "mp", "kmp", "bm", "hor", "qs", "raita", "tunedbm", "so", "sa", "kr",
@@ -140,6 +141,7 @@ SYMBOLS = [
     ("sb_text_length", C.c_size_t, [C.c_void_p]),
     ("sb_text_shards", C.c_int, [C.c_void_p]),
     ("sb_text_entropy_bits", C.c_double, [C.c_void_p]),
+    ("sb_text_packed_bits", C.c_int, [C.c_void_p]),
     ("sb_text_download", C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
     ("sb_text_free", None, [C.c_void_p]),
     ("sb_textgen_host", None, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_uint64]),
@@ -271,6 +273,11 @@ class Text:
     @property
     def entropy_bits(self) -> float:
         return lib().sb_text_entropy_bits(self._h)
+
+    @property
+    def packed_bits(self) -> int:
+        """2 when the text (<= 4 distinct byte values) also has a 2-bit packed copy in HBM, else 0"""
+        return lib().sb_text_packed_bits(self._h)
 
     def download(self, off: int, length: int) -> np.ndarray:
         out = np.empty(length, dtype=np.uint8)

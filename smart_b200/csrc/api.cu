@@ -58,6 +58,9 @@ constexpr int kU = SB_U;                      // 256-bit loads in flight per thr
 constexpr size_t kGroupLong = kU * 1024;      // bytes per warp iteration of those kernels
 constexpr int kFilterShort = 0, kFilterWindow8 = 1, kFilterWindow16 = 3;  // 2 = the 12-byte window
 constexpr int kFilterPair = 20;               // scan_block<2,L>: windows at even positions, L = 4..8 in Plan::flen
+/* scan_packed<8> moves 4 x 7.2 = 29 T characters/s; scan_skip passes that from a stride of ~400 bytes on */
+constexpr int kPackedBeatsSkipBelow = 448;
+constexpr int kFilterPacked = 300;             // + K (301, 302, 304, 308): scan_packed<K> on the 2-bit recoding
 constexpr int kFilterSkip = 100;              // + gram bytes (108, 116, 132): scan_skip<G>
 constexpr size_t kAuxWords = sb::kBloomWords + 2 * sb::kSkipTableSize;
 
@@ -77,6 +80,7 @@ struct DevCtx {                               // per-device scratch, created on 
     size_t pos_cap = 0;
     void *d_sort_temp = nullptr;              // cub::DeviceRadixSort scratch
     size_t sort_temp_bytes = 0;
+    int occ_packed[4] = {0};                  // ... for scan_packed<K>, K = 1, 2, 4, 8
     int occ_pair[5] = {0};                    // ... for scan_block<2,L>, index L-4
     int occ_block[7] = {0};                   // resident CTAs/SM for scan_block<B,L>, index block_index()
     int occ_window[24] = {0};                 // ... for scan_window<NW,OFF,DENSE>, index window_index()
@@ -157,6 +161,10 @@ DevCtx *get_ctx(int dev)
     c.occ_multi[0] = occupancy(sb::scan_multi_kernel<4, kU>);
     c.occ_multi[1] = occupancy(sb::scan_multi_kernel<8, kU>);
     c.occ_multi[2] = occupancy(sb::scan_multi_kernel<16, kU>);
+    c.occ_packed[0] = occupancy(sb::scan_packed_kernel<1>);
+    c.occ_packed[1] = occupancy(sb::scan_packed_kernel<2>);
+    c.occ_packed[2] = occupancy(sb::scan_packed_kernel<4>);
+    c.occ_packed[3] = occupancy(sb::scan_packed_kernel<8>);
     c.occ_pair[0] = occupancy(sb::scan_block_kernel<2, 4, kU>);
     c.occ_pair[1] = occupancy(sb::scan_block_kernel<2, 5, kU>);
     c.occ_pair[2] = occupancy(sb::scan_block_kernel<2, 6, kU>);
@@ -194,6 +202,8 @@ struct Shard {
     size_t base = 0;      // global offset of local byte 0
     size_t own = 0;       // start positions [base, base+own) belong to this shard
     size_t len = 0;       // valid bytes in the buffer (own + halo, clipped to the text end)
+    uint32_t *d_packed = nullptr;  // 2-bit recoding, 16 characters per word (texts over <= 4 byte values), or nullptr
+    size_t packed_bytes = 0;       // allocated bytes of d_packed (zero padded like the text)
 };
 
 /* Selectivity estimate per text byte from a byte histogram.  For a uniform alphabet both terms are log2(sigma).
@@ -332,21 +342,31 @@ bool use_tma()
     return v == 1;
 }
 
+/* what make_plan needs to know about a resident text's 2-bit recoding */
+struct PackInfo {
+    bool packed = false;
+    int nsym = 0;
+    unsigned char sym[4] = {0, 0, 0, 0};  // byte value of code c
+};
+
 struct Plan {
     int filter;
     int flen;           // scan_block: fingerprint length L (>= filter = B)
     int skip_grams;     // scan_skip: entries of the fingerprint list (= stride), 0 otherwise
     uint32_t list[4224]; // scan_skip: fingerprints of the pattern grams
     bool sparse;        // scan_swar: a match of the whole pattern is rare in this text
+    int packed_K;       // scan_packed: sampling period in words; 0 with filter == kFilterPacked: pattern outside the alphabet
     sb::ScanArgs args;  // text/base/hi/ngroups/counters/pos filled per shard
 };
 
-void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m, unsigned flags, double bits)
+void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m, unsigned flags, double bits,
+               const PackInfo *pk = nullptr)
 {
     memset(&pl.args, 0, sizeof pl.args);
     pl.filter = choose_filter(m, flags, bits, &pl.flen);
     pl.sparse = m * bits >= dense_bits() && !(flags & SB_FLAG_DENSE);  // scan_swar; scan_window decides below
     pl.skip_grams = 0;
+    pl.packed_K = 0;
     sb::ScanArgs &a = pl.args;
     a.m = m;
     a.nwords = (m + 3) / 4;
@@ -363,7 +383,8 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
     const unsigned forced = SB_FLAG_FILTER_SHIFT | SB_FLAG_FILTER_B4 | SB_FLAG_FILTER_B8 | SB_FLAG_FILTER_B16 |
                             SB_FLAG_FILTER_B32 | SB_FLAG_FILTER_B4L8 | SB_FLAG_FILTER_B4L16 | SB_FLAG_FILTER_B8L16 |
                             SB_FLAG_FILTER_B2 | SB_FLAG_NO_SKIP;
-    if (desc->anchor == SB_ANCHOR_SUFFIX && !(flags & forced)) {
+    const bool can_pack = pk && pk->packed && !(flags & (SB_FLAG_NO_PACK | SB_FLAG_DENSE));
+    if (desc->anchor == SB_ANCHOR_SUFFIX && !(flags & forced) && !(can_pack && m < kPackedBeatsSkipBelow)) {
         for (int G = 8; G <= 32; G *= 2) {
             const int stride = ((m - (G - 1)) / 32) * 32;
             if (stride < skip_min_stride()) break;
@@ -387,6 +408,45 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
             pl.filter = kFilterSkip + G;
             pl.skip_grams = stride;
             a.stride = stride;
+            a.anchor = anchor;
+            return;
+        }
+    }
+    /* Texts over <= 4 byte values: scan the 2-bit recoding (a quarter of the bytes).  Every K-th packed word is
+     * looked up among the 16K words packed from x[anchor+d ..], d < 16K; needs m >= 16K+15. */
+    if (pk && pk->packed && m >= 31 && !(flags & (forced | SB_FLAG_NO_PACK | SB_FLAG_DENSE))) {
+        int K = 8;
+        while (16 * K + 15 > m) K >>= 1;
+        const int span = 16 * K;
+        const int anchor = desc->anchor == SB_ANCHOR_SUFFIX ? m - (span + 15) : 0;
+        unsigned char code[256];
+        memset(code, 0xff, sizeof code);
+        for (int c = pk->nsym - 1; c >= 0; c--) code[pk->sym[c]] = (unsigned char)c;
+        bool inside = true;
+        for (int i = 0; i < m && inside; i++) inside = code[x[i]] != 0xff;
+        if (!inside) {  // a byte the text does not contain: no occurrence, nothing to scan
+            pl.filter = kFilterPacked;
+            pl.packed_K = 0;
+            return;
+        }
+        for (int d = 0; d < span; d++) {
+            uint32_t w = 0;
+            for (int k = 0; k < 16; k++) w |= (uint32_t)code[x[anchor + d + k]] << (2 * k);
+            pl.list[d] = w;
+        }
+        uint32_t sorted[160];
+        memcpy(sorted, pl.list, (size_t)span * sizeof(uint32_t));
+        std::sort(sorted, sorted + span);
+        int run = 1, worst = 1;
+        for (int d = 1; d < span; d++) {
+            run = sorted[d] == sorted[d - 1] ? run + 1 : 1;
+            worst = std::max(worst, run);
+        }
+        if (worst <= 8) {  // periodic patterns stay on the byte kernels (same reason as for scan_skip above)
+            pl.filter = kFilterPacked + K;
+            pl.packed_K = K;
+            pl.skip_grams = span;
+            a.stride = span;
             a.anchor = anchor;
             return;
         }
@@ -418,6 +478,7 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
 int filter_kind_of(const Plan &pl)
 {
     if (pl.filter == kFilterPair) return 20 + pl.flen;
+    if (pl.filter >= kFilterPacked) return pl.filter;
     if (pl.filter >= 4 && pl.filter < kFilterSkip && pl.flen != pl.filter) return pl.filter * 100 + pl.flen;
     return pl.filter;
 }
@@ -429,6 +490,24 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
     int per_sm;
     size_t group;
     const bool want_pos = a.pos != nullptr;
+    if (pl.filter >= kFilterPacked) {
+        if (!pl.packed_K) return cudaSuccess;  // pattern outside the text's alphabet: the count stays 0
+        a.aux = c.d_aux;
+        const unsigned long long end = (unsigned long long)a.hi + a.anchor + a.stride + 15;  // characters that matter
+        a.nsamples = (end + 15) / 16;                                                         // packed words
+        a.ngroups = (a.nsamples * 4 + kGroupLong - 1) / kGroupLong;
+        const int ki = pl.packed_K == 1 ? 0 : pl.packed_K == 2 ? 1 : pl.packed_K == 4 ? 2 : 3;
+        const unsigned long long want_ctas = (a.ngroups + (sb::kThreads / 32) - 1) / (sb::kThreads / 32);
+        const unsigned g = (unsigned)std::max(1ull, std::min(want_ctas, (unsigned long long)c.sms * c.occ_packed[ki]));
+        switch (pl.packed_K) {
+        case 1: sb::scan_packed_kernel<1><<<g, sb::kThreads, 0, stream>>>(a); break;
+        case 2: sb::scan_packed_kernel<2><<<g, sb::kThreads, 0, stream>>>(a); break;
+        case 4: sb::scan_packed_kernel<4><<<g, sb::kThreads, 0, stream>>>(a); break;
+        default: sb::scan_packed_kernel<8><<<g, sb::kThreads, 0, stream>>>(a); break;
+        }
+        (void)want_pos;
+        return cudaGetLastError();
+    }
     if (pl.filter >= kFilterSkip) {
         const int G = pl.filter - kFilterSkip;
         a.aux = c.d_aux;
@@ -587,6 +666,8 @@ struct sb_text {
     size_t n = 0;
     int nshards = 0;
     double bits = 8.0;  // collision entropy per byte (min over shards), from a sampled histogram
+    bool present[256] = {false};  // byte values seen in the histogram samples (a guess, verified by pack2_kernel)
+    PackInfo pack;      // the 2-bit recoding, when every byte of every shard is one of <= 4 values
     Shard sh[kMaxShards];
 };
 
@@ -699,6 +780,60 @@ static sb_text *text_alloc(size_t n, const int *devices, int nparts, int first, 
 }
 
 /* sampled byte histogram of every shard -> t->bits (min over shards) */
+/* Texts over at most four byte values also get a 2-bit recoding for scan_packed (a quarter of the bytes to
+ * stream).  The alphabet is guessed from the histogram samples and VERIFIED by the packing pass over every byte;
+ * a text that turns out to hold a fifth value simply has no packed copy.  SMART_B200_NO_PACK=1 disables it.
+ * Costs n/4 bytes of HBM and one extra pass at upload/generation time. */
+static bool text_try_pack(sb_text *t)
+{
+    static const bool off = getenv("SMART_B200_NO_PACK") && atoi(getenv("SMART_B200_NO_PACK")) > 0;
+    int nsym = 0;
+    unsigned char sym[4] = {0, 0, 0, 0};
+    for (int b = 0; b < 256; b++)
+        if (t->present[b]) {
+            if (nsym < 4) sym[nsym] = (unsigned char)b;
+            nsym++;
+        }
+    if (off || nsym < 1 || nsym > 4 || t->n < (1u << 16)) return true;
+    sb::PackLut lut;
+    for (int c = 0; c < 4; c++) lut.sym[c] = c < nsym ? sym[c] : 0xffffffffu;  // unused codes match no byte
+    bool ok = true;
+    for (int g = 0; g < t->nshards && ok; g++) {
+        Shard &s = t->sh[g];
+        DevCtx *c = get_ctx(s.dev);
+        if (!c) return false;
+        cudaSetDevice(s.dev);
+        s.packed_bytes = round_up((s.cap + 3) / 4, sb::kPadBytes) + sb::kPadBytes;
+        if (cudaMalloc(&s.d_packed, s.packed_bytes) != cudaSuccess) {
+            cudaGetLastError();  // not fatal: the byte kernels need no packed copy
+            s.d_packed = nullptr;
+            ok = false;
+            break;
+        }
+        unsigned bad = 0;
+        if (cudaMemsetAsync(c->d_hist, 0, sizeof(unsigned), c->stream) != cudaSuccess) return false;
+        sb::pack2_kernel<<<c->sms * 8, 256, 0, c->stream>>>(s.d_text, s.len, s.cap, s.packed_bytes / 4, s.d_packed, lut,
+                                                          reinterpret_cast<unsigned *>(c->d_hist));
+        if (cudaMemcpyAsync(&bad, c->d_hist, sizeof bad, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return false;
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
+        ok = bad == 0;
+    }
+    if (!ok) {  // a fifth byte value somewhere (or no memory): drop every packed copy
+        for (int g = 0; g < t->nshards; g++)
+            if (t->sh[g].d_packed) {
+                cudaSetDevice(t->sh[g].dev);
+                cudaFree(t->sh[g].d_packed);
+                t->sh[g].d_packed = nullptr;
+                t->sh[g].packed_bytes = 0;
+            }
+        return true;
+    }
+    t->pack.packed = true;
+    t->pack.nsym = nsym;
+    memcpy(t->pack.sym, sym, sizeof sym);
+    return true;
+}
+
 static bool text_measure_bits(sb_text *t)
 {
     double bits = 8.0;
@@ -717,9 +852,10 @@ static bool text_measure_bits(sb_text *t)
         if (cudaMemcpyAsync(hist, c->d_hist, sizeof hist, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return false;
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
         bits = std::min(bits, collision_bits(hist));
+        for (int b = 0; b < 256; b++) t->present[b] = t->present[b] || hist[b] != 0;
     }
     t->bits = bits;
-    return true;
+    return text_try_pack(t);
 }
 
 static sb_text *text_fill_upload(sb_text *t, const unsigned char *host)
@@ -832,6 +968,7 @@ sb_text *sb_text_generate_part(size_t n_total, int sigma, uint64_t seed, int npa
 size_t sb_text_length(const sb_text *t) { return t ? t->n : 0; }
 int sb_text_shards(const sb_text *t) { return t ? t->nshards : 0; }
 double sb_text_entropy_bits(const sb_text *t) { return t ? t->bits : 0.0; }
+int sb_text_packed_bits(const sb_text *t) { return t && t->pack.packed ? 2 : 0; }
 
 int sb_text_download(const sb_text *t, size_t off, size_t len, unsigned char *host)
 {
@@ -865,6 +1002,7 @@ void sb_text_free(sb_text *t)
         if (t->sh[g].d_text) {
             cudaSetDevice(t->sh[g].dev);
             cudaFree(t->sh[g].d_text);
+            if (t->sh[g].d_packed) cudaFree(t->sh[g].d_packed);
         }
     delete t;
 }
@@ -925,7 +1063,7 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
     if (!tab) return SB_ERR_NOMEM;
     sb_prep_tables(algo, x, m, tab);
     Plan pl;
-    make_plan(pl, desc, x, m, flags, t->bits);
+    make_plan(pl, desc, x, m, flags, t->bits, &t->pack);
     const double t1 = now_ms();
 
     DevCtx *ctx[kMaxShards];
@@ -963,6 +1101,7 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
         DevCtx &c = *ctx[g];
         sb::ScanArgs a = pl.args;
         a.text = s.d_text;
+        a.packed = s.d_packed;
         a.pat = c.d_pat;
         a.counters = c.d_counters;
         a.base = s.base;
@@ -972,6 +1111,7 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
         a.pos = with_pos ? c.d_pos : nullptr;
         a.pos_cap = with_pos ? c.pos_cap : 0;
         if (a.hi <= 0) return cudaSuccess;
+        if (pl.filter == kFilterPacked && !pl.packed_K) return cudaSuccess;  // a pattern byte the text lacks: count 0
         launched++;
         return launch_scan(c, pl, a, c.stream);
     };

@@ -52,6 +52,7 @@ __host__ __device__ __forceinline__ uint32_t fp32(uint32_t lo16, uint32_t hi16) 
 
 struct ScanArgs {
     const uint8_t *text;          // shard buffer, 32-B aligned, zero padded (kPadBytes rule)
+    const uint32_t *packed;       // scan_packed: 2-bit recoding of the shard, 16 characters per word (or nullptr)
     const uint32_t *pat;          // pattern as little-endian words, zero padded
     unsigned long long *counters; // [0] match count, [1] position cursor, [2] verified candidates
     unsigned long long *pos;      // position sink (unsorted) or nullptr
@@ -762,6 +763,97 @@ __global__ void __launch_bounds__(kThreads) scan_skip_kernel(const __grid_consta
     block_reduce_count(a, cnt, nver);
 }
 
+
+/* ===================================================================== scan_packed<K> (alphabets of <= 4 symbols) */
+
+/* A text over at most four distinct byte values (DNA, sigma <= 4 generators) is also kept as a 2-bit recoding:
+ * character i lives in word i/16, bits 2*(i%16).. (pack2_kernel, once per text).  A word is then an EXACT
+ * 16-character fingerprint, and the scan reads a quarter of the bytes:
+ *   every occurrence of length m >= 16K+15 contains the 16 characters of some word whose index is a multiple of K;
+ *   that word equals one of the 16K words packed from x[anchor+d .. anchor+d+16), d < 16K.
+ * So the kernel streams the packed buffer (256-bit loads, as scan_block), looks every K-th word up in the Bloom
+ * bitmap of those 16K words (shared memory, 2 probes) and sends the rare hits through the exact table and the
+ * byte-wise verification of scan_skip (skip_candidates: positions and counts come from the ORIGINAL text).
+ * Text rate = 4 x the packed-byte rate: above the read-once HBM roofline of the byte text, like scan_skip. */
+struct PackLut {
+    uint32_t sym[4];  // byte values of codes 0..3 (an unused code holds a value no byte has)
+};
+
+__device__ __forceinline__ uint32_t pack_code(uint32_t b, const PackLut &lut, bool &ok)
+{
+    uint32_t c = 0;
+    if (b == lut.sym[1]) c = 1;
+    if (b == lut.sym[2]) c = 2;
+    if (b == lut.sym[3]) c = 3;
+    ok = (b == lut.sym[c]);
+    return c;
+}
+
+/* out[w] packs text[16w .. 16w+16); bytes at or beyond `len` pack as code 0; *bad is set if a byte below `len`
+ * is none of the four symbols (the caller then drops the packed copy) */
+__global__ void __launch_bounds__(256) pack2_kernel(const uint8_t *text, unsigned long long len, unsigned long long cap,
+                                                    unsigned long long nwords, uint32_t *out, const PackLut lut,
+                                                    unsigned *bad)
+{
+    bool any_bad = false;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords;
+         w += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t word = 0;
+        if (16 * w + 16 <= cap) {
+            const uint4 v = ldg_stream128(text + 16 * w);
+            const uint32_t src[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                bool ok;
+                const uint32_t c = pack_code((src[i >> 2] >> (8 * (i & 3))) & 0xffu, lut, ok);
+                if (16 * w + i < len) {
+                    word |= c << (2 * i);
+                    any_bad |= !ok;
+                }
+            }
+        }
+        out[w] = word;
+    }
+    if (any_bad) atomicOr(bad, 1u);
+}
+
+template <int K>
+__global__ void __launch_bounds__(kThreads) scan_packed_kernel(const __grid_constant__ ScanArgs a)
+{
+    constexpr int U = 4;
+    __shared__ uint32_t bloom[kBloomWords];
+    for (int i = threadIdx.x; i < kBloomWords; i += kThreads) bloom[i] = __ldg(a.aux + i);
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long warp = ((unsigned long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * kThreads) >> 5;
+    const uint8_t *pk = reinterpret_cast<const uint8_t *>(a.packed);
+    unsigned cnt = 0, nver = 0;
+
+    for (unsigned long long g = warp; g < a.ngroups; g += nwarps) {
+        const uint8_t *p = pk + g * (U * 1024ull) + lane * 32;
+        V8 v[U];
+#pragma unroll
+        for (int c = 0; c < U; c++) v[c] = ldg_stream256(p + c * 1024);
+#pragma unroll
+        for (int c = 0; c < U; c++) {
+            const unsigned long long q0 = (g * (U * 1024ull) + c * 1024 + lane * 32) >> 2;  // word index of w[0]
+#pragma unroll
+            for (int k = 0; k < 8; k += K) {  // q0 is a multiple of 8: word q0+k has index = k (mod K)
+                const uint32_t w = v[c].w[k];
+                const uint32_t s1 = bloom_slot(w), s2 = bloom_slot2(w);
+                const bool hit =
+                    ((bloom[s1 >> 5] >> (s1 & 31)) & (bloom[s2 >> 5] >> (s2 & 31)) & 1u) && q0 + k < a.nsamples;
+                if (__any_sync(kFull, hit)) {
+                    const uint2 r = skip_candidates(a, w, (long long)((q0 + k) * 16ull), hit, lane);
+                    cnt += r.x;
+                    nver += r.y;
+                }
+            }
+        }
+    }
+    block_reduce_count(a, cnt, nver);
+}
 
 /* ===================================================================== scan_multi<B> */
 

@@ -195,7 +195,7 @@ def test_low_entropy_windows(oracle):
         for m in (5, 6, 7, 8, 9, 11, 12, 13, 15, 16, 17, 19, 23, 30, 31):
             x = y[1_000_000 : 1_000_000 + m].copy()
             want = oracle.bf_positions(x, y)
-            r = sb.search("bf", t, x)
+            r = sb.search("bf", t, x, flags=sb.FLAG_NO_PACK)  # the byte kernels (the 2-bit copy takes m >= 31)
             kinds[m] = sb.last_timing().filter_kind
             assert r.count == want.size, m
             r = sb.search("kmp", t, x, flags=sb.FLAG_POSITIONS, positions_cap=y.size)
@@ -216,7 +216,8 @@ def test_skip_kernel_is_selected_and_exact(oracle):
                 x = y[3_000_000 - m : 3_000_000].copy()
                 want = oracle.bf_positions(x, y)
                 for a in ("hor", "bm", "qs", "hash3", "qf23", "tunedbm", "raita"):
-                    r = sb.search(a, t, x, flags=sb.FLAG_POSITIONS, positions_cap=1 << 20)
+                    # NO_PACK: this test is about the byte-sampling kernel (sigma <= 4 texts also have a 2-bit copy)
+                    r = sb.search(a, t, x, flags=sb.FLAG_POSITIONS | sb.FLAG_NO_PACK, positions_cap=1 << 20)
                     k = sb.last_timing().filter_kind
                     G = {256: 8, 4: 16, 2: 32}[sigma]
                     stride = (m - (G - 1)) // 32 * 32
@@ -225,7 +226,7 @@ def test_skip_kernel_is_selected_and_exact(oracle):
                     else:
                         assert k == 100 + G, (sigma, m, a, k)
                     assert r.count == want.size and np.array_equal(r.positions, want), (sigma, m, a)
-                assert sb.search("bf", t, x).count == want.size  # prefix family never skips
+                assert sb.search("bf", t, x, flags=sb.FLAG_NO_PACK).count == want.size  # prefix family never skips
                 assert sb.last_timing().filter_kind < 100
     # periodic pattern: few distinct grams -> stays on the read-every-byte kernels; still exact
     y = np.frombuffer(b"ab" * 40000, dtype=np.uint8)
@@ -440,3 +441,60 @@ def test_host_buffer_entries_follow_sb_set_device(oracle):
         assert sb.search_host("kmp", x, y).count == want
         assert sb.plugin_search("hor", x, y) == want
     sb.set_device(0)
+
+
+def test_packed_scan_of_small_alphabet_texts(oracle):
+    """Texts over <= 4 byte values keep a 2-bit recoding; patterns of m >= 31 are scanned there (filter kinds
+    301/302/304/308 = every 1st/2nd/4th/8th packed word), counts and positions still come from the byte text."""
+    rng = np.random.default_rng(12)
+    n = 3 * (1 << 20) + 4099
+    dna = np.frombuffer(b"acgt", dtype=np.uint8)[rng.integers(0, 4, n)].copy()
+    texts = {"gen4": sb.textgen_host(0, n, 4, 5), "gen2": sb.textgen_host(0, n, 2, 6), "dna": dna}
+    for name, y in texts.items():
+        with sb.Text.upload(y) as t, sb.Text.upload(y, devices=[0, 0, 0]) as t3:
+            assert t.packed_bits == 2 and t3.packed_bits == 2, name
+            for m in (31, 32, 46, 47, 63, 78, 79, 100, 142, 143, 200, 447, 448, 1000, 4200):
+                for k in (0, n // 2 + 3, n - m):
+                    x = y[k:k + m].copy()
+                    want = oracle.bf_positions(x, y)
+                    for algo in ("bf", "hor"):
+                        r = sb.search(algo, t, x)
+                        kind = sb.last_timing().filter_kind
+                        assert r.count == want.size, (name, m, k, algo, kind)
+                        if algo == "bf" or m < 448:
+                            K = 8 if m >= 143 else 4 if m >= 79 else 2 if m >= 47 else 1
+                            assert kind == 300 + K, (name, m, algo, kind)
+                        else:
+                            assert 100 < kind < 200, (name, m, algo, kind)  # the byte-sampling kernel wins from here on
+                    assert sb.search("kmp", t3, x).count == want.size
+                    assert sb.search("bf", t, x, flags=sb.FLAG_NO_PACK).count == want.size
+                    assert sb.last_timing().filter_kind < 100
+                    r = sb.search("so", t3, x, flags=sb.FLAG_POSITIONS, positions_cap=want.size + 2)
+                    assert np.array_equal(r.positions, want), (name, m, k)
+                # absent pattern: last character changed to another symbol of the alphabet
+                x = y[100:100 + m].copy()
+                x[-1] = y[y != x[-1]][0]
+                assert sb.search("bf", t, x).count == oracle.bf_count(x, y)
+                # a byte the text does not contain: nothing is scanned
+                x[m // 2] = 200
+                assert sb.search("kmp", t, x).count == 0 and sb.last_timing().filter_kind == 300
+                assert sb.last_timing().kernels_launched == 0
+    # periodic text and pattern: few distinct words -> the byte kernels keep it (candidates spread over all warps)
+    y = np.frombuffer(b"ab" * 100000, dtype=np.uint8).copy()
+    with sb.Text.upload(y) as t:
+        assert t.packed_bits == 2
+        x = y[:64].copy()
+        assert sb.search("bf", t, x).count == oracle.bf_count(x, y) and sb.last_timing().filter_kind < 100
+    # a fifth byte value anywhere drops the packed copy; so does an alphabet of more than 4
+    y = texts["gen4"].copy()
+    y[-1] = 77
+    with sb.Text.upload(y) as t:
+        assert t.packed_bits == 0
+        assert sb.search("bf", t, y[5000:5040]).count == oracle.bf_count(y[5000:5040], y)
+    with sb.Text.generate(1 << 20, 8, 3) as t:
+        assert t.packed_bits == 0
+    with sb.Text.generate(1 << 22, 4, 3) as t, sb.Text.generate(1 << 22, 4, 3, devices=[0, 0]) as t2:  # generated in place
+        assert t.packed_bits == 2 and t2.packed_bits == 2
+        x = sb.textgen_host(12345, 90, 4, 3)
+        want = sb.search("bf", t, x, flags=sb.FLAG_NO_PACK).count
+        assert want >= 1 and sb.search("bf", t, x).count == want and sb.search("hor", t2, x).count == want
