@@ -772,7 +772,7 @@ __global__ void __launch_bounds__(kThreads) scan_skip_kernel(const __grid_consta
  *   every occurrence of length m >= 16K+15 contains the 16 characters of some word whose index is a multiple of K;
  *   that word equals one of the 16K words packed from x[anchor+d .. anchor+d+16), d < 16K.
  * So the kernel streams the packed buffer (256-bit loads, as scan_block), looks every K-th word up in the Bloom
- * bitmap of those 16K words (shared memory, 2 probes) and sends the rare hits through the exact table and the
+ * bitmap of those 16K words (shared memory, 1 probe) and sends the rare hits through the exact table and the
  * byte-wise verification of scan_skip (skip_candidates: positions and counts come from the ORIGINAL text).
  * Text rate = 4 x the packed-byte rate: above the read-once HBM roofline of the byte text, like scan_skip. */
 struct PackLut {
@@ -840,10 +840,11 @@ __global__ void __launch_bounds__(kThreads) scan_packed_kernel(const __grid_cons
             const unsigned long long q0 = (g * (U * 1024ull) + c * 1024 + lane * 32) >> 2;  // word index of w[0]
 #pragma unroll
             for (int k = 0; k < 8; k += K) {  // q0 is a multiple of 8: word q0+k has index = k (mod K)
+                // ONE probe: at most 128 words in 2^18 bits give < 5e-4 false hits per word, and the exact table
+                // behind skip_candidates settles them; the second probe cost more than it saved
                 const uint32_t w = v[c].w[k];
-                const uint32_t s1 = bloom_slot(w), s2 = bloom_slot2(w);
-                const bool hit =
-                    ((bloom[s1 >> 5] >> (s1 & 31)) & (bloom[s2 >> 5] >> (s2 & 31)) & 1u) && q0 + k < a.nsamples;
+                const uint32_t s1 = bloom_slot(w);
+                const bool hit = ((bloom[s1 >> 5] >> (s1 & 31)) & 1u) && q0 + k < a.nsamples;
                 if (__any_sync(kFull, hit)) {
                     const uint2 r = skip_candidates(a, w, (long long)((q0 + k) * 16ull), hit, lane);
                     cnt += r.x;
