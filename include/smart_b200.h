@@ -148,7 +148,7 @@ typedef struct sb_timing {
                               408/416/816 = scan_block<B,L> (overlapping windows),
                               24..28 = scan_block<2,L> (L = 4..8 bytes at every even position),
                               301/302/304/308 = scan_packed<K> on the 2-bit recoding (300: pattern has a byte
-                              the text does not contain, nothing scanned),
+                              the text does not contain, nothing scanned), 311/312 = scan_packed_half<KH>,
                               108/116/132 = scan_skip<G>, 204/208/216 = scan_multi<B>, -1 = per-pattern fallback */
     unsigned long long verified; /* candidates sent to exact verification (all shards) */
 } sb_timing;

@@ -81,6 +81,7 @@ struct DevCtx {                               // per-device scratch, created on 
     void *d_sort_temp = nullptr;              // cub::DeviceRadixSort scratch
     size_t sort_temp_bytes = 0;
     int occ_packed[4] = {0};                  // ... for scan_packed<K>, K = 1, 2, 4, 8
+    int occ_packed_half[2] = {0};             // ... for scan_packed_half<KH>, KH = 1, 2
     int occ_pair[5] = {0};                    // ... for scan_block<2,L>, index L-4
     int occ_block[7] = {0};                   // resident CTAs/SM for scan_block<B,L>, index block_index()
     int occ_window[24] = {0};                 // ... for scan_window<NW,OFF,DENSE>, index window_index()
@@ -165,6 +166,8 @@ DevCtx *get_ctx(int dev)
     c.occ_packed[1] = occupancy(sb::scan_packed_kernel<2>);
     c.occ_packed[2] = occupancy(sb::scan_packed_kernel<4>);
     c.occ_packed[3] = occupancy(sb::scan_packed_kernel<8>);
+    c.occ_packed_half[0] = occupancy(sb::scan_packed_half_kernel<1>);
+    c.occ_packed_half[1] = occupancy(sb::scan_packed_half_kernel<2>);
     c.occ_pair[0] = occupancy(sb::scan_block_kernel<2, 4, kU>);
     c.occ_pair[1] = occupancy(sb::scan_block_kernel<2, 5, kU>);
     c.occ_pair[2] = occupancy(sb::scan_block_kernel<2, 6, kU>);
@@ -355,6 +358,7 @@ struct Plan {
     int skip_grams;     // scan_skip: entries of the fingerprint list (= stride), 0 otherwise
     uint32_t list[4224]; // scan_skip: fingerprints of the pattern grams
     bool sparse;        // scan_swar: a match of the whole pattern is rare in this text
+    int packed_half;    // scan_packed_half: sampling period in half-words (1, 2), 0 = word variants
     int packed_K;       // scan_packed: sampling period in words; 0 with filter == kFilterPacked: pattern outside the alphabet
     sb::ScanArgs args;  // text/base/hi/ngroups/counters/pos filled per shard
 };
@@ -367,6 +371,7 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
     pl.sparse = m * bits >= dense_bits() && !(flags & SB_FLAG_DENSE);  // scan_swar; scan_window decides below
     pl.skip_grams = 0;
     pl.packed_K = 0;
+    pl.packed_half = 0;
     sb::ScanArgs &a = pl.args;
     a.m = m;
     a.nwords = (m + 3) / 4;
@@ -412,13 +417,17 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
             return;
         }
     }
-    /* Texts over <= 4 byte values: scan the 2-bit recoding (a quarter of the bytes).  Every K-th packed word is
-     * looked up among the 16K words packed from x[anchor+d ..], d < 16K; needs m >= 16K+15. */
-    if (pk && pk->packed && m >= 31 && !(flags & (forced | SB_FLAG_NO_PACK | SB_FLAG_DENSE))) {
-        int K = 8;
-        while (16 * K + 15 > m) K >>= 1;
-        const int span = 16 * K;
-        const int anchor = desc->anchor == SB_ANCHOR_SUFFIX ? m - (span + 15) : 0;
+    /* Texts over <= 4 byte values: scan the 2-bit recoding (a quarter of the bytes).  Every K-th fingerprint (a
+     * packed word or half-word) is looked up among those packed from x[anchor+d ..], d < span.
+     * m >= 31: whole words (16 characters), every K-th one, K = 1, 2, 4, 8 with m >= 16K+15;
+     * 15 <= m < 31: half-words (8 characters, only if 8 characters carry >= 14 bits), both halves or the low one. */
+    const bool half_ok = m >= 15 && m < 31 && 8.0 * bits >= 14.0;
+    if (pk && pk->packed && (m >= 31 || half_ok) && !(flags & (forced | SB_FLAG_NO_PACK | SB_FLAG_DENSE))) {
+        const int gram = m >= 31 ? 16 : 8;  // characters per fingerprint
+        int K = m >= 31 ? 8 : 2;            // sampling period in fingerprints
+        while (gram * K + gram - 1 > m) K >>= 1;
+        const int span = gram * K;
+        const int anchor = desc->anchor == SB_ANCHOR_SUFFIX ? m - (span + gram - 1) : 0;
         unsigned char code[256];
         memset(code, 0xff, sizeof code);
         for (int c = pk->nsym - 1; c >= 0; c--) code[pk->sym[c]] = (unsigned char)c;
@@ -431,7 +440,7 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
         }
         for (int d = 0; d < span; d++) {
             uint32_t w = 0;
-            for (int k = 0; k < 16; k++) w |= (uint32_t)code[x[anchor + d + k]] << (2 * k);
+            for (int k = 0; k < gram; k++) w |= (uint32_t)code[x[anchor + d + k]] << (2 * k);
             pl.list[d] = w;
         }
         uint32_t sorted[160];
@@ -443,8 +452,9 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
             worst = std::max(worst, run);
         }
         if (worst <= 8) {  // periodic patterns stay on the byte kernels (same reason as for scan_skip above)
-            pl.filter = kFilterPacked + K;
+            pl.filter = kFilterPacked + (gram == 16 ? K : 10 + K);
             pl.packed_K = K;
+            pl.packed_half = gram == 8 ? K : 0;
             pl.skip_grams = span;
             a.stride = span;
             a.anchor = anchor;
@@ -493,12 +503,21 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
     if (pl.filter >= kFilterPacked) {
         if (!pl.packed_K) return cudaSuccess;  // pattern outside the text's alphabet: the count stays 0
         a.aux = c.d_aux;
-        const unsigned long long end = (unsigned long long)a.hi + a.anchor + a.stride + 15;  // characters that matter
+        const unsigned long long end = (unsigned long long)a.hi + a.anchor + a.stride + 15;  // characters that matter (upper bound)
         a.nsamples = (end + 15) / 16;                                                         // packed words
         a.ngroups = (a.nsamples * 4 + kGroupLong - 1) / kGroupLong;
         const int ki = pl.packed_K == 1 ? 0 : pl.packed_K == 2 ? 1 : pl.packed_K == 4 ? 2 : 3;
         const unsigned long long want_ctas = (a.ngroups + (sb::kThreads / 32) - 1) / (sb::kThreads / 32);
-        const unsigned g = (unsigned)std::max(1ull, std::min(want_ctas, (unsigned long long)c.sms * c.occ_packed[ki]));
+        const int occ = pl.packed_half ? c.occ_packed_half[pl.packed_half - 1] : c.occ_packed[ki];
+        const unsigned g = (unsigned)std::max(1ull, std::min(want_ctas, (unsigned long long)c.sms * occ));
+        if (pl.packed_half == 1) {
+            sb::scan_packed_half_kernel<1><<<g, sb::kThreads, 0, stream>>>(a);
+            return cudaGetLastError();
+        }
+        if (pl.packed_half == 2) {
+            sb::scan_packed_half_kernel<2><<<g, sb::kThreads, 0, stream>>>(a);
+            return cudaGetLastError();
+        }
         switch (pl.packed_K) {
         case 1: sb::scan_packed_kernel<1><<<g, sb::kThreads, 0, stream>>>(a); break;
         case 2: sb::scan_packed_kernel<2><<<g, sb::kThreads, 0, stream>>>(a); break;
@@ -621,9 +640,13 @@ size_t stage_aux(DevCtx &c, const Plan &pl)
     memset(c.h_aux, 0, kAuxWords * sizeof(uint32_t));
     uint32_t *table = c.h_aux + sb::kBloomWords;
     for (int d = 0; d < pl.skip_grams; d++) {
-        const uint32_t s1 = sb::bloom_slot(pl.list[d]), s2 = sb::bloom_slot2(pl.list[d]);
-        c.h_aux[s1 >> 5] |= 1u << (s1 & 31);
-        c.h_aux[s2 >> 5] |= 1u << (s2 & 31);
+        if (pl.packed_half) {  // 16-bit fingerprints index the bitmap directly (scan_packed_half)
+            c.h_aux[pl.list[d] >> 5] |= 1u << (pl.list[d] & 31);
+        } else {
+            const uint32_t s1 = sb::bloom_slot(pl.list[d]), s2 = sb::bloom_slot2(pl.list[d]);
+            c.h_aux[s1 >> 5] |= 1u << (s1 & 31);
+            c.h_aux[s2 >> 5] |= 1u << (s2 & 31);
+        }
         uint32_t slot = sb::table_slot(pl.list[d]);
         while (table[2 * slot + 1]) slot = (slot + 1) & (sb::kSkipTableSize - 1);  // linear probing
         table[2 * slot] = pl.list[d];

@@ -856,6 +856,51 @@ __global__ void __launch_bounds__(kThreads) scan_packed_kernel(const __grid_cons
     block_reduce_count(a, cnt, nver);
 }
 
+/* Shorter patterns on the 2-bit recoding (15 <= m < 31): a 16-bit half-word is an exact 8-character
+ * fingerprint and indexes a 65536-bit bitmap DIRECTLY (8 KiB of shared memory, no hashing).  KH = 1: both halves
+ * of every word (m >= 15, 8 pattern alignments); KH = 2: the low half only (m >= 23, 16 alignments). */
+constexpr int kHalfMapWords = 65536 / 32;
+
+template <int KH>
+__global__ void __launch_bounds__(kThreads) scan_packed_half_kernel(const __grid_constant__ ScanArgs a)
+{
+    constexpr int U = 4;
+    __shared__ uint32_t bitmap[kHalfMapWords];
+    for (int i = threadIdx.x; i < kHalfMapWords; i += kThreads) bitmap[i] = __ldg(a.aux + i);
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long warp = ((unsigned long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * kThreads) >> 5;
+    const uint8_t *pk = reinterpret_cast<const uint8_t *>(a.packed);
+    unsigned cnt = 0, nver = 0;
+
+    for (unsigned long long g = warp; g < a.ngroups; g += nwarps) {
+        const uint8_t *p = pk + g * (U * 1024ull) + lane * 32;
+        V8 v[U];
+#pragma unroll
+        for (int c = 0; c < U; c++) v[c] = ldg_stream256(p + c * 1024);
+#pragma unroll
+        for (int c = 0; c < U; c++) {
+            const unsigned long long q0 = (g * (U * 1024ull) + c * 1024 + lane * 32) >> 2;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t w = v[c].w[k];
+#pragma unroll
+                for (int half = 0; half < (KH == 1 ? 2 : 1); half++) {
+                    const uint32_t h = half ? (w >> 16) : (w & 0xffffu);
+                    const bool hit = ((bitmap[h >> 5] >> (h & 31)) & 1u) && q0 + k < a.nsamples;
+                    if (__any_sync(kFull, hit)) {
+                        const uint2 r = skip_candidates(a, h, (long long)((q0 + k) * 16ull + half * 8), hit, lane);
+                        cnt += r.x;
+                        nver += r.y;
+                    }
+                }
+            }
+        }
+    }
+    block_reduce_count(a, cnt, nver);
+}
+
 /* ===================================================================== scan_multi<B> */
 
 /* Multi-pattern scan: ALL `npat` patterns of one length are counted in ONE pass over

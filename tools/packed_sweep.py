@@ -16,7 +16,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gib", type=float, default=4.0)
     ap.add_argument("--sigma", type=int, default=4)
-    ap.add_argument("--ms", default="31,40,47,64,79,100,128,143,160,200,256,400,512,1024")
+    ap.add_argument("--ms", default="15,16,20,23,24,30,31,40,47,64,79,100,128,143,160,200,256,400,512,1024")
     ap.add_argument("--reps", type=int, default=7)
     ap.add_argument("--out", default="gpurun_out/packed_sweep.jsonl")
     a = ap.parse_args()
