@@ -276,7 +276,7 @@ class Text:
 
     @property
     def packed_bits(self) -> int:
-        """2 when the text (<= 4 distinct byte values) also has a 2-bit packed copy in HBM, else 0"""
+        """bits per character of the packed copy of a text over <= 4 distinct byte values (2, or 1 for two), else 0"""
         return lib().sb_text_packed_bits(self._h)
 
     def download(self, off: int, length: int) -> np.ndarray:

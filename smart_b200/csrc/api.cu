@@ -348,6 +348,7 @@ bool use_tma()
 /* what make_plan needs to know about a resident text's 2-bit recoding */
 struct PackInfo {
     bool packed = false;
+    int bits = 0;   // bits per character of the recoding: 1 (two symbols) or 2
     int nsym = 0;
     unsigned char sym[4] = {0, 0, 0, 0};  // byte value of code c
 };
@@ -419,12 +420,14 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
     }
     /* Texts over <= 4 byte values: scan the 2-bit recoding (a quarter of the bytes).  Every K-th fingerprint (a
      * packed word or half-word) is looked up among those packed from x[anchor+d ..], d < span.
-     * m >= 31: whole words (16 characters), every K-th one, K = 1, 2, 4, 8 with m >= 16K+15;
-     * 15 <= m < 31: half-words (8 characters, only if 8 characters carry >= 14 bits), both halves or the low one. */
-    const bool half_ok = m >= 15 && m < 31 && 8.0 * bits >= 14.0;
-    if (pk && pk->packed && (m >= 31 || half_ok) && !(flags & (forced | SB_FLAG_NO_PACK | SB_FLAG_DENSE))) {
-        const int gram = m >= 31 ? 16 : 8;  // characters per fingerprint
-        int K = m >= 31 ? 8 : 2;            // sampling period in fingerprints
+     * CPW = 16 characters per word (32 for two-symbol texts, 1 bit each).  m >= 2*CPW-1: whole words, every K-th
+     * one, K = 1, 2, 4, 8 with m >= CPW*(K+1)-1; CPW-1 <= m < 2*CPW-1: half-words (only if CPW/2 characters carry
+     * >= 14 bits), both halves or the low one. */
+    const int cpw = pk && pk->packed ? 32 / pk->bits : 16;  // characters per packed word
+    const bool half_ok = m >= cpw - 1 && m < 2 * cpw - 1 && (cpw / 2) * bits >= 14.0;
+    if (pk && pk->packed && (m >= 2 * cpw - 1 || half_ok) && !(flags & (forced | SB_FLAG_NO_PACK | SB_FLAG_DENSE))) {
+        const int gram = m >= 2 * cpw - 1 ? cpw : cpw / 2;  // characters per fingerprint
+        int K = gram == cpw ? 8 : 2;                        // sampling period in fingerprints
         while (gram * K + gram - 1 > m) K >>= 1;
         const int span = gram * K;
         const int anchor = desc->anchor == SB_ANCHOR_SUFFIX ? m - (span + gram - 1) : 0;
@@ -440,10 +443,10 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
         }
         for (int d = 0; d < span; d++) {
             uint32_t w = 0;
-            for (int k = 0; k < gram; k++) w |= (uint32_t)code[x[anchor + d + k]] << (2 * k);
+            for (int k = 0; k < gram; k++) w |= (uint32_t)code[x[anchor + d + k]] << (pk->bits * k);
             pl.list[d] = w;
         }
-        uint32_t sorted[160];
+        uint32_t sorted[288];
         memcpy(sorted, pl.list, (size_t)span * sizeof(uint32_t));
         std::sort(sorted, sorted + span);
         int run = 1, worst = 1;
@@ -452,9 +455,10 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
             worst = std::max(worst, run);
         }
         if (worst <= 8) {  // periodic patterns stay on the byte kernels (same reason as for scan_skip above)
-            pl.filter = kFilterPacked + (gram == 16 ? K : 10 + K);
+            pl.filter = kFilterPacked + (gram == cpw ? K : 10 + K);
             pl.packed_K = K;
-            pl.packed_half = gram == 8 ? K : 0;
+            pl.packed_half = gram == cpw ? 0 : K;
+            a.cpw = cpw;
             pl.skip_grams = span;
             a.stride = span;
             a.anchor = anchor;
@@ -503,8 +507,8 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
     if (pl.filter >= kFilterPacked) {
         if (!pl.packed_K) return cudaSuccess;  // pattern outside the text's alphabet: the count stays 0
         a.aux = c.d_aux;
-        const unsigned long long end = (unsigned long long)a.hi + a.anchor + a.stride + 15;  // characters that matter (upper bound)
-        a.nsamples = (end + 15) / 16;                                                         // packed words
+        const unsigned long long end = (unsigned long long)a.hi + a.anchor + a.stride + 31;  // characters that matter (upper bound)
+        a.nsamples = (end + a.cpw - 1) / a.cpw;                                               // packed words
         a.ngroups = (a.nsamples * 4 + kGroupLong - 1) / kGroupLong;
         const int ki = pl.packed_K == 1 ? 0 : pl.packed_K == 2 ? 1 : pl.packed_K == 4 ? 2 : 3;
         const unsigned long long want_ctas = (a.ngroups + (sb::kThreads / 32) - 1) / (sb::kThreads / 32);
@@ -803,10 +807,10 @@ static sb_text *text_alloc(size_t n, const int *devices, int nparts, int first, 
 }
 
 /* sampled byte histogram of every shard -> t->bits (min over shards) */
-/* Texts over at most four byte values also get a 2-bit recoding for scan_packed (a quarter of the bytes to
- * stream).  The alphabet is guessed from the histogram samples and VERIFIED by the packing pass over every byte;
+/* Texts over at most four byte values also get a 2-bit recoding (1 bit for two symbols) for scan_packed (a
+ * quarter / an eighth of the bytes to stream).  The alphabet is guessed from the histogram samples and VERIFIED by the packing pass over every byte;
  * a text that turns out to hold a fifth value simply has no packed copy.  SMART_B200_NO_PACK=1 disables it.
- * Costs n/4 bytes of HBM and one extra pass at upload/generation time. */
+ * Costs n/4 (n/8) bytes of HBM and one extra pass at upload/generation time. */
 static bool text_try_pack(sb_text *t)
 {
     static const bool off = getenv("SMART_B200_NO_PACK") && atoi(getenv("SMART_B200_NO_PACK")) > 0;
@@ -818,6 +822,7 @@ static bool text_try_pack(sb_text *t)
             nsym++;
         }
     if (off || nsym < 1 || nsym > 4 || t->n < (1u << 16)) return true;
+    const int bits = nsym <= 2 ? 1 : 2;
     sb::PackLut lut;
     for (int c = 0; c < 4; c++) lut.sym[c] = c < nsym ? sym[c] : 0xffffffffu;  // unused codes match no byte
     bool ok = true;
@@ -826,7 +831,7 @@ static bool text_try_pack(sb_text *t)
         DevCtx *c = get_ctx(s.dev);
         if (!c) return false;
         cudaSetDevice(s.dev);
-        s.packed_bytes = round_up((s.cap + 3) / 4, sb::kPadBytes) + sb::kPadBytes;
+        s.packed_bytes = round_up((s.cap * bits + 7) / 8, sb::kPadBytes) + sb::kPadBytes;
         if (cudaMalloc(&s.d_packed, s.packed_bytes) != cudaSuccess) {
             cudaGetLastError();  // not fatal: the byte kernels need no packed copy
             s.d_packed = nullptr;
@@ -835,8 +840,12 @@ static bool text_try_pack(sb_text *t)
         }
         unsigned bad = 0;
         if (cudaMemsetAsync(c->d_hist, 0, sizeof(unsigned), c->stream) != cudaSuccess) return false;
-        sb::pack2_kernel<<<c->sms * 8, 256, 0, c->stream>>>(s.d_text, s.len, s.cap, s.packed_bytes / 4, s.d_packed, lut,
-                                                          reinterpret_cast<unsigned *>(c->d_hist));
+        if (bits == 1)
+            sb::pack_kernel<1><<<c->sms * 8, 256, 0, c->stream>>>(s.d_text, s.len, s.cap, s.packed_bytes / 4, s.d_packed,
+                                                                 lut, reinterpret_cast<unsigned *>(c->d_hist));
+        else
+            sb::pack_kernel<2><<<c->sms * 8, 256, 0, c->stream>>>(s.d_text, s.len, s.cap, s.packed_bytes / 4, s.d_packed,
+                                                                 lut, reinterpret_cast<unsigned *>(c->d_hist));
         if (cudaMemcpyAsync(&bad, c->d_hist, sizeof bad, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return false;
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
         ok = bad == 0;
@@ -852,6 +861,7 @@ static bool text_try_pack(sb_text *t)
         return true;
     }
     t->pack.packed = true;
+    t->pack.bits = bits;
     t->pack.nsym = nsym;
     memcpy(t->pack.sym, sym, sizeof sym);
     return true;
@@ -991,7 +1001,7 @@ sb_text *sb_text_generate_part(size_t n_total, int sigma, uint64_t seed, int npa
 size_t sb_text_length(const sb_text *t) { return t ? t->n : 0; }
 int sb_text_shards(const sb_text *t) { return t ? t->nshards : 0; }
 double sb_text_entropy_bits(const sb_text *t) { return t ? t->bits : 0.0; }
-int sb_text_packed_bits(const sb_text *t) { return t && t->pack.packed ? 2 : 0; }
+int sb_text_packed_bits(const sb_text *t) { return t && t->pack.packed ? t->pack.bits : 0; }
 
 int sb_text_download(const sb_text *t, size_t off, size_t len, unsigned char *host)
 {

@@ -52,7 +52,8 @@ __host__ __device__ __forceinline__ uint32_t fp32(uint32_t lo16, uint32_t hi16) 
 
 struct ScanArgs {
     const uint8_t *text;          // shard buffer, 32-B aligned, zero padded (kPadBytes rule)
-    const uint32_t *packed;       // scan_packed: 2-bit recoding of the shard, 16 characters per word (or nullptr)
+    const uint32_t *packed;       // scan_packed: 2-bit (1-bit for two symbols) recoding of the shard, or nullptr
+    int cpw;                      // scan_packed: characters per packed word (16 or 32)
     const uint32_t *pat;          // pattern as little-endian words, zero padded
     unsigned long long *counters; // [0] match count, [1] position cursor, [2] verified candidates
     unsigned long long *pos;      // position sink (unsorted) or nullptr
@@ -766,9 +767,10 @@ __global__ void __launch_bounds__(kThreads) scan_skip_kernel(const __grid_consta
 
 /* ===================================================================== scan_packed<K> (alphabets of <= 4 symbols) */
 
-/* A text over at most four distinct byte values (DNA, sigma <= 4 generators) is also kept as a 2-bit recoding:
- * character i lives in word i/16, bits 2*(i%16).. (pack2_kernel, once per text).  A word is then an EXACT
- * 16-character fingerprint, and the scan reads a quarter of the bytes:
+/* A text over at most four distinct byte values (DNA, sigma <= 4 generators) is also kept as a 2-bit recoding
+ * (1 bit for two symbols): character i lives in word i/CPW at bits BITS*(i%CPW).., CPW = 32/BITS (pack_kernel,
+ * once per text).  A word is then an EXACT CPW-character fingerprint, and the scan reads 1/4 (1/8) of the bytes.
+ * Stated for CPW = 16:
  *   every occurrence of length m >= 16K+15 contains the 16 characters of some word whose index is a multiple of K;
  *   that word equals one of the 16K words packed from x[anchor+d .. anchor+d+16), d < 16K.
  * So the kernel streams the packed buffer (256-bit loads, as scan_block), looks every K-th word up in the Bloom
@@ -789,26 +791,32 @@ __device__ __forceinline__ uint32_t pack_code(uint32_t b, const PackLut &lut, bo
     return c;
 }
 
-/* out[w] packs text[16w .. 16w+16); bytes at or beyond `len` pack as code 0; *bad is set if a byte below `len`
- * is none of the four symbols (the caller then drops the packed copy) */
-__global__ void __launch_bounds__(256) pack2_kernel(const uint8_t *text, unsigned long long len, unsigned long long cap,
-                                                    unsigned long long nwords, uint32_t *out, const PackLut lut,
-                                                    unsigned *bad)
+/* out[w] packs the CPW = 32/BITS characters text[CPW*w .. CPW*(w+1)), character i at bits BITS*i..; bytes at or
+ * beyond `len` pack as code 0; *bad is set if a byte below `len` is none of the symbols (the caller then drops
+ * the packed copy).  BITS = 1 for two-symbol texts, 2 for three or four symbols. */
+template <int BITS>
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t *text, unsigned long long len, unsigned long long cap,
+                                                   unsigned long long nwords, uint32_t *out, const PackLut lut,
+                                                   unsigned *bad)
 {
+    constexpr int CPW = 32 / BITS;
     bool any_bad = false;
     for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords;
          w += (unsigned long long)gridDim.x * blockDim.x) {
         uint32_t word = 0;
-        if (16 * w + 16 <= cap) {
-            const uint4 v = ldg_stream128(text + 16 * w);
-            const uint32_t src[4] = {v.x, v.y, v.z, v.w};
+        if (CPW * w + CPW <= cap) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                bool ok;
-                const uint32_t c = pack_code((src[i >> 2] >> (8 * (i & 3))) & 0xffu, lut, ok);
-                if (16 * w + i < len) {
-                    word |= c << (2 * i);
-                    any_bad |= !ok;
+            for (int v16 = 0; v16 < CPW / 16; v16++) {
+                const uint4 v = ldg_stream128(text + CPW * w + 16 * v16);
+                const uint32_t src[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    bool ok;
+                    const uint32_t c = pack_code((src[i >> 2] >> (8 * (i & 3))) & 0xffu, lut, ok);
+                    if (CPW * w + 16 * v16 + i < len) {
+                        word |= c << (BITS * (16 * v16 + i));
+                        any_bad |= !ok;
+                    }
                 }
             }
         }
@@ -846,7 +854,7 @@ __global__ void __launch_bounds__(kThreads) scan_packed_kernel(const __grid_cons
                 const uint32_t s1 = bloom_slot(w);
                 const bool hit = ((bloom[s1 >> 5] >> (s1 & 31)) & 1u) && q0 + k < a.nsamples;
                 if (__any_sync(kFull, hit)) {
-                    const uint2 r = skip_candidates(a, w, (long long)((q0 + k) * 16ull), hit, lane);
+                    const uint2 r = skip_candidates(a, w, (long long)((q0 + k) * (unsigned long long)a.cpw), hit, lane);
                     cnt += r.x;
                     nver += r.y;
                 }
@@ -856,7 +864,7 @@ __global__ void __launch_bounds__(kThreads) scan_packed_kernel(const __grid_cons
     block_reduce_count(a, cnt, nver);
 }
 
-/* Shorter patterns on the 2-bit recoding (15 <= m < 31): a 16-bit half-word is an exact 8-character
+/* Shorter patterns on the recoding (CPW-1 <= m < 2*CPW-1): a 16-bit half-word is an exact CPW/2-character
  * fingerprint and indexes a 65536-bit bitmap DIRECTLY (8 KiB of shared memory, no hashing).  KH = 1: both halves
  * of every word (m >= 15, 8 pattern alignments); KH = 2: the low half only (m >= 23, 16 alignments). */
 constexpr int kHalfMapWords = 65536 / 32;
@@ -890,7 +898,8 @@ __global__ void __launch_bounds__(kThreads) scan_packed_half_kernel(const __grid
                     const uint32_t h = half ? (w >> 16) : (w & 0xffffu);
                     const bool hit = ((bitmap[h >> 5] >> (h & 31)) & 1u) && q0 + k < a.nsamples;
                     if (__any_sync(kFull, hit)) {
-                        const uint2 r = skip_candidates(a, h, (long long)((q0 + k) * 16ull + half * 8), hit, lane);
+                        const uint2 r = skip_candidates(
+                            a, h, (long long)((q0 + k) * (unsigned long long)a.cpw + half * (a.cpw >> 1)), hit, lane);
                         cnt += r.x;
                         nver += r.y;
                     }

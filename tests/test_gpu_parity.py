@@ -445,15 +445,18 @@ def test_host_buffer_entries_follow_sb_set_device(oracle):
 
 def test_packed_scan_of_small_alphabet_texts(oracle):
     """Texts over <= 4 byte values keep a 2-bit recoding; patterns of m >= 31 are scanned there (filter kinds
-    301/302/304/308 = every 1st/2nd/4th/8th packed word), counts and positions still come from the byte text."""
+    301/302/304/308 = every 1st/2nd/4th/8th packed word, 311/312 = half-words), two-symbol texts a 1-bit one;
+    counts and positions still come from the byte text."""
     rng = np.random.default_rng(12)
     n = 3 * (1 << 20) + 4099
     dna = np.frombuffer(b"acgt", dtype=np.uint8)[rng.integers(0, 4, n)].copy()
     texts = {"gen4": sb.textgen_host(0, n, 4, 5), "gen2": sb.textgen_host(0, n, 2, 6), "dna": dna}
     for name, y in texts.items():
         with sb.Text.upload(y) as t, sb.Text.upload(y, devices=[0, 0, 0]) as t3:
-            assert t.packed_bits == 2 and t3.packed_bits == 2, name
-            for m in (15, 16, 22, 23, 30, 31, 32, 46, 47, 63, 78, 79, 100, 142, 143, 200, 447, 448, 1000, 4200):
+            cpw = 32 if name == "gen2" else 16  # characters per packed word: two symbols take 1 bit each
+            assert t.packed_bits == 32 // cpw and t3.packed_bits == 32 // cpw, name
+            for m in (15, 16, 22, 23, 30, 31, 32, 46, 47, 62, 63, 78, 79, 94, 95, 100, 142, 143, 158, 159, 200, 286, 287,
+                      447, 448, 1000, 4200):
                 for k in (0, n // 2 + 3, n - m):
                     x = y[k:k + m].copy()
                     want = oracle.bf_positions(x, y)
@@ -461,13 +464,12 @@ def test_packed_scan_of_small_alphabet_texts(oracle):
                         r = sb.search(algo, t, x)
                         kind = sb.last_timing().filter_kind
                         assert r.count == want.size, (name, m, k, algo, kind)
-                        if m < 31:  # half-words: 8 characters must carry >= 14 bits (not on the 2-symbol text)
-                            if name == "gen2":
-                                assert kind < 100 or kind in (408, 416, 816), (name, m, algo, kind)
-                            else:
-                                assert kind == (311 if m < 23 else 312), (name, m, algo, kind)
+                        if m < cpw - 1:  # too short for a half-word fingerprint
+                            assert kind < 100 or kind in (408, 416, 816), (name, m, algo, kind)
+                        elif m < 2 * cpw - 1:  # half-words, both halves or the low one
+                            assert kind == (311 if m < cpw + cpw // 2 - 1 else 312), (name, m, algo, kind)
                         elif algo == "bf" or m < 448:
-                            K = 8 if m >= 143 else 4 if m >= 79 else 2 if m >= 47 else 1
+                            K = max(k2 for k2 in (1, 2, 4, 8) if cpw * (k2 + 1) - 1 <= m)
                             assert kind == 300 + K, (name, m, algo, kind)
                         else:
                             assert 100 < kind < 200, (name, m, algo, kind)  # the byte-sampling kernel wins from here on
@@ -483,12 +485,12 @@ def test_packed_scan_of_small_alphabet_texts(oracle):
                 # a byte the text does not contain: nothing is scanned
                 x[m // 2] = 200
                 assert sb.search("kmp", t, x).count == 0
-                if m >= 31 or name != "gen2":
+                if m >= cpw - 1:
                     assert sb.last_timing().filter_kind == 300 and sb.last_timing().kernels_launched == 0
     # periodic text and pattern: few distinct words -> the byte kernels keep it (candidates spread over all warps)
     y = np.frombuffer(b"ab" * 100000, dtype=np.uint8).copy()
     with sb.Text.upload(y) as t:
-        assert t.packed_bits == 2
+        assert t.packed_bits == 1
         x = y[:64].copy()
         assert sb.search("bf", t, x).count == oracle.bf_count(x, y) and sb.last_timing().filter_kind < 100
     # a fifth byte value anywhere drops the packed copy; so does an alphabet of more than 4

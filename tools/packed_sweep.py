@@ -23,7 +23,7 @@ def main():
     n = int(a.gib * (1 << 30))
     out = open(a.out, "w")
     with sb.Text.generate(n, a.sigma, 1000 + a.sigma) as t:
-        assert t.packed_bits == 2
+        assert t.packed_bits in (1, 2)
         for m in [int(v) for v in a.ms.split(",")]:
             x = sb.textgen_host(n // 3 + 17, m, a.sigma, 1000 + a.sigma)
             for algo in ("bf", "hor"):
