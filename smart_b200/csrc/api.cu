@@ -58,8 +58,9 @@ constexpr int kU = SB_U;                      // 256-bit loads in flight per thr
 constexpr size_t kGroupLong = kU * 1024;      // bytes per warp iteration of those kernels
 constexpr int kFilterShort = 0, kFilterWindow8 = 1, kFilterWindow16 = 3;  // 2 = the 12-byte window
 constexpr int kFilterPair = 20;               // scan_block<2,L>: windows at even positions, L = 4..8 in Plan::flen
-/* scan_packed<8> moves 4 x 7.2 = 29 T characters/s; scan_skip passes that from a stride of ~400 bytes on */
-constexpr int kPackedBeatsSkipBelow = 448;
+/* scan_packed<8> moves ~26 T characters/s on a 2-bit copy and ~49 T on a 1-bit one; scan_skip passes that from
+ * m ~ 450 resp. ~1200 on (measured, profiles/packed_sweep_r1_*.jsonl) */
+constexpr int kPackedBeatsSkipBelow2 = 448, kPackedBeatsSkipBelow1 = 1200;
 constexpr int kFilterPacked = 300;             // + K (301, 302, 304, 308): scan_packed<K> on the 2-bit recoding
 constexpr int kFilterSkip = 100;              // + gram bytes (108, 116, 132): scan_skip<G>
 constexpr size_t kAuxWords = sb::kBloomWords + 2 * sb::kSkipTableSize;
@@ -390,7 +391,7 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
                             SB_FLAG_FILTER_B32 | SB_FLAG_FILTER_B4L8 | SB_FLAG_FILTER_B4L16 | SB_FLAG_FILTER_B8L16 |
                             SB_FLAG_FILTER_B2 | SB_FLAG_NO_SKIP;
     const bool can_pack = pk && pk->packed && !(flags & (SB_FLAG_NO_PACK | SB_FLAG_DENSE));
-    if (desc->anchor == SB_ANCHOR_SUFFIX && !(flags & forced) && !(can_pack && m < kPackedBeatsSkipBelow)) {
+    if (desc->anchor == SB_ANCHOR_SUFFIX && !(flags & forced) && !(can_pack && m < (pk->bits == 1 ? kPackedBeatsSkipBelow1 : kPackedBeatsSkipBelow2))) {
         for (int G = 8; G <= 32; G *= 2) {
             const int stride = ((m - (G - 1)) / 32) * 32;
             if (stride < skip_min_stride()) break;

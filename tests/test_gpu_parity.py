@@ -468,7 +468,7 @@ def test_packed_scan_of_small_alphabet_texts(oracle):
                             assert kind < 100 or kind in (408, 416, 816), (name, m, algo, kind)
                         elif m < 2 * cpw - 1:  # half-words, both halves or the low one
                             assert kind == (311 if m < cpw + cpw // 2 - 1 else 312), (name, m, algo, kind)
-                        elif algo == "bf" or m < 448:
+                        elif algo == "bf" or m < (1200 if cpw == 32 else 448):
                             K = max(k2 for k2 in (1, 2, 4, 8) if cpw * (k2 + 1) - 1 <= m)
                             assert kind == 300 + K, (name, m, algo, kind)
                         else:
