@@ -63,7 +63,7 @@ extern "C" {
 #define SB_FLAG_FILTER_B4L16 0x400u  /* 4-byte alignment, 16-byte fingerprint (m >= 19) */
 #define SB_FLAG_FILTER_B8L16 0x800u  /* 8-byte alignment, 16-byte fingerprint (m >= 23) */
 #define SB_FLAG_FILTER_B2 0x1000u    /* windows of min(8, m-1) bytes at every even position (m >= 5) */
-#define SB_FLAG_NO_PACK 0x2000u      /* do not use the 2-bit / 1-bit recoding of a text over <= 4 byte values */
+#define SB_FLAG_NO_PACK 0x2000u      /* do not use the packed recoding of a text over <= 16 byte values */
 
 /* ---- algorithm registry (names are the lower-cased SMART registry names, smart.c:142) ---- */
 int sb_algo_count(void);
@@ -105,8 +105,8 @@ size_t sb_text_length(const sb_text *t);
  * histogram taken when the text was created; log2(sigma) for uniform texts); drives the choice of candidate
  * filter (a B-byte fingerprint passes ~2^-(B*bits) of positions) */
 double sb_text_entropy_bits(const sb_text *t);
-/* bits per character of the packed copy kept next to a text over <= 4 distinct byte values (2; 1 for two
- * values), else 0 */
+/* bits per character of the packed copy kept next to a text over <= 16 distinct byte values (4; 2 for <= 4
+ * values; 1 for two), else 0 */
 int sb_text_packed_bits(const sb_text *t);
 int sb_text_shards(const sb_text *t);
 /* copy text bytes [off, off+len) back to the host (tests, pattern extraction) */

@@ -58,9 +58,9 @@ constexpr int kU = SB_U;                      // 256-bit loads in flight per thr
 constexpr size_t kGroupLong = kU * 1024;      // bytes per warp iteration of those kernels
 constexpr int kFilterShort = 0, kFilterWindow8 = 1, kFilterWindow16 = 3;  // 2 = the 12-byte window
 constexpr int kFilterPair = 20;               // scan_block<2,L>: windows at even positions, L = 4..8 in Plan::flen
-/* scan_packed<8> moves ~26 T characters/s on a 2-bit copy and ~49 T on a 1-bit one; scan_skip passes that from
- * m ~ 450 resp. ~1200 on (measured, profiles/packed_sweep_r1_*.jsonl) */
-constexpr int kPackedBeatsSkipBelow2 = 448, kPackedBeatsSkipBelow1 = 1200;
+/* scan_packed<8> moves ~26 T characters/s on a 2-bit copy and ~49 T on a 1-bit one (~13 T on a 4-bit one);
+ * scan_skip passes that from m ~ 450 resp. ~1200 on (and beats the 4-bit copy as soon as it applies, m >= 167) (measured, profiles/packed_sweep_r1_*.jsonl) */
+constexpr int kPackedBeatsSkipBelow4 = 167, kPackedBeatsSkipBelow2 = 448, kPackedBeatsSkipBelow1 = 1200;
 constexpr int kFilterPacked = 300;             // + K (301, 302, 304, 308): scan_packed<K> on the 2-bit recoding
 constexpr int kFilterSkip = 100;              // + gram bytes (108, 116, 132): scan_skip<G>
 constexpr size_t kAuxWords = sb::kBloomWords + 2 * sb::kSkipTableSize;
@@ -349,9 +349,9 @@ bool use_tma()
 /* what make_plan needs to know about a resident text's 2-bit recoding */
 struct PackInfo {
     bool packed = false;
-    int bits = 0;   // bits per character of the recoding: 1 (two symbols) or 2
+    int bits = 0;   // bits per character of the recoding: 1 (two symbols), 2 (up to four) or 4 (up to sixteen)
     int nsym = 0;
-    unsigned char sym[4] = {0, 0, 0, 0};  // byte value of code c
+    unsigned char sym[16] = {0};  // byte value of code c
 };
 
 struct Plan {
@@ -391,7 +391,7 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
                             SB_FLAG_FILTER_B32 | SB_FLAG_FILTER_B4L8 | SB_FLAG_FILTER_B4L16 | SB_FLAG_FILTER_B8L16 |
                             SB_FLAG_FILTER_B2 | SB_FLAG_NO_SKIP;
     const bool can_pack = pk && pk->packed && !(flags & (SB_FLAG_NO_PACK | SB_FLAG_DENSE));
-    if (desc->anchor == SB_ANCHOR_SUFFIX && !(flags & forced) && !(can_pack && m < (pk->bits == 1 ? kPackedBeatsSkipBelow1 : kPackedBeatsSkipBelow2))) {
+    if (desc->anchor == SB_ANCHOR_SUFFIX && !(flags & forced) && !(can_pack && m < (pk->bits == 1 ? kPackedBeatsSkipBelow1 : pk->bits == 2 ? kPackedBeatsSkipBelow2 : kPackedBeatsSkipBelow4))) {
         for (int G = 8; G <= 32; G *= 2) {
             const int stride = ((m - (G - 1)) / 32) * 32;
             if (stride < skip_min_stride()) break;
@@ -425,9 +425,13 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
      * one, K = 1, 2, 4, 8 with m >= CPW*(K+1)-1; CPW-1 <= m < 2*CPW-1: half-words (only if CPW/2 characters carry
      * >= 14 bits), both halves or the low one. */
     const int cpw = pk && pk->packed ? 32 / pk->bits : 16;  // characters per packed word
-    const bool half_ok = m >= cpw - 1 && m < 2 * cpw - 1 && (cpw / 2) * bits >= 14.0;
-    if (pk && pk->packed && (m >= 2 * cpw - 1 || half_ok) && !(flags & (forced | SB_FLAG_NO_PACK | SB_FLAG_DENSE))) {
-        const int gram = m >= 2 * cpw - 1 ? cpw : cpw / 2;  // characters per fingerprint
+    /* a 4-bit copy only halves the bytes: it pays from K = 2 on (m >= 23), not for K = 1 or half-words, whose
+     * probe-bound rates (3.6 / 2-3.4 TB/s of packed bytes) would then be no better than the byte kernels */
+    const bool wide = pk && pk->packed && pk->bits == 4;
+    const bool half_ok = !wide && m >= cpw - 1 && m < 2 * cpw - 1 && (cpw / 2) * bits >= 14.0;
+    const bool word_ok = m >= (wide ? 3 * cpw - 1 : 2 * cpw - 1);
+    if (pk && pk->packed && (word_ok || half_ok) && !(flags & (forced | SB_FLAG_NO_PACK | SB_FLAG_DENSE))) {
+        const int gram = word_ok ? cpw : cpw / 2;           // characters per fingerprint
         int K = gram == cpw ? 8 : 2;                        // sampling period in fingerprints
         while (gram * K + gram - 1 > m) K >>= 1;
         const int span = gram * K;
@@ -808,24 +812,24 @@ static sb_text *text_alloc(size_t n, const int *devices, int nparts, int first, 
 }
 
 /* sampled byte histogram of every shard -> t->bits (min over shards) */
-/* Texts over at most four byte values also get a 2-bit recoding (1 bit for two symbols) for scan_packed (a
- * quarter / an eighth of the bytes to stream).  The alphabet is guessed from the histogram samples and VERIFIED by the packing pass over every byte;
- * a text that turns out to hold a fifth value simply has no packed copy.  SMART_B200_NO_PACK=1 disables it.
- * Costs n/4 (n/8) bytes of HBM and one extra pass at upload/generation time. */
+/* Texts over at most sixteen byte values also get a recoding at 4, 2 (<= 4 values) or 1 (two values) bits per
+ * character for scan_packed (a half / a quarter / an eighth of the bytes to stream).  The alphabet is guessed from the histogram samples and VERIFIED by the packing pass over every byte;
+ * a text that turns out to hold another value simply has no packed copy.  SMART_B200_NO_PACK=1 disables it.
+ * Costs n/2, n/4 or n/8 bytes of HBM and one extra pass at upload/generation time. */
 static bool text_try_pack(sb_text *t)
 {
     static const bool off = getenv("SMART_B200_NO_PACK") && atoi(getenv("SMART_B200_NO_PACK")) > 0;
     int nsym = 0;
-    unsigned char sym[4] = {0, 0, 0, 0};
+    unsigned char sym[16] = {0};
     for (int b = 0; b < 256; b++)
         if (t->present[b]) {
-            if (nsym < 4) sym[nsym] = (unsigned char)b;
+            if (nsym < 16) sym[nsym] = (unsigned char)b;
             nsym++;
         }
-    if (off || nsym < 1 || nsym > 4 || t->n < (1u << 16)) return true;
-    const int bits = nsym <= 2 ? 1 : 2;
+    if (off || nsym < 1 || nsym > 16 || t->n < (1u << 16)) return true;
+    const int bits = nsym <= 2 ? 1 : nsym <= 4 ? 2 : 4;
     sb::PackLut lut;
-    for (int c = 0; c < 4; c++) lut.sym[c] = c < nsym ? sym[c] : 0xffffffffu;  // unused codes match no byte
+    for (int c = 0; c < 16; c++) lut.sym[c] = c < nsym ? sym[c] : 0xffffffffu;  // unused codes match no byte
     bool ok = true;
     for (int g = 0; g < t->nshards && ok; g++) {
         Shard &s = t->sh[g];
@@ -844,8 +848,11 @@ static bool text_try_pack(sb_text *t)
         if (bits == 1)
             sb::pack_kernel<1><<<c->sms * 8, 256, 0, c->stream>>>(s.d_text, s.len, s.cap, s.packed_bytes / 4, s.d_packed,
                                                                  lut, reinterpret_cast<unsigned *>(c->d_hist));
-        else
+        else if (bits == 2)
             sb::pack_kernel<2><<<c->sms * 8, 256, 0, c->stream>>>(s.d_text, s.len, s.cap, s.packed_bytes / 4, s.d_packed,
+                                                                 lut, reinterpret_cast<unsigned *>(c->d_hist));
+        else
+            sb::pack_kernel<4><<<c->sms * 8, 256, 0, c->stream>>>(s.d_text, s.len, s.cap, s.packed_bytes / 4, s.d_packed,
                                                                  lut, reinterpret_cast<unsigned *>(c->d_hist));
         if (cudaMemcpyAsync(&bad, c->d_hist, sizeof bad, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return false;
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;

@@ -778,49 +778,56 @@ __global__ void __launch_bounds__(kThreads) scan_skip_kernel(const __grid_consta
  * byte-wise verification of scan_skip (skip_candidates: positions and counts come from the ORIGINAL text).
  * Text rate = 4 x the packed-byte rate: above the read-once HBM roofline of the byte text, like scan_skip. */
 struct PackLut {
-    uint32_t sym[4];  // byte values of codes 0..3 (an unused code holds a value no byte has)
+    uint32_t sym[16];  // byte values of codes 0..15 (an unused code holds a value no byte has)
 };
 
+template <int BITS>
 __device__ __forceinline__ uint32_t pack_code(uint32_t b, const PackLut &lut, bool &ok)
 {
     uint32_t c = 0;
-    if (b == lut.sym[1]) c = 1;
-    if (b == lut.sym[2]) c = 2;
-    if (b == lut.sym[3]) c = 3;
+#pragma unroll
+    for (int i = 1; i < (1 << BITS); i++)
+        if (b == lut.sym[i]) c = i;
     ok = (b == lut.sym[c]);
     return c;
 }
 
-/* out[w] packs the CPW = 32/BITS characters text[CPW*w .. CPW*(w+1)), character i at bits BITS*i..; bytes at or
- * beyond `len` pack as code 0; *bad is set if a byte below `len` is none of the symbols (the caller then drops
- * the packed copy).  BITS = 1 for two-symbol texts, 2 for three or four symbols. */
+/* Packs the text at BITS per character: word w holds the CPW = 32/BITS characters text[CPW*w .. CPW*(w+1)),
+ * character i at bits BITS*i...  Each thread turns 32 text bytes into 32/CPW words.  Bytes at or beyond `len`
+ * pack as code 0; *bad is set if a byte below `len` is none of the symbols (the caller then drops the packed
+ * copy).  BITS = 1 for two-symbol texts, 2 for up to four symbols, 4 for up to sixteen. */
 template <int BITS>
 __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *text, unsigned long long len, unsigned long long cap,
                                                    unsigned long long nwords, uint32_t *out, const PackLut lut,
                                                    unsigned *bad)
 {
-    constexpr int CPW = 32 / BITS;
+    constexpr int CPW = 32 / BITS, WPU = 32 / CPW;  // characters per word, words per 32-byte unit
     bool any_bad = false;
-    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords;
-         w += (unsigned long long)gridDim.x * blockDim.x) {
-        uint32_t word = 0;
-        if (CPW * w + CPW <= cap) {
+    const unsigned long long nunits = nwords / WPU;
+    for (unsigned long long u = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; u < nunits;
+         u += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t word[WPU];
 #pragma unroll
-            for (int v16 = 0; v16 < CPW / 16; v16++) {
-                const uint4 v = ldg_stream128(text + CPW * w + 16 * v16);
+        for (int k = 0; k < WPU; k++) word[k] = 0;
+        if (32 * u + 32 <= cap) {
+#pragma unroll
+            for (int v16 = 0; v16 < 2; v16++) {
+                const uint4 v = ldg_stream128(text + 32 * u + 16 * v16);
                 const uint32_t src[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
                     bool ok;
-                    const uint32_t c = pack_code((src[i >> 2] >> (8 * (i & 3))) & 0xffu, lut, ok);
-                    if (CPW * w + 16 * v16 + i < len) {
-                        word |= c << (BITS * (16 * v16 + i));
+                    const uint32_t c = pack_code<BITS>((src[i >> 2] >> (8 * (i & 3))) & 0xffu, lut, ok);
+                    const int ch = 16 * v16 + i;  // character index inside the unit
+                    if (32 * u + ch < len) {
+                        word[ch / CPW] |= c << (BITS * (ch % CPW));
                         any_bad |= !ok;
                     }
                 }
             }
         }
-        out[w] = word;
+#pragma unroll
+        for (int k = 0; k < WPU; k++) out[u * WPU + k] = word[k];
     }
     if (any_bad) atomicOr(bad, 1u);
 }

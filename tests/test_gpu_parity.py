@@ -499,8 +499,26 @@ def test_packed_scan_of_small_alphabet_texts(oracle):
     with sb.Text.upload(y) as t:
         assert t.packed_bits == 0
         assert sb.search("bf", t, y[5000:5040]).count == oracle.bf_count(y[5000:5040], y)
-    with sb.Text.generate(1 << 20, 8, 3) as t:
+    with sb.Text.generate(1 << 20, 32, 3) as t:
         assert t.packed_bits == 0
+    # up to sixteen byte values: 4 bits per character, used from m = 23 (every 2nd word) on
+    for sigma in (5, 8, 16):
+        y = sb.textgen_host(0, 2_500_003, sigma, 31)
+        with sb.Text.upload(y) as t, sb.Text.upload(y, devices=[0, 0]) as t2:
+            assert t.packed_bits == 4
+            for m in (8, 22, 23, 24, 38, 39, 70, 71, 150, 191, 192, 600):
+                for k in (0, y.size // 3, y.size - m):
+                    x = y[k:k + m].copy()
+                    want = oracle.bf_positions(x, y)
+                    for algo in ("kmp", "qs"):
+                        assert sb.search(algo, t, x).count == want.size, (sigma, m, k, algo)
+                        kind = sb.last_timing().filter_kind
+                        if m < 23:
+                            assert kind < 100 or kind in (408, 416, 816), (sigma, m, kind)
+                        elif algo == "kmp" or m < 167:
+                            assert kind == 300 + max(k2 for k2 in (2, 4, 8) if 8 * (k2 + 1) - 1 <= m), (sigma, m, kind)
+                    r = sb.search("bf", t2, x, flags=sb.FLAG_POSITIONS, positions_cap=want.size + 1)
+                    assert np.array_equal(r.positions, want), (sigma, m, k)
     with sb.Text.generate(1 << 22, 4, 3) as t, sb.Text.generate(1 << 22, 4, 3, devices=[0, 0]) as t2:  # generated in place
         assert t.packed_bits == 2 and t2.packed_bits == 2
         x = sb.textgen_host(12345, 90, 4, 3)

@@ -15,7 +15,7 @@ import smart_b200 as sb  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gib", type=float, default=4.0)
-    ap.add_argument("--sigma", type=int, default=4)
+    ap.add_argument("--sigma", type=int, default=4)  # 2 -> 1-bit, 3..4 -> 2-bit, 5..16 -> 4-bit copy
     ap.add_argument("--ms", default="15,16,20,23,24,30,31,40,47,64,79,100,128,143,160,200,256,400,512,1024")
     ap.add_argument("--reps", type=int, default=7)
     ap.add_argument("--out", default="gpurun_out/packed_sweep.jsonl")
@@ -23,7 +23,7 @@ def main():
     n = int(a.gib * (1 << 30))
     out = open(a.out, "w")
     with sb.Text.generate(n, a.sigma, 1000 + a.sigma) as t:
-        assert t.packed_bits in (1, 2)
+        assert t.packed_bits in (1, 2, 4)
         for m in [int(v) for v in a.ms.split(",")]:
             x = sb.textgen_host(n // 3 + 17, m, a.sigma, 1000 + a.sigma)
             for algo in ("bf", "hor"):
