@@ -16,8 +16,14 @@
  *       * scan_window<NW,OFF> (5 <= m, low-entropy texts or m < 2B-1): an 8/12/16-byte window
  *         fingerprint at EVERY start position (SHF funnel shift + IMAD + ISETP.EQ.OR per position);
  *         the halo comes from the neighbouring lane by shuffle, not from memory;
+ *       * scan_block<2,L> (5 <= m <= 10): the same with windows at every EVEN position (one funnel shift per word);
  *       * scan_swar<M> (m <= 4): exact byte-parallel compare, four start positions per instruction,
  *         counted with POPC in registers;
+ *   - sub-linear variants read less than the text: scan_skip<G> samples one gram per `stride` bytes (skip
+ *     families, long patterns), scan_packed<K> / scan_packed_half<KH> stream a 4/2/1-bit recoding of a text over
+ *     <= 16 byte values; both resolve hits through a shared-memory bitmap and an exact table;
+ *   - scan_multi<B> counts a whole pattern set in one pass; scan_block_tma<B> is the TMA-fed (cp.async.bulk +
+ *     mbarrier ring) variant of scan_block kept as a measured experiment;
  *   - candidates (rare) go to an exact verification that reads the text through L2 with unaligned
  *     32-bit windows (warp-cooperative, 128 bytes per step, in scan_block);
  *   - counts are reduced with warp shuffles and ONE atomicAdd per block.
