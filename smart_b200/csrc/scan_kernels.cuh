@@ -237,7 +237,7 @@ template <int L>
 __host__ __device__ __forceinline__ uint32_t pair_fp(uint32_t lo, uint32_t hi)
 {
     if (L == 4) return lo;
-    return lo * K3 + hi * (1u << (8 * (8 - L)));
+    return lo * K3 + hi * (1u << (L > 4 ? 8 * (8 - L) : 0));
 }
 
 /* words a lane needs for its 32-byte vector: 8 own + halo from the next lane */
@@ -862,7 +862,9 @@ __global__ void __launch_bounds__(kThreads) scan_packed_kernel(const __grid_cons
 #pragma unroll
             for (int k = 0; k < 8; k += K) {  // q0 is a multiple of 8: word q0+k has index = k (mod K)
                 // ONE probe: at most 128 words in 2^18 bits give < 5e-4 false hits per word, and the exact table
-                // behind skip_candidates settles them; the second probe cost more than it saved
+                // behind skip_candidates settles them; the second probe cost more than it saved.  (Also measured: a
+                // bank-conflict-free 4096-bit pre-filter in 32 copies in front of this probe - slower, 14.5 -> 11.6
+                // T characters/s at K = 1: the variant is issue-bound, not bank-conflict-bound.)
                 const uint32_t w = v[c].w[k];
                 const uint32_t s1 = bloom_slot(w);
                 const bool hit = ((bloom[s1 >> 5] >> (s1 & 31)) & 1u) && q0 + k < a.nsamples;
