@@ -95,21 +95,21 @@ static const sb_algo_desc g_algos[] = {
     {"bww", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* bww.c:28 */
     {"dbww", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 2}, /* dbww.c:28, n/m<2 -> -1 (:35) */
     {"dbww2", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 2}, /* dbww2.c:31, n/m<2 -> -1 (:38) */
-    {"bom", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* bom.c:77 */
-    {"bom2", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* bom2.c:28 */
-    {"ebom", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* ebom.c:28, m<2 -> -1 (:35) */
-    {"fbom", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* fbom.c:28 */
-    {"sebom", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* sebom.c:25, m<2 -> -1 (:32) */
-    {"sfbom", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* sfbom.c:25 */
-    {"ildm1", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* ildm1.c:29 */
-    {"ildm2", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* ildm2.c:40 */
-    {"fdm", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* fdm.c:27 */
-    {"bsdm", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* bsdm.c:30 */
-    {"bsdm4", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 4, 0}, /* bsdm4.c:32, m<4 -> -1 (:36) */
-    {"bsdm5", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 5, 0}, /* bsdm5.c:32, m<5 -> -1 (:36) */
-    {"bsdm7", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 7, 0}, /* bsdm7.c:32, m<7 -> -1 (:36) */
-    {"bsdm8", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 8, 0}, /* bsdm8.c:32, m<8 -> -1 (:36) */
-    {"ww", SB_FAM_ORACLE, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* ww.c:43 */
+    {"bom", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* bom.c:77 */
+    {"bom2", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* bom2.c:28 */
+    {"ebom", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* ebom.c:28, m<2 -> -1 (:35) */
+    {"fbom", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* fbom.c:28 */
+    {"sebom", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* sebom.c:25, m<2 -> -1 (:32) */
+    {"sfbom", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* sfbom.c:25 */
+    {"ildm1", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* ildm1.c:29 */
+    {"ildm2", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* ildm2.c:40 */
+    {"fdm", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* fdm.c:27 */
+    {"bsdm", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* bsdm.c:30 */
+    {"bsdm4", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 4, 0}, /* bsdm4.c:32, m<4 -> -1 (:36) */
+    {"bsdm5", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 5, 0}, /* bsdm5.c:32, m<5 -> -1 (:36) */
+    {"bsdm7", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 7, 0}, /* bsdm7.c:32, m<7 -> -1 (:36) */
+    {"bsdm8", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 8, 0}, /* bsdm8.c:32, m<8 -> -1 (:36) */
+    {"ww", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* ww.c:43 */
     {"wfr", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* wfr.c:61 */
     {"wfr2", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* wfr2.c:61, m<2 -> -1 (:65) */
     {"wfr3", SB_FAM_WFR, SB_ANCHOR_SUFFIX, 0, 0, 0, 3, 0}, /* wfr3.c:60, m<3 -> -1 (:64) */

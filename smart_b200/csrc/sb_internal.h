@@ -39,7 +39,7 @@ enum sb_family {
     SB_FAM_AUT,     /* deterministic automaton: aut */
     SB_FAM_TWOWAY,  /* constant-space linear: smoa, tw, rcolussi */
     SB_FAM_BNDMX,   /* backward bit-parallel windows: bndmq*, lbndm, sbndm*, fsbndm-w2, fndm, tndm*, bxs*, bww, dbww* */
-    SB_FAM_ORACLE,  /* factor oracles / suffix automata: bom*, ebom, fbom, sebom, sfbom, ildm*, fdm, bsdm*, ww */
+    SB_FAM_FACTOR,  /* factor oracles / suffix automata: bom*, ebom, fbom, sebom, sfbom, ildm*, fdm, bsdm*, ww */
     SB_FAM_WFR,     /* hashed weak-factor recognition: wfr*, twfr*, lwfr* */
     SB_FAM_SKIPQ,   /* q-gram bucket skip search: skip3..8 */
     SB_FAM_BADCHAR, /* further bad-character / good-suffix shift variants: bfs, ffs, iom, wom, pbmh, qlqs, tsw, wc, zt, ... */

@@ -4,7 +4,7 @@
 # resident GPU worker, once with the REFERENCE executables on the host CPU, same seed => same pattern sets.
 # Needs data_local/ = a git-ignored copy of the reference data: mkdir data_local && cp -r /root/reference/data/{englishTexts,italianTexts,frenchTexts,chineseTexts,protein,midimusic} data_local/
 set -e
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 W=${1:-gpurun_out/corpus_demo}
 mkdir -p "$W"
 TEXTS=englishTexts-italianTexts-frenchTexts-chineseTexts-protein-midimusic

@@ -3,7 +3,7 @@
 # run the same experiment (same seed => same pattern sets) with OUR per-algorithm executables (resident GPU
 # worker) and with the REFERENCE's executables (oracle/_ref/bin, CPU), and keep both transcripts.
 set -e
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 W=${1:-gpurun_out/driver_demo}
 mkdir -p "$W"
 bin/textgen -data "$W/data" -only 4 > /dev/null
