@@ -62,3 +62,56 @@ def test_random_pattern_sets(oracle, seed, sigma, m):
     with sb.Text.upload(y) as t:
         counts, _, _ = sb.search_multi("bf", t, pats)
         assert counts.tolist() == [oracle.bf_count(p, y) for p in pats]
+
+
+@st.composite
+def packed_text_and_pattern(draw):
+    """texts of at least 64 KiB over 2..16 byte values (they also get a packed copy), every pattern shape"""
+    nsym = draw(st.sampled_from([2, 3, 4, 5, 9, 16]))
+    seed = draw(st.integers(0, 2**31 - 1))
+    rng = np.random.default_rng(seed)
+    alphabet = rng.choice(256, nsym, replace=False).astype(np.uint8)
+    n = draw(st.integers(65536, 300000))
+    kind = draw(st.sampled_from(["uniform", "skewed", "periodic", "blocks"]))
+    if kind == "uniform":
+        idx = rng.integers(0, nsym, n)
+    elif kind == "skewed":
+        p = rng.dirichlet(np.full(nsym, 0.4))
+        idx = rng.choice(nsym, n, p=p)
+    elif kind == "periodic":
+        idx = np.resize(rng.integers(0, nsym, draw(st.integers(1, 700))), n)
+    else:  # long runs with noise
+        idx = np.repeat(rng.integers(0, nsym, n // 50 + 1), 50)[:n]
+        noise = rng.integers(0, n, n // 200)
+        idx[noise] = rng.integers(0, nsym, noise.size)
+    y = alphabet[idx]
+    m = draw(st.integers(7, 1300))
+    k = draw(st.sampled_from([0, n - m, int(rng.integers(0, n - m))]))
+    x = y[k:k + m].copy()
+    mut = draw(st.sampled_from(["none", "last", "first", "middle", "foreign"]))
+    if mut == "last":
+        x[-1] = alphabet[(int(np.where(alphabet == x[-1])[0][0]) + 1) % nsym]
+    elif mut == "first":
+        x[0] = alphabet[(int(np.where(alphabet == x[0])[0][0]) + 1) % nsym]
+    elif mut == "middle":
+        x[m // 2] = alphabet[(int(np.where(alphabet == x[m // 2])[0][0]) + 1) % nsym]
+    elif mut == "foreign":
+        x[m // 3] = next(b for b in range(256) if b not in set(alphabet.tolist()))
+    return y, x
+
+
+@settings(max_examples=200, deadline=None, suppress_health_check=list(HealthCheck))
+@given(packed_text_and_pattern())
+def test_random_packed_texts(oracle, case):
+    """The packed-copy kernels (and whatever the planner picks instead) against the oracle: counts for a prefix-
+    and a suffix-anchored family, sharded and unsharded, and the sorted positions."""
+    y, x = case
+    want = oracle.bf_positions(x, y)
+    with sb.Text.upload(y) as t, sb.Text.upload(y, devices=[0, 0, 0]) as t3:
+        assert t.packed_bits in (1, 2, 4)
+        for a in ("bf", "hor", "kmp", "wfr", "sbndm"):
+            assert sb.search(a, t, x).count == want.size, (a, x.size, y.size, sb.last_timing().filter_kind)
+        assert sb.search("qs", t3, x).count == want.size
+        assert sb.search("bf", t, x, flags=sb.FLAG_NO_PACK).count == want.size
+        r = sb.search("so", t3, x, flags=sb.FLAG_POSITIONS, positions_cap=want.size + 1)
+        assert np.array_equal(r.positions, want)
