@@ -62,7 +62,7 @@ extern "C" {
 #define SB_FLAG_FILTER_B4L8 0x200u   /* overlapping windows: 4-byte alignment, 8-byte fingerprint (m >= 11) */
 #define SB_FLAG_FILTER_B4L16 0x400u  /* 4-byte alignment, 16-byte fingerprint (m >= 19) */
 #define SB_FLAG_FILTER_B8L16 0x800u  /* 8-byte alignment, 16-byte fingerprint (m >= 23) */
-#define SB_FLAG_FILTER_B2 0x1000u    /* windows of min(8, m-1) bytes at every even position (m >= 5) */
+#define SB_FLAG_FILTER_B2 0x1000u    /* windows of min(8, m-1) bytes at every even position (m >= 4) */
 #define SB_FLAG_NO_PACK 0x2000u      /* do not use the packed recoding of a text over <= 16 byte values */
 
 /* ---- algorithm registry (names are the lower-cased SMART registry names, smart.c:142) ---- */
@@ -147,7 +147,7 @@ typedef struct sb_timing {
     int kernels_launched;  /* scan kernels launched by the last search (all shards) */
     int filter_kind;       /* 0 = scan_swar (m <= 4), 1/2/3 = scan_window 8/12/16 B, 4/8/16/32 = scan_block<B,B>,
                               408/416/816 = scan_block<B,L> (overlapping windows),
-                              24..28 = scan_block<2,L> (L = 4..8 bytes at every even position),
+                              23..28 = scan_block<2,L> (L = 3..8 bytes at every even position),
                               301/302/304/308 = scan_packed<K> on the 2-bit recoding (300: pattern has a byte
                               the text does not contain, nothing scanned), 311/312 = scan_packed_half<KH>,
                               108/116/132 = scan_skip<G>, 204/208/216 = scan_multi<B>, -1 = per-pattern fallback */

@@ -83,7 +83,7 @@ struct DevCtx {                               // per-device scratch, created on 
     size_t sort_temp_bytes = 0;
     int occ_packed[4] = {0};                  // ... for scan_packed<K>, K = 1, 2, 4, 8
     int occ_packed_half[2] = {0};             // ... for scan_packed_half<KH>, KH = 1, 2
-    int occ_pair[5] = {0};                    // ... for scan_block<2,L>, index L-4
+    int occ_pair[6] = {0};                    // ... for scan_block<2,L>, index L-3
     int occ_block[7] = {0};                   // resident CTAs/SM for scan_block<B,L>, index block_index()
     int occ_window[24] = {0};                 // ... for scan_window<NW,OFF,DENSE>, index window_index()
     int occ_swar[8] = {0};                    // ... for scan_swar<M, DENSE>, index (M-1)*2 + DENSE
@@ -169,11 +169,12 @@ DevCtx *get_ctx(int dev)
     c.occ_packed[3] = occupancy(sb::scan_packed_kernel<8>);
     c.occ_packed_half[0] = occupancy(sb::scan_packed_half_kernel<1>);
     c.occ_packed_half[1] = occupancy(sb::scan_packed_half_kernel<2>);
-    c.occ_pair[0] = occupancy(sb::scan_block_kernel<2, 4, kU>);
-    c.occ_pair[1] = occupancy(sb::scan_block_kernel<2, 5, kU>);
-    c.occ_pair[2] = occupancy(sb::scan_block_kernel<2, 6, kU>);
-    c.occ_pair[3] = occupancy(sb::scan_block_kernel<2, 7, kU>);
-    c.occ_pair[4] = occupancy(sb::scan_block_kernel<2, 8, kU>);
+    c.occ_pair[0] = occupancy(sb::scan_block_kernel<2, 3, kU>);
+    c.occ_pair[1] = occupancy(sb::scan_block_kernel<2, 4, kU>);
+    c.occ_pair[2] = occupancy(sb::scan_block_kernel<2, 5, kU>);
+    c.occ_pair[3] = occupancy(sb::scan_block_kernel<2, 6, kU>);
+    c.occ_pair[4] = occupancy(sb::scan_block_kernel<2, 7, kU>);
+    c.occ_pair[5] = occupancy(sb::scan_block_kernel<2, 8, kU>);
     c.occ_block[block_index(4, 4)] = occupancy(sb::scan_block_kernel<4, 4, kU>);
     c.occ_block[block_index(8, 8)] = occupancy(sb::scan_block_kernel<8, 8, kU>);
     c.occ_block[block_index(16, 16)] = occupancy(sb::scan_block_kernel<16, 16, kU>);
@@ -252,8 +253,9 @@ uint32_t fingerprint(const unsigned char *p, int B)
 
 uint32_t fingerprint_pair(const unsigned char *p, int L)
 {
-    const uint32_t lo = load_le32(p, 4), hi = L > 4 ? load_le32(p + 4, L - 4) : 0u;
+    const uint32_t lo = load_le32(p, L < 4 ? L : 4), hi = L > 4 ? load_le32(p + 4, L - 4) : 0u;
     switch (L) {
+    case 3: return sb::pair_fp<3>(lo, hi);
     case 4: return sb::pair_fp<4>(lo, hi);
     case 5: return sb::pair_fp<5>(lo, hi);
     case 6: return sb::pair_fp<6>(lo, hi);
@@ -275,7 +277,7 @@ int choose_filter(int m, unsigned flags, double bits, int *flen)
 {
     static const int variants[7][2] = {{4, 4}, {8, 8}, {4, 8}, {16, 16}, {8, 16}, {4, 16}, {32, 32}};  // by L, widest B first
     *flen = 0;
-    if ((flags & SB_FLAG_FILTER_B2) && m >= 5) return *flen = (m - 1 < 8 ? m - 1 : 8), kFilterPair;
+    if ((flags & SB_FLAG_FILTER_B2) && m >= 4) return *flen = (m - 1 < 8 ? m - 1 : 8), kFilterPair;
     if ((flags & SB_FLAG_FILTER_B32) && m >= 63) return *flen = 32;
     if ((flags & SB_FLAG_FILTER_B8L16) && m >= 23) return *flen = 16, 8;
     if ((flags & SB_FLAG_FILTER_B4L16) && m >= 19) return *flen = 16, 4;
@@ -283,6 +285,7 @@ int choose_filter(int m, unsigned flags, double bits, int *flen)
     if ((flags & SB_FLAG_FILTER_B16) && m >= 31) return *flen = 16;
     if ((flags & SB_FLAG_FILTER_B8) && m >= 15) return *flen = 8;
     if ((flags & SB_FLAG_FILTER_B4) && m >= 7) return *flen = 4;
+    if (m == 4 && 3 * bits >= 15.0 && !(flags & (SB_FLAG_DENSE | SB_FLAG_FILTER_SHIFT))) return *flen = 3, kFilterPair;  // rare 4-byte pattern
     if (m <= 4) return kFilterShort;
     if (flags & SB_FLAG_FILTER_SHIFT) return kFilterWindow8;  // 8-byte window (exact for m <= 8)
     int bestB = 0, bestL = 0;
@@ -566,7 +569,7 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
         const bool pair = pl.filter == kFilterPair;
         const unsigned long long end = (unsigned long long)a.hi + a.anchor + (pair ? 2 : pl.filter) + pl.flen;
         a.ngroups = (end + group - 1) / group;
-        per_sm = pair ? c.occ_pair[pl.flen - 4] : c.occ_block[block_index(pl.filter, pl.flen)];
+        per_sm = pair ? c.occ_pair[pl.flen - 3] : c.occ_block[block_index(pl.filter, pl.flen)];
     }
     unsigned long long want = (a.ngroups + (sb::kThreads / 32) - 1) / (sb::kThreads / 32);
     unsigned long long maxb = (unsigned long long)c.sms * per_sm;
@@ -595,6 +598,7 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
 #undef SB_WIN_LAUNCH
     } else if (pl.filter == kFilterPair) {
         switch (pl.flen) {
+        case 3: sb::scan_block_kernel<2, 3, kU><<<grid, sb::kThreads, 0, stream>>>(a); break;
         case 4: sb::scan_block_kernel<2, 4, kU><<<grid, sb::kThreads, 0, stream>>>(a); break;
         case 5: sb::scan_block_kernel<2, 5, kU><<<grid, sb::kThreads, 0, stream>>>(a); break;
         case 6: sb::scan_block_kernel<2, 6, kU><<<grid, sb::kThreads, 0, stream>>>(a); break;

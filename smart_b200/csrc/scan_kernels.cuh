@@ -231,12 +231,13 @@ __device__ __forceinline__ uint32_t block_fp(const uint32_t *W, int q)
     return fp32(fp16(W[0], W[1], W[2], W[3]), fp16(W[4], W[5], W[6], W[7]));
 }
 
-/* B = 2 (windows at every EVEN text position, L = 4..8 bytes): fingerprint of the L bytes lo|hi, the bytes of
+/* B = 2 (windows at every EVEN text position, L = 3..8 bytes): fingerprint of the L bytes lo|hi, the bytes of
  * hi beyond L multiplied away (hi * 2^(8*(8-L)) keeps its low L-4 bytes): IMADs only, no mask */
 template <int L>
 __host__ __device__ __forceinline__ uint32_t pair_fp(uint32_t lo, uint32_t hi)
 {
     if (L == 4) return lo;
+    if (L == 3) return lo * 256u;  // three bytes: the fourth is multiplied away
     return lo * K3 + hi * (1u << (L > 4 ? 8 * (8 - L) : 0));
 }
 

@@ -14,7 +14,7 @@ from golden_texts import ALGOS, GOLDEN, TEXT_NAMES, make_patterns, make_text, ex
 
 pytestmark = pytest.mark.gpu
 
-# filter kinds reported by sb_last_timing: 0 scan_swar, 1 scan_window8, 4/8/16/32 scan_block<B>, 24..28 scan_block<2,L>
+# filter kinds reported by sb_last_timing: 0 scan_swar, 1 scan_window8, 4/8/16/32 scan_block<B>, 23..28 scan_block<2,L>
 FILTERS = {0: 0, 1: sb.FLAG_FILTER_SHIFT, 2: sb.FLAG_FILTER_B2, 4: sb.FLAG_FILTER_B4, 8: sb.FLAG_FILTER_B8, 16: sb.FLAG_FILTER_B16,
            32: sb.FLAG_FILTER_B32, 408: sb.FLAG_FILTER_B4L8, 416: sb.FLAG_FILTER_B4L16, 816: sb.FLAG_FILTER_B8L16}
 
