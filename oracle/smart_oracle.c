@@ -3,8 +3,9 @@
  *
  * A plain-C CPU restatement of the reference's (ostafen/smart) exact-string-matching path:
  * the brute-force result that defines every algorithm's count, the preprocessing tables of
- * the north-star algorithm families, and each family's sequential scan (40 algorithms; a
- * further 102 are covered by result specification + domain rule, see "Tier 2" below).  Only tests/,
+ * the north-star algorithm families, and each family's sequential scan (48 algorithms, the
+ * last eight being wfr and wfrq2..8; a further 94 are covered by result specification +
+ * domain rule, see "Tier 2" below).  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
  * file's shared object; nothing under smart_b200/ links or calls it.
  *
@@ -958,6 +959,95 @@ long long ora_search_graspm(const unsigned char *x, int m, const unsigned char *
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Weak Factor Recognition.  Table: wfr.c:41-58 (Q <= 1) and wfrq4.c:50-65 (q-gram variants): F[h] = 1 for the
+ * 16-bit hash of every pattern factor the scan can ask about, hashes built right to left. */
+void ora_pre_wfr(const unsigned char *x, int m, int Q, unsigned char *F)
+{
+    memset(F, 0, 65536);
+    if (Q <= 1) {
+        const int fact = m < 16 ? m : 16;
+        for (int i = 0; i < m; i++) {
+            unsigned short h = 0;
+            for (int j = i; j >= 0 && j > i - fact; j--) {
+                h = (unsigned short)((h << 2) + x[j]);
+                F[h] = 1;
+            }
+        }
+        return;
+    }
+    const int fact = m < 8 ? m : 8;
+    for (int i = Q - 1; i < m; i++) {
+        const int stop = i - fact + 1 >= Q - 1 ? i - fact + 1 : Q - 1;
+        unsigned short h = 0;
+        for (int e = i; e == i || e >= stop; e -= Q) {
+            unsigned g = 0;
+            for (int k = 0; k < Q; k++) g += (unsigned)x[e - k] << (2 * (Q - 1 - k));
+            h = (unsigned short)(e == i ? g : ((unsigned)h << (2 * Q)) + g);
+            F[h] = 1;
+        }
+    }
+}
+
+/* wfr.c:73-92: the window [i, i+m) is read right to left while the hash of what was read is some factor's;
+ * reaching the window start triggers the comparison; the next window starts m after the stopping point.
+ * (The reference also copies x to y[n..n+m); the loop never reads there, so the bounded version drops it.) */
+long long ora_search_wfr(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    unsigned char *F = malloc(65536);
+    long long count = 0;
+    ora_pre_wfr(x, m, 0, F);
+    long long j = m - 1;
+    while (j < (long long)n) {
+        unsigned short h = y[j];
+        const long long i = j - (m - 1);
+        int test;
+        while ((test = F[h]) && j > i) {
+            j--;
+            h = (unsigned short)((h << 2) + y[j]);
+        }
+        if (j == i && test && memcmp(x, y + i, (size_t)m) == 0) count++;
+        j += m;
+    }
+    free(F);
+    return count;
+}
+
+/* wfrq2.c .. wfrq8.c (the scan of wfrq4.c:80-100 with Q characters per step): the window is the pattern cut to
+ * a multiple of Q, its q-grams are hashed right to left; position 0 is compared up front (:84); m < Q -> -1 (:71) */
+long long ora_search_wfrq(const unsigned char *x, int m, const unsigned char *y, size_t n, int Q)
+{
+    if (m < Q) return -1;
+    if ((size_t)m > n) return 0;
+    const int plen = m;
+    m -= m % Q;
+    unsigned char *F = malloc(65536);
+    long long count = 0;
+    ora_pre_wfr(x, m, Q, F);
+#define ORA_WFRQ_GRAM(pos)                                                                     \
+    ({                                                                                         \
+        unsigned g_ = 0;                                                                       \
+        for (int k_ = 0; k_ < Q; k_++) g_ += (unsigned)y[(pos) - k_] << (2 * (Q - 1 - k_));    \
+        g_;                                                                                    \
+    })
+    if (memcmp(x, y, (size_t)plen) == 0) count++;
+    long long j = m;
+    while (j < (long long)n) {
+        unsigned short h = (unsigned short)ORA_WFRQ_GRAM(j);
+        const long long i = j - m + 1;
+        int test;
+        while ((test = F[h]) && j > i + Q - 1) {
+            j -= Q;
+            h = (unsigned short)(((unsigned)h << (2 * Q)) + ORA_WFRQ_GRAM(j));
+        }
+        if (j == i + Q - 1 && test && i + plen <= (long long)n && memcmp(x, y + i, (size_t)plen) == 0) count++;
+        j += m - Q + 1;
+    }
+#undef ORA_WFRQ_GRAM
+    free(F);
+    return count;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Tier 2: the other reference algorithms that agree with bf.c on every golden input (SURVEY.md Appendix A
  * "always clean", minus kbndm, ksa and ssm which the golden sweep caught).  Their scans are NOT restated
  * here: each of them returns the brute-force count (bf.c:33-36) outside its `return -1` domain, so the
@@ -1118,6 +1208,8 @@ long long ora_search(const char *algo, const unsigned char *x, int m, const unsi
     if (!strncmp(algo, "hash", 4) && algo[4] && !algo[5]) return ora_search_hashq(x, m, y, n, algo[4] - '0');
     if (!strncmp(algo, "qf", 2) && algo[2] && algo[3] && !algo[4])
         return ora_search_qf(x, m, y, n, algo[2] - '0', algo[3] - '0');
+    if (!strcmp(algo, "wfr")) return (size_t)m > n ? 0 : ora_search_wfr(x, m, y, n);
+    if (!strncmp(algo, "wfrq", 4) && algo[4] >= '2' && algo[4] <= '8' && !algo[5]) return ora_search_wfrq(x, m, y, n, algo[4] - '0');
     return ora_search_tier2(algo, x, m, y, n);
 }
 
