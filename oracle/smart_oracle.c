@@ -3,8 +3,8 @@
  *
  * A plain-C CPU restatement of the reference's (ostafen/smart) exact-string-matching path:
  * the brute-force result that defines every algorithm's count, the preprocessing tables of
- * the north-star algorithm families, and each family's sequential scan (48 algorithms, the
- * last eight being wfr and wfrq2..8; a further 94 are covered by result specification +
+ * the north-star algorithm families, and each family's sequential scan (53 algorithms, the
+ * last thirteen being wfr, wfrq2..8 and skip3/5/6/7/8; a further 89 are covered by result specification +
  * domain rule, see "Tier 2" below).  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
  * file's shared object; nothing under smart_b200/ links or calls it.
@@ -1047,6 +1047,42 @@ long long ora_search_wfrq(const unsigned char *x, int m, const unsigned char *y,
     return count;
 }
 
+/* skip3.c, skip5.c .. skip8.c (:28-57): Skip Search on q-grams.  Every pattern q-gram is filed under its hash
+ * (skip3: x[i]<<4 + x[i+1]<<2 + x[i+2]; skipQ, Q >= 5: sum x[i+k] << (Q-1-k)); the text is sampled every
+ * m-Q+1 positions and each pattern offset filed under the sampled gram's hash is verified.  m < Q -> -1 (:31).
+ * The reference hashes y[j..j+Q) for every sampled j < n, reading past y[n] near the end; a sample with
+ * j+Q > n cannot belong to an occurrence inside the text, so the bounded scan stops before it. */
+static unsigned ora_skipq_hash(const unsigned char *p, int Q)
+{
+    if (Q == 3) return ((unsigned)p[0] << 4) + ((unsigned)p[1] << 2) + p[2];
+    unsigned h = 0;
+    for (int k = 0; k < Q; k++) h += (unsigned)p[k] << (Q - 1 - k);
+    return h;
+}
+
+long long ora_search_skipq(const unsigned char *x, int m, const unsigned char *y, size_t n, int Q)
+{
+    if (m < Q) return -1;
+    if ((size_t)m > n) return 0;
+    int *head = malloc(sizeof(int) * 65536), *next = malloc(sizeof(int) * (size_t)m);
+    long long count = 0;
+    for (int i = 0; i < 65536; i++) head[i] = -1;
+    for (int i = 0; i + Q <= m; i++) {
+        const unsigned h = ora_skipq_hash(x + i, Q);
+        next[i] = head[h];
+        head[h] = i;
+    }
+    const long long mq = m - Q + 1, nn = (long long)n;
+    for (long long j = mq - 1; j + Q <= nn; j += mq)
+        for (int e = head[ora_skipq_hash(y + j, Q)]; e >= 0; e = next[e]) {
+            const long long h = j - e;
+            if (h <= nn - m && memcmp(x, y + h, (size_t)m) == 0) count++;
+        }
+    free(head);
+    free(next);
+    return count;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Tier 2: the other reference algorithms that agree with bf.c on every golden input (SURVEY.md Appendix A
  * "always clean", minus kbndm, ksa and ssm which the golden sweep caught).  Their scans are NOT restated
@@ -1208,6 +1244,7 @@ long long ora_search(const char *algo, const unsigned char *x, int m, const unsi
     if (!strncmp(algo, "hash", 4) && algo[4] && !algo[5]) return ora_search_hashq(x, m, y, n, algo[4] - '0');
     if (!strncmp(algo, "qf", 2) && algo[2] && algo[3] && !algo[4])
         return ora_search_qf(x, m, y, n, algo[2] - '0', algo[3] - '0');
+    if (!strncmp(algo, "skip", 4) && algo[4] >= '3' && algo[4] <= '8' && !algo[5]) return ora_search_skipq(x, m, y, n, algo[4] - '0');
     if (!strcmp(algo, "wfr")) return (size_t)m > n ? 0 : ora_search_wfr(x, m, y, n);
     if (!strncmp(algo, "wfrq", 4) && algo[4] >= '2' && algo[4] <= '8' && !algo[5]) return ora_search_wfrq(x, m, y, n, algo[4] - '0');
     return ora_search_tier2(algo, x, m, y, n);
