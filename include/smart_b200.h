@@ -200,6 +200,7 @@ typedef struct sb_tables {
     int qfB[1 << 18];           /* qf23.c:50-56; entries [0, 1<<(Q*S)) */
     int wfrQ;                   /* wfrq<Q>.c / twfrq<Q>.c: q-gram length; 0 for wfr, wfr2..8, twfr*, lwfr* */
     unsigned char wfrF[65536];  /* wfr.c:41-58, wfrq4.c:50-65: weak-factor table, 1 = some factor hashes here */
+    int ztBc[SB_SIGMA * SB_SIGMA]; /* zt.c:64-74, row-major [a][b]; filled for zt only */
 } sb_tables;
 /* Build every table the algorithm family of `algo` uses (others are left zeroed).
  * Returns 0, or -1 when the algorithm is not applicable to m (same rule as sb_search64). */

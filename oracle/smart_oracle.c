@@ -3,8 +3,8 @@
  *
  * A plain-C CPU restatement of the reference's (ostafen/smart) exact-string-matching path:
  * the brute-force result that defines every algorithm's count, the preprocessing tables of
- * the north-star algorithm families, and each family's sequential scan (53 algorithms, the
- * last thirteen being wfr, wfrq2..8 and skip3/5/6/7/8; a further 89 are covered by result specification +
+ * the north-star algorithm families, and each family's sequential scan (54 algorithms, the
+ * last fourteen being wfr, wfrq2..8, skip3/5/6/7/8 and zt; a further 88 are covered by result specification +
  * domain rule, see "Tier 2" below).  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
  * file's shared object; nothing under smart_b200/ links or calls it.
@@ -1047,6 +1047,41 @@ long long ora_search_wfrq(const unsigned char *x, int m, const unsigned char *y,
     return count;
 }
 
+/* Zhu-Takaoka (zt.c): two-character bad-character table (:64-74) + the Boyer-Moore good-suffix table (:52-62);
+ * right-to-left comparison, shift = max(bmGs[i], ztBc[y[j+m-2]][y[j+m-1]]) (:88-99).  For m = 1 the reference
+ * indexes y[j-1] (before the buffer at j = 0); every ztBc entry is then <= 1 = bmGs[0], so the bounded version
+ * takes the shift 1 without that read. */
+void ora_pre_ztbc(const unsigned char *x, int m, int *ztBc)
+{
+    for (int i = 0; i < 65536; i++) ztBc[i] = m;
+    for (int a = 0; a < 256; a++) ztBc[a * 256 + x[0]] = m - 1;
+    for (int i = 1; i < m - 1; i++) ztBc[x[i - 1] * 256 + x[i]] = m - 1 - i;
+}
+
+long long ora_search_zt(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    int *zt = malloc(sizeof(int) * 65536), *suff = malloc(sizeof(int) * (size_t)m), *gs = malloc(sizeof(int) * (size_t)m);
+    long long count = 0;
+    ora_pre_ztbc(x, m, zt);
+    ora_pre_bmgs(x, m, suff, gs);
+    for (size_t j = 0; j + (size_t)m <= n;) {
+        int i = m - 1;
+        while (i >= 0 && x[i] == y[i + j]) --i;
+        if (i < 0) {
+            count++;
+            j += (size_t)gs[0];
+        } else {
+            const int bc = m >= 2 ? zt[y[j + m - 2] * 256 + y[j + m - 1]] : 1;
+            j += (size_t)(gs[i] > bc ? gs[i] : bc);
+        }
+    }
+    free(zt);
+    free(suff);
+    free(gs);
+    return count;
+}
+
 /* skip3.c, skip5.c .. skip8.c (:28-57): Skip Search on q-grams.  Every pattern q-gram is filed under its hash
  * (skip3: x[i]<<4 + x[i+1]<<2 + x[i+2]; skipQ, Q >= 5: sum x[i+k] << (Q-1-k)); the text is sampled every
  * m-Q+1 positions and each pattern offset filed under the sampled gram's hash is verified.  m < Q -> -1 (:31).
@@ -1245,6 +1280,7 @@ long long ora_search(const char *algo, const unsigned char *x, int m, const unsi
     if (!strncmp(algo, "qf", 2) && algo[2] && algo[3] && !algo[4])
         return ora_search_qf(x, m, y, n, algo[2] - '0', algo[3] - '0');
     if (!strncmp(algo, "skip", 4) && algo[4] >= '3' && algo[4] <= '8' && !algo[5]) return ora_search_skipq(x, m, y, n, algo[4] - '0');
+    if (!strcmp(algo, "zt")) return ora_search_zt(x, m, y, n);
     if (!strcmp(algo, "wfr")) return (size_t)m > n ? 0 : ora_search_wfr(x, m, y, n);
     if (!strncmp(algo, "wfrq", 4) && algo[4] >= '2' && algo[4] <= '8' && !algo[5]) return ora_search_wfrq(x, m, y, n, algo[4] - '0');
     return ora_search_tier2(algo, x, m, y, n);

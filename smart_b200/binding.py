@@ -116,6 +116,7 @@ class Tables(C.Structure):
         ("qfB", C.c_int * (1 << 18)),
         ("wfrQ", C.c_int),
         ("wfrF", C.c_ubyte * 65536),
+        ("ztBc", C.c_int * 65536),
     ]
 
 

@@ -461,6 +461,16 @@ void sb_prep_qf(const unsigned char *x, int m, int Q, int S, int *B)
     }
 }
 
+/* Zhu-Takaoka two-character shift (zt.c:64-74), row-major [a][b]: how far the window may move when its last two
+ * characters are a, b: m if the pair does not occur (m-1 if b is the first pattern character), else the distance
+ * of the pair's rightmost occurrence that ends before the last pattern character from the window end. */
+void sb_prep_ztbc(const unsigned char *x, int m, int *ztBc)
+{
+    for (int i = 0; i < 65536; i++) ztBc[i] = m;
+    for (int a = 0; a < 256; a++) ztBc[a * 256 + x[0]] = m - 1;
+    for (int i = 1; i < m - 1; i++) ztBc[x[i - 1] * 256 + x[i]] = m - 1 - i;
+}
+
 /* Weak-factor-recognition table (wfr.c:41-58, wfrq4.c:50-65): F[h] = 1 for the 16-bit hash h of every pattern
  * factor the scan can ask about.  The hash is built right to left, as the scan reads the window.
  * Q <= 1 (wfr, wfr2..8, twfr*, lwfr*): every factor x[j..i] of at most 16 characters, h <- (h << 2) + x[j].
@@ -585,6 +595,7 @@ int sb_prep_tables(int algo, const unsigned char *x, int m, sb_tables *out)
         else if (!strcmp(d->name, "zt")) {                                   /* zt.c suffixes/preBmGs == bm.c:36-66 */
             sb_prep_suffixes(x, m, out->suff);
             sb_prep_bmgs(x, m, out->suff, out->bmGs);
+            sb_prep_ztbc(x, m, out->ztBc);                                   /* zt.c:64-74 */
         }
         break;
     default: break; /* the other second-batch families expose no tables yet */

@@ -81,6 +81,7 @@ void sb_prep_hashq(const unsigned char *x, int m, int q, int *shift, int *sh1);
 void sb_prep_kr(const unsigned char *x, int m, int *d, int *hx);
 void sb_prep_qf(const unsigned char *x, int m, int Q, int S, int *B);
 void sb_prep_wfr(const unsigned char *x, int m, int Q, unsigned char *F);
+void sb_prep_ztbc(const unsigned char *x, int m, int *ztBc);
 
 #ifdef __cplusplus
 }

@@ -120,6 +120,8 @@ class Oracle:
             t = ia(65536); L.ora_pre_brbc(_ptr(x), m, _ptr(t)); return t
         if name == "acEll":
             return int(L.ora_pre_ac_ell(_ptr(x), m))
+        if name == "ztBc":
+            t = ia(65536); L.ora_pre_ztbc(_ptr(x), m, _ptr(t)); return t
         if name == "wfr":
             t = np.zeros(65536, dtype=np.uint8); L.ora_pre_wfr(_ptr(x), m, int(kw.get("Q", 0)), _ptr(t)); return t
         if name == "qf":

@@ -55,6 +55,9 @@ def test_tables_vs_reference_dump(table_cases, oracle):
         assert arr(sb.prep_tables("qlqs", x).qsBc, 256) == ent["qsBc"]
         t = sb.prep_tables("zt", x)
         assert arr(t.suff, m) == ent["suff"] and arr(t.bmGs, m) == ent["bmGs"]
+        zt = np.ctypeslib.as_array(t.ztBc).astype(np.int32)
+        assert hashlib.sha1(zt.tobytes()).hexdigest() == ent["ztBc_sha1"]
+        assert hashlib.sha1(oracle.table("ztBc", x).astype(np.int32).tobytes()).hexdigest() == ent["ztBc_sha1"]
         if m >= 4:
             assert arr(sb.prep_tables("lwfr4", x).kmpNext, m + 1) == ent["kmpNext"]
         tsw = np.ctypeslib.as_array(sb.prep_tables("tsw", x).brBc).astype(np.int32)
