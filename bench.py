@@ -1,13 +1,20 @@
 #!/usr/bin/env python
 """bench.py — text GB/s scanned (HBM-resident) on B200, the metric of BASELINE.json.
 
-Workload (BASELINE.json configs[2], the "1xB200 roofline run"): a synthetic uniform sigma=256 text of
+Headline workload (BASELINE.json configs[2], the "1xB200 roofline run"): a synthetic uniform sigma=256 text of
 4 GiB PER GPU, resident in HBM, generated on the device by the counter-based generator (textgen-style raw
 byte values); one STEP = one pass of the search hot path for every (algorithm, m) in
-{bf, kmp, hor, so} x {4, 16, 64, 256} = 16 searches = 64 GiB of text scanned per GPU per step.  Patterns are
-cut out of the text at seeded offsets (so every search must find >= 1 occurrence, smart.c:148-158,330).
-With N GPUs (one process per GPU under torchrun) the global text is N x 4 GiB, sharded with an m-1 halo;
-per-part counts are summed; there is no collective on the data path ("scaling": "weak").
+{bf, kmp, hor, so} x {4, 16, 64, 256} = 16 searches = 64 GiB of text scanned per GPU per step, submitted
+asynchronously (sb_search64_submit) and collected at the end of the step.  Patterns are cut out of the text at
+seeded offsets (so every search must find >= 1 occurrence, smart.c:148-158,330).  With N GPUs (one process per
+GPU under torchrun) the global text is N x 4 GiB, sharded with an m-1 halo; per-part counts are summed; there is
+no collective on the data path ("scaling": "weak").
+
+Second leg on the same JSON line, `config4` (BASELINE.json configs[3], the north-star multi-GPU shape): ONE
+64 GiB sigma=4 text, 64/N GiB per rank, m in {8, 64, 1024}, STRONG scaling (same text at every N), byte kernels
+(SB_FLAG_NO_PACK|SB_FLAG_NO_SKIP: the read-once roofline) and default kernels reported separately, time = max
+over ranks, counts summed over ranks; plus `config4.inprocess`: the same text through the single-box partitioner
+(sb_text_generate over devices 0..N-1 in ONE process, rank 0) with its counts checked against the per-rank sums.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
   python bench.py --impl reference [...]                          the reference's own CPU search() (oracle/_ref)
@@ -15,7 +22,8 @@ per-part counts are summed; there is no collective on the data path ("scaling": 
 Prints ONE JSON line (rank 0).  `value` is timed with the text already in HBM; `e2e` runs the same searches
 through the host-buffer entry the legacy plugins use (sb_search_host), host->device copy of the text inside
 the timed region; `roofline` is the dominant scan kernel against the measured HBM bandwidth;
-`cpu_baseline` is the reference's search() of the same algorithms on this box's host cores.
+`cpu_baseline` is the reference's search() of the same algorithms on this box's host cores, with the
+reference's fastest CPU code (EPSM, SSE4.2) beside it as `cpu_baseline.best`.
 """
 from __future__ import annotations
 
@@ -61,18 +69,21 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample-mib", type=int, default=128)
     ap.add_argument("--flags", type=int, default=0, help="SB_FLAG_* tuning overrides passed to every search")
+    ap.add_argument("--no-config4", action="store_true", help="skip the 64 GiB sigma=4 strong-scaling leg")
+    ap.add_argument("--c4-gib", type=float, default=64.0, help="total text size of the config4 leg")
+    ap.add_argument("--c4-reps", type=int, default=10)
     return ap.parse_args()
 
 
 def patterns_for(n_total, sigma, ms):
     """Same patterns on every rank: cut from the GLOBAL text via the host mirror of the generator."""
-    import smart_b200 as sb
+    import oracle_lib
 
     rng = np.random.default_rng(SEED)
     pats = {}
     for m in ms:
         off = int(rng.integers(0, n_total - m))
-        pats[m] = sb.textgen_host(off, m, sigma, SEED)
+        pats[m] = oracle_lib.textgen_np(off, m, sigma, SEED)
     return pats
 
 
@@ -168,12 +179,12 @@ def _cpu_worker(job):
 
 def cpu_reference_setup(sample_bytes, sigma, ms, cores, n_total):
     """Text sample = first `sample_bytes` of the workload text, cut into one chunk per core with an
-    (max m)-1 overlap so the chunks can be searched independently."""
+    (max m)-1 overlap so the chunks can be searched independently.  Built with the numpy
+    mirror of the generator: nothing on the CPU legs loads libsmartb200.so."""
     import oracle_lib
-    import smart_b200 as sb
 
-    y = sb.textgen_host(0, sample_bytes, sigma, SEED)
-    pats = {m: sb.textgen_host(1000 + 7 * m, m, sigma, SEED) for m in ms}  # cut from inside the sample
+    y = oracle_lib.textgen_np(0, sample_bytes, sigma, SEED)
+    pats = {m: oracle_lib.textgen_np(1000 + 7 * m, m, sigma, SEED) for m in ms}  # cut from inside the sample
     mmax = max(ms)
     per = (sample_bytes + cores - 1) // cores
     chunks = []
@@ -182,40 +193,56 @@ def cpu_reference_setup(sample_bytes, sigma, ms, cores, n_total):
         hi = min(sample_bytes, lo + per + mmax - 1)
         if lo >= sample_bytes:
             break
-        buf = np.zeros(hi - lo + oracle_lib.RefAlgo.SLACK, dtype=np.uint8)
+        buf = np.zeros(hi - lo + oracle_lib.RefAlgo.SLACK, dtype=np.uint8)  # calloc: 16-byte aligned (epsm.c reads __m128i)
         buf[: hi - lo] = y[lo:hi]
         chunks.append((buf, hi - lo))
     _CPU.update(refs={}, chunks=chunks, pats=pats, kind="reference" if oracle_lib.ref_available() else "port")
     return len(chunks)
 
 
-def cpu_reference_step(pool, algos, ms, nchunks):
+def cpu_reference_step(pool, algos, ms, nchunks, must_find=True):
     """One step of the workload on the CPU sample; returns seconds."""
     t0 = time.perf_counter()
     for a in algos:
         for m in ms:
             res = pool.map(_cpu_worker, [(a, ci, m) for ci in range(nchunks)])
-            if any(r == 0 for r in res) and sum(res) == 0:
+            if must_find and sum(res) == 0:
                 raise RuntimeError(f"reference {a} found no occurrence of a text-extracted pattern (m={m})")
     return time.perf_counter() - t0
 
 
-def run_cpu_reference(args, algos, ms, steps, warmup, n_total):
+def run_cpu_reference(args, algos, ms, steps, warmup, n_total, with_best=True):
     import multiprocessing as mp
+
+    import oracle_lib
 
     cores = len(os.sched_getaffinity(0))
     sample = args.cpu_sample_mib << 20
     nchunks = cpu_reference_setup(sample, args.sigma, ms, cores, n_total)
     ctx = mp.get_context("fork")
+    best = None
     with ctx.Pool(processes=nchunks) as pool:
         for _ in range(warmup):
             cpu_reference_step(pool, algos, ms, nchunks)
         t = 0.0
         for _ in range(steps):
             t += cpu_reference_step(pool, algos, ms, nchunks)
+        # the reference's fastest CPU code on the same sample and lengths (SURVEY.md section 8 row a9): EPSM,
+        # SSE4.2 (epsm.c:341-419, search16 :225-338).  A speed baseline only: for m >= 16 it misses an occurrence
+        # that ends on the last text byte (epsm.c:330), so its count is not checked.
+        if with_best and _CPU["kind"] == "reference" and oracle_lib.ref_available("epsm"):
+            try:
+                cpu_reference_step(pool, ["epsm"], ms, nchunks, must_find=False)
+                tb = cpu_reference_step(pool, ["epsm"], ms, nchunks, must_find=False)
+                best = {"algo": "epsm", "value": sample * len(ms) / tb / 1e9, "unit": UNIT, "cores": nchunks,
+                        "m": list(ms), "seconds": tb,
+                        "note": "reference src/algos/epsm.c (SSE4.2), same sample, one search per m; speed only "
+                                "(drops an occurrence ending on the last text byte for m >= 16, epsm.c:330)"}
+            except Exception as e:  # reported, never required
+                best = {"algo": "epsm", "value": None, "error": repr(e)}
     bytes_per_step = sample * len(algos) * len(ms)
     gbs = bytes_per_step * steps / t / 1e9
-    return {"value": gbs, "unit": UNIT, "cores": nchunks, "kind": _CPU["kind"],
+    return {"value": gbs, "unit": UNIT, "cores": nchunks, "kind": _CPU["kind"], "best": best,
             "sample": f"first {args.cpu_sample_mib} MiB of the workload text, {len(algos)}x{len(ms)} searches per step "
                       f"({','.join(algos)} x m={','.join(map(str, ms))}), one chunk per core with m-1 overlap, "
                       + ("reference search() compiled -O3 -msse4 (oracle/_ref)" if _CPU["kind"] == "reference"
@@ -237,7 +264,7 @@ def main_reference(args, algos, ms):
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(args, algos, ms, n_total),
         "cpu_baseline": {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"],
-                         "sample": cb["sample"]},
+                         "sample": cb["sample"], "best": cb["best"]},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -266,6 +293,7 @@ def main_ours(args, algos, ms):
     torch.cuda.set_device(info.local_rank)
     device = f"cuda:{info.local_rank}"
     dist = ranks.init_process_group("nccl")
+    cpu_group = ranks.cpu_group(dist)  # host-side barrier for the legs where only rank 0 works
     world = info.world
     if world != args.gpus and info.rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
@@ -277,18 +305,19 @@ def main_ours(args, algos, ms):
     pats = patterns_for(n_total, args.sigma, ms)
 
     def step():
+        """all searches of the step are submitted before the first result is waited for"""
+        tickets = [sb.submit(a, text, pats[m], flags=args.flags) for a in algos for m in ms]
         cnt, kms, launches = 0, {}, 0
-        for a in algos:
-            for m in ms:
-                r = sb.search(a, text, pats[m], flags=args.flags)
-                if r.count < 0:
-                    raise RuntimeError(f"{a} not applicable to m={m}")
-                tm = sb.last_timing()
-                cnt += r.count
-                launches += tm.kernels_launched
-                k = kms.setdefault(tm.filter_kind, [0.0, 0])
-                k[0] += tm.kernel_ms
-                k[1] += tm.kernels_launched
+        for tk in tickets:
+            r = sb.collect(tk)
+            if r.count < 0:
+                raise RuntimeError("algorithm not applicable to a bench pattern length")
+            tm = sb.last_timing()
+            cnt += r.count
+            launches += tm.kernels_launched
+            k = kms.setdefault(tm.filter_kind, [0.0, 0])
+            k[0] += tm.kernel_ms
+            k[1] += tm.kernels_launched
         return cnt, kms, launches
 
     for _ in range(max(args.warmup, 3)):
@@ -353,10 +382,12 @@ def main_ours(args, algos, ms):
     # ---- (f)-3 extra: the driver's real shape, 500 patterns of one length, counted in ONE pass
     multi = None
     try:
+        import oracle_lib
+
         mp = 16
         rngp = np.random.default_rng(SEED + 1)
         offs = rngp.integers(0, n_total - mp, 500)
-        pats500 = np.stack([sb.textgen_host(int(o), mp, args.sigma, SEED) for o in offs])
+        pats500 = np.stack([oracle_lib.textgen_np(int(o), mp, args.sigma, SEED) for o in offs])
         sb.search_multi("bf", text, pats500)
         ranks.barrier(dist, device)
         tm0 = time.perf_counter()
@@ -395,15 +426,27 @@ def main_ours(args, algos, ms):
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(sb, ranks, dist, device, text, base, own, n_total, pats, algos, ms, args)
+    text.free()
 
-    # ---- CPU baseline (rank 0, N=1 only): reference search() on this box's host cores
+    # ---- config4: ONE 64 GiB sigma=4 text, strong scaling (BASELINE.json configs[3])
+    config4 = None
+    if not args.no_config4:
+        try:
+            config4 = run_config4(sb, ranks, dist, cpu_group, device, info, world, args)
+        except Exception as e:  # reported on the line, never silently dropped
+            config4 = {"error": repr(e)}
+
+    # ---- CPU baseline (rank 0, at every N): reference search() on this box's host cores; the other ranks wait
+    # on the host-side barrier (no GPU kernel spins meanwhile)
     cpu = None
-    if info.rank == 0 and world == 1 and not args.no_cpu:
+    if info.rank == 0 and not args.no_cpu:
         try:
             cb = run_cpu_reference(args, algos, ms, 1, 0, n_total)
-            cpu = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
+            cpu = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"],
+                   "best": cb["best"]}
         except Exception as e:  # the baseline is reported, never required
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+    ranks.host_barrier(cpu_group)
 
     if info.rank == 0:
         line = {
@@ -416,15 +459,101 @@ def main_ours(args, algos, ms):
             "value_kernels_only": bytes_per_step_rank * args.steps / (max_kernel_ms * 1e-3) / 1e9 * world,
             "value_host_clock": bytes_per_step * args.steps / (max_host_ms * 1e-3) / 1e9,
             "per_m": per_m_rates, "occurrences_per_step": sum_cnt // args.steps, "multi_pattern": multi,
+            "config4": config4,
             "timing": "CUDA events on the library's launching stream bracketing the K timed steps (between "
-                      "barrier+synchronize pairs), max over ranks; value_host_clock = same region by the host clock; "
-                      "value_kernels_only = sum of per-kernel event times",
+                      "barrier+synchronize pairs), max over ranks; every step submits its 16 searches asynchronously "
+                      "and collects them (sb_search64_submit / sb_search_collect); value_host_clock = same region by "
+                      "the host clock; value_kernels_only = sum of per-kernel event times",
         }
         print_json(line)
-    text.free()
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+C4_SEED = 64
+
+
+def run_config4(sb, ranks, dist, cpu_group, device, info, world, args):
+    """BASELINE.json configs[3]: ONE sigma=4 text of --c4-gib GiB (default 64), part r of N on rank r (m-1 halo),
+    m in {8, 64, 1024}; strong scaling: the text is the same at every N.  Every (mode, algorithm, m) is timed as
+    --c4-reps scans submitted back to back (CUDA events on the scan stream, max over ranks)."""
+    import torch
+
+    import oracle_lib
+
+    n = int(args.c4_gib * GIB)
+    sigma, ms4, reps = 4, (8, 64, 1024), max(1, args.c4_reps)
+    pats = {m: oracle_lib.textgen_np(n // 2 - m // 2, m, sigma, C4_SEED) for m in ms4}  # straddle a seam for even N
+    modes = (("byte_kernels", sb.FLAG_NO_PACK | sb.FLAG_NO_SKIP), ("default", 0))
+    combos = [(mode, fl, a, m) for mode, fl in modes for a in ("bf", "hor") for m in ms4]
+    peak, _ = measured_peak()
+
+    t0 = time.perf_counter()
+    text = sb.Text.generate_part(n, sigma, C4_SEED, world, info.rank, info.local_rank)
+    gen_s = time.perf_counter() - t0
+    results, counts = [], {}
+    try:
+        for mode, fl, a, m in combos:
+            sb.search(a, text, pats[m], flags=fl)  # warm-up (plan and aux block cached, clocks up)
+            ranks.barrier(dist, device)
+            torch.cuda.synchronize()
+            sb.stream_timer_begin(info.local_rank)
+            tickets = [sb.submit(a, text, pats[m], flags=fl) for _ in range(reps)]
+            got = [sb.collect(tk) for tk in tickets]
+            tm = sb.last_timing()
+            ev_ms = sb.stream_timer_end_ms(info.local_rank)
+            if len({r.count for r in got}) != 1:
+                raise RuntimeError(f"config4: repeated scans disagree ({a}, m={m})")
+            cnt, max_ms, max_k = ranks.reduce_step(dist, device, got[0].count, ev_ms, float(np.median([r.run_ms for r in got])))
+            counts.setdefault(m, set()).add(cnt)
+            gbs = n * reps / (max_ms * 1e-3) / 1e9
+            results.append({"mode": mode, "algo": a, "m": m, "count": cnt, "ms_per_scan": max_ms / reps,
+                            "kernel_ms_median_max_over_ranks": max_k, "text_GBps": gbs,
+                            "frac_of_measured_hbm": gbs / (peak * world), "frac_of_nominal_8TBps": gbs / (8000.0 * world),
+                            "kernel": FILTER_NAMES.get(tm.filter_kind, str(tm.filter_kind))})
+    finally:
+        text.free()
+    for m, cs in counts.items():
+        if len(cs) != 1 or min(cs) < 1:
+            raise RuntimeError(f"config4: modes/algorithms disagree on the count for m={m}: {cs}")
+
+    # ---- the same text through the in-process partitioner, one process driving all N devices (rank 0)
+    ranks.host_barrier(cpu_group)  # every rank has freed its part
+    inproc = None
+    if info.rank == 0:
+        try:
+            t0 = time.perf_counter()
+            with sb.Text.generate(n, sigma, C4_SEED, devices=list(range(world))) as whole:
+                gen2_s = time.perf_counter() - t0
+                rows = []
+                for mode, fl, a, m in combos:
+                    sb.search(a, whole, pats[m], flags=fl)
+                    t1 = time.perf_counter()
+                    tickets = [sb.submit(a, whole, pats[m], flags=fl) for _ in range(reps)]
+                    got = [sb.collect(tk) for tk in tickets]
+                    wall = time.perf_counter() - t1
+                    rows.append({"mode": mode, "algo": a, "m": m, "count": got[0].count,
+                                 "same_as_per_rank_sum": {got[0].count} == counts[m],
+                                 "wall_ms_per_scan": wall * 1e3 / reps,
+                                 "kernel_ms_max_over_devices_median": float(np.median([r.run_ms for r in got])),
+                                 "text_GBps_wall": n * reps / wall / 1e9})
+                inproc = {"shards": whole.shards, "text_generation_s": round(gen2_s, 3), "results": rows,
+                          "api": "sb_text_generate(devices=0..N-1) + sb_search64_submit/collect in ONE process: "
+                                 "one scan stream per device, per-shard counts summed on the host"}
+                if not all(r["same_as_per_rank_sum"] for r in rows):
+                    raise RuntimeError("config4: in-process partitioner and per-rank parts disagree")
+        except Exception as e:
+            inproc = {"error": repr(e)}
+    ranks.host_barrier(cpu_group)
+    return {"workload": f"BASELINE configs[3]: ONE synthetic uniform rand{sigma} text of {args.c4_gib:g} GiB, "
+                        f"{args.c4_gib / world:g} GiB per GPU with an m-1 halo, m in {{8,64,1024}}, bf and hor",
+            "scaling": "strong", "n_gpus": world, "text_bytes_total": n, "seed": C4_SEED, "reps": reps,
+            "text_generation_s": round(gen_s, 3),
+            "modes": {"byte_kernels": "SB_FLAG_NO_PACK|SB_FLAG_NO_SKIP: every text byte is read once (the HBM "
+                                      "roofline applies)",
+                      "default": "the library's own choice (2-bit packed copy / sampling kernels: less than n bytes read)"},
+            "results": results, "inprocess": inproc}
 
 
 def run_e2e(sb, ranks, dist, device, text, base, own, n_total, pats, algos, ms, args):
@@ -470,13 +599,14 @@ def run_e2e(sb, ranks, dist, device, text, base, own, n_total, pats, algos, ms, 
         pin.free()
 
 
-def ensure_built():
+def ensure_built(impl):
     """Binaries are git-ignored; a fresh checkout builds them (nvcc/gcc are in the image). Not a fallback:
-    a failed build stops the bench."""
-    import smart_b200
+    a failed build stops the bench.  The reference arm needs (and loads) only the checker under oracle/."""
+    if impl != "reference":
+        import smart_b200
 
-    if not os.path.exists(smart_b200.library_path()):
-        smart_b200.build_library()
+        if not os.path.exists(smart_b200.library_path()):
+            smart_b200.build_library()
     if not os.path.exists(os.path.join(ROOT, "oracle", "libsmart_oracle.so")):
         subprocess.run(["make", "-j8", "-C", os.path.join(ROOT, "oracle"), "oracle", "ref"], check=True, capture_output=True)
 
@@ -493,8 +623,8 @@ def main():
     global print_json
     print_json = lambda obj: os.write(real_stdout, (json.dumps(obj) + "\n").encode())
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
-        ensure_built()
-    else:  # the other ranks wait for local rank 0's build (normally the prebuilt library is already there)
+        ensure_built(args.impl)
+    elif args.impl != "reference":  # the other ranks wait for local rank 0's build (normally it is prebuilt)
         import smart_b200
 
         for _ in range(600):

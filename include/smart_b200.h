@@ -15,8 +15,8 @@
  *   XSIZE/SIGMA/WSIZE/WORD (define.h:25-32)           SB_XSIZE/SB_SIGMA/SB_WSIZE/SB_WORD
  *   getText() text buffer in shm (smart.c:95-138)     sb_text (device-resident, possibly sharded)
  *   textgen (textgen.c:34-54)                         sb_text_generate / sb_textgen_host
- *   preKmp/preMp/Pre_Horspool/preBmBc/preBmGs/        sb_prep_* table builders (bit-identical tables,
- *     preQsBc/preSo/preSA + inline HASHq/KR/QF tables   built once per pattern, uploaded to the device)
+ *   preKmp/preMp/Pre_Horspool/preBmBc/preBmGs/        sb_prep_tables: stand-alone builders of bit-identical
+ *     preQsBc/preSo/preSA + inline HASHq/KR/QF tables   tables (an ABI and parity artefact, see below)
  *
  * Counting semantics are those of src/algos/bf.c:33-36: the number of (overlapping)
  * start positions j in [0, n-m] with x[0..m) == y[j..j+m).  A return of -1 means
@@ -131,6 +131,18 @@ void sb_host_free(void *p);
 long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m, unsigned flags,
                       unsigned long long *positions, size_t cap, double *pre_ms, double *run_ms);
 
+/* Asynchronous form of the count-only search: the shape of the driver's loop (smart.c:312-345) is MANY searches
+ * over one resident text, so the hot path must not wait for each 32-byte result before launching the next scan.
+ * sb_search64_submit enqueues the search (pattern upload, one scan kernel per shard, count read-back — each on
+ * its own stream so the scan stream carries kernels back to back) and returns a ticket >= 0, or an SB_ERR_* code;
+ * up to 256 tickets may be outstanding.  sb_search_collect waits for ONE ticket (in any order), frees it and
+ * returns what sb_search64 would have returned (count, SB_NOT_APPLICABLE, SB_ERR_*); *pre_ms = host preprocessing
+ * + enqueue time, *run_ms = CUDA-event time of the ticket's scan kernels (max over devices; wall time has no
+ * meaning for a pipelined search).  SB_FLAG_POSITIONS is not accepted here (position output is a blocking call).
+ * The pattern bytes are copied at submit time: x may be reused as soon as submit returns. */
+long long sb_search64_submit(int algo, const sb_text *t, const unsigned char *x, int m, unsigned flags);
+long long sb_search_collect(long long ticket, double *pre_ms, double *run_ms);
+
 /* Multi-pattern entry: count `npat` patterns of the SAME length m (stored back
  * to back, npat*m bytes) in ONE pass over the resident text instead of npat passes — the shape of the driver's
  * inner loop (smart.c:312: 500 patterns per length).  counts[p] receives the occurrence count of pattern p;
@@ -172,7 +184,12 @@ long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned
 int sb_plugin_search(int algo, unsigned char *x, int m, unsigned char *y, int n, double *pre_ms,
                      double *run_ms);
 
-/* ---- pattern preprocessing stage (tables bit-identical to the reference's) ---- */
+/* ---- pattern preprocessing stage (tables bit-identical to the reference's) ----
+ * sb_prep_tables is a stand-alone entry point: the search calls do NOT run it.  What a search preprocesses and
+ * places on the device is its scan plan: the pattern words, the candidate fingerprints of the scan direction of
+ * the algorithm (kernel parameter block = constant bank), the pattern's period from the border table (mp.c:26-35)
+ * and, for the sampling kernels, a Bloom bitmap + exact q-gram table (shared memory / L2) — cached per pattern.
+ */
 typedef struct sb_tables {
     int m;
     int mpNext[SB_XSIZE + 1];   /* mp.c:26-35 */
@@ -202,7 +219,9 @@ typedef struct sb_tables {
     unsigned char wfrF[65536];  /* wfr.c:41-58, wfrq4.c:50-65: weak-factor table, 1 = some factor hashes here */
     int ztBc[SB_SIGMA * SB_SIGMA]; /* zt.c:64-74, row-major [a][b]; filled for zt only */
 } sb_tables;
-/* Build every table the algorithm family of `algo` uses (others are left zeroed).
+/* Build every table the algorithm family of `algo` uses.  The other small tables and all scalars (qfQ, qfS, wfrQ,
+ * hashQ, ...) are zeroed; the four big arrays (brBc, qfB, wfrF, ztBc) are written only for the families that use
+ * them and are otherwise left as the caller passed them.
  * Returns 0, or -1 when the algorithm is not applicable to m (same rule as sb_search64). */
 int sb_prep_tables(int algo, const unsigned char *x, int m, sb_tables *out);
 

@@ -150,6 +150,8 @@ SYMBOLS = [
     ("sb_host_free", None, [C.c_void_p]),
     ("sb_search64", C.c_longlong, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_void_p, C.c_size_t,
                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    ("sb_search64_submit", C.c_longlong, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint]),
+    ("sb_search_collect", C.c_longlong, [C.c_longlong, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("sb_search_multi64", C.c_longlong, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p,
                                          C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("sb_last_timing", None, [C.POINTER(Timing)]),
@@ -345,6 +347,24 @@ def search(algo: str, text: Text, pattern, flags: int = 0, positions_cap: int = 
     if pos is not None:
         pos = pos[: max(0, min(int(r), positions_cap))]
     return SearchResult(int(r), pre.value, run.value, pos)
+
+
+def submit(algo: str, text: Text, pattern, flags: int = 0) -> int:
+    """sb_search64_submit: enqueue a count-only search, return its ticket (the pattern is copied at submit time)."""
+    ptr, m, keep = _as_bytes_ptr(pattern)
+    tk = lib().sb_search64_submit(algo_id(algo), text._h, ptr, m, flags)
+    if tk < 0:
+        raise SmartB200Error(f"sb_search64_submit failed ({tk}): {_err()}")
+    return int(tk)
+
+
+def collect(ticket: int) -> SearchResult:
+    """sb_search_collect: wait for one ticket; run_ms is the CUDA-event time of its scan kernels."""
+    pre, run = C.c_double(0), C.c_double(0)
+    r = lib().sb_search_collect(ticket, C.byref(pre), C.byref(run))
+    if r < -1:
+        raise SmartB200Error(f"sb_search_collect failed ({r}): {_err()}")
+    return SearchResult(int(r), pre.value, run.value)
 
 
 def search_multi(algo: str, text: Text, patterns, flags: int = 0):

@@ -65,17 +65,40 @@ constexpr int kFilterPacked = 300;             // + K (301, 302, 304, 308): scan
 constexpr int kFilterSkip = 100;              // + gram bytes (108, 116, 132): scan_skip<G>
 constexpr size_t kAuxWords = sb::kBloomWords + 2 * sb::kSkipTableSize;
 
+constexpr int kTickets = 256;                 // outstanding asynchronous searches (sb_search64_submit)
+constexpr int kSyncSlot = kTickets;           // pattern/counter slot of the blocking paths (positions, host text, multi)
+constexpr int kAuxSlots = 8;                  // cached Bloom/table blocks per device
+
+/* One cached aux block (Bloom bitmap + exact fingerprint table of a scan_skip / scan_packed plan).  The
+ * driver's algorithm loop searches the same pattern with many algorithms: the block is built and uploaded once. */
+struct AuxSlot {
+    uint32_t *d = nullptr, *h = nullptr;      // device block, pinned staging
+    cudaEvent_t staged = nullptr;             // fired once the H2D copy from h has run: h may be rewritten
+    cudaEvent_t last_use = nullptr;           // fired once the last kernel reading d has finished
+    bool used = false, valid = false;
+    bool half = false;                        // scan_packed_half layout (16-bit fingerprints index the bitmap)
+    unsigned long long stamp = 0;             // LRU clock
+    std::vector<uint32_t> list;               // the fingerprints the block was built from (cache key)
+};
+
 struct DevCtx {                               // per-device scratch, created on first use
     bool ready = false;
     int dev = -1;
     int sms = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t stream = nullptr;            // scan kernels
+    cudaStream_t ustream = nullptr;           // pattern / aux uploads of the asynchronous path (overlap the previous scan)
+    cudaStream_t dstream = nullptr;           // counter read-backs of the asynchronous path
+    cudaEvent_t e0 = nullptr, e1 = nullptr;   // blocking paths
     cudaEvent_t t0 = nullptr, t1 = nullptr;   // sb_stream_timer_*
-    uint32_t *d_pat = nullptr;                // pattern words
-    unsigned long long *d_counters = nullptr; // 4 x u64
-    unsigned long long *h_counters = nullptr; // pinned mirror
-    uint32_t *h_pat = nullptr;                // pinned staging for the pattern
+    // slot s of kTickets+1: pattern words, 4 x u64 counters (device + pinned mirrors); slot kSyncSlot belongs to
+    // the blocking paths.  The counters of the ticket slots are never zeroed: `prev` remembers what the slot
+    // held after its previous search and the result is the difference (no memset node per search).
+    uint32_t *d_pat = nullptr, *h_pat = nullptr;
+    unsigned long long *d_counters = nullptr, *h_counters = nullptr;
+    unsigned long long prev[kTickets + 1][4] = {{0}};
+    cudaEvent_t ev_up[kTickets] = {nullptr}, ev0[kTickets] = {nullptr}, ev1[kTickets] = {nullptr}, ev_done[kTickets] = {nullptr};
+    AuxSlot aux[kAuxSlots];
+    unsigned long long aux_clock = 0;
     unsigned long long *d_pos = nullptr;      // position sink, grown on demand
     unsigned long long *d_pos_alt = nullptr;  // radix-sort output (same capacity)
     size_t pos_cap = 0;
@@ -88,7 +111,6 @@ struct DevCtx {                               // per-device scratch, created on 
     int occ_window[24] = {0};                 // ... for scan_window<NW,OFF,DENSE>, index window_index()
     int occ_swar[8] = {0};                    // ... for scan_swar<M, DENSE>, index (M-1)*2 + DENSE
     unsigned long long *d_hist = nullptr;     // 256-bin byte histogram scratch
-    uint32_t *d_aux = nullptr, *h_aux = nullptr; // scan_skip / scan_multi: Bloom bitmap + exact fingerprint table
     uint32_t *d_mpat = nullptr;               // scan_multi: pattern set (words), grown on demand
     size_t mpat_words = 0;
     unsigned long long *d_mcounts = nullptr;  // scan_multi: per-pattern counts
@@ -99,6 +121,11 @@ struct DevCtx {                               // per-device scratch, created on 
     uint8_t *d_chunk[2] = {nullptr, nullptr};
     size_t chunk_cap = 0;
     cudaStream_t cstream[2] = {nullptr, nullptr};
+
+    uint32_t *pat_dev(int slot) const { return d_pat + (size_t)slot * (kPatBytes / 4); }
+    uint32_t *pat_host(int slot) const { return h_pat + (size_t)slot * (kPatBytes / 4); }
+    unsigned long long *cnt_dev(int slot) const { return d_counters + 4 * (size_t)slot; }
+    unsigned long long *cnt_host(int slot) const { return h_counters + 4 * (size_t)slot; }
 };
 
 DevCtx g_ctx[64];
@@ -144,19 +171,21 @@ DevCtx *get_ctx(int dev)
     if (const char *e = getenv("SMART_B200_L2_FETCH"))  // tuning: DRAM->L2 fetch granularity hint (32/64/128)
         cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
     CU_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), nullptr);
+    CU_TRY(cudaStreamCreateWithFlags(&c.ustream, cudaStreamNonBlocking), nullptr);
+    CU_TRY(cudaStreamCreateWithFlags(&c.dstream, cudaStreamNonBlocking), nullptr);
     CU_TRY(cudaStreamCreateWithFlags(&c.cstream[0], cudaStreamNonBlocking), nullptr);
     CU_TRY(cudaStreamCreateWithFlags(&c.cstream[1], cudaStreamNonBlocking), nullptr);
     CU_TRY(cudaEventCreate(&c.e0), nullptr);
     CU_TRY(cudaEventCreate(&c.e1), nullptr);
     CU_TRY(cudaEventCreate(&c.t0), nullptr);
     CU_TRY(cudaEventCreate(&c.t1), nullptr);
-    CU_TRY(cudaMalloc(&c.d_pat, kPatBytes), nullptr);
-    CU_TRY(cudaMalloc(&c.d_counters, 4 * sizeof(unsigned long long)), nullptr);
-    CU_TRY(cudaHostAlloc(&c.h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault), nullptr);
-    CU_TRY(cudaHostAlloc(&c.h_pat, kPatBytes, cudaHostAllocDefault), nullptr);
+    CU_TRY(cudaMalloc(&c.d_pat, (kTickets + 1) * kPatBytes), nullptr);
+    CU_TRY(cudaHostAlloc(&c.h_pat, (kTickets + 1) * kPatBytes, cudaHostAllocDefault), nullptr);
+    CU_TRY(cudaMalloc(&c.d_counters, (kTickets + 1) * 4 * sizeof(unsigned long long)), nullptr);
+    CU_TRY(cudaHostAlloc(&c.h_counters, (kTickets + 1) * 4 * sizeof(unsigned long long), cudaHostAllocDefault), nullptr);
+    CU_TRY(cudaMemset(c.d_counters, 0, (kTickets + 1) * 4 * sizeof(unsigned long long)), nullptr);
+    memset(c.h_pat, 0, (kTickets + 1) * kPatBytes);
     CU_TRY(cudaMalloc(&c.d_hist, 256 * sizeof(unsigned long long)), nullptr);
-    CU_TRY(cudaMalloc(&c.d_aux, kAuxWords * sizeof(uint32_t)), nullptr);
-    CU_TRY(cudaHostAlloc(&c.h_aux, kAuxWords * sizeof(uint32_t), cudaHostAllocDefault), nullptr);
     c.occ_skip[0] = occupancy(sb::scan_skip_kernel<8>);
     c.occ_skip[1] = occupancy(sb::scan_skip_kernel<16>);
     c.occ_skip[2] = occupancy(sb::scan_skip_kernel<32>);
@@ -514,7 +543,6 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
     const bool want_pos = a.pos != nullptr;
     if (pl.filter >= kFilterPacked) {
         if (!pl.packed_K) return cudaSuccess;  // pattern outside the text's alphabet: the count stays 0
-        a.aux = c.d_aux;
         const unsigned long long end = (unsigned long long)a.hi + a.anchor + a.stride + 31;  // characters that matter (upper bound)
         a.nsamples = (end + a.cpw - 1) / a.cpw;                                               // packed words
         a.ngroups = (a.nsamples * 4 + kGroupLong - 1) / kGroupLong;
@@ -541,7 +569,6 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
     }
     if (pl.filter >= kFilterSkip) {
         const int G = pl.filter - kFilterSkip;
-        a.aux = c.d_aux;
         a.nsamples = ((unsigned long long)a.hi + a.anchor + a.stride - 2) / a.stride + 1;
         const unsigned long long per_cta = 32ull * 8 * (sb::kThreads / 32);
         const unsigned long long want_ctas = (a.nsamples + per_cta - 1) / per_cta;
@@ -639,40 +666,146 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
     return cudaGetLastError();
 }
 
-/* stage the pattern words for upload */
-void stage_pattern(DevCtx &c, const unsigned char *x, int m)
+/* stage the pattern words of slot `slot` for upload; returns the bytes to copy (zero padded past m) */
+size_t stage_pattern(DevCtx &c, int slot, const unsigned char *x, int m)
 {
-    memset(c.h_pat, 0, kPatBytes);
-    memcpy(c.h_pat, x, (size_t)m);
+    const size_t bytes = round_up((size_t)m + 8, 16);
+    unsigned char *h = reinterpret_cast<unsigned char *>(c.pat_host(slot));
+    memcpy(h, x, (size_t)m);
+    memset(h + m, 0, bytes - (size_t)m);
+    return bytes;
 }
 
-/* Bloom bitmap + fingerprint list of a skip plan, staged in pinned memory; returns the bytes to upload */
-size_t stage_aux(DevCtx &c, const Plan &pl)
+/* Bloom bitmap + exact table {fingerprint, d+1} of a skip / packed plan, built in pinned memory */
+void build_aux(uint32_t *h, const uint32_t *list, int n, bool half)
 {
-    if (!pl.skip_grams) return 0;
-    memset(c.h_aux, 0, kAuxWords * sizeof(uint32_t));
-    uint32_t *table = c.h_aux + sb::kBloomWords;
-    for (int d = 0; d < pl.skip_grams; d++) {
-        if (pl.packed_half) {  // 16-bit fingerprints index the bitmap directly (scan_packed_half)
-            c.h_aux[pl.list[d] >> 5] |= 1u << (pl.list[d] & 31);
+    memset(h, 0, kAuxWords * sizeof(uint32_t));
+    uint32_t *table = h + sb::kBloomWords;
+    for (int d = 0; d < n; d++) {
+        if (half) {  // 16-bit fingerprints index the bitmap directly (scan_packed_half)
+            h[list[d] >> 5] |= 1u << (list[d] & 31);
         } else {
-            const uint32_t s1 = sb::bloom_slot(pl.list[d]), s2 = sb::bloom_slot2(pl.list[d]);
-            c.h_aux[s1 >> 5] |= 1u << (s1 & 31);
-            c.h_aux[s2 >> 5] |= 1u << (s2 & 31);
+            const uint32_t s1 = sb::bloom_slot(list[d]), s2 = sb::bloom_slot2(list[d]);
+            h[s1 >> 5] |= 1u << (s1 & 31);
+            h[s2 >> 5] |= 1u << (s2 & 31);
         }
-        uint32_t slot = sb::table_slot(pl.list[d]);
+        uint32_t slot = sb::table_slot(list[d]);
         while (table[2 * slot + 1]) slot = (slot + 1) & (sb::kSkipTableSize - 1);  // linear probing
-        table[2 * slot] = pl.list[d];
+        table[2 * slot] = list[d];
         table[2 * slot + 1] = (uint32_t)d + 1;
     }
-    return kAuxWords * sizeof(uint32_t);
 }
 
-sb_tables *tables_scratch()
+/* least recently used aux slot of a device, ready to be refilled: its pinned staging is no longer being read
+ * by a copy, and `up` (the stream that will overwrite the device block) waits for the last kernel reading it */
+AuxSlot *aux_evict(DevCtx &c, cudaStream_t up)
 {
-    static thread_local sb_tables *t = nullptr;
-    if (!t) t = (sb_tables *)calloc(1, sizeof(sb_tables));
-    return t;
+    AuxSlot *best = nullptr;
+    for (int i = 0; i < kAuxSlots; i++) {
+        AuxSlot &s = c.aux[i];
+        if (!s.used) {
+            best = &s;
+            break;
+        }
+        if (!best || s.stamp < best->stamp) best = &s;
+    }
+    AuxSlot &s = *best;
+    if (!s.used) {
+        if (cudaMalloc(&s.d, kAuxWords * sizeof(uint32_t)) != cudaSuccess ||
+            cudaHostAlloc(&s.h, kAuxWords * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.staged, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.last_use, cudaEventDisableTiming) != cudaSuccess) {
+            set_err("allocation of an aux block failed%s%s");
+            return nullptr;
+        }
+        s.used = true;
+    }
+    s.valid = false;
+    if (cudaEventSynchronize(s.staged) != cudaSuccess || cudaStreamWaitEvent(up, s.last_use, 0) != cudaSuccess) {
+        set_err("aux block synchronisation failed%s%s");
+        return nullptr;
+    }
+    s.stamp = ++c.aux_clock;
+    return &s;
+}
+
+/* device block with the aux data of plan `pl`: the cached one, or built and uploaded on `up` */
+AuxSlot *aux_acquire(DevCtx &c, const Plan &pl, cudaStream_t up)
+{
+    const bool half = pl.packed_half != 0;
+    for (int i = 0; i < kAuxSlots; i++) {
+        AuxSlot &s = c.aux[i];
+        if (s.valid && s.half == half && (int)s.list.size() == pl.skip_grams &&
+            memcmp(s.list.data(), pl.list, (size_t)pl.skip_grams * sizeof(uint32_t)) == 0) {
+            s.stamp = ++c.aux_clock;
+            return &s;
+        }
+    }
+    AuxSlot *s = aux_evict(c, up);
+    if (!s) return nullptr;
+    build_aux(s->h, pl.list, pl.skip_grams, half);
+    if (cudaMemcpyAsync(s->d, s->h, kAuxWords * sizeof(uint32_t), cudaMemcpyHostToDevice, up) != cudaSuccess ||
+        cudaEventRecord(s->staged, up) != cudaSuccess) {
+        set_err("aux block upload failed%s%s");
+        return nullptr;
+    }
+    s->list.assign(pl.list, pl.list + pl.skip_grams);
+    s->half = half;
+    s->valid = true;
+    return s;
+}
+
+/* Plans are cached per (scan direction, pattern, flags, text statistics): the driver's loop searches one pattern
+ * with every selected algorithm (smart.c:312-345), and all algorithms of one scan direction share a plan. */
+struct PlanEntry {
+    bool valid = false;
+    int anchor = 0, m = 0;
+    unsigned flags = 0;
+    double bits = 0;
+    PackInfo pack;
+    unsigned long long stamp = 0;
+    unsigned char x[SB_XSIZE];
+    Plan plan;
+};
+constexpr int kPlanCache = 8;
+PlanEntry *g_plans = nullptr;
+unsigned long long g_plan_clock = 0;
+std::mutex g_plan_mu;
+
+bool same_pack(const PackInfo &a, const PackInfo &b)
+{
+    return a.packed == b.packed && (!a.packed || (a.bits == b.bits && a.nsym == b.nsym && memcmp(a.sym, b.sym, sizeof a.sym) == 0));
+}
+
+void plan_get(Plan &out, const sb_algo_desc *desc, const unsigned char *x, int m, unsigned flags, double bits,
+              const PackInfo *pk)
+{
+    static const PackInfo none;
+    const PackInfo &pack = pk ? *pk : none;
+    flags &= ~SB_FLAG_POSITIONS;
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    if (!g_plans) g_plans = new PlanEntry[kPlanCache];
+    PlanEntry *lru = nullptr;  // an unused entry, else the least recently used one
+    for (int i = 0; i < kPlanCache; i++) {
+        PlanEntry &e = g_plans[i];
+        if (e.valid && e.anchor == desc->anchor && e.m == m && e.flags == flags && e.bits == bits && same_pack(e.pack, pack) &&
+            memcmp(e.x, x, (size_t)m) == 0) {
+            e.stamp = ++g_plan_clock;
+            out = e.plan;
+            return;
+        }
+        if (!lru || (lru->valid && (!e.valid || e.stamp < lru->stamp))) lru = &e;
+    }
+    make_plan(lru->plan, desc, x, m, flags, bits, pk);
+    lru->valid = true;
+    lru->anchor = desc->anchor;
+    lru->m = m;
+    lru->flags = flags;
+    lru->bits = bits;
+    lru->pack = pack;
+    memcpy(lru->x, x, (size_t)m);
+    lru->stamp = ++g_plan_clock;
+    out = lru->plan;
 }
 
 /* grow the position sink (and its sort buffer) of a device to at least `need` entries */
@@ -1084,6 +1217,214 @@ static bool outside_domain(const sb_algo_desc *d, int m, unsigned long long n)
     return m < d->min_m || (d->min_ratio > 0 && n / (unsigned long long)m < (unsigned long long)d->min_ratio);
 }
 
+/* ---- asynchronous searches: tickets ------------------------------------------------------------------
+ * A ticket owns slot `idx` (pattern buffer, counters, events) on every device of its text.  submit enqueues
+ *   ustream: pattern (+ aux block if not cached) H2D, event ev_up
+ *   stream : wait ev_up, ev0, one scan kernel per shard, ev1
+ *   dstream: wait ev1, counters D2H, ev_done
+ * and returns; collect waits for ev_done only.  The scan stream therefore carries nothing but kernels, back to
+ * back, while uploads and read-backs of neighbouring searches overlap them. */
+struct Ticket {
+    int state = 0;          // 0 free, 1 in flight, 2 finished at submit time (result in `immediate`)
+    long long immediate = 0;
+    int ndev = 0;
+    int devs[kMaxShards];
+    double prep_ms = 0, upload_ms = 0;
+    int launched = 0, filter_kind = 0;
+};
+static Ticket g_tickets[kTickets];
+static int g_ticket_cursor = 0;
+static std::mutex g_ticket_mu;
+
+static int ticket_alloc()
+{
+    std::lock_guard<std::mutex> lk(g_ticket_mu);
+    for (int i = 0; i < kTickets; i++) {
+        const int idx = (g_ticket_cursor + i) % kTickets;
+        if (g_tickets[idx].state == 0) {
+            g_tickets[idx] = Ticket();
+            g_tickets[idx].state = 1;
+            g_ticket_cursor = (idx + 1) % kTickets;
+            return idx;
+        }
+    }
+    return -1;
+}
+
+static void ticket_release(int idx)
+{
+    std::lock_guard<std::mutex> lk(g_ticket_mu);
+    g_tickets[idx].state = 0;
+}
+
+static bool ticket_events(DevCtx &c, int idx)
+{
+    if (c.ev_done[idx]) return true;
+    return cudaEventCreateWithFlags(&c.ev_up[idx], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreate(&c.ev0[idx]) == cudaSuccess && cudaEventCreate(&c.ev1[idx]) == cudaSuccess &&
+           cudaEventCreateWithFlags(&c.ev_done[idx], cudaEventDisableTiming) == cudaSuccess;
+}
+
+/* per-shard kernel arguments of a plan */
+static sb::ScanArgs shard_args(const Plan &pl, const sb_text *t, int g, int m)
+{
+    const Shard &s = t->sh[g];
+    sb::ScanArgs a = pl.args;
+    a.text = s.d_text;
+    a.packed = s.d_packed;
+    a.base = s.base;
+    long long hi = (long long)t->n - m + 1 - (long long)s.base;
+    if (hi > (long long)s.own) hi = (long long)s.own;
+    a.hi = hi > 0 ? hi : 0;
+    return a;
+}
+
+/* enqueue a count-only search; returns the ticket index or an SB_ERR_* code */
+static long long submit_core(const sb_algo_desc *desc, const sb_text *t, const unsigned char *x, int m, unsigned flags)
+{
+    const int idx = ticket_alloc();
+    if (idx < 0) {
+        set_err("too many outstanding searches: collect some tickets first%s%s");
+        return SB_ERR_ARG;
+    }
+    Ticket &tk = g_tickets[idx];
+    if (outside_domain(desc, m, t->n)) {
+        tk.state = 2;
+        tk.immediate = SB_NOT_APPLICABLE;
+        return idx;
+    }
+    /* ---- preprocessing stage: the plan (fingerprints, period, aux list) comes from the cache or is built ---- */
+    const double t0 = now_ms();
+    Plan pl;
+    plan_get(pl, desc, x, m, flags, t->bits, &t->pack);
+    const double t1 = now_ms();
+    tk.filter_kind = filter_kind_of(pl);
+    tk.prep_ms = t1 - t0;
+    if ((long long)t->n - m + 1 <= 0 || (pl.filter == kFilterPacked && !pl.packed_K)) {
+        tk.state = 2;  // pattern longer than the text, or with a byte the text does not contain: count 0
+        tk.immediate = 0;
+        return idx;
+    }
+#define SUBMIT_TRY(expr)                                                            \
+    do {                                                                            \
+        cudaError_t e_ = (expr);                                                    \
+        if (e_ != cudaSuccess) {                                                    \
+            set_err("CUDA error in %s: %s", #expr, cudaGetErrorString(e_));         \
+            ticket_release(idx);                                                    \
+            return SB_ERR_CUDA;                                                     \
+        }                                                                           \
+    } while (0)
+    for (int g = 0; g < t->nshards; g++) {
+        bool first = true;  // shards may share a device (tests): one slot, one upload, one read-back per DEVICE
+        for (int k = 0; k < g; k++) first = first && (t->sh[k].dev != t->sh[g].dev);
+        if (!first) continue;
+        DevCtx *c = get_ctx(t->sh[g].dev);
+        if (!c || !ticket_events(*c, idx)) {
+            ticket_release(idx);
+            return SB_ERR_CUDA;
+        }
+        const size_t pat_bytes = stage_pattern(*c, idx, x, m);
+        SUBMIT_TRY(cudaMemcpyAsync(c->pat_dev(idx), c->pat_host(idx), pat_bytes, cudaMemcpyHostToDevice, c->ustream));
+        AuxSlot *aux = nullptr;
+        if (pl.skip_grams) {
+            aux = aux_acquire(*c, pl, c->ustream);
+            if (!aux) {
+                ticket_release(idx);
+                return SB_ERR_CUDA;
+            }
+        }
+        SUBMIT_TRY(cudaEventRecord(c->ev_up[idx], c->ustream));
+        SUBMIT_TRY(cudaStreamWaitEvent(c->stream, c->ev_up[idx], 0));
+        SUBMIT_TRY(cudaEventRecord(c->ev0[idx], c->stream));
+        for (int k = g; k < t->nshards; k++) {
+            if (t->sh[k].dev != t->sh[g].dev) continue;
+            sb::ScanArgs a = shard_args(pl, t, k, m);
+            if (a.hi <= 0) continue;
+            a.pat = c->pat_dev(idx);
+            a.counters = c->cnt_dev(idx);
+            a.aux = aux ? aux->d : nullptr;
+            SUBMIT_TRY(launch_scan(*c, pl, a, c->stream));
+            tk.launched++;
+        }
+        if (aux) SUBMIT_TRY(cudaEventRecord(aux->last_use, c->stream));
+        SUBMIT_TRY(cudaEventRecord(c->ev1[idx], c->stream));
+        SUBMIT_TRY(cudaStreamWaitEvent(c->dstream, c->ev1[idx], 0));
+        SUBMIT_TRY(cudaMemcpyAsync(c->cnt_host(idx), c->cnt_dev(idx), 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                   c->dstream));
+        SUBMIT_TRY(cudaEventRecord(c->ev_done[idx], c->dstream));
+        tk.devs[tk.ndev++] = t->sh[g].dev;
+    }
+#undef SUBMIT_TRY
+    tk.upload_ms = now_ms() - t1;
+    return idx;
+}
+
+/* wait for a ticket; fills g_timing (kernel_ms = max over devices of the CUDA-event time of its kernels) */
+static long long collect_core(int idx)
+{
+    Ticket &tk = g_tickets[idx];
+    memset(&g_timing, 0, sizeof g_timing);
+    g_timing.prep_host_ms = tk.prep_ms;
+    g_timing.upload_ms = tk.upload_ms;
+    g_timing.filter_kind = tk.filter_kind;
+    g_timing.kernels_launched = tk.launched;
+    if (tk.state == 2) {
+        const long long r = tk.immediate;
+        ticket_release(idx);
+        return r;
+    }
+    unsigned long long total = 0, verified = 0;
+    double kernel_ms = 0;
+    long long err = 0;
+    for (int i = 0; i < tk.ndev; i++) {
+        DevCtx *c = get_ctx(tk.devs[i]);
+        cudaError_t e = c ? cudaEventSynchronize(c->ev_done[idx]) : cudaErrorUnknown;
+        float ms = 0;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, c->ev0[idx], c->ev1[idx]);
+        if (e != cudaSuccess) {
+            set_err("CUDA error while collecting a search: %s%s", cudaGetErrorString(e));
+            err = SB_ERR_CUDA;
+            continue;
+        }
+        kernel_ms = std::max(kernel_ms, (double)ms);
+        const unsigned long long *h = c->cnt_host(idx);
+        total += h[0] - c->prev[idx][0];
+        verified += h[2] - c->prev[idx][2];
+        for (int k = 0; k < 4; k++) c->prev[idx][k] = h[k];
+    }
+    g_timing.kernel_ms = kernel_ms;
+    g_timing.verified = verified;
+    ticket_release(idx);
+    return err ? err : (long long)total;
+}
+
+long long sb_search64_submit(int algo, const sb_text *t, const unsigned char *x, int m, unsigned flags)
+{
+    const sb_algo_desc *desc = sb_algo_desc_get(algo);
+    if (!desc || !t || !x || m < 1 || m > SB_XSIZE || (flags & SB_FLAG_POSITIONS)) {
+        set_err("bad argument to sb_search64_submit (algo/text/pattern/m, or SB_FLAG_POSITIONS)%s%s");
+        return SB_ERR_ARG;
+    }
+    return submit_core(desc, t, x, m, flags);
+}
+
+long long sb_search_collect(long long ticket, double *pre_ms, double *run_ms)
+{
+    if (pre_ms) *pre_ms = 0;
+    if (run_ms) *run_ms = 0;
+    if (ticket < 0 || ticket >= kTickets || g_tickets[ticket].state == 0) {
+        set_err("sb_search_collect: no such ticket%s%s");
+        return SB_ERR_ARG;
+    }
+    const long long r = collect_core((int)ticket);
+    if (pre_ms) *pre_ms = g_timing.prep_host_ms + g_timing.upload_ms;
+    if (run_ms) *run_ms = g_timing.kernel_ms > 0 ? g_timing.kernel_ms : 1e-6;
+    return r;
+}
+
+static long long search_positions(const sb_algo_desc *desc, const sb_text *t, const unsigned char *x, int m, unsigned flags,
+                                  unsigned long long *positions, size_t cap, double *pre_ms, double *run_ms);
+
 long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m, unsigned flags,
                       unsigned long long *positions, size_t cap, double *pre_ms, double *run_ms)
 {
@@ -1100,76 +1441,82 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
     memset(&g_timing, 0, sizeof g_timing);
     if (pre_ms) *pre_ms = 0;
     if (run_ms) *run_ms = 0;
-    if (outside_domain(desc, m, t->n)) return SB_NOT_APPLICABLE;
-
-    /* ---- preprocessing stage: tables + fingerprints on the host, then upload ---- */
+    if (want_pos && positions && cap > 0 && (long long)t->n - m + 1 > 0 && !outside_domain(desc, m, t->n))
+        return search_positions(desc, t, x, m, flags, positions, cap, pre_ms, run_ms);
+    /* count only: one submit, one collect */
     const double t0 = now_ms();
-    sb_tables *tab = tables_scratch();
-    if (!tab) return SB_ERR_NOMEM;
-    sb_prep_tables(algo, x, m, tab);
+    const long long idx = submit_core(desc, t, x, m, flags & ~SB_FLAG_POSITIONS);
+    if (idx < 0) return idx;
+    const double t2 = now_ms();
+    const long long r = collect_core((int)idx);
+    const double t3 = now_ms();
+    g_timing.wall_ms = t3 - t2;
+    if (r >= 0) {
+        if (pre_ms) *pre_ms = t2 - t0;
+        if (run_ms) *run_ms = (t3 - t2) > 0 ? (t3 - t2) : 1e-6;
+    }
+    return r;
+}
+
+/* Blocking search with position output: the min(count, cap) smallest positions, ascending. */
+static long long search_positions(const sb_algo_desc *desc, const sb_text *t, const unsigned char *x, int m, unsigned flags,
+                                  unsigned long long *positions, size_t cap, double *pre_ms, double *run_ms)
+{
+    const double t0 = now_ms();
     Plan pl;
-    make_plan(pl, desc, x, m, flags, t->bits, &t->pack);
+    plan_get(pl, desc, x, m, flags, t->bits, &t->pack);
     const double t1 = now_ms();
 
     DevCtx *ctx[kMaxShards];
+    AuxSlot *aux[kMaxShards] = {nullptr};
+    bool dev_first[kMaxShards];
     for (int g = 0; g < t->nshards; g++) {
         ctx[g] = get_ctx(t->sh[g].dev);
         if (!ctx[g]) return SB_ERR_CUDA;
-        // one pattern upload per DEVICE (shards may share a device in tests)
-        bool first = true;
-        for (int k = 0; k < g; k++) first = first && (t->sh[k].dev != t->sh[g].dev);
-        if (!first) continue;
-        stage_pattern(*ctx[g], x, m);
-        CU_TRY(cudaMemcpyAsync(ctx[g]->d_pat, ctx[g]->h_pat, round_up((size_t)m + 8, 16), cudaMemcpyHostToDevice,
-                               ctx[g]->stream),
+        dev_first[g] = true;
+        for (int k = 0; k < g; k++)
+            if (t->sh[k].dev == t->sh[g].dev) {
+                dev_first[g] = false;
+                aux[g] = aux[k];
+            }
+        if (!dev_first[g]) continue;
+        DevCtx &c = *ctx[g];
+        const size_t pat_bytes = stage_pattern(c, kSyncSlot, x, m);
+        CU_TRY(cudaMemcpyAsync(c.pat_dev(kSyncSlot), c.pat_host(kSyncSlot), pat_bytes, cudaMemcpyHostToDevice, c.stream),
                SB_ERR_CUDA);
-        if (const size_t aux_bytes = stage_aux(*ctx[g], pl))
-            CU_TRY(cudaMemcpyAsync(ctx[g]->d_aux, ctx[g]->h_aux, aux_bytes, cudaMemcpyHostToDevice, ctx[g]->stream),
-                   SB_ERR_CUDA);
-        CU_TRY(cudaMemsetAsync(ctx[g]->d_counters, 0, 4 * sizeof(unsigned long long), ctx[g]->stream), SB_ERR_CUDA);
+        if (pl.skip_grams) {
+            aux[g] = aux_acquire(c, pl, c.stream);
+            if (!aux[g]) return SB_ERR_CUDA;
+        }
+        CU_TRY(cudaMemsetAsync(c.cnt_dev(kSyncSlot), 0, 4 * sizeof(unsigned long long), c.stream), SB_ERR_CUDA);
     }
-    /* no synchronisation here: the uploads and the scan are ordered by the stream.  pre_ms therefore covers
-     * the table build and the enqueue of the uploads; the (few-KB) copies themselves overlap the launch. */
     const double t2 = now_ms();
 
-    /* ---- scan: one kernel per shard, all devices concurrently ---- */
     const long long total_starts = (long long)t->n - m + 1;
     int launched = 0;
-    bool dev_first[kMaxShards];
-    for (int g = 0; g < t->nshards; g++) {
-        dev_first[g] = true;
-        for (int k = 0; k < g; k++) dev_first[g] = dev_first[g] && (t->sh[k].dev != t->sh[g].dev);
-    }
-    // launch the scan of shard g; positions (global offsets, unsorted) go to the device's sink if asked
-    auto launch_shard = [&](int g, bool with_pos) -> cudaError_t {
-        const Shard &s = t->sh[g];
+    // launch the scan of shard g; positions (global offsets, unsorted) go to the device's sink
+    auto launch_shard = [&](int g) -> cudaError_t {
         DevCtx &c = *ctx[g];
-        sb::ScanArgs a = pl.args;
-        a.text = s.d_text;
-        a.packed = s.d_packed;
-        a.pat = c.d_pat;
-        a.counters = c.d_counters;
-        a.base = s.base;
-        long long hi = total_starts - (long long)s.base;
-        if (hi > (long long)s.own) hi = (long long)s.own;
-        a.hi = hi > 0 ? hi : 0;
-        a.pos = with_pos ? c.d_pos : nullptr;
-        a.pos_cap = with_pos ? c.pos_cap : 0;
+        sb::ScanArgs a = shard_args(pl, t, g, m);
+        a.pat = c.pat_dev(kSyncSlot);
+        a.counters = c.cnt_dev(kSyncSlot);
+        a.aux = aux[g] ? aux[g]->d : nullptr;
+        a.pos = c.d_pos;
+        a.pos_cap = c.pos_cap;
         if (a.hi <= 0) return cudaSuccess;
         if (pl.filter == kFilterPacked && !pl.packed_K) return cudaSuccess;  // a pattern byte the text lacks: count 0
         launched++;
         return launch_scan(c, pl, a, c.stream);
     };
-    const bool collect = want_pos && positions && cap > 0 && total_starts > 0;
     for (int g = 0; g < t->nshards; g++) {
         DevCtx &c = *ctx[g];
         CU_TRY(cudaSetDevice(t->sh[g].dev), SB_ERR_CUDA);
-        if (collect && dev_first[g]) {
+        if (dev_first[g]) {
             // first guess for the sink: room for `cap` positions (a device may hold several shards)
             if (!ensure_pos_capacity(c, std::min((size_t)cap, (size_t)total_starts))) return SB_ERR_NOMEM;
+            CU_TRY(cudaEventRecord(c.e0, c.stream), SB_ERR_CUDA);
         }
-        if (dev_first[g]) CU_TRY(cudaEventRecord(c.e0, c.stream), SB_ERR_CUDA);
-        CU_TRY(launch_shard(g, collect), SB_ERR_CUDA);
+        CU_TRY(launch_shard(g), SB_ERR_CUDA);
     }
     for (int g = t->nshards - 1; g >= 0; g--) {
         // last shard of each device records the end event and the counter read-back
@@ -1179,8 +1526,8 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
         DevCtx &c = *ctx[g];
         CU_TRY(cudaSetDevice(t->sh[g].dev), SB_ERR_CUDA);
         CU_TRY(cudaEventRecord(c.e1, c.stream), SB_ERR_CUDA);
-        CU_TRY(cudaMemcpyAsync(c.h_counters, c.d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                               c.stream),
+        CU_TRY(cudaMemcpyAsync(c.cnt_host(kSyncSlot), c.cnt_dev(kSyncSlot), 4 * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, c.stream),
                SB_ERR_CUDA);
     }
     unsigned long long total = 0, verified = 0;
@@ -1194,13 +1541,13 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
         float ms = 0;
         CU_TRY(cudaEventElapsedTime(&ms, c.e0, c.e1), SB_ERR_CUDA);
         kernel_ms = std::max(kernel_ms, (double)ms);
-        total += c.h_counters[0];
-        verified += c.h_counters[2];
+        total += c.cnt_host(kSyncSlot)[0];
+        verified += c.cnt_host(kSyncSlot)[2];
         ndev_used++;
     }
 
     /* ---- positions: complete the sinks, sort on the device, return the smallest `cap` ascending ---- */
-    if (collect) {
+    {
         std::vector<unsigned long long> merged;  // only used when several devices contribute
         size_t written = 0;
         int end_bit = 1;
@@ -1209,14 +1556,14 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
             if (!dev_first[g]) continue;
             DevCtx &c = *ctx[g];
             CU_TRY(cudaSetDevice(t->sh[g].dev), SB_ERR_CUDA);
-            size_t found = (size_t)c.h_counters[1];
+            size_t found = (size_t)c.cnt_host(kSyncSlot)[1];
             if (found > c.pos_cap) {
                 // the sink overflowed (more occurrences than `cap`): the entries it holds are an arbitrary
                 // subset, so grow it to the exact size and scan this device's shards once more
                 if (!ensure_pos_capacity(c, found)) return SB_ERR_NOMEM;
-                CU_TRY(cudaMemsetAsync(c.d_counters, 0, 4 * sizeof(unsigned long long), c.stream), SB_ERR_CUDA);
+                CU_TRY(cudaMemsetAsync(c.cnt_dev(kSyncSlot), 0, 4 * sizeof(unsigned long long), c.stream), SB_ERR_CUDA);
                 for (int k = g; k < t->nshards; k++)
-                    if (t->sh[k].dev == t->sh[g].dev) CU_TRY(launch_shard(k, true), SB_ERR_CUDA);
+                    if (t->sh[k].dev == t->sh[g].dev) CU_TRY(launch_shard(k), SB_ERR_CUDA);
                 CU_TRY(cudaStreamSynchronize(c.stream), SB_ERR_CUDA);
             }
             if (!found) continue;
@@ -1337,6 +1684,7 @@ long long sb_search_multi64(int algo, const sb_text *t, const unsigned char *pat
         // one staging per DEVICE
         bool dev_first[kMaxShards];
         DevCtx *ctx[kMaxShards];
+        AuxSlot *maux[kMaxShards] = {nullptr};
         for (int g = 0; g < t->nshards; g++) {
             dev_first[g] = true;
             for (int k = 0; k < g; k++) dev_first[g] = dev_first[g] && (t->sh[k].dev != t->sh[g].dev);
@@ -1361,26 +1709,30 @@ long long sb_search_multi64(int algo, const sb_text *t, const unsigned char *pat
                 c.mcounts_cap = (size_t)np;
             }
             // Bloom bitmap (3 probes) + exact table {fingerprint, ((pattern << 5) | d) + 1}
-            memset(c.h_aux, 0, kAuxWords * sizeof(uint32_t));
-            uint32_t *table = c.h_aux + sb::kBloomWords;
+            AuxSlot *ax = aux_evict(c, c.stream);
+            if (!ax) return SB_ERR_CUDA;
+            maux[g] = ax;
+            uint32_t *h_aux = ax->h;
+            memset(h_aux, 0, kAuxWords * sizeof(uint32_t));
+            uint32_t *table = h_aux + sb::kBloomWords;
             for (int p = 0; p < np; p++)
                 for (int d = 0; d < B; d++) {
                     const uint32_t h = fingerprint(patterns + (size_t)(p0 + p) * m + anchor + d, B);
                     const uint32_t s1 = sb::bloom_slot(h), s2 = sb::bloom_slot2(h), s3 = sb::bloom_slot3(h);
-                    c.h_aux[s1 >> 5] |= 1u << (s1 & 31);
-                    c.h_aux[s2 >> 5] |= 1u << (s2 & 31);
-                    c.h_aux[s3 >> 5] |= 1u << (s3 & 31);
+                    h_aux[s1 >> 5] |= 1u << (s1 & 31);
+                    h_aux[s2 >> 5] |= 1u << (s2 & 31);
+                    h_aux[s3 >> 5] |= 1u << (s3 & 31);
                     uint32_t slot = sb::table_slot(h);
                     while (table[2 * slot + 1]) slot = (slot + 1) & (sb::kSkipTableSize - 1);
                     table[2 * slot] = h;
                     table[2 * slot + 1] = (((uint32_t)p << 5) | (uint32_t)d) + 1;
                 }
-            CU_TRY(cudaMemcpyAsync(c.d_aux, c.h_aux, kAuxWords * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream), SB_ERR_CUDA);
+            CU_TRY(cudaMemcpyAsync(ax->d, h_aux, kAuxWords * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream), SB_ERR_CUDA);
             CU_TRY(cudaMemcpyAsync(c.d_mpat, hpat.data(), hpat.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream),
                    SB_ERR_CUDA);
             CU_TRY(cudaMemsetAsync(c.d_mcounts, 0, (size_t)np * sizeof(unsigned long long), c.stream), SB_ERR_CUDA);
-            CU_TRY(cudaMemsetAsync(c.d_counters, 0, 4 * sizeof(unsigned long long), c.stream), SB_ERR_CUDA);
-            CU_TRY(cudaStreamSynchronize(c.stream), SB_ERR_CUDA);  // hpat / h_aux are reused by the next device
+            CU_TRY(cudaMemsetAsync(c.cnt_dev(kSyncSlot), 0, 4 * sizeof(unsigned long long), c.stream), SB_ERR_CUDA);
+            CU_TRY(cudaStreamSynchronize(c.stream), SB_ERR_CUDA);  // hpat is reused by the next device
         }
         const double b1 = now_ms();
         for (int g = 0; g < t->nshards; g++) {
@@ -1394,8 +1746,9 @@ long long sb_search_multi64(int algo, const sb_text *t, const unsigned char *pat
             a.pat_stride_words = stride_words;
             a.npat = np;
             a.multi_counts = c.d_mcounts;
-            a.counters = c.d_counters;
-            a.aux = c.d_aux;
+            a.counters = c.cnt_dev(kSyncSlot);
+            for (int k = 0; k <= g; k++)  // the block staged by the first shard of this device
+                if (maux[k] && t->sh[k].dev == sh.dev) a.aux = maux[k]->d;
             a.base = sh.base;
             a.m = m;
             a.nwords = nwords;
@@ -1429,14 +1782,14 @@ long long sb_search_multi64(int algo, const sb_text *t, const unsigned char *pat
             CU_TRY(cudaMemcpyAsync(part.data(), c.d_mcounts, (size_t)np * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                    c.stream),
                    SB_ERR_CUDA);
-            CU_TRY(cudaMemcpyAsync(c.h_counters, c.d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                                   c.stream),
+            CU_TRY(cudaMemcpyAsync(c.cnt_host(kSyncSlot), c.cnt_dev(kSyncSlot), 4 * sizeof(unsigned long long),
+                                   cudaMemcpyDeviceToHost, c.stream),
                    SB_ERR_CUDA);
             CU_TRY(cudaStreamSynchronize(c.stream), SB_ERR_CUDA);
             float ms = 0;
             CU_TRY(cudaEventElapsedTime(&ms, c.e0, c.e1), SB_ERR_CUDA);
             kernel_ms = std::max(kernel_ms, (double)ms);
-            verified += c.h_counters[2];
+            verified += c.cnt_host(kSyncSlot)[2];
             for (int p = 0; p < np; p++) counts[p0 + p] += part[(size_t)p];
         }
         const double b2 = now_ms();
@@ -1472,14 +1825,11 @@ long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned
     if (!c) return SB_ERR_CUDA;
 
     const double t0 = now_ms();
-    sb_tables *tab = tables_scratch();
-    if (!tab) return SB_ERR_NOMEM;
-    sb_prep_tables(algo, x, m, tab);
     Plan pl;
     /* selectivity estimate from a host-side sample of the text (first 64 KiB) */
     unsigned long long hist[256] = {0};
     for (size_t i = 0, e = std::min<size_t>(n, 65536); i < e; i++) hist[y[i]]++;
-    make_plan(pl, desc, x, m, flags & ~SB_FLAG_POSITIONS, n >= 4096 ? collision_bits(hist) : 8.0);
+    plan_get(pl, desc, x, m, flags & ~SB_FLAG_POSITIONS, n >= 4096 ? collision_bits(hist) : 8.0, nullptr);
     const double t1 = now_ms();
 
     /* chunk buffers: 64 MiB of start positions + halo each, double buffered */
@@ -1501,12 +1851,15 @@ long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned
         }
         c->chunk_cap = need;
     }
-    stage_pattern(*c, x, m);
-    CU_TRY(cudaMemcpyAsync(c->d_pat, c->h_pat, round_up((size_t)m + 8, 16), cudaMemcpyHostToDevice, c->stream),
+    const size_t pat_bytes = stage_pattern(*c, kSyncSlot, x, m);
+    CU_TRY(cudaMemcpyAsync(c->pat_dev(kSyncSlot), c->pat_host(kSyncSlot), pat_bytes, cudaMemcpyHostToDevice, c->stream),
            SB_ERR_CUDA);
-    if (const size_t aux_bytes = stage_aux(*c, pl))
-        CU_TRY(cudaMemcpyAsync(c->d_aux, c->h_aux, aux_bytes, cudaMemcpyHostToDevice, c->stream), SB_ERR_CUDA);
-    CU_TRY(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream), SB_ERR_CUDA);
+    AuxSlot *aux = nullptr;
+    if (pl.skip_grams) {
+        aux = aux_acquire(*c, pl, c->stream);
+        if (!aux) return SB_ERR_CUDA;
+    }
+    CU_TRY(cudaMemsetAsync(c->cnt_dev(kSyncSlot), 0, 4 * sizeof(unsigned long long), c->stream), SB_ERR_CUDA);
     CU_TRY(cudaStreamSynchronize(c->stream), SB_ERR_CUDA);
     const double t2 = now_ms();
 
@@ -1523,8 +1876,9 @@ long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned
         CU_TRY(cudaMemsetAsync(c->d_chunk[b] + len, 0, pad_end - len, c->cstream[b]), SB_ERR_CUDA);
         sb::ScanArgs a = pl.args;
         a.text = c->d_chunk[b];
-        a.pat = c->d_pat;
-        a.counters = c->d_counters;
+        a.pat = c->pat_dev(kSyncSlot);
+        a.counters = c->cnt_dev(kSyncSlot);
+        a.aux = aux ? aux->d : nullptr;
         a.base = base;
         a.hi = hi;
         CU_TRY(launch_scan(*c, pl, a, c->cstream[b]), SB_ERR_CUDA);
@@ -1532,7 +1886,8 @@ long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned
     }
     CU_TRY(cudaStreamSynchronize(c->cstream[0]), SB_ERR_CUDA);
     CU_TRY(cudaStreamSynchronize(c->cstream[1]), SB_ERR_CUDA);
-    CU_TRY(cudaMemcpy(c->h_counters, c->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost),
+    unsigned long long *h_counters = c->cnt_host(kSyncSlot);
+    CU_TRY(cudaMemcpy(h_counters, c->cnt_dev(kSyncSlot), 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost),
            SB_ERR_CUDA);
     const double t3 = now_ms();
     g_timing.prep_host_ms = t1 - t0;
@@ -1540,10 +1895,10 @@ long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned
     g_timing.wall_ms = t3 - t2;
     g_timing.kernels_launched = launched;
     g_timing.filter_kind = filter_kind_of(pl);
-    g_timing.verified = c->h_counters[2];
+    g_timing.verified = h_counters[2];
     if (pre_ms) *pre_ms = t2 - t0;
     if (run_ms) *run_ms = (t3 - t2) > 0 ? (t3 - t2) : 1e-6;
-    return (long long)c->h_counters[0];
+    return (long long)h_counters[0];
 }
 
 int sb_plugin_search(int algo, unsigned char *x, int m, unsigned char *y, int n, double *pre_ms, double *run_ms)

@@ -1,6 +1,8 @@
 /*
- * Pattern-preprocessing stage (host side, C): the per-algorithm tables of the SMART
- * algorithm families, built once per pattern and then uploaded to the device.
+ * Pattern-preprocessing stage (host side, C): the algorithm registry (names, -1 domains, scan
+ * direction) and the per-algorithm tables of the SMART algorithm families.  The search entry points use
+ * the registry and sb_prep_mp (the pattern's period); the full table set is built only when a caller asks
+ * through sb_prep_tables (parity tests, the table-driven device filters) — never on the timed search path.
  *
  * Each builder must produce a table bit-identical to the one the reference builds
  * (tests compare against oracle/ and against the reference's own exported pre*
@@ -511,7 +513,11 @@ int sb_prep_tables(int algo, const unsigned char *x, int m, sb_tables *out)
 {
     const sb_algo_desc *d = sb_algo_desc_get(algo);
     if (!d || !x || !out || m < 1 || m > SB_XSIZE) return -2;
+    /* everything up to the first big array is cleared, and so are the scalars that lie between the big arrays;
+     * the big arrays themselves (brBc, qfB, wfrF, ztBc: 256 KiB - 1 MiB each) are only DEFINED for the families
+     * that fill them - a reused struct may still hold another family's values there */
     memset(out, 0, offsetof(sb_tables, brBc));
+    out->qfQ = out->qfS = out->wfrQ = 0;
     out->m = m;
     if (m < d->min_m) return -1;
     switch (d->family) {

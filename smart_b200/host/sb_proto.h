@@ -8,7 +8,11 @@
 #include <stdint.h>
 
 #define SB_PROTO_MAGIC 0x53423230u /* "SB20" */
-enum { SB_REQ_SEARCH = 1, SB_REQ_PING = 2, SB_REQ_QUIT = 3, SB_REQ_STATS = 4, SB_REQ_SEARCH_MULTI = 5 };
+enum { SB_REQ_SEARCH = 1, SB_REQ_PING = 2, SB_REQ_QUIT = 3, SB_REQ_STATS = 4, SB_REQ_SEARCH_MULTI = 5,
+       /* the pattern set of one length as npat INDEPENDENT searches, pipelined with sb_search64_submit /
+        * sb_search_collect (one scan per pattern, no wait between them); the result segment holds npat counts
+        * (uint64), then npat scan times and npat preprocessing times (double, ms) */
+       SB_REQ_SEARCH_SET = 6 };
 
 typedef struct sb_request {
     uint32_t magic;
@@ -18,8 +22,8 @@ typedef struct sb_request {
     int32_t m;
     int32_t tkey; /* SysV key of the text segment */
     int32_t n;
-    int32_t npat; /* SEARCH_MULTI: the pattern segment holds npat patterns of length m back to back */
-    int32_t ckey; /* SEARCH_MULTI: SysV key of the per-pattern count segment (npat x uint64) */
+    int32_t npat; /* SEARCH_MULTI / SEARCH_SET: the pattern segment holds npat patterns of length m back to back */
+    int32_t ckey; /* SEARCH_MULTI: SysV key of the per-pattern count segment (npat x uint64); SEARCH_SET: npat x 24 bytes */
     int32_t reserved;
     char algo_name[24]; /* used when algo < 0 (the driver does not link the library's registry) */
     uint64_t text_gen;  /* non-zero: the sender vouches that (tkey, n, text_gen) identifies the text content

@@ -63,6 +63,7 @@ typedef struct {
     unsigned seed;
     int use_worker;
     int batch;      /* -batch: one worker request per (algorithm, length) for the whole pattern set */
+    int pipeline;   /* -pipeline: the pattern set as independent searches, submitted without waiting for each other */
     char bindir[512];
     char datadir[512];
     char resdir[512];
@@ -108,7 +109,10 @@ static void usage(void)
            "\t-seed S          seed for pattern sampling (default: time)\n"
            "\t-noworker        do not start the resident GPU worker\n"
            "\t-batch           scan the text ONCE per (algorithm, length) for the whole pattern set\n"
-           "\t                 (needs the worker; reported time = time of the pass / number of patterns)\n\n");
+           "\t                 (needs the worker; reported time = time of the pass / number of patterns)\n"
+           "\t-pipeline        one scan per pattern as usual, but the whole set of a length is handed to the\n"
+           "\t                 worker at once and the scans run back to back on the GPU (asynchronous\n"
+           "\t                 submit/collect); reported time = CUDA-event time of each pattern's own scan\n\n");
 }
 
 /* ---- shared memory: keys are small random integers like the reference's rand()%1000 ---- */
@@ -271,14 +275,20 @@ static int run_search(const config *cf, const char *algo, int m, long n)
 /* ---- resident worker ---- */
 static int worker_started;
 
+static int worker_shared; /* a worker somebody else started is listening: use it, never stop it */
+
 static void worker_start(const config *cf, const char *selfdir)
 {
     char cmd[1200];
     if (!cf->use_worker) return;
     snprintf(cmd, sizeof cmd, "%s/smartd > /dev/null 2>&1", selfdir);
-    if (system(cmd) == 0) {
+    const int rc = system(cmd);
+    if (rc == 0) {
         worker_started = 1;
         printf("\tResident GPU worker started (text stays in HBM across searches)\n");
+    } else if (rc != -1 && WIFEXITED(rc) && WEXITSTATUS(rc) == 7) {
+        worker_shared = 1;
+        printf("\tResident GPU worker already running (shared; it is left running at the end)\n");
     } else {
         printf("\tNo resident GPU worker (each search runs in its own process)\n");
     }
@@ -337,6 +347,43 @@ static int run_batch(const config *cf, const char *algo, int m, long n, unsigned
     }
     *pre_ms = rp.pre_ms + rp.upload_ms;
     *run_ms = rp.run_ms;
+    return 0;
+}
+
+/* -pipeline: the pattern set of length m as npat independent scans in one worker request (SB_REQ_SEARCH_SET);
+ * counts[k], run[k], pre[k] per pattern.  Returns 0, or -1 (worker unreachable / failed). */
+static int run_pipeline(const config *cf, const char *algo, int m, long n, unsigned char (*set)[XSIZE + 1],
+                        const unsigned long long **counts, const double **run, const double **pre)
+{
+    unsigned char *dst = seg_mpat.ptr;
+    unsigned char *res = seg_mcounts.ptr;
+    for (int i = 0; i < cf->npat; i++) memcpy(dst + (size_t)i * m, set[i], (size_t)m);
+    memset(res, 0, (size_t)cf->npat * 24);
+    sb_request rq;
+    sb_reply rp;
+    memset(&rq, 0, sizeof rq);
+    rq.magic = SB_PROTO_MAGIC;
+    rq.kind = SB_REQ_SEARCH_SET;
+    rq.algo = -1;
+    snprintf(rq.algo_name, sizeof rq.algo_name, "%s", algo);
+    rq.pkey = seg_mpat.key;
+    rq.m = m;
+    rq.tkey = seg_text.key;
+    rq.n = (int)n;
+    rq.npat = cf->npat;
+    rq.ckey = seg_mcounts.key;
+    {
+        const char *gen = getenv("SMART_B200_TEXT_GEN");
+        rq.text_gen = gen ? strtoull(gen, NULL, 10) : 0;
+    }
+    int fd = sb_worker_connect();
+    if (fd < 0) return -1;
+    int rc = sb_worker_call(fd, &rq, &rp);
+    close(fd);
+    if (rc != 0 || rp.status != 0) return -1;
+    *counts = (const unsigned long long *)res;
+    *run = (const double *)(res + (size_t)cf->npat * 8);
+    *pre = (const double *)(res + (size_t)cf->npat * 16);
     return 0;
 }
 
@@ -404,6 +451,31 @@ static void run_experiment(const config *cf, const char *label, unsigned char *T
                     done = cf->npat;
                     if (per > cf->limit_ms) verdict = -2;
                 }
+            } else if (cf->pipeline && !simple) {
+                const unsigned long long *counts;
+                const double *run_k, *pre_k;
+                if (run_pipeline(cf, cf->algos[a], m, n, set, &counts, &run_k, &pre_k) != 0) verdict = -1;
+                else
+                    for (int k = 0; k < cf->npat; k++) { /* same verdict rules as the per-process loop below */
+                        const long long occ = (long long)counts[k];
+                        double t = run_k[k];
+                        if (!cf->pre) t += pre_k[k];
+                        samples[k] = t;
+                        sum += t;
+                        sum_pre += pre_k[k];
+                        if (t < best) best = t;
+                        if (t > worst) worst = t;
+                        total_occ += occ;
+                        done++;
+                        if (occ <= 0) {
+                            verdict = occ == 0 ? 0 : -1;
+                            break;
+                        }
+                        if (t > cf->limit_ms) {
+                            verdict = -2;
+                            break;
+                        }
+                    }
             } else
             for (int k = 0; k < cf->npat; k++) {
                 memcpy(P, set[k], (size_t)m);
@@ -649,6 +721,7 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "-seed")) { NEED(1); cf.seed = (unsigned)strtoul(argv[++i], NULL, 10); }
         else if (!strcmp(a, "-noworker")) cf.use_worker = 0;
         else if (!strcmp(a, "-batch")) cf.batch = 1;
+        else if (!strcmp(a, "-pipeline")) cf.pipeline = 1;
         else { printf("Error in input parameters. Use -h for help.\n\n"); return 0; }
     }
     if (cf.minlen < 1 || cf.minlen > XSIZE || cf.maxlen < cf.minlen) {
@@ -677,15 +750,15 @@ int main(int argc, char **argv)
     if (seg_create(&seg_count, 4, o4, 4)) { destroy_all(); return 1; }
     unsigned char *T = seg_text.ptr;
 
-    if (cf.batch) {
+    if (cf.batch || cf.pipeline) {
         const segment *o5[] = {&seg_text, &seg_time, &seg_pre, &seg_pat, &seg_count};
         if (seg_create(&seg_mpat, (size_t)cf.npat * XSIZE, o5, 5)) { destroy_all(); return 1; }
         const segment *o6[] = {&seg_text, &seg_time, &seg_pre, &seg_pat, &seg_count, &seg_mpat};
-        if (seg_create(&seg_mcounts, (size_t)cf.npat * 8, o6, 6)) { destroy_all(); return 1; }
+        if (seg_create(&seg_mcounts, (size_t)cf.npat * 24, o6, 6)) { destroy_all(); return 1; }
     }
     worker_start(&cf, selfdir);
-    if (cf.batch && !worker_started) {
-        printf("\t-batch needs the resident GPU worker\n");
+    if ((cf.batch || cf.pipeline) && !worker_started && !worker_shared) {
+        printf("\t-batch / -pipeline need the resident GPU worker\n");
         destroy_all();
         return 1;
     }

@@ -36,35 +36,25 @@ static double now_ms(void)
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
-/* content hash of the text: every byte for texts up to 64 MiB, 16384 evenly spaced 4 KiB blocks above */
+/* content hash of the text, every byte (used up to 64 MiB; larger texts without a generation number are
+ * re-uploaded instead: at PCIe Gen5 rates the copy is faster than hashing them) */
 static uint64_t text_hash(const unsigned char *t, size_t n)
 {
-    uint64_t h = 0x9E3779B97F4A7C15ull ^ n;
-    const size_t full = (size_t)64 << 20;
-    size_t nblk = 1, blk = n, stride = 0;
-    if (n > full) {
-        nblk = 16384;
-        blk = 4096;
-        stride = (n - blk) / (nblk - 1);
+    uint64_t a = 0x9E3779B97F4A7C15ull ^ n, c = ~a;
+    size_t i = 0;
+    for (; i + 16 <= n; i += 16) {
+        uint64_t u, v;
+        memcpy(&u, t + i, 8);
+        memcpy(&v, t + i + 8, 8);
+        a = (a ^ u) * 0xFF51AFD7ED558CCDull;
+        a = (a << 29) | (a >> 35);
+        c = (c ^ v) * 0xC4CEB9FE1A85EC53ull;
+        c = (c << 31) | (c >> 33);
     }
-    for (size_t b = 0; b < nblk; b++) {
-        const unsigned char *p = t + b * stride;
-        size_t i = 0;
-        uint64_t a = h, c = ~h;
-        for (; i + 16 <= blk; i += 16) {
-            uint64_t u, v;
-            memcpy(&u, p + i, 8);
-            memcpy(&v, p + i + 8, 8);
-            a = (a ^ u) * 0xFF51AFD7ED558CCDull;
-            a = (a << 29) | (a >> 35);
-            c = (c ^ v) * 0xC4CEB9FE1A85EC53ull;
-            c = (c << 31) | (c >> 33);
-        }
-        for (; i < blk; i++) a = (a ^ p[i]) * 0x100000001B3ull;
-        h = (a ^ (c * 0x9E3779B97F4A7C15ull)) + b;
-    }
-    return h;
+    for (; i < n; i++) a = (a ^ t[i]) * 0x100000001B3ull;
+    return a ^ (c * 0x9E3779B97F4A7C15ull);
 }
+#define SB_HASH_LIMIT ((size_t)64 << 20)
 
 static struct {
     int tkey, shmid;
@@ -81,15 +71,22 @@ static struct {
 
 static uint64_t g_searches, g_uploads;
 
-static const unsigned char *attach(int key, size_t size, int *shmid_io, const unsigned char *old, int oldkey)
+/* Attach segment `key`, reusing the cached attachment (*host_io, *key_io, *shmid_io) when it is the same
+ * segment.  On any failure the cache is CLEARED: a detached pointer must never be handed out again. */
+static const unsigned char *attach(int key, size_t size, int *shmid_io, const unsigned char **host_io, int *key_io)
 {
     int id = shmget((key_t)key, size, 0666);
+    if (id >= 0 && *host_io && key == *key_io && id == *shmid_io) return *host_io; /* same segment still attached */
+    if (*host_io) shmdt(*host_io);
+    *host_io = NULL;
+    *key_io = -1;
+    *shmid_io = -1;
     if (id < 0) return NULL;
-    if (old && key == oldkey && id == *shmid_io) return old; /* same segment still attached */
-    if (old) shmdt(old);
     void *p = shmat(id, NULL, SHM_RDONLY);
     if (p == (void *)-1) return NULL;
     *shmid_io = id;
+    *key_io = key;
+    *host_io = p;
     return p;
 }
 
@@ -102,9 +99,7 @@ static void serve_search(const sb_request *rq, sb_reply *rp)
         rp->status = EINVAL;
         return;
     }
-    g_pat.host = attach(rq->pkey, (size_t)rq->m, &g_pat.shmid, g_pat.host, g_pat.pkey);
-    g_pat.pkey = rq->pkey;
-    if (!g_pat.host) {
+    if (!attach(rq->pkey, (size_t)rq->m, &g_pat.shmid, &g_pat.host, &g_pat.pkey)) {
         rp->status = errno ? errno : ENOENT;
         return;
     }
@@ -122,17 +117,22 @@ static void serve_search(const sb_request *rq, sb_reply *rp)
 /* make sure the resident copy of the text segment (tkey, n) is current; returns 0 or an errno */
 static int ensure_text(int tkey, int n, uint64_t gen, double *upload_ms)
 {
-    const unsigned char *t = attach(tkey, (size_t)n, &g_text.shmid, g_text.host, g_text.tkey);
-    if (!t) return errno ? errno : ENOENT;
+    const unsigned char *before = g_text.host;
+    const unsigned char *t = attach(tkey, (size_t)n, &g_text.shmid, &g_text.host, &g_text.tkey);
+    if (!t) {
+        if (g_text.dev) sb_text_free(g_text.dev); /* the resident copy belonged to the segment just detached */
+        g_text.dev = NULL;
+        return errno ? errno : ENOENT;
+    }
     const double t0 = now_ms();
-    /* a sender-provided generation number identifies the content; otherwise hash the text */
-    const uint64_t h = gen ? 0 : text_hash(t, (size_t)n);
-    if (!g_text.dev || t != g_text.host || g_text.tkey != tkey || g_text.n != (size_t)n || g_text.gen != gen ||
-        g_text.hash != h) {
+    /* a sender-provided generation number identifies the content; otherwise every byte of the text is hashed
+     * (up to 64 MiB), and a larger text is uploaded again for every search: never a sampled hash, which could
+     * serve a stale resident copy of a text that was rewritten in place between the samples */
+    const int trust_hash = gen || (size_t)n <= SB_HASH_LIMIT;
+    const uint64_t h = gen ? 0 : (trust_hash ? text_hash(t, (size_t)n) : 0);
+    if (!g_text.dev || t != before || g_text.n != (size_t)n || g_text.gen != gen || !trust_hash || g_text.hash != h) {
         if (g_text.dev) sb_text_free(g_text.dev);
         g_text.dev = sb_text_upload(t, (size_t)n, NULL, 1);
-        g_text.host = t;
-        g_text.tkey = tkey;
         g_text.n = (size_t)n;
         g_text.hash = h;
         g_text.gen = gen;
@@ -178,20 +178,93 @@ static void serve_multi(const sb_request *rq, sb_reply *rp)
     if (counts != (void *)-1) shmdt(counts);
 }
 
+/* SEARCH_SET: npat independent searches of one length, submitted back to back and collected afterwards */
+static void serve_set(const sb_request *rq, sb_reply *rp)
+{
+    rp->status = 0;
+    if (rq->m < 1 || rq->m > SB_XSIZE || rq->n < 0 || rq->npat < 1) {
+        rp->status = EINVAL;
+        return;
+    }
+    const size_t np = (size_t)rq->npat;
+    int pid = shmget((key_t)rq->pkey, np * (size_t)rq->m, 0666);
+    int cid = shmget((key_t)rq->ckey, np * 24, 0666);
+    const unsigned char *pats = pid >= 0 ? shmat(pid, NULL, SHM_RDONLY) : (void *)-1;
+    unsigned char *res = cid >= 0 ? shmat(cid, NULL, 0) : (void *)-1;
+    if (pats == (void *)-1 || res == (void *)-1) {
+        rp->status = errno ? errno : ENOENT;
+    } else if ((rp->status = ensure_text(rq->tkey, rq->n, rq->text_gen, &rp->upload_ms)) == 0) {
+        char name[sizeof rq->algo_name + 1];
+        memcpy(name, rq->algo_name, sizeof rq->algo_name);
+        name[sizeof rq->algo_name] = 0;
+        const int algo = rq->algo >= 0 ? rq->algo : sb_algo_id(name);
+        unsigned long long *counts = (unsigned long long *)res;
+        double *run = (double *)(res + np * 8), *pre = (double *)(res + np * 16);
+        enum { WINDOW = 128 };  /* tickets in flight (the library allows 256) */
+        long long tickets[WINDOW];
+        long long total = 0;
+        size_t sent = 0, done = 0;
+        const double t0 = now_ms();
+        while (done < np && rp->status == 0) {
+            while (sent < np && sent - done < WINDOW) {
+                tickets[sent % WINDOW] = sb_search64_submit(algo, g_text.dev, pats + sent * (size_t)rq->m, rq->m, 0);
+                if (tickets[sent % WINDOW] < 0) {
+                    rp->status = EIO;
+                    break;
+                }
+                sent++;
+            }
+            if (done < sent) {
+                const long long c = sb_search_collect(tickets[done % WINDOW], &pre[done], &run[done]);
+                if (c < -1) rp->status = EIO;
+                counts[done] = (unsigned long long)c; /* -1 (not applicable) is stored as ~0 */
+                if (c > 0) total += c;
+                if (c == -1) total = -1;
+                done++;
+            }
+        }
+        while (done < sent) { /* drain after an error */
+            double a, b;
+            sb_search_collect(tickets[done % WINDOW], &a, &b);
+            done++;
+        }
+        if (rp->status) fprintf(stderr, "smartd: pipelined search failed: %s\n", sb_last_error());
+        rp->count = total;
+        rp->run_ms = now_ms() - t0; /* wall time of the whole set */
+        g_searches += (uint64_t)np;
+    }
+    if (pats != (void *)-1) shmdt(pats);
+    if (res != (void *)-1) shmdt(res);
+}
+
+/* A live worker already listening on `path` keeps its socket (and its CUDA context and resident text): a second
+ * worker must not take it over.  Only a dead socket file is removed.  umask 077 makes the socket private from
+ * the moment bind() creates it. */
 static int listen_on(const char *path)
 {
     struct sockaddr_un sa;
-    int fd = socket(AF_UNIX, SOCK_STREAM, 0);
-    if (fd < 0) return -1;
     memset(&sa, 0, sizeof sa);
     sa.sun_family = AF_UNIX;
     snprintf(sa.sun_path, sizeof sa.sun_path, "%s", path);
-    unlink(path);
-    if (bind(fd, (struct sockaddr *)&sa, sizeof sa) != 0 || listen(fd, 64) != 0) {
+    int probe = socket(AF_UNIX, SOCK_STREAM, 0);
+    if (probe >= 0) {
+        const int alive = connect(probe, (struct sockaddr *)&sa, sizeof sa) == 0;
+        close(probe);
+        if (alive) {
+            errno = EADDRINUSE;
+            return -2;
+        }
+    }
+    int fd = socket(AF_UNIX, SOCK_STREAM, 0);
+    if (fd < 0) return -1;
+    unlink(path); /* nobody answered: a stale file of a worker that died */
+    const mode_t old = umask(077);
+    const int rc = bind(fd, (struct sockaddr *)&sa, sizeof sa);
+    umask(old);
+    if (rc != 0 || listen(fd, 64) != 0) {
         close(fd);
         return -1;
     }
-    chmod(path, 0600);
     return fd;
 }
 
@@ -277,6 +350,7 @@ int main(int argc, char **argv)
         sb_text_free(w);
     }
     int ls = listen_on(path);
+    if (ls == -2) FAIL_START(7, "a worker is already running on %s", path);
     if (ls < 0) FAIL_START(4, "cannot bind %s: %s", path, strerror(errno));
     if (report[1] >= 0) {
         if (write(report[1], "ok", 2) < 0) {}
@@ -306,6 +380,7 @@ int main(int argc, char **argv)
         if (got == sizeof rq && rq.magic == SB_PROTO_MAGIC) {
             if (rq.kind == SB_REQ_SEARCH) serve_search(&rq, &rp);
             else if (rq.kind == SB_REQ_SEARCH_MULTI) serve_multi(&rq, &rp);
+            else if (rq.kind == SB_REQ_SEARCH_SET) serve_set(&rq, &rp);
             else if (rq.kind == SB_REQ_QUIT) quit = 1;
             rp.searches = g_searches;
             rp.text_uploads = g_uploads;

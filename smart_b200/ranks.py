@@ -54,3 +54,20 @@ def barrier(dist, device=None):
         dist.barrier(device_ids=[torch.device(device).index])
     else:
         dist.barrier()
+
+
+def cpu_group(dist):
+    """A gloo group next to the NCCL one: its barrier blocks on the HOST.  Used around the legs where only rank 0
+    works (in-process multi-device run, CPU baseline): an NCCL barrier would keep a kernel spinning on every other
+    GPU meanwhile."""
+    if dist is None:
+        return None
+    return dist.new_group(backend="gloo")
+
+
+def host_barrier(group):
+    if group is None:
+        return
+    import torch.distributed as dist
+
+    dist.barrier(group=group)

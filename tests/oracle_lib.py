@@ -130,6 +130,33 @@ class Oracle:
         raise KeyError(name)
 
 
+def textgen_np(off: int, length: int, sigma: int, seed: int) -> np.ndarray:
+    """numpy restatement of the product's counter-based text generator (include/smart_b200.h sb_textgen_host):
+    bytes [off, off+length) of stream (seed, sigma).  Lets the reference arm of bench.py and the CPU baseline build
+    the workload text without loading libsmartb200.so.  Word q (8 bytes, little endian) is
+    mix64(seed + (q+1)*0x9E3779B97F4A7C15) (splitmix64 finaliser); sigma = 256 keeps the bytes, a power of two masks
+    each byte with sigma-1, any other sigma maps byte b to (b*sigma) >> 8."""
+    if length <= 0:
+        return np.zeros(0, dtype=np.uint8)
+    q0, q1 = off >> 3, (off + length + 7) >> 3
+    with np.errstate(over="ignore"):
+        q = np.arange(q0 + 1, q1 + 1, dtype=np.uint64)
+        z = np.uint64(seed & 0xFFFFFFFFFFFFFFFF) + q * np.uint64(0x9E3779B97F4A7C15)
+        z ^= z >> np.uint64(30)
+        z *= np.uint64(0xBF58476D1CE4E5B9)
+        z ^= z >> np.uint64(27)
+        z *= np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+    b = z.view(np.uint8) if z.dtype.byteorder in ("=", "<", "|") else z.byteswap().view(np.uint8)
+    if sigma != 256:
+        if sigma & (sigma - 1) == 0:
+            b = b & np.uint8(sigma - 1)
+        else:
+            b = ((b.astype(np.uint16) * np.uint16(sigma)) >> np.uint16(8)).astype(np.uint8)
+    lo = off - (q0 << 3)
+    return np.ascontiguousarray(b[lo: lo + length])
+
+
 def ref_available(algo: str = "bf") -> bool:
     return os.path.exists(os.path.join(REF_DIR, f"{algo}.so"))
 

@@ -20,7 +20,9 @@ def run_bench(*args, timeout=600):
     return json.loads(lines[0])
 
 
-def test_reference_arm_json():
+def test_reference_arm_json(monkeypatch):
+    # the reference arm must not need (or map) the product library: point it at a path that does not exist
+    monkeypatch.setenv("SMART_B200_LIB", "/nonexistent/libsmartb200.so")
     d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-sample-mib", "8")
     assert BASE_KEYS <= set(d)
     assert d["impl"] == "reference" and d["unit"] == "GB/s" and d["higher_is_better"] is True
@@ -28,6 +30,9 @@ def test_reference_arm_json():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    best = d["cpu_baseline"]["best"]  # the reference's fastest CPU code (EPSM) beside the same-algorithm number
+    if d["cpu_baseline"]["kind"] == "reference":
+        assert best["algo"] == "epsm" and best["value"] > 0
 
 
 def test_reference_arm_other_ranks_exit_quietly():
@@ -38,7 +43,8 @@ def test_reference_arm_other_ranks_exit_quietly():
 
 @pytest.mark.gpu
 def test_our_arm_json_small():
-    d = run_bench("--gib-per-gpu", "0.25", "--steps", "2", "--warmup", "3", "--cpu-sample-mib", "8")
+    d = run_bench("--gib-per-gpu", "0.25", "--steps", "2", "--warmup", "3", "--cpu-sample-mib", "8", "--c4-gib", "1",
+                  "--c4-reps", "3")
     assert BASE_KEYS | {"roofline", "clocks"} <= set(d)
     assert "impl" not in d and d["n_gpus"] == 1 and d["scaling"] == "weak" and d["data"] == "synthetic"
     rf = d["roofline"]
@@ -51,3 +57,10 @@ def test_our_arm_json_small():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["value"] > 0 and cb["cores"] >= 1 and "sample" in cb
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    c4 = d["config4"]  # the strong-scaling leg: one sigma=4 text, byte kernels and default kernels, same counts
+    assert c4["scaling"] == "strong" and c4["text_bytes_total"] == 1 << 30 and len(c4["results"]) == 12
+    assert {r["mode"] for r in c4["results"]} == {"byte_kernels", "default"}
+    for m in (8, 64, 1024):
+        assert len({r["count"] for r in c4["results"] if r["m"] == m}) == 1
+    assert all(r["same_as_per_rank_sum"] for r in c4["inprocess"]["results"])
+    assert abs(d["value"] / d["value_kernels_only"] - 1) < 0.1

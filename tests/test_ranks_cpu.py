@@ -37,6 +37,7 @@ def _worker(rank, world, port, n, m, out_q):
     hi = max(0, min(own, n - m + 1 - base))          # owned start positions
     local = ora.bf_count(x, part[: min(ln, hi + m - 1)]) if hi > 0 else 0
     ranks.barrier(dist, "cpu")
+    ranks.host_barrier(ranks.cpu_group(dist))  # the host-side barrier bench.py uses around rank-0-only legs
     total, max_ms, max_k = ranks.reduce_step(dist, "cpu", local, 10.0 * (rank + 1), 1.0 + rank)
     out_q.put((rank, local, total, max_ms, max_k))
     dist.destroy_process_group()
@@ -73,3 +74,15 @@ def test_single_rank_is_identity():
 
     assert ranks.reduce_step(None, "cpu", 5, 1.5, 0.5) == (5, 1.5, 0.5)
     ranks.barrier(None)
+    ranks.host_barrier(ranks.cpu_group(None))
+
+
+def test_numpy_text_generator_equals_the_library():
+    """bench.py's CPU legs build the workload text with oracle_lib.textgen_np so that the reference arm never
+    loads libsmartb200.so; it must be the same stream as sb_textgen_host / the device generator."""
+    import oracle_lib
+    import smart_b200 as sb
+
+    for sigma in (256, 4, 2, 16, 3, 250, 1):
+        for off, ln in ((0, 100), (5, 77), (123457, 4096), (8, 8), (7, 1), (1 << 33, 65)):
+            assert np.array_equal(oracle_lib.textgen_np(off, ln, sigma, 20261018), sb.textgen_host(off, ln, sigma, 20261018))
