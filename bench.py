@@ -52,7 +52,9 @@ FILTER_NAMES = {0: "scan_swar_kernel", 1: "scan_window8_kernel", 4: "scan_block_
                 416: "scan_block_kernel<4,16>", 816: "scan_block_kernel<8,16>",
                 **{20 + L: f"scan_block_kernel<2,{L}>" for L in range(3, 9)},
                 **{300 + K: f"scan_packed_kernel<{K}>" for K in (1, 2, 4, 8)},
-                311: "scan_packed_half_kernel<1>", 312: "scan_packed_half_kernel<2>"}
+                311: "scan_packed_half_kernel<1>", 312: "scan_packed_half_kernel<2>",
+                **{500 + k: f"scan_pswar_kernel<1,{k}>" for k in range(1, 33)},
+                **{540 + k: f"scan_pswar_kernel<2,{k}>" for k in range(1, 17)}}
 
 
 def parse_args():

@@ -162,6 +162,8 @@ typedef struct sb_timing {
                               23..28 = scan_block<2,L> (L = 3..8 bytes at every even position),
                               301/302/304/308 = scan_packed<K> on the 2-bit recoding (300: pattern has a byte
                               the text does not contain, nothing scanned), 311/312 = scan_packed_half<KH>,
+                              501..532 = scan_pswar<1,KF> (SWAR chain of KF characters on the 1-bit recoding; exact when
+                              KF == m), 541..556 = scan_pswar<2,KF> on the 2-bit recoding,
                               108/116/132 = scan_skip<G>, 204/208/216 = scan_multi<B>, -1 = per-pattern fallback */
     unsigned long long verified; /* candidates sent to exact verification (all shards) */
 } sb_timing;

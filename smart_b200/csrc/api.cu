@@ -56,6 +56,7 @@ constexpr size_t kPatBytes = 4352;            // device pattern buffer (>= SB_XS
 #endif
 constexpr int kU = SB_U;                      // 256-bit loads in flight per thread (scan_block / scan_window8)
 constexpr size_t kGroupLong = kU * 1024;      // bytes per warp iteration of those kernels
+constexpr size_t kGroupPacked = 4 * 1024;     // ... of the kernels whose U is fixed at 4 (scan_swar, scan_packed*, scan_pswar)
 constexpr int kFilterShort = 0, kFilterWindow8 = 1, kFilterWindow16 = 3;  // 2 = the 12-byte window
 constexpr int kFilterPair = 20;               // scan_block<2,L>: windows at even positions, L = 4..8 in Plan::flen
 /* scan_packed<8> moves ~26 T characters/s on a 2-bit copy and ~49 T on a 1-bit one (~13 T on a 4-bit one);
@@ -63,6 +64,9 @@ constexpr int kFilterPair = 20;               // scan_block<2,L>: windows at eve
 constexpr int kPackedBeatsSkipBelow4 = 167, kPackedBeatsSkipBelow2 = 448, kPackedBeatsSkipBelow1 = 1200;
 constexpr int kFilterPacked = 300;             // + K (301, 302, 304, 308): scan_packed<K> on the 2-bit recoding
 constexpr int kFilterSkip = 100;              // + gram bytes (108, 116, 132): scan_skip<G>
+constexpr int kFilterPswar = 500;             // scan_pswar<BITS,KF>: reported as 500 + KF (1 bit) / 540 + KF (2 bits)
+/* scan_pswar covers m <= 30 on a 1-bit copy and m <= 22 on a 2-bit one; beyond, the half-word bitmap kernels are faster */
+constexpr int kPswarMaxM1 = 30, kPswarMaxM2 = 22;
 constexpr size_t kAuxWords = sb::kBloomWords + 2 * sb::kSkipTableSize;
 
 constexpr int kTickets = 256;                 // outstanding asynchronous searches (sb_search64_submit)
@@ -110,6 +114,7 @@ struct DevCtx {                               // per-device scratch, created on 
     int occ_block[7] = {0};                   // resident CTAs/SM for scan_block<B,L>, index block_index()
     int occ_window[24] = {0};                 // ... for scan_window<NW,OFF,DENSE>, index window_index()
     int occ_swar[8] = {0};                    // ... for scan_swar<M, DENSE>, index (M-1)*2 + DENSE
+    mutable int occ_pswar[2][33][2] = {{{0}}};  // ... for scan_pswar<BITS,KF,EXACT>, filled on first use
     unsigned long long *d_hist = nullptr;     // 256-bin byte histogram scratch
     uint32_t *d_mpat = nullptr;               // scan_multi: pattern set (words), grown on demand
     size_t mpat_words = 0;
@@ -394,6 +399,8 @@ struct Plan {
     bool sparse;        // scan_swar: a match of the whole pattern is rare in this text
     int packed_half;    // scan_packed_half: sampling period in half-words (1, 2), 0 = word variants
     int packed_K;       // scan_packed: sampling period in words; 0 with filter == kFilterPacked: pattern outside the alphabet
+    int pswar_bits;     // scan_pswar: bits per character of the recoding (1, 2); flen = KF, the chain length
+    bool pswar_exact;   // scan_pswar: KF == m, the chain decides, nothing to verify
     sb::ScanArgs args;  // text/base/hi/ngroups/counters/pos filled per shard
 };
 
@@ -406,6 +413,8 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
     pl.skip_grams = 0;
     pl.packed_K = 0;
     pl.packed_half = 0;
+    pl.pswar_bits = 0;
+    pl.pswar_exact = false;
     sb::ScanArgs &a = pl.args;
     a.m = m;
     a.nwords = (m + 3) / 4;
@@ -456,6 +465,37 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
      * CPW = 16 characters per word (32 for two-symbol texts, 1 bit each).  m >= 2*CPW-1: whole words, every K-th
      * one, K = 1, 2, 4, 8 with m >= CPW*(K+1)-1; CPW-1 <= m < 2*CPW-1: half-words (only if CPW/2 characters carry
      * >= 14 bits), both halves or the low one. */
+    /* Short patterns on a 1- or 2-bit recoding: the SWAR chain of scan_pswar, 32 / 16 start positions per
+     * instruction.  The chain holds KF pattern characters: all m of them when that fits one word and fewer than 20
+     * bits of selectivity are at stake otherwise (EXACT: nothing to verify, dense matches are counted in
+     * registers), else the ~20-bit prefix/suffix of the pattern as a filter in front of the byte-wise verification. */
+    if (pk && pk->packed && pk->bits <= 2 && m <= (pk->bits == 1 ? kPswarMaxM1 : kPswarMaxM2) &&
+        !(flags & (forced | SB_FLAG_NO_PACK | SB_FLAG_DENSE))) {
+        unsigned char code[256];
+        memset(code, 0xff, sizeof code);
+        for (int c = pk->nsym - 1; c >= 0; c--) code[pk->sym[c]] = (unsigned char)c;
+        bool inside = true;
+        for (int i = 0; i < m && inside; i++) inside = code[x[i]] != 0xff;
+        if (!inside) {  // a byte the text does not contain: no occurrence, nothing to scan
+            pl.filter = kFilterPacked;
+            pl.packed_K = 0;
+            return;
+        }
+        const int chain_max = 32 / pk->bits;
+        int kf = (int)ceil(20.0 / (bits > 0.05 ? bits : 0.05) - 0.05);  // (a sampled histogram gives 0.999 for 1 bit)
+        if (kf > chain_max) kf = chain_max;
+        if (kf >= m || m <= 4) kf = m <= chain_max ? m : chain_max;
+        pl.filter = kFilterPswar;
+        pl.flen = kf;
+        pl.pswar_bits = pk->bits;
+        pl.pswar_exact = kf == m;
+        a.cpw = chain_max;
+        a.stride = kf;
+        a.anchor = (desc->anchor == SB_ANCHOR_SUFFIX) ? m - kf : 0;
+        const uint32_t unit = pk->bits == 1 ? 0xffffffffu : 0x55555555u;
+        for (int k = 0; k < kf; k++) a.H[k] = (uint32_t)code[x[a.anchor + k]] * unit;
+        return;
+    }
     const int cpw = pk && pk->packed ? 32 / pk->bits : 16;  // characters per packed word
     /* a 4-bit copy only halves the bytes: it pays from K = 2 on (m >= 23), not for K = 1 or half-words, whose
      * probe-bound rates (3.6 / 2-3.4 TB/s of packed bytes) would then be no better than the byte kernels */
@@ -528,11 +568,28 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
 /* what sb_last_timing reports: see include/smart_b200.h */
 int filter_kind_of(const Plan &pl)
 {
+    if (pl.filter == kFilterPswar) return kFilterPswar + (pl.pswar_bits == 2 ? 40 : 0) + pl.flen;
     if (pl.filter == kFilterPair) return 20 + pl.flen;
     if (pl.filter >= kFilterPacked) return pl.filter;
     if (pl.filter >= 4 && pl.filter < kFilterSkip && pl.flen != pl.filter) return pl.filter * 100 + pl.flen;
     return pl.filter;
 }
+
+/* scan_pswar<BITS, KF, EXACT> instances: [KF][EXACT] */
+using PswarFn = void (*)(const sb::ScanArgs);
+#define SB_PSWAR_ROW(B, K) {sb::scan_pswar_kernel<B, K, false>, sb::scan_pswar_kernel<B, K, true>}
+const PswarFn kPswar1[33][2] = {
+    {nullptr, nullptr},   SB_PSWAR_ROW(1, 1),  SB_PSWAR_ROW(1, 2),  SB_PSWAR_ROW(1, 3),  SB_PSWAR_ROW(1, 4),  SB_PSWAR_ROW(1, 5),
+    SB_PSWAR_ROW(1, 6),   SB_PSWAR_ROW(1, 7),  SB_PSWAR_ROW(1, 8),  SB_PSWAR_ROW(1, 9),  SB_PSWAR_ROW(1, 10), SB_PSWAR_ROW(1, 11),
+    SB_PSWAR_ROW(1, 12),  SB_PSWAR_ROW(1, 13), SB_PSWAR_ROW(1, 14), SB_PSWAR_ROW(1, 15), SB_PSWAR_ROW(1, 16), SB_PSWAR_ROW(1, 17),
+    SB_PSWAR_ROW(1, 18),  SB_PSWAR_ROW(1, 19), SB_PSWAR_ROW(1, 20), SB_PSWAR_ROW(1, 21), SB_PSWAR_ROW(1, 22), SB_PSWAR_ROW(1, 23),
+    SB_PSWAR_ROW(1, 24),  SB_PSWAR_ROW(1, 25), SB_PSWAR_ROW(1, 26), SB_PSWAR_ROW(1, 27), SB_PSWAR_ROW(1, 28), SB_PSWAR_ROW(1, 29),
+    SB_PSWAR_ROW(1, 30),  SB_PSWAR_ROW(1, 31), SB_PSWAR_ROW(1, 32)};
+const PswarFn kPswar2[17][2] = {
+    {nullptr, nullptr},   SB_PSWAR_ROW(2, 1),  SB_PSWAR_ROW(2, 2),  SB_PSWAR_ROW(2, 3),  SB_PSWAR_ROW(2, 4),  SB_PSWAR_ROW(2, 5),
+    SB_PSWAR_ROW(2, 6),   SB_PSWAR_ROW(2, 7),  SB_PSWAR_ROW(2, 8),  SB_PSWAR_ROW(2, 9),  SB_PSWAR_ROW(2, 10), SB_PSWAR_ROW(2, 11),
+    SB_PSWAR_ROW(2, 12),  SB_PSWAR_ROW(2, 13), SB_PSWAR_ROW(2, 14), SB_PSWAR_ROW(2, 15), SB_PSWAR_ROW(2, 16)};
+#undef SB_PSWAR_ROW
 
 /* launch the scan of one buffer on `stream`; the caller has set the device */
 cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStream_t stream)
@@ -541,11 +598,29 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
     int per_sm;
     size_t group;
     const bool want_pos = a.pos != nullptr;
+    if (pl.filter == kFilterPswar) {
+        const int B = pl.pswar_bits, KF = pl.flen, ex = pl.pswar_exact ? 1 : 0;
+        const PswarFn fn = B == 1 ? kPswar1[KF][ex] : kPswar2[KF][ex];
+        int &occ = c.occ_pswar[B - 1][KF][ex];
+        if (!occ) {
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, sb::kThreads, 0) != cudaSuccess || nb < 1) nb = 1;
+            occ = nb;
+        }
+        const unsigned long long end = (unsigned long long)a.hi + a.anchor + KF;  // characters the chain can touch
+        const unsigned long long words = (end + a.cpw - 1) / a.cpw;
+        static_assert(kGroupPacked == 4 * 1024, "scan_pswar / scan_packed / scan_swar step U = 4 KiB per warp");
+        a.ngroups = (words * 4 + kGroupPacked - 1) / kGroupPacked;
+        const unsigned long long want_ctas = (a.ngroups + (sb::kThreads / 32) - 1) / (sb::kThreads / 32);
+        const unsigned g = (unsigned)std::max(1ull, std::min(want_ctas, (unsigned long long)c.sms * occ));
+        fn<<<g, sb::kThreads, 0, stream>>>(a);
+        return cudaGetLastError();
+    }
     if (pl.filter >= kFilterPacked) {
         if (!pl.packed_K) return cudaSuccess;  // pattern outside the text's alphabet: the count stays 0
         const unsigned long long end = (unsigned long long)a.hi + a.anchor + a.stride + 31;  // characters that matter (upper bound)
         a.nsamples = (end + a.cpw - 1) / a.cpw;                                               // packed words
-        a.ngroups = (a.nsamples * 4 + kGroupLong - 1) / kGroupLong;
+        a.ngroups = (a.nsamples * 4 + kGroupPacked - 1) / kGroupPacked;
         const int ki = pl.packed_K == 1 ? 0 : pl.packed_K == 2 ? 1 : pl.packed_K == 4 ? 2 : 3;
         const unsigned long long want_ctas = (a.ngroups + (sb::kThreads / 32) - 1) / (sb::kThreads / 32);
         const int occ = pl.packed_half ? c.occ_packed_half[pl.packed_half - 1] : c.occ_packed[ki];
@@ -583,7 +658,7 @@ cudaError_t launch_scan(const DevCtx &c, const Plan &pl, sb::ScanArgs a, cudaStr
     const bool swar_dense = !pl.sparse && !want_pos;
     if (swar) {
         a.period = 1;  // the kernel's multiplier-by-one (see scan_swar_kernel)
-        group = kGroupLong;
+        group = kGroupPacked;
         a.ngroups = ((unsigned long long)a.hi + group - 1) / group;
         per_sm = c.occ_swar[(a.m - 1) * 2 + (swar_dense ? 1 : 0)];
     } else if (pl.filter <= kFilterWindow16) {

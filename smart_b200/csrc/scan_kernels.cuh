@@ -926,6 +926,111 @@ __global__ void __launch_bounds__(kThreads) scan_packed_half_kernel(const __grid
     block_reduce_count(a, cnt, nver);
 }
 
+/* ===================================================================== scan_pswar<BITS, KF, EXACT> */
+
+/* Short patterns on the 1-/2-bit recoding, SIMD within a register: CPW = 32/BITS start positions per instruction.
+ * For packed word q (characters CPW*q ..) and pattern character k, the word S_k = funnelshift(W[q], W[q+1], BITS*k)
+ * holds text character p+k at the lane (bit field) of start position p, so
+ *     BITS = 1:  acc  &= ~(S_k ^ splat(x[k]))     one LOP3 per pattern character, acc = match mask
+ *     BITS = 2:  diff |=  (S_k ^ splat(x[k]))     one LOP3; a lane of diff is 00 iff all characters matched
+ * cost 1 SHF + 1 LOP3 per pattern character for 32 (sigma = 2) or 16 (sigma <= 4) start positions, on 1/8 or 1/4 of
+ * the bytes: the per-position window kernels this replaces spent a SHF + IMAD + ISETP per POSITION (ALU-bound at
+ * 3.5-5.2 TB/s).  KF = number of pattern characters in the chain (KF*BITS <= 32, one halo word).
+ *   EXACT (KF == m): the mask IS the set of occurrences: counted with POPC in registers, nothing to verify
+ *                    (this is also the linear-time path for texts where every position matches);
+ *   !EXACT (KF < m): the chain is a KF-character filter (chosen to carry >= 20 bits) on x[anchor .. anchor+KF);
+ *                    surviving positions are verified on the byte text.
+ * a.H[k] = splat of the code of x[anchor+k]; a.stride = KF (unused by the kernel, kept for the launch arithmetic). */
+template <int BITS>
+__device__ __noinline__ uint2 pswar_matches(const ScanArgs &a, uint32_t mask, long long pbase, bool exact)
+{
+    unsigned cnt = 0, nver = 0;
+    while (mask) {
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const long long j = pbase + b / BITS - a.anchor;
+        if (j < 0 || j >= a.hi) continue;
+        if (!exact) {
+            nver++;
+            if (!lane_verify(a, j, 0)) continue;
+        }
+        cnt++;
+        emit_match(a, j);
+    }
+    return make_uint2(cnt, nver);
+}
+
+template <int BITS, int KF, bool EXACT>
+__global__ void __launch_bounds__(kThreads) scan_pswar_kernel(const __grid_constant__ ScanArgs a)
+{
+    static_assert(BITS * KF <= 32 && KF >= 1, "the chain must fit one halo word");
+    constexpr int U = 4;
+    constexpr int CPW = 32 / BITS;
+    constexpr uint32_t LANES = BITS == 1 ? 0xffffffffu : 0x55555555u;  // bit 0 of every character lane
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long warp = ((unsigned long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * kThreads) >> 5;
+    const uint8_t *pk = reinterpret_cast<const uint8_t *>(a.packed);
+    unsigned cnt = 0, nver = 0;
+
+    for (unsigned long long g = warp; g < a.ngroups; g += nwarps) {
+        const uint8_t *p = pk + g * (U * 1024ull) + lane * 32;
+        V8 v[U];
+#pragma unroll
+        for (int c = 0; c < U; c++) v[c] = ldg_stream256(p + c * 1024);
+        uint32_t gn = 0;
+        if (KF > 1 && lane == 0) gn = __ldg(reinterpret_cast<const uint32_t *>(pk + (g + 1) * (U * 1024ull)));
+#pragma unroll
+        for (int c = 0; c < U; c++) {
+            uint32_t W[9];
+#pragma unroll
+            for (int i = 0; i < 8; i++) W[i] = v[c].w[i];
+            W[8] = 0u;
+            if (KF > 1) {
+                const uint32_t nxt = (c + 1 < U) ? v[(c + 1 < U) ? c + 1 : c].w[0] : gn;
+                W[8] = __shfl_sync(kFull, lane == 0 ? nxt : v[c].w[0], (lane + 1) & 31);
+            }
+            // first text character of this lane's vector, and whether all its start positions are owned
+            const long long pbase = (long long)(((g * (U * 1024ull) + c * 1024 + lane * 32) >> 2) * CPW);
+            const bool inside = pbase - a.anchor >= 0 && pbase + 8 * CPW - a.anchor <= a.hi;
+            uint32_t mk[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (BITS == 1) {
+                    uint32_t acc = ~(W[q] ^ a.H[0]);
+#pragma unroll
+                    for (int k = 1; k < KF; k++) acc &= ~(__funnelshift_r(W[q], W[q + 1], k) ^ a.H[k]);
+                    mk[q] = acc;
+                } else {
+                    uint32_t diff = W[q] ^ a.H[0];
+#pragma unroll
+                    for (int k = 1; k < KF; k++) diff |= __funnelshift_r(W[q], W[q + 1], BITS * k) ^ a.H[k];
+                    mk[q] = ~(diff | (diff >> 1)) & LANES;
+                }
+            }
+            if (EXACT && inside && !a.pos) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) cnt += __popc(mk[q]);
+                continue;
+            }
+            uint32_t any = mk[0];
+#pragma unroll
+            for (int q = 1; q < 8; q++) any |= mk[q];
+            if (any != 0u && pbase - a.anchor < a.hi) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    if (mk[q]) {
+                        const uint2 r = pswar_matches<BITS>(a, mk[q], pbase + q * CPW, EXACT);
+                        cnt += r.x;
+                        nver += r.y;
+                    }
+                }
+            }
+        }
+    }
+    block_reduce_count(a, cnt, nver);
+}
+
 /* ===================================================================== scan_multi<B> */
 
 /* Multi-pattern scan: ALL `npat` patterns of one length are counted in ONE pass over

@@ -63,4 +63,4 @@ def test_our_arm_json_small():
     for m in (8, 64, 1024):
         assert len({r["count"] for r in c4["results"] if r["m"] == m}) == 1
     assert all(r["same_as_per_rank_sum"] for r in c4["inprocess"]["results"])
-    assert abs(d["value"] / d["value_kernels_only"] - 1) < 0.1
+    assert d["value"] <= d["value_kernels_only"] * 1.001  # the step includes the gaps between its kernels

@@ -15,7 +15,7 @@ from golden_texts import ALGOS, GOLDEN, TEXT_NAMES, make_patterns, make_text, ex
 pytestmark = pytest.mark.gpu
 
 # filter kinds reported by sb_last_timing: 0 scan_swar, 1 scan_window8, 4/8/16/32 scan_block<B>, 23..28 scan_block<2,L>
-FILTERS = {0: 0, 1: sb.FLAG_FILTER_SHIFT, 2: sb.FLAG_FILTER_B2, 4: sb.FLAG_FILTER_B4, 8: sb.FLAG_FILTER_B8, 16: sb.FLAG_FILTER_B16,
+FILTERS = {0: sb.FLAG_NO_PACK, 1: sb.FLAG_FILTER_SHIFT, 2: sb.FLAG_FILTER_B2, 4: sb.FLAG_FILTER_B4, 8: sb.FLAG_FILTER_B8, 16: sb.FLAG_FILTER_B16,
            32: sb.FLAG_FILTER_B32, 408: sb.FLAG_FILTER_B4L8, 416: sb.FLAG_FILTER_B4L16, 816: sb.FLAG_FILTER_B8L16}
 
 
@@ -186,6 +186,56 @@ def test_sharded_counts_equal_unsharded(oracle):
         assert total == want
 
 
+def test_async_submit_collect(oracle):
+    """sb_search64_submit / sb_search_collect: many searches in flight over one resident text, collected in any
+    order, each with its own counters; results equal the blocking call and the oracle."""
+    y = sb.textgen_host(0, 5_000_000, 4, 17)
+    rng = np.random.default_rng(4)
+    with sb.Text.upload(y) as t, sb.Text.upload(y, devices=[0, 0, 0]) as t3:
+        jobs = []
+        for i in range(120):
+            m = int(rng.choice([1, 3, 5, 8, 12, 16, 24, 40, 64, 200, 1000]))
+            k = int(rng.integers(0, y.size - m))
+            x = y[k:k + m].copy()
+            if i % 7 == 0:
+                x[-1] = 9  # a byte the text lacks: finished at submit time, count 0
+            a = ("bf", "kmp", "hor", "so", "hash3", "qf23", "bm")[i % 7]
+            fl = (0, sb.FLAG_NO_PACK, sb.FLAG_NO_PACK | sb.FLAG_NO_SKIP)[i % 3]
+            jobs.append((a, x, fl, t if i % 2 else t3))
+        tickets = [sb.submit(a, tt, x, flags=fl) for a, x, fl, tt in jobs]
+        x_reused = jobs[0][1]
+        x_reused[:] = 0  # the pattern was copied at submit time
+        jobs[0] = (jobs[0][0], None, jobs[0][2], jobs[0][3])
+        assert len(set(tickets)) == len(tickets)
+        for i in reversed(range(len(jobs))):
+            a, x, fl, tt = jobs[i]
+            r = sb.collect(tickets[i])
+            if x is None:
+                continue
+            want = expected(a, x.size, oracle.bf_count(x, y), y.size)
+            assert r.count == want, (i, a, x.size, fl)
+            if want > 0:
+                assert r.run_ms > 0 and sb.last_timing().kernels_launched >= 1
+        # a collected ticket is gone; the positions flag belongs to the blocking call
+        with pytest.raises(sb.SmartB200Error):
+            sb.collect(tickets[0])
+        with pytest.raises(sb.SmartB200Error):
+            sb.submit("bf", t, y[:8].copy(), flags=sb.FLAG_POSITIONS)
+        # -1 domains travel through the ticket
+        assert sb.collect(sb.submit("hash8", t, y[:5].copy())).count == -1
+        # 256 searches may be outstanding; the 257th is refused until one is collected
+        x = y[777:777 + 16].copy()
+        want = oracle.bf_count(x, y)
+        tickets = [sb.submit("bf", t, x) for _ in range(256)]
+        with pytest.raises(sb.SmartB200Error):
+            sb.submit("bf", t, x)
+        assert sb.collect(tickets.pop()).count == want
+        tickets.append(sb.submit("kmp", t3, x))
+        assert all(sb.collect(tk).count == want for tk in tickets)
+        # the blocking call is submit + collect
+        assert sb.search("bf", t, x).count == want
+
+
 def test_low_entropy_windows(oracle):
     """sigma=2: 8 bytes carry 8 bits, so 12 <= m < 31 uses the 12/16-byte per-position windows (kinds 2, 3);
     frequent short patterns are counted in registers (dense mode).  All against the oracle."""
@@ -204,6 +254,52 @@ def test_low_entropy_windows(oracle):
         # 19..22: 16-byte fingerprints at 4-byte alignment; 23..30: at 8-byte alignment; 31+: disjoint 16-byte blocks
         assert [kinds[m] for m in (5, 8, 9, 12, 13, 15, 16, 17, 19, 23, 30, 31)] == \
             [1, 1, 2, 2, 3, 3, 3, 3, 416, 816, 816, 16]
+
+
+def test_swar_chain_on_the_packed_copy(oracle):
+    """sigma <= 4 texts, short patterns: scan_pswar counts 32 / 16 start positions per instruction on the 1-/2-bit
+    recoding (kinds 500+KF / 540+KF).  Every m of its range, exact chains (KF == m, dense matches counted in
+    registers) and filter chains (KF < m, verified on the byte text), prefix and suffix anchors, text ends,
+    shard seams, sorted positions - all against the oracle."""
+    rng = np.random.default_rng(2)
+    n = 700_001
+    skew2 = (rng.random(n) < 0.9).astype(np.uint8)  # 0.15 + 0.47 bits per character: long exact chains
+    runs4 = np.repeat(rng.integers(0, 4, n // 40 + 1, dtype=np.uint8), 40)[:n].copy()
+    texts = {"gen2": (sb.textgen_host(0, n, 2, 6), 1), "gen4": (sb.textgen_host(0, n, 4, 5), 2),
+             "gen3": (sb.textgen_host(0, n, 3, 8) + 65, 2), "skew2": (skew2, 1), "runs4": (runs4, 2),
+             "ones": (np.full(n, 7, dtype=np.uint8), 1)}
+    for name, (y, bits) in texts.items():
+        with sb.Text.upload(y) as t, sb.Text.upload(y, devices=[0, 0, 0]) as t3:
+            assert t.packed_bits == bits, name
+            mmax = 30 if bits == 1 else 22
+            base3, own3, _ = sb.shard_range(n, 3, 1)
+            for m in list(range(1, mmax + 1)):
+                for k in (0, n - m, base3 + own3 - m // 2, n // 2 + 5):
+                    x = y[k:k + m].copy()
+                    want = oracle.bf_positions(x, y)
+                    for algo in ("bf", "hor"):
+                        r = sb.search(algo, t, x)
+                        kind = sb.last_timing().filter_kind
+                        assert r.count == want.size, (name, m, k, algo, kind)
+                        assert kind - (500 if bits == 1 else 540) in range(1, min(m, 32 // bits) + 1), (name, m, kind)
+                    assert sb.search("kmp", t3, x).count == want.size, (name, m, k)
+                    r = sb.search("qs", t3, x, flags=sb.FLAG_POSITIONS, positions_cap=want.size + 1)
+                    assert np.array_equal(r.positions, want), (name, m, k)
+                    if want.size > 2:  # a short buffer still receives the smallest positions
+                        r = sb.search("bf", t, x, flags=sb.FLAG_POSITIONS, positions_cap=2)
+                        assert r.count == want.size and np.array_equal(r.positions, want[:2]), (name, m)
+                # (probably) absent: one character of the alphabet swapped in
+                x = y[1000:1000 + m].copy()
+                x[m // 2] = y[y != x[m // 2]][0] if (y != x[m // 2]).any() else x[m // 2]
+                assert sb.search("so", t, x).count == oracle.bf_count(x, y), (name, m)
+    # the chain length follows the text's entropy: uniform sigma=2 stops at 20 characters, sigma=4 at 10
+    with sb.Text.generate(1 << 20, 2, 3) as t2, sb.Text.generate(1 << 20, 4, 3) as t4:
+        for t, sigma, kf in ((t2, 2, 20), (t4, 4, 10)):
+            for m in (5, kf, kf + 1, kf + 5):
+                x = sb.textgen_host(4321, m, sigma, 3)
+                assert sb.search("bf", t, x).count == sb.search("bf", t, x, flags=sb.FLAG_NO_PACK).count >= 1
+                sb.search("bf", t, x)
+                assert sb.last_timing().filter_kind == (500 if sigma == 2 else 540) + min(m, kf), (sigma, m)
 
 
 def test_skip_kernel_is_selected_and_exact(oracle):
@@ -464,8 +560,8 @@ def test_packed_scan_of_small_alphabet_texts(oracle):
                         r = sb.search(algo, t, x)
                         kind = sb.last_timing().filter_kind
                         assert r.count == want.size, (name, m, k, algo, kind)
-                        if m < cpw - 1:  # too short for a half-word fingerprint
-                            assert kind < 100 or kind in (408, 416, 816), (name, m, algo, kind)
+                        if m <= (30 if cpw == 32 else 22):  # the SWAR chain on the recoding: a ~20-bit filter
+                            assert kind == (500 + min(m, 20) if cpw == 32 else 540 + min(m, 10)), (name, m, algo, kind)
                         elif m < 2 * cpw - 1:  # half-words, both halves or the low one
                             assert kind == (311 if m < cpw + cpw // 2 - 1 else 312), (name, m, algo, kind)
                         elif algo == "bf" or m < (1200 if cpw == 32 else 448):
@@ -485,8 +581,7 @@ def test_packed_scan_of_small_alphabet_texts(oracle):
                 # a byte the text does not contain: nothing is scanned
                 x[m // 2] = 200
                 assert sb.search("kmp", t, x).count == 0
-                if m >= cpw - 1:
-                    assert sb.last_timing().filter_kind == 300 and sb.last_timing().kernels_launched == 0
+                assert sb.last_timing().filter_kind == 300 and sb.last_timing().kernels_launched == 0
     # periodic text and pattern: few distinct words -> the byte kernels keep it (candidates spread over all warps)
     y = np.frombuffer(b"ab" * 100000, dtype=np.uint8).copy()
     with sb.Text.upload(y) as t:

@@ -85,7 +85,7 @@ def packed_text_and_pattern(draw):
         noise = rng.integers(0, n, n // 200)
         idx[noise] = rng.integers(0, nsym, noise.size)
     y = alphabet[idx]
-    m = draw(st.integers(7, 1300))
+    m = draw(st.one_of(st.integers(1, 40), st.integers(7, 1300)))  # the short ones: scan_pswar on the 1-/2-bit copy
     k = draw(st.sampled_from([0, n - m, int(rng.integers(0, n - m))]))
     x = y[k:k + m].copy()
     mut = draw(st.sampled_from(["none", "last", "first", "middle", "foreign"]))
