@@ -123,7 +123,7 @@ struct DevCtx {                               // per-device scratch, created on 
     int occ_multi[3] = {0, 0, 0};             // resident CTAs/SM for scan_multi<4,8,16>
     int occ_skip[3] = {0, 0, 0};              // resident CTAs/SM for scan_skip<8,16,32>
     // host-buffer streaming path
-    uint8_t *d_chunk[2] = {nullptr, nullptr};
+    uint8_t *d_chunk[2] = {nullptr, nullptr};   // each preceded by kPadBytes of zeros (see text_alloc)
     size_t chunk_cap = 0;
     cudaStream_t cstream[2] = {nullptr, nullptr};
 
@@ -236,6 +236,7 @@ size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Shard {
     int dev = 0;
+    uint8_t *d_alloc = nullptr;   // cudaMalloc'ed block: kPadBytes of zeros, then the text (d_text)
     uint8_t *d_text = nullptr;
     size_t cap = 0;       // allocated bytes (group multiple + one spare group, zero padded)
     size_t base = 0;      // global offset of local byte 0
@@ -264,6 +265,21 @@ double collision_bits(const unsigned long long *hist)
     double bits = 0.5 * (-log2(s2) - log2(pmax));
     if (bits < 0.05) bits = 0.05;
     return bits > 8.0 ? 8.0 : bits;
+}
+
+/* relative frequencies + a signature of them (texts with the same statistics share cached plans) */
+void freq_from_hist(const double *hist, float *freq, uint64_t *sig)
+{
+    double tot = 0;
+    for (int c = 0; c < 256; c++) tot += hist[c];
+    uint64_t h = 0xCBF29CE484222325ull;
+    for (int c = 0; c < 256; c++) {
+        freq[c] = tot > 0 ? (float)(hist[c] / tot) : 1.0f / 256;
+        uint32_t bits32;
+        memcpy(&bits32, &freq[c], 4);
+        h = (h ^ bits32) * 0x100000001B3ull;
+    }
+    *sig = h ? h : 1;
 }
 
 uint32_t load_le32(const unsigned char *p, int avail)
@@ -307,7 +323,7 @@ uint32_t fingerprint_pair(const unsigned char *p, int L)
  * lets ~2^-(L*bits) of all start positions through to verification: pick the shortest L that carries
  * >= 20 bits (with the widest alignment B <= L that still fits the pattern), else the longest feasible L if it
  * carries >= 14 bits (or is 32), else a per-position window. */
-int choose_filter(int m, unsigned flags, double bits, int *flen)
+int choose_filter(int m, unsigned flags, double bits, int *flen, bool periodic = false)
 {
     static const int variants[7][2] = {{4, 4}, {8, 8}, {4, 8}, {16, 16}, {8, 16}, {4, 16}, {32, 32}};  // by L, widest B first
     *flen = 0;
@@ -331,6 +347,13 @@ int choose_filter(int m, unsigned flags, double bits, int *flen)
         if (L * bits >= 20.0) return *flen = L, B;
     }
     if (bestL && (bestL * bits >= 14.0 || bestL > 16)) return *flen = bestL, bestB;
+    /* a periodic pattern (period <= m/2) too long for an exact window: the block kernels count its dense runs
+     * arithmetically (extend_run) and pre-check 32 candidates at a time, the per-position window kernels would
+     * verify every position of a run lane by lane */
+    if (bestL && periodic && m >= 17) return *flen = bestL, bestB;
+    /* nearly constant texts (a 16-byte window carries < 8 bits): every position passes any fingerprint; the block
+     * kernels probe 32 consecutive candidates per load instruction, the window kernels verify lane by lane */
+    if (bestL && m >= 17 && 16.0 * bits < 8.0) return *flen = bestL, bestB;
     // 5 <= m < 11 (or 4 bytes too weak): windows of min(8, m-1) bytes at every even position
     if (m >= 5) {
         const int L = m - 1 < 8 ? m - 1 : 8;
@@ -405,10 +428,13 @@ struct Plan {
 };
 
 void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m, unsigned flags, double bits,
-               const PackInfo *pk = nullptr)
+               const PackInfo *pk = nullptr, const float *freq = nullptr)
 {
     memset(&pl.args, 0, sizeof pl.args);
-    pl.filter = choose_filter(m, flags, bits, &pl.flen);
+    static thread_local int border[SB_XSIZE + 1];
+    sb_prep_mp(x, m, border);  // the border table (mp.c:26-35): the pattern's smallest period is m - border[m]
+    const int period = m - border[m];
+    pl.filter = choose_filter(m, flags, bits, &pl.flen, period * 2 <= m && !(flags & SB_FLAG_NO_PERIOD));
     pl.sparse = m * bits >= dense_bits() && !(flags & SB_FLAG_DENSE);  // scan_swar; scan_window decides below
     pl.skip_grams = 0;
     pl.packed_K = 0;
@@ -419,12 +445,23 @@ void make_plan(Plan &pl, const sb_algo_desc *desc, const unsigned char *x, int m
     a.m = m;
     a.nwords = (m + 3) / 4;
     a.tailmask = (m & 3) ? ((1u << (8 * (m & 3))) - 1u) : 0xffffffffu;
-    {   /* the pattern's smallest period, from the border table (mp.c:26-35): used on the device by the
-         * period-aware verification of scan_block when the pattern is at least two periods long */
-        static thread_local int border[SB_XSIZE + 1];
-        sb_prep_mp(x, m, border);
-        const int period = m - border[m];
-        a.period = (period * 2 <= m && !(flags & SB_FLAG_NO_PERIOD)) ? period : 0;
+    /* used on the device by the period-aware verification and the run counting of scan_block when the pattern is
+     * at least two periods long */
+    a.period = (period * 2 <= m && !(flags & SB_FLAG_NO_PERIOD)) ? period : 0;
+    {   /* probe word: the pattern word with the byte that is rarest in the text (ties: the first one) */
+        int r = m - 1;
+        if (freq) {
+            float best = 2.0f;
+            for (int i = 0; i < m; i++)
+                if (freq[x[i]] < best) {
+                    best = freq[x[i]];
+                    r = i;
+                }
+        }
+        a.probe = r / 4;
+        /* no byte of the pattern is rare in this text (>= 1/32 of the samples): the third probe word would reject
+         * next to nothing, the pre-check keeps to the first and the last word */
+        if (freq && freq[x[r]] >= 1.0f / 32) a.probe = -1;
     }
     /* Sub-linear sampling for the skip families: one G-byte gram every `stride` bytes (a multiple of the
      * 32-byte DRAM sector), G wide enough that a text gram rarely equals one of `stride` pattern grams. */
@@ -837,6 +874,7 @@ struct PlanEntry {
     int anchor = 0, m = 0;
     unsigned flags = 0;
     double bits = 0;
+    uint64_t sig = 0;   // signature of the text's byte histogram (the probe word depends on it)
     PackInfo pack;
     unsigned long long stamp = 0;
     unsigned char x[SB_XSIZE];
@@ -853,7 +891,7 @@ bool same_pack(const PackInfo &a, const PackInfo &b)
 }
 
 void plan_get(Plan &out, const sb_algo_desc *desc, const unsigned char *x, int m, unsigned flags, double bits,
-              const PackInfo *pk)
+              const PackInfo *pk, const float *freq = nullptr, uint64_t sig = 0)
 {
     static const PackInfo none;
     const PackInfo &pack = pk ? *pk : none;
@@ -863,7 +901,7 @@ void plan_get(Plan &out, const sb_algo_desc *desc, const unsigned char *x, int m
     PlanEntry *lru = nullptr;  // an unused entry, else the least recently used one
     for (int i = 0; i < kPlanCache; i++) {
         PlanEntry &e = g_plans[i];
-        if (e.valid && e.anchor == desc->anchor && e.m == m && e.flags == flags && e.bits == bits && same_pack(e.pack, pack) &&
+        if (e.valid && e.anchor == desc->anchor && e.m == m && e.flags == flags && e.bits == bits && e.sig == sig && same_pack(e.pack, pack) &&
             memcmp(e.x, x, (size_t)m) == 0) {
             e.stamp = ++g_plan_clock;
             out = e.plan;
@@ -871,8 +909,9 @@ void plan_get(Plan &out, const sb_algo_desc *desc, const unsigned char *x, int m
         }
         if (!lru || (lru->valid && (!e.valid || e.stamp < lru->stamp))) lru = &e;
     }
-    make_plan(lru->plan, desc, x, m, flags, bits, pk);
+    make_plan(lru->plan, desc, x, m, flags, bits, pk, freq);
     lru->valid = true;
+    lru->sig = sig;
     lru->anchor = desc->anchor;
     lru->m = m;
     lru->flags = flags;
@@ -910,6 +949,9 @@ struct sb_text {
     size_t n = 0;
     int nshards = 0;
     double bits = 8.0;  // collision entropy per byte (min over shards), from a sampled histogram
+    float freq[256];    // relative byte frequencies of the samples (all shards): the probe word of a plan
+    uint64_t sig = 0;   // signature of freq (plan cache key)
+    bool have_freq = false;
     bool present[256] = {false};  // byte values seen in the histogram samples (a guess, verified by pack2_kernel)
     PackInfo pack;      // the 2-bit recoding, when every byte of every shard is one of <= 4 values
     Shard sh[kMaxShards];
@@ -1013,9 +1055,17 @@ static sb_text *text_alloc(size_t n, const int *devices, int nparts, int first, 
             sb_text_free(t);
             return nullptr;
         }
-        if (cudaMalloc(&s.d_text, s.cap) != cudaSuccess) {
+        /* a zeroed front pad: the slow paths read probe words of candidates that start up to SB_XSIZE + 31 bytes
+         * BEFORE local byte 0 (start positions owned by the previous shard) without a bounds check */
+        if (cudaMalloc(&s.d_alloc, s.cap + 2 * sb::kPadBytes) != cudaSuccess) {  // + a back pad the same reads may touch
             set_err("cudaMalloc of a text shard failed%s%s");
-            s.d_text = nullptr;
+            s.d_alloc = nullptr;
+            sb_text_free(t);
+            return nullptr;
+        }
+        s.d_text = s.d_alloc + sb::kPadBytes;
+        if (cudaMemsetAsync(s.d_alloc, 0, sb::kPadBytes, c->stream) != cudaSuccess) {
+            set_err("cudaMemset of a text shard failed%s%s");
             sb_text_free(t);
             return nullptr;
         }
@@ -1090,6 +1140,7 @@ static bool text_try_pack(sb_text *t)
 static bool text_measure_bits(sb_text *t)
 {
     double bits = 8.0;
+    double total[256] = {0};
     for (int g = 0; g < t->nshards; g++) {
         Shard &s = t->sh[g];
         if (s.len < 4096) continue;
@@ -1105,9 +1156,14 @@ static bool text_measure_bits(sb_text *t)
         if (cudaMemcpyAsync(hist, c->d_hist, sizeof hist, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return false;
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) return false;
         bits = std::min(bits, collision_bits(hist));
-        for (int b = 0; b < 256; b++) t->present[b] = t->present[b] || hist[b] != 0;
+        for (int b = 0; b < 256; b++) {
+            t->present[b] = t->present[b] || hist[b] != 0;
+            total[b] += (double)hist[b];
+        }
     }
     t->bits = bits;
+    freq_from_hist(total, t->freq, &t->sig);
+    t->have_freq = true;
     return text_try_pack(t);
 }
 
@@ -1252,9 +1308,9 @@ void sb_text_free(sb_text *t)
 {
     if (!t) return;
     for (int g = 0; g < t->nshards; g++)
-        if (t->sh[g].d_text) {
+        if (t->sh[g].d_alloc) {
             cudaSetDevice(t->sh[g].dev);
-            cudaFree(t->sh[g].d_text);
+            cudaFree(t->sh[g].d_alloc);
             if (t->sh[g].d_packed) cudaFree(t->sh[g].d_packed);
         }
     delete t;
@@ -1371,7 +1427,7 @@ static long long submit_core(const sb_algo_desc *desc, const sb_text *t, const u
     /* ---- preprocessing stage: the plan (fingerprints, period, aux list) comes from the cache or is built ---- */
     const double t0 = now_ms();
     Plan pl;
-    plan_get(pl, desc, x, m, flags, t->bits, &t->pack);
+    plan_get(pl, desc, x, m, flags, t->bits, &t->pack, t->have_freq ? t->freq : nullptr, t->have_freq ? t->sig : 0);
     const double t1 = now_ms();
     tk.filter_kind = filter_kind_of(pl);
     tk.prep_ms = t1 - t0;
@@ -1539,7 +1595,7 @@ static long long search_positions(const sb_algo_desc *desc, const sb_text *t, co
 {
     const double t0 = now_ms();
     Plan pl;
-    plan_get(pl, desc, x, m, flags, t->bits, &t->pack);
+    plan_get(pl, desc, x, m, flags, t->bits, &t->pack, t->have_freq ? t->freq : nullptr, t->have_freq ? t->sig : 0);
     const double t1 = now_ms();
 
     DevCtx *ctx[kMaxShards];
@@ -1904,7 +1960,15 @@ long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned
     /* selectivity estimate from a host-side sample of the text (first 64 KiB) */
     unsigned long long hist[256] = {0};
     for (size_t i = 0, e = std::min<size_t>(n, 65536); i < e; i++) hist[y[i]]++;
-    plan_get(pl, desc, x, m, flags & ~SB_FLAG_POSITIONS, n >= 4096 ? collision_bits(hist) : 8.0, nullptr);
+    float freq[256];
+    uint64_t sig = 0;
+    {
+        double hd[256];
+        for (int b = 0; b < 256; b++) hd[b] = (double)hist[b];
+        freq_from_hist(hd, freq, &sig);
+    }
+    plan_get(pl, desc, x, m, flags & ~SB_FLAG_POSITIONS, n >= 4096 ? collision_bits(hist) : 8.0, nullptr,
+             n >= 4096 ? freq : nullptr, n >= 4096 ? sig : 0);
     const double t1 = now_ms();
 
     /* chunk buffers: 64 MiB of start positions + halo each, double buffered */
@@ -1913,16 +1977,18 @@ long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned
     const size_t need = round_up(chunk + kHalo, sb::kPadBytes) + sb::kPadBytes;
     if (c->chunk_cap < need) {
         for (int b = 0; b < 2; b++) {
-            if (c->d_chunk[b]) cudaFree(c->d_chunk[b]);
+            if (c->d_chunk[b]) cudaFree(c->d_chunk[b] - sb::kPadBytes);
             c->d_chunk[b] = nullptr;
         }
         c->chunk_cap = 0;
         for (int b = 0; b < 2; b++) {
-            if (cudaMalloc(&c->d_chunk[b], need) != cudaSuccess) {
+            uint8_t *blk = nullptr;
+            if (cudaMalloc(&blk, need + 2 * sb::kPadBytes) != cudaSuccess) {
                 set_err("cudaMalloc of a streaming chunk failed%s%s");
                 return SB_ERR_NOMEM;
             }
-            CU_TRY(cudaMemset(c->d_chunk[b], 0, need), SB_ERR_CUDA);
+            CU_TRY(cudaMemset(blk, 0, need + 2 * sb::kPadBytes), SB_ERR_CUDA);
+            c->d_chunk[b] = blk + sb::kPadBytes;
         }
         c->chunk_cap = need;
     }

@@ -41,6 +41,9 @@ constexpr int kThreads = 256;       // threads per CTA
 #ifndef SB_MINB
 #define SB_MINB 1                   // __launch_bounds__ min CTAs/SM for the streaming kernels (tuning knob)
 #endif
+#ifndef SB_PROBE_ROUNDS
+#define SB_PROBE_ROUNDS 4               // candidate rounds in flight in the slow path of scan_block (tuning knob)
+#endif
 constexpr int kPadBytes = 8192;     // every text buffer is zero padded to a multiple of this plus this much
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -88,6 +91,10 @@ struct ScanArgs {
     // Drives period-aware verification in scan_block: after a verified occurrence at j, a candidate at
     // j + k*period (< j + m) only needs its last k*period bytes compared.
     int period;
+    // word index of the pattern word that holds its RAREST byte (by the text's byte histogram): one of the three
+    // words the lane-parallel pre-check of a candidate looks at (first, last, rarest) before the exact verification;
+    // -1: no byte of the pattern is rare, two probe words
+    int probe;
 };
 
 constexpr int kBloomBits = 18;                       // 2^18-bit Bloom bitmap = 32 KiB of shared memory, 2 probes
@@ -179,6 +186,84 @@ __device__ __forceinline__ bool lane_verify(const ScanArgs &a, long long j, int 
     return true;
 }
 
+/* Pre-check of ONE candidate per lane: three probe words - the first and the last word of the pattern (an
+ * aligned-block fingerprint only sees an end byte in one of its B alignments) and the word with the rarest byte of
+ * the pattern (by the text's histogram).  Dense near-misses (a^(m-1)c in a^n: every position passes the
+ * fingerprints) are rejected here 32 consecutive positions per load instruction instead of one warp-cooperative
+ * verification each.  Returns 0 iff the words agree; an invalid candidate reads position 0 (always inside the
+ * buffer) and reports a difference, so the loads of several candidates are issued back to back. */
+struct ProbeWords {
+    int k1, last;        // word index of the rarest byte (-1: none); index of the last word
+    uint32_t x0, x1, xl; // pattern words: first, rarest, last
+    uint32_t m1;         // mask of the rarest word (the last pattern word may be partial)
+};
+
+__device__ __forceinline__ ProbeWords probe_words(const ScanArgs &a, const uint32_t *pat)
+{
+    ProbeWords w;
+    w.last = a.nwords - 1;
+    w.k1 = a.probe < 0 ? -1 : (a.probe < w.last ? a.probe : w.last);
+    w.x0 = __ldg(pat);
+    w.x1 = __ldg(pat + (w.k1 < 0 ? 0 : w.k1));
+    w.xl = __ldg(pat + w.last);
+    w.m1 = w.k1 == w.last ? a.tailmask : 0xffffffffu;
+    return w;
+}
+
+__device__ __forceinline__ uint32_t probe_diff(const ScanArgs &a, const ProbeWords &w, long long j, bool valid)
+{
+    const long long js = valid ? j : 0;
+    uint32_t d = (text_window32(a.text, js + 4ll * w.last) ^ w.xl) & a.tailmask;
+    if (w.k1 > 0 && w.k1 < w.last) d |= text_window32(a.text, js + 4ll * w.k1) ^ w.x1;
+    if (w.last > 0) d |= text_window32(a.text, js) ^ w.x0;
+    return valid ? d : 1u;
+}
+
+/* Linear-time handling of dense periodic matches (the job kmp.c:56-65 does with its failure function).
+ * x has smallest period p with 2p <= m, and text[j .. j+m) == x.  While text[e] == text[e-p] holds from e = j+m on,
+ * every j + i*p with j + i*p + m <= e is an occurrence, and NO other position inside the run is (a second
+ * alignment would give x a period shorter than p).  Streams that comparison forward and returns how many further
+ * occurrences j + i*p (i >= 1) start below own_end - the positions this warp's group owns.
+ * From the first word boundary at or after j+m on, text[i..] is read as aligned words and text[i-p..] as a funnel
+ * shift of two aligned words with ONE shift amount for the whole warp: 512 bytes per step, 12 coalesced loads a lane. */
+__device__ __forceinline__ long long extend_run(const ScanArgs &a, long long j, long long own_end, unsigned lane)
+{
+    const long long p = a.period;
+    if (own_end > a.hi) own_end = a.hi;
+    if (j + p >= own_end) return 0;
+    const long long lim = own_end - 1 + a.m;  // the text bytes that matter end here
+    long long e = j + a.m;
+    while ((e & 3) && e < lim && a.text[e] == a.text[e - p]) e++;  // up to 3 bytes (uniform loads) to a word boundary
+    if ((e & 3) || e >= lim) {                                      // the run ends before it
+        if (e > lim) e = lim;
+        const long long k0 = (e - a.m - j) / p, kmax0 = (own_end - 1 - j) / p;
+        return k0 < kmax0 ? k0 : kmax0;
+    }
+    const uint32_t *hi_w = reinterpret_cast<const uint32_t *>(a.text) + (e >> 2) + lane;       // text[e + 4*lane ..]
+    const uint32_t *lo_w = reinterpret_cast<const uint32_t *>(a.text) + ((e - p) >> 2) + lane;  // text[e - p + 4*lane ..]
+    const unsigned sh = (unsigned)((e - p) & 3) * 8u;
+    while (e < lim) {
+        int bad = 512;  // first differing byte among this lane's four words (word k of lane l: e + 128k + 4l)
+#pragma unroll
+        for (int k = 3; k >= 0; k--) {
+            const uint32_t dd = __ldg(hi_w + 32 * k) ^ __funnelshift_r(__ldg(lo_w + 32 * k), __ldg(lo_w + 32 * k + 1), sh);
+            if (dd) bad = 128 * k + 4 * (int)lane + ((__ffs(dd) - 1) >> 3);
+        }
+        const int first = __reduce_min_sync(kFull, bad);
+        if (first == 512) {
+            e += 512;
+            hi_w += 128;
+            lo_w += 128;
+            continue;
+        }
+        e += first;
+        break;
+    }
+    if (e > lim) e = lim;
+    const long long k = (e - a.m - j) / p, kmax = (own_end - 1 - j) / p;
+    return k < kmax ? k : kmax;
+}
+
 __device__ __forceinline__ void emit_match(const ScanArgs &a, long long j)
 {
     if (a.pos) {
@@ -220,6 +305,8 @@ struct CandResult {
     unsigned cnt, nver;
     long long run_j;  // start of the last verified occurrence seen by this warp (-1: none)
 };
+/* (run_j also marks how far the warp has DECIDED: candidates are visited in ascending order, and after a run of a
+ * periodic pattern was counted arithmetically run_j is its last occurrence - every candidate <= run_j is settled) */
 
 /* fingerprint of the L bytes starting at word q of W (L = 4, 8, 16 or 32; L == 32 only with q == 0) */
 template <int L>
@@ -261,53 +348,118 @@ __device__ __forceinline__ uint32_t slot_fp(const uint32_t *s, int i)
     return block_fp<L>(s, i * (B / 4));
 }
 
-/* Slow path of scan_block: some lane of this warp saw a fingerprint hit in its 32-byte vector.
- * For each such lane the whole warp re-derives which of the 32 (block, d) slots hit (one slot per
- * lane) and verifies each candidate cooperatively.  v0..v10: the lane's 8 words + up to 3 halo words. */
-template <int B, int L>
-__device__ __noinline__ CandResult block_candidates(const ScanArgs &a, uint32_t v0, uint32_t v1, uint32_t v2,
-                                                    uint32_t v3, uint32_t v4, uint32_t v5, uint32_t v6, uint32_t v7,
-                                                    uint32_t v8, uint32_t v9, uint32_t v10, long long voff, bool hit,
-                                                    unsigned lane, long long run_j)
+/* Slow path of scan_block: some lane of this warp saw a fingerprint hit in one of the 1 KiB chunks of its
+ * group; cbase = byte offset of that chunk.  Nothing but scalars is passed in and the call is made after the
+ * group's vectors are dead: every lane re-reads its 32-byte vector (+ halo) from memory - an L2 hit.  Steps:
+ *   1. lane-local: which of the 32 (block, d) slots of the vector hit -> a candidate start position each;
+ *   2. only when candidates are dense: three probe words per candidate, 32 consecutive candidates per load
+ *      instruction - dense near-misses die here (skipped for periodic patterns, whose dense candidates are runs);
+ *   3. warp-cooperative: the survivors, in ascending order, are verified exactly; after a verified occurrence of a
+ *      periodic pattern the rest of its run is counted arithmetically (extend_run) and everything up to the last
+ *      occurrence of the run is settled (run_j). */
+template <int B, int L, int GROUP>
+__device__ __noinline__ CandResult block_candidates(const ScanArgs &a, long long cbase, unsigned lane, long long run_j)
 {
-    // everything by value and the result returned: a by-reference vector would force the caller to
-    // keep a copy of every loaded vector in local memory (an STL per load in the hot loop)
-    const uint32_t vw[11] = {v0, v1, v2, v3, v4, v5, v6, v7, v8, v9, v10};
     constexpr int NWORDS = BlockShape<B, L>::NWORDS;
+    // GROUP = bytes of text one warp iteration owns: the candidates of this group start below own_end
+    const long long own_end = (cbase / GROUP + 1) * GROUP - (B - 1) - a.anchor;
     unsigned cnt = 0, nver = 0;
-    unsigned pending = __ballot_sync(kFull, hit);
-    while (pending) {
-        const int src = __ffs(pending) - 1;
-        pending &= pending - 1;
-        uint32_t s[11] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    {
+        const long long voff = cbase + lane * 32;
+        // 1. own slots.  Slot sl = blk*B + dd stands for the candidate voff + blk*B - (B-1-dd) - anchor: ascending in sl
+        unsigned own = 0;
+        {
+            uint32_t W[11] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(a.text + voff);
 #pragma unroll
-        for (int i = 0; i < NWORDS; i++) s[i] = __shfl_sync(kFull, vw[i], src);
-        const long long soff = __shfl_sync(kFull, voff, src);
-        // slot of this lane; d runs DOWN inside a block so that the candidate positions of a vector are
-        // visited in ascending order (the period-aware shortcut below relies on that)
-        const int blk = (int)lane / B, d = B - 1 - (int)lane % B;
-        uint32_t h = slot_fp<B, L>(s, 0);
+            for (int i = 0; i < NWORDS; i++) W[i] = __ldg(w + i);
 #pragma unroll
-        for (int i = 1; i < 32 / B; i++) h = (blk == i) ? slot_fp<B, L>(s, i) : h;
-        unsigned slots = __ballot_sync(kFull, h == a.H[d]);
-        while (slots) {
-            const int sl = __ffs(slots) - 1;
-            slots &= slots - 1;
-            const long long j = soff + (sl / B) * B - (B - 1 - sl % B) - a.anchor;
-            if (j >= 0 && j < a.hi) {
+            for (int blk = 0; blk < 32 / B; blk++) {
+                const uint32_t h = slot_fp<B, L>(W, blk);
+#pragma unroll
+                for (int dd = 0; dd < B; dd++) own |= (h == a.H[B - 1 - dd] ? 1u : 0u) << (blk * B + dd);
+            }
+        }
+        // 2. probe words - only when candidates are DENSE.  A handful of candidates (the normal case) and the
+        //    candidates of a periodic pattern (runs) go straight to step 3 ("direct").  Otherwise round r looks at
+        //    vector r: lane l takes its slot l, so the 32 lanes probe 32 CONSECUTIVE start positions (coalesced
+        //    loads), NP rounds in flight.  survT is the transposed survivor map: bit r of lane l <=> slot l of
+        //    vector r survives.
+        const bool direct = a.period != 0 || __reduce_add_sync(kFull, (unsigned)__popc(own)) <= 4u;
+        unsigned survT = 0;
+        if (!direct) {
+            constexpr int NP = SB_PROBE_ROUNDS;
+            const ProbeWords pw = probe_words(a, a.pat);
+            // The candidates of a lane are 32 bytes apart (j0 + 32r), so the word pointers and the funnel-shift
+            // amount are computed ONCE; a round costs two loads and a shift per probe word, no bounds check: reads
+            // before local byte 0 / past the text stay inside the buffer's zeroed pads (kPadBytes each side).
+            const long long j0 = cbase + (long long)lane - (B - 1) - a.anchor;  // slot l of vector 0
+            const uint32_t *pl = reinterpret_cast<const uint32_t *>(a.text) + (j0 >> 2) + pw.last;  // (floor shift)
+            const uint32_t *p1 = pl - pw.last + (pw.k1 > 0 ? pw.k1 : 0);
+            const uint32_t *p0 = pl - pw.last;
+            const unsigned sh = (unsigned)(j0 & 3) * 8u;
+            const bool use1 = pw.k1 > 0 && pw.k1 < pw.last, use0 = pw.last > 0;
+            // rounds whose candidate of this lane is an owned start position not yet settled
+            const long long lo_j = run_j + 1 > 0 ? run_j + 1 : 0;
+            const int r_lo = j0 >= lo_j ? 0 : (int)((lo_j - j0 + 31) >> 5);
+            const int r_hi = j0 >= a.hi ? -1 : (int)min(31ll, (a.hi - 1 - j0) >> 5);
+#pragma unroll 1
+            for (int r0 = 0; r0 < 32; r0 += NP, pl += 8 * NP, p1 += 8 * NP, p0 += 8 * NP) {
+                unsigned mk[NP];
+                unsigned anyv = 0;
+#pragma unroll
+                for (int k = 0; k < NP; k++) {
+                    mk[k] = __shfl_sync(kFull, own, r0 + k);
+                    anyv |= mk[k];
+                }
+                if (!anyv) continue;  // (uniform)
+                uint32_t d[NP];
+#pragma unroll
+                for (int k = 0; k < NP; k++) {
+                    d[k] = (__funnelshift_r(__ldg(pl + 8 * k), __ldg(pl + 8 * k + 1), sh) ^ pw.xl) & a.tailmask;
+                    if (use1) d[k] |= (__funnelshift_r(__ldg(p1 + 8 * k), __ldg(p1 + 8 * k + 1), sh) ^ pw.x1) & pw.m1;
+                    if (use0) d[k] |= __funnelshift_r(__ldg(p0 + 8 * k), __ldg(p0 + 8 * k + 1), sh) ^ pw.x0;
+                }
+#pragma unroll
+                for (int k = 0; k < NP; k++)
+                    survT |= (d[k] == 0 && ((mk[k] >> lane) & 1u) && r0 + k >= r_lo && r0 + k <= r_hi ? 1u : 0u) << (r0 + k);
+            }
+        }
+        // 3. exact verification of the survivors, vector by vector, slot by slot: ascending start positions
+        unsigned pending = direct ? __ballot_sync(kFull, own != 0) : __reduce_or_sync(kFull, survT);  // bit r: vector r
+        while (pending) {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const long long soff = cbase + src * 32;
+            if (cbase + 1024 - B - a.anchor <= run_j) break;  // a counted run settled the rest of the chunk
+            if (soff + 32 - B - a.anchor <= run_j) continue;
+            unsigned slots = direct ? __shfl_sync(kFull, own, src) : __ballot_sync(kFull, (survT >> src) & 1u);
+            while (slots) {
+                const int sl = __ffs(slots) - 1;
+                slots &= slots - 1;
+                const long long j = soff + (sl / B) * B - (B - 1 - sl % B) - a.anchor;
+                if (j <= run_j || j < 0 || j >= a.hi) continue;  // settled by a counted run, or not an owned start
                 nver += (lane == 0);
                 // Period-aware verification: x has period p and text[run_j .. run_j+m) == x.  If j = run_j + k*p
                 // lies inside that occurrence, text[j .. run_j+m) equals x[0 .. m-k*p) by periodicity and only
                 // the last k*p bytes remain to be compared (rounded down to a word).
                 int from_word = 0;
                 const long long delta = j - run_j;
-                if (a.period && run_j >= 0 && delta > 0 && delta < a.m && delta % a.period == 0)
-                    from_word = (a.m - (int)delta) >> 2;
+                if (a.period && run_j >= 0 && delta < a.m && delta % a.period == 0) from_word = (a.m - (int)delta) >> 2;
                 if (warp_verify(a, j, lane, nullptr, from_word)) {
                     run_j = j;
                     if (lane == 0) {
                         cnt++;
                         emit_match(a, j);
+                    }
+                    if (a.period) {  // count the rest of a periodic run arithmetically
+                        const long long k = extend_run(a, j, own_end, lane);
+                        if (k > 0) {
+                            if (lane == 0) cnt += (unsigned)k;
+                            if (a.pos)
+                                for (long long i = 1 + lane; i <= k; i += 32) emit_match(a, j + i * a.period);
+                            run_j = j + k * a.period;
+                        }
                     }
                 }
             }
@@ -358,9 +510,15 @@ __device__ __forceinline__ bool block_hit(const ScanArgs &a, const uint32_t *W)
     return hit;
 }
 
+/* The hot loop only NOTES that a chunk needs the slow path; the chunks are resolved after the group's last chunk,
+ * when no loaded vector is live any more (the slow path needs many registers: called mid-group it made the hot loop
+ * spill).  Deliberately a real call: the rarely taken branch around it ends the basic block of each chunk, which
+ * keeps the chunks' instruction streams in load order (one vote per group instead measured 2-19% slower). */
+__device__ __noinline__ unsigned note_hit(unsigned pend, int c) { return pend | (1u << c); }
+
 /* group = U x 1 KiB per warp */
 template <int B, int L, int U>
-__global__ void __launch_bounds__(kThreads, (L > B || B == 2) ? 3 : SB_MINB) scan_block_kernel(const __grid_constant__ ScanArgs a)
+__global__ void __launch_bounds__(kThreads, 3) scan_block_kernel(const __grid_constant__ ScanArgs a)
 {
     constexpr int HALO = BlockShape<B, L>::HALO;  // words needed from the next lane
     const unsigned lane = threadIdx.x & 31;
@@ -368,6 +526,7 @@ __global__ void __launch_bounds__(kThreads, (L > B || B == 2) ? 3 : SB_MINB) sca
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * kThreads) >> 5;
     unsigned cnt = 0, nver = 0;
     long long run_j = -1;  // last verified occurrence of this warp, for period-aware verification
+    unsigned pend = 0;     // bit c: chunk c of the current group passed the filter in some lane (warp-uniform)
 
     for (unsigned long long g = warp; g < a.ngroups; g += nwarps) {
         const uint8_t *p = a.text + g * (U * 1024ull) + lane * 32;
@@ -395,15 +554,20 @@ __global__ void __launch_bounds__(kThreads, (L > B || B == 2) ? 3 : SB_MINB) sca
                     W[8 + i] = __shfl_sync(kFull, lane == 0 ? nxt : v[c].w[i], (lane + 1) & 31);
                 }
             }
-            const bool hit = block_hit<B, L>(a, W);
-            if (__any_sync(kFull, hit)) {
-                const long long voff = (long long)(g * (U * 1024ull)) + c * 1024 + lane * 32;
-                const CandResult r = block_candidates<B, L>(a, W[0], W[1], W[2], W[3], W[4], W[5], W[6], W[7], W[8],
-                                                            W[9], W[10], voff, hit, lane, run_j);
-                cnt += r.cnt;
-                nver += r.nver;
-                run_j = r.run_j;
+            if (__any_sync(kFull, block_hit<B, L>(a, W))) pend = note_hit(pend, c);
+        }
+        if (pend) {  // rare: resolve the noted chunks in ascending order
+#pragma unroll 1
+            for (int c = 0; c < U; c++) {
+                const long long cbase = (long long)(g * (U * 1024ull)) + c * 1024;
+                if (((pend >> c) & 1u) && cbase + 1024 - B - a.anchor > run_j) {  // else: settled by a counted run
+                    const CandResult r = block_candidates<B, L, U * 1024>(a, cbase, lane, run_j);
+                    cnt += r.cnt;
+                    nver += r.nver;
+                    run_j = r.run_j;
+                }
             }
+            pend = 0;
         }
     }
     block_reduce_count(a, cnt, nver);
@@ -507,12 +671,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1) scan_block_tma_kernel(const __
             if (lane == 0) mbar_arrive(&empty[s]);  // the slice is in registers: the stage may be refilled
 #pragma unroll
             for (int c = 0; c < 2; c++) {
-                const bool hit = block_hit<B, B>(a, v[c].w);
-                if (__any_sync(kFull, hit)) {
-                    const long long voff = (long long)(tile * kTmaTile) + warp * 2048 + c * 1024 + lane * 32;
-                    const CandResult r = block_candidates<B, B>(a, v[c].w[0], v[c].w[1], v[c].w[2], v[c].w[3], v[c].w[4],
-                                                                v[c].w[5], v[c].w[6], v[c].w[7], 0u, 0u, 0u, voff, hit,
-                                                                lane, run_j);
+                if (__any_sync(kFull, block_hit<B, B>(a, v[c].w))) {
+                    const long long cbase = (long long)(tile * kTmaTile) + warp * 2048 + c * 1024;  // 2 KiB slice per warp
+                    const CandResult r = block_candidates<B, B, 2048>(a, cbase, lane, run_j);
                     cnt += r.cnt;
                     nver += r.nver;
                     run_j = r.run_j;
@@ -557,6 +718,9 @@ __device__ __noinline__ uint2 window_matches(const ScanArgs &a, unsigned mm, lon
         if (j >= a.hi) break;
         if (a.nwords > from) {
             nver++;
+            // the last word first: a near-miss at the far end must not cost a walk over the whole pattern
+            const int last = a.nwords - 1;
+            if ((text_window32(a.text, j + 4ll * last) ^ __ldg(a.pat + last)) & a.tailmask) continue;
             if (!lane_verify(a, j, from)) continue;
         }
         cnt++;
@@ -704,6 +868,7 @@ __device__ __noinline__ uint2 skip_candidates(const ScanArgs &a, uint32_t h, lon
 {
     unsigned cnt = 0, nver = 0;
     const uint2 *table = reinterpret_cast<const uint2 *>(a.aux + kBloomWords);
+    const ProbeWords pw = probe_words(a, a.pat);
     unsigned pending = __ballot_sync(kFull, hit);
     while (pending) {
         const int src = __ffs(pending) - 1;
@@ -715,19 +880,20 @@ __device__ __noinline__ uint2 skip_candidates(const ScanArgs &a, uint32_t h, lon
         for (int round = 0; round < kSkipTableSize / 32; round++) {
             const uint2 e = __ldg(table + ((base + round * 32 + lane) & (kSkipTableSize - 1)));
             const unsigned empty = __ballot_sync(kFull, e.y == 0);
-            unsigned eq = __ballot_sync(kFull, e.y != 0 && e.x == sh);
+            // every matching entry is an alignment d: the lane that holds it pre-checks its candidate (probe words)
+            const long long jl = st - ((int)e.y - 1) - a.anchor;
+            bool cand = e.y != 0 && e.x == sh && jl >= 0 && jl < a.hi;
+            cand = probe_diff(a, pw, jl, cand) == 0;
+            unsigned eq = __ballot_sync(kFull, cand);
             if (empty) eq &= (1u << (__ffs(empty) - 1)) - 1u;
             while (eq) {
                 const int l = __ffs(eq) - 1;
                 eq &= eq - 1;
-                const int d = (int)__shfl_sync(kFull, e.y, l) - 1;
-                const long long j = st - d - a.anchor;
-                if (j >= 0 && j < a.hi) {
-                    nver += (lane == 0);
-                    if (warp_verify(a, j, lane) && lane == 0) {
-                        cnt++;
-                        emit_match(a, j);
-                    }
+                const long long j = __shfl_sync(kFull, jl, l);
+                nver += (lane == 0);
+                if (warp_verify(a, j, lane) && lane == 0) {
+                    cnt++;
+                    emit_match(a, j);
                 }
             }
             if (empty) break;

@@ -186,6 +186,46 @@ def test_sharded_counts_equal_unsharded(oracle):
         assert total == want
 
 
+def test_dense_periodic_runs_are_counted_arithmetically(oracle):
+    """Periodic pattern in a periodic text: every p-th position is an occurrence.  scan_block verifies the first
+    occurrence of a run, extends the run by streaming text[i] == text[i-p] (extend_run) and counts the rest
+    arithmetically; runs broken by noise, run ends, shard seams, position output and the near-miss pre-check are all
+    compared with the oracle.  `verified` (candidates that reached the exact verification) stays far below the count."""
+    rng = np.random.default_rng(8)
+    n = 400_000
+    for unit in (b"a", b"ab", b"aab", b"abcabcd"):
+        clean = np.frombuffer((unit * (n // len(unit) + 1))[:n], dtype=np.uint8).copy()
+        noisy = clean.copy()
+        noisy[rng.integers(0, n, 40)] = ord("z")   # breaks the runs at 40 places
+        noisy[-1] = ord("c")
+        for tname, y in (("clean", clean), ("noisy", noisy)):
+            with sb.Text.upload(y) as t, sb.Text.upload(y, devices=[0, 0, 0]) as t3:
+                for m in (17, 24, 40, 63, 64, 100, 256, 1000, 4200):
+                    if m < 2 * len(unit):
+                        continue
+                    for k in (0, 1, len(unit) + 2):
+                        x = clean[k:k + m].copy()
+                        want = oracle.bf_positions(x, y)
+                        for algo in ("bf", "hor"):
+                            r = sb.search(algo, t, x, flags=sb.FLAG_NO_PACK)
+                            tm = sb.last_timing()
+                            assert r.count == want.size, (unit, tname, m, k, algo, tm.filter_kind)
+                            assert tm.filter_kind in (4, 8, 16, 32, 408, 416, 816), (unit, m, tm.filter_kind)
+                            if want.size > 10000 and tname == "clean":  # (a noisy text fails ~m candidates per noise byte)
+                                assert tm.verified < want.size // 20, (unit, tname, m, tm.verified, want.size)
+                        assert sb.search("kmp", t3, x).count == want.size, (unit, tname, m, k)
+                        assert sb.search("bf", t, x, flags=sb.FLAG_NO_PERIOD | sb.FLAG_NO_PACK).count == want.size
+                        r = sb.search("bm", t3, x, flags=sb.FLAG_POSITIONS | sb.FLAG_NO_PACK, positions_cap=want.size + 1)
+                        assert np.array_equal(r.positions, want), (unit, tname, m, k)
+                    # near misses: a foreign / swapped last byte, a foreign middle byte
+                    for pos, val in ((m - 1, ord("c")), (m - 1, unit[0] ^ 3), (m // 2, ord("z")), (0, ord("z"))):
+                        x = clean[:m].copy()
+                        x[pos] = val
+                        want = oracle.bf_count(x, y)
+                        assert sb.search("bf", t, x, flags=sb.FLAG_NO_PACK).count == want, (unit, tname, m, pos)
+                        assert sb.search("hor", t3, x).count == want, (unit, tname, m, pos)
+
+
 def test_async_submit_collect(oracle):
     """sb_search64_submit / sb_search_collect: many searches in flight over one resident text, collected in any
     order, each with its own counters; results equal the blocking call and the oracle."""

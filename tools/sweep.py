@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--out", default="gpurun_out/sweep.jsonl")
     ap.add_argument("--default-only", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="SB_FLAG_* ORed into every search (8192 = NO_PACK: byte kernels)")
     a = ap.parse_args()
     n = int(a.gib * (1 << 30))
     out = open(a.out, "w")
@@ -38,7 +39,7 @@ def main():
                     fl = [None] + ([0] if m <= 4 else [1, 2]) + [b for b in (4, 8, 16, 32) if m >= 2 * b - 1]
                     fl += [k for k, need in ((408, 11), (416, 19), (816, 23)) if m >= need]
                 for f in fl:
-                    flags = 0 if f is None else FILTERS[f]
+                    flags = a.flags | (0 if f is None else FILTERS[f])
                     ts, cnt = [], None
                     for _ in range(a.reps):
                         r = sb.search(a.algo, t, x, flags=flags)
