@@ -181,6 +181,23 @@ double sb_stream_timer_end_ms(int device);
 long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned char *y, size_t n,
                          unsigned flags, double *pre_ms, double *run_ms);
 
+/* Batch form of the host-buffer entry: MANY searches over ONE host text - the shape of the driver's loop, which
+ * runs every selected algorithm and every pattern of a set over the same text segment (smart.c:290-380).  The text
+ * crosses PCIe once per call (per 32 jobs), not once per search: every 64 MiB chunk is copied and then scanned by
+ * all jobs.  count receives what sb_search_host would return for that job (count, SB_NOT_APPLICABLE, SB_ERR_ARG);
+ * pre_ms / run_ms receive the job's share of the call.  Returns the sum of the non-negative counts, or SB_ERR_*. */
+typedef struct sb_host_job {
+    int algo;
+    const unsigned char *x;
+    int m;
+    unsigned flags;
+    unsigned long long starts; /* 0: every start position; else only start positions j < starts are counted (the host
+                                  buffer is one part of a larger text followed by its m-1 halo: the part's own starts) */
+    long long count;
+    double pre_ms, run_ms;
+} sb_host_job;
+long long sb_search_host_batch(sb_host_job *jobs, int njobs, const unsigned char *y, size_t n);
+
 /* Legacy plugin body: exact reference signature semantics (main.h:39), int n, int count.
  * Returns -1 where the reference algorithm does; counts above INT_MAX saturate to INT_MAX. */
 int sb_plugin_search(int algo, unsigned char *x, int m, unsigned char *y, int n, double *pre_ms,

@@ -54,6 +54,8 @@ ALGORITHMS = (
     "twfrq3", "twfrq4", "twfrq5", "twfrq6", "twfrq7", "twfrq8", "lwfr2", "lwfr3", "lwfr4", "lwfr5", "lwfr6", "lwfr7",
     "lwfr8", "skip3", "skip5", "skip6", "skip7", "skip8", "bfs", "ffs", "iom", "wom", "pbmh", "qlqs",
     "tsw", "wc", "zt", "tvsbs-w2", "fs-w1", "ssef",
+    # the reference's default selection (src/algorithms.h:133); exact count also where the reference's own is wrong
+    "sbndm2",
 )
 
 
@@ -120,6 +122,19 @@ class Tables(C.Structure):
     ]
 
 
+class HostJob(C.Structure):
+    _fields_ = [
+        ("algo", C.c_int),
+        ("x", C.c_void_p),
+        ("m", C.c_int),
+        ("flags", C.c_uint),
+        ("starts", C.c_ulonglong),
+        ("count", C.c_longlong),
+        ("pre_ms", C.c_double),
+        ("run_ms", C.c_double),
+    ]
+
+
 _lib = None
 
 # every symbol include/smart_b200.h declares: (name, restype, argtypes)
@@ -159,6 +174,7 @@ SYMBOLS = [
     ("sb_stream_timer_end_ms", C.c_double, [C.c_int]),
     ("sb_search_host", C.c_longlong, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_uint,
                                       C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    ("sb_search_host_batch", C.c_longlong, [C.POINTER(HostJob), C.c_int, C.c_void_p, C.c_size_t]),
     ("sb_plugin_search", C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("sb_prep_tables", C.c_int, [C.c_int, C.c_void_p, C.c_int, C.POINTER(Tables)]),
@@ -393,6 +409,25 @@ def search_host(algo: str, pattern, text, flags: int = 0) -> SearchResult:
     if r < -1:
         raise SmartB200Error(f"sb_search_host failed ({r}): {_err()}")
     return SearchResult(int(r), pre.value, run.value)
+
+
+def search_host_batch(jobs, text, starts: int = 0):
+    """sb_search_host_batch: `jobs` is a list of (algo, pattern) or (algo, pattern, flags); the host text crosses PCIe
+    once for all of them.  starts > 0: only start positions below it are counted (the buffer is one part of a larger
+    text plus its halo).  Returns a list of SearchResult (count -1 where the algorithm is not applicable)."""
+    tptr, n, keep_t = _as_bytes_ptr(text)
+    arr = (HostJob * len(jobs))()
+    keep = []
+    for i, job in enumerate(jobs):
+        algo, pattern = job[0], job[1]
+        pptr, m, k = _as_bytes_ptr(pattern)
+        keep.append(k)
+        arr[i].algo, arr[i].x, arr[i].m, arr[i].flags = algo_id(algo), pptr, m, (job[2] if len(job) > 2 else 0)
+        arr[i].starts = starts
+    r = lib().sb_search_host_batch(arr, len(jobs), tptr, n)
+    if r < -1:
+        raise SmartB200Error(f"sb_search_host_batch failed ({r}): {_err()}")
+    return [SearchResult(int(j.count), j.pre_ms, j.run_ms) for j in arr]
 
 
 def plugin_search(algo: str, pattern, text) -> int:

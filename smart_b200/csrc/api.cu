@@ -70,8 +70,11 @@ constexpr int kPswarMaxM1 = 30, kPswarMaxM2 = 22;
 constexpr size_t kAuxWords = sb::kBloomWords + 2 * sb::kSkipTableSize;
 
 constexpr int kTickets = 256;                 // outstanding asynchronous searches (sb_search64_submit)
-constexpr int kSyncSlot = kTickets;           // pattern/counter slot of the blocking paths (positions, host text, multi)
-constexpr int kAuxSlots = 8;                  // cached Bloom/table blocks per device
+constexpr int kSyncSlot = kTickets;           // pattern/counter slot of the blocking paths (positions, multi)
+constexpr int kBatchJobs = 32;                // searches per pass of sb_search_host_batch
+constexpr int kBatchSlot0 = kTickets + 1;     // their pattern/counter slots
+constexpr int kSlots = kTickets + 1 + kBatchJobs;
+constexpr int kAuxSlots = 40;                 // cached Bloom/table blocks per device (>= kBatchJobs: a batch pins one per job)
 
 /* One cached aux block (Bloom bitmap + exact fingerprint table of a scan_skip / scan_packed plan).  The
  * driver's algorithm loop searches the same pattern with many algorithms: the block is built and uploaded once. */
@@ -94,12 +97,12 @@ struct DevCtx {                               // per-device scratch, created on 
     cudaStream_t dstream = nullptr;           // counter read-backs of the asynchronous path
     cudaEvent_t e0 = nullptr, e1 = nullptr;   // blocking paths
     cudaEvent_t t0 = nullptr, t1 = nullptr;   // sb_stream_timer_*
-    // slot s of kTickets+1: pattern words, 4 x u64 counters (device + pinned mirrors); slot kSyncSlot belongs to
-    // the blocking paths.  The counters of the ticket slots are never zeroed: `prev` remembers what the slot
+    // slot s of kSlots: pattern words, 4 x u64 counters (device + pinned mirrors); slot kSyncSlot and the kBatchJobs
+    // slots after it belong to the blocking paths.  The counters of the ticket slots are never zeroed: `prev` remembers what the slot
     // held after its previous search and the result is the difference (no memset node per search).
     uint32_t *d_pat = nullptr, *h_pat = nullptr;
     unsigned long long *d_counters = nullptr, *h_counters = nullptr;
-    unsigned long long prev[kTickets + 1][4] = {{0}};
+    unsigned long long prev[kTickets][4] = {{0}};
     cudaEvent_t ev_up[kTickets] = {nullptr}, ev0[kTickets] = {nullptr}, ev1[kTickets] = {nullptr}, ev_done[kTickets] = {nullptr};
     AuxSlot aux[kAuxSlots];
     unsigned long long aux_clock = 0;
@@ -184,12 +187,12 @@ DevCtx *get_ctx(int dev)
     CU_TRY(cudaEventCreate(&c.e1), nullptr);
     CU_TRY(cudaEventCreate(&c.t0), nullptr);
     CU_TRY(cudaEventCreate(&c.t1), nullptr);
-    CU_TRY(cudaMalloc(&c.d_pat, (kTickets + 1) * kPatBytes), nullptr);
-    CU_TRY(cudaHostAlloc(&c.h_pat, (kTickets + 1) * kPatBytes, cudaHostAllocDefault), nullptr);
-    CU_TRY(cudaMalloc(&c.d_counters, (kTickets + 1) * 4 * sizeof(unsigned long long)), nullptr);
-    CU_TRY(cudaHostAlloc(&c.h_counters, (kTickets + 1) * 4 * sizeof(unsigned long long), cudaHostAllocDefault), nullptr);
-    CU_TRY(cudaMemset(c.d_counters, 0, (kTickets + 1) * 4 * sizeof(unsigned long long)), nullptr);
-    memset(c.h_pat, 0, (kTickets + 1) * kPatBytes);
+    CU_TRY(cudaMalloc(&c.d_pat, kSlots * kPatBytes), nullptr);
+    CU_TRY(cudaHostAlloc(&c.h_pat, kSlots * kPatBytes, cudaHostAllocDefault), nullptr);
+    CU_TRY(cudaMalloc(&c.d_counters, kSlots * 4 * sizeof(unsigned long long)), nullptr);
+    CU_TRY(cudaHostAlloc(&c.h_counters, kSlots * 4 * sizeof(unsigned long long), cudaHostAllocDefault), nullptr);
+    CU_TRY(cudaMemset(c.d_counters, 0, kSlots * 4 * sizeof(unsigned long long)), nullptr);
+    memset(c.h_pat, 0, kSlots * kPatBytes);
     CU_TRY(cudaMalloc(&c.d_hist, 256 * sizeof(unsigned long long)), nullptr);
     c.occ_skip[0] = occupancy(sb::scan_skip_kernel<8>);
     c.occ_skip[1] = occupancy(sb::scan_skip_kernel<16>);
@@ -1940,36 +1943,45 @@ long long sb_search_multi64(int algo, const sb_text *t, const unsigned char *pat
     return total;
 }
 
-long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned char *y, size_t n, unsigned flags,
-                         double *pre_ms, double *run_ms)
+/* one pass of the host text through the device for up to kBatchJobs searches: every 64 MiB chunk is copied ONCE
+ * and scanned by every job before the buffer is reused; the copy of chunk k+1 overlaps the scans of chunk k */
+static long long host_batch_pass(DevCtx *c, sb_host_job *jobs, int njobs, const unsigned char *y, size_t n, double bits,
+                                 const float *freq, uint64_t sig, int *launched_out, double *prep_out)
 {
-    const sb_algo_desc *desc = sb_algo_desc_get(algo);
-    if (!desc || !x || (!y && n) || m < 1 || m > SB_XSIZE) {
-        set_err("bad argument to sb_search_host%s%s");
-        return SB_ERR_ARG;
-    }
-    memset(&g_timing, 0, sizeof g_timing);
-    if (pre_ms) *pre_ms = 0;
-    if (run_ms) *run_ms = 0;
-    if (outside_domain(desc, m, n)) return SB_NOT_APPLICABLE;
-    DevCtx *c = get_ctx(host_device());
-    if (!c) return SB_ERR_CUDA;
-
     const double t0 = now_ms();
-    Plan pl;
-    /* selectivity estimate from a host-side sample of the text (first 64 KiB) */
-    unsigned long long hist[256] = {0};
-    for (size_t i = 0, e = std::min<size_t>(n, 65536); i < e; i++) hist[y[i]]++;
-    float freq[256];
-    uint64_t sig = 0;
-    {
-        double hd[256];
-        for (int b = 0; b < 256; b++) hd[b] = (double)hist[b];
-        freq_from_hist(hd, freq, &sig);
+    std::vector<Plan> plans((size_t)njobs);
+    std::vector<AuxSlot *> aux((size_t)njobs, nullptr);
+    std::vector<char> live((size_t)njobs, 0);
+    int mmax = 1;
+    for (int i = 0; i < njobs; i++) {
+        sb_host_job &jb = jobs[i];
+        const sb_algo_desc *desc = sb_algo_desc_get(jb.algo);
+        jb.pre_ms = jb.run_ms = 0;
+        if (!desc || !jb.x || jb.m < 1 || jb.m > SB_XSIZE) {
+            jb.count = SB_ERR_ARG;
+            continue;
+        }
+        if (outside_domain(desc, jb.m, n)) {
+            jb.count = SB_NOT_APPLICABLE;
+            continue;
+        }
+        jb.count = 0;
+        if ((long long)n - jb.m + 1 <= 0) continue;
+        plan_get(plans[i], desc, jb.x, jb.m, jb.flags & ~SB_FLAG_POSITIONS, bits, nullptr, freq, sig);
+        live[i] = 1;
+        mmax = std::max(mmax, jb.m);
+        const size_t pat_bytes = stage_pattern(*c, kBatchSlot0 + i, jb.x, jb.m);
+        CU_TRY(cudaMemcpyAsync(c->pat_dev(kBatchSlot0 + i), c->pat_host(kBatchSlot0 + i), pat_bytes, cudaMemcpyHostToDevice,
+                               c->stream),
+               SB_ERR_CUDA);
+        if (plans[i].skip_grams) {
+            aux[i] = aux_acquire(*c, plans[i], c->stream);
+            if (!aux[i]) return SB_ERR_CUDA;
+        }
     }
-    plan_get(pl, desc, x, m, flags & ~SB_FLAG_POSITIONS, n >= 4096 ? collision_bits(hist) : 8.0, nullptr,
-             n >= 4096 ? freq : nullptr, n >= 4096 ? sig : 0);
-    const double t1 = now_ms();
+    CU_TRY(cudaMemsetAsync(c->cnt_dev(kBatchSlot0), 0, (size_t)njobs * 4 * sizeof(unsigned long long), c->stream), SB_ERR_CUDA);
+    CU_TRY(cudaStreamSynchronize(c->stream), SB_ERR_CUDA);
+    *prep_out = now_ms() - t0;
 
     /* chunk buffers: 64 MiB of start positions + halo each, double buffered */
     const size_t kChunk = (size_t)64 << 20;
@@ -1992,54 +2004,118 @@ long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned
         }
         c->chunk_cap = need;
     }
-    const size_t pat_bytes = stage_pattern(*c, kSyncSlot, x, m);
-    CU_TRY(cudaMemcpyAsync(c->pat_dev(kSyncSlot), c->pat_host(kSyncSlot), pat_bytes, cudaMemcpyHostToDevice, c->stream),
-           SB_ERR_CUDA);
-    AuxSlot *aux = nullptr;
-    if (pl.skip_grams) {
-        aux = aux_acquire(*c, pl, c->stream);
-        if (!aux) return SB_ERR_CUDA;
-    }
-    CU_TRY(cudaMemsetAsync(c->cnt_dev(kSyncSlot), 0, 4 * sizeof(unsigned long long), c->stream), SB_ERR_CUDA);
-    CU_TRY(cudaStreamSynchronize(c->stream), SB_ERR_CUDA);
-    const double t2 = now_ms();
-
-    const long long total_starts = (long long)n - m + 1;
     int launched = 0;
     size_t k = 0;
-    for (size_t base = 0; (long long)base < total_starts; base += chunk, k++) {
+    const long long starts_any = (long long)n;  // chunks are cut by start position; each job clips its own range
+    for (size_t base = 0; (long long)base < starts_any; base += chunk, k++) {
         const int b = (int)(k & 1);
-        const size_t len = std::min(n - base, chunk + (size_t)m - 1);
-        long long hi = std::min<long long>(total_starts - (long long)base, (long long)chunk);
+        const size_t len = std::min(n - base, chunk + (size_t)mmax - 1);
         CU_TRY(cudaMemcpyAsync(c->d_chunk[b], y + base, len, cudaMemcpyHostToDevice, c->cstream[b]), SB_ERR_CUDA);
         // bytes past `len` may be stale from an earlier chunk: zero what the last group can touch
         const size_t pad_end = std::min(c->chunk_cap, round_up(len, sb::kPadBytes) + sb::kPadBytes);
         CU_TRY(cudaMemsetAsync(c->d_chunk[b] + len, 0, pad_end - len, c->cstream[b]), SB_ERR_CUDA);
-        sb::ScanArgs a = pl.args;
-        a.text = c->d_chunk[b];
-        a.pat = c->pat_dev(kSyncSlot);
-        a.counters = c->cnt_dev(kSyncSlot);
-        a.aux = aux ? aux->d : nullptr;
-        a.base = base;
-        a.hi = hi;
-        CU_TRY(launch_scan(*c, pl, a, c->cstream[b]), SB_ERR_CUDA);
-        launched++;
+        for (int i = 0; i < njobs; i++) {
+            if (!live[i]) continue;
+            long long total_starts = (long long)n - jobs[i].m + 1;
+            if (jobs[i].starts && (long long)jobs[i].starts < total_starts) total_starts = (long long)jobs[i].starts;
+            const long long hi = std::min<long long>(total_starts - (long long)base, (long long)chunk);
+            if (hi <= 0) continue;
+            sb::ScanArgs a = plans[i].args;
+            a.text = c->d_chunk[b];
+            a.pat = c->pat_dev(kBatchSlot0 + i);
+            a.counters = c->cnt_dev(kBatchSlot0 + i);
+            a.aux = aux[i] ? aux[i]->d : nullptr;
+            a.base = base;
+            a.hi = hi;
+            CU_TRY(launch_scan(*c, plans[i], a, c->cstream[b]), SB_ERR_CUDA);
+            launched++;
+        }
     }
     CU_TRY(cudaStreamSynchronize(c->cstream[0]), SB_ERR_CUDA);
     CU_TRY(cudaStreamSynchronize(c->cstream[1]), SB_ERR_CUDA);
-    unsigned long long *h_counters = c->cnt_host(kSyncSlot);
-    CU_TRY(cudaMemcpy(h_counters, c->cnt_dev(kSyncSlot), 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost),
+    unsigned long long *h = c->cnt_host(kBatchSlot0);
+    CU_TRY(cudaMemcpy(h, c->cnt_dev(kBatchSlot0), (size_t)njobs * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost),
            SB_ERR_CUDA);
-    const double t3 = now_ms();
-    g_timing.prep_host_ms = t1 - t0;
-    g_timing.upload_ms = t2 - t1;
-    g_timing.wall_ms = t3 - t2;
+    unsigned long long verified = 0;
+    for (int i = 0; i < njobs; i++)
+        if (live[i]) {
+            jobs[i].count = (long long)h[4 * i];
+            verified += h[4 * i + 2];
+        }
+    g_timing.verified = verified;
+    g_timing.filter_kind = njobs == 1 && live[0] ? filter_kind_of(plans[0]) : 0;
+    *launched_out = launched;
+    return 0;
+}
+
+long long sb_search_host_batch(sb_host_job *jobs, int njobs, const unsigned char *y, size_t n)
+{
+    if (!jobs || njobs < 1 || (!y && n)) {
+        set_err("bad argument to sb_search_host_batch%s%s");
+        return SB_ERR_ARG;
+    }
+    memset(&g_timing, 0, sizeof g_timing);
+    DevCtx *c = get_ctx(host_device());
+    if (!c) return SB_ERR_CUDA;
+    /* selectivity estimate and byte frequencies from a host-side sample of the text (first 64 KiB) */
+    unsigned long long hist[256] = {0};
+    for (size_t i = 0, e = std::min<size_t>(n, 65536); i < e; i++) hist[y[i]]++;
+    float freq[256];
+    uint64_t sig = 0;
+    {
+        double hd[256];
+        for (int b = 0; b < 256; b++) hd[b] = (double)hist[b];
+        freq_from_hist(hd, freq, &sig);
+    }
+    const bool stats = n >= 4096;
+    const double bits = stats ? collision_bits(hist) : 8.0;
+    long long total = 0;
+    int launched = 0;
+    double prep = 0;
+    const double t0 = now_ms();
+    for (int first = 0; first < njobs; first += kBatchJobs) {  // more jobs than slots: one pass of the text per group
+        const int cnt = std::min(kBatchJobs, njobs - first);
+        int l = 0;
+        double p = 0;
+        const long long rc = host_batch_pass(c, jobs + first, cnt, y, n, bits, stats ? freq : nullptr, stats ? sig : 0, &l, &p);
+        if (rc < 0) return rc;
+        launched += l;
+        prep += p;
+    }
+    const double wall = now_ms() - t0;
+    for (int i = 0; i < njobs; i++) {
+        jobs[i].pre_ms = prep / njobs;
+        jobs[i].run_ms = std::max((wall - prep) / njobs, 1e-6);
+        if (jobs[i].count > 0) total += jobs[i].count;
+    }
+    g_timing.prep_host_ms = prep;
+    g_timing.wall_ms = wall - prep;
     g_timing.kernels_launched = launched;
-    g_timing.filter_kind = filter_kind_of(pl);
-    g_timing.verified = h_counters[2];
-    if (pre_ms) *pre_ms = t2 - t0;
-    if (run_ms) *run_ms = (t3 - t2) > 0 ? (t3 - t2) : 1e-6;
-    return (long long)h_counters[0];
+    return total;
+}
+
+long long sb_search_host(int algo, const unsigned char *x, int m, const unsigned char *y, size_t n, unsigned flags,
+                         double *pre_ms, double *run_ms)
+{
+    if (pre_ms) *pre_ms = 0;
+    if (run_ms) *run_ms = 0;
+    if (!sb_algo_desc_get(algo) || !x || (!y && n) || m < 1 || m > SB_XSIZE) {
+        set_err("bad argument to sb_search_host%s%s");
+        return SB_ERR_ARG;
+    }
+    sb_host_job job;
+    memset(&job, 0, sizeof job);
+    job.algo = algo;
+    job.x = x;
+    job.m = m;
+    job.flags = flags;
+    const long long rc = sb_search_host_batch(&job, 1, y, n);
+    if (rc < 0) return rc;
+    if (job.count >= 0) {
+        if (pre_ms) *pre_ms = job.pre_ms;
+        if (run_ms) *run_ms = job.run_ms;
+    }
+    return job.count;
 }
 
 int sb_plugin_search(int algo, unsigned char *x, int m, unsigned char *y, int n, double *pre_ms, double *run_ms)

@@ -31,10 +31,14 @@ TIER2 = (
     "tsw", "wc", "zt", "tvsbs-w2", "fs-w1", "ssef",
 )
 ALGOS = TIER1 + TIER2
+# registered for drop-in completeness although the reference's own output is not always the true count:
+# sbndm2 is the reference's default selection (src/algorithms.h:133) and is wrong for periodic patterns with m > 32
+# (SURVEY A.2b); ours returns the exact count.  Not part of the recorded golden outputs (counts.json is ALGOS-ordered).
+EXTRA_ALGOS = ("sbndm2",)
 
 # -1 domains (Appendix A.1 of SURVEY.md; the `return -1` guards of the sources)
 MIN_M = {"raita": 2, "hash3": 3, "hash5": 5, "hash8": 8, "aoso2": 3, "aoso4": 5, "aoso6": 7, "faoso2": 3, "faoso4": 5,
-         "ebom": 2, "lbndm": 2, "sbndm": 2, "sbndm-bmh": 2, "sebom": 2, "ssef": 32}
+         "ebom": 2, "lbndm": 2, "sbndm": 2, "sbndm-bmh": 2, "sebom": 2, "ssef": 32, "sbndm2": 2}
 MIN_RATIO = {"dbww": 2, "dbww2": 2}
 
 

@@ -112,7 +112,7 @@ def test_our_driver_drives_reference_executables(tmp_path):
     assert rows[2].split()[1] == "-"  # hash3 @ m=2: no result
     xml = list((tmp_path / "results").glob("EXP*/mini.xml"))[0].read_text()
     assert xml.startswith("<RESULTS>") and xml.count("<ALGO>") == 4 and xml.count("<NAME>HASH3</NAME>") == 1
-    assert xml.count("<DATA>-</DATA>") == 1 and xml.count("<SEARCH>") == 8 * 4 - 1 and "<BEST>" in xml
+    assert xml.count("<DATA>-</DATA>") == 1 and xml.count("<SEARCH>") == 8 * 4 and "<BEST>" in xml  # (output.h:225-228)
     # -tex (output.h:153-194) and -html (+ index.html, output.h:635-745)
     tex = list((tmp_path / "results").glob("EXP*/mini.tex"))[0].read_text()
     assert tex.startswith("\\begin{tabular}{|l|llllllll|}") and tex.endswith("\\end{tabular}")
@@ -127,23 +127,65 @@ def test_our_driver_drives_reference_executables(tmp_path):
     assert "occ 4" in r.stdout
 
 
+@needs_ref
+def test_report_files_equal_the_reference_drivers(tmp_path):
+    """-txt / -xml / -tex written by OUR driver against the files the UNMODIFIED reference driver (oracle/_ref/smart)
+    writes for the same text, lengths and algorithms (both drive the reference's executables here).  Timings differ
+    and the reference seeds its patterns with time(NULL) (smart.c:435), so numbers are masked; everything else - rows,
+    columns, names, the "-" cells, the XML schema including outputXML's doubled DATA node (output.h:225-228) - must be
+    byte-identical."""
+    refsmart = os.path.join(ROOT, "oracle", "_ref", "smart")
+    if not os.path.exists(refsmart):
+        pytest.skip("oracle/_ref/smart not built")
+    text = open(os.path.join(ROOT, "tests", "golden", "bible64k.bin"), "rb").read()
+    # the reference only accepts the buffer names of its settings table (smart.c:80-87): use one of them
+    data = tmp_path / "data" / "englishTexts"
+    data.mkdir(parents=True)
+    (data / "part1.txt").write_bytes(text[:30000])
+    (data / "part2.txt").write_bytes(text[30000:])
+    (data / "index.txt").write_text("#part1.txt#\n#part2.txt#\n")
+    # the layout the reference sources hard-code: ./source/bin/<algo>, ./source/algorithms.h, ./results (smart.c:142)
+    (tmp_path / "source").mkdir()
+    os.symlink(REFBIN, tmp_path / "source" / "bin")
+    (tmp_path / "source" / "algorithms.h").write_text("".join(f"#1 #{a} \n" for a in ("bf", "kmp", "hash3", "raita")))
+    (tmp_path / "results").mkdir()
+    r = run([refsmart, "-text", "englishTexts", "-pset", "3", "-plen", "2", "16", "-short", "-txt", "-tex"], cwd=tmp_path)
+    assert r.returncode == 0 and "OUTPUT RUNNING TIMES" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    ours = tmp_path / "ours"
+    ours.mkdir()
+    r = run([os.path.join(BIN, "smart"), "-text", "englishTexts", "-data", str(tmp_path / "data"), "-results",
+             str(ours / "results"), "-pset", "3", "-plen", "2", "16", "-short", "-algo", "bf,kmp,hash3,raita", "-bin", REFBIN,
+             "-txt", "-xml", "-tex", "-seed", "5", "-noworker"], cwd=ours)
+    assert r.returncode == 0, r.stderr
+
+    def masked(path):
+        s = re.sub(r"EXP\d+", "EXP", open(path).read())
+        return re.sub(r"\d+\.\d+", "N", s)
+
+    for ext in ("txt", "xml", "tex"):
+        theirs = list((tmp_path / "results").glob(f"EXP*/englishTexts.{ext}"))
+        mine = list((ours / "results").glob(f"EXP*/englishTexts.{ext}"))
+        assert len(theirs) == 1 and len(mine) == 1, ext
+        assert masked(mine[0]) == masked(theirs[0]), ext
+
+
 def test_select_edits_a_registry_like_the_reference_tool(tmp_path):
     """bin/select: the command line of src/select.c on the '#<0|1> #<name>' registry format."""
     sel = os.path.join(BIN, "select")
     reg = str(tmp_path / "algorithms.h")
     common = ["-file", reg, "-bin", os.path.join(BIN, "algos")]
     r = run([sel, "-init", *common])
-    assert r.returncode == 0 and "142 algorithms registered" in r.stdout
+    assert r.returncode == 0 and "143 algorithms registered" in r.stdout
     lines = open(reg).read().splitlines()
-    assert len(lines) == 142 and lines == sorted(lines) and all(ln.startswith("#0 #") for ln in lines)
-    assert run([sel, "-show", *common]).stdout.count("\n") == 143
+    assert len(lines) == 143 and lines == sorted(lines) and all(ln.startswith("#0 #") for ln in lines)
+    assert run([sel, "-show", *common]).stdout.count("\n") == 144
     r = run([sel, "bf", "kmp", *common])
     assert "The bf algorithm has been selected" in r.stdout and "The kmp algorithm has been selected" in r.stdout
     assert run([sel, "-which", *common]).stdout.split() == ["The", "list", "of", "selected", "algorithms:", "-bf", "-kmp"]
     assert "has been deselected" in run([sel, "kmp", *common]).stdout
     assert "#1 #bf " in open(reg).read() and "#0 #kmp " in open(reg).read()
     run([sel, "-all", *common])
-    assert open(reg).read().count("#1 #") == 142
+    assert open(reg).read().count("#1 #") == 143
     run([sel, "-none", *common])
     assert open(reg).read().count("#1 #") == 0
     assert "no parameter nosuch" in run([sel, "nosuch", *common]).stdout
