@@ -167,10 +167,11 @@ static const sb_algo_desc g_algos[] = {
     {"fs-w1", SB_FAM_BADCHAR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* fs-w1.c:65 */
     {"ssef", SB_FAM_SSEF, SB_ANCHOR_SUFFIX, 0, 0, 0, 32, 0}, /* ssef.c:40, m<32 -> -1 (:41) */
     /* sbndm2 is the ONE algorithm the reference enables by default (src/algorithms.h:133), so a drop-in must know the
-     * name.  Its own output is the exact count for m <= 32 and for aperiodic patterns; for periodic patterns with
-     * m > 32 its search_large shifts by a value computed on the 32-character prefix and misses occurrences (SURVEY
-     * A.2b: a^33 in a^65536 gives 2185 instead of 65504).  We return the exact count there - a documented divergence
-     * from the reference's (wrong) answer, never from bf.c. */
+     * name.  Its own output is the exact count for m <= 32; for m > 32 its search_large works on the 32-character
+     * prefix and is unreliable: periodic patterns lose occurrences (a^33 in a^65536 gives 2185 instead of
+     * 65504) and a pattern that shares only that prefix with the text can be counted (bible64k, m = 33, last byte
+     * changed: 1 instead of 0).  We return the exact count there - a documented divergence from the reference's
+     * (wrong) answer, never from bf.c. */
     {"sbndm2", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* sbndm2.c:27, m<2 -> -1 (:30), search_large :77 */
 };
 #define SB_NALGOS ((int)(sizeof(g_algos) / sizeof(g_algos[0])))

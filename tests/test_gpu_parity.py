@@ -77,8 +77,9 @@ def test_golden_reference_counts(oracle, golden, tname):
 def test_sbndm2_the_reference_default_selection(oracle, golden):
     """sbndm2 is the one algorithm src/algorithms.h:133 enables, so it is registered although the reference's own
     output is wrong for periodic patterns with m > 32.  Ours: the exact count everywhere, -1 for m < 2
-    (sbndm2.c:30).  Where the compiled reference is present: it agrees with us on every golden case with m <= 32 or
-    an aperiodic pattern, and the known divergence is shown, not hidden."""
+    (sbndm2.c:30).  Where the compiled reference is present: it agrees with us on every golden case with m <= 32, and
+    the known divergence of its search_large (m > 32: a^33 in a^65536 -> 2185 instead of 65504; a pattern that only
+    shares its 32-character prefix with the text counted once on bible64k) is shown, not hidden."""
     import oracle_lib
 
     ref = oracle_lib.RefAlgo("sbndm2") if oracle_lib.ref_available("sbndm2") else None
@@ -93,9 +94,9 @@ def test_sbndm2_the_reference_default_selection(oracle, golden):
                 assert got == want, (tname, c["m"], c["pi"])
                 if ref is not None and c["m"] >= 2:
                     r = ref.search(x, y)
-                    if c["m"] <= 32 or tname in ("bible64k", "rand2", "gen4"):
+                    if c["m"] <= 32:
                         assert r == got, (tname, c["m"], c["pi"], r, got)
-                    diverged += r != got
+                    diverged += r != got  # m > 32: search_large (sbndm2.c:77) misses or invents occurrences
     if ref is not None:
         a = np.full(65536, ord("a"), dtype=np.uint8)
         with sb.Text.upload(a) as t:
