@@ -124,8 +124,8 @@ void sb_host_free(void *p);
 /* Extended entry (64-bit n and count; SURVEY.md section 8b "Extended ABI").
  * Returns the occurrence count (>=0), SB_NOT_APPLICABLE, or an SB_ERR_* code.
  * positions/cap are used only with SB_FLAG_POSITIONS: the min(count, cap) SMALLEST occurrence positions
- * are written, ascending (sorted on the device); the return value is still the full count.  When the
- * count exceeds `cap` the text is scanned a second time with an exactly sized sink.
+ * are written, ascending; the return value is still the full count.  The text is scanned once: the kernels mark
+ * occurrences in a bitmap over the start positions, which is compacted in order on the device (no sort).
  * *pre_ms  = table build + upload (wall, ms)   -> replaces *pre_time (main.h:30)
  * *run_ms  = scan incl. count read-back (ms)   -> replaces *run_time (main.h:31); never left 0 */
 long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m, unsigned flags,

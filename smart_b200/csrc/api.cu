@@ -19,7 +19,6 @@
 #include <mutex>
 #include <vector>
 
-#include <cub/device/device_radix_sort.cuh>
 
 namespace {
 
@@ -106,11 +105,12 @@ struct DevCtx {                               // per-device scratch, created on 
     cudaEvent_t ev_up[kTickets] = {nullptr}, ev0[kTickets] = {nullptr}, ev1[kTickets] = {nullptr}, ev_done[kTickets] = {nullptr};
     AuxSlot aux[kAuxSlots];
     unsigned long long aux_clock = 0;
-    unsigned long long *d_pos = nullptr;      // position sink, grown on demand
-    unsigned long long *d_pos_alt = nullptr;  // radix-sort output (same capacity)
+    unsigned long long *d_pos = nullptr;      // sorted position output, grown on demand
     size_t pos_cap = 0;
-    void *d_sort_temp = nullptr;              // cub::DeviceRadixSort scratch
-    size_t sort_temp_bytes = 0;
+    uint32_t *d_posbits = nullptr;            // position bitmap of one window of start positions (kPosWindow bits)
+    unsigned *d_blocksum = nullptr;           // per-CTA popcounts of the bitmap
+    unsigned long long *d_blockoff = nullptr; // their exclusive scan (+ the running output offset)
+    unsigned long long *d_written = nullptr;  // running output offset = occurrences seen so far on this device
     int occ_packed[4] = {0};                  // ... for scan_packed<K>, K = 1, 2, 4, 8
     int occ_packed_half[2] = {0};             // ... for scan_packed_half<KH>, KH = 1, 2
     int occ_pair[6] = {0};                    // ... for scan_block<2,L>, index L-3
@@ -925,21 +925,29 @@ void plan_get(Plan &out, const sb_algo_desc *desc, const unsigned char *x, int m
     out = lru->plan;
 }
 
-/* grow the position sink (and its sort buffer) of a device to at least `need` entries */
+/* positions are produced window by window: a bitmap of kPosWindow start positions (256 MiB) at a time */
+constexpr unsigned long long kPosWindow = 1ull << 31;
+constexpr unsigned kPosBlocks = (unsigned)(kPosWindow / 32 / sb::kCompactWords);  // compaction CTAs per full window
+
+/* position output buffers of a device: room for `need` sorted positions, the window bitmap and its scan arrays */
 bool ensure_pos_capacity(DevCtx &c, size_t need)
 {
     if (need < 1) need = 1;
+    if (!c.d_posbits) {
+        if (cudaMalloc(&c.d_posbits, kPosWindow / 8) != cudaSuccess || cudaMalloc(&c.d_blocksum, kPosBlocks * sizeof(unsigned)) != cudaSuccess ||
+            cudaMalloc(&c.d_blockoff, kPosBlocks * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMalloc(&c.d_written, sizeof(unsigned long long)) != cudaSuccess) {
+            set_err("cudaMalloc of the position bitmap failed%s%s");
+            return false;
+        }
+    }
     if (c.pos_cap >= need) return true;
     cudaStreamSynchronize(c.stream);
     if (c.d_pos) cudaFree(c.d_pos);
-    if (c.d_pos_alt) cudaFree(c.d_pos_alt);
-    c.d_pos = c.d_pos_alt = nullptr;
+    c.d_pos = nullptr;
     c.pos_cap = 0;
-    if (cudaMalloc(&c.d_pos, need * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMalloc(&c.d_pos_alt, need * sizeof(unsigned long long)) != cudaSuccess) {
-        set_err("cudaMalloc of the position sink failed%s%s");
-        if (c.d_pos) cudaFree(c.d_pos);
-        c.d_pos = nullptr;
+    if (cudaMalloc(&c.d_pos, need * sizeof(unsigned long long)) != cudaSuccess) {
+        set_err("cudaMalloc of the position buffer failed%s%s");
         return false;
     }
     c.pos_cap = need;
@@ -1592,7 +1600,11 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
     return r;
 }
 
-/* Blocking search with position output: the min(count, cap) smallest positions, ascending. */
+/* Blocking search with position output: the min(count, cap) smallest positions, ascending.
+ * Every shard is scanned ONCE, in windows of kPosWindow start positions: the scan kernels mark each occurrence in
+ * the window's bitmap (emit_match), three small kernels compact the bitmap in order behind what the device has
+ * already written (bitmap_count / bitmap_scan / bitmap_write) - no sort, and no second scan when `cap` is short:
+ * the ordered write simply stops at cap while the count stays complete. */
 static long long search_positions(const sb_algo_desc *desc, const sb_text *t, const unsigned char *x, int m, unsigned flags,
                                   unsigned long long *positions, size_t cap, double *pre_ms, double *run_ms)
 {
@@ -1600,6 +1612,8 @@ static long long search_positions(const sb_algo_desc *desc, const sb_text *t, co
     Plan pl;
     plan_get(pl, desc, x, m, flags, t->bits, &t->pack, t->have_freq ? t->freq : nullptr, t->have_freq ? t->sig : 0);
     const double t1 = now_ms();
+    const long long total_starts = (long long)t->n - m + 1;
+    const size_t want = std::min((size_t)cap, (size_t)total_starts);
 
     DevCtx *ctx[kMaxShards];
     AuxSlot *aux[kMaxShards] = {nullptr};
@@ -1615,6 +1629,7 @@ static long long search_positions(const sb_algo_desc *desc, const sb_text *t, co
             }
         if (!dev_first[g]) continue;
         DevCtx &c = *ctx[g];
+        if (!ensure_pos_capacity(c, want)) return SB_ERR_NOMEM;
         const size_t pat_bytes = stage_pattern(c, kSyncSlot, x, m);
         CU_TRY(cudaMemcpyAsync(c.pat_dev(kSyncSlot), c.pat_host(kSyncSlot), pat_bytes, cudaMemcpyHostToDevice, c.stream),
                SB_ERR_CUDA);
@@ -1623,122 +1638,86 @@ static long long search_positions(const sb_algo_desc *desc, const sb_text *t, co
             if (!aux[g]) return SB_ERR_CUDA;
         }
         CU_TRY(cudaMemsetAsync(c.cnt_dev(kSyncSlot), 0, 4 * sizeof(unsigned long long), c.stream), SB_ERR_CUDA);
+        CU_TRY(cudaMemsetAsync(c.d_written, 0, sizeof(unsigned long long), c.stream), SB_ERR_CUDA);
+        CU_TRY(cudaEventRecord(c.e0, c.stream), SB_ERR_CUDA);
     }
     const double t2 = now_ms();
 
-    const long long total_starts = (long long)t->n - m + 1;
     int launched = 0;
-    // launch the scan of shard g; positions (global offsets, unsorted) go to the device's sink
-    auto launch_shard = [&](int g) -> cudaError_t {
+    const bool nothing = pl.filter == kFilterPacked && !pl.packed_K;  // a pattern byte the text lacks: count 0
+    const int pbits = t->pack.packed ? t->pack.bits : 0;
+    for (int g = 0; g < t->nshards && !nothing; g++) {  // shards in text order; each device's stream keeps that order
         DevCtx &c = *ctx[g];
-        sb::ScanArgs a = shard_args(pl, t, g, m);
-        a.pat = c.pat_dev(kSyncSlot);
-        a.counters = c.cnt_dev(kSyncSlot);
-        a.aux = aux[g] ? aux[g]->d : nullptr;
-        a.pos = c.d_pos;
-        a.pos_cap = c.pos_cap;
-        if (a.hi <= 0) return cudaSuccess;
-        if (pl.filter == kFilterPacked && !pl.packed_K) return cudaSuccess;  // a pattern byte the text lacks: count 0
-        launched++;
-        return launch_scan(c, pl, a, c.stream);
-    };
-    for (int g = 0; g < t->nshards; g++) {
-        DevCtx &c = *ctx[g];
-        CU_TRY(cudaSetDevice(t->sh[g].dev), SB_ERR_CUDA);
-        if (dev_first[g]) {
-            // first guess for the sink: room for `cap` positions (a device may hold several shards)
-            if (!ensure_pos_capacity(c, std::min((size_t)cap, (size_t)total_starts))) return SB_ERR_NOMEM;
-            CU_TRY(cudaEventRecord(c.e0, c.stream), SB_ERR_CUDA);
+        const Shard &s = t->sh[g];
+        CU_TRY(cudaSetDevice(s.dev), SB_ERR_CUDA);
+        const sb::ScanArgs whole = shard_args(pl, t, g, m);
+        for (long long lo = 0; lo < whole.hi; lo += (long long)kPosWindow) {
+            sb::ScanArgs a = whole;
+            a.text = s.d_text + lo;  // a window is a shard of its own: its starts, the rest of the buffer as halo
+            a.packed = (s.d_packed && pbits) ? s.d_packed + (unsigned long long)lo * pbits / 32 : nullptr;
+            a.base = s.base + (unsigned long long)lo;
+            a.hi = std::min<long long>(whole.hi - lo, (long long)kPosWindow);
+            a.pat = c.pat_dev(kSyncSlot);
+            a.counters = c.cnt_dev(kSyncSlot);
+            a.aux = aux[g] ? aux[g]->d : nullptr;
+            a.pos = c.d_posbits;
+            const unsigned long long nwords = round_up(((unsigned long long)a.hi + 31) / 32, sb::kCompactWords);
+            const unsigned nblocks = (unsigned)(nwords / sb::kCompactWords);
+            CU_TRY(cudaMemsetAsync(c.d_posbits, 0, nwords * sizeof(uint32_t), c.stream), SB_ERR_CUDA);
+            CU_TRY(launch_scan(c, pl, a, c.stream), SB_ERR_CUDA);
+            launched++;
+            sb::bitmap_count_kernel<<<nblocks, sb::kCompactThreads, 0, c.stream>>>(c.d_posbits, nwords, c.d_blocksum);
+            sb::bitmap_scan_kernel<<<1, 1024, 0, c.stream>>>(c.d_blocksum, nblocks, c.d_blockoff, c.d_written);
+            sb::bitmap_write_kernel<<<nblocks, sb::kCompactThreads, 0, c.stream>>>(c.d_posbits, nwords, c.d_blockoff, a.base, c.d_pos,
+                                                                                   (unsigned long long)c.pos_cap < (unsigned long long)want
+                                                                                       ? (unsigned long long)c.pos_cap
+                                                                                       : (unsigned long long)want);
+            CU_TRY(cudaGetLastError(), SB_ERR_CUDA);
         }
-        CU_TRY(launch_shard(g), SB_ERR_CUDA);
-    }
-    for (int g = t->nshards - 1; g >= 0; g--) {
-        // last shard of each device records the end event and the counter read-back
-        bool last = true;
-        for (int k = g + 1; k < t->nshards; k++) last = last && (t->sh[k].dev != t->sh[g].dev);
-        if (!last) continue;
-        DevCtx &c = *ctx[g];
-        CU_TRY(cudaSetDevice(t->sh[g].dev), SB_ERR_CUDA);
-        CU_TRY(cudaEventRecord(c.e1, c.stream), SB_ERR_CUDA);
-        CU_TRY(cudaMemcpyAsync(c.cnt_host(kSyncSlot), c.cnt_dev(kSyncSlot), 4 * sizeof(unsigned long long),
-                               cudaMemcpyDeviceToHost, c.stream),
-               SB_ERR_CUDA);
     }
     unsigned long long total = 0, verified = 0;
     double kernel_ms = 0;
+    std::vector<unsigned long long> merged;  // only used when several devices contribute
     int ndev_used = 0;
+    for (int g = 0; g < t->nshards; g++) ndev_used += dev_first[g] ? 1 : 0;
+    size_t written = 0;
     for (int g = 0; g < t->nshards; g++) {
         if (!dev_first[g]) continue;
         DevCtx &c = *ctx[g];
         CU_TRY(cudaSetDevice(t->sh[g].dev), SB_ERR_CUDA);
+        CU_TRY(cudaEventRecord(c.e1, c.stream), SB_ERR_CUDA);
+        unsigned long long *h = c.cnt_host(kSyncSlot);
+        CU_TRY(cudaMemcpyAsync(h, c.cnt_dev(kSyncSlot), 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream),
+               SB_ERR_CUDA);
+        CU_TRY(cudaMemcpyAsync(h + 1, c.d_written, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream), SB_ERR_CUDA);
         CU_TRY(cudaStreamSynchronize(c.stream), SB_ERR_CUDA);
         float ms = 0;
         CU_TRY(cudaEventElapsedTime(&ms, c.e0, c.e1), SB_ERR_CUDA);
         kernel_ms = std::max(kernel_ms, (double)ms);
-        total += c.cnt_host(kSyncSlot)[0];
-        verified += c.cnt_host(kSyncSlot)[2];
-        ndev_used++;
-    }
-
-    /* ---- positions: complete the sinks, sort on the device, return the smallest `cap` ascending ---- */
-    {
-        std::vector<unsigned long long> merged;  // only used when several devices contribute
-        size_t written = 0;
-        int end_bit = 1;
-        while (end_bit < 64 && (t->n >> end_bit)) end_bit++;
-        for (int g = 0; g < t->nshards; g++) {
-            if (!dev_first[g]) continue;
-            DevCtx &c = *ctx[g];
-            CU_TRY(cudaSetDevice(t->sh[g].dev), SB_ERR_CUDA);
-            size_t found = (size_t)c.cnt_host(kSyncSlot)[1];
-            if (found > c.pos_cap) {
-                // the sink overflowed (more occurrences than `cap`): the entries it holds are an arbitrary
-                // subset, so grow it to the exact size and scan this device's shards once more
-                if (!ensure_pos_capacity(c, found)) return SB_ERR_NOMEM;
-                CU_TRY(cudaMemsetAsync(c.cnt_dev(kSyncSlot), 0, 4 * sizeof(unsigned long long), c.stream), SB_ERR_CUDA);
-                for (int k = g; k < t->nshards; k++)
-                    if (t->sh[k].dev == t->sh[g].dev) CU_TRY(launch_shard(k), SB_ERR_CUDA);
-                CU_TRY(cudaStreamSynchronize(c.stream), SB_ERR_CUDA);
-            }
-            if (!found) continue;
-            size_t temp_bytes = 0;
-            cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, c.d_pos, c.d_pos_alt, found, 0, end_bit, c.stream);
-            if (c.sort_temp_bytes < temp_bytes) {
-                if (c.d_sort_temp) cudaFree(c.d_sort_temp);
-                c.d_sort_temp = nullptr;
-                c.sort_temp_bytes = 0;
-                if (cudaMalloc(&c.d_sort_temp, temp_bytes) != cudaSuccess) {
-                    set_err("cudaMalloc of the sort scratch failed%s%s");
-                    return SB_ERR_NOMEM;
-                }
-                c.sort_temp_bytes = temp_bytes;
-            }
-            CU_TRY(cub::DeviceRadixSort::SortKeys(c.d_sort_temp, temp_bytes, c.d_pos, c.d_pos_alt, found, 0, end_bit,
-                                                  c.stream),
+        total += h[0];
+        verified += h[2];
+        if (h[1] != h[0]) {  // every counted occurrence must have been marked exactly once
+            set_err("internal error: position bitmap and occurrence count disagree%s%s");
+            return SB_ERR_CUDA;
+        }
+        const size_t take = (size_t)std::min<unsigned long long>(h[0], want);
+        if (!take) continue;
+        if (ndev_used == 1) {
+            CU_TRY(cudaMemcpy(positions, c.d_pos, take * sizeof(unsigned long long), cudaMemcpyDeviceToHost), SB_ERR_CUDA);
+            written = take;
+        } else {
+            const size_t old = merged.size();
+            merged.resize(old + take);
+            CU_TRY(cudaMemcpy(merged.data() + old, c.d_pos, take * sizeof(unsigned long long), cudaMemcpyDeviceToHost),
                    SB_ERR_CUDA);
-            const size_t take = std::min(found, (size_t)cap);
-            if (ndev_used == 1) {
-                CU_TRY(cudaMemcpyAsync(positions, c.d_pos_alt, take * sizeof(unsigned long long),
-                                       cudaMemcpyDeviceToHost, c.stream),
-                       SB_ERR_CUDA);
-                CU_TRY(cudaStreamSynchronize(c.stream), SB_ERR_CUDA);
-                written = take;
-            } else {
-                const size_t old = merged.size();
-                merged.resize(old + take);
-                CU_TRY(cudaMemcpyAsync(merged.data() + old, c.d_pos_alt, take * sizeof(unsigned long long),
-                                       cudaMemcpyDeviceToHost, c.stream),
-                       SB_ERR_CUDA);
-                CU_TRY(cudaStreamSynchronize(c.stream), SB_ERR_CUDA);
-            }
         }
-        if (ndev_used > 1) {
-            std::sort(merged.begin(), merged.end());  // each device's list is sorted; devices may interleave shards
-            written = std::min(merged.size(), (size_t)cap);
-            memcpy(positions, merged.data(), written * sizeof(unsigned long long));
-        }
-        (void)written;
     }
+    if (ndev_used > 1) {
+        std::sort(merged.begin(), merged.end());  // each device's list is sorted; devices may interleave shards
+        written = std::min(merged.size(), (size_t)cap);
+        memcpy(positions, merged.data(), written * sizeof(unsigned long long));
+    }
+    (void)written;
     const double t3 = now_ms();
 
     g_timing.prep_host_ms = t1 - t0;

@@ -64,9 +64,9 @@ struct ScanArgs {
     const uint32_t *packed;       // scan_packed: 2-bit (1-bit for two symbols) recoding of the shard, or nullptr
     int cpw;                      // scan_packed: characters per packed word (16 or 32)
     const uint32_t *pat;          // pattern as little-endian words, zero padded
-    unsigned long long *counters; // [0] match count, [1] position cursor, [2] verified candidates
-    unsigned long long *pos;      // position sink (unsorted) or nullptr
-    unsigned long long pos_cap;
+    unsigned long long *counters; // [0] match count, [2] verified candidates
+    uint32_t *pos;                // position output: bitmap over the scanned start positions (bit j <=> an occurrence
+                                  // starts at local position j), or nullptr; compacted in order by bitmap_write_kernel
     unsigned long long base;      // global offset of local byte 0
     long long hi;                 // owned local start positions are [0, hi)
     unsigned long long ngroups;   // groups to scan (group size depends on the kernel)
@@ -266,10 +266,7 @@ __device__ __forceinline__ long long extend_run(const ScanArgs &a, long long j, 
 
 __device__ __forceinline__ void emit_match(const ScanArgs &a, long long j)
 {
-    if (a.pos) {
-        unsigned long long idx = atomicAdd(a.counters + 1, 1ull);
-        if (idx < a.pos_cap) a.pos[idx] = a.base + (unsigned long long)j;
-    }
+    if (a.pos) atomicOr(a.pos + (j >> 5), 1u << (j & 31));
 }
 
 __device__ __forceinline__ void block_reduce_count(const ScanArgs &a, unsigned cnt, unsigned nverified)
@@ -1407,6 +1404,117 @@ __global__ void __launch_bounds__(kThreads) scan_swar_kernel(const __grid_consta
         }
     }
     block_reduce_count(a, cnt, 0u);
+}
+
+/* ===================================================================== position output */
+
+/* Occurrence positions leave the scan kernels as a BITMAP over the scanned start positions (emit_match: one
+ * atomicOr per occurrence, no cursor, no ordering problem).  Three small kernels turn it into the sorted list:
+ * per-CTA popcounts, an exclusive scan of those (one CTA; it also advances the running output offset, so windows
+ * and shards are chained on the device without a host round trip), and an ordered write that stops at `cap`.
+ * This is SURVEY section 7.6's "per-tile counts -> exclusive scan -> ordered write" with the tile's content kept as
+ * bits: one scan of the text, no sort, no second scan when the caller's buffer is short. */
+constexpr int kCompactWords = 4096;    // bitmap words per CTA = 131072 start positions
+constexpr int kCompactThreads = 256;   // 16 consecutive words per thread
+
+__global__ void __launch_bounds__(kCompactThreads) bitmap_count_kernel(const uint32_t *bits, unsigned long long nwords,
+                                                                        unsigned *block_sums)
+{
+    __shared__ unsigned s_sum[kCompactThreads / 32];
+    const unsigned long long w0 = (unsigned long long)blockIdx.x * kCompactWords + threadIdx.x * 16ull;
+    unsigned c = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (w0 + 4 * q < nwords) {  // (nwords is a multiple of 4: the bitmap is allocated in whole CTAs)
+            const uint4 v = *reinterpret_cast<const uint4 *>(bits + w0 + 4 * q);
+            c += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+#pragma unroll
+        for (int w = 0; w < kCompactThreads / 32; w++) t += s_sum[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+/* one CTA of 1024 threads: block_off[b] = *running + sum of block_sums[0..b); then *running += total */
+__global__ void __launch_bounds__(1024) bitmap_scan_kernel(const unsigned *block_sums, unsigned nblocks,
+                                                             unsigned long long *block_off, unsigned long long *running)
+{
+    __shared__ unsigned long long s_part[1024];
+    const unsigned per = (nblocks + 1023) / 1024;
+    const unsigned lo = threadIdx.x * per, hi = min(nblocks, lo + per);
+    unsigned long long sum = 0;
+    for (unsigned b = lo; b < hi; b++) sum += block_sums[b];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // inclusive scan of the per-thread sums
+        const unsigned long long v = threadIdx.x >= (unsigned)o ? s_part[threadIdx.x - o] : 0ull;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const unsigned long long base = *running;
+    unsigned long long off = base + s_part[threadIdx.x] - sum;
+    for (unsigned b = lo; b < hi; b++) {
+        block_off[b] = off;
+        off += block_sums[b];
+    }
+    __syncthreads();  // every thread has read *running
+    if (threadIdx.x == 1023) *running = base + s_part[1023];
+}
+
+/* ordered write: bit i of the bitmap -> out[block_off + rank] = first + i, for output slots below cap */
+__global__ void __launch_bounds__(kCompactThreads) bitmap_write_kernel(const uint32_t *bits, unsigned long long nwords,
+                                                                        const unsigned long long *block_off,
+                                                                        unsigned long long first, unsigned long long *out,
+                                                                        unsigned long long cap)
+{
+    __shared__ unsigned s_warp[kCompactThreads / 32];
+    unsigned long long off = block_off[blockIdx.x];
+    if (off >= cap) return;  // (uniform) everything this CTA holds lies beyond the caller's buffer
+    const unsigned long long w0 = (unsigned long long)blockIdx.x * kCompactWords + threadIdx.x * 16ull;
+    uint32_t w[16];
+    unsigned c = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (w0 + 4 * q < nwords) v = *reinterpret_cast<const uint4 *>(bits + w0 + 4 * q);
+        w[4 * q] = v.x;
+        w[4 * q + 1] = v.y;
+        w[4 * q + 2] = v.z;
+        w[4 * q + 3] = v.w;
+        c += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    }
+    // exclusive prefix of c over the CTA's threads
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(kFull, incl, o);
+        if (lane >= (unsigned)o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned before = 0;
+    for (unsigned k = 0; k < warp; k++) before += s_warp[k];
+    off += before + incl - c;
+    if (!c) return;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        uint32_t v = w[k];
+        while (v) {
+            const int b = __ffs(v) - 1;
+            v &= v - 1;
+            if (off < cap) out[off] = first + (w0 + k) * 32ull + b;
+            off++;
+        }
+    }
 }
 
 /* ===================================================================== text statistics */

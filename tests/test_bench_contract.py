@@ -52,7 +52,9 @@ def test_our_arm_json_small():
     assert rf["kernel"].startswith("scan_") and rf["achieved"] > 100
     assert d["gpu_launches"] == 2 * 16 and d["value"] > 100
     e = d["e2e"]
-    assert e["value"] > 1 and e["h2d_bytes_per_step"] >= 16 * (1 << 28) and e["d2h_bytes_per_step"] > 0
+    # e2e: the batch entry copies the text once per step, the per-call entry once per search
+    assert e["value"] > 1 and e["h2d_bytes_per_step"] >= (1 << 28) and e["d2h_bytes_per_step"] > 0
+    assert e["per_call"]["h2d_bytes_per_step"] >= 16 * (1 << 28) and 1 < e["per_call"]["value"] < e["value"]
     assert e["value"] < d["value"]  # the end-to-end path pays the host->device copy
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["value"] > 0 and cb["cores"] >= 1 and "sample" in cb
