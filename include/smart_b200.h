@@ -64,6 +64,12 @@ extern "C" {
 #define SB_FLAG_FILTER_B8L16 0x800u  /* 8-byte alignment, 16-byte fingerprint (m >= 23) */
 #define SB_FLAG_FILTER_B2 0x1000u    /* windows of min(8, m-1) bytes at every even position (m >= 4) */
 #define SB_FLAG_NO_PACK 0x2000u      /* do not use the packed recoding of a text over <= 16 byte values */
+#define SB_FLAG_TABLE_SCAN 0x4000u   /* run the algorithm's OWN table-driven scan on the device: its preprocessing table
+                                        (kmpNext / mpNext, hbc, Shift-Or/And masks, HASHq shift table - bit-identical to
+                                        the reference's) is uploaded, staged in shared memory and drives the scan loop of
+                                        kmp.c / mp.c / hor.c / so.c / sa.c / hash3,5,8.c, one thread per text segment.
+                                        Same counts as every other mode; slower than the default fingerprint filters
+                                        (DESIGN.md section 3.4).  Count only; other algorithms ignore the flag. */
 
 /* ---- algorithm registry (names are the lower-cased SMART registry names, smart.c:142) ---- */
 int sb_algo_count(void);
@@ -164,7 +170,9 @@ typedef struct sb_timing {
                               the text does not contain, nothing scanned), 311/312 = scan_packed_half<KH>,
                               501..532 = scan_pswar<1,KF> (SWAR chain of KF characters on the 1-bit recoding; exact when
                               KF == m), 541..556 = scan_pswar<2,KF> on the 2-bit recoding,
-                              108/116/132 = scan_skip<G>, 204/208/216 = scan_multi<B>, -1 = per-pattern fallback */
+                              108/116/132 = scan_skip<G>, 204/208/216 = scan_multi<B>, -1 = per-pattern fallback,
+                              601 kmp / 602 mp / 603 hor / 604 so / 605 sa / 606 hashq = table-driven scans
+                              (SB_FLAG_TABLE_SCAN) */
     unsigned long long verified; /* candidates sent to exact verification (all shards) */
 } sb_timing;
 void sb_last_timing(sb_timing *out);

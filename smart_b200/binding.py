@@ -36,6 +36,7 @@ FLAG_FILTER_B4L16 = 0x400
 FLAG_FILTER_B8L16 = 0x800
 FLAG_FILTER_B2 = 0x1000
 FLAG_NO_PACK = 0x2000
+FLAG_TABLE_SCAN = 0x4000
 
 ALGORITHMS = (
     "bf", "mp", "kmp", "bm", "hor", "qs", "raita", "tunedbm", "so", "sa", "kr",

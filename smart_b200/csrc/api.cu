@@ -8,6 +8,7 @@
  */
 #include "sb_internal.h"
 #include "scan_kernels.cuh"
+#include "table_kernels.cuh"
 
 #include <algorithm>
 #include <climits>
@@ -119,6 +120,7 @@ struct DevCtx {                               // per-device scratch, created on 
     int occ_swar[8] = {0};                    // ... for scan_swar<M, DENSE>, index (M-1)*2 + DENSE
     mutable int occ_pswar[2][33][2] = {{{0}}};  // ... for scan_pswar<BITS,KF,EXACT>, filled on first use
     unsigned long long *d_hist = nullptr;     // 256-bin byte histogram scratch
+    int32_t *d_table = nullptr;               // SB_FLAG_TABLE_SCAN: the algorithm's table (<= SB_XSIZE + 1 ints)
     uint32_t *d_mpat = nullptr;               // scan_multi: pattern set (words), grown on demand
     size_t mpat_words = 0;
     unsigned long long *d_mcounts = nullptr;  // scan_multi: per-pattern counts
@@ -1567,6 +1569,105 @@ long long sb_search_collect(long long ticket, double *pre_ms, double *run_ms)
 static long long search_positions(const sb_algo_desc *desc, const sb_text *t, const unsigned char *x, int m, unsigned flags,
                                   unsigned long long *positions, size_t cap, double *pre_ms, double *run_ms);
 
+/* SB_FLAG_TABLE_SCAN: the reference algorithm's own table, built by prep.c, uploaded and used by its own scan loop on
+ * the device (table_kernels.cuh).  Returns -100 when the family has no table-driven kernel (caller takes the default). */
+static long long search_table(const sb_algo_desc *desc, const sb_text *t, const unsigned char *x, int m, double *pre_ms,
+                              double *run_ms)
+{
+    int kind = 0;
+    switch (desc->family) {
+    case SB_FAM_KMP: kind = 601; break;
+    case SB_FAM_MP: kind = 602; break;
+    case SB_FAM_HOR: kind = 603; break;
+    case SB_FAM_SO: kind = 604; break;
+    case SB_FAM_SA: kind = 605; break;
+    case SB_FAM_HASHQ: kind = 606; break;
+    default: return -100;
+    }
+    const double t0 = now_ms();
+    static thread_local int table[SB_XSIZE + 1], scratch[SB_XSIZE + 1];
+    int ntable = 256, sh1 = 0;
+    unsigned lim = 0;
+    switch (kind) {  // the preprocessing stage proper: bit-identical to preKmp / preMp / Pre_Horspool / preSo / preSA / hash3.c:37-55
+    case 601:
+        sb_prep_mp(x, m, scratch);
+        sb_prep_kmp(x, m, scratch, table);
+        ntable = m + 1;
+        break;
+    case 602:
+        sb_prep_mp(x, m, table);
+        ntable = m + 1;
+        break;
+    case 603: sb_prep_hbc(x, m, table); break;
+    case 604: lim = sb_prep_so(x, m, reinterpret_cast<unsigned int *>(table)); break;
+    case 605: lim = sb_prep_sa(x, m, reinterpret_cast<unsigned int *>(table)); break;
+    default: sb_prep_hashq(x, m, desc->q, table, &sh1); break;
+    }
+    const double t1 = now_ms();
+    const long long total_starts = (long long)t->n - m + 1;
+    unsigned long long total = 0;
+    double kernel_ms = 0;
+    int launched = 0;
+    for (int g = 0; g < t->nshards && total_starts > 0; g++) {  // one shard after the other: a blocking, selectable mode
+        const Shard &s = t->sh[g];
+        DevCtx *c = get_ctx(s.dev);
+        if (!c) return SB_ERR_CUDA;
+        if (!c->d_table) CU_TRY(cudaMalloc(&c->d_table, (SB_XSIZE + 1) * sizeof(int32_t)), SB_ERR_NOMEM);
+        long long hi = total_starts - (long long)s.base;
+        if (hi > (long long)s.own) hi = (long long)s.own;
+        if (hi <= 0) continue;
+        const size_t pat_bytes = stage_pattern(*c, kSyncSlot, x, m);
+        CU_TRY(cudaMemcpyAsync(c->pat_dev(kSyncSlot), c->pat_host(kSyncSlot), pat_bytes, cudaMemcpyHostToDevice, c->stream),
+               SB_ERR_CUDA);
+        CU_TRY(cudaMemcpyAsync(c->d_table, table, (size_t)ntable * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream),
+               SB_ERR_CUDA);
+        CU_TRY(cudaMemsetAsync(c->cnt_dev(kSyncSlot), 0, 4 * sizeof(unsigned long long), c->stream), SB_ERR_CUDA);
+        sb::TableArgs a;
+        memset(&a, 0, sizeof a);
+        a.text = s.d_text;
+        a.pat = reinterpret_cast<const uint8_t *>(c->pat_dev(kSyncSlot));
+        a.table = c->d_table;
+        a.counters = c->cnt_dev(kSyncSlot);
+        a.hi = hi;
+        a.m = m;
+        a.seg = m <= 1024 ? 4096 : 16384;  // start positions per thread; each thread also reads the m-1 bytes behind them
+        a.q = desc->q;
+        a.sh1 = sh1;
+        a.lim = lim;
+        const unsigned long long nthreads = ((unsigned long long)hi + a.seg - 1) / a.seg;
+        const unsigned grid = (unsigned)((nthreads + sb::kTableThreads - 1) / sb::kTableThreads);
+        CU_TRY(cudaEventRecord(c->e0, c->stream), SB_ERR_CUDA);
+        switch (kind) {
+        case 601:
+        case 602: sb::table_kmp_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 603: sb::table_hor_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 604: sb::table_so_kernel<false><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 605: sb::table_so_kernel<true><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        default: sb::table_hashq_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        }
+        CU_TRY(cudaGetLastError(), SB_ERR_CUDA);
+        CU_TRY(cudaEventRecord(c->e1, c->stream), SB_ERR_CUDA);
+        unsigned long long *h = c->cnt_host(kSyncSlot);
+        CU_TRY(cudaMemcpyAsync(h, c->cnt_dev(kSyncSlot), 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream),
+               SB_ERR_CUDA);
+        CU_TRY(cudaStreamSynchronize(c->stream), SB_ERR_CUDA);
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, c->e0, c->e1), SB_ERR_CUDA);
+        kernel_ms += ms;  // shards are scanned one after the other
+        total += h[0];
+        launched++;
+    }
+    const double t2 = now_ms();
+    g_timing.prep_host_ms = t1 - t0;
+    g_timing.kernel_ms = kernel_ms;
+    g_timing.wall_ms = t2 - t1;
+    g_timing.kernels_launched = launched;
+    g_timing.filter_kind = kind;
+    if (pre_ms) *pre_ms = t1 - t0;
+    if (run_ms) *run_ms = (t2 - t1) > 0 ? (t2 - t1) : 1e-6;
+    return (long long)total;
+}
+
 long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m, unsigned flags,
                       unsigned long long *positions, size_t cap, double *pre_ms, double *run_ms)
 {
@@ -1585,6 +1686,10 @@ long long sb_search64(int algo, const sb_text *t, const unsigned char *x, int m,
     if (run_ms) *run_ms = 0;
     if (want_pos && positions && cap > 0 && (long long)t->n - m + 1 > 0 && !outside_domain(desc, m, t->n))
         return search_positions(desc, t, x, m, flags, positions, cap, pre_ms, run_ms);
+    if ((flags & SB_FLAG_TABLE_SCAN) && !outside_domain(desc, m, t->n)) {
+        const long long r = search_table(desc, t, x, m, pre_ms, run_ms);
+        if (r != -100) return r;
+    }
     /* count only: one submit, one collect */
     const double t0 = now_ms();
     const long long idx = submit_core(desc, t, x, m, flags & ~SB_FLAG_POSITIONS);

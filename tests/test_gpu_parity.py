@@ -74,6 +74,59 @@ def test_golden_reference_counts(oracle, golden, tname):
                 assert got == ref[a], (tname, c["m"], c["pi"], a, got, ref[a])
 
 
+TABLE_KIND = {"kmp": 601, "mp": 602, "hor": 603, "so": 604, "sa": 605, "hash3": 606, "hash5": 606, "hash8": 606}
+
+
+@pytest.mark.parametrize("tname", TEXT_NAMES)
+def test_table_driven_scans_match_the_reference(oracle, golden, tname):
+    """SB_FLAG_TABLE_SCAN: the algorithm's own preprocessing table (kmpNext, mpNext, hbc, Shift-Or / Shift-And masks,
+    HASHq shift table) is uploaded, staged in shared memory and drives the reference's own scan loop on the device.
+    Every golden case: the count the UNMODIFIED reference algorithm returned, -1 domains included; sharded texts too."""
+    y = make_text(tname, oracle)
+    with sb.Text.upload(y) as t, sb.Text.upload(y, devices=[0, 0, 0]) as t3:
+        for c in (c for c in golden["cases"] if c["text"] == tname):
+            x = make_patterns(tname, y, c["m"])[c["pi"]]
+            ref = dict(zip(ALGOS, c["ref"]))
+            for a, kind in TABLE_KIND.items():
+                got = sb.search(a, t, x, flags=sb.FLAG_TABLE_SCAN).count
+                assert got == ref[a], (tname, c["m"], c["pi"], a, got, ref[a])
+                if ref[a] >= 0:
+                    assert sb.last_timing().filter_kind == kind and sb.last_timing().kernels_launched == 1, (a, c["m"])
+            assert sb.search("kmp", t3, x, flags=sb.FLAG_TABLE_SCAN).count == ref["kmp"]
+            assert sb.search("hor", t3, x, flags=sb.FLAG_TABLE_SCAN).count == ref["hor"]
+            # an algorithm without a table-driven kernel ignores the flag
+            assert sb.search("bm", t, x, flags=sb.FLAG_TABLE_SCAN).count == ref["bm"]
+            assert sb.last_timing().filter_kind not in range(601, 607)
+
+
+def test_table_driven_scans_segment_seams(oracle):
+    """One thread per 4 KiB (16 KiB for m > 1024) of start positions, each reading the m-1 bytes behind its segment:
+    occurrences across every seam, dense overlapping occurrences, text ends."""
+    rng = np.random.default_rng(31)
+    n = 300_000
+    texts = {"rand2": rng.integers(0, 2, n, dtype=np.uint8), "rand4": rng.integers(97, 101, n, dtype=np.uint8),
+             "aaa": np.full(n, 97, dtype=np.uint8), "abab": np.resize(np.frombuffer(b"ab", np.uint8), n).copy()}
+    for name, y in texts.items():
+        with sb.Text.upload(y) as t, sb.Text.upload(y, devices=[0, 0]) as t2:
+            for m in (1, 2, 3, 5, 8, 9, 31, 32, 33, 40, 64, 100, 1000, 1025, 4200):
+                if m > 100 and name in ("aaa", "abab"):
+                    continue  # hor.c / hash3.c compare every window in full on these: O(n*m), on the device as on the CPU
+                for k in (0, 4096 - m // 2, 16384 - 1, n - m):
+                    if k < 0:
+                        continue
+                    x = y[k:k + m].copy()
+                    want = oracle.bf_count(x, y)
+                    for a in TABLE_KIND:
+                        exp = expected(a, m, want, n)
+                        assert sb.search(a, t, x, flags=sb.FLAG_TABLE_SCAN).count == exp, (name, m, k, a)
+                    assert sb.search("so", t2, x, flags=sb.FLAG_TABLE_SCAN).count == want, (name, m, k)
+                x = y[100:100 + m].copy()
+                x[-1] ^= 0x1F  # (probably) absent
+                want = oracle.bf_count(x, y)
+                for a in ("kmp", "hor", "so", "hash3"):
+                    assert sb.search(a, t, x, flags=sb.FLAG_TABLE_SCAN).count == expected(a, m, want, n), (name, m, a)
+
+
 def test_sbndm2_the_reference_default_selection(oracle, golden):
     """sbndm2 is the one algorithm src/algorithms.h:133 enables, so it is registered although the reference's own
     output is wrong for periodic patterns with m > 32.  Ours: the exact count everywhere, -1 for m < 2
