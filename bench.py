@@ -382,6 +382,23 @@ def main_ours(args, algos, ms):
                                "GBps_kernel_median": own / (float(np.median(ts)) * 1e-3) / 1e9,
                                "GBps_kernel_best": own / (min(ts) * 1e-3) / 1e9}
 
+    # ---- the algorithm axis: the same searches with each algorithm's OWN table driving the scan on the device
+    # (SB_FLAG_TABLE_SCAN: kmpNext / hbc / Shift-Or masks in shared memory, table_kernels.cuh); bf has no table
+    table_scan = {}
+    try:
+        for a in algos:
+            if a == "bf":
+                continue
+            row = {}
+            for m in ms:
+                r = sb.search(a, text, pats[m], flags=sb.FLAG_TABLE_SCAN)
+                tm = sb.last_timing()
+                if tm.filter_kind in range(601, 607) and r.count == sb.search(a, text, pats[m]).count:
+                    row[str(m)] = own / (tm.kernel_ms * 1e-3) / 1e9
+            table_scan[a] = row
+    except Exception as e:  # an extra, never fatal
+        table_scan = {"error": repr(e)}
+
     # ---- (f)-3 extra: the driver's real shape, 500 patterns of one length, counted in ONE pass
     multi = None
     try:
@@ -462,6 +479,7 @@ def main_ours(args, algos, ms):
             "value_kernels_only": bytes_per_step_rank * args.steps / (max_kernel_ms * 1e-3) / 1e9 * world,
             "value_host_clock": bytes_per_step * args.steps / (max_host_ms * 1e-3) / 1e9,
             "per_m": per_m_rates, "occurrences_per_step": sum_cnt // args.steps, "multi_pattern": multi,
+            "table_scan_GBps": table_scan,
             "config4": config4,
             "timing": "CUDA events on the library's launching stream bracketing the K timed steps (between "
                       "barrier+synchronize pairs), max over ranks; every step submits its 16 searches asynchronously "

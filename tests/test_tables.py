@@ -179,3 +179,26 @@ def test_not_applicable_domains():
     for name in ALGOS + EXTRA_ALGOS:
         for m in (1, 2, 3, 4, 5, 6, 7, 8, 9, 31, 32, 33):
             assert sb.applicable(name, m) == (m >= rule(name)), (name, m)
+
+
+def test_prep_tables_struct_can_be_reused_across_families():
+    """the scalars that lie between the big arrays (qfQ, qfS, wfrQ) and everything before them are reset
+    on every call; a struct that last held a QF or WFR pattern does not leak that into the next family."""
+    x = np.frombuffer(b"abracadabra", dtype=np.uint8)
+    t = sb.Tables()
+    L = sb.lib()
+    import ctypes as C
+
+    def prep(name):
+        assert L.sb_prep_tables(sb.algo_id(name), x.ctypes.data, x.size, C.byref(t)) == 0
+
+    prep("qf23")
+    assert (t.qfQ, t.qfS) == (2, 3)
+    prep("wfrq4")
+    assert t.wfrQ == 4 and (t.qfQ, t.qfS) == (0, 0)
+    prep("hash3")
+    assert t.hashQ == 3 and t.wfrQ == 0 and (t.qfQ, t.qfS) == (0, 0)
+    prep("kmp")
+    assert t.hashQ == 0 and t.wfrQ == 0 and t.kmpNext[0] == -1 and t.m == x.size
+    fresh = sb.prep_tables("kmp", x)
+    assert list(t.kmpNext[: x.size + 1]) == list(fresh.kmpNext[: x.size + 1]) and list(t.hbc) == list(fresh.hbc)
