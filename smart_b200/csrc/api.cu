@@ -68,6 +68,7 @@ constexpr int kFilterPswar = 500;             // scan_pswar<BITS,KF>: reported a
 /* scan_pswar covers m <= 30 on a 1-bit copy and m <= 22 on a 2-bit one; beyond, the half-word bitmap kernels are faster */
 constexpr int kPswarMaxM1 = 30, kPswarMaxM2 = 22;
 constexpr size_t kAuxWords = sb::kBloomWords + 2 * sb::kSkipTableSize;
+constexpr size_t kTableInts = (size_t)1 << 18;  // SB_FLAG_TABLE_SCAN: the largest table is qf's B[2^18]
 
 constexpr int kTickets = 256;                 // outstanding asynchronous searches (sb_search64_submit)
 constexpr int kSyncSlot = kTickets;           // pattern/counter slot of the blocking paths (positions, multi)
@@ -120,7 +121,7 @@ struct DevCtx {                               // per-device scratch, created on 
     int occ_swar[8] = {0};                    // ... for scan_swar<M, DENSE>, index (M-1)*2 + DENSE
     mutable int occ_pswar[2][33][2] = {{{0}}};  // ... for scan_pswar<BITS,KF,EXACT>, filled on first use
     unsigned long long *d_hist = nullptr;     // 256-bin byte histogram scratch
-    int32_t *d_table = nullptr;               // SB_FLAG_TABLE_SCAN: the algorithm's table (<= SB_XSIZE + 1 ints)
+    int32_t *d_table = nullptr;               // SB_FLAG_TABLE_SCAN: the algorithm's table (kTableInts ints)
     uint32_t *d_mpat = nullptr;               // scan_multi: pattern set (words), grown on demand
     size_t mpat_words = 0;
     unsigned long long *d_mcounts = nullptr;  // scan_multi: per-pattern counts
@@ -1582,11 +1583,21 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
     case SB_FAM_SO: kind = 604; break;
     case SB_FAM_SA: kind = 605; break;
     case SB_FAM_HASHQ: kind = 606; break;
-    default: return -100;
+    case SB_FAM_BM: kind = 607; break;
+    case SB_FAM_QS: kind = strcmp(desc->name, "qs") == 0 ? 608 : 0; break;  // (ssabs shares the family, not the loop)
+    case SB_FAM_RAITA: kind = 609; break;
+    case SB_FAM_TUNEDBM: kind = 610; break;
+    case SB_FAM_KR: kind = 611; break;
+    case SB_FAM_QF: kind = 612; break;
+    default: break;
     }
+    if (!kind) return -100;
     const double t0 = now_ms();
-    static thread_local int table[SB_XSIZE + 1], scratch[SB_XSIZE + 1];
-    int ntable = 256, sh1 = 0;
+    static thread_local int *table = nullptr;
+    static thread_local int scratch[SB_XSIZE + 1];
+    if (!table) table = (int *)malloc(kTableInts * sizeof(int));
+    if (!table) return SB_ERR_NOMEM;
+    int ntable = 256, sh1 = 0, qq = desc->q;
     unsigned lim = 0;
     switch (kind) {  // the preprocessing stage proper: bit-identical to preKmp / preMp / Pre_Horspool / preSo / preSA / hash3.c:37-55
     case 601:
@@ -1601,7 +1612,30 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
     case 603: sb_prep_hbc(x, m, table); break;
     case 604: lim = sb_prep_so(x, m, reinterpret_cast<unsigned int *>(table)); break;
     case 605: lim = sb_prep_sa(x, m, reinterpret_cast<unsigned int *>(table)); break;
-    default: sb_prep_hashq(x, m, desc->q, table, &sh1); break;
+    case 606: sb_prep_hashq(x, m, desc->q, table, &sh1); break;
+    case 607:  // bmBc[256] then bmGs[0..m)
+        sb_prep_hbc(x, m, table);
+        sb_prep_bmgs(x, m, scratch, table + 256);
+        ntable = 256 + m;
+        break;
+    case 608: sb_prep_qsbc(x, m, table); break;
+    case 609:
+    case 610: sb_prep_hbc(x, m, table); break;  // preBmBc of raita.c:26-32 / tunedbm.c:26-32 == Pre_Horspool
+    case 611: {
+        int d = 0, hx = 0;
+        sb_prep_kr(x, m, &d, &hx);
+        lim = (unsigned)d;
+        sh1 = hx;
+        ntable = 1;
+        table[0] = 0;
+        break;
+    }
+    default:  // qf<Q><S>
+        sb_prep_qf(x, m, desc->Q, desc->S, table);
+        ntable = 1 << (desc->Q * desc->S);
+        qq = desc->Q;
+        sh1 = desc->S;
+        break;
     }
     const double t1 = now_ms();
     const long long total_starts = (long long)t->n - m + 1;
@@ -1612,7 +1646,7 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         const Shard &s = t->sh[g];
         DevCtx *c = get_ctx(s.dev);
         if (!c) return SB_ERR_CUDA;
-        if (!c->d_table) CU_TRY(cudaMalloc(&c->d_table, (SB_XSIZE + 1) * sizeof(int32_t)), SB_ERR_NOMEM);
+        if (!c->d_table) CU_TRY(cudaMalloc(&c->d_table, kTableInts * sizeof(int32_t)), SB_ERR_NOMEM);
         long long hi = total_starts - (long long)s.base;
         if (hi > (long long)s.own) hi = (long long)s.own;
         if (hi <= 0) continue;
@@ -1631,7 +1665,7 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         a.hi = hi;
         a.m = m;
         a.seg = m <= 1024 ? 4096 : 16384;  // start positions per thread; each thread also reads the m-1 bytes behind them
-        a.q = desc->q;
+        a.q = qq;
         a.sh1 = sh1;
         a.lim = lim;
         const unsigned long long nthreads = ((unsigned long long)hi + a.seg - 1) / a.seg;
@@ -1643,7 +1677,13 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         case 603: sb::table_hor_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 604: sb::table_so_kernel<false><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 605: sb::table_so_kernel<true><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
-        default: sb::table_hashq_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 606: sb::table_hashq_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 607: sb::table_bm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 608: sb::table_bc_kernel<sb::kBcQs><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 609: sb::table_bc_kernel<sb::kBcRaita><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 610: sb::table_bc_kernel<sb::kBcTuned><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 611: sb::table_kr_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        default: sb::table_qf_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         }
         CU_TRY(cudaGetLastError(), SB_ERR_CUDA);
         CU_TRY(cudaEventRecord(c->e1, c->stream), SB_ERR_CUDA);

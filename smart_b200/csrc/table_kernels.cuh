@@ -11,6 +11,15 @@
  *                remaining bytes, as search_large does (so.c:85-93) - without reading past the text
  *   hash3/5/8    shift[256] and sh1 (hash3.c:37-55): skip while shift[h(q-gram)] != 0, verify at 0, then += sh1
  *                (hash3.c:66-81) - without the pattern sentinel the reference writes behind the text (hash3.c:61)
+ *   bm           bmBc[256] + bmGs[0..m) (bm.c:27-66): right-to-left compare, j += MAX(bmGs[i], bmBc[y[i+j]]-m+1+i)
+ *   qs           qsBc[256] (qs.c:26-30): compare, then s += qsBc[y[s+m]] (qs.c:46-50)
+ *   raita        bmBc[256] (raita.c:26-32): last, middle, first character, then the rest (raita.c:54-60)
+ *   tunedbm      bmBc[256] with bmBc[x[m-1]] = 0 and `shift` (tunedbm.c:38-42): the unrolled skip loop (:48-53)
+ *                bounded by the segment instead of the sentinel the reference writes behind the text (:42)
+ *   kr           d = 2^(m-1) and hx (kr.c:34-40): rolling hash REHASH (kr.c:26), memcmp on a hash hit (:48)
+ *   qf<Q><S>     B[1 << (Q*S)] (qf23.c:50-56): the q-gram at every (m-Q+1)-th position and, while bits survive,
+ *                every Q-th one before it; surviving alignments are compared (qf23.c:61-82).  B sits in shared
+ *                memory up to 8192 entries, else in global memory (L2: 2^16 or 2^18 entries)
  *
  * Parallelisation: the scan loops are inherently sequential, so the text is cut into segments of `seg` start
  * positions, one THREAD per segment, each reading m-1 bytes past its segment (the same m-1 halo rule as the shards).
@@ -179,6 +188,168 @@ __global__ void __launch_bounds__(kTableThreads) table_hashq_kernel(const __grid
             while (j < a.m && s_x[j] == __ldg(a.text + st + j)) j++;
             if (j == a.m) cnt++;
             i += a.sh1;
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Boyer-Moore: table = bmBc[256] followed by bmGs[0..m) ---- */
+__global__ void __launch_bounds__(kTableThreads) table_bm_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ int s_bc[256];
+    __shared__ int s_gs[SB_XSIZE];
+    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_bc[i] = a.table[i];
+    for (int i = threadIdx.x; i < a.m; i += kTableThreads) s_gs[i] = a.table[256 + i];
+    stage_pattern_smem(s_x, a);
+    __syncthreads();
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        long long j = lo;
+        while (j < own_end) {
+            int i = a.m - 1;
+            unsigned c = 0;
+            while (i >= 0 && s_x[i] == (c = __ldg(a.text + i + j))) --i;  // bm.c:83
+            if (i < 0) {
+                cnt++;
+                j += s_gs[0];                                              // bm.c:86
+            } else {
+                const int bc = s_bc[c] - a.m + 1 + i;
+                j += s_gs[i] > bc ? s_gs[i] : bc;                          // bm.c:89
+            }
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- bad-character scans: table = qsBc[256] (QS) or bmBc[256] (RAITA, TUNED) ---- */
+enum { kBcQs = 0, kBcRaita = 1, kBcTuned = 2 };
+template <int KIND>
+__global__ void __launch_bounds__(kTableThreads) table_bc_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ int s_bc[256];
+    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_bc[i] = a.table[i];
+    stage_pattern_smem(s_x, a);
+    __syncthreads();
+    const int m = a.m;
+    const unsigned last_ch = s_x[m - 1];
+    const int shift = s_bc[last_ch];                  // tunedbm.c:40 (read before the entry is zeroed)
+    __syncthreads();
+    if (KIND == kBcTuned && threadIdx.x == 0) s_bc[last_ch] = 0;  // tunedbm.c:41
+    __syncthreads();
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        long long s = lo;
+        while (s < own_end) {
+            if (KIND == kBcQs) {
+                int i = 0;
+                while (i < m && s_x[i] == __ldg(a.text + s + i)) i++;  // qs.c:47-48
+                if (i == m) cnt++;
+                s += s_bc[__ldg(a.text + s + m)];                      // qs.c:50 (the byte after the window)
+            } else if (KIND == kBcRaita) {
+                const unsigned c = __ldg(a.text + s + m - 1);
+                if (c == last_ch && s_x[m / 2] == __ldg(a.text + s + m / 2) && s_x[0] == __ldg(a.text + s)) {  // raita.c:55-57
+                    int i = 1;
+                    while (i < m - 1 && s_x[i] == __ldg(a.text + s + i)) i++;                                   // raita.c:58
+                    if (i >= m - 1) cnt++;
+                }
+                s += s_bc[c];                                                                                  // raita.c:60
+            } else {
+                int k = s_bc[__ldg(a.text + s + m - 1)];  // tunedbm.c:48-53, bounded by the segment, not a sentinel
+                while (k != 0 && s < own_end) {
+                    s += k;
+                    k = s_bc[__ldg(a.text + s + m - 1)];
+                }
+                if (s < own_end && k == 0) {
+                    int i = 0;
+                    while (i < m - 1 && s_x[i] == __ldg(a.text + s + i)) i++;  // tunedbm.c:54: the first m-1 bytes
+                    if (i >= m - 1) cnt++;
+                }
+                s += shift;                                                     // tunedbm.c:56
+            }
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Karp-Rabin: a.lim = d = 2^(m-1) (wrapping), a.sh1 = hx ---- */
+__global__ void __launch_bounds__(kTableThreads) table_kr_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    stage_pattern_smem(s_x, a);
+    __syncthreads();
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        const unsigned d = a.lim, hx = (unsigned)a.sh1;
+        unsigned hy = 0;
+        for (int i = 0; i < a.m; i++) hy = (hy << 1) + __ldg(a.text + lo + i);  // kr.c:37-40 for this segment's first window
+        for (long long j = lo; j < own_end; j++) {
+            if (hx == hy) {                                                      // kr.c:48
+                int i = 0;
+                while (i < a.m && s_x[i] == __ldg(a.text + j + i)) i++;
+                if (i == a.m) cnt++;
+            }
+            hy = ((hy - __ldg(a.text + j) * d) << 1) + __ldg(a.text + j + a.m);  // REHASH, kr.c:26,49
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Q-gram filtering: table = B[1 << (Q*S)]; a.q = Q, a.sh1 = S ---- */
+constexpr int kQfSharedEntries = 8192;
+__global__ void __launch_bounds__(kTableThreads) table_qf_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ int s_B[kQfSharedEntries];
+    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    const int Q = a.q, S = a.sh1, asize = 1 << (Q * S);
+    const bool small = asize <= kQfSharedEntries;
+    if (small)
+        for (int i = threadIdx.x; i < asize; i += kTableThreads) s_B[i] = a.table[i];
+    stage_pattern_smem(s_x, a);
+    __syncthreads();
+    const int *B = small ? s_B : a.table;
+    const unsigned mask = (unsigned)asize - 1u;
+    const int m = a.m, mq1 = m - Q + 1;
+    const long long n = a.hi + m - 1;  // text bytes of this shard's own windows
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    auto gram = [&](long long i) {  // qf23.c:62 / qf33.c:58-60: ((..y[i+Q-1] << S) + ..) << S) + y[i]
+        unsigned ch = __ldg(a.text + i + Q - 1);
+        for (int t = Q - 2; t >= 0; t--) ch = (ch << S) + __ldg(a.text + i + t);
+        return ch & mask;
+    };
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        // qf23.c:61: the scan state is the index i alone, so a segment starts like the text does (i = mq1-1, at lo)
+        for (long long i = lo + mq1 - 1; i <= n - Q && i - mq1 + 1 < own_end; i += mq1) {
+            unsigned D = small ? (unsigned)B[gram(i)] : (unsigned)__ldg(B + gram(i));
+            if (!D) continue;
+            const long long j = i - mq1 + Q;
+            for (;;) {                                      // qf23.c:65-72 ("more:")
+                i -= Q;
+                if (i >= j) {
+                    D &= small ? (unsigned)B[gram(i)] : (unsigned)__ldg(B + gram(i));
+                    if (D == 0) break;
+                } else {                                    // qf23.c:73-81: verify the surviving alignments
+                    i = j;
+                    long long k = j - Q + 1, top = j > n - m ? n - m : j;
+                    if (k < lo) k = lo;                     // (start positions of this segment only)
+                    if (top > own_end - 1) top = own_end - 1;
+                    for (; k <= top; k++) {
+                        int t = 0;
+                        while (t < m && s_x[t] == __ldg(a.text + k + t)) t++;
+                        if (t == m) cnt++;
+                    }
+                    break;
+                }
+            }
         }
     }
     table_reduce(a, cnt);

@@ -74,7 +74,11 @@ def test_golden_reference_counts(oracle, golden, tname):
                 assert got == ref[a], (tname, c["m"], c["pi"], a, got, ref[a])
 
 
-TABLE_KIND = {"kmp": 601, "mp": 602, "hor": 603, "so": 604, "sa": 605, "hash3": 606, "hash5": 606, "hash8": 606}
+TABLE_KIND = {"kmp": 601, "mp": 602, "hor": 603, "so": 604, "sa": 605, "hash3": 606, "hash5": 606, "hash8": 606,
+              "bm": 607, "qs": 608, "raita": 609, "tunedbm": 610, "kr": 611,
+              **{f"qf{q}{s_}": 612 for q, s_ in ((2, 3), (2, 4), (2, 6), (2, 8), (3, 3), (3, 4), (3, 6), (4, 2), (4, 3), (4, 4),
+                                               (6, 2), (6, 3))}}
+QUADRATIC = tuple(k for k in TABLE_KIND if k not in ("kmp", "mp", "so", "sa"))  # compare whole windows: O(n*m) on a^n
 
 
 @pytest.mark.parametrize("tname", TEXT_NAMES)
@@ -89,7 +93,7 @@ def test_table_driven_scans_match_the_reference(oracle, golden, tname):
             ref = dict(zip(ALGOS, c["ref"]))
             quadratic = tname in ("a16k", "ab16k", "aab16k") and c["m"] > 256  # hor/hash*: every window compared in full
             for a, kind in TABLE_KIND.items():
-                if quadratic and a in ("hor", "hash3", "hash5", "hash8"):
+                if quadratic and a in QUADRATIC:  # O(n*m) on periodic inputs, on the device as on the CPU
                     continue
                 got = sb.search(a, t, x, flags=sb.FLAG_TABLE_SCAN).count
                 assert got == ref[a], (tname, c["m"], c["pi"], a, got, ref[a])
@@ -99,8 +103,8 @@ def test_table_driven_scans_match_the_reference(oracle, golden, tname):
             if not quadratic:
                 assert sb.search("hor", t3, x, flags=sb.FLAG_TABLE_SCAN).count == ref["hor"]
             # an algorithm without a table-driven kernel ignores the flag
-            assert sb.search("bm", t, x, flags=sb.FLAG_TABLE_SCAN).count == ref["bm"]
-            assert sb.last_timing().filter_kind not in range(601, 607)
+            assert sb.search("smith", t, x, flags=sb.FLAG_TABLE_SCAN).count == ref["smith"]
+            assert sb.last_timing().filter_kind not in range(601, 613)
 
 
 def test_table_driven_scans_segment_seams(oracle):
@@ -114,7 +118,7 @@ def test_table_driven_scans_segment_seams(oracle):
         with sb.Text.upload(y) as t, sb.Text.upload(y, devices=[0, 0]) as t2:
             for m in (1, 2, 3, 5, 8, 9, 31, 32, 33, 40, 64, 100, 1000, 1025, 4200):
                 if m > 100 and name in ("aaa", "abab"):
-                    continue  # hor.c / hash3.c compare every window in full on these: O(n*m), on the device as on the CPU
+                    continue  # all but kmp/mp/so/sa compare every window in full on these: O(n*m), as on the CPU
                 for k in (0, 4096 - m // 2, 16384 - 1, n - m):
                     if k < 0:
                         continue
@@ -127,7 +131,7 @@ def test_table_driven_scans_segment_seams(oracle):
                 x = y[100:100 + m].copy()
                 x[-1] ^= 0x1F  # (probably) absent
                 want = oracle.bf_count(x, y)
-                for a in ("kmp", "hor", "so", "hash3"):
+                for a in ("kmp", "hor", "so", "hash3", "bm", "qs", "kr", "qf23", "qf63", "tunedbm", "raita"):
                     assert sb.search(a, t, x, flags=sb.FLAG_TABLE_SCAN).count == expected(a, m, want, n), (name, m, a)
 
 
