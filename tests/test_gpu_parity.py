@@ -91,7 +91,7 @@ def test_table_driven_scans_match_the_reference(oracle, golden, tname):
         for c in (c for c in golden["cases"] if c["text"] == tname):
             x = make_patterns(tname, y, c["m"])[c["pi"]]
             ref = dict(zip(ALGOS, c["ref"]))
-            quadratic = tname in ("a16k", "ab16k", "aab16k") and c["m"] > 256  # hor/hash*: every window compared in full
+            quadratic = tname in ("a16k", "ab16k", "aab16k") and c["m"] > 16  # every window compared in full: O(n*m) per thread
             for a, kind in TABLE_KIND.items():
                 if quadratic and a in QUADRATIC:  # O(n*m) on periodic inputs, on the device as on the CPU
                     continue
