@@ -99,6 +99,14 @@ sb_text *sb_text_upload(const unsigned char *host, size_t n, const int *devices,
 /* Generate n bytes ON the device(s) with the counter-based generator (see sb_textgen_host):
  * byte i depends only on (seed, sigma, i), so shards are generated in place. sigma in [1,256]. */
 sb_text *sb_text_generate(size_t n, int sigma, uint64_t seed, const int *devices, int ndev);
+/* textgen PARITY mode: the first n bytes (n <= 5 000 000) of SMART's own data/rand<sigma>/rand<sigma>.txt, generated
+ * ON the device(s).  src/textgen.c:34-54 writes those files as byte = rand() % sigma from one never-seeded glibc
+ * rand() stream (sigma = 2, 4, 8, 16, 32, 64, 128, 250 in that order, 5 000 000 bytes each); glibc's generator is the
+ * linear recurrence r[i] = r[i-3] + r[i-31], so the host jumps to every 4096-output block and the blocks are
+ * generated in parallel.  Bit-identical to the files (md5 in SURVEY.md Appendix B). */
+sb_text *sb_text_generate_rand(int sigma, size_t n, const int *devices, int ndev);
+/* host mirror: bytes [off, off+len) of rand<sigma>.txt by the same jump + recurrence (0, or -1 on bad arguments) */
+int sb_textgen_rand_host(unsigned char *dst, int sigma, size_t off, size_t len);
 /* One process per GPU (bench.py under torchrun): this process holds only part `part` of `nparts` of a
  * global text of n_total bytes, on `device`. Searches on such a handle count only the start positions the
  * part owns; the caller sums the per-part counts (no collective on the data path). */

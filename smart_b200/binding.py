@@ -151,6 +151,8 @@ SYMBOLS = [
     ("sb_version", C.c_char_p, []),
     ("sb_text_upload", C.c_void_p, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.c_int]),
     ("sb_text_generate", C.c_void_p, [C.c_size_t, C.c_int, C.c_uint64, C.POINTER(C.c_int), C.c_int]),
+    ("sb_text_generate_rand", C.c_void_p, [C.c_int, C.c_size_t, C.POINTER(C.c_int), C.c_int]),
+    ("sb_textgen_rand_host", C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t]),
     ("sb_text_generate_part", C.c_void_p, [C.c_size_t, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int]),
     ("sb_text_upload_part", C.c_void_p, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int]),
     ("sb_shard_range", C.c_int, [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
@@ -273,6 +275,12 @@ class Text:
     def generate(cls, n: int, sigma: int, seed: int, devices=None) -> "Text":
         dev, nd = _devices(devices)
         return cls(lib().sb_text_generate(n, sigma, seed, dev, nd))
+
+    @classmethod
+    def generate_rand(cls, sigma: int, n: int = 5000000, devices=None) -> "Text":
+        """SMART's own rand<sigma> buffer (src/textgen.c: glibc rand() % sigma), generated on the device"""
+        dev, nd = _devices(devices)
+        return cls(lib().sb_text_generate_rand(sigma, n, dev, nd))
 
     @classmethod
     def generate_part(cls, n_total: int, sigma: int, seed: int, nparts: int, part: int, device: int = 0) -> "Text":
@@ -449,6 +457,14 @@ def prep_tables(algo: str, pattern) -> Tables | None:
     if r != 0:
         raise SmartB200Error("sb_prep_tables: bad argument")
     return t
+
+
+def textgen_rand_host(sigma: int, off: int, length: int) -> np.ndarray:
+    """host mirror of Text.generate_rand: bytes [off, off+length) of SMART's rand<sigma>.txt"""
+    out = np.empty(length, dtype=np.uint8)
+    if lib().sb_textgen_rand_host(out.ctypes.data, sigma, off, length) != 0:
+        raise SmartB200Error("sb_textgen_rand_host: bad arguments")
+    return out
 
 
 def textgen_host(off: int, length: int, sigma: int, seed: int) -> np.ndarray:

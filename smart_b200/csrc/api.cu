@@ -1279,6 +1279,145 @@ sb_text *sb_text_generate(size_t n, int sigma, uint64_t seed, const int *devices
     return text_fill_generate(text_alloc(n, devices, ndev, 0, ndev), sigma, seed);
 }
 
+/* ---- SMART's own rand<sigma> buffers (src/textgen.c:34-54), generated on the device ---- */
+namespace {
+constexpr int kRandDeg = 31;  // r[i] = r[i-3] + r[i-31]: characteristic polynomial x^31 - x^28 - 1 over Z_2^32
+struct RandPoly {
+    uint32_t c[kRandDeg];
+};
+RandPoly rand_mul(const RandPoly &p, const RandPoly &q)
+{
+    uint32_t prod[2 * kRandDeg - 1] = {0};
+    for (int i = 0; i < kRandDeg; i++)
+        for (int j = 0; j < kRandDeg; j++) prod[i + j] += p.c[i] * q.c[j];
+    for (int d = 2 * kRandDeg - 2; d >= kRandDeg; d--) {  // x^d = x^(d-3) + x^(d-31)
+        prod[d - 3] += prod[d];
+        prod[d - 31] += prod[d];
+    }
+    RandPoly r;
+    memcpy(r.c, prod, sizeof r.c);
+    return r;
+}
+RandPoly rand_xpow(unsigned long long n)
+{
+    RandPoly result = {{1}}, base = {{0, 1}};
+    while (n) {
+        if (n & 1) result = rand_mul(result, base);
+        base = rand_mul(base, base);
+        n >>= 1;
+    }
+    return result;
+}
+/* the 31 values a_0..a_30 the recurrence starts from: glibc srandom(1) (r[0] = 1, r[i] = 16807 r[i-1] mod 2^31-1 by
+ * Schrage's method, r[31..33] = r[0..2]); a_n = r[n+3], and rand()'s k-th output is a_(k+341) >> 1 */
+void rand_base(uint32_t *a)
+{
+    int32_t r[34];
+    r[0] = 1;
+    for (int i = 1; i < 31; i++) {
+        const long hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+        long w = 16807 * lo - 2836 * hi;
+        if (w < 0) w += 2147483647;
+        r[i] = (int32_t)w;
+    }
+    for (int i = 31; i < 34; i++) r[i] = r[i - 31];
+    for (int n = 0; n < kRandDeg; n++) a[n] = (uint32_t)r[n + 3];
+}
+}  // namespace
+
+/* 31 consecutive values a_P .. a_(P+30) of the stream, by jumping (no stepping from the start) */
+static void rand_state_at(unsigned long long P, const RandPoly *xP, uint32_t *out)
+{
+    uint32_t base[kRandDeg];
+    rand_base(base);
+    RandPoly q = xP ? *xP : rand_xpow(P);
+    for (int j = 0; j < kRandDeg; j++) {  // a_(P+j) = sum_k coeff_k(x^(P+j)) a_k
+        uint32_t v = 0;
+        for (int k = 0; k < kRandDeg; k++) v += q.c[k] * base[k];
+        out[j] = v;
+        const uint32_t top = q.c[kRandDeg - 1];  // multiply by x: x^31 = x^28 + 1
+        for (int k = kRandDeg - 1; k > 0; k--) q.c[k] = q.c[k - 1];
+        q.c[0] = top;
+        q.c[28] += top;
+    }
+}
+
+static int rand_file_index(int sigma)
+{
+    static const int sigmas[8] = {2, 4, 8, 16, 32, 64, 128, 250};  // the files textgen.c writes, in stream order
+    for (int f = 0; f < 8; f++)
+        if (sigmas[f] == sigma) return f;
+    return -1;
+}
+
+int sb_textgen_rand_host(unsigned char *dst, int sigma, size_t off, size_t len)
+{
+    const int file = rand_file_index(sigma);
+    if (file < 0 || !dst || off > 5000000 || len > 5000000 - off) return -1;
+    uint32_t a[kRandDeg];
+    rand_state_at(341ull + 5000000ull * (unsigned long long)file + off, nullptr, a);
+    int head = 0;
+    for (size_t i = 0; i < len; i++) {  // the same ring the device threads run (rand_textgen_kernel)
+        const uint32_t out = a[head];
+        dst[i] = (unsigned char)((out >> 1) % (uint32_t)sigma);
+        const int k28 = head + 28 >= 31 ? head + 28 - 31 : head + 28;
+        a[head] = a[k28] + out;
+        head = head + 1 == 31 ? 0 : head + 1;
+    }
+    return 0;
+}
+
+sb_text *sb_text_generate_rand(int sigma, size_t n, const int *devices, int ndev)
+{
+    const int file = rand_file_index(sigma);
+    if (file < 0 || n < 1 || n > 5000000) {
+        set_err("sb_text_generate_rand: sigma must be one of SMART's rand buffers (2..128, 250) and n <= 5000000%s%s");
+        return nullptr;
+    }
+    if (ndev <= 0) ndev = 1;
+    sb_text *t = text_alloc(n, devices, ndev, 0, ndev);
+    if (!t) return nullptr;
+    const RandPoly xB = rand_xpow(sb::kRandBlock);
+    for (int g = 0; g < t->nshards; g++) {
+        Shard &s = t->sh[g];
+        DevCtx *c = get_ctx(s.dev);
+        if (!c) {
+            sb_text_free(t);
+            return nullptr;
+        }
+        const unsigned nblocks = (unsigned)((s.len + sb::kRandBlock - 1) / sb::kRandBlock);
+        std::vector<uint32_t> states((size_t)nblocks * kRandDeg);
+        // stream index of the shard's first byte: 5 000 000 outputs per earlier file, then the offset inside this one
+        RandPoly p = rand_xpow(341ull + 5000000ull * (unsigned long long)file + s.base);
+        for (unsigned b = 0; b < nblocks; b++) {
+            rand_state_at(0, &p, states.data() + (size_t)b * kRandDeg);
+            p = rand_mul(p, xB);
+        }
+        uint32_t *d_states = nullptr;
+        bool ok = nblocks == 0 || cudaMalloc(&d_states, states.size() * sizeof(uint32_t)) == cudaSuccess;
+        ok = ok && cudaMemsetAsync(s.d_text, 0, s.cap, c->stream) == cudaSuccess;
+        if (ok && nblocks) {
+            ok = cudaMemcpyAsync(d_states, states.data(), states.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream) ==
+                 cudaSuccess;
+            if (ok) sb::rand_textgen_kernel<<<(nblocks + 127) / 128, 128, 0, c->stream>>>(s.d_text, s.len, d_states, nblocks, sigma);
+            ok = ok && cudaGetLastError() == cudaSuccess;
+        }
+        ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+        if (d_states) cudaFree(d_states);
+        if (!ok) {
+            set_err("sb_text_generate_rand failed: %s%s", cudaGetErrorString(cudaGetLastError()));
+            sb_text_free(t);
+            return nullptr;
+        }
+    }
+    if (!text_measure_bits(t)) {
+        set_err("text statistics kernel failed: %s%s", cudaGetErrorString(cudaGetLastError()));
+        sb_text_free(t);
+        return nullptr;
+    }
+    return t;
+}
+
 sb_text *sb_text_generate_part(size_t n_total, int sigma, uint64_t seed, int nparts, int part, int device)
 {
     if (sigma < 1 || sigma > 256) {

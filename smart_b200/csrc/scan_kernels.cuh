@@ -1612,4 +1612,32 @@ __global__ void __launch_bounds__(256) textgen_kernel(uint4 *dst, unsigned long 
     }
 }
 
+/* ---- textgen parity mode: SMART's own random buffers, generated on the device ----
+ * src/textgen.c:34-54 writes data/rand<sigma>/rand<sigma>.txt as byte = rand() % sigma from ONE glibc rand() stream
+ * that is never seeded.  glibc's rand() is the additive feedback generator r[i] = r[i-3] + r[i-31] (mod 2^32),
+ * output r[i] >> 1: linear, so the host jumps to the start of every block of kRandBlock outputs (x^P modulo
+ * x^31 - x^28 - 1, api.cu) and each thread runs the recurrence for its block from those 31 words. */
+constexpr int kRandBlock = 4096;
+
+__global__ void __launch_bounds__(128) rand_textgen_kernel(uint8_t *dst, unsigned long long nbytes, const uint32_t *states,
+                                                            unsigned nblocks, int sigma)
+{
+    const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    uint32_t a[31];  // a[k] = the value 31-k steps back ... kept as a ring: a[(i + k) % 31]
+#pragma unroll
+    for (int k = 0; k < 31; k++) a[k] = states[31ull * b + k];
+    const unsigned long long lo = (unsigned long long)b * kRandBlock;
+    const unsigned long long hi = min(nbytes, lo + kRandBlock);
+    int head = 0;  // a[head] is the oldest value = the next output
+    for (unsigned long long i = lo; i < hi; i++) {
+        const uint32_t out = a[head];
+        dst[i] = (uint8_t)((out >> 1) % (uint32_t)sigma);
+        // the value 31 steps later: a_{n+31} = a_{n+28} + a_n
+        const int k28 = head + 28 >= 31 ? head + 28 - 31 : head + 28;
+        a[head] = a[k28] + out;
+        head = head + 1 == 31 ? 0 : head + 1;
+    }
+}
+
 }  // namespace sb

@@ -479,6 +479,31 @@ def test_generated_text_matches_host_mirror():
             assert np.array_equal(t.download(n - 100, 100), host[-100:])
 
 
+def test_device_generates_smarts_rand_buffers(oracle):
+    """textgen parity mode: SMART's data/rand<sigma>/rand<sigma>.txt (glibc rand() % sigma, one continuous stream,
+    src/textgen.c:34-54) generated ON the device, bit-identical to the reference stream (the oracle replays glibc's
+    rand()), sharded or not, and searchable like any other text."""
+    import hashlib
+
+    ref2, ref250 = oracle.textgen(0, 5000000), oracle.textgen(7, 5000000)
+    with sb.Text.generate_rand(2) as t2, sb.Text.generate_rand(2, devices=[0, 0, 0]) as t2s, \
+            sb.Text.generate_rand(250, 1234567) as t250:
+        assert len(t2) == 5000000 and len(t250) == 1234567
+        got = t2.download(0, 5000000)
+        assert hashlib.md5(got.tobytes()).hexdigest() == "a8e4cecf43689f3964b4fdfe191aa01b"  # SURVEY.md Appendix B
+        assert np.array_equal(got, ref2) and np.array_equal(t2s.download(0, 5000000), ref2)
+        assert np.array_equal(t250.download(0, 1234567), ref250[:1234567])
+        assert t2.packed_bits == 1 and t250.packed_bits == 0
+        for m in (2, 8, 32, 100):
+            x = ref2[777777:777777 + m].copy()
+            want = oracle.bf_count(x, ref2)
+            assert sb.search("bf", t2, x).count == want and sb.search("hor", t2s, x).count == want
+    with sb.Text.generate_rand(4) as t4:
+        assert hashlib.md5(t4.download(0, 5000000).tobytes()).hexdigest() == "c371ad58eda30fa18f35a77b1e775ece"
+    with pytest.raises(sb.SmartB200Error):
+        sb.Text.generate_rand(3)
+
+
 @pytest.mark.parametrize("sigma,ms", [(256, (4, 16, 64, 256)), (4, (8, 64, 1024)), (2, (1024, 2048, 4096))])
 def test_full_size_properties(oracle, sigma, ms):
     """BASELINE.json configs 3-5 at 4 GiB: the count of a text-extracted pattern is >= 1 (smart.c:330's own

@@ -114,3 +114,26 @@ def test_oracle_vs_live_reference(oracle):
             x = y[k : k + m].copy()
             for a in ALGOS:
                 assert oracle.search(a, x, y) == refs[a].search(x, y), (sigma, m, a)
+
+
+def test_rand_parity_generator_host_mirror_equals_glibc_stream(oracle):
+    """sb_textgen_rand_host jumps into glibc's rand() stream (x^P mod x^31 - x^28 - 1 over Z_2^32) instead of stepping
+    from the start; it must reproduce SMART's rand<sigma>.txt files (src/textgen.c:34-54) at any offset.  The device
+    generator (sb_text_generate_rand) runs the same jump + recurrence per 4096-byte block."""
+    import hashlib
+
+    import smart_b200 as sb
+
+    md5 = {2: "a8e4cecf43689f3964b4fdfe191aa01b", 4: "c371ad58eda30fa18f35a77b1e775ece"}  # SURVEY.md Appendix B
+    for which, sigma in enumerate((2, 4, 8, 16, 32, 64, 128, 250)):
+        if which not in (0, 1, 3, 7):
+            continue  # (each oracle call replays the stream from its start)
+        ref = oracle.textgen(which, 5000000)
+        whole = sb.textgen_rand_host(sigma, 0, 5000000)
+        assert np.array_equal(whole, ref), sigma
+        if sigma in md5:
+            assert hashlib.md5(whole.tobytes()).hexdigest() == md5[sigma]
+        for off, ln in ((1, 100), (4095, 10), (4096, 5000), (1234567, 4099), (4999990, 10)):
+            assert np.array_equal(sb.textgen_rand_host(sigma, off, ln), ref[off:off + ln]), (sigma, off)
+    with pytest.raises(sb.SmartB200Error):
+        sb.textgen_rand_host(3, 0, 10)
