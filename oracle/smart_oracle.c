@@ -1232,6 +1232,36 @@ static const struct ora_tier2 {
     {"ssef", 32, 0}, /* ssef.c:41 */
 };
 
+/* aut.c:26-45 with preSMA (include/AUTOMATON.h:185-198): the automaton is grown state by state; the new state's
+ * row is a copy of the row of the state the old transition on x[i] led to.  ttrans has (m+1)*256 ints. */
+void ora_pre_aut(const unsigned char *x, int m, int *ttrans)
+{
+    for (int c = 0; c < 256; c++) ttrans[c] = 0;
+    int state = 0;
+    for (int i = 0; i < m; i++) {
+        const int old_target = ttrans[state * 256 + x[i]];
+        const int target = state + 1;
+        ttrans[state * 256 + x[i]] = target;
+        for (int c = 0; c < 256; c++) ttrans[target * 256 + c] = ttrans[old_target * 256 + c];
+        state = target;
+    }
+}
+
+static long long ora_search_aut(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    int *ttrans = malloc((size_t)(m + 1) * 256 * sizeof(int));
+    if (!ttrans) return -2;
+    ora_pre_aut(x, m, ttrans);
+    long long count = 0;
+    int state = 0;
+    for (size_t j = 0; j < n; j++) { /* aut.c:38-41 */
+        state = ttrans[state * 256 + y[j]];
+        if (state == m) count++;
+    }
+    free(ttrans);
+    return count;
+}
+
 int ora_tier2_count(void) { return (int)(sizeof ora_tier2 / sizeof ora_tier2[0]); }
 const char *ora_tier2_name(int i) { return i >= 0 && i < ora_tier2_count() ? ora_tier2[i].name : NULL; }
 
@@ -1281,6 +1311,7 @@ long long ora_search(const char *algo, const unsigned char *x, int m, const unsi
         return ora_search_qf(x, m, y, n, algo[2] - '0', algo[3] - '0');
     if (!strncmp(algo, "skip", 4) && algo[4] >= '3' && algo[4] <= '8' && !algo[5]) return ora_search_skipq(x, m, y, n, algo[4] - '0');
     if (!strcmp(algo, "zt")) return ora_search_zt(x, m, y, n);
+    if (!strcmp(algo, "aut")) return ora_search_aut(x, m, y, n);
     if (!strcmp(algo, "wfr")) return (size_t)m > n ? 0 : ora_search_wfr(x, m, y, n);
     if (!strncmp(algo, "wfrq", 4) && algo[4] >= '2' && algo[4] <= '8' && !algo[5]) return ora_search_wfrq(x, m, y, n, algo[4] - '0');
     return ora_search_tier2(algo, x, m, y, n);

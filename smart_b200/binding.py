@@ -181,6 +181,7 @@ SYMBOLS = [
     ("sb_plugin_search", C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("sb_prep_tables", C.c_int, [C.c_int, C.c_void_p, C.c_int, C.POINTER(Tables)]),
+    ("sb_prep_automaton", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
 ]
 
 
@@ -457,6 +458,15 @@ def prep_tables(algo: str, pattern) -> Tables | None:
     if r != 0:
         raise SmartB200Error("sb_prep_tables: bad argument")
     return t
+
+
+def prep_automaton(pattern) -> np.ndarray:
+    """sb_prep_automaton: the transition table of aut.c as an (m+1) x 256 uint16 array"""
+    ptr, m, keep = _as_bytes_ptr(pattern)
+    out = np.zeros((m + 1, 256), dtype=np.uint16)
+    if lib().sb_prep_automaton(ptr, m, out.ctypes.data) != 0:
+        raise SmartB200Error("sb_prep_automaton: bad argument")
+    return out
 
 
 def textgen_rand_host(sigma: int, off: int, length: int) -> np.ndarray:

@@ -516,6 +516,26 @@ void sb_prep_wfr(const unsigned char *x, int m, int Q, unsigned char *F)
 
 /* ------------------------------------------------------------------ all tables of a family */
 
+/* String-matching automaton of aut.c:26-45 (table built by preSMA, include/AUTOMATON.h:185-198): state q = length of
+ * the longest prefix of x that is a suffix of the text read so far; delta[q*256 + c] = next state, q in [0, m].
+ * From the definition: delta(q, c) = q+1 if q < m and x[q] == c, else delta(border(q), c), delta(0, c) = [c == x[0]];
+ * border(q) = mpNext[q] (mp.c:26-35).  States fit 16 bits (m <= 4200). */
+int sb_prep_automaton(const unsigned char *x, int m, unsigned short *delta)
+{
+    static _Thread_local int border[SB_XSIZE + 1];
+    if (!x || !delta || m < 1 || m > SB_XSIZE) return -2;
+    sb_prep_mp(x, m, border);
+    for (int c = 0; c < SB_SIGMA; c++) delta[c] = 0;
+    delta[x[0]] = 1;
+    for (int q = 1; q <= m; q++) {
+        const unsigned short *fall = delta + (size_t)border[q] * SB_SIGMA;
+        unsigned short *row = delta + (size_t)q * SB_SIGMA;
+        for (int c = 0; c < SB_SIGMA; c++) row[c] = fall[c];
+        if (q < m) row[x[q]] = (unsigned short)(q + 1);
+    }
+    return 0;
+}
+
 int sb_prep_tables(int algo, const unsigned char *x, int m, sb_tables *out)
 {
     const sb_algo_desc *d = sb_algo_desc_get(algo);

@@ -20,6 +20,8 @@
  *   qf<Q><S>     B[1 << (Q*S)] (qf23.c:50-56): the q-gram at every (m-Q+1)-th position and, while bits survive,
  *                every Q-th one before it; surviving alignments are compared (qf23.c:61-82).  B sits in shared
  *                memory up to 8192 entries, else in global memory (L2: 2^16 or 2^18 entries)
+ *   aut          delta[(m+1)*256] (aut.c:26-45, preSMA): state = delta[state][y[j]], occurrence iff state == m; 16-bit
+ *                entries, in shared memory up to m = 94 (47.5 KiB), else read through L1/L2
  *
  * Parallelisation: the scan loops are inherently sequential, so the text is cut into segments of `seg` start
  * positions, one THREAD per segment, each reading m-1 bytes past its segment (the same m-1 halo rule as the shards).
@@ -297,6 +299,34 @@ __global__ void __launch_bounds__(kTableThreads) table_kr_kernel(const __grid_co
                 if (i == a.m) cnt++;
             }
             hy = ((hy - __ldg(a.text + j) * d) << 1) + __ldg(a.text + j + a.m);  // REHASH, kr.c:26,49
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- deterministic automaton: table = delta as 16-bit entries, (m+1) rows of 256 ---- */
+constexpr int kAutSharedRows = 95;  // 95 * 256 * 2 B = 47.5 KiB (+ the reduction scratch) of the 48 KiB static limit
+__global__ void __launch_bounds__(kTableThreads) table_aut_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ unsigned short s_delta[kAutSharedRows * 256];
+    const unsigned short *gdelta = reinterpret_cast<const unsigned short *>(a.table);
+    const bool small = a.m + 1 <= kAutSharedRows;
+    if (small)
+        for (int i = threadIdx.x; i < (a.m + 1) * 256; i += kTableThreads) s_delta[i] = gdelta[i];
+    __syncthreads();
+    const unsigned short *delta = small ? s_delta : gdelta;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        const long long end = own_end + a.m - 1;
+        unsigned state = 0;  // a segment starts like the text does: only occurrences that start at or after lo are seen
+        uint32_t w = 0;
+        for (long long j = lo; j < end; j++) {
+            if ((j & 3) == 0) w = __ldg(reinterpret_cast<const uint32_t *>(a.text + j));
+            state = small ? delta[state * 256 + (w & 0xffu)] : __ldg(delta + state * 256 + (w & 0xffu));  // aut.c:39
+            w >>= 8;
+            cnt += state == (unsigned)a.m;                                                                 // aut.c:40
         }
     }
     table_reduce(a, cnt);

@@ -202,3 +202,26 @@ def test_prep_tables_struct_can_be_reused_across_families():
     assert t.hashQ == 0 and t.wfrQ == 0 and t.kmpNext[0] == -1 and t.m == x.size
     fresh = sb.prep_tables("kmp", x)
     assert list(t.kmpNext[: x.size + 1]) == list(fresh.kmpNext[: x.size + 1]) and list(t.hbc) == list(fresh.hbc)
+
+
+def test_automaton_table_equals_the_reference_builder(oracle):
+    """sb_prep_automaton (from the border table) == the oracle's restatement of preSMA == the reference's own preSMA
+    (include/AUTOMATON.h:185-198, exported by oracle/_ref/aut.so) on random and periodic patterns."""
+    import ctypes as C
+
+    import oracle_lib
+
+    rng = np.random.default_rng(9)
+    ref = oracle_lib.RefAlgo("aut") if oracle_lib.ref_available("aut") else None
+    pats = [np.frombuffer(b"abracadabra", np.uint8), np.frombuffer(b"aaaaaaaa", np.uint8), np.frombuffer(b"a", np.uint8),
+            np.frombuffer(b"abababab" * 20, np.uint8)]
+    pats += [rng.integers(0, s_, m, dtype=np.uint8) for s_ in (2, 4, 256) for m in (1, 2, 7, 33, 300, 4200)]
+    for x in pats:
+        x = np.ascontiguousarray(x)
+        ours = sb.prep_automaton(x).astype(np.int32)
+        want = oracle.table("aut", x)
+        assert np.array_equal(ours, want), x.size
+        if ref is not None and x.size <= 300:
+            t = np.full((x.size + 1) * 256, -1, dtype=np.int32)  # aut.c:33 memset(-1) before preSMA
+            ref.call_pre("preSMA", x.ctypes.data_as(C.c_void_p), C.c_int(x.size), t.ctypes.data_as(C.c_void_p))
+            assert np.array_equal(t.reshape(x.size + 1, 256), want), x.size
