@@ -129,6 +129,40 @@ def test_driver_batch_mode_matches_per_pattern_mode(tmp_path):
     assert sum(1 for x in b if x[1] == "--") == 1  # hash3 at m=2
 
 
+def test_driver_pipeline_mode_matches_per_pattern_mode(tmp_path):
+    """-pipeline: the pattern set of a length goes to the worker in ONE request (SB_REQ_SEARCH_SET) and is searched
+    as independent scans submitted asynchronously (sb_search64_submit / sb_search_collect); same verdicts and
+    occurrence columns as the process-per-search run with the same seed, -1 domains and a second worker included."""
+    data = tmp_path / "data" / "mini"
+    data.mkdir(parents=True)
+    text = open(os.path.join(ROOT, "tests", "golden", "bible64k.bin"), "rb").read()
+    (data / "a.txt").write_bytes(text)
+    (data / "index.txt").write_text("#a.txt#\n")
+    env = {**os.environ, "SMART_B200_SOCK": str(tmp_path / "p.sock")}
+    def args(npat):
+        return [os.path.join(BIN, "smart"), "-text", "mini", "-data", str(tmp_path / "data"), "-pset", str(npat), "-plen", "2",
+                "32", "-short", "-occ", "-seed", "29", "-algo", "bf,kmp,hor,hash3,sbndm2", "-pre"]
+
+    single = run(args(30), cwd=tmp_path, env=env)
+    piped30 = run([*args(30), "-pipeline"], cwd=tmp_path, env=env)
+    piped = run([*args(300), "-pipeline"], cwd=tmp_path, env=env)  # more patterns per set than tickets in flight
+    assert single.returncode == 0 and piped30.returncode == 0 and piped.returncode == 0, (single.stderr, piped.stderr)
+    occ = lambda s: re.findall(r"\] ([\w-]+) \.+\[(\w+|--)\](?:.*?occ (\d+))?", s)
+    a, b, c = occ(single.stdout), occ(piped30.stdout), occ(piped.stdout)
+    assert len(a) == 16 * 5 and a == b, [(x, y) for x, y in zip(a, b) if x != y][:5]
+    assert [x[:2] for x in c] == [x[:2] for x in a] and all(x[1] in ("OK", "--") for x in c)
+    assert sum(1 for x in b if x[1] == "--") == 1  # hash3 at m=2
+    # a worker that is already running is shared, not replaced (smartd exits 7) and not stopped by the second driver
+    started = run([os.path.join(BIN, "smartd")], env=env)
+    assert started.returncode == 0 and "ready" in started.stdout
+    again = run([os.path.join(BIN, "smartd")], env=env)
+    assert again.returncode == 7 and "already running" in again.stderr
+    shared = run([*args(30), "-pipeline"], cwd=tmp_path, env=env)
+    assert "already running (shared" in shared.stdout and occ(shared.stdout) == a
+    assert run([os.path.join(BIN, "smartd"), "-stats"], env=env).returncode == 0  # still alive after the driver left
+    assert run([os.path.join(BIN, "smartd"), "-stop"], env=env).returncode == 0
+
+
 def test_plain_c_client_of_the_abi():
     """tests/c/abi_demo.c: a C program against include/smart_b200.h only (no Python in the loop)."""
     r = run([os.path.join(BIN, "abi_demo")])
