@@ -317,7 +317,7 @@ int main(int argc, char **argv)
                 return 0;
             }
             fprintf(stderr, "smartd: %s\n", k > 0 ? msg : "worker died during start-up");
-            return 3;
+            return (k > 0 && strstr(msg, "already running")) ? 7 : 3; /* 7: a live worker owns the socket (shared) */
         }
         close(report[0]);
         setsid();
