@@ -42,7 +42,7 @@ constexpr int kThreads = 256;       // threads per CTA
 #define SB_MINB 1                   // __launch_bounds__ min CTAs/SM for the streaming kernels (tuning knob)
 #endif
 #ifndef SB_PROBE_ROUNDS
-#define SB_PROBE_ROUNDS 4               // candidate rounds in flight in the slow path of scan_block (tuning knob)
+#define SB_PROBE_ROUNDS 8               // candidate rounds in flight in the slow path of scan_block (tuning knob)
 #endif
 constexpr int kPadBytes = 8192;     // every text buffer is zero padded to a multiple of this plus this much
 constexpr unsigned kFull = 0xffffffffu;
