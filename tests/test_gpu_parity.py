@@ -529,6 +529,16 @@ def test_full_size_properties(oracle, sigma, ms):
             assert whole >= 1
             assert sb.search("hor", t, x).count == whole
             assert sb.search("bf", t4, x).count == whole
+            # every algorithm of section 8(a) and a few of 8(f)-1, asynchronously, on both handles; the byte kernels
+            # alone; and the algorithm's own table-driven scan for the linear-time ones (a 4 GiB pass each)
+            names = ("kmp", "mp", "so", "sa", "bm", "qs", "raita", "tunedbm", "kr", "hash3", "hash5", "hash8", "qf23", "qf44",
+                     "qf63", "smith", "bndm", "br", "skip", "wfr", "sbndm2", "aut", "ebom", "tw")
+            tickets = [(a, tt, sb.submit(a, tt, x)) for a in names for tt in (t, t4)]
+            for a, tt, tk in tickets:
+                assert sb.collect(tk).count == expected(a, m, whole, n), (sigma, m, a)
+            assert sb.search("kmp", t, x, flags=sb.FLAG_NO_PACK | sb.FLAG_NO_SKIP).count == whole
+            for a in ("so", "kmp"):
+                assert sb.search(a, t4, x, flags=sb.FLAG_TABLE_SCAN).count == whole, (sigma, m, a)
             # positions inside the window must be exactly the oracle's
             r = sb.search("bf", t, x, flags=sb.FLAG_POSITIONS, positions_cap=1 << 22)
             if r.count <= (1 << 22):
@@ -660,6 +670,10 @@ def test_64GiB_text_on_one_gpu(oracle):
             x = host_win[777:777 + m].copy()
             whole[m] = (x, sb.search("bf", t, x).count, sb.search("hor", t, x).count)
             assert whole[m][1] >= 1 and whole[m][1] == whole[m][2]
+            tickets = [(a, sb.submit(a, t, x)) for a in ("kmp", "so", "bm", "qs", "hash3", "qf34", "kr", "wfr", "sbndm2", "aut")]
+            for a, tk in tickets:
+                assert sb.collect(tk).count == whole[m][1], (m, a)
+            assert sb.search("so", t, x, flags=sb.FLAG_NO_PACK | sb.FLAG_NO_SKIP).count == whole[m][1]
         x8 = whole[8][0]
         r = sb.search("bf", t, x8, flags=sb.FLAG_POSITIONS, positions_cap=1 << 22)
         assert r.count == whole[8][1] and r.count <= (1 << 22)
