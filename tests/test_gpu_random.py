@@ -47,6 +47,14 @@ def test_random_small_cases(oracle, case):
         assert np.array_equal(r.positions, want)
         for flags in (sb.FLAG_DENSE, sb.FLAG_FILTER_SHIFT if x.size >= 5 else 0, sb.FLAG_NO_SKIP, sb.FLAG_NO_PERIOD):
             assert sb.search("hor", t, x, flags=flags).count == want.size
+        # the algorithms' own table-driven scans (kmpNext, hbc, bmGs, masks, shift tables, QF bits, the automaton)
+        for a in ("kmp", "mp", "hor", "bm", "qs", "raita", "tunedbm", "so", "sa", "kr", "hash3", "hash5", "hash8", "qf23",
+                  "qf34", "qf62", "aut"):
+            assert sb.search(a, t2, x, flags=sb.FLAG_TABLE_SCAN).count == expected(a, x.size, want.size, y.size), (a, x.size)
+        # asynchronous tickets give the same answers as the blocking calls
+        tickets = [sb.submit(a, t, x) for a in ("bf", "bm", "so", "qf23", "wfr", "sbndm2")]
+        assert [sb.collect(tk).count for tk in tickets] == [expected(a, x.size, want.size, y.size)
+                                                             for a in ("bf", "bm", "so", "qf23", "wfr", "sbndm2")]
     assert sb.search_host("bm", x, y).count == want.size
 
 
@@ -115,3 +123,7 @@ def test_random_packed_texts(oracle, case):
         assert sb.search("bf", t, x, flags=sb.FLAG_NO_PACK).count == want.size
         r = sb.search("so", t3, x, flags=sb.FLAG_POSITIONS, positions_cap=want.size + 1)
         assert np.array_equal(r.positions, want)
+        if want.size > 1:  # a short buffer gets the smallest positions, the count stays complete
+            r = sb.search("bf", t, x, flags=sb.FLAG_POSITIONS, positions_cap=want.size // 2)
+            assert r.count == want.size and np.array_equal(r.positions, want[: want.size // 2])
+        assert [r.count for r in sb.search_host_batch([("bf", x), ("hor", x)], y)] == [want.size, want.size]
