@@ -68,7 +68,7 @@ extern "C" {
                                         (kmpNext / mpNext, hbc, Shift-Or/And masks, HASHq shift table - bit-identical to
                                         the reference's; also bmBc+bmGs, qsBc, the Karp-Rabin hash, the QF bit table) is
                                         uploaded, staged in shared memory and drives the scan loop of kmp.c / mp.c / hor.c /
-                                        bm.c / qs.c / raita.c / tunedbm.c / so.c / sa.c / kr.c / hash3,5,8.c / qf*.c / aut.c, one
+                                        bm.c / qs.c / raita.c / tunedbm.c / so.c / sa.c / kr.c / hash3,5,8.c / qf*.c / aut.c / bom.c, one
                                         thread per text segment.
                                         Same counts as every other mode; slower than the default fingerprint filters
                                         (DESIGN.md section 3.4).  Count only; other algorithms ignore the flag. */
@@ -182,7 +182,7 @@ typedef struct sb_timing {
                               KF == m), 541..556 = scan_pswar<2,KF> on the 2-bit recoding,
                               108/116/132 = scan_skip<G>, 204/208/216 = scan_multi<B>, -1 = per-pattern fallback,
                               601 kmp / 602 mp / 603 hor / 604 so / 605 sa / 606 hashq / 607 bm / 608 qs / 609 raita /
-                              610 tunedbm / 611 kr / 612 qf / 613 aut = table-driven scans (SB_FLAG_TABLE_SCAN) */
+                              610 tunedbm / 611 kr / 612 qf / 613 aut / 614 bom = table-driven scans (SB_FLAG_TABLE_SCAN) */
     unsigned long long verified; /* candidates sent to exact verification (all shards) */
 } sb_timing;
 void sb_last_timing(sb_timing *out);
@@ -265,6 +265,10 @@ int sb_prep_tables(int algo, const unsigned char *x, int m, sb_tables *out);
  * for q in [0, m] (entries equal the reference's int table; 16 bits suffice).  delta holds (m+1)*256 entries.
  * Used by SB_FLAG_TABLE_SCAN for `aut`.  Returns 0, or -2 on bad arguments. */
 int sb_prep_automaton(const unsigned char *x, int m, unsigned short *delta);
+/* The factor oracle of bom.c:49-70 as a dense table: trans[p*256 + c] = target state or -1 for p in [0, m] (what
+ * getTransition, bom.c:28-39, answers on the reference's lists), term[p] = 1 for the states on the supply path of
+ * state 0 (bom.c:65-69).  trans holds (m+1)*256 entries, term m+1.  Used by SB_FLAG_TABLE_SCAN for `bom`. */
+int sb_prep_bom(const unsigned char *x, int m, short *trans, unsigned char *term);
 
 #ifdef __cplusplus
 }

@@ -1262,6 +1262,83 @@ static long long ora_search_aut(const unsigned char *x, int m, const unsigned ch
     return count;
 }
 
+/* bom.c:28-70: the factor oracle kept the way the reference keeps it - the "spine" transition p -> p-1 by x[p-1]
+ * is implicit, the other transitions of a state are a list (here: next-pointer arrays, newest first). */
+typedef struct {
+    int head[4202];   /* first external transition of state p, -1 = none */
+    int target[4202]; /* transition k: target state */
+    int next[4202];   /* transition k: next transition of the same state */
+    int ntrans;
+    char term[4202];
+} ora_bom_t;
+
+static int ora_bom_get(const ora_bom_t *o, const unsigned char *x, int p, unsigned char c)
+{
+    if (p > 0 && x[p - 1] == c) return p - 1; /* bom.c:30 */
+    for (int k = o->head[p]; k >= 0; k = o->next[k])
+        if (x[o->target[k]] == c) return o->target[k]; /* bom.c:33-35 */
+    return -1;
+}
+
+static void ora_pre_bom_lists(const unsigned char *x, int m, ora_bom_t *o)
+{
+    static int S[4202];
+    for (int i = 0; i <= m; i++) {
+        o->head[i] = -1;
+        o->term[i] = 0;
+    }
+    o->ntrans = 0;
+    S[m] = m + 1;
+    for (int i = m; i > 0; --i) { /* bom.c:54-63 */
+        const unsigned char c = x[i - 1];
+        int p = S[i], q = -1;
+        while (p <= m && (q = ora_bom_get(o, x, p, c)) == -1) {
+            o->target[o->ntrans] = i - 1;
+            o->next[o->ntrans] = o->head[p];
+            o->head[p] = o->ntrans++;
+            p = S[p];
+        }
+        S[i - 1] = (p == m + 1 ? m : q);
+    }
+    for (int p = 0; p <= m; p = S[p]) o->term[p] = 1; /* bom.c:65-69 */
+}
+
+/* dense view for the table tests: trans[p*256 + c] = getTransition(x, p, L, c), term[p] */
+void ora_pre_bom(const unsigned char *x, int m, short *trans, unsigned char *term)
+{
+    static ora_bom_t o;
+    ora_pre_bom_lists(x, m, &o);
+    for (int p = 0; p <= m; p++) {
+        for (int c = 0; c < 256; c++) trans[p * 256 + c] = (short)ora_bom_get(&o, x, p, (unsigned char)c);
+        term[p] = (unsigned char)o.term[p];
+    }
+}
+
+static long long ora_search_bom(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    static ora_bom_t o;
+    ora_pre_bom_lists(x, m, &o);
+    long long count = 0;
+    long long j = 0;
+    while (j <= (long long)n - m) { /* bom.c:90-106 */
+        int i = m - 1, r = m, shift = m, period = m, q;
+        while (i + j >= 0 && i >= 0 && (q = ora_bom_get(&o, x, r, y[i + j])) != -1) {
+            r = q;
+            if (o.term[r]) {
+                period = shift;
+                shift = i;
+            }
+            --i;
+        }
+        if (i < 0) {
+            count++;
+            shift = period;
+        }
+        j += shift;
+    }
+    return count;
+}
+
 int ora_tier2_count(void) { return (int)(sizeof ora_tier2 / sizeof ora_tier2[0]); }
 const char *ora_tier2_name(int i) { return i >= 0 && i < ora_tier2_count() ? ora_tier2[i].name : NULL; }
 
@@ -1312,6 +1389,7 @@ long long ora_search(const char *algo, const unsigned char *x, int m, const unsi
     if (!strncmp(algo, "skip", 4) && algo[4] >= '3' && algo[4] <= '8' && !algo[5]) return ora_search_skipq(x, m, y, n, algo[4] - '0');
     if (!strcmp(algo, "zt")) return ora_search_zt(x, m, y, n);
     if (!strcmp(algo, "aut")) return ora_search_aut(x, m, y, n);
+    if (!strcmp(algo, "bom")) return (size_t)m > n ? 0 : ora_search_bom(x, m, y, n);
     if (!strcmp(algo, "wfr")) return (size_t)m > n ? 0 : ora_search_wfr(x, m, y, n);
     if (!strncmp(algo, "wfrq", 4) && algo[4] >= '2' && algo[4] <= '8' && !algo[5]) return ora_search_wfrq(x, m, y, n, algo[4] - '0');
     return ora_search_tier2(algo, x, m, y, n);

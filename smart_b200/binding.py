@@ -182,6 +182,7 @@ SYMBOLS = [
                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("sb_prep_tables", C.c_int, [C.c_int, C.c_void_p, C.c_int, C.POINTER(Tables)]),
     ("sb_prep_automaton", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    ("sb_prep_bom", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
 ]
 
 
@@ -467,6 +468,16 @@ def prep_automaton(pattern) -> np.ndarray:
     if lib().sb_prep_automaton(ptr, m, out.ctypes.data) != 0:
         raise SmartB200Error("sb_prep_automaton: bad argument")
     return out
+
+
+def prep_bom(pattern):
+    """sb_prep_bom: (trans, term) of bom.c's factor oracle: (m+1) x 256 int16 (-1 = undefined) and m+1 flags"""
+    ptr, m, keep = _as_bytes_ptr(pattern)
+    trans = np.zeros((m + 1, 256), dtype=np.int16)
+    term = np.zeros(m + 1, dtype=np.uint8)
+    if lib().sb_prep_bom(ptr, m, trans.ctypes.data, term.ctypes.data) != 0:
+        raise SmartB200Error("sb_prep_bom: bad argument")
+    return trans, term
 
 
 def textgen_rand_host(sigma: int, off: int, length: int) -> np.ndarray:

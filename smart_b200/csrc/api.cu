@@ -68,7 +68,7 @@ constexpr int kFilterPswar = 500;             // scan_pswar<BITS,KF>: reported a
 /* scan_pswar covers m <= 30 on a 1-bit copy and m <= 22 on a 2-bit one; beyond, the half-word bitmap kernels are faster */
 constexpr int kPswarMaxM1 = 30, kPswarMaxM2 = 22;
 constexpr size_t kAuxWords = sb::kBloomWords + 2 * sb::kSkipTableSize;
-constexpr size_t kTableInts = (size_t)(SB_XSIZE + 1) * 128 + 64;  // SB_FLAG_TABLE_SCAN: the largest table is aut's (m+1) x 256 x 16 bit (qf: 2^18 ints)
+constexpr size_t kTableInts = (size_t)(SB_XSIZE + 1) * 128 + SB_XSIZE / 4 + 64;  // SB_FLAG_TABLE_SCAN: the largest table is aut's (m+1) x 256 x 16 bit (qf: 2^18 ints)
 
 constexpr int kTickets = 256;                 // outstanding asynchronous searches (sb_search64_submit)
 constexpr int kSyncSlot = kTickets;           // pattern/counter slot of the blocking paths (positions, multi)
@@ -1729,6 +1729,7 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
     case SB_FAM_KR: kind = 611; break;
     case SB_FAM_QF: kind = 612; break;
     case SB_FAM_AUT: kind = 613; break;
+    case SB_FAM_FACTOR: kind = strcmp(desc->name, "bom") == 0 ? 614 : 0; break;
     default: break;
     }
     if (!kind) return -100;
@@ -1774,6 +1775,12 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         sb_prep_automaton(x, m, reinterpret_cast<unsigned short *>(table));
         ntable = ((m + 1) * 256 + 1) / 2;
         break;
+    case 614: {  // (m+1) x 256 16-bit transitions, then m+1 terminal flags
+        short *tr = reinterpret_cast<short *>(table);
+        sb_prep_bom(x, m, tr, reinterpret_cast<unsigned char *>(tr + (size_t)(m + 1) * 256));
+        ntable = ((m + 1) * 256 * 2 + (m + 1) + 3) / 4;
+        break;
+    }
     default:  // qf<Q><S>
         sb_prep_qf(x, m, desc->Q, desc->S, table);
         ntable = 1 << (desc->Q * desc->S);
@@ -1828,6 +1835,7 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         case 610: sb::table_bc_kernel<sb::kBcTuned><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 611: sb::table_kr_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 613: sb::table_aut_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 614: sb::table_bom_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         default: sb::table_qf_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         }
         CU_TRY(cudaGetLastError(), SB_ERR_CUDA);

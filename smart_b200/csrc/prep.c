@@ -536,6 +536,33 @@ int sb_prep_automaton(const unsigned char *x, int m, unsigned short *delta)
     return 0;
 }
 
+/* Factor oracle of bom.c:49-70 (Backward Oracle Matching) as a dense table.  State i (0 <= i <= m) stands for the
+ * suffix x[i..m); the oracle is grown from state m down to 0: state i-1 is entered from i by x[i-1], and every state
+ * on the supply path of i that has no transition by x[i-1] yet gets one to i-1 (the online construction of the
+ * factor oracle, here on the reversed reading direction the backward scan needs).  trans[p*256 + c] = target state or
+ * -1 (bom.c:28-39 getTransition), term[p] = 1 for the states on the supply path of state 0 (bom.c:65-69): reaching
+ * one of them means a prefix of x ends here.  supply[] is scratch of m+2 ints. */
+int sb_prep_bom(const unsigned char *x, int m, short *trans, unsigned char *term)
+{
+    static _Thread_local int supply[SB_XSIZE + 2];
+    if (!x || !trans || !term || m < 1 || m > SB_XSIZE) return -2;
+    for (size_t i = 0; i < (size_t)(m + 1) * SB_SIGMA; i++) trans[i] = -1;
+    for (int i = 0; i <= m; i++) term[i] = 0;
+    supply[m] = m + 1;  /* "no state" */
+    for (int i = m; i > 0; --i) {
+        const unsigned char c = x[i - 1];
+        trans[(size_t)i * SB_SIGMA + c] = (short)(i - 1);
+        int p = supply[i], q = -1;
+        while (p <= m && (q = trans[(size_t)p * SB_SIGMA + c]) < 0) {
+            trans[(size_t)p * SB_SIGMA + c] = (short)(i - 1);
+            p = supply[p];
+        }
+        supply[i - 1] = p == m + 1 ? m : q;
+    }
+    for (int p = 0; p <= m; p = supply[p]) term[p] = 1;
+    return 0;
+}
+
 int sb_prep_tables(int algo, const unsigned char *x, int m, sb_tables *out)
 {
     const sb_algo_desc *d = sb_algo_desc_get(algo);

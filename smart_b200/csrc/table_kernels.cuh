@@ -22,6 +22,9 @@
  *                memory up to 8192 entries, else in global memory (L2: 2^16 or 2^18 entries)
  *   aut          delta[(m+1)*256] (aut.c:26-45, preSMA): state = delta[state][y[j]], occurrence iff state == m; 16-bit
  *                entries, in shared memory up to m = 94 (47.5 KiB), else read through L1/L2
+ *   bom          the factor oracle of the reversed pattern as a dense table trans[(m+1)*256] + terminal flags
+ *                (bom.c:49-70): windows are read right to left through the oracle, the shift is the position of the
+ *                last terminal state seen (bom.c:90-106); shared memory up to m = 93, else L1/L2
  *
  * Parallelisation: the scan loops are inherently sequential, so the text is cut into segments of `seg` start
  * positions, one THREAD per segment, each reading m-1 bytes past its segment (the same m-1 halo rule as the shards).
@@ -327,6 +330,48 @@ __global__ void __launch_bounds__(kTableThreads) table_aut_kernel(const __grid_c
             state = small ? delta[state * 256 + (w & 0xffu)] : __ldg(delta + state * 256 + (w & 0xffu));  // aut.c:39
             w >>= 8;
             cnt += state == (unsigned)a.m;                                                                 // aut.c:40
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Backward Oracle Matching: table = trans as 16-bit entries ((m+1) rows of 256), then m+1 terminal bytes ---- */
+constexpr int kBomSharedRows = 94;
+__global__ void __launch_bounds__(kTableThreads) table_bom_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ short s_trans[kBomSharedRows * 256];
+    __shared__ unsigned char s_term[kBomSharedRows];
+    const int m = a.m;
+    const short *gtrans = reinterpret_cast<const short *>(a.table);
+    const unsigned char *gterm = reinterpret_cast<const unsigned char *>(gtrans + (size_t)(m + 1) * 256);
+    const bool small = m + 1 <= kBomSharedRows;
+    if (small) {
+        for (int i = threadIdx.x; i < (m + 1) * 256; i += kTableThreads) s_trans[i] = gtrans[i];
+        for (int i = threadIdx.x; i <= m; i += kTableThreads) s_term[i] = gterm[i];
+    }
+    __syncthreads();
+    const short *trans = small ? s_trans : gtrans;
+    const unsigned char *term = small ? s_term : gterm;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        long long j = lo;
+        while (j < own_end) {       // bom.c:90-106
+            int i = m - 1, r = m, shift = m, period = m, q;
+            while (i >= 0 && (q = small ? trans[r * 256 + __ldg(a.text + i + j)] : __ldg(trans + r * 256 + __ldg(a.text + i + j))) >= 0) {
+                r = q;
+                if (small ? term[r] : __ldg(term + r)) {
+                    period = shift;
+                    shift = i;
+                }
+                --i;
+            }
+            if (i < 0) {
+                cnt++;
+                shift = period;
+            }
+            j += shift;
         }
     }
     table_reduce(a, cnt);

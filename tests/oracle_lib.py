@@ -126,6 +126,9 @@ class Oracle:
             t = np.zeros(65536, dtype=np.uint8); L.ora_pre_wfr(_ptr(x), m, int(kw.get("Q", 0)), _ptr(t)); return t
         if name == "aut":
             t = ia((m + 1) * 256); L.ora_pre_aut(_ptr(x), m, _ptr(t)); return t.reshape(m + 1, 256)
+        if name == "bom":
+            tr = np.zeros((m + 1) * 256, dtype=np.int16); te = np.zeros(m + 1, dtype=np.uint8)
+            L.ora_pre_bom(_ptr(x), m, _ptr(tr), _ptr(te)); return tr.reshape(m + 1, 256), te
         if name == "qf":
             Q, S = int(kw["Q"]), int(kw["S"])
             t = ia(1 << (Q * S)); L.ora_pre_qf(_ptr(x), m, Q, S, _ptr(t)); return t

@@ -225,3 +225,34 @@ def test_automaton_table_equals_the_reference_builder(oracle):
             t = np.full((x.size + 1) * 256, -1, dtype=np.int32)  # aut.c:33 memset(-1) before preSMA
             ref.call_pre("preSMA", x.ctypes.data_as(C.c_void_p), C.c_int(x.size), t.ctypes.data_as(C.c_void_p))
             assert np.array_equal(t.reshape(x.size + 1, 256), want), x.size
+
+
+def test_bom_factor_oracle_equals_the_reference_builder(oracle):
+    """sb_prep_bom (dense table) == the oracle's list-based restatement == the reference's own oracle() queried through
+    its getTransition() (bom.c:28-70, both exported by oracle/_ref/bom.so), transitions and terminal flags."""
+    import ctypes as C
+
+    import oracle_lib
+
+    rng = np.random.default_rng(19)
+    ref = oracle_lib.RefAlgo("bom") if oracle_lib.ref_available("bom") else None
+    pats = [np.frombuffer(b"abracadabra", np.uint8), np.frombuffer(b"aaaaaaaa", np.uint8), np.frombuffer(b"a", np.uint8),
+            np.frombuffer(b"abababab" * 9, np.uint8), np.frombuffer(b"gcagagag", np.uint8)]
+    pats += [rng.integers(0, s_, m, dtype=np.uint8) for s_ in (2, 4, 256) for m in (1, 2, 7, 33, 200, 4200)]
+    for x in pats:
+        x = np.ascontiguousarray(x)
+        m = x.size
+        trans, term = sb.prep_bom(x)
+        otrans, oterm = oracle.table("bom", x)
+        assert np.array_equal(trans, otrans) and np.array_equal(term, oterm), m
+        if ref is not None and m <= 200:
+            L = (C.c_void_p * 4202)()
+            T = (C.c_char * 4202)()
+            ref.L.oracle.restype = None
+            ref.L.oracle(x.ctypes.data_as(C.c_void_p), C.c_int(m), T, L)
+            ref.L.getTransition.restype = C.c_int
+            for p in range(m + 1):
+                assert (T[p] != b"\x00") == bool(term[p]), (m, p)
+                for c in set(x.tolist()) | {0, 255}:
+                    got = ref.L.getTransition(x.ctypes.data_as(C.c_void_p), C.c_int(p), L, C.c_ubyte(c))
+                    assert got == trans[p, c], (m, p, c)
