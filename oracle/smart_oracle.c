@@ -1339,6 +1339,53 @@ static long long ora_search_bom(const unsigned char *x, int m, const unsigned ch
     return count;
 }
 
+/* ebom.c:28-85: the oracle of bom.c as a dense table (built directly, as ebom.c:38-51 does) plus FT[256][256], the
+ * state after the window's last two characters; m < 2 -> -1 (ebom.c:35).  The pattern copy the reference writes
+ * behind the text (ebom.c:63) is replaced by an explicit bound. */
+static long long ora_search_ebom(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if (m < 2) return -1;
+    if ((size_t)m > n) return 0;
+    static int S[4202];
+    short *trans = malloc((size_t)(m + 2) * 256 * sizeof(short));
+    short *FT = malloc(65536 * sizeof(short));
+    if (!trans || !FT) return -2;
+    for (size_t i = 0; i < (size_t)(m + 2) * 256; i++) trans[i] = -1;
+    S[m] = m + 1;
+    for (int i = m; i > 0; --i) { /* ebom.c:39-51 */
+        const unsigned char c = x[i - 1];
+        trans[i * 256 + c] = (short)(i - 1);
+        int p = S[i], q = -1;
+        while (p <= m && (q = trans[p * 256 + c]) == -1) {
+            trans[p * 256 + c] = (short)(i - 1);
+            p = S[p];
+        }
+        S[i - 1] = (p == m + 1 ? m : q);
+    }
+    for (int a = 0; a < 256; a++) { /* ebom.c:54-59 */
+        const int q = trans[m * 256 + a];
+        for (int b = 0; b < 256; b++) FT[a * 256 + b] = q >= 0 ? trans[q * 256 + b] : (short)-1;
+    }
+    long long count = memcmp(x, y, (size_t)m) == 0; /* ebom.c:64 */
+    long long j = m;
+    const long long nn = (long long)n;
+    while (j < nn) { /* ebom.c:67-77 */
+        int p;
+        while (j < nn && (p = FT[y[j] * 256 + y[j - 1]]) == -1) j += m - 1;
+        if (j >= nn) break;
+        long long i = j - 2;
+        while (i >= 0 && (p = trans[p * 256 + y[i]]) != -1) i--;
+        if (i < j - (m - 1)) {
+            count++;
+            i++;
+        }
+        j = i + m;
+    }
+    free(trans);
+    free(FT);
+    return count;
+}
+
 int ora_tier2_count(void) { return (int)(sizeof ora_tier2 / sizeof ora_tier2[0]); }
 const char *ora_tier2_name(int i) { return i >= 0 && i < ora_tier2_count() ? ora_tier2[i].name : NULL; }
 
@@ -1390,6 +1437,7 @@ long long ora_search(const char *algo, const unsigned char *x, int m, const unsi
     if (!strcmp(algo, "zt")) return ora_search_zt(x, m, y, n);
     if (!strcmp(algo, "aut")) return ora_search_aut(x, m, y, n);
     if (!strcmp(algo, "bom")) return (size_t)m > n ? 0 : ora_search_bom(x, m, y, n);
+    if (!strcmp(algo, "ebom")) return ora_search_ebom(x, m, y, n);
     if (!strcmp(algo, "wfr")) return (size_t)m > n ? 0 : ora_search_wfr(x, m, y, n);
     if (!strncmp(algo, "wfrq", 4) && algo[4] >= '2' && algo[4] <= '8' && !algo[5]) return ora_search_wfrq(x, m, y, n, algo[4] - '0');
     return ora_search_tier2(algo, x, m, y, n);

@@ -68,7 +68,7 @@ constexpr int kFilterPswar = 500;             // scan_pswar<BITS,KF>: reported a
 /* scan_pswar covers m <= 30 on a 1-bit copy and m <= 22 on a 2-bit one; beyond, the half-word bitmap kernels are faster */
 constexpr int kPswarMaxM1 = 30, kPswarMaxM2 = 22;
 constexpr size_t kAuxWords = sb::kBloomWords + 2 * sb::kSkipTableSize;
-constexpr size_t kTableInts = (size_t)(SB_XSIZE + 1) * 128 + SB_XSIZE / 4 + 64;  // SB_FLAG_TABLE_SCAN: the largest table is aut's (m+1) x 256 x 16 bit (qf: 2^18 ints)
+constexpr size_t kTableInts = (size_t)(SB_XSIZE + 1) * 128 + SB_XSIZE / 4 + 64 + 32768;  // (+ ebom's FT)  // SB_FLAG_TABLE_SCAN: the largest table is aut's (m+1) x 256 x 16 bit (qf: 2^18 ints)
 
 constexpr int kTickets = 256;                 // outstanding asynchronous searches (sb_search64_submit)
 constexpr int kSyncSlot = kTickets;           // pattern/counter slot of the blocking paths (positions, multi)
@@ -1729,7 +1729,7 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
     case SB_FAM_KR: kind = 611; break;
     case SB_FAM_QF: kind = 612; break;
     case SB_FAM_AUT: kind = 613; break;
-    case SB_FAM_FACTOR: kind = strcmp(desc->name, "bom") == 0 ? 614 : 0; break;
+    case SB_FAM_FACTOR: kind = strcmp(desc->name, "bom") == 0 ? 614 : strcmp(desc->name, "ebom") == 0 ? 615 : 0; break;
     default: break;
     }
     if (!kind) return -100;
@@ -1779,6 +1779,19 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         short *tr = reinterpret_cast<short *>(table);
         sb_prep_bom(x, m, tr, reinterpret_cast<unsigned char *>(tr + (size_t)(m + 1) * 256));
         ntable = ((m + 1) * 256 * 2 + (m + 1) + 3) / 4;
+        break;
+    }
+    case 615: {  // the oracle of bom, then FT[256][256] (ebom.c:54-59)
+        short *tr = reinterpret_cast<short *>(table);
+        sb_prep_bom(x, m, tr, reinterpret_cast<unsigned char *>(tr + (size_t)(m + 1) * 256));
+        const size_t ft_off = (((size_t)(m + 1) * 256 * 2 + (m + 1) + 3) / 4) * 2;  // in shorts, 4-byte aligned
+        short *FT = tr + ft_off;
+        for (int c1 = 0; c1 < 256; c1++) {
+            const int q = tr[(size_t)m * 256 + c1];
+            for (int c2 = 0; c2 < 256; c2++) FT[c1 * 256 + c2] = q >= 0 ? tr[(size_t)q * 256 + c2] : (short)-1;
+        }
+        lim = (unsigned)ft_off;
+        ntable = (int)(ft_off / 2 + 32768);
         break;
     }
     default:  // qf<Q><S>
@@ -1836,6 +1849,7 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         case 611: sb::table_kr_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 613: sb::table_aut_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 614: sb::table_bom_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 615: sb::table_ebom_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         default: sb::table_qf_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         }
         CU_TRY(cudaGetLastError(), SB_ERR_CUDA);

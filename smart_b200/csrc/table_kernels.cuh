@@ -25,6 +25,9 @@
  *   bom          the factor oracle of the reversed pattern as a dense table trans[(m+1)*256] + terminal flags
  *                (bom.c:49-70): windows are read right to left through the oracle, the shift is the position of the
  *                last terminal state seen (bom.c:90-106); shared memory up to m = 93, else L1/L2
+ *   ebom         the same oracle + the first-transition table FT[256][256] = state after the window's last two
+ *                characters (ebom.c:54-59): windows without a defined FT entry are skipped m-1 at a time (ebom.c:68);
+ *                the oracle rows through L1/L2, FT (128 KiB) likewise
  *
  * Parallelisation: the scan loops are inherently sequential, so the text is cut into segments of `seg` start
  * positions, one THREAD per segment, each reading m-1 bytes past its segment (the same m-1 halo rule as the shards).
@@ -372,6 +375,45 @@ __global__ void __launch_bounds__(kTableThreads) table_bom_kernel(const __grid_c
                 shift = period;
             }
             j += shift;
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Extended BOM: table = trans ((m+1) x 256 x 16 bit), m+1 terminal bytes (unused), padding to 4 bytes, then
+ *      FT[256][256] as 16-bit entries (FT[a][b] = trans[trans[m][a]][b], ebom.c:54-59); a.lim = offset of FT in shorts ---- */
+__global__ void __launch_bounds__(kTableThreads) table_ebom_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    stage_pattern_smem(s_x, a);
+    __syncthreads();
+    const int m = a.m;
+    const short *trans = reinterpret_cast<const short *>(a.table);
+    const short *FT = trans + a.lim;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        {   // ebom.c:64: the first window of the segment is compared directly
+            int i = 0;
+            while (i < m && s_x[i] == __ldg(a.text + lo + i)) i++;
+            cnt += i == m;
+        }
+        long long j = lo + m;  // index of the window's last character (ebom.c:65)
+        while (j - m + 1 < own_end) {
+            int p;
+            while ((p = __ldg(FT + __ldg(a.text + j) * 256 + __ldg(a.text + j - 1))) < 0) {  // ebom.c:68
+                j += m - 1;
+                if (j - m + 1 >= own_end) break;  // (the reference stops on the pattern copy it writes behind the text)
+            }
+            if (j - m + 1 >= own_end) break;
+            long long i = j - 2;
+            while (i >= j - m && (p = __ldg(trans + p * 256 + __ldg(a.text + i))) >= 0) i--;  // ebom.c:71 (never past the
+            if (i < j - (m - 1)) {                                                                // window: state 0 has no exits)
+                cnt++;   // ebom.c:72-75
+                i++;
+            }
+            j = i + m;
         }
     }
     table_reduce(a, cnt);

@@ -39,7 +39,7 @@ def main():
                     r = sb.search("bm", t3, x, flags=sb.FLAG_POSITIONS, positions_cap=want.size + 1)
                     assert np.array_equal(r.positions, want), (name, m, k)
                     if m <= 300 or name in ("s256", "s4"):
-                        for a in ("kmp", "so", "hor", "bm", "qs", "raita", "tunedbm", "kr", "hash3", "qf34", "aut", "bom"):
+                        for a in ("kmp", "so", "hor", "bm", "qs", "raita", "tunedbm", "kr", "hash3", "qf34", "aut", "bom", "ebom"):
                             if sb.applicable(a, m):
                                 assert sb.search(a, t, x, flags=sb.FLAG_TABLE_SCAN).count == want.size, (name, m, a)
                     x2 = x.copy()
