@@ -1386,6 +1386,42 @@ static long long ora_search_ebom(const unsigned char *x, int m, const unsigned c
     return count;
 }
 
+/* sbndm2.c:27-71 for m <= 32 (its search_large for longer patterns is not restated: it is wrong).
+ * m < 2 -> -1 (sbndm2.c:30).  Returns -3 for m > 32. */
+static long long ora_search_sbndm2(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if (m < 2) return -1;
+    if (m > 32) return -3;
+    if ((size_t)m > n) return 0;
+    unsigned B[256], D;
+    for (int i = 0; i < 256; i++) B[i] = 0;
+    for (int i = 1; i <= m; ++i) B[x[m - i]] |= 1u << (i - 1); /* sbndm2.c:38 */
+    int shift = 0, jj = 1;
+    D = B[x[m - 2]]; /* sbndm2.c:40-47 */
+    if (D & (1u << (m - 1))) shift = m - jj;
+    for (int i = m - 3; i >= 0; i--) {
+        D = (D << 1) & B[x[i]];
+        jj++;
+        if (D & (1u << (m - 1))) shift = m - jj;
+    }
+    long long count = memcmp(x, y, (size_t)m) == 0;
+    long long j = m;
+    while (j < (long long)n) { /* sbndm2.c:53-67 */
+        D = (B[y[j]] << 1) & B[y[j - 1]];
+        if (D != 0) {
+            const long long pos = j;
+            while ((D = (D << 1) & B[y[j - 2]]) != 0) --j;
+            j += m - 2;
+            if (j == pos) {
+                count++;
+                j += shift;
+            }
+        } else
+            j += m - 1;
+    }
+    return count;
+}
+
 int ora_tier2_count(void) { return (int)(sizeof ora_tier2 / sizeof ora_tier2[0]); }
 const char *ora_tier2_name(int i) { return i >= 0 && i < ora_tier2_count() ? ora_tier2[i].name : NULL; }
 
@@ -1438,6 +1474,7 @@ long long ora_search(const char *algo, const unsigned char *x, int m, const unsi
     if (!strcmp(algo, "aut")) return ora_search_aut(x, m, y, n);
     if (!strcmp(algo, "bom")) return (size_t)m > n ? 0 : ora_search_bom(x, m, y, n);
     if (!strcmp(algo, "ebom")) return ora_search_ebom(x, m, y, n);
+    if (!strcmp(algo, "sbndm2")) return ora_search_sbndm2(x, m, y, n);
     if (!strcmp(algo, "wfr")) return (size_t)m > n ? 0 : ora_search_wfr(x, m, y, n);
     if (!strncmp(algo, "wfrq", 4) && algo[4] >= '2' && algo[4] <= '8' && !algo[5]) return ora_search_wfrq(x, m, y, n, algo[4] - '0');
     return ora_search_tier2(algo, x, m, y, n);

@@ -1729,6 +1729,7 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
     case SB_FAM_KR: kind = 611; break;
     case SB_FAM_QF: kind = 612; break;
     case SB_FAM_AUT: kind = 613; break;
+    case SB_FAM_BNDMX: kind = (strcmp(desc->name, "sbndm2") == 0 && m <= SB_WORD) ? 616 : 0; break;  // (m > 32: the default mode)
     case SB_FAM_FACTOR: kind = strcmp(desc->name, "bom") == 0 ? 614 : strcmp(desc->name, "ebom") == 0 ? 615 : 0; break;
     default: break;
     }
@@ -1794,6 +1795,7 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         ntable = (int)(ft_off / 2 + 32768);
         break;
     }
+    case 616: sb_prep_sbndm2(x, m, reinterpret_cast<unsigned int *>(table), &sh1); break;
     default:  // qf<Q><S>
         sb_prep_qf(x, m, desc->Q, desc->S, table);
         ntable = 1 << (desc->Q * desc->S);
@@ -1850,6 +1852,7 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         case 613: sb::table_aut_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 614: sb::table_bom_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 615: sb::table_ebom_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 616: sb::table_sbndm2_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         default: sb::table_qf_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         }
         CU_TRY(cudaGetLastError(), SB_ERR_CUDA);

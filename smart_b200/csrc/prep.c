@@ -563,6 +563,21 @@ int sb_prep_bom(const unsigned char *x, int m, short *trans, unsigned char *term
     return 0;
 }
 
+/* sbndm2.c:33-47 (m <= 32): B[c] has bit b set iff x[m-1-b] == c (the pattern read right to left), and the shift
+ * after an occurrence, m - j for the longest j <= m-1 such that the j characters before the last one, x[m-1-j .. m-2],
+ * are a prefix of x.  (j = m-1 always qualifies - x[0 .. m-2] is a prefix of x - so the reference's shift is 1.) */
+int sb_prep_sbndm2(const unsigned char *x, int m, unsigned int *B, int *shift)
+{
+    if (!x || !B || !shift || m < 2 || m > SB_WORD) return -2;
+    for (int c = 0; c < SB_SIGMA; c++) B[c] = 0;
+    for (int b = 0; b < m; b++) B[x[m - 1 - b]] |= 1u << b;
+    int best = 0;
+    for (int j = 1; j <= m - 1; j++)
+        if (memcmp(x + (m - 1 - j), x, (size_t)j) == 0) best = j;
+    *shift = best ? m - best : 0;
+    return 0;
+}
+
 int sb_prep_tables(int algo, const unsigned char *x, int m, sb_tables *out)
 {
     const sb_algo_desc *d = sb_algo_desc_get(algo);

@@ -28,6 +28,9 @@
  *   ebom         the same oracle + the first-transition table FT[256][256] = state after the window's last two
  *                characters (ebom.c:54-59): windows without a defined FT entry are skipped m-1 at a time (ebom.c:68);
  *                the oracle rows through L1/L2, FT (128 KiB) likewise
+ *   sbndm2       (m <= 32; the reference's default selection, algorithms.h:133) B[256] = the pattern's positions per
+ *                character, read right to left; D = (B[y[j]] << 1) & B[y[j-1]] on the window's last two characters,
+ *                then one more character per step while D != 0 (sbndm2.c:52-66)
  *
  * Parallelisation: the scan loops are inherently sequential, so the text is cut into segments of `seg` start
  * positions, one THREAD per segment, each reading m-1 bytes past its segment (the same m-1 halo rule as the shards).
@@ -414,6 +417,43 @@ __global__ void __launch_bounds__(kTableThreads) table_ebom_kernel(const __grid_
                 i++;
             }
             j = i + m;
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- SBNDM2 (m <= 32): table = B[256]; a.sh1 = the shift after an occurrence ---- */
+__global__ void __launch_bounds__(kTableThreads) table_sbndm2_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ unsigned s_B[256];
+    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_B[i] = (unsigned)a.table[i];
+    stage_pattern_smem(s_x, a);
+    __syncthreads();
+    const int m = a.m;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        {   // sbndm2.c:51: the first window is compared directly
+            int i = 0;
+            while (i < m && s_x[i] == __ldg(a.text + lo + i)) i++;
+            cnt += i == m;
+        }
+        long long j = lo + m;  // index of the window's last character
+        while (j - m + 1 < own_end) {
+            unsigned D = (s_B[__ldg(a.text + j)] << 1) & s_B[__ldg(a.text + j - 1)];  // sbndm2.c:54
+            if (D != 0) {
+                const long long pos = j;
+                while ((D = (D << 1) & s_B[__ldg(a.text + j - 2)]) != 0) --j;           // sbndm2.c:57-58
+                j += m - 2;
+                if (j == pos) {                                                         // sbndm2.c:60-63
+                    cnt++;
+                    j += a.sh1;
+                }
+            } else {
+                j += m - 1;                                                             // sbndm2.c:65
+            }
         }
     }
     table_reduce(a, cnt);

@@ -108,7 +108,7 @@ def test_table_driven_scans_match_the_reference(oracle, golden, tname):
                 assert sb.search("hor", t3, x, flags=sb.FLAG_TABLE_SCAN).count == ref["hor"]
             # an algorithm without a table-driven kernel ignores the flag
             assert sb.search("smith", t, x, flags=sb.FLAG_TABLE_SCAN).count == ref["smith"]
-            assert sb.last_timing().filter_kind not in range(601, 616)
+            assert sb.last_timing().filter_kind not in range(601, 617)
 
 
 def test_table_driven_scans_segment_seams(oracle):
@@ -166,6 +166,12 @@ def test_sbndm2_the_reference_default_selection(oracle, golden):
                     if c["m"] <= 32:
                         assert r == got, (tname, c["m"], c["pi"], r, got)
                     diverged += r != got  # m > 32: search_large (sbndm2.c:77) misses or invents occurrences
+            # the table-driven sbndm2 kernel (m <= 32): B[256] in shared memory, the loop of sbndm2.c:52-66
+            for c in (c for c in golden["cases"] if c["text"] == tname and 2 <= c["m"] <= 32):
+                x = make_patterns(tname, y, c["m"])[c["pi"]]
+                assert sb.search("sbndm2", t, x, flags=sb.FLAG_TABLE_SCAN).count == c["ref"][0], (tname, c["m"], c["pi"])
+                assert sb.last_timing().filter_kind == 616
+                assert oracle.search("sbndm2", x, y) == c["ref"][0]
     if ref is not None:
         a = np.full(65536, ord("a"), dtype=np.uint8)
         with sb.Text.upload(a) as t:
