@@ -1729,6 +1729,11 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
     case SB_FAM_KR: kind = 611; break;
     case SB_FAM_QF: kind = 612; break;
     case SB_FAM_AUT: kind = 613; break;
+    case SB_FAM_BNDM: kind = 617; break;
+    case SB_FAM_BR: kind = strcmp(desc->name, "br") == 0 ? 618 : strcmp(desc->name, "tvsbs") == 0 ? 619 : 0; break;
+    case SB_FAM_SMITH: kind = 620; break;
+    case SB_FAM_SKIP: kind = 621; break;
+    case SB_FAM_FJS: kind = 622; break;
     case SB_FAM_BNDMX: kind = (strcmp(desc->name, "sbndm2") == 0 && m <= SB_WORD) ? 616 : 0; break;  // (m > 32: the default mode)
     case SB_FAM_FACTOR: kind = strcmp(desc->name, "bom") == 0 ? 614 : strcmp(desc->name, "ebom") == 0 ? 615 : 0; break;
     default: break;
@@ -1796,6 +1801,27 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         break;
     }
     case 616: sb_prep_sbndm2(x, m, reinterpret_cast<unsigned int *>(table), &sh1); break;
+    case 617: sb_prep_bndm(x, m, reinterpret_cast<unsigned int *>(table)); break;
+    case 618:
+    case 619:
+        sb_prep_brbc(x, m, table);
+        ntable = 65536;
+        break;
+    case 620:
+        sb_prep_hbc(x, m, table);
+        sb_prep_qsbc(x, m, table + 256);
+        ntable = 512;
+        break;
+    case 621:
+        sb_prep_buckets(x, m, table, table + 256);
+        ntable = 256 + m;
+        break;
+    case 622:
+        sb_prep_qsbc(x, m, table);
+        sb_prep_mp(x, m, scratch);
+        sb_prep_kmp(x, m, scratch, table + 256);
+        ntable = 256 + m + 1;
+        break;
     default:  // qf<Q><S>
         sb_prep_qf(x, m, desc->Q, desc->S, table);
         ntable = 1 << (desc->Q * desc->S);
@@ -1853,6 +1879,12 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         case 614: sb::table_bom_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 615: sb::table_ebom_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 616: sb::table_sbndm2_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 617: sb::table_bndm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 618: sb::table_br_kernel<false><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 619: sb::table_br_kernel<true><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 620: sb::table_smith_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 621: sb::table_skip_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 622: sb::table_fjs_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         default: sb::table_qf_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         }
         CU_TRY(cudaGetLastError(), SB_ERR_CUDA);

@@ -31,6 +31,15 @@
  *   sbndm2       (m <= 32; the reference's default selection, algorithms.h:133) B[256] = the pattern's positions per
  *                character, read right to left; D = (B[y[j]] << 1) & B[y[j-1]] on the window's last two characters,
  *                then one more character per step while D != 0 (sbndm2.c:52-66)
+ *   bndm         B[256] (bndm.c:33-38; the 32-character prefix for m > 32): the window is read right to left through
+ *                the bit-parallel suffix automaton, `last` = the longest window suffix that is a pattern prefix
+ *                (bndm.c:44-58); m > 32: search_large's prefix automaton + comparison of the rest (bndm.c:62-110)
+ *   br / tvsbs   brBc[256][256] (br.c:26-37): compare (tvsbs: last and first character first, tvsbs.c:50-56), then
+ *                j += brBc[y[j+m]][y[j+m+1]] (br.c:58); the 256 KiB table is read through L1/L2
+ *   smith        bmBc[256] + qsBc[256] (smith.c:41-63): j += MAX(bmBc[y[j+m-1]], qsBc[y[j+m]])
+ *   skip         z[256] + list[m] (skip.c:31-39): every m-th text character selects the alignments to compare
+ *   fjs          qsBc[256] + kmpNext[0..m] (fjs.c:47-73): Sunday shifts until the last character matches, then a
+ *                left-to-right compare and a KMP shift
  *
  * Parallelisation: the scan loops are inherently sequential, so the text is cut into segments of `seg` start
  * positions, one THREAD per segment, each reading m-1 bytes past its segment (the same m-1 halo rule as the shards).
@@ -454,6 +463,155 @@ __global__ void __launch_bounds__(kTableThreads) table_sbndm2_kernel(const __gri
             } else {
                 j += m - 1;                                                             // sbndm2.c:65
             }
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- BNDM: table = B[256] over the first min(m,32) characters, reversed ---- */
+__global__ void __launch_bounds__(kTableThreads) table_bndm_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ unsigned s_B[256];
+    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_B[i] = (unsigned)a.table[i];
+    stage_pattern_smem(s_x, a);
+    __syncthreads();
+    const int m = a.m, w = m < SB_WORD ? m : SB_WORD;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        long long j = lo;
+        while (j < own_end) {  // bndm.c:44-58
+            int i = w - 1, last = w;
+            unsigned D = ~0u;
+            while (i >= 0 && D != 0) {
+                D &= s_B[__ldg(a.text + j + i)];
+                i--;
+                if (D != 0) {
+                    if (i >= 0) {
+                        last = i + 1;
+                    } else {  // the (prefix of the) pattern matched: bndm.c:52 / search_large :97-101
+                        int k = w;
+                        while (k < m && s_x[k] == __ldg(a.text + j + k)) k++;
+                        cnt += k == m;
+                    }
+                }
+                D <<= 1;
+            }
+            j += last;
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Berry-Ravindran (TVSBS = false) / TVSBS (true): table = brBc[256*256] ---- */
+template <bool TVSBS>
+__global__ void __launch_bounds__(kTableThreads) table_br_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    stage_pattern_smem(s_x, a);
+    __syncthreads();
+    const int m = a.m;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        long long j = lo;
+        while (j < own_end) {
+            if (!TVSBS) {  // br.c:54-56
+                int i = 0;
+                while (i < m && s_x[i] == __ldg(a.text + j + i)) i++;
+                cnt += i >= m;
+            } else if (s_x[m - 1] == __ldg(a.text + j + m - 1) && s_x[0] == __ldg(a.text + j)) {  // tvsbs.c:50-56
+                int i = m - 2;
+                while (i > 0 && s_x[i] == __ldg(a.text + j + i)) i--;
+                cnt += i <= 0;
+            }
+            // the two characters after the window (behind the text they read as 0, like the driver's NUL bytes)
+            j += __ldg(a.table + __ldg(a.text + j + m) * 256 + __ldg(a.text + j + m + 1));  // br.c:58
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Smith: table = bmBc[256] then qsBc[256] ---- */
+__global__ void __launch_bounds__(kTableThreads) table_smith_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ int s_bc[512];
+    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 512; i += kTableThreads) s_bc[i] = a.table[i];
+    stage_pattern_smem(s_x, a);
+    __syncthreads();
+    const int m = a.m;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        long long j = lo;
+        while (j < own_end) {  // smith.c:54-60
+            int i = 0;
+            while (i < m && s_x[i] == __ldg(a.text + j + i)) i++;
+            cnt += i == m;
+            const int b1 = s_bc[__ldg(a.text + j + m - 1)], b2 = s_bc[256 + __ldg(a.text + j + m)];
+            j += b1 > b2 ? b1 : b2;
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Skip Search: table = z[256] then list[m] ---- */
+__global__ void __launch_bounds__(kTableThreads) table_skip_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ int s_z[256];
+    __shared__ int s_list[SB_XSIZE];
+    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_z[i] = a.table[i];
+    for (int i = threadIdx.x; i < a.m; i += kTableThreads) s_list[i] = a.table[256 + i];
+    stage_pattern_smem(s_x, a);
+    __syncthreads();
+    const int m = a.m;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        // skip.c:44-49: one text character out of m; an occurrence that starts in [lo, own_end) contains exactly one
+        // of the sample points lo+m-1, lo+2m-1, ...
+        for (long long j = lo + m - 1; j - (m - 1) < own_end; j += m)
+            for (int e = s_z[__ldg(a.text + j)]; e >= 0; e = s_list[e]) {
+                const long long st = j - e;
+                if (st < lo || st >= own_end) continue;
+                int i = 0;
+                while (i < m && s_x[i] == __ldg(a.text + st + i)) i++;
+                cnt += i == m;
+            }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Franek-Jennings-Smyth: table = qsBc[256] then kmpNext[0..m] ---- */
+__global__ void __launch_bounds__(kTableThreads) table_fjs_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ int s_qs[256];
+    __shared__ int s_next[SB_XSIZE + 1];
+    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_qs[i] = a.table[i];
+    for (int i = threadIdx.x; i <= a.m; i += kTableThreads) s_next[i] = a.table[256 + i];
+    stage_pattern_smem(s_x, a);
+    __syncthreads();
+    const int m = a.m;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        long long s = lo;
+        while (s < own_end) {  // fjs.c:57-70
+            while (s < own_end && s_x[m - 1] != __ldg(a.text + s + m - 1)) s += s_qs[__ldg(a.text + s + m)];
+            if (s >= own_end) break;
+            int i = 0;
+            while (i < m && s_x[i] == __ldg(a.text + s + i)) i++;
+            cnt += i >= m;
+            s += i - s_next[i];
         }
     }
     table_reduce(a, cnt);
