@@ -68,7 +68,7 @@ extern "C" {
                                         (kmpNext / mpNext, hbc, Shift-Or/And masks, HASHq shift table - bit-identical to
                                         the reference's; also bmBc+bmGs, qsBc, the Karp-Rabin hash, the QF bit table) is
                                         uploaded, staged in shared memory and drives the scan loop of kmp.c / mp.c / hor.c /
-                                        bm.c / qs.c / raita.c / tunedbm.c / so.c / sa.c / kr.c / hash3,5,8.c / qf*.c / aut.c / bom.c / ebom.c / sbndm2.c (m <= 32) / bndm.c / br.c / tvsbs.c / smith.c / skip.c / fjs.c, one
+                                        bm.c / qs.c / raita.c / tunedbm.c / so.c / sa.c / kr.c / hash3,5,8.c / qf*.c / aut.c / bom.c / ebom.c / sbndm2.c (m <= 32) / bndm.c / br.c / tvsbs.c / smith.c / skip.c / fjs.c / ssabs.c / fs.c / graspm.c / tbm.c / ac.c, one
                                         thread per text segment.
                                         Same counts as every other mode; slower than the default fingerprint filters
                                         (DESIGN.md section 3.4).  Count only; other algorithms ignore the flag. */
@@ -182,7 +182,7 @@ typedef struct sb_timing {
                               KF == m), 541..556 = scan_pswar<2,KF> on the 2-bit recoding,
                               108/116/132 = scan_skip<G>, 204/208/216 = scan_multi<B>, -1 = per-pattern fallback,
                               601 kmp / 602 mp / 603 hor / 604 so / 605 sa / 606 hashq / 607 bm / 608 qs / 609 raita /
-                              610 tunedbm / 611 kr / 612 qf / 613 aut / 614 bom / 615 ebom / 616 sbndm2 (m <= 32) / 617 bndm / 618 br / 619 tvsbs / 620 smith / 621 skip / 622 fjs = table-driven scans (SB_FLAG_TABLE_SCAN) */
+                              610 tunedbm / 611 kr / 612 qf / 613 aut / 614 bom / 615 ebom / 616 sbndm2 (m <= 32) / 617 bndm / 618 br / 619 tvsbs / 620 smith / 621 skip / 622 fjs / 623 ssabs / 624 fs / 625 graspm / 626 tbm / 627 ac = table-driven scans (SB_FLAG_TABLE_SCAN) */
     unsigned long long verified; /* candidates sent to exact verification (all shards) */
 } sb_timing;
 void sb_last_timing(sb_timing *out);

@@ -1723,7 +1723,11 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
     case SB_FAM_SA: kind = 605; break;
     case SB_FAM_HASHQ: kind = 606; break;
     case SB_FAM_BM: kind = 607; break;
-    case SB_FAM_QS: kind = strcmp(desc->name, "qs") == 0 ? 608 : 0; break;  // (ssabs shares the family, not the loop)
+    case SB_FAM_QS: kind = strcmp(desc->name, "qs") == 0 ? 608 : strcmp(desc->name, "ssabs") == 0 ? 623 : 0; break;
+    case SB_FAM_FS: kind = 624; break;
+    case SB_FAM_GRASPM: kind = 625; break;
+    case SB_FAM_TBM: kind = 626; break;
+    case SB_FAM_AC: kind = 627; break;
     case SB_FAM_RAITA: kind = 609; break;
     case SB_FAM_TUNEDBM: kind = 610; break;
     case SB_FAM_KR: kind = 611; break;
@@ -1802,6 +1806,31 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
     }
     case 616: sb_prep_sbndm2(x, m, reinterpret_cast<unsigned int *>(table), &sh1); break;
     case 617: sb_prep_bndm(x, m, reinterpret_cast<unsigned int *>(table)); break;
+    case 623: sb_prep_qsbc(x, m, table); break;
+    case 624:
+        sb_prep_lastocc(x, m, table);
+        sb_prep_fsgs(x, m, table + 256);
+        ntable = 256 + m + 1;
+        break;
+    case 625:
+        sb_prep_lastocc(x, m, table);
+        sb_prep_graspm(x, m, table + 256, table + 512);
+        ntable = 512 + m + 1;
+        break;
+    case 626:
+        sb_prep_hbc(x, m, table);
+        sb_prep_bmgs(x, m, scratch, table + 256);
+        ntable = 256 + m;
+        break;
+    case 627: {
+        sb_prep_mp(x, m, scratch);
+        sb_prep_kmp(x, m, scratch, table);
+        ntable = m + 1;
+        int ell = 1;  // ac.c:52-53: the leading run of x[0], 0 when the pattern is one run
+        while (ell < m && x[ell] == x[0]) ell++;
+        qq = ell == m ? 0 : ell;
+        break;
+    }
     case 618:
     case 619:
         sb_prep_brbc(x, m, table);
@@ -1885,6 +1914,11 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         case 620: sb::table_smith_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 621: sb::table_skip_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 622: sb::table_fjs_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 623: sb::table_ssabs_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 624: sb::table_fs_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 625: sb::table_graspm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 626: sb::table_tbm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 627: sb::table_ac_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         default: sb::table_qf_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         }
         CU_TRY(cudaGetLastError(), SB_ERR_CUDA);

@@ -40,6 +40,12 @@
  *   skip         z[256] + list[m] (skip.c:31-39): every m-th text character selects the alignments to compare
  *   fjs          qsBc[256] + kmpNext[0..m] (fjs.c:47-73): Sunday shifts until the last character matches, then a
  *                left-to-right compare and a KMP shift
+ *   ssabs        qsBc[256] (ssabs.c:35-58): last and first character, the inside backwards, then j += qsBc[y[j+m]]
+ *   fs           bc[256] over all m characters + Pre_GS (fs.c:26-51): skip until bc == 0, compare backwards, shift gs
+ *   graspm       bc[256] + candidate lists keyed by the character before (graspm.c:37-70)
+ *   tbm          bmBc[256] + bmGs[0..m) (tbm.c:66-111): Turbo-BM, the factor matched by the previous attempt is
+ *                remembered (u) and jumped over; a segment starts with u = 0 like the text does
+ *   ac           kmpNext[0..m] + ell (ac.c:44-86): Apostolico-Crochemore
  *
  * Parallelisation: the scan loops are inherently sequential, so the text is cut into segments of `seg` start
  * positions, one THREAD per segment, each reading m-1 bytes past its segment (the same m-1 halo rule as the shards).
@@ -612,6 +618,179 @@ __global__ void __launch_bounds__(kTableThreads) table_fjs_kernel(const __grid_c
             while (i < m && s_x[i] == __ldg(a.text + s + i)) i++;
             cnt += i >= m;
             s += i - s_next[i];
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- SSABS: table = qsBc[256] ---- */
+__global__ void __launch_bounds__(kTableThreads) table_ssabs_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ int s_qs[256];
+    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_qs[i] = a.table[i];
+    stage_pattern_smem(s_x, a);
+    __syncthreads();
+    const int m = a.m;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        for (long long j = lo; j < own_end; j += s_qs[__ldg(a.text + j + m)]) {  // ssabs.c:46-56
+            if (s_x[m - 1] == __ldg(a.text + j + m - 1) && s_x[0] == __ldg(a.text + j)) {
+                int i = m - 2;
+                while (i > 0 && s_x[i] == __ldg(a.text + j + i)) i--;
+                cnt += i <= 0;
+            }
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Fast-Search: table = bc[256] (all m characters) then gs[0..m] ---- */
+__global__ void __launch_bounds__(kTableThreads) table_fs_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ int s_bc[256];
+    __shared__ int s_gs[SB_XSIZE + 1];
+    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_bc[i] = a.table[i];
+    for (int i = threadIdx.x; i <= a.m; i += kTableThreads) s_gs[i] = a.table[256 + i];
+    stage_pattern_smem(s_x, a);
+    __syncthreads();
+    const int m = a.m;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        {   // fs.c:56: the first window is compared directly
+            int i = 0;
+            while (i < m && s_x[i] == __ldg(a.text + lo + i)) i++;
+            cnt += i == m;
+        }
+        long long s = lo + m;  // index of the window's last character
+        while (s - m + 1 < own_end) {  // fs.c:58-66
+            int k;
+            while (s - m + 1 < own_end && (k = s_bc[__ldg(a.text + s)]) != 0) s += k;
+            if (s - m + 1 >= own_end) break;
+            int j = 2;
+            while (j <= m && s_x[m - j] == __ldg(a.text + s - j + 1)) j++;
+            cnt += j > m;
+            s += s_gs[m - j + 1];
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- GRASPm: table = bc[256], head[256], next[0..m] ---- */
+__global__ void __launch_bounds__(kTableThreads) table_graspm_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ int s_bc[256];
+    __shared__ int s_head[256];
+    __shared__ int s_next[SB_XSIZE + 1];
+    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) {
+        s_bc[i] = a.table[i];
+        s_head[i] = a.table[256 + i];
+    }
+    for (int i = threadIdx.x; i <= a.m; i += kTableThreads) s_next[i] = a.table[512 + i];
+    stage_pattern_smem(s_x, a);
+    __syncthreads();
+    const int m = a.m;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        long long j = lo + m - 1;
+        while (j - (m - 1) < own_end) {  // graspm.c:52-67
+            int k;
+            while (j - (m - 1) < own_end && (k = s_bc[__ldg(a.text + j)]) != 0) j += k;
+            if (j - (m - 1) >= own_end) break;
+            for (int e = s_head[__ldg(a.text + j - 1)]; e >= 0; e = s_next[e]) {  // (j >= 1: m >= 1 and j >= lo + m - 1;
+                const long long first = j - e;                                     //  for m == 1 the byte before local 0 is pad)
+                if (first < lo || first >= own_end) continue;
+                int i = 0;
+                while (i < m && s_x[i] == __ldg(a.text + first + i)) i++;
+                cnt += i == m;
+            }
+            j += m;
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Turbo-BM: table = bmBc[256] then bmGs[0..m) ---- */
+__global__ void __launch_bounds__(kTableThreads) table_tbm_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ int s_bc[256];
+    __shared__ int s_gs[SB_XSIZE];
+    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_bc[i] = a.table[i];
+    for (int i = threadIdx.x; i < a.m; i += kTableThreads) s_gs[i] = a.table[256 + i];
+    stage_pattern_smem(s_x, a);
+    __syncthreads();
+    const int m = a.m;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        int u = 0, shift = m;
+        for (long long j = lo; j < own_end; j += shift) {  // tbm.c:80-108
+            int i = m - 1;
+            unsigned c = 0;
+            while (i >= 0 && s_x[i] == (c = __ldg(a.text + i + j))) {
+                --i;
+                if (u != 0 && i == m - 1 - shift) i -= u;
+            }
+            if (i < 0) {
+                cnt++;
+                shift = s_gs[0];
+                u = m - shift;
+            } else {
+                const int v = m - 1 - i, turbo = u - v, bcs = s_bc[c] - m + 1 + i;
+                shift = turbo > bcs ? turbo : bcs;
+                if (s_gs[i] > shift) shift = s_gs[i];
+                if (shift == s_gs[i]) {
+                    u = (m - shift < v) ? m - shift : v;
+                } else {
+                    if (turbo < bcs && u + 1 > shift) shift = u + 1;
+                    u = 0;
+                }
+            }
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Apostolico-Crochemore: table = kmpNext[0..m]; a.q = ell ---- */
+__global__ void __launch_bounds__(kTableThreads) table_ac_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ int s_next[SB_XSIZE + 1];
+    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i <= a.m; i += kTableThreads) s_next[i] = a.table[i];
+    stage_pattern_smem(s_x, a);
+    __syncthreads();
+    const int m = a.m, ell = a.q;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        int i = ell, k = 0;
+        for (long long j = lo; j < own_end;) {  // ac.c:57-83
+            while (i < m && s_x[i] == __ldg(a.text + i + j)) ++i;
+            if (i >= m) {
+                while (k < ell && s_x[k] == __ldg(a.text + j + k)) ++k;
+                cnt += k >= ell;
+            }
+            j += i - s_next[i];
+            if (i == ell) {
+                k = k - 1 > 0 ? k - 1 : 0;
+            } else if (s_next[i] <= ell) {
+                k = s_next[i] > 0 ? s_next[i] : 0;
+                i = ell;
+            } else {
+                k = ell;
+                i = s_next[i];
+            }
         }
     }
     table_reduce(a, cnt);
