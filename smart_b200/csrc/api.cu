@@ -1896,15 +1896,28 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         case 601:
         case 602: sb::table_kmp_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 603: sb::table_hor_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
-        case 604: sb::table_so_kernel<false><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
-        case 605: sb::table_so_kernel<true><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 604:
+            if (m > SB_WORD) sb::table_so_kernel<false, true><<<grid, sb::kTableThreads, 0, c->stream>>>(a);
+            else sb::table_so_kernel<false, false><<<grid, sb::kTableThreads, 0, c->stream>>>(a);
+            break;
+        case 605:
+            if (m > SB_WORD) sb::table_so_kernel<true, true><<<grid, sb::kTableThreads, 0, c->stream>>>(a);
+            else sb::table_so_kernel<true, false><<<grid, sb::kTableThreads, 0, c->stream>>>(a);
+            break;
         case 606: sb::table_hashq_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 607: sb::table_bm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 608: sb::table_bc_kernel<sb::kBcQs><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 609: sb::table_bc_kernel<sb::kBcRaita><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 610: sb::table_bc_kernel<sb::kBcTuned><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 611: sb::table_kr_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
-        case 613: sb::table_aut_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 613: {
+            const size_t rows = (size_t)(m + 1) * 512;
+            const size_t dyn = rows <= (size_t)sb::kAutSharedBytes ? rows : 0;
+            CU_TRY(cudaFuncSetAttribute(sb::table_aut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        sb::kAutSharedBytes), SB_ERR_CUDA);
+            sb::table_aut_kernel<<<grid, sb::kTableThreads, dyn, c->stream>>>(a);
+            break;
+        }
         case 614: sb::table_bom_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 615: sb::table_ebom_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 616: sb::table_sbndm2_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;

@@ -51,8 +51,9 @@
  * positions, one THREAD per segment, each reading m-1 bytes past its segment (the same m-1 halo rule as the shards).
  * A thread that starts its automaton at the segment's first byte finds exactly the occurrences that start inside
  * the segment.  Lanes of a warp therefore read addresses `seg` bytes apart: every load instruction touches 32
- * sectors and the kernels are bound by the L1/LSU sector rate, not by HBM - measured 0.2-1.3 TB/s against 7.2 TB/s
- * for the fingerprint kernels, which is why these are a selectable mode and not the default.
+ * sectors, and the kernels that read single bytes are bound by the L1/LSU wavefront rate, not by HBM (the forward
+ * automata stream 256-bit vectors instead, see stream_segment) - which is why these are a selectable mode and not
+ * the default.
  * What they return is bit-identical to everything else: the count of bf.c:33-36.
  */
 #pragma once
@@ -89,38 +90,115 @@ __device__ __forceinline__ void table_reduce(const TableArgs &a, unsigned cnt)
     }
 }
 
+/*
+ * Read-only view of a shared-memory table.  nvcc for sm_100a re-derives the shared window base (S2R SR_CgaCtaId +
+ * LEA) in front of every indexed LDS inside these branchy loops - a 20+ cycle special-register read on the
+ * dependency chain of every table lookup.  The view converts the base once, launders it through a volatile move
+ * so it cannot be rematerialised, and reads with ld.shared at base + index * sizeof(T).  Constructed after the
+ * __syncthreads() that ends the staging; the tables are never written again.
+ */
+template <class T>
+struct Smem {
+    uint32_t base;
+    __device__ __forceinline__ explicit Smem(const T *p)
+    {
+        const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+        asm volatile("mov.u32 %0, %1;" : "=r"(base) : "r"(a));
+    }
+    __device__ __forceinline__ T at_byte(uint32_t byte_off) const  // byte_off a multiple of sizeof(T)
+    {
+        uint32_t v;
+        if (sizeof(T) == 1)
+            asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + byte_off));
+        else if (sizeof(T) == 2)
+            asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(base + byte_off));
+        else
+            asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + byte_off));
+        return (T)v;
+    }
+    __device__ __forceinline__ T operator[](int i) const { return at_byte((uint32_t)i * (uint32_t)sizeof(T)); }
+};
+
 /* pattern bytes into shared memory (padded to a word) */
 __device__ __forceinline__ void stage_pattern_smem(uint8_t *sx, const TableArgs &a)
 {
     for (int i = threadIdx.x; i < a.m; i += kTableThreads) sx[i] = a.pat[i];
 }
 
+/*
+ * The forward automata (kmp, mp, so, sa, aut) consume the text strictly one byte after the other, so a thread streams
+ * its segment with 256-bit loads - 64 B (two sectors of one line, a full DRAM burst) per step, the next 64 B
+ * requested before the current ones are consumed - and takes the bytes out of registers at compile-time offsets.
+ * A warp-wide byte or word load over 32 segments costs 32 L1 wavefronts per 32 / 128 bytes; the vector load pays
+ * the same 32 wavefronts per 1024 bytes, which moves these kernels from the LSU bound to their shared-memory
+ * table lookups.  `lo` is a multiple of 64 (segments are multiples of 4 KiB); the last step reads up to 127 bytes
+ * past `end`, inside the shard buffer's zeroed back pad (kPadBytes).  f(c, j): byte c at text index j.
+ */
+struct StreamNoFlush {
+    __device__ __forceinline__ void operator()(long long) const {}
+};
+
+template <class F, class G>
+__device__ __forceinline__ void stream_words(const V8 &v, long long j0, F &&f, G &&flush)
+{
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t w = v.w[k];
+        f(w & 0xffu, j0 + 4 * k, 4 * k);
+        f((w >> 8) & 0xffu, j0 + 4 * k + 1, 4 * k + 1);
+        f((w >> 16) & 0xffu, j0 + 4 * k + 2, 4 * k + 2);
+        f(w >> 24, j0 + 4 * k + 3, 4 * k + 3);
+    }
+    flush(j0);
+}
+
+/* f(c, j, k): byte c at text index j, k = j - j0 in 0..31 a compile-time constant; flush(j0) after each 32 bytes */
+template <class F, class G = StreamNoFlush>
+__device__ __forceinline__ void stream_segment(const uint8_t *text, long long lo, long long end, F &&f, G &&flush = G())
+{
+    V8 a = ldg_stream256(text + lo), b = ldg_stream256(text + lo + 32);
+    long long j = lo;
+    for (; j + 64 <= end; j += 64) {
+        const V8 na = ldg_stream256(text + j + 64), nb = ldg_stream256(text + j + 96);
+        stream_words(a, j, f, flush);
+        stream_words(b, j + 32, f, flush);
+        a = na;
+        b = nb;
+    }
+    if (j < end) {  // the last, partial step
+        auto g = [&](unsigned c, long long jj, int k) {
+            if (jj < end) f(c, jj, k);
+        };
+        stream_words(a, j, g, flush);
+        stream_words(b, j + 32, g, flush);
+    }
+}
+
 /* ---- Knuth-Morris-Pratt / Morris-Pratt: table = kmpNext[0..m] or mpNext[0..m] ---- */
 __global__ void __launch_bounds__(kTableThreads) table_kmp_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ int s_next[SB_XSIZE + 1];
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    for (int i = threadIdx.x; i <= a.m; i += kTableThreads) s_next[i] = a.table[i];
-    stage_pattern_smem(s_x, a);
+    __shared__ int raw_next[SB_XSIZE + 1];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i <= a.m; i += kTableThreads) raw_next[i] = a.table[i];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
+    const Smem<int> s_next(raw_next);
+    const Smem<uint8_t> s_x(raw_x);
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
     if (lo < a.hi) {
         const long long own_end = min(lo + a.seg, a.hi);   // starts [lo, own_end)
         const long long end = own_end + a.m - 1;           // text bytes [lo, end)
         int i = 0;
-        uint32_t w = 0;
-        for (long long j = lo; j < end; j++) {
-            if ((j & 3) == 0) w = __ldg(reinterpret_cast<const uint32_t *>(a.text + j));  // lo is a multiple of 4
-            const int c = (int)(w & 0xffu);
-            w >>= 8;
-            while (i > -1 && (int)s_x[i] != c) i = s_next[i];  // kmp.c:57-58
+        const int m = a.m;
+        stream_segment(a.text, lo, end, [&](unsigned c, long long, int) {
+            while (i > -1 && (unsigned)s_x[i] != c) i = s_next[i];  // kmp.c:57-58
             i++;
-            if (i >= a.m) {                                     // kmp.c:61-64: OUTPUT(j - i) with j already advanced
-                cnt++;                                          // the start j+1-m is >= lo (i began at 0) and < own_end
+            if (i >= m) {                                           // kmp.c:61-64: OUTPUT(j - i) with j already advanced
+                cnt++;                                              // the start j+1-m is >= lo (i began at 0) and < own_end
                 i = s_next[i];
             }
-        }
+        });
     }
     table_reduce(a, cnt);
 }
@@ -128,11 +206,13 @@ __global__ void __launch_bounds__(kTableThreads) table_kmp_kernel(const __grid_c
 /* ---- Horspool: table = hbc[256] ---- */
 __global__ void __launch_bounds__(kTableThreads) table_hor_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ int s_hbc[256];
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_hbc[i] = a.table[i];
-    stage_pattern_smem(s_x, a);
+    __shared__ int raw_hbc[256];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_hbc[i] = a.table[i];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
+    const Smem<int> s_hbc(raw_hbc);
+    const Smem<uint8_t> s_x(raw_x);
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
     if (lo < a.hi) {
@@ -149,41 +229,55 @@ __global__ void __launch_bounds__(kTableThreads) table_hor_kernel(const __grid_c
 }
 
 /* ---- Shift-Or (AND = false) / Shift-And (AND = true): table = S[256] over the first min(m,32) characters ---- */
-template <bool AND>
+/* so.c:88-91 / sa.c:86-89: the bytes after the 32-character prefix (m > 32 only; out of line, it is rare) */
+__device__ __noinline__ unsigned so_verify_rest(const uint8_t *text, const uint8_t *pat, long long st, int m)
+{
+    int i = SB_WORD;
+    while (i < m && __ldg(pat + i) == __ldg(text + st + i)) i++;
+    return i == m;
+}
+
+template <bool AND, bool LARGE>
 __global__ void __launch_bounds__(kTableThreads) table_so_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ unsigned s_S[256];
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_S[i] = (unsigned)a.table[i];
-    stage_pattern_smem(s_x, a);
+    __shared__ unsigned raw_S[256 * 32];  // one copy of S per lane, entry c of lane l in bank l: lookups never conflict
+    for (int i = threadIdx.x; i < 256 * 32; i += kTableThreads) raw_S[i] = (unsigned)a.table[i >> 5];
     __syncthreads();
+    const Smem<unsigned> S(raw_S + (threadIdx.x & 31));
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
-    const int k = a.m < SB_WORD ? a.m : SB_WORD;  // characters in the automaton (search_large: the 32-char prefix)
+    const int k = LARGE ? SB_WORD : a.m;  // characters in the automaton (search_large: the 32-character prefix)
     unsigned cnt = 0;
     if (lo < a.hi) {
         const long long own_end = min(lo + a.seg, a.hi);
         const long long end = own_end + k - 1;  // the prefix automaton reads [lo, end)
         unsigned D = AND ? 0u : ~0u;
-        uint32_t w = 0;
-        for (long long j = lo; j < end; j++) {
-            if ((j & 3) == 0) w = __ldg(reinterpret_cast<const uint32_t *>(a.text + j));
-            const unsigned c = w & 0xffu;
-            w >>= 8;
-            bool hit;
-            if (AND) {
-                D = ((D << 1) | 1u) & s_S[c];  // sa.c:50
-                hit = (D & a.lim) != 0;        // sa.c:51 (F = 1 << (k-1))
-            } else {
-                D = (D << 1) | s_S[c];         // so.c:55
-                hit = D < a.lim;               // so.c:56
-            }
-            if (hit) {
-                const long long st = j - k + 1;  // >= lo: the automaton started empty at lo
-                int i = k;                       // so.c:88-91: the bytes after the prefix
-                while (i < a.m && s_x[i] == __ldg(a.text + st + i)) i++;
-                if (i == a.m) cnt++;
-            }
-        }
+        const unsigned lim = a.lim;
+        unsigned hits = 0;  // LARGE: prefix hits among the 32 bytes in flight, verified after them
+        stream_segment(
+            a.text, lo, end,
+            [&](unsigned c, long long, int b) {
+                bool hit;
+                if (AND) {
+                    D = ((D << 1) | 1u) & S.at_byte(c * 128);  // sa.c:50
+                    hit = (D & lim) != 0;                      // sa.c:51 (F = 1 << (k-1))
+                } else {
+                    D = (D << 1) | S.at_byte(c * 128);         // so.c:55
+                    hit = D < lim;                             // so.c:56
+                }
+                if (LARGE) {
+                    if (hit) hits |= 1u << b;
+                } else {
+                    cnt += hit;
+                }
+            },
+            [&](long long j0) {
+                if (!LARGE) return;
+                while (hits) {  // the start j - 31 is >= lo: D began empty at lo
+                    const int b = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    cnt += so_verify_rest(a.text, a.pat, j0 + b - (SB_WORD - 1), a.m);
+                }
+            });
     }
     table_reduce(a, cnt);
 }
@@ -191,11 +285,13 @@ __global__ void __launch_bounds__(kTableThreads) table_so_kernel(const __grid_co
 /* ---- HASHq: table = shift[256]; a.q = 3, 5 or 8; a.sh1 ---- */
 __global__ void __launch_bounds__(kTableThreads) table_hashq_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ int s_shift[256];
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_shift[i] = a.table[i];
-    stage_pattern_smem(s_x, a);
+    __shared__ int raw_shift[256];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_shift[i] = a.table[i];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
+    const Smem<int> s_shift(raw_shift);
+    const Smem<uint8_t> s_x(raw_x);
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
     if (lo < a.hi) {
@@ -222,13 +318,16 @@ __global__ void __launch_bounds__(kTableThreads) table_hashq_kernel(const __grid
 /* ---- Boyer-Moore: table = bmBc[256] followed by bmGs[0..m) ---- */
 __global__ void __launch_bounds__(kTableThreads) table_bm_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ int s_bc[256];
-    __shared__ int s_gs[SB_XSIZE];
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_bc[i] = a.table[i];
-    for (int i = threadIdx.x; i < a.m; i += kTableThreads) s_gs[i] = a.table[256 + i];
-    stage_pattern_smem(s_x, a);
+    __shared__ int raw_bc[256];
+    __shared__ int raw_gs[SB_XSIZE];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_bc[i] = a.table[i];
+    for (int i = threadIdx.x; i < a.m; i += kTableThreads) raw_gs[i] = a.table[256 + i];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
+    const Smem<int> s_bc(raw_bc);
+    const Smem<int> s_gs(raw_gs);
+    const Smem<uint8_t> s_x(raw_x);
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
     if (lo < a.hi) {
@@ -255,17 +354,19 @@ enum { kBcQs = 0, kBcRaita = 1, kBcTuned = 2 };
 template <int KIND>
 __global__ void __launch_bounds__(kTableThreads) table_bc_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ int s_bc[256];
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_bc[i] = a.table[i];
-    stage_pattern_smem(s_x, a);
+    __shared__ int raw_bc[256];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_bc[i] = a.table[i];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
     const int m = a.m;
-    const unsigned last_ch = s_x[m - 1];
-    const int shift = s_bc[last_ch];                  // tunedbm.c:40 (read before the entry is zeroed)
+    const unsigned last_ch = raw_x[m - 1];
+    const int shift = raw_bc[last_ch];                  // tunedbm.c:40 (read before the entry is zeroed)
     __syncthreads();
-    if (KIND == kBcTuned && threadIdx.x == 0) s_bc[last_ch] = 0;  // tunedbm.c:41
+    if (KIND == kBcTuned && threadIdx.x == 0) raw_bc[last_ch] = 0;  // tunedbm.c:41
     __syncthreads();
+    const Smem<int> s_bc(raw_bc);
+    const Smem<uint8_t> s_x(raw_x);
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
     if (lo < a.hi) {
@@ -306,9 +407,10 @@ __global__ void __launch_bounds__(kTableThreads) table_bc_kernel(const __grid_co
 /* ---- Karp-Rabin: a.lim = d = 2^(m-1) (wrapping), a.sh1 = hx ---- */
 __global__ void __launch_bounds__(kTableThreads) table_kr_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    stage_pattern_smem(s_x, a);
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
+    const Smem<uint8_t> s_x(raw_x);
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
     if (lo < a.hi) {
@@ -329,28 +431,38 @@ __global__ void __launch_bounds__(kTableThreads) table_kr_kernel(const __grid_co
 }
 
 /* ---- deterministic automaton: table = delta as 16-bit entries, (m+1) rows of 256 ---- */
-constexpr int kAutSharedRows = 95;  // 95 * 256 * 2 B = 47.5 KiB (+ the reduction scratch) of the 48 KiB static limit
+/* the rows sit in DYNAMIC shared memory, (m+1) * 512 bytes, when that is at most kAutSharedBytes (four CTAs per SM
+ * still fit); longer patterns read delta through L1/L2 (smem == nullptr view: `rows` = 0) */
+constexpr int kAutSharedBytes = 56 * 1024;
 __global__ void __launch_bounds__(kTableThreads) table_aut_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ unsigned short s_delta[kAutSharedRows * 256];
+    extern __shared__ __align__(16) unsigned short raw_delta[];
     const unsigned short *gdelta = reinterpret_cast<const unsigned short *>(a.table);
-    const bool small = a.m + 1 <= kAutSharedRows;
-    if (small)
-        for (int i = threadIdx.x; i < (a.m + 1) * 256; i += kTableThreads) s_delta[i] = gdelta[i];
+    const bool small = (a.m + 1) * 512 <= kAutSharedBytes;
+    if (small) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(gdelta);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(raw_delta);
+        for (int i = threadIdx.x; i < (a.m + 1) * 128; i += kTableThreads) dst[i] = src[i];
+    }
     __syncthreads();
-    const unsigned short *delta = small ? s_delta : gdelta;
+    const Smem<unsigned short> s_delta(raw_delta);
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
     if (lo < a.hi) {
         const long long own_end = min(lo + a.seg, a.hi);
         const long long end = own_end + a.m - 1;
         unsigned state = 0;  // a segment starts like the text does: only occurrences that start at or after lo are seen
-        uint32_t w = 0;
-        for (long long j = lo; j < end; j++) {
-            if ((j & 3) == 0) w = __ldg(reinterpret_cast<const uint32_t *>(a.text + j));
-            state = small ? delta[state * 256 + (w & 0xffu)] : __ldg(delta + state * 256 + (w & 0xffu));  // aut.c:39
-            w >>= 8;
-            cnt += state == (unsigned)a.m;                                                                 // aut.c:40
+        const unsigned m = (unsigned)a.m;
+        if (small) {
+            stream_segment(a.text, lo, end, [&](unsigned c, long long, int) {
+                state = s_delta.at_byte(state * 512 + c * 2);  // aut.c:39
+                cnt += state == m;                             // aut.c:40
+            });
+        } else {
+            stream_segment(a.text, lo, end, [&](unsigned c, long long, int) {
+                state = __ldg(gdelta + state * 256 + c);
+                cnt += state == m;
+            });
         }
     }
     table_reduce(a, cnt);
@@ -360,19 +472,19 @@ __global__ void __launch_bounds__(kTableThreads) table_aut_kernel(const __grid_c
 constexpr int kBomSharedRows = 94;
 __global__ void __launch_bounds__(kTableThreads) table_bom_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ short s_trans[kBomSharedRows * 256];
-    __shared__ unsigned char s_term[kBomSharedRows];
+    __shared__ short raw_trans[kBomSharedRows * 256];
+    __shared__ unsigned char raw_term[kBomSharedRows];
     const int m = a.m;
     const short *gtrans = reinterpret_cast<const short *>(a.table);
     const unsigned char *gterm = reinterpret_cast<const unsigned char *>(gtrans + (size_t)(m + 1) * 256);
     const bool small = m + 1 <= kBomSharedRows;
     if (small) {
-        for (int i = threadIdx.x; i < (m + 1) * 256; i += kTableThreads) s_trans[i] = gtrans[i];
-        for (int i = threadIdx.x; i <= m; i += kTableThreads) s_term[i] = gterm[i];
+        for (int i = threadIdx.x; i < (m + 1) * 256; i += kTableThreads) raw_trans[i] = gtrans[i];
+        for (int i = threadIdx.x; i <= m; i += kTableThreads) raw_term[i] = gterm[i];
     }
     __syncthreads();
-    const short *trans = small ? s_trans : gtrans;
-    const unsigned char *term = small ? s_term : gterm;
+    const Smem<short> s_trans(raw_trans);
+    const Smem<unsigned char> s_term(raw_term);
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
     if (lo < a.hi) {
@@ -380,9 +492,9 @@ __global__ void __launch_bounds__(kTableThreads) table_bom_kernel(const __grid_c
         long long j = lo;
         while (j < own_end) {       // bom.c:90-106
             int i = m - 1, r = m, shift = m, period = m, q;
-            while (i >= 0 && (q = small ? trans[r * 256 + __ldg(a.text + i + j)] : __ldg(trans + r * 256 + __ldg(a.text + i + j))) >= 0) {
+            while (i >= 0 && (q = small ? s_trans[r * 256 + __ldg(a.text + i + j)] : __ldg(gtrans + r * 256 + __ldg(a.text + i + j))) >= 0) {
                 r = q;
-                if (small ? term[r] : __ldg(term + r)) {
+                if (small ? s_term[r] : __ldg(gterm + r)) {
                     period = shift;
                     shift = i;
                 }
@@ -402,9 +514,10 @@ __global__ void __launch_bounds__(kTableThreads) table_bom_kernel(const __grid_c
  *      FT[256][256] as 16-bit entries (FT[a][b] = trans[trans[m][a]][b], ebom.c:54-59); a.lim = offset of FT in shorts ---- */
 __global__ void __launch_bounds__(kTableThreads) table_ebom_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    stage_pattern_smem(s_x, a);
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
+    const Smem<uint8_t> s_x(raw_x);
     const int m = a.m;
     const short *trans = reinterpret_cast<const short *>(a.table);
     const short *FT = trans + a.lim;
@@ -440,11 +553,13 @@ __global__ void __launch_bounds__(kTableThreads) table_ebom_kernel(const __grid_
 /* ---- SBNDM2 (m <= 32): table = B[256]; a.sh1 = the shift after an occurrence ---- */
 __global__ void __launch_bounds__(kTableThreads) table_sbndm2_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ unsigned s_B[256];
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_B[i] = (unsigned)a.table[i];
-    stage_pattern_smem(s_x, a);
+    __shared__ unsigned raw_B[256];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_B[i] = (unsigned)a.table[i];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
+    const Smem<unsigned> s_B(raw_B);
+    const Smem<uint8_t> s_x(raw_x);
     const int m = a.m;
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
@@ -477,11 +592,13 @@ __global__ void __launch_bounds__(kTableThreads) table_sbndm2_kernel(const __gri
 /* ---- BNDM: table = B[256] over the first min(m,32) characters, reversed ---- */
 __global__ void __launch_bounds__(kTableThreads) table_bndm_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ unsigned s_B[256];
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_B[i] = (unsigned)a.table[i];
-    stage_pattern_smem(s_x, a);
+    __shared__ unsigned raw_B[256];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_B[i] = (unsigned)a.table[i];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
+    const Smem<unsigned> s_B(raw_B);
+    const Smem<uint8_t> s_x(raw_x);
     const int m = a.m, w = m < SB_WORD ? m : SB_WORD;
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
@@ -515,9 +632,10 @@ __global__ void __launch_bounds__(kTableThreads) table_bndm_kernel(const __grid_
 template <bool TVSBS>
 __global__ void __launch_bounds__(kTableThreads) table_br_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    stage_pattern_smem(s_x, a);
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
+    const Smem<uint8_t> s_x(raw_x);
     const int m = a.m;
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
@@ -544,11 +662,13 @@ __global__ void __launch_bounds__(kTableThreads) table_br_kernel(const __grid_co
 /* ---- Smith: table = bmBc[256] then qsBc[256] ---- */
 __global__ void __launch_bounds__(kTableThreads) table_smith_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ int s_bc[512];
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    for (int i = threadIdx.x; i < 512; i += kTableThreads) s_bc[i] = a.table[i];
-    stage_pattern_smem(s_x, a);
+    __shared__ int raw_bc[512];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 512; i += kTableThreads) raw_bc[i] = a.table[i];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
+    const Smem<int> s_bc(raw_bc);
+    const Smem<uint8_t> s_x(raw_x);
     const int m = a.m;
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
@@ -569,13 +689,16 @@ __global__ void __launch_bounds__(kTableThreads) table_smith_kernel(const __grid
 /* ---- Skip Search: table = z[256] then list[m] ---- */
 __global__ void __launch_bounds__(kTableThreads) table_skip_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ int s_z[256];
-    __shared__ int s_list[SB_XSIZE];
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_z[i] = a.table[i];
-    for (int i = threadIdx.x; i < a.m; i += kTableThreads) s_list[i] = a.table[256 + i];
-    stage_pattern_smem(s_x, a);
+    __shared__ int raw_z[256];
+    __shared__ int raw_list[SB_XSIZE];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_z[i] = a.table[i];
+    for (int i = threadIdx.x; i < a.m; i += kTableThreads) raw_list[i] = a.table[256 + i];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
+    const Smem<int> s_z(raw_z);
+    const Smem<int> s_list(raw_list);
+    const Smem<uint8_t> s_x(raw_x);
     const int m = a.m;
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
@@ -598,13 +721,16 @@ __global__ void __launch_bounds__(kTableThreads) table_skip_kernel(const __grid_
 /* ---- Franek-Jennings-Smyth: table = qsBc[256] then kmpNext[0..m] ---- */
 __global__ void __launch_bounds__(kTableThreads) table_fjs_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ int s_qs[256];
-    __shared__ int s_next[SB_XSIZE + 1];
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_qs[i] = a.table[i];
-    for (int i = threadIdx.x; i <= a.m; i += kTableThreads) s_next[i] = a.table[256 + i];
-    stage_pattern_smem(s_x, a);
+    __shared__ int raw_qs[256];
+    __shared__ int raw_next[SB_XSIZE + 1];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_qs[i] = a.table[i];
+    for (int i = threadIdx.x; i <= a.m; i += kTableThreads) raw_next[i] = a.table[256 + i];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
+    const Smem<int> s_qs(raw_qs);
+    const Smem<int> s_next(raw_next);
+    const Smem<uint8_t> s_x(raw_x);
     const int m = a.m;
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
@@ -626,11 +752,13 @@ __global__ void __launch_bounds__(kTableThreads) table_fjs_kernel(const __grid_c
 /* ---- SSABS: table = qsBc[256] ---- */
 __global__ void __launch_bounds__(kTableThreads) table_ssabs_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ int s_qs[256];
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_qs[i] = a.table[i];
-    stage_pattern_smem(s_x, a);
+    __shared__ int raw_qs[256];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_qs[i] = a.table[i];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
+    const Smem<int> s_qs(raw_qs);
+    const Smem<uint8_t> s_x(raw_x);
     const int m = a.m;
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
@@ -650,13 +778,16 @@ __global__ void __launch_bounds__(kTableThreads) table_ssabs_kernel(const __grid
 /* ---- Fast-Search: table = bc[256] (all m characters) then gs[0..m] ---- */
 __global__ void __launch_bounds__(kTableThreads) table_fs_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ int s_bc[256];
-    __shared__ int s_gs[SB_XSIZE + 1];
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_bc[i] = a.table[i];
-    for (int i = threadIdx.x; i <= a.m; i += kTableThreads) s_gs[i] = a.table[256 + i];
-    stage_pattern_smem(s_x, a);
+    __shared__ int raw_bc[256];
+    __shared__ int raw_gs[SB_XSIZE + 1];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_bc[i] = a.table[i];
+    for (int i = threadIdx.x; i <= a.m; i += kTableThreads) raw_gs[i] = a.table[256 + i];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
+    const Smem<int> s_bc(raw_bc);
+    const Smem<int> s_gs(raw_gs);
+    const Smem<uint8_t> s_x(raw_x);
     const int m = a.m;
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
@@ -684,17 +815,21 @@ __global__ void __launch_bounds__(kTableThreads) table_fs_kernel(const __grid_co
 /* ---- GRASPm: table = bc[256], head[256], next[0..m] ---- */
 __global__ void __launch_bounds__(kTableThreads) table_graspm_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ int s_bc[256];
-    __shared__ int s_head[256];
-    __shared__ int s_next[SB_XSIZE + 1];
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    __shared__ int raw_bc[256];
+    __shared__ int raw_head[256];
+    __shared__ int raw_next[SB_XSIZE + 1];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
     for (int i = threadIdx.x; i < 256; i += kTableThreads) {
-        s_bc[i] = a.table[i];
-        s_head[i] = a.table[256 + i];
+        raw_bc[i] = a.table[i];
+        raw_head[i] = a.table[256 + i];
     }
-    for (int i = threadIdx.x; i <= a.m; i += kTableThreads) s_next[i] = a.table[512 + i];
-    stage_pattern_smem(s_x, a);
+    for (int i = threadIdx.x; i <= a.m; i += kTableThreads) raw_next[i] = a.table[512 + i];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
+    const Smem<int> s_bc(raw_bc);
+    const Smem<int> s_head(raw_head);
+    const Smem<int> s_next(raw_next);
+    const Smem<uint8_t> s_x(raw_x);
     const int m = a.m;
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
@@ -721,13 +856,16 @@ __global__ void __launch_bounds__(kTableThreads) table_graspm_kernel(const __gri
 /* ---- Turbo-BM: table = bmBc[256] then bmGs[0..m) ---- */
 __global__ void __launch_bounds__(kTableThreads) table_tbm_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ int s_bc[256];
-    __shared__ int s_gs[SB_XSIZE];
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    for (int i = threadIdx.x; i < 256; i += kTableThreads) s_bc[i] = a.table[i];
-    for (int i = threadIdx.x; i < a.m; i += kTableThreads) s_gs[i] = a.table[256 + i];
-    stage_pattern_smem(s_x, a);
+    __shared__ int raw_bc[256];
+    __shared__ int raw_gs[SB_XSIZE];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_bc[i] = a.table[i];
+    for (int i = threadIdx.x; i < a.m; i += kTableThreads) raw_gs[i] = a.table[256 + i];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
+    const Smem<int> s_bc(raw_bc);
+    const Smem<int> s_gs(raw_gs);
+    const Smem<uint8_t> s_x(raw_x);
     const int m = a.m;
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
@@ -764,11 +902,13 @@ __global__ void __launch_bounds__(kTableThreads) table_tbm_kernel(const __grid_c
 /* ---- Apostolico-Crochemore: table = kmpNext[0..m]; a.q = ell ---- */
 __global__ void __launch_bounds__(kTableThreads) table_ac_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ int s_next[SB_XSIZE + 1];
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
-    for (int i = threadIdx.x; i <= a.m; i += kTableThreads) s_next[i] = a.table[i];
-    stage_pattern_smem(s_x, a);
+    __shared__ int raw_next[SB_XSIZE + 1];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i <= a.m; i += kTableThreads) raw_next[i] = a.table[i];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
+    const Smem<int> s_next(raw_next);
+    const Smem<uint8_t> s_x(raw_x);
     const int m = a.m, ell = a.q;
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
@@ -800,15 +940,16 @@ __global__ void __launch_bounds__(kTableThreads) table_ac_kernel(const __grid_co
 constexpr int kQfSharedEntries = 8192;
 __global__ void __launch_bounds__(kTableThreads) table_qf_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ int s_B[kQfSharedEntries];
-    __shared__ uint8_t s_x[SB_XSIZE + 8];
+    __shared__ int raw_B[kQfSharedEntries];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
     const int Q = a.q, S = a.sh1, asize = 1 << (Q * S);
     const bool small = asize <= kQfSharedEntries;
     if (small)
-        for (int i = threadIdx.x; i < asize; i += kTableThreads) s_B[i] = a.table[i];
-    stage_pattern_smem(s_x, a);
+        for (int i = threadIdx.x; i < asize; i += kTableThreads) raw_B[i] = a.table[i];
+    stage_pattern_smem(raw_x, a);
     __syncthreads();
-    const int *B = small ? s_B : a.table;
+    const Smem<int> s_B(raw_B);
+    const Smem<uint8_t> s_x(raw_x);
     const unsigned mask = (unsigned)asize - 1u;
     const int m = a.m, mq1 = m - Q + 1;
     const long long n = a.hi + m - 1;  // text bytes of this shard's own windows
@@ -823,13 +964,13 @@ __global__ void __launch_bounds__(kTableThreads) table_qf_kernel(const __grid_co
         const long long own_end = min(lo + a.seg, a.hi);
         // qf23.c:61: the scan state is the index i alone, so a segment starts like the text does (i = mq1-1, at lo)
         for (long long i = lo + mq1 - 1; i <= n - Q && i - mq1 + 1 < own_end; i += mq1) {
-            unsigned D = small ? (unsigned)B[gram(i)] : (unsigned)__ldg(B + gram(i));
+            unsigned D = small ? (unsigned)s_B[gram(i)] : (unsigned)__ldg(a.table + gram(i));
             if (!D) continue;
             const long long j = i - mq1 + Q;
             for (;;) {                                      // qf23.c:65-72 ("more:")
                 i -= Q;
                 if (i >= j) {
-                    D &= small ? (unsigned)B[gram(i)] : (unsigned)__ldg(B + gram(i));
+                    D &= small ? (unsigned)s_B[gram(i)] : (unsigned)__ldg(a.table + gram(i));
                     if (D == 0) break;
                 } else {                                    // qf23.c:73-81: verify the surviving alignments
                     i = j;

@@ -24,10 +24,11 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--out", default="gpurun_out/sweep.jsonl")
     ap.add_argument("--default-only", action="store_true")
+    ap.add_argument("--append", action="store_true", help="append to --out instead of replacing it")
     ap.add_argument("--flags", type=int, default=0, help="SB_FLAG_* ORed into every search (8192 = NO_PACK: byte kernels)")
     a = ap.parse_args()
     n = int(a.gib * (1 << 30))
-    out = open(a.out, "w")
+    out = open(a.out, "a" if a.append else "w")
     for sigma in [int(s) for s in a.sigmas.split(",")]:
         seed = 1000 + sigma
         with sb.Text.generate(n, sigma, seed) as t:
@@ -46,7 +47,7 @@ def main():
                         tm = sb.last_timing()
                         ts.append(tm.kernel_ms)
                         cnt = r.count
-                    rec = {"sigma": sigma, "m": m, "filter": tm.filter_kind, "default": f is None, "count": cnt, "verified": tm.verified,
+                    rec = {"algo": a.algo, "sigma": sigma, "m": m, "filter": tm.filter_kind, "default": f is None, "count": cnt, "verified": tm.verified,
                            "kernel_ms_median": float(np.median(ts)), "GBps": n / (float(np.median(ts)) * 1e-3) / 1e9,
                            "GBps_best": n / (min(ts) * 1e-3) / 1e9}
                     out.write(json.dumps(rec) + "\n")
