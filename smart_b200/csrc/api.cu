@@ -1728,6 +1728,11 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
     case SB_FAM_GRASPM: kind = 625; break;
     case SB_FAM_TBM: kind = 626; break;
     case SB_FAM_AC: kind = 627; break;
+    case SB_FAM_BADCHAR: kind = strcmp(desc->name, "zt") == 0 ? 628 : 0; break;
+    case SB_FAM_SKIPQ: kind = 629; break;
+    case SB_FAM_WFR:  // the scans restated so far: wfr (wfr.c) and wfrq2..8 (wfrq4.c)
+        kind = (strcmp(desc->name, "wfr") == 0 || strncmp(desc->name, "wfrq", 4) == 0) ? 630 : 0;
+        break;
     case SB_FAM_RAITA: kind = 609; break;
     case SB_FAM_TUNEDBM: kind = 610; break;
     case SB_FAM_KR: kind = 611; break;
@@ -1822,6 +1827,28 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         sb_prep_bmgs(x, m, scratch, table + 256);
         ntable = 256 + m;
         break;
+    case 628:
+        sb_prep_bmgs(x, m, scratch, table);
+        sb_prep_ztbc(x, m, table + m);
+        ntable = m + 65536;
+        break;
+    case 629:
+        qq = desc->min_m;  // the q-gram length is the family's smallest m (skip3.c:31)
+        sb_prep_skipq(x, m, qq, table + m, table);
+        ntable = m + 65536;
+        break;
+    case 630: {
+        static thread_local unsigned char F[65536];
+        qq = desc->Q;
+        sb_prep_wfr(x, qq > 1 ? m - m % qq : m, qq, F);  // wfrq4.c:75: the table is built over the cut pattern
+        for (int i = 0; i < 2048; i++) {
+            unsigned w = 0;
+            for (int b = 0; b < 32; b++) w |= (unsigned)(F[i * 32 + b] != 0) << b;
+            table[i] = (int)w;
+        }
+        ntable = 2048;
+        break;
+    }
     case 627: {
         sb_prep_mp(x, m, scratch);
         sb_prep_kmp(x, m, scratch, table);
@@ -1909,7 +1936,10 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         case 608: sb::table_bc_kernel<sb::kBcQs><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 609: sb::table_bc_kernel<sb::kBcRaita><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 610: sb::table_bc_kernel<sb::kBcTuned><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
-        case 611: sb::table_kr_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 611:
+            if (m <= SB_WORD) sb::table_kr_kernel<true><<<grid, sb::kTableThreads, 0, c->stream>>>(a);
+            else sb::table_kr_kernel<false><<<grid, sb::kTableThreads, 0, c->stream>>>(a);
+            break;
         case 613: {
             const size_t rows = (size_t)(m + 1) * 512;
             const size_t dyn = rows <= (size_t)sb::kAutSharedBytes ? rows : 0;
@@ -1932,6 +1962,9 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         case 625: sb::table_graspm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 626: sb::table_tbm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 627: sb::table_ac_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 628: sb::table_zt_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 629: sb::table_skipq_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 630: sb::table_wfr_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         default: sb::table_qf_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         }
         CU_TRY(cudaGetLastError(), SB_ERR_CUDA);

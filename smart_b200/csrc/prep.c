@@ -480,6 +480,27 @@ void sb_prep_ztbc(const unsigned char *x, int m, int *ztBc)
     for (int i = 1; i < m - 1; i++) ztBc[x[i - 1] * 256 + x[i]] = m - 1 - i;
 }
 
+/* Skip Search on q-grams (skip3.c:33-42, skip5.c:36-45): pattern offset i is filed under the hash of x[i..i+Q);
+ * head[h] = the last offset filed under h (-1: none), next[i] = the one filed before i.  skip3 hashes
+ * x[i]<<4 + x[i+1]<<2 + x[i+2] (skip3.c:25), skipQ for Q >= 5 sum_k x[i+k] << (Q-1-k) (skip5.c:25): < 65536. */
+static unsigned skipq_hash(const unsigned char *p, int Q)
+{
+    if (Q == 3) return ((unsigned)p[0] << 4) + ((unsigned)p[1] << 2) + p[2];
+    unsigned h = 0;
+    for (int k = 0; k < Q; k++) h += (unsigned)p[k] << (Q - 1 - k);
+    return h;
+}
+
+void sb_prep_skipq(const unsigned char *x, int m, int Q, int *head, int *next)
+{
+    for (int i = 0; i < 65536; i++) head[i] = -1;
+    for (int i = 0; i + Q <= m; i++) {
+        const unsigned h = skipq_hash(x + i, Q);
+        next[i] = head[h];
+        head[h] = i;
+    }
+}
+
 /* Weak-factor-recognition table (wfr.c:41-58, wfrq4.c:50-65): F[h] = 1 for the 16-bit hash h of every pattern
  * factor the scan can ask about.  The hash is built right to left, as the scan reads the window.
  * Q <= 1 (wfr, wfr2..8, twfr*, lwfr*): every factor x[j..i] of at most 16 characters, h <- (h << 2) + x[j].

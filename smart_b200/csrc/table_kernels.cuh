@@ -46,6 +46,11 @@
  *   tbm          bmBc[256] + bmGs[0..m) (tbm.c:66-111): Turbo-BM, the factor matched by the previous attempt is
  *                remembered (u) and jumped over; a segment starts with u = 0 like the text does
  *   ac           kmpNext[0..m] + ell (ac.c:44-86): Apostolico-Crochemore
+ *   zt           ztBc[256][256] (zt.c:64-74, 256 KiB through L1/L2) + bmGs[0..m): BM with a two-character shift
+ *   skip3/5..8   q-gram buckets head[65536] + next[m] (skip5.c:36-45): every (m-Q+1)-th text q-gram selects the
+ *                alignments to compare (skip5.c:50-57)
+ *   wfr, wfrq2..8  the weak-factor bit table F (wfr.c:41-58, wfrq4.c:50-65; 65536 bits = 8 KiB of shared memory):
+ *                the window is hashed right to left while the hash is some pattern factor's (wfr.c:73-92)
  *
  * Parallelisation: the scan loops are inherently sequential, so the text is cut into segments of `seg` start
  * positions, one THREAD per segment, each reading m-1 bytes past its segment (the same m-1 halo rule as the shards).
@@ -405,26 +410,79 @@ __global__ void __launch_bounds__(kTableThreads) table_bc_kernel(const __grid_co
 }
 
 /* ---- Karp-Rabin: a.lim = d = 2^(m-1) (wrapping), a.sh1 = hx ---- */
+/*
+ * kr.c:44-52 is a forward stream with two read heads m bytes apart: hy = REHASH(y[j], y[j+m], hy) =
+ * ((hy - y[j]*d) << 1) + y[j+m] (kr.c:26).  The thread streams the LEADING head with 256-bit loads like the other
+ * forward automata; the trailing byte y[e-m] of step e comes out of the previous and the current vector, shifted by
+ * 32-m bytes once per 32 bytes (m <= 32).  For m >= 33 the reference's int d = 2^(m-1) has wrapped to 0 (kr.c:38)
+ * and the trailing head drops out of the arithmetic altogether (LAG = false).  The first window of a segment is the
+ * same recurrence with nothing to take out (kr.c:39-41), so the trailing bytes before the segment read as 0.
+ */
+__device__ __noinline__ unsigned kr_verify(const uint8_t *text, const uint8_t *pat, long long st, int m)
+{
+    int i = 0;
+    while (i < m && __ldg(pat + i) == __ldg(text + st + i)) i++;  // memcmp, kr.c:48
+    return i == m;
+}
+
+template <bool LAG>
 __global__ void __launch_bounds__(kTableThreads) table_kr_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ uint8_t raw_x[SB_XSIZE + 8];
-    stage_pattern_smem(raw_x, a);
-    __syncthreads();
-    const Smem<uint8_t> s_x(raw_x);
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
     if (lo < a.hi) {
+        const int m = a.m;
         const long long own_end = min(lo + a.seg, a.hi);
-        const unsigned d = a.lim, hx = (unsigned)a.sh1;
+        const long long end = own_end + m - 1;  // the leading head reads [lo, end)
+        const unsigned negd = 0u - a.lim, hx = (unsigned)a.sh1;
+        const int q = LAG ? (32 - m) >> 2 : 0;
+        const unsigned r8 = LAG ? 8u * ((32 - m) & 3) : 0u;
         unsigned hy = 0;
-        for (int i = 0; i < a.m; i++) hy = (hy << 1) + __ldg(a.text + lo + i);  // kr.c:37-40 for this segment's first window
-        for (long long j = lo; j < own_end; j++) {
-            if (hx == hy) {                                                      // kr.c:48
-                int i = 0;
-                while (i < a.m && s_x[i] == __ldg(a.text + j + i)) i++;
-                if (i == a.m) cnt++;
+        V8 P = {{0, 0, 0, 0, 0, 0, 0, 0}};
+        V8 C = ldg_stream256(a.text + lo);
+        for (long long j0 = lo; j0 < end; j0 += 32) {
+            const V8 N = ldg_stream256(a.text + j0 + 32);  // (at most 63 bytes past `end`: the back pad)
+            V8 L = {{0, 0, 0, 0, 0, 0, 0, 0}};
+            if (LAG) {  // L = the 32 bytes that start m before j0
+                uint32_t X[16];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    X[i] = P.w[i];
+                    X[8 + i] = C.w[i];
+                }
+#define SB_KR_LAG(Q)                                                                      \
+    case Q:                                                                               \
+        _Pragma("unroll") for (int i = 0; i < 8; i++) L.w[i] = __funnelshift_r(X[Q + i], X[Q + i + 1], r8); \
+        break;
+                switch (q) {
+                    SB_KR_LAG(0) SB_KR_LAG(1) SB_KR_LAG(2) SB_KR_LAG(3) SB_KR_LAG(4) SB_KR_LAG(5) SB_KR_LAG(6)
+                    default:
+#pragma unroll
+                        for (int i = 0; i < 8; i++) L.w[i] = __funnelshift_r(X[7 + i], X[8 + i], r8);
+                        break;
+                }
+#undef SB_KR_LAG
             }
-            hy = ((hy - __ldg(a.text + j) * d) << 1) + __ldg(a.text + j + a.m);  // REHASH, kr.c:26,49
+            unsigned hits = 0;
+#pragma unroll
+            for (int k = 0; k < 32; k++) {
+                const unsigned c = (C.w[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                if (LAG) {
+                    const unsigned l = (L.w[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                    hy = ((hy + l * negd) << 1) + c;  // REHASH, kr.c:26,49
+                } else {
+                    hy = (hy << 1) + c;               // d == 0
+                }
+                if (hy == hx) hits |= 1u << k;        // kr.c:48, the comparison after these 32 bytes
+            }
+            while (hits) {
+                const int k = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const long long st = j0 + k - m + 1;  // the window that ends at byte j0 + k
+                if (st >= lo && st < own_end) cnt += kr_verify(a.text, a.pat, st, m);
+            }
+            P = C;
+            C = N;
         }
     }
     table_reduce(a, cnt);
@@ -930,6 +988,135 @@ __global__ void __launch_bounds__(kTableThreads) table_ac_kernel(const __grid_co
             } else {
                 k = ell;
                 i = s_next[i];
+            }
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Zhu-Takaoka: table = bmGs[0..m) then ztBc[256][256] (read through L1/L2) ---- */
+__global__ void __launch_bounds__(kTableThreads) table_zt_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ int raw_gs[SB_XSIZE];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < a.m; i += kTableThreads) raw_gs[i] = a.table[i];
+    stage_pattern_smem(raw_x, a);
+    __syncthreads();
+    const Smem<int> s_gs(raw_gs);
+    const Smem<uint8_t> s_x(raw_x);
+    const int m = a.m;
+    const int32_t *zt = a.table + m;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        for (long long j = lo; j < own_end;) {  // zt.c:88-99
+            int i = m - 1;
+            while (i >= 0 && s_x[i] == __ldg(a.text + i + j)) --i;
+            if (i < 0) {
+                cnt++;
+                j += s_gs[0];
+            } else {  // (m == 1: every ztBc entry is <= 1 = bmGs[0]; the reference reads y[j-1] for it)
+                const int bc = m >= 2 ? __ldg(zt + __ldg(a.text + j + m - 2) * 256 + __ldg(a.text + j + m - 1)) : 1;
+                const int gs = s_gs[i];
+                j += gs > bc ? gs : bc;
+            }
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Skip Search on q-grams (skip3, skip5..8): table = next[0..m) then head[65536] (L1/L2); a.q = Q ---- */
+__global__ void __launch_bounds__(kTableThreads) table_skipq_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ int raw_next[SB_XSIZE];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < a.m; i += kTableThreads) raw_next[i] = a.table[i];
+    stage_pattern_smem(raw_x, a);
+    __syncthreads();
+    const Smem<int> s_next(raw_next);
+    const Smem<uint8_t> s_x(raw_x);
+    const int m = a.m, Q = a.q, mq = m - Q + 1;
+    const int32_t *head = a.table + m;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        // skip5.c:50-57: every mq-th position is sampled; an occurrence at h is met by the one sample in [h, h+mq),
+        // so the segment's own grid (from lo + mq - 1) finds every occurrence that starts in it
+        for (long long j = lo + mq - 1; j - (m - Q) < own_end; j += mq) {
+            unsigned h = 0;
+            if (Q == 3) {
+                h = ((unsigned)__ldg(a.text + j) << 4) + ((unsigned)__ldg(a.text + j + 1) << 2) + __ldg(a.text + j + 2);
+            } else {
+                for (int k = 0; k < Q; k++) h += (unsigned)__ldg(a.text + j + k) << (Q - 1 - k);
+            }
+            for (int e = __ldg(head + h); e >= 0; e = s_next[e]) {
+                const long long st = j - e;
+                if (st < lo || st >= own_end) continue;
+                int k = 0;
+                while (k < m && s_x[k] == __ldg(a.text + st + k)) k++;
+                cnt += k == m;
+            }
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Weak Factor Recognition (wfr, wfrq2..8): table = F as 65536 bits; a.q = Q (<= 1: wfr) ---- */
+__global__ void __launch_bounds__(kTableThreads) table_wfr_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ unsigned raw_F[2048];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 2048; i += kTableThreads) raw_F[i] = (unsigned)a.table[i];
+    stage_pattern_smem(raw_x, a);
+    __syncthreads();
+    const Smem<unsigned> s_F(raw_F);
+    const Smem<uint8_t> s_x(raw_x);
+    const int plen = a.m, Q = a.q;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    auto factor = [&](unsigned h) { return (s_F[(h & 0xffffu) >> 5] >> (h & 31u)) & 1u; };
+    auto whole = [&](long long st) {
+        int k = 0;
+        while (k < plen && s_x[k] == __ldg(a.text + st + k)) k++;
+        return k == plen;
+    };
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        if (Q <= 1) {  // wfr.c:73-92
+            const int m = plen;
+            long long j = lo + m - 1;
+            while (j - (m - 1) < own_end) {
+                unsigned h = __ldg(a.text + j);
+                const long long i = j - (m - 1);
+                unsigned test;
+                while ((test = factor(h)) && j > i) {
+                    j--;
+                    h = ((h << 2) + __ldg(a.text + j)) & 0xffffu;
+                }
+                if (j == i && test) cnt += whole(i);
+                j += m;
+            }
+        } else {  // wfrq4.c:80-100: the window is the pattern cut to a multiple of Q
+            const int m = plen - plen % Q;
+            auto gram = [&](long long pos) {
+                unsigned g = 0;
+                for (int k = 0; k < Q; k++) g += (unsigned)__ldg(a.text + pos - k) << (2 * (Q - 1 - k));
+                return g;
+            };
+            cnt += whole(lo);  // wfrq4.c:84: the first position is compared up front
+            long long j = lo + m;
+            while (j - m + 1 < own_end) {
+                unsigned h = gram(j) & 0xffffu;
+                const long long i = j - m + 1;
+                unsigned test;
+                while ((test = factor(h)) && j > i + Q - 1) {
+                    j -= Q;
+                    h = ((h << (2 * Q)) + gram(j)) & 0xffffu;
+                }
+                if (j == i + Q - 1 && test) cnt += whole(i);
+                j += m - Q + 1;
             }
         }
     }
