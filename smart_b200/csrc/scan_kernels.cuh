@@ -41,9 +41,6 @@ constexpr int kThreads = 256;       // threads per CTA
 #ifndef SB_MINB
 #define SB_MINB 1                   // __launch_bounds__ min CTAs/SM for the streaming kernels (tuning knob)
 #endif
-#ifndef SB_PROBE_ROUNDS
-#define SB_PROBE_ROUNDS 8               // candidate rounds in flight in the slow path of scan_block (tuning knob)
-#endif
 constexpr int kPadBytes = 8192;     // every text buffer is zero padded to a multiple of this plus this much
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -354,6 +351,29 @@ __device__ __forceinline__ uint32_t slot_fp(const uint32_t *s, int i)
  *   3. warp-cooperative: the survivors, in ascending order, are verified exactly; after a verified occurrence of a
  *      periodic pattern the rest of its run is counted arithmetically (extend_run) and everything up to the last
  *      occurrence of the run is settled (run_j). */
+/* Bit k set <=> the text word at byte jl + k + 4*widx equals x under `msk`, for the 32 consecutive start positions
+ * jl .. jl+31 (any alignment, jl may lie before local byte 0: the zeroed front pad).  Ten aligned words are loaded,
+ * realigned once by the dynamic byte offset, and the 32 windows come out of them at compile-time shifts. */
+__device__ __forceinline__ unsigned probe_mask32(const uint8_t *text, long long jl, int widx, uint32_t x, uint32_t msk)
+{
+    const long long b = jl + 4ll * widx;
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(text) + (b >> 2);  // (floor)
+    const unsigned sh = (unsigned)(b & 3) * 8u;
+    uint32_t T[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) T[i] = __ldg(p + i);
+    uint32_t R[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) R[i] = __funnelshift_r(T[i], T[i + 1], sh);
+    unsigned mk = 0;
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        const uint32_t w = (k & 3) == 0 ? R[k >> 2] : __funnelshift_r(R[k >> 2], R[(k >> 2) + 1], 8 * (k & 3));
+        mk |= (((w ^ x) & msk) == 0 ? 1u : 0u) << k;
+    }
+    return mk;
+}
+
 template <int B, int L, int GROUP>
 __device__ __noinline__ CandResult block_candidates(const ScanArgs &a, long long cbase, unsigned lane, long long run_j)
 {
@@ -378,59 +398,31 @@ __device__ __noinline__ CandResult block_candidates(const ScanArgs &a, long long
             }
         }
         // 2. probe words - only when candidates are DENSE.  A handful of candidates (the normal case) and the
-        //    candidates of a periodic pattern (runs) go straight to step 3 ("direct").  Otherwise round r looks at
-        //    vector r: lane l takes its slot l, so the 32 lanes probe 32 CONSECUTIVE start positions (coalesced
-        //    loads), NP rounds in flight.  survT is the transposed survivor map: bit r of lane l <=> slot l of
-        //    vector r survives.
+        //    candidates of a periodic pattern (runs) go straight to step 3 ("direct").  Otherwise every lane tests
+        //    one pattern word against ALL 32 of its slots at once: the slots of a lane are 32 consecutive start
+        //    positions, so their words are the 32 byte-shifted windows of ten text words (probe_mask32).  The most
+        //    selective word first - the one with the text's rarest byte, else the last one (the fingerprints sit at
+        //    the other end for prefix anchors) - and the next word only while some candidate of the chunk is
+        //    still alive (a warp vote): a text that looks like the pattern everywhere except in one place costs
+        //    one probe per chunk, not three per candidate.
         const bool direct = a.period != 0 || __reduce_add_sync(kFull, (unsigned)__popc(own)) <= 4u;
-        unsigned survT = 0;
         if (!direct) {
-            constexpr int NP = SB_PROBE_ROUNDS;
             const ProbeWords pw = probe_words(a, a.pat);
-            // The candidates of a lane are 32 bytes apart (j0 + 32r), so the word pointers and the funnel-shift
-            // amount are computed ONCE; a round costs two loads and a shift per probe word, no bounds check: reads
-            // before local byte 0 / past the text stay inside the buffer's zeroed pads (kPadBytes each side).
-            const long long j0 = cbase + (long long)lane - (B - 1) - a.anchor;  // slot l of vector 0
-            const uint32_t *pl = reinterpret_cast<const uint32_t *>(a.text) + (j0 >> 2) + pw.last;  // (floor shift)
-            const uint32_t *p1 = pl - pw.last + (pw.k1 > 0 ? pw.k1 : 0);
-            const uint32_t *p0 = pl - pw.last;
-            const unsigned sh = (unsigned)(j0 & 3) * 8u;
+            const long long jl = voff - (B - 1) - a.anchor;  // slot sl of this lane is the start position jl + sl
             const bool use1 = pw.k1 > 0 && pw.k1 < pw.last, use0 = pw.last > 0;
-            // rounds whose candidate of this lane is an owned start position not yet settled
-            const long long lo_j = run_j + 1 > 0 ? run_j + 1 : 0;
-            const int r_lo = j0 >= lo_j ? 0 : (int)((lo_j - j0 + 31) >> 5);
-            const int r_hi = j0 >= a.hi ? -1 : (int)min(31ll, (a.hi - 1 - j0) >> 5);
-#pragma unroll 1
-            for (int r0 = 0; r0 < 32; r0 += NP, pl += 8 * NP, p1 += 8 * NP, p0 += 8 * NP) {
-                unsigned mk[NP];
-                unsigned anyv = 0;
-#pragma unroll
-                for (int k = 0; k < NP; k++) {
-                    mk[k] = __shfl_sync(kFull, own, r0 + k);
-                    anyv |= mk[k];
-                }
-                if (!anyv) continue;  // (uniform)
-                uint32_t d[NP];
-#pragma unroll
-                for (int k = 0; k < NP; k++) {
-                    d[k] = (__funnelshift_r(__ldg(pl + 8 * k), __ldg(pl + 8 * k + 1), sh) ^ pw.xl) & a.tailmask;
-                    if (use1) d[k] |= (__funnelshift_r(__ldg(p1 + 8 * k), __ldg(p1 + 8 * k + 1), sh) ^ pw.x1) & pw.m1;
-                    if (use0) d[k] |= __funnelshift_r(__ldg(p0 + 8 * k), __ldg(p0 + 8 * k + 1), sh) ^ pw.x0;
-                }
-#pragma unroll
-                for (int k = 0; k < NP; k++)
-                    survT |= (d[k] == 0 && ((mk[k] >> lane) & 1u) && r0 + k >= r_lo && r0 + k <= r_hi ? 1u : 0u) << (r0 + k);
-            }
+            if (use1) own &= probe_mask32(a.text, jl, pw.k1, pw.x1, 0xffffffffu);
+            if (!use1 || __any_sync(kFull, own != 0)) own &= probe_mask32(a.text, jl, pw.last, pw.xl, a.tailmask);
+            if (use0 && __any_sync(kFull, own != 0)) own &= probe_mask32(a.text, jl, 0, pw.x0, 0xffffffffu);
         }
         // 3. exact verification of the survivors, vector by vector, slot by slot: ascending start positions
-        unsigned pending = direct ? __ballot_sync(kFull, own != 0) : __reduce_or_sync(kFull, survT);  // bit r: vector r
+        unsigned pending = __ballot_sync(kFull, own != 0);  // bit r: vector r
         while (pending) {
             const int src = __ffs(pending) - 1;
             pending &= pending - 1;
             const long long soff = cbase + src * 32;
             if (cbase + 1024 - B - a.anchor <= run_j) break;  // a counted run settled the rest of the chunk
             if (soff + 32 - B - a.anchor <= run_j) continue;
-            unsigned slots = direct ? __shfl_sync(kFull, own, src) : __ballot_sync(kFull, (survT >> src) & 1u);
+            unsigned slots = __shfl_sync(kFull, own, src);
             while (slots) {
                 const int sl = __ffs(slots) - 1;
                 slots &= slots - 1;
