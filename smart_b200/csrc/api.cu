@@ -1743,7 +1743,12 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
     case SB_FAM_SMITH: kind = 620; break;
     case SB_FAM_SKIP: kind = 621; break;
     case SB_FAM_FJS: kind = 622; break;
-    case SB_FAM_BNDMX: kind = (strcmp(desc->name, "sbndm2") == 0 && m <= SB_WORD) ? 616 : 0; break;  // (m > 32: the default mode)
+    case SB_FAM_BNDMX:
+        if (strcmp(desc->name, "sbndm2") == 0) kind = m <= SB_WORD ? 616 : 0;  // (m > 32: the default mode)
+        else if (strncmp(desc->name, "bndmq", 5) == 0) kind = 631;
+        else if (strcmp(desc->name, "fndm") == 0) kind = 632;
+        else if (strcmp(desc->name, "sbndm") == 0) kind = 633;
+        break;
     case SB_FAM_FACTOR: kind = strcmp(desc->name, "bom") == 0 ? 614 : strcmp(desc->name, "ebom") == 0 ? 615 : 0; break;
     default: break;
     }
@@ -1827,6 +1832,24 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         sb_prep_bmgs(x, m, scratch, table + 256);
         ntable = 256 + m;
         break;
+    case 631:
+        qq = desc->min_m;  // the q-gram length is the family's smallest m (bndmq2.c:35)
+        sb_prep_bndm(x, m, reinterpret_cast<unsigned int *>(table));
+        break;
+    case 632: {
+        const int k = m < SB_WORD ? m : SB_WORD;
+        sb_prep_so(x, m, reinterpret_cast<unsigned int *>(table));  // fndm.c:36-37 == the masks of so.c:27-38
+        lim = ~0u << (k - 1);                                         // NEG0m1, fndm.c:39
+        break;
+    }
+    case 633: {
+        const int k = m < SB_WORD ? m : SB_WORD;
+        sb_prep_bndm(x, m, reinterpret_cast<unsigned int *>(table));
+        for (int c = 0; c < 256; c++) table[c] = (int)((unsigned)table[c] << (SB_WORD - k));  // sbndm.c:42
+        sb_prep_mp(x, k, scratch);
+        sh1 = k - scratch[k];  // restore[0] (sbndm.c:44-55): the smallest period of the (32-character) window
+        break;
+    }
     case 628:
         sb_prep_bmgs(x, m, scratch, table);
         sb_prep_ztbc(x, m, table + m);
@@ -1963,6 +1986,13 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         case 626: sb::table_tbm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 627: sb::table_ac_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 628: sb::table_zt_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 631:
+            if (qq == 2) sb::table_bndmq_kernel<2><<<grid, sb::kTableThreads, 0, c->stream>>>(a);
+            else if (qq == 4) sb::table_bndmq_kernel<4><<<grid, sb::kTableThreads, 0, c->stream>>>(a);
+            else sb::table_bndmq_kernel<6><<<grid, sb::kTableThreads, 0, c->stream>>>(a);
+            break;
+        case 632: sb::table_fndm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 633: sb::table_sbndm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 629: sb::table_skipq_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 630: sb::table_wfr_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         default: sb::table_qf_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;

@@ -46,6 +46,9 @@
  *   tbm          bmBc[256] + bmGs[0..m) (tbm.c:66-111): Turbo-BM, the factor matched by the previous attempt is
  *                remembered (u) and jumped over; a segment starts with u = 0 like the text does
  *   ac           kmpNext[0..m] + ell (ac.c:44-86): Apostolico-Crochemore
+ *   bndmq2/4/6   B[256] (bndm.c:33-38): the window's last q characters at once, then right to left (bndmq2.c:59-73)
+ *   fndm         the Shift-Or masks driving a forward factor scan from the window's last character (fndm.c:44-57)
+ *   sbndm        B[256] aligned to the top of the word + the pattern's period as the shift (sbndm.c:44-83)
  *   zt           ztBc[256][256] (zt.c:64-74, 256 KiB through L1/L2) + bmGs[0..m): BM with a two-character shift
  *   skip3/5..8   q-gram buckets head[65536] + next[m] (skip5.c:36-45): every (m-Q+1)-th text q-gram selects the
  *                alignments to compare (skip5.c:50-57)
@@ -1117,6 +1120,125 @@ __global__ void __launch_bounds__(kTableThreads) table_wfr_kernel(const __grid_c
                 }
                 if (j == i + Q - 1 && test) cnt += whole(i);
                 j += m - Q + 1;
+            }
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- bit-parallel window scans of the BNDM family: table = B[256] over the first k = min(m, 32) characters ---- */
+/* the whole pattern at one start position (the comparison the reference makes up front and, for m > 32, after its
+ * 32-character prefix automaton reports a window) */
+__device__ __noinline__ unsigned whole_pattern(const uint8_t *text, const uint8_t *pat, long long st, int m)
+{
+    int i = 0;
+    while (i < m && __ldg(pat + i) == __ldg(text + st + i)) i++;
+    return i == m;
+}
+
+/* BNDM with q-grams (bndmq2.c:31-71, search_large :79-127; bndmq4.c, bndmq6.c): B as in bndm.c.  The window's last
+ * Q characters are read at once (GRAMq); while factors survive, one more character to the left; a set top bit is a
+ * pattern prefix - the whole window when the scan stands at its first character, else the next window starts there */
+template <int Q>
+__global__ void __launch_bounds__(kTableThreads) table_bndmq_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ unsigned raw_B[256];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_B[i] = (unsigned)a.table[i];
+    __syncthreads();
+    const Smem<unsigned> s_B(raw_B);
+    const int m = a.m, k = m < SB_WORD ? m : SB_WORD;
+    const unsigned M = 1u << (k - 1);
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        cnt += whole_pattern(a.text, a.pat, lo, m);  // bndmq2.c:57: position 0 is compared up front
+        long long i = lo + k + 1 - Q;
+        while (i - (k - Q) < own_end) {               // bndmq2.c:59-73
+            unsigned D = s_B[__ldg(a.text + i)];
+#pragma unroll
+            for (int t = 1; t < Q; t++) D &= s_B[__ldg(a.text + i + t)] << t;
+            if (D != 0) {
+                long long j = i;
+                const long long first = i - (k - Q);
+                do {
+                    if (D >= M) {
+                        if (j > first) i = j - 1;
+                        else if (first < own_end) cnt += m > SB_WORD ? whole_pattern(a.text, a.pat, first, m) : 1u;
+                    }
+                    j--;
+                    D = (D << 1) & s_B[__ldg(a.text + j)];
+                } while (D != 0);
+            }
+            i += k - Q + 1;
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* Forward NDM (fndm.c:28-60, search_large :68-104): the Shift-Or masks (bit j clear <=> x[j] == c, so.c:27-38)
+ * drive a FORWARD factor scan from the window's last character; a clear top bit is a pattern suffix ending here and
+ * the window is compared; when no factor survives the scan jumps m (k) ahead.  table = S[256], a.lim = ~0 << (k-1) */
+__global__ void __launch_bounds__(kTableThreads) table_fndm_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ unsigned raw_S[256];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_S[i] = (unsigned)a.table[i];
+    __syncthreads();
+    const Smem<unsigned> s_S(raw_S);
+    const int m = a.m, k = m < SB_WORD ? m : SB_WORD;
+    const unsigned top = a.lim;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        long long i = lo + k - 1;
+        while (i - (k - 1) < own_end) {  // fndm.c:44-57
+            unsigned D = s_S[__ldg(a.text + i)];
+            while (D != ~0u && i - (k - 1) < own_end) {  // (windows that start at own_end or later are not this segment's)
+                if (D < top) cnt += whole_pattern(a.text, a.pat, i - k + 1, m);
+                i++;
+                D = (D << 1) | s_S[__ldg(a.text + i)];
+            }
+            i += k;
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* Simplified BNDM (sbndm.c:28-84, search_large :92-146): B aligned to the top of the word, the window read right to
+ * left until the factor dies or its first character is reached; after an occurrence the shift is the pattern's
+ * period (sbndm.c:44-55 `restore[0]`).  table = B[256] (top aligned), a.sh1 = shift */
+__global__ void __launch_bounds__(kTableThreads) table_sbndm_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ unsigned raw_B[256];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_B[i] = (unsigned)a.table[i];
+    __syncthreads();
+    const Smem<unsigned> s_B(raw_B);
+    const int m = a.m, k = m < SB_WORD ? m : SB_WORD, shift = a.sh1;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        cnt += whole_pattern(a.text, a.pat, lo, m);  // sbndm.c:61
+        long long i = lo + k;                         // the window's last character
+        while (i - k + 1 < own_end) {                 // sbndm.c:63-83 (bounded by the segment, not by the sentinel)
+            unsigned D = s_B[__ldg(a.text + i)];
+            if (m > SB_WORD && D == 0) {              // search_large's skip loop, sbndm.c:128
+                i += k;
+                continue;
+            }
+            long long j = i - 1;
+            const long long first = i - k + 1;
+            for (;;) {
+                D = (D << 1) & s_B[__ldg(a.text + j)];
+                if (!((j - first) && D)) break;
+                j--;
+            }
+            if (D != 0) {
+                cnt += m > SB_WORD ? whole_pattern(a.text, a.pat, first, m) : 1u;
+                i += shift;
+            } else {
+                i = j + k;
             }
         }
     }
