@@ -185,26 +185,30 @@ __device__ __forceinline__ void stream_segment(const uint8_t *text, long long lo
 /* ---- Knuth-Morris-Pratt / Morris-Pratt: table = kmpNext[0..m] or mpNext[0..m] ---- */
 __global__ void __launch_bounds__(kTableThreads) table_kmp_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ int raw_next[SB_XSIZE + 1];
-    __shared__ uint8_t raw_x[SB_XSIZE + 8];
-    for (int i = threadIdx.x; i <= a.m; i += kTableThreads) raw_next[i] = a.table[i];
-    stage_pattern_smem(raw_x, a);
+    // one shared-memory word per pattern position: x[i] in the high half, kmpNext[i] (>= -1) in the low half, so a
+    // step of the failure loop is ONE lookup on the dependency chain instead of two
+    __shared__ unsigned raw_xn[SB_XSIZE + 1];
+    for (int i = threadIdx.x; i < a.m; i += kTableThreads)
+        raw_xn[i] = ((unsigned)a.pat[i] << 16) | ((unsigned)a.table[i] & 0xffffu);
     __syncthreads();
-    const Smem<int> s_next(raw_next);
-    const Smem<uint8_t> s_x(raw_x);
+    const Smem<unsigned> s_xn(raw_xn);
     const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
     unsigned cnt = 0;
     if (lo < a.hi) {
         const long long own_end = min(lo + a.seg, a.hi);   // starts [lo, own_end)
         const long long end = own_end + a.m - 1;           // text bytes [lo, end)
         int i = 0;
-        const int m = a.m;
+        const int m = a.m, next_m = __ldg(a.table + a.m);
         stream_segment(a.text, lo, end, [&](unsigned c, long long, int) {
-            while (i > -1 && (unsigned)s_x[i] != c) i = s_next[i];  // kmp.c:57-58
+            while (i > -1) {                                // kmp.c:57-58: while (i > -1 && x[i] != y[j]) i = kmpNext[i]
+                const unsigned v = s_xn[i];
+                if ((v >> 16) == c) break;
+                i = (int)(short)(v & 0xffffu);
+            }
             i++;
-            if (i >= m) {                                           // kmp.c:61-64: OUTPUT(j - i) with j already advanced
-                cnt++;                                              // the start j+1-m is >= lo (i began at 0) and < own_end
-                i = s_next[i];
+            if (i >= m) {                                   // kmp.c:61-64: OUTPUT(j - i) with j already advanced
+                cnt++;                                      // the start j+1-m is >= lo (i began at 0) and < own_end
+                i = next_m;
             }
         });
     }
