@@ -1743,13 +1743,19 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
     case SB_FAM_SMITH: kind = 620; break;
     case SB_FAM_SKIP: kind = 621; break;
     case SB_FAM_FJS: kind = 622; break;
+    case SB_FAM_BF: kind = strcmp(desc->name, "ts") == 0 ? 634 : 0; break;  // (bf itself IS the default mode)
+    case SB_FAM_KMPSKIP: kind = 635; break;
     case SB_FAM_BNDMX:
         if (strcmp(desc->name, "sbndm2") == 0) kind = m <= SB_WORD ? 616 : 0;  // (m > 32: the default mode)
         else if (strncmp(desc->name, "bndmq", 5) == 0) kind = 631;
         else if (strcmp(desc->name, "fndm") == 0) kind = 632;
         else if (strcmp(desc->name, "sbndm") == 0) kind = 633;
         break;
-    case SB_FAM_FACTOR: kind = strcmp(desc->name, "bom") == 0 ? 614 : strcmp(desc->name, "ebom") == 0 ? 615 : 0; break;
+    case SB_FAM_FACTOR:
+        if (strcmp(desc->name, "bom") == 0) kind = 614;
+        else if (strcmp(desc->name, "ebom") == 0 || strcmp(desc->name, "sebom") == 0) kind = 615;  // sebom.c:61-77 is ebom.c:62-78
+        else if (strcmp(desc->name, "bom2") == 0) kind = 636;
+        break;
     default: break;
     }
     if (!kind) return -100;
@@ -1795,6 +1801,7 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         sb_prep_automaton(x, m, reinterpret_cast<unsigned short *>(table));
         ntable = ((m + 1) * 256 + 1) / 2;
         break;
+    case 636:
     case 614: {  // (m+1) x 256 16-bit transitions, then m+1 terminal flags
         short *tr = reinterpret_cast<short *>(table);
         sb_prep_bom(x, m, tr, reinterpret_cast<unsigned char *>(tr + (size_t)(m + 1) * 256));
@@ -1831,6 +1838,16 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         sb_prep_hbc(x, m, table);
         sb_prep_bmgs(x, m, scratch, table + 256);
         ntable = 256 + m;
+        break;
+    case 634:
+        ntable = 1;
+        table[0] = 0;
+        break;
+    case 635:
+        sb_prep_mp(x, m, table);
+        sb_prep_kmp(x, m, table, table + m + 1);
+        sb_prep_buckets(x, m, table + 2 * (m + 1), table + 2 * (m + 1) + 256);
+        ntable = 2 * (m + 1) + 256 + m;
         break;
     case 631:
         qq = desc->min_m;  // the q-gram length is the family's smallest m (bndmq2.c:35)
@@ -1971,7 +1988,8 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
             sb::table_aut_kernel<<<grid, sb::kTableThreads, dyn, c->stream>>>(a);
             break;
         }
-        case 614: sb::table_bom_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 614: sb::table_bom_kernel<false><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 636: sb::table_bom_kernel<true><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 615: sb::table_ebom_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 616: sb::table_sbndm2_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 617: sb::table_bndm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
@@ -1992,6 +2010,8 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
             else sb::table_bndmq_kernel<6><<<grid, sb::kTableThreads, 0, c->stream>>>(a);
             break;
         case 632: sb::table_fndm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 634: sb::table_ts_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 635: sb::table_kmpskip_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 633: sb::table_sbndm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 629: sb::table_skipq_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 630: sb::table_wfr_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;

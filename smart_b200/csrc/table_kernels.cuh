@@ -49,6 +49,8 @@
  *   bndmq2/4/6   B[256] (bndm.c:33-38): the window's last q characters at once, then right to left (bndmq2.c:59-73)
  *   fndm         the Shift-Or masks driving a forward factor scan from the window's last character (fndm.c:44-57)
  *   sbndm        B[256] aligned to the top of the word + the pattern's period as the shift (sbndm.c:44-83)
+ *   ts           no table: Tailed-Substring's two probing phases over the pattern in shared memory (ts.c:25-59)
+ *   kmpskip      mpNext, kmpNext and the character buckets z[256] / list[m] (kmpskip.c:59-146), 16-bit entries
  *   zt           ztBc[256][256] (zt.c:64-74, 256 KiB through L1/L2) + bmGs[0..m): BM with a two-character shift
  *   skip3/5..8   q-gram buckets head[65536] + next[m] (skip5.c:36-45): every (m-Q+1)-th text q-gram selects the
  *                alignments to compare (skip5.c:50-57)
@@ -535,6 +537,7 @@ __global__ void __launch_bounds__(kTableThreads) table_aut_kernel(const __grid_c
 
 /* ---- Backward Oracle Matching: table = trans as 16-bit entries ((m+1) rows of 256), then m+1 terminal bytes ---- */
 constexpr int kBomSharedRows = 94;
+template <bool BOM2>  // bom2.c:58-75: the same oracle without the terminal flags, shift = what was left unread (+1 on a match)
 __global__ void __launch_bounds__(kTableThreads) table_bom_kernel(const __grid_constant__ TableArgs a)
 {
     __shared__ short raw_trans[kBomSharedRows * 256];
@@ -559,11 +562,16 @@ __global__ void __launch_bounds__(kTableThreads) table_bom_kernel(const __grid_c
             int i = m - 1, r = m, shift = m, period = m, q;
             while (i >= 0 && (q = small ? s_trans[r * 256 + __ldg(a.text + i + j)] : __ldg(gtrans + r * 256 + __ldg(a.text + i + j))) >= 0) {
                 r = q;
-                if (small ? s_term[r] : __ldg(gterm + r)) {
+                if (!BOM2 && (small ? s_term[r] : __ldg(gterm + r))) {
                     period = shift;
                     shift = i;
                 }
                 --i;
+            }
+            if (BOM2) {           // bom2.c:69-73
+                cnt += i < 0;
+                j += i < 0 ? 1 : i + 1;
+                continue;
             }
             if (i < 0) {
                 cnt++;
@@ -1243,6 +1251,126 @@ __global__ void __launch_bounds__(kTableThreads) table_sbndm_kernel(const __grid
                 i += shift;
             } else {
                 i = j + k;
+            }
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Tailed-Substring (ts.c:25-59): no table, the pattern in shared memory ---- */
+/* phase 1 probes pattern position i and looks for the position whose previous equal character is furthest away
+ * (dim, k); phase 2 keeps probing position k and shifts by dim.  Every segment runs both phases from scratch, as
+ * the reference does from the start of the text. */
+__global__ void __launch_bounds__(kTableThreads) table_ts_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    stage_pattern_smem(raw_x, a);
+    __syncthreads();
+    const Smem<uint8_t> s_x(raw_x);
+    const int m = a.m;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    auto whole = [&](long long st) {
+        int j = 0;
+        while (j < m && s_x[j] == __ldg(a.text + st + j)) j++;
+        return j == m;
+    };
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        long long s = lo;
+        int i = m - 1, k = m - 1, dim = 1;
+        while (s < own_end && i - dim >= 0) {  // ts.c:33-47
+            if (s_x[i] != __ldg(a.text + s + i)) {
+                s++;
+            } else {
+                cnt += whole(s);
+                int h = i - 1;
+                const unsigned xi = s_x[i];
+                while (h >= 0 && s_x[h] != xi) h--;
+                if (dim < i - h) {
+                    k = i;
+                    dim = i - h;
+                }
+                s += i - h;
+                i--;
+            }
+        }
+        const unsigned xk = s_x[k];
+        while (s < own_end) {                  // ts.c:49-57
+            if (xk != __ldg(a.text + s + k)) {
+                s++;
+            } else {
+                cnt += whole(s);
+                s += dim;
+            }
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- KMP-Skip-Search (kmpskip.c:59-146): table = mpNext[0..m], kmpNext[0..m], z[256], list[0..m) ---- */
+/* staged as 16-bit entries (every value lies in [-1, m]) */
+__global__ void __launch_bounds__(kTableThreads) table_kmpskip_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ short raw_mp[SB_XSIZE + 1];
+    __shared__ short raw_kmp[SB_XSIZE + 1];
+    __shared__ short raw_list[SB_XSIZE];
+    __shared__ short raw_z[256];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    const int m = a.m;
+    for (int i = threadIdx.x; i <= m; i += kTableThreads) {
+        raw_mp[i] = (short)a.table[i];
+        raw_kmp[i] = (short)a.table[m + 1 + i];
+    }
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_z[i] = (short)a.table[2 * (m + 1) + i];
+    for (int i = threadIdx.x; i < m; i += kTableThreads) raw_list[i] = (short)a.table[2 * (m + 1) + 256 + i];
+    stage_pattern_smem(raw_x, a);
+    __syncthreads();
+    const Smem<short> s_mp(raw_mp), s_kmp(raw_kmp), s_list(raw_list), s_z(raw_z);
+    const Smem<uint8_t> s_x(raw_x);
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        const long long nn = own_end + m - 1;  // text bytes the segment's windows may touch: [lo, nn)
+        const int per = m - s_kmp[m];
+        long long j = lo - 1, start, wall = lo, kmpStart;
+        int i = -1, k;
+        // kmpskip.c:83-90 / :104-111 / :121-128: the next sampled character whose bucket is not empty
+        auto next_bucket = [&]() {
+            do {
+                j += m;
+            } while (j < nn && s_z[__ldg(a.text + j)] < 0);
+            if (j >= nn) return false;
+            i = s_z[__ldg(a.text + j)];
+            return true;
+        };
+        bool more = next_bucket();
+        start = j - i;
+        while (more && start < own_end) {  // kmpskip.c:92-143
+            if (start > wall) wall = start;
+            k = (int)(wall - start);
+            while (k < m && s_x[k] == __ldg(a.text + k + start)) ++k;
+            wall = start + k;
+            if (k == m) {
+                cnt += start >= lo;  // (a candidate left of the segment belongs to the previous thread)
+                i -= per;
+            } else {
+                i = s_list[i];
+            }
+            if (i < 0 && !(more = next_bucket())) break;
+            kmpStart = start + k - s_kmp[k];
+            k = s_kmp[k];
+            start = j - i;
+            while (start < kmpStart || (kmpStart < start && start < wall)) {
+                if (start < kmpStart) {
+                    i = s_list[i];
+                    if (i < 0 && !(more = next_bucket())) break;
+                    start = j - i;
+                } else {
+                    kmpStart += k - s_mp[k];
+                    k = s_mp[k];
+                }
             }
         }
     }
