@@ -1728,7 +1728,13 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
     case SB_FAM_GRASPM: kind = 625; break;
     case SB_FAM_TBM: kind = 626; break;
     case SB_FAM_AC: kind = 627; break;
-    case SB_FAM_BADCHAR: kind = strcmp(desc->name, "zt") == 0 ? 628 : 0; break;
+    case SB_FAM_BADCHAR:
+        if (strcmp(desc->name, "zt") == 0) kind = 628;
+        else if (strcmp(desc->name, "iom") == 0) kind = 637;
+        else if (strcmp(desc->name, "qlqs") == 0) kind = 638;
+        else if (strcmp(desc->name, "tsw") == 0) kind = 639;
+        else if (strcmp(desc->name, "tvsbs-w2") == 0) kind = 640;
+        break;
     case SB_FAM_SKIPQ: kind = 629; break;
     case SB_FAM_WFR:  // the scans restated so far: wfr (wfr.c) and wfrq2..8 (wfrq4.c)
         kind = (strcmp(desc->name, "wfr") == 0 || strncmp(desc->name, "wfrq", 4) == 0) ? 630 : 0;
@@ -1839,6 +1845,39 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         sb_prep_bmgs(x, m, scratch, table + 256);
         ntable = 256 + m;
         break;
+    case 637: {  // iom.c:36-41: the look-ahead distance after a last-character match / mismatch, and their tables
+        int step1 = 2 * m - 1, step2 = 2 * m - 1;
+        for (int i = 0; i < m - 1; i++) {
+            if (x[i] == x[m - 1]) step1 = 2 * m - i - 2;
+            else step2 = 2 * m - i - 2;
+        }
+        for (int t = 0; t < 2; t++) {
+            const int step = t ? step2 : step1;
+            for (int c = 0; c < 256; c++) table[256 * t + c] = step + 1;
+            for (int i = 0; i < m; i++) table[256 * t + x[i]] = step - i;
+        }
+        qq = step1;
+        sh1 = step2;
+        ntable = 512;
+        break;
+    }
+    case 638: {  // qlqs.c:45-48
+        static thread_local unsigned char rev[SB_XSIZE];
+        for (int i = 0; i < m; i++) rev[i] = x[m - 1 - i];
+        sb_prep_qsbc(x, m, table);
+        sb_prep_qsbc(rev, m, table + 256);
+        ntable = 512;
+        break;
+    }
+    case 639:
+    case 640: {  // tsw.c:52-53, tvsbs-w2.c:44-47
+        static thread_local unsigned char rev[SB_XSIZE];
+        for (int i = 0; i < m; i++) rev[i] = x[m - 1 - i];
+        sb_prep_brbc(x, m, table);
+        sb_prep_brbc(rev, m, table + 65536);
+        ntable = 131072;
+        break;
+    }
     case 634:
         ntable = 1;
         table[0] = 0;
@@ -2011,6 +2050,10 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
             break;
         case 632: sb::table_fndm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 634: sb::table_ts_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 637: sb::table_iom_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 638: sb::table_qlqs_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 639: sb::table_br2_kernel<false><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 640: sb::table_br2_kernel<true><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 635: sb::table_kmpskip_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 633: sb::table_sbndm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 629: sb::table_skipq_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;

@@ -49,6 +49,9 @@
  *   bndmq2/4/6   B[256] (bndm.c:33-38): the window's last q characters at once, then right to left (bndmq2.c:59-73)
  *   fndm         the Shift-Or masks driving a forward factor scan from the window's last character (fndm.c:44-57)
  *   sbndm        B[256] aligned to the top of the word + the pattern's period as the shift (sbndm.c:44-83)
+ *   iom          ibc1[256], ibc2[256] and the two look-ahead distances (iom.c:28-41)
+ *   qlqs         qsBc of the pattern and of its reverse: the Quick-Search shift or a leap of m + m/2 (qlqs.c:52-57)
+ *   tsw, tvsbs-w2  brBc of the pattern and of its reverse: one window moves up, one moves down (tsw.c:58-68)
  *   ts           no table: Tailed-Substring's two probing phases over the pattern in shared memory (ts.c:25-59)
  *   kmpskip      mpNext, kmpNext and the character buckets z[256] / list[m] (kmpskip.c:59-146), 16-bit entries
  *   zt           ztBc[256][256] (zt.c:64-74, 256 KiB through L1/L2) + bmGs[0..m): BM with a two-character shift
@@ -1372,6 +1375,103 @@ __global__ void __launch_bounds__(kTableThreads) table_kmpskip_kernel(const __gr
                     k = s_mp[k];
                 }
             }
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Improved Occurrence Matcher (iom.c:28-56): table = ibc1[256], ibc2[256]; a.q = step1, a.sh1 = step2 ---- */
+/* the shift is read from the character `step` positions ahead - up to m-1 behind the window; past the text that is
+ * the zero pad, which can only concern windows that do not lie inside the text */
+__global__ void __launch_bounds__(kTableThreads) table_iom_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ int raw_ibc[512];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 512; i += kTableThreads) raw_ibc[i] = a.table[i];
+    stage_pattern_smem(raw_x, a);
+    __syncthreads();
+    const Smem<int> s_ibc(raw_ibc);
+    const Smem<uint8_t> s_x(raw_x);
+    const int m = a.m, step1 = a.q, step2 = a.sh1;
+    const unsigned last_ch = s_x[m - 1];
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        for (long long s = lo; s < own_end;) {  // iom.c:44-53
+            if (last_ch == __ldg(a.text + s + m - 1)) {
+                int i = 0;
+                while (i < m && s_x[i] == __ldg(a.text + s + i)) i++;
+                cnt += i == m;
+                s += s_ibc[__ldg(a.text + s + step1)];
+            } else {
+                s += s_ibc[256 + __ldg(a.text + s + step2)];
+            }
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Quantum-Leap Quick-Search (qlqs.c:38-62): table = qsBc of x, then qsBc of the reversed x ---- */
+__global__ void __launch_bounds__(kTableThreads) table_qlqs_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ int raw_qs[512];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 512; i += kTableThreads) raw_qs[i] = a.table[i];
+    stage_pattern_smem(raw_x, a);
+    __syncthreads();
+    const Smem<int> s_qs(raw_qs);
+    const Smem<uint8_t> s_x(raw_x);
+    const int m = a.m, z = m + m / 2;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        for (long long i = lo; i < own_end;) {  // qlqs.c:52-57
+            int k = 0;
+            while (k < m && s_x[k] == __ldg(a.text + i + k)) k++;
+            cnt += k == m;
+            const int f = s_qs[__ldg(a.text + i + m)], b = s_qs[256 + __ldg(a.text + i + z - 1)];
+            i += f > z - b ? z : f;
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- two-ended Berry-Ravindran scans: table = brBc of x, then brBc of the reversed x (2 x 256 KiB, L1/L2) ---- */
+/* tsw.c:40-71 and tvsbs-w2.c:36-71 move one window up from the start and one down from the end until they cross;
+ * a segment does that between its own first and last start position.  tvsbs-w2 looks at the first and last
+ * character of both windows before comparing (:57-58). */
+template <bool TVSBS>
+__global__ void __launch_bounds__(kTableThreads) table_br2_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    stage_pattern_smem(raw_x, a);
+    __syncthreads();
+    const Smem<uint8_t> s_x(raw_x);
+    const int m = a.m;
+    const int32_t *L = a.table, *R = a.table + 65536;
+    const unsigned first_ch = s_x[0], last_ch = s_x[m - 1];
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    auto whole = [&](long long st) {
+        int i = 0;
+        while (i < m && s_x[i] == __ldg(a.text + st + i)) i++;
+        return i == m;
+    };
+    if (lo < a.hi) {
+        long long j = lo, e = min(lo + a.seg, a.hi) - 1;  // the first and the last start position of the segment
+        while (j <= e) {
+            bool look = true;
+            if (TVSBS)
+                look = (first_ch == __ldg(a.text + j) || first_ch == __ldg(a.text + e)) &&
+                       (last_ch == __ldg(a.text + j + m - 1) || last_ch == __ldg(a.text + e + m - 1));
+            if (look) {
+                cnt += whole(j);
+                if (j < e) cnt += whole(e);
+            }
+            j += __ldg(L + __ldg(a.text + j + m) * 256 + __ldg(a.text + j + m + 1));
+            e -= __ldg(R + __ldg(a.text + e - 1) * 256 + __ldg(a.text + e - 2));
         }
     }
     table_reduce(a, cnt);
