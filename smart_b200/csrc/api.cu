@@ -1736,8 +1736,8 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         else if (strcmp(desc->name, "tvsbs-w2") == 0) kind = 640;
         break;
     case SB_FAM_SKIPQ: kind = 629; break;
-    case SB_FAM_WFR:  // the scans restated so far: wfr (wfr.c) and wfrq2..8 (wfrq4.c)
-        kind = (strcmp(desc->name, "wfr") == 0 || strncmp(desc->name, "wfrq", 4) == 0) ? 630 : 0;
+    case SB_FAM_WFR:  // wfr (wfr.c), wfrq2..8 (wfrq4.c) and wfr2..8 (wfr4.c: wfrq's scan over wfr's table); not twfr*, lwfr*
+        kind = (strncmp(desc->name, "wfr", 3) == 0 || strncmp(desc->name, "twfr", 4) == 0) ? 630 : 0;  // (twfr*: + the skip loop)
         break;
     case SB_FAM_RAITA: kind = 609; break;
     case SB_FAM_TUNEDBM: kind = 610; break;
@@ -1918,8 +1918,10 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         break;
     case 630: {
         static thread_local unsigned char F[65536];
-        qq = desc->Q;
-        sb_prep_wfr(x, qq > 1 ? m - m % qq : m, qq, F);  // wfrq4.c:75: the table is built over the cut pattern
+        // characters per scan step: 1 for wfr, Q for wfrqQ and for wfrQ (whose registry Q is 0: wfr's table builder)
+        qq = (strcmp(desc->name, "wfr") == 0 || strcmp(desc->name, "twfr") == 0) ? 1 : desc->min_m;
+        sh1 = desc->name[0] == 't';  // twfr.c:57, twfr4.c:63-66: the tuned variants skip windows whose last gram is no factor
+        sb_prep_wfr(x, qq > 1 ? m - m % qq : m, desc->Q, F);  // wfrq4.c:75, wfr4.c:70: built over the cut pattern
         for (int i = 0; i < 2048; i++) {
             unsigned w = 0;
             for (int b = 0; b < 32; b++) w |= (unsigned)(F[i * 32 + b] != 0) << b;

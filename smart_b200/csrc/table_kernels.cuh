@@ -57,7 +57,7 @@
  *   zt           ztBc[256][256] (zt.c:64-74, 256 KiB through L1/L2) + bmGs[0..m): BM with a two-character shift
  *   skip3/5..8   q-gram buckets head[65536] + next[m] (skip5.c:36-45): every (m-Q+1)-th text q-gram selects the
  *                alignments to compare (skip5.c:50-57)
- *   wfr, wfrq2..8  the weak-factor bit table F (wfr.c:41-58, wfrq4.c:50-65; 65536 bits = 8 KiB of shared memory):
+ *   wfr*, wfrq*, twfr*, twfrq*  the weak-factor bit table F (wfr.c:41-58, wfrq4.c:50-65; 65536 bits = 8 KiB of shared memory):
  *                the window is hashed right to left while the hash is some pattern factor's (wfr.c:73-92)
  *
  * Parallelisation: the scan loops are inherently sequential, so the text is cut into segments of `seg` start
@@ -1081,7 +1081,7 @@ __global__ void __launch_bounds__(kTableThreads) table_skipq_kernel(const __grid
     table_reduce(a, cnt);
 }
 
-/* ---- Weak Factor Recognition (wfr, wfrq2..8): table = F as 65536 bits; a.q = Q (<= 1: wfr) ---- */
+/* ---- Weak Factor Recognition (wfr, wfrq2..8, wfr2..8 and the tuned twfr*): table = F as 65536 bits; a.q = characters per step ---- */
 __global__ void __launch_bounds__(kTableThreads) table_wfr_kernel(const __grid_constant__ TableArgs a)
 {
     __shared__ unsigned raw_F[2048];
@@ -1107,6 +1107,12 @@ __global__ void __launch_bounds__(kTableThreads) table_wfr_kernel(const __grid_c
             long long j = lo + m - 1;
             while (j - (m - 1) < own_end) {
                 unsigned h = __ldg(a.text + j);
+                if (a.sh1) {  // twfr.c:57: while (!F[y[j]]) j += m - bounded by the segment instead of the sentinel
+                    while (!factor(h) && j + m - (m - 1) < own_end) {
+                        j += m;
+                        h = __ldg(a.text + j);
+                    }
+                }
                 const long long i = j - (m - 1);
                 unsigned test;
                 while ((test = factor(h)) && j > i) {
@@ -1127,6 +1133,12 @@ __global__ void __launch_bounds__(kTableThreads) table_wfr_kernel(const __grid_c
             long long j = lo + m;
             while (j - m + 1 < own_end) {
                 unsigned h = gram(j) & 0xffffu;
+                if (a.sh1) {  // twfr4.c:63-66
+                    while (!factor(h) && j + (m - Q + 1) - m + 1 < own_end) {
+                        j += m - Q + 1;
+                        h = gram(j) & 0xffffu;
+                    }
+                }
                 const long long i = j - m + 1;
                 unsigned test;
                 while ((test = factor(h)) && j > i + Q - 1) {
