@@ -1993,7 +1993,18 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         a.counters = c->cnt_dev(kSyncSlot);
         a.hi = hi;
         a.m = m;
-        a.seg = m <= 1024 ? 4096 : 16384;  // start positions per thread; each thread also reads the m-1 bytes behind them
+        // start positions per thread; each thread also reads the m-1 bytes behind them.  4 KiB / 16 KiB keep that
+        // halo small on a text that fills the device; a short text (the corpus buffers are 1-6 MiB) is cut finer so
+        // that there are threads for every SM and a thread's sequential walk is short: down to 64 positions
+        a.seg = m <= 1024 ? 4096 : 16384;
+        {
+            const long long want_threads = 148ll * 4 * sb::kTableThreads;
+            long long fine = (hi / want_threads + 63) / 64 * 64;
+            if (fine < 64) fine = 64;
+            if (fine < a.seg) a.seg = (int)fine;
+            const char *e = getenv("SMART_B200_TABLE_SEG");  // tests / tuning: force the segment length (multiple of 64)
+            if (e && atoi(e) >= 64 && atoi(e) % 64 == 0) a.seg = atoi(e);
+        }
         a.q = qq;
         a.sh1 = sh1;
         a.lim = lim;

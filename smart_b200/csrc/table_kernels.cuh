@@ -81,7 +81,7 @@ struct TableArgs {
     unsigned long long *counters; // [0] match count
     long long hi;                 // owned start positions [0, hi)
     int m;
-    int seg;                      // start positions per thread (multiple of 4)
+    int seg;                      // start positions per thread (multiple of 64: the streaming kernels load aligned vectors)
     int q, sh1;                   // HASHq: q-gram length, the shift after a verification (hash3.c:53-55)
     unsigned lim;                 // Shift-Or: lim (so.c:37); Shift-And: F (sa.c:45)
 };
@@ -144,7 +144,7 @@ __device__ __forceinline__ void stage_pattern_smem(uint8_t *sx, const TableArgs 
  * requested before the current ones are consumed - and takes the bytes out of registers at compile-time offsets.
  * A warp-wide byte or word load over 32 segments costs 32 L1 wavefronts per 32 / 128 bytes; the vector load pays
  * the same 32 wavefronts per 1024 bytes, which moves these kernels from the LSU bound to their shared-memory
- * table lookups.  `lo` is a multiple of 64 (segments are multiples of 4 KiB); the last step reads up to 127 bytes
+ * table lookups.  `lo` is a multiple of 64 (segments are multiples of 64 start positions); the last step reads up to 127 bytes
  * past `end`, inside the shard buffer's zeroed back pad (kPadBytes).  f(c, j): byte c at text index j.
  */
 struct StreamNoFlush {

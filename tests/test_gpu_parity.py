@@ -121,9 +121,16 @@ def test_table_driven_scans_match_the_reference(oracle, golden, tname):
             assert sb.last_timing().filter_kind not in range(601, 641)
 
 
-def test_table_driven_scans_segment_seams(oracle):
-    """One thread per 4 KiB (16 KiB for m > 1024) of start positions, each reading the m-1 bytes behind its segment:
-    occurrences across every seam, dense overlapping occurrences, text ends."""
+@pytest.mark.parametrize("seg", (0, 4096))
+def test_table_driven_scans_segment_seams(oracle, seg, monkeypatch):
+    """One thread per segment of start positions, each reading the m-1 bytes behind its segment: occurrences across
+    every seam, dense overlapping occurrences, text ends.  A text that fills the device is cut into 4 KiB (16 KiB for
+    m > 1024) segments, a short one down to 64 positions (seg = 0: what the library picks for this text); the 4 KiB
+    segments are forced here (SMART_B200_TABLE_SEG) so that their seams are crossed too."""
+    if seg:
+        monkeypatch.setenv("SMART_B200_TABLE_SEG", str(seg))
+    else:
+        monkeypatch.delenv("SMART_B200_TABLE_SEG", raising=False)
     rng = np.random.default_rng(31)
     n = 100_000
     texts = {"rand2": rng.integers(0, 2, n, dtype=np.uint8), "rand4": rng.integers(97, 101, n, dtype=np.uint8),
@@ -139,7 +146,7 @@ def test_table_driven_scans_segment_seams(oracle):
                     x = y[k:k + m].copy()
                     want = oracle.bf_count(x, y)
                     for ai, a in enumerate(TABLE_KIND):
-                        if (ai + mi) % 4 and a not in ("kmp", "so"):
+                        if (ai + mi + seg // 4096) % 8 and a not in ("kmp", "so"):
                             continue
                         if a.startswith("qf") and (name != "rand4" or m > 64):
                             continue  # a saturated bit table verifies every window (the reference's [OUT] cases)
