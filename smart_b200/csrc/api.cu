@@ -1756,6 +1756,9 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         else if (strncmp(desc->name, "bndmq", 5) == 0) kind = 631;
         else if (strcmp(desc->name, "fndm") == 0) kind = 632;
         else if (strcmp(desc->name, "sbndm") == 0) kind = 633;
+        else if (strncmp(desc->name, "bxs", 3) == 0) kind = 641;
+        else if (strcmp(desc->name, "sbndm-bmh") == 0) kind = 642;
+        else if (strcmp(desc->name, "lbndm") == 0) kind = 643;
         break;
     case SB_FAM_FACTOR:
         if (strcmp(desc->name, "bom") == 0) kind = 614;
@@ -1898,12 +1901,29 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         lim = ~0u << (k - 1);                                         // NEG0m1, fndm.c:39
         break;
     }
+    case 641:
+        qq = desc->min_m;  // bxs: 1, bxsQ: Q
+        sb_prep_bndm(x, m, reinterpret_cast<unsigned int *>(table));  // bxs.c:44-48 (the first min(m, 32) characters)
+        break;
+    case 643: {  // lbndm.c:53-61: group g (from the right) of k characters shares bit WORD-1-g... as the reference loops
+        const int k = (m - 1) / SB_WORD + 1;
+        for (int c = 0; c < 256; c++) table[c] = 0;
+        for (int i = m / k, l = m; i > 0; i--, l -= k)
+            for (int j = k; j > 0; j--) table[x[l - j]] = (int)((unsigned)table[x[l - j]] | (1u << (SB_WORD - i)));
+        break;
+    }
+    case 642:
     case 633: {
         const int k = m < SB_WORD ? m : SB_WORD;
         sb_prep_bndm(x, m, reinterpret_cast<unsigned int *>(table));
         for (int c = 0; c < 256; c++) table[c] = (int)((unsigned)table[c] << (SB_WORD - k));  // sbndm.c:42
         sb_prep_mp(x, k, scratch);
         sh1 = k - scratch[k];  // restore[0] (sbndm.c:44-55): the smallest period of the (32-character) window
+        if (kind == 642) {     // sbndm-bmh.c:41-42
+            for (int c = 0; c < 256; c++) table[256 + c] = 2 * k;
+            for (int i = 0; i < k; i++) table[256 + x[i]] = 2 * k - i - 1;
+            ntable = 512;
+        }
         break;
     }
     case 628:
@@ -2068,7 +2088,18 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         case 639: sb::table_br2_kernel<false><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 640: sb::table_br2_kernel<true><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 635: sb::table_kmpskip_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
-        case 633: sb::table_sbndm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 633: sb::table_sbndm_kernel<false><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 642: sb::table_sbndm_kernel<true><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 643: sb::table_lbndm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 641:
+            switch (qq) {
+            case 1: sb::table_bxs_kernel<1><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+            case 2: sb::table_bxs_kernel<2><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+            case 4: sb::table_bxs_kernel<4><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+            case 6: sb::table_bxs_kernel<6><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+            default: sb::table_bxs_kernel<8><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+            }
+            break;
         case 629: sb::table_skipq_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 630: sb::table_wfr_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         default: sb::table_qf_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;

@@ -48,6 +48,9 @@
  *   ac           kmpNext[0..m] + ell (ac.c:44-86): Apostolico-Crochemore
  *   bndmq2/4/6   B[256] (bndm.c:33-38): the window's last q characters at once, then right to left (bndmq2.c:59-73)
  *   fndm         the Shift-Or masks driving a forward factor scan from the window's last character (fndm.c:44-57)
+ *   bxs, bxs2..8 B[256] (bndm.c:33-38): BNDM over every (m-q+1)-th q-gram with the sample grid re-anchored at prefixes
+ *   lbndm        B[256] with ceil(m/32) pattern characters per bit (lbndm.c:53-61)
+ *   sbndm-bmh    sbndm + hbc[256] = 2m-1-i (sbndm-bmh.c:41-42): a Horspool-like skip in front of every window
  *   sbndm        B[256] aligned to the top of the word + the pattern's period as the shift (sbndm.c:44-83)
  *   iom          ibc1[256], ibc2[256] and the two look-ahead distances (iom.c:28-41)
  *   qlqs         qsBc of the pattern and of its reverse: the Quick-Search shift or a leap of m + m/2 (qlqs.c:52-57)
@@ -1235,10 +1238,11 @@ __global__ void __launch_bounds__(kTableThreads) table_fndm_kernel(const __grid_
 /* Simplified BNDM (sbndm.c:28-84, search_large :92-146): B aligned to the top of the word, the window read right to
  * left until the factor dies or its first character is reached; after an occurrence the shift is the pattern's
  * period (sbndm.c:44-55 `restore[0]`).  table = B[256] (top aligned), a.sh1 = shift */
+template <bool BMH>  // sbndm-bmh.c:27-84: + a Horspool-like skip on the character k behind the window while B[y[i]] == 0
 __global__ void __launch_bounds__(kTableThreads) table_sbndm_kernel(const __grid_constant__ TableArgs a)
 {
-    __shared__ unsigned raw_B[256];
-    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_B[i] = (unsigned)a.table[i];
+    __shared__ unsigned raw_B[512];
+    for (int i = threadIdx.x; i < (BMH ? 512 : 256); i += kTableThreads) raw_B[i] = (unsigned)a.table[i];
     __syncthreads();
     const Smem<unsigned> s_B(raw_B);
     const int m = a.m, k = m < SB_WORD ? m : SB_WORD, shift = a.sh1;
@@ -1250,7 +1254,13 @@ __global__ void __launch_bounds__(kTableThreads) table_sbndm_kernel(const __grid
         long long i = lo + k;                         // the window's last character
         while (i - k + 1 < own_end) {                 // sbndm.c:63-83 (bounded by the segment, not by the sentinel)
             unsigned D = s_B[__ldg(a.text + i)];
-            if (m > SB_WORD && D == 0) {              // search_large's skip loop, sbndm.c:128
+            if (BMH) {                                // sbndm-bmh.c:61: hbc[c] = 2k - 1 - (last position of c), 2k if absent
+                while (D == 0 && i - k + 1 < own_end) {
+                    i += (int)s_B[256 + __ldg(a.text + i + k)];
+                    D = s_B[__ldg(a.text + i)];
+                }
+                if (i - k + 1 >= own_end) break;
+            } else if (m > SB_WORD && D == 0) {       // search_large's skip loop, sbndm.c:128
                 i += k;
                 continue;
             }
@@ -1484,6 +1494,79 @@ __global__ void __launch_bounds__(kTableThreads) table_br2_kernel(const __grid_c
             }
             j += __ldg(L + __ldg(a.text + j + m) * 256 + __ldg(a.text + j + m + 1));
             e -= __ldg(R + __ldg(a.text + e - 1) * 256 + __ldg(a.text + e - 2));
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* BXS (bxs.c:30-75, bxs2.c .. bxs8.c): BNDM over every (k-Q+1)-th q-gram; a set top bit away from the window start
+ * moves the sample grid there and re-enters the bit (`(D<<1)|1`), at the window start the whole pattern is compared */
+template <int Q>
+__global__ void __launch_bounds__(kTableThreads) table_bxs_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ unsigned raw_B[256];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_B[i] = (unsigned)a.table[i];
+    __syncthreads();
+    const Smem<unsigned> s_B(raw_B);
+    const int len = a.m, k = len < SB_WORD ? len : SB_WORD, mq1 = k - Q + 1;
+    const unsigned mask = 1u << (k - 1);
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        for (long long i = lo + mq1 - 1; i - mq1 + 1 < own_end; i += mq1) {  // bxs2.c:53-72; the window starts at i-mq1+1
+            unsigned D = s_B[__ldg(a.text + i + Q - 1)];
+#pragma unroll
+            for (int t = Q - 2; t >= 0; t--) D = (D << 1) & s_B[__ldg(a.text + i + t)];
+            if (D) {
+                long long j = i;
+                const long long first = i - mq1;
+                do {
+                    j--;
+                    if (D >= mask) {
+                        if (j - first) i = j;
+                        else if (first + 1 < own_end) cnt += whole_pattern(a.text, a.pat, first + 1, len);
+                        D = ((D << 1) | 1u) & s_B[__ldg(a.text + j)];
+                    } else {
+                        D = (D << 1) & s_B[__ldg(a.text + j)];
+                    }
+                } while (D && j > first);
+            }
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* Long BNDM (lbndm.c:42-85): the pattern is cut into groups of k = ceil(m/32) characters that share one bit, the
+ * window is sampled every k-th character; a surviving top bit near the window start has the k alignments compared */
+__global__ void __launch_bounds__(kTableThreads) table_lbndm_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ unsigned raw_B[256];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_B[i] = (unsigned)a.table[i];
+    __syncthreads();
+    const Smem<unsigned> s_B(raw_B);
+    const int m = a.m, k = (m - 1) / SB_WORD + 1, m1 = m - 1, m2 = m1 - k, rmd = m - (m / k) * k;
+    const unsigned M = 1u << (SB_WORD - 1);
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        for (long long j = lo; j < own_end;) {  // lbndm.c:64-82
+            unsigned D = s_B[__ldg(a.text + j + m1)];
+            int last = (D & M) ? m - k - rmd : m - rmd;
+            int l = m2;
+            while (D) {
+                D = (D << 1) & s_B[__ldg(a.text + j + l)];
+                if (D & M) {
+                    if (l < k + rmd) {  // verify (lbndm.c:29-40): the k alignments from j on, inside the segment
+                        for (int t = 0; t < k && j + t < own_end; t++) cnt += whole_pattern(a.text, a.pat, j + t, m);
+                        break;
+                    }
+                    last = l - (k + rmd) + 1;
+                }
+                l -= k;
+            }
+            j += last;
         }
     }
     table_reduce(a, cnt);
