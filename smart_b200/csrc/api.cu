@@ -1764,6 +1764,7 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         if (strcmp(desc->name, "bom") == 0) kind = 614;
         else if (strcmp(desc->name, "ebom") == 0 || strcmp(desc->name, "sebom") == 0) kind = 615;  // sebom.c:61-77 is ebom.c:62-78
         else if (strcmp(desc->name, "bom2") == 0) kind = 636;
+        else if (strncmp(desc->name, "bsdm", 4) == 0) kind = 644;
         break;
     default: break;
     }
@@ -1899,6 +1900,15 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         const int k = m < SB_WORD ? m : SB_WORD;
         sb_prep_so(x, m, reinterpret_cast<unsigned int *>(table));  // fndm.c:36-37 == the masks of so.c:27-38
         lim = ~0u << (k - 1);                                         // NEG0m1, fndm.c:39
+        break;
+    }
+    case 644: {
+        int st = 0, len = 0;
+        qq = desc->min_m;  // bsdm: 1, bsdmQ: Q
+        sb_prep_bsdm(x, m, qq, table, &st, &len);
+        sh1 = st;
+        lim = (unsigned)len;
+        ntable = 65536;
         break;
     }
     case 641:
@@ -2091,6 +2101,7 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         case 633: sb::table_sbndm_kernel<false><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 642: sb::table_sbndm_kernel<true><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 643: sb::table_lbndm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 644: sb::table_bsdm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 641:
             switch (qq) {
             case 1: sb::table_bxs_kernel<1><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;

@@ -501,6 +501,47 @@ void sb_prep_skipq(const unsigned char *x, int m, int Q, int *head, int *next)
     }
 }
 
+/* Backward SNR DAWG Matching (bsdm.c:33-55, bsdm4.c:38-66): the longest run of pattern q-grams without a repeated
+ * q-gram (its first gram index st, its length len in grams) and pos[h] = index inside that run of the gram that
+ * hashes to h (-1: not in the run).  Q = 1: single characters (pos[256] in the reference, the first 256 entries
+ * here); the hash shifts by 2 bits per character for Q = 4, by 1 bit for Q = 5, 7, 8 (bsdm4.c:29, bsdm5.c:29). */
+static unsigned bsdm_hash(const unsigned char *p, int Q)
+{
+    const int step = Q == 4 ? 2 : 1;
+    unsigned h = 0;
+    for (int t = 0; t < Q; t++) h += (unsigned)p[t] << (step * (Q - 1 - t));
+    return h & 0xffffu;
+}
+
+void sb_prep_bsdm(const unsigned char *x, int m, int Q, int *pos, int *st_out, int *len_out)
+{
+    static _Thread_local unsigned char occ[65536];
+    memset(occ, 0, sizeof occ);
+    int st = 0, len = 0;
+    for (int i = 0, j = 0; i < m - Q + 1; i++) {
+        const unsigned c = bsdm_hash(x + i, Q);
+        if (occ[c]) {
+            unsigned d = bsdm_hash(x + j, Q);
+            while (d != c) {
+                occ[d] = 0;
+                j++;
+                d = bsdm_hash(x + j, Q);
+            }
+            occ[d] = 0;
+            j++;
+        }
+        occ[c] = 1;
+        if (len < i - j + 1) {
+            len = i - j + 1;
+            st = j;
+        }
+    }
+    for (int i = 0; i < 65536; i++) pos[i] = -1;
+    for (int i = 0; i < len; i++) pos[bsdm_hash(x + st + i, Q)] = i;
+    *st_out = st;
+    *len_out = len;
+}
+
 /* Weak-factor-recognition table (wfr.c:41-58, wfrq4.c:50-65): F[h] = 1 for the 16-bit hash h of every pattern
  * factor the scan can ask about.  The hash is built right to left, as the scan reads the window.
  * Q <= 1 (wfr, wfr2..8, twfr*, lwfr*): every factor x[j..i] of at most 16 characters, h <- (h << 2) + x[j].

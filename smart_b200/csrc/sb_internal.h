@@ -83,6 +83,7 @@ void sb_prep_qf(const unsigned char *x, int m, int Q, int S, int *B);
 void sb_prep_wfr(const unsigned char *x, int m, int Q, unsigned char *F);
 void sb_prep_ztbc(const unsigned char *x, int m, int *ztBc);
 void sb_prep_skipq(const unsigned char *x, int m, int Q, int *head, int *next);
+void sb_prep_bsdm(const unsigned char *x, int m, int Q, int *pos, int *st, int *len);
 int sb_prep_sbndm2(const unsigned char *x, int m, unsigned int *B, int *shift);
 
 #ifdef __cplusplus

@@ -55,6 +55,7 @@
  *   iom          ibc1[256], ibc2[256] and the two look-ahead distances (iom.c:28-41)
  *   qlqs         qsBc of the pattern and of its reverse: the Quick-Search shift or a leap of m + m/2 (qlqs.c:52-57)
  *   tsw, tvsbs-w2  brBc of the pattern and of its reverse: one window moves up, one moves down (tsw.c:58-68)
+ *   bsdm, bsdm4/5/7/8  pos[65536] over the pattern's longest run of distinct q-grams (bsdm.c:33-55)
  *   ts           no table: Tailed-Substring's two probing phases over the pattern in shared memory (ts.c:25-59)
  *   kmpskip      mpNext, kmpNext and the character buckets z[256] / list[m] (kmpskip.c:59-146), 16-bit entries
  *   zt           ztBc[256][256] (zt.c:64-74, 256 KiB through L1/L2) + bmGs[0..m): BM with a two-character shift
@@ -1567,6 +1568,49 @@ __global__ void __launch_bounds__(kTableThreads) table_lbndm_kernel(const __grid
                 l -= k;
             }
             j += last;
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Backward SNR DAWG Matching (bsdm.c:57-76, bsdm4.c:68-93): table = pos[65536] (L1/L2); a.q = Q,
+ *      a.sh1 = st, a.lim = len (the longest run of pattern q-grams without a repeat) ---- */
+__global__ void __launch_bounds__(kTableThreads) table_bsdm_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    stage_pattern_smem(raw_x, a);
+    __syncthreads();
+    const Smem<uint8_t> s_x(raw_x);
+    const int m = a.m, Q = a.q, st = a.sh1, len = (int)a.lim, offset = st + len - 1, step = Q == 4 ? 2 : 1;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    auto gram = [&](long long j) {
+        unsigned h = 0;
+        for (int t = 0; t < Q; t++) h += (unsigned)__ldg(a.text + j + t) << (step * (Q - 1 - t));
+        return h & 0xffffu;
+    };
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        long long j = lo + (Q == 1 ? offset : len - 1);  // bsdm.c:62 / bsdm4.c:73
+        while (j - offset < own_end) {
+            int i;
+            while ((i = __ldg(a.table + gram(j))) < 0 && j - offset < own_end) j += len;  // the fast loop, bounded by the segment
+            if (i < 0) break;
+            int k = 1;
+            while (k <= i && s_x[st + i - k] == __ldg(a.text + j - k)) k++;
+            if (k > i) {  // the run's prefix up to this gram stands in the text
+                if (k == len) {
+                    const long long s = j - offset;
+                    if (s >= lo && s < own_end) {
+                        int t = 0;
+                        while (t < m && s_x[t] == __ldg(a.text + s + t)) t++;
+                        cnt += t == m;
+                    }
+                } else {
+                    j -= k;
+                }
+            }
+            j += len;
         }
     }
     table_reduce(a, cnt);
