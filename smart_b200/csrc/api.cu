@@ -1751,6 +1751,7 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
     case SB_FAM_FJS: kind = 622; break;
     case SB_FAM_BF: kind = strcmp(desc->name, "ts") == 0 ? 634 : 0; break;  // (bf itself IS the default mode)
     case SB_FAM_KMPSKIP: kind = 635; break;
+    case SB_FAM_BITPAR: kind = strncmp(desc->name, "aoso", 4) == 0 ? 645 : 0; break;
     case SB_FAM_BNDMX:
         if (strcmp(desc->name, "sbndm2") == 0) kind = m <= SB_WORD ? 616 : 0;  // (m > 32: the default mode)
         else if (strncmp(desc->name, "bndmq", 5) == 0) kind = 631;
@@ -1900,6 +1901,21 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         const int k = m < SB_WORD ? m : SB_WORD;
         sb_prep_so(x, m, reinterpret_cast<unsigned int *>(table));  // fndm.c:36-37 == the masks of so.c:27-38
         lim = ~0u << (k - 1);                                         // NEG0m1, fndm.c:39
+        break;
+    }
+    case 645: {  // aoso2.c:50-62 over the first min(m, 32) characters (search_large :106-117)
+        const int k = m < SB_WORD ? m : SB_WORD;
+        qq = desc->min_m - 1;  // aosoQ: m <= Q -> -1 (aoso2.c:47)
+        unsigned h = 0, mm = 0;
+        for (int c = 0; c < 256; c++) table[c] = -1;
+        for (int j = 0; j < qq; j++) {
+            for (int i = 0; i < k / qq; i++) {
+                table[x[i * qq + j]] = (int)((unsigned)table[x[i * qq + j]] & ~(1u << h));
+                h++;
+            }
+            mm |= 1u << (h - 1);
+        }
+        lim = mm;
         break;
     }
     case 644: {
@@ -2102,6 +2118,7 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         case 642: sb::table_sbndm_kernel<true><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 643: sb::table_lbndm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 644: sb::table_bsdm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 645: sb::table_aoso_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 641:
             switch (qq) {
             case 1: sb::table_bxs_kernel<1><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;

@@ -55,6 +55,7 @@
  *   iom          ibc1[256], ibc2[256] and the two look-ahead distances (iom.c:28-41)
  *   qlqs         qsBc of the pattern and of its reverse: the Quick-Search shift or a leap of m + m/2 (qlqs.c:52-57)
  *   tsw, tvsbs-w2  brBc of the pattern and of its reverse: one window moves up, one moves down (tsw.c:58-68)
+ *   aoso2/4/6    B[256] of q interleaved Shift-Or automata and their top-bit mask mm (aoso2.c:50-62)
  *   bsdm, bsdm4/5/7/8  pos[65536] over the pattern's longest run of distinct q-grams (bsdm.c:33-55)
  *   ts           no table: Tailed-Substring's two probing phases over the pattern in shared memory (ts.c:25-59)
  *   kmpskip      mpNext, kmpNext and the character buckets z[256] / list[m] (kmpskip.c:59-146), 16-bit entries
@@ -1568,6 +1569,40 @@ __global__ void __launch_bounds__(kTableThreads) table_lbndm_kernel(const __grid
                 l -= k;
             }
             j += last;
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Average-Optimal Shift-Or (aoso2.c:42-77, search_large :99-132; aoso4.c, aoso6.c): table = B[256];
+ *      a.q = q, a.lim = mm.  q interleaved Shift-Or automata over every q-th pattern character share one word; the
+ *      text is sampled every q-th character, a zero among the automata's top bits names the alignments to compare.
+ *      Any sample grid works (an occurrence is met by the sub-pattern that falls on it), so a segment starts its own. ---- */
+__global__ void __launch_bounds__(kTableThreads) table_aoso_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ unsigned raw_B[256];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_B[i] = (unsigned)a.table[i];
+    __syncthreads();
+    const Smem<unsigned> s_B(raw_B);
+    const int m = a.m, q = a.q, k = m < SB_WORD ? m : SB_WORD, mq = k / q;
+    const unsigned mm = a.lim;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        const long long end = own_end + m - 1;  // text bytes of this segment's windows
+        unsigned D = ~0u;
+        for (long long j = lo; j < end; j += q) {  // aoso2.c:68-74
+            D = ((D & ~mm) << 1) | s_B[__ldg(a.text + j)];
+            if ((D & mm) != mm) {                  // verify, aoso2.c:28-40
+                unsigned E = (D & mm) ^ mm;
+                while (E) {
+                    const int s = 31 - __clz(E);
+                    const long long i = j - (long long)(mq - 1) * q - s / mq;
+                    if (i >= lo && i < own_end) cnt += whole_pattern(a.text, a.pat, i, m);
+                    E &= ~(1u << s);
+                }
+            }
         }
     }
     table_reduce(a, cnt);
