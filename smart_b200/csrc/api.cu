@@ -1734,6 +1734,8 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         else if (strcmp(desc->name, "qlqs") == 0) kind = 638;
         else if (strcmp(desc->name, "tsw") == 0) kind = 639;
         else if (strcmp(desc->name, "tvsbs-w2") == 0) kind = 640;
+        else if (strcmp(desc->name, "wc") == 0) kind = 647;
+        else if (strcmp(desc->name, "fs-w1") == 0) kind = 648;
         break;
     case SB_FAM_SKIPQ: kind = 629; break;
     case SB_FAM_WFR:  // wfr (wfr.c), wfrq2..8 (wfrq4.c) and wfr2..8 (wfr4.c: wfrq's scan over wfr's table); not twfr*, lwfr*
@@ -1751,7 +1753,7 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
     case SB_FAM_FJS: kind = 622; break;
     case SB_FAM_BF: kind = strcmp(desc->name, "ts") == 0 ? 634 : 0; break;  // (bf itself IS the default mode)
     case SB_FAM_KMPSKIP: kind = 635; break;
-    case SB_FAM_BITPAR: kind = strncmp(desc->name, "aoso", 4) == 0 ? 645 : 0; break;
+    case SB_FAM_BITPAR: kind = strncmp(desc->name, "aoso", 4) == 0 ? 645 : strcmp(desc->name, "svm0") == 0 ? 646 : 0; break;
     case SB_FAM_BNDMX:
         if (strcmp(desc->name, "sbndm2") == 0) kind = m <= SB_WORD ? 616 : 0;  // (m > 32: the default mode)
         else if (strncmp(desc->name, "bndmq", 5) == 0) kind = 631;
@@ -1835,6 +1837,32 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
     case 616: sb_prep_sbndm2(x, m, reinterpret_cast<unsigned int *>(table), &sh1); break;
     case 617: sb_prep_bndm(x, m, reinterpret_cast<unsigned int *>(table)); break;
     case 623: sb_prep_qsbc(x, m, table); break;
+    case 646: {  // svm0.c:44-52 over the first min(m, 31) characters
+        const int k = m < SB_WORD - 1 ? m : SB_WORD - 1;
+        const unsigned all = ~0u >> (SB_WORD - k);
+        for (int c = 0; c < 256; c++) table[c] = (int)all;
+        for (int j = k - 1, b = 0; j >= 0; j--, b++) table[x[j]] = (int)((unsigned)table[x[j]] & ~(1u << b));
+        break;
+    }
+    case 647: {  // wc.c:41-70 FindBadPos (the reference keeps `max` in an int: the comparison truncates) + PreBadPosBC
+        int last[256], pos = 0, mx = 1;
+        double adv = 1;
+        for (int c = 0; c < 256; c++) last[c] = -1;
+        for (int i = 1; i <= m; i++) {
+            const int gbc = i - last[x[i - 1]] - 1;
+            adv = adv - (double)gbc * 0.5 + 1;
+            last[x[i - 1]] = i - 1;
+            if (adv > mx) {
+                mx = (int)adv;
+                pos = i;
+            }
+        }
+        for (int c = 0; c < 256; c++) table[c] = pos + 1;
+        for (int i = 0; i < pos; i++) table[x[i]] = pos - i;
+        qq = pos;
+        break;
+    }
+    case 648:
     case 624:
         sb_prep_lastocc(x, m, table);
         sb_prep_fsgs(x, m, table + 256);
@@ -2097,7 +2125,10 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         case 621: sb::table_skip_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 622: sb::table_fjs_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 623: sb::table_ssabs_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
-        case 624: sb::table_fs_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 624: sb::table_fs_kernel<false><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 648: sb::table_fs_kernel<true><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 646: sb::table_svm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 647: sb::table_wc_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 625: sb::table_graspm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 626: sb::table_tbm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 627: sb::table_ac_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;

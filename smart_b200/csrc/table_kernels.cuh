@@ -55,6 +55,9 @@
  *   iom          ibc1[256], ibc2[256] and the two look-ahead distances (iom.c:28-41)
  *   qlqs         qsBc of the pattern and of its reverse: the Quick-Search shift or a leap of m + m/2 (qlqs.c:52-57)
  *   tsw, tvsbs-w2  brBc of the pattern and of its reverse: one window moves up, one moves down (tsw.c:58-68)
+ *   svm0         cv[256] (svm0.c:44-52): the shift vector of the next 32 window positions
+ *   wc           bc[256] for the worst character position (wc.c:28-70)
+ *   fs-w1        fs's tables (fs-w1.c:72-80)
  *   aoso2/4/6    B[256] of q interleaved Shift-Or automata and their top-bit mask mm (aoso2.c:50-62)
  *   bsdm, bsdm4/5/7/8  pos[65536] over the pattern's longest run of distinct q-grams (bsdm.c:33-55)
  *   ts           no table: Tailed-Substring's two probing phases over the pattern in shared memory (ts.c:25-59)
@@ -857,6 +860,7 @@ __global__ void __launch_bounds__(kTableThreads) table_ssabs_kernel(const __grid
 }
 
 /* ---- Fast-Search: table = bc[256] (all m characters) then gs[0..m] ---- */
+template <bool W1>  // fs-w1.c:65-101: the same tables and shifts, the scan simply starts on the first window's last character
 __global__ void __launch_bounds__(kTableThreads) table_fs_kernel(const __grid_constant__ TableArgs a)
 {
     __shared__ int raw_bc[256];
@@ -874,12 +878,12 @@ __global__ void __launch_bounds__(kTableThreads) table_fs_kernel(const __grid_co
     unsigned cnt = 0;
     if (lo < a.hi) {
         const long long own_end = min(lo + a.seg, a.hi);
-        {   // fs.c:56: the first window is compared directly
+        if (!W1) {  // fs.c:56: the first window is compared directly
             int i = 0;
             while (i < m && s_x[i] == __ldg(a.text + lo + i)) i++;
             cnt += i == m;
         }
-        long long s = lo + m;  // index of the window's last character
+        long long s = lo + (W1 ? m - 1 : m);  // index of the window's last character (fs.c:57 / fs-w1.c:87)
         while (s - m + 1 < own_end) {  // fs.c:58-66
             int k;
             while (s - m + 1 < own_end && (k = s_bc[__ldg(a.text + s)]) != 0) s += k;
@@ -1603,6 +1607,67 @@ __global__ void __launch_bounds__(kTableThreads) table_aoso_kernel(const __grid_
                     E &= ~(1u << s);
                 }
             }
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Shift Vector Matching (svm0.c:36-72, search_large :80-124): table = cv[256] over the first k = min(m, 31)
+ *      characters (bit b clear <=> x[k-1-b] == c).  sv collects, for the next 32 window positions, which are already
+ *      ruled out; a window is read right to left while position 0 is still possible, then the scan moves to the next
+ *      possible position (bsf).  A segment starts with an empty vector. ---- */
+__global__ void __launch_bounds__(kTableThreads) table_svm_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ unsigned raw_cv[256];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_cv[i] = (unsigned)a.table[i];
+    __syncthreads();
+    const Smem<unsigned> s_cv(raw_cv);
+    const int m = a.m, k = m < SB_WORD - 1 ? m : SB_WORD - 1;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        cnt += whole_pattern(a.text, a.pat, lo, m);  // svm0.c:56
+        unsigned sv = 0;
+        for (long long s = lo + k; s - k + 1 < own_end;) {  // s: the window's last character (svm0.c:58-70)
+            sv |= s_cv[__ldg(a.text + s)];
+            int j = 1;
+            while ((sv & 1u) == 0) {
+                if (j >= k) {
+                    cnt += m > k ? whole_pattern(a.text, a.pat, s - k + 1, m) : 1u;
+                    break;
+                }
+                sv |= s_cv[__ldg(a.text + s - j)] >> j;
+                j++;
+            }
+            const int adv = __ffs(~(sv >> 1));  // bsf + 1: bit 31 of ~(sv >> 1) is always set
+            sv = adv < 32 ? sv >> adv : 0u;
+            s += adv;
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Worst-Character rule (wc.c:75-96): table = bc[256] for the position `pos` = a.q that FindBadPos picks ---- */
+__global__ void __launch_bounds__(kTableThreads) table_wc_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ int raw_bc[256];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_bc[i] = a.table[i];
+    stage_pattern_smem(raw_x, a);
+    __syncthreads();
+    const Smem<int> s_bc(raw_bc);
+    const Smem<uint8_t> s_x(raw_x);
+    const int m = a.m, pos = a.q;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        for (long long s = lo; s < own_end;) {  // wc.c:84-93
+            int i = 0;
+            while (i < m && s_x[i] == __ldg(a.text + s + i)) i++;
+            cnt += i == m;
+            s += s_bc[__ldg(a.text + s + pos)];
         }
     }
     table_reduce(a, cnt);
