@@ -1768,6 +1768,7 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         else if (strcmp(desc->name, "ebom") == 0 || strcmp(desc->name, "sebom") == 0) kind = 615;  // sebom.c:61-77 is ebom.c:62-78
         else if (strcmp(desc->name, "bom2") == 0) kind = 636;
         else if (strncmp(desc->name, "bsdm", 4) == 0) kind = 644;
+        else if (strcmp(desc->name, "fbom") == 0 || strcmp(desc->name, "sfbom") == 0) kind = 649;
         break;
     default: break;
     }
@@ -1830,6 +1831,26 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
             const int q = tr[(size_t)m * 256 + c1];
             for (int c2 = 0; c2 < 256; c2++) FT[c1 * 256 + c2] = q >= 0 ? tr[(size_t)q * 256 + c2] : (short)-1;
         }
+        lim = (unsigned)ft_off;
+        ntable = (int)(ft_off / 2 + 32768);
+        break;
+    }
+    case 649: {  // the oracle of bom, then the look-ahead table of fbom.c:53-64
+        short *tr = reinterpret_cast<short *>(table);
+        sb_prep_bom(x, m, tr, reinterpret_cast<unsigned char *>(tr + (size_t)(m + 1) * 256));
+        const size_t ft_off = (((size_t)(m + 1) * 256 * 2 + (m + 1) + 3) / 4) * 2;  // in shorts, 4-byte aligned
+        short *FT = tr + ft_off;
+        for (int c1 = 0; c1 < 256; c1++) {
+            const int q = tr[(size_t)m * 256 + c1];
+            for (int c2 = 0; c2 < 256; c2++) {
+                const int p = q >= 0 ? tr[(size_t)q * 256 + c2] : -1;
+                FT[c1 * 256 + c2] = (short)(p >= 0 ? p : 2 * m + 1);
+            }
+        }
+        const short q = tr[(size_t)m * 256 + x[m - 1]];
+        for (int c1 = 0; c1 < 256; c1++) FT[c1 * 256 + x[m - 1]] = q;
+        for (int c2 = 0; c2 < 256; c2++)
+            if (FT[x[0] * 256 + c2] > m) FT[x[0] * 256 + c2] -= 1;
         lim = (unsigned)ft_off;
         ntable = (int)(ft_off / 2 + 32768);
         break;
@@ -2128,6 +2149,7 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         case 624: sb::table_fs_kernel<false><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 648: sb::table_fs_kernel<true><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 646: sb::table_svm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 649: sb::table_fbom_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 647: sb::table_wc_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 625: sb::table_graspm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 626: sb::table_tbm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;

@@ -55,6 +55,7 @@
  *   iom          ibc1[256], ibc2[256] and the two look-ahead distances (iom.c:28-41)
  *   qlqs         qsBc of the pattern and of its reverse: the Quick-Search shift or a leap of m + m/2 (qlqs.c:52-57)
  *   tsw, tvsbs-w2  brBc of the pattern and of its reverse: one window moves up, one moves down (tsw.c:58-68)
+ *   fbom, sfbom  the oracle of bom + a look-ahead FT[256][256] over the character behind the window (fbom.c:53-64)
  *   svm0         cv[256] (svm0.c:44-52): the shift vector of the next 32 window positions
  *   wc           bc[256] for the worst character position (wc.c:28-70)
  *   fs-w1        fs's tables (fs-w1.c:72-80)
@@ -1607,6 +1608,37 @@ __global__ void __launch_bounds__(kTableThreads) table_aoso_kernel(const __grid_
                     E &= ~(1u << s);
                 }
             }
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Forward BOM (fbom.c:28-96, sfbom.c): table = the oracle of bom ((m+1) x 256 x 16 bit, m+1 terminal bytes,
+ *      padding), then FT[256][256] at a.lim shorts: FT[b][a] for the character b BEHIND the window and its last
+ *      character a = the state after reading b, a (a window one further right), or a shift coded as m + shift when
+ *      "ab" is no factor; a = x[m-1] always enters the oracle with the window's own last character (fbom.c:53-64) ---- */
+__global__ void __launch_bounds__(kTableThreads) table_fbom_kernel(const __grid_constant__ TableArgs a)
+{
+    const int m = a.m;
+    const short *trans = reinterpret_cast<const short *>(a.table);
+    const short *FT = trans + a.lim;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        cnt += whole_pattern(a.text, a.pat, lo, m);  // fbom.c:68
+        long long j = lo + m;                         // the window's last character
+        while (j - m + 1 < own_end) {                 // fbom.c:71-80
+            int p;
+            while ((p = __ldg(FT + __ldg(a.text + j + 1) * 256 + __ldg(a.text + j))) > m && j - m + 1 < own_end) j += p - m;
+            if (p > m) break;
+            long long i = j - 1;
+            while (i >= j - m && (p = __ldg(trans + p * 256 + __ldg(a.text + i))) >= 0) i--;  // (state 0 has no exits)
+            if (i < j - (m - 1)) {
+                cnt += j - m + 1 < own_end;
+                i++;
+            }
+            j = i + m;
         }
     }
     table_reduce(a, cnt);
