@@ -182,7 +182,7 @@ typedef struct sb_timing {
                               KF == m), 541..556 = scan_pswar<2,KF> on the 2-bit recoding,
                               108/116/132 = scan_skip<G>, 204/208/216 = scan_multi<B>, -1 = per-pattern fallback,
                               601 kmp / 602 mp / 603 hor / 604 so / 605 sa / 606 hashq / 607 bm / 608 qs / 609 raita /
-                              610 tunedbm / 611 kr / 612 qf / 613 aut / 614 bom / 615 ebom / 616 sbndm2 (m <= 32) / 617 bndm / 618 br / 619 tvsbs / 620 smith / 621 skip / 622 fjs / 623 ssabs / 624 fs / 625 graspm / 626 tbm / 627 ac / 628 zt / 629 skip3,5..8 / 630 wfr, wfr2..8, wfrq2..8, twfr, twfr2..8, twfrq2..8 / 631 bndmq2,4,6 / 632 fndm / 633 sbndm / 634 ts / 635 kmpskip / 636 bom2 / 637 iom / 638 qlqs / 639 tsw / 640 tvsbs-w2 / 641 bxs, bxs2..8 / 642 sbndm-bmh / 643 lbndm / 644 bsdm, bsdm4,5,7,8 / 645 aoso2,4,6 / 646 svm0 / 647 wc / 648 fs-w1 / 649 fbom, sfbom = table-driven scans; sebom runs 615 (SB_FLAG_TABLE_SCAN) */
+                              610 tunedbm / 611 kr / 612 qf / 613 aut / 614 bom / 615 ebom / 616 sbndm2 (m <= 32) / 617 bndm / 618 br / 619 tvsbs / 620 smith / 621 skip / 622 fjs / 623 ssabs / 624 fs / 625 graspm / 626 tbm / 627 ac / 628 zt / 629 skip3,5..8 / 630 wfr, wfr2..8, wfrq2..8, twfr, twfr2..8, twfrq2..8 / 631 bndmq2,4,6 / 632 fndm / 633 sbndm / 634 ts / 635 kmpskip / 636 bom2 / 637 iom / 638 qlqs / 639 tsw / 640 tvsbs-w2 / 641 bxs, bxs2..8 / 642 sbndm-bmh / 643 lbndm / 644 bsdm, bsdm4,5,7,8 / 645 aoso2,4,6 / 646 svm0 / 647 wc / 648 fs-w1 / 649 fbom, sfbom / 650 wom / 651 pbmh = table-driven scans; sebom runs 615 (SB_FLAG_TABLE_SCAN) */
     unsigned long long verified; /* candidates sent to exact verification (all shards) */
 } sb_timing;
 void sb_last_timing(sb_timing *out);

@@ -1735,6 +1735,8 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         else if (strcmp(desc->name, "tsw") == 0) kind = 639;
         else if (strcmp(desc->name, "tvsbs-w2") == 0) kind = 640;
         else if (strcmp(desc->name, "wc") == 0) kind = 647;
+        else if (strcmp(desc->name, "wom") == 0) kind = 650;
+        else if (strcmp(desc->name, "pbmh") == 0) kind = 651;
         else if (strcmp(desc->name, "fs-w1") == 0) kind = 648;
         break;
     case SB_FAM_SKIPQ: kind = 629; break;
@@ -1881,6 +1883,46 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         for (int c = 0; c < 256; c++) table[c] = pos + 1;
         for (int i = 0; i < pos; i++) table[x[i]] = pos - i;
         qq = pos;
+        break;
+    }
+    case 650:
+    case 651: {  // both rank characters by their count among the text's first 100 characters (wom.c:29-33, pbmh.c:33-34)
+        unsigned char head[100] = {0};
+        const size_t have = t->n < 100 ? t->n : 100;  // (the reference reads 100 bytes whatever n is)
+        if (t->nshards > 0 && have > 0) {
+            CU_TRY(cudaSetDevice(t->sh[0].dev), SB_ERR_CUDA);
+            CU_TRY(cudaMemcpy(head, t->sh[0].d_text, have < t->sh[0].len ? have : t->sh[0].len, cudaMemcpyDeviceToHost),
+                   SB_ERR_CUDA);
+        }
+        int cntc[256] = {0};
+        for (int i = 0; i < 100; i++) cntc[head[i]]++;
+        if (kind == 650) {  // wom.c:35-56 FindWorstOccurrence + PrecomputeWOH
+            double freq[256], adv = 1.0, mx = 1.0;
+            int lp[256], q = 0;
+            for (int c = 0; c < 256; c++) {
+                freq[c] = cntc[c] / 100.0;
+                lp[c] = -1;
+            }
+            for (int i = 1; i <= m; i++) {
+                const int gbc = i - lp[x[i - 1]] - 1;
+                adv = adv - freq[x[i - 1]] * gbc + 1.0;
+                lp[x[i - 1]] = i - 1;
+                if (adv > mx) {
+                    mx = adv;
+                    q = i;
+                }
+            }
+            for (int c = 0; c < 256; c++) table[c] = q + 1;
+            for (int i = 0; i < q; i++) table[x[i]] = q - i;
+            qq = q;
+        } else {            // pbmh.c:36-47: positions by ascending frequency (the reference's bubble sort is stable)
+            static thread_local int order[SB_XSIZE];
+            for (int i = 0; i < m; i++) order[i] = i;
+            std::stable_sort(order, order + m, [&](int u, int v) { return cntc[x[u]] < cntc[x[v]]; });
+            sb_prep_hbc(x, m, table);
+            for (int i = 0; i < m; i++) table[256 + i] = order[i];
+            ntable = 256 + m;
+        }
         break;
     }
     case 648:
@@ -2150,7 +2192,9 @@ static long long search_table(const sb_algo_desc *desc, const sb_text *t, const 
         case 648: sb::table_fs_kernel<true><<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 646: sb::table_svm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 649: sb::table_fbom_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 650:
         case 647: sb::table_wc_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
+        case 651: sb::table_pbmh_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 625: sb::table_graspm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 626: sb::table_tbm_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;
         case 627: sb::table_ac_kernel<<<grid, sb::kTableThreads, 0, c->stream>>>(a); break;

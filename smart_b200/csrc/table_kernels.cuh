@@ -56,6 +56,9 @@
  *   qlqs         qsBc of the pattern and of its reverse: the Quick-Search shift or a leap of m + m/2 (qlqs.c:52-57)
  *   tsw, tvsbs-w2  brBc of the pattern and of its reverse: one window moves up, one moves down (tsw.c:58-68)
  *   fbom, sfbom  the oracle of bom + a look-ahead FT[256][256] over the character behind the window (fbom.c:53-64)
+ *   wom          wo[256] for the worst occurrence position under the character frequencies of the text's first 100
+ *                characters (wom.c:28-56); the scan loop is wc's (wom.c:70-76)
+ *   pbmh         hbc[256] + the comparison order by those frequencies (pbmh.c:36-47)
  *   svm0         cv[256] (svm0.c:44-52): the shift vector of the next 32 window positions
  *   wc           bc[256] for the worst character position (wc.c:28-70)
  *   fs-w1        fs's tables (fs-w1.c:72-80)
@@ -1680,7 +1683,8 @@ __global__ void __launch_bounds__(kTableThreads) table_svm_kernel(const __grid_c
     table_reduce(a, cnt);
 }
 
-/* ---- Worst-Character rule (wc.c:75-96): table = bc[256] for the position `pos` = a.q that FindBadPos picks ---- */
+/* ---- Worst-Character rule (wc.c:75-96) and Worst-Occurrence Matcher (wom.c:58-80): table = the shift table for
+ *      the position `pos` = a.q that FindBadPos / FindWorstOccurrence picks; compare, then shift on y[s + pos] ---- */
 __global__ void __launch_bounds__(kTableThreads) table_wc_kernel(const __grid_constant__ TableArgs a)
 {
     __shared__ int raw_bc[256];
@@ -1700,6 +1704,39 @@ __global__ void __launch_bounds__(kTableThreads) table_wc_kernel(const __grid_co
             while (i < m && s_x[i] == __ldg(a.text + s + i)) i++;
             cnt += i == m;
             s += s_bc[__ldg(a.text + s + pos)];
+        }
+    }
+    table_reduce(a, cnt);
+}
+
+/* ---- Probabilistic BMH (pbmh.c:29-61): table = hbc[256] (hor.c:26-30), then the comparison order v[0..m): the
+ *      pattern positions sorted by the frequency of their character among the text's first 100 characters ---- */
+__global__ void __launch_bounds__(kTableThreads) table_pbmh_kernel(const __grid_constant__ TableArgs a)
+{
+    __shared__ int raw_hbc[256];
+    __shared__ short raw_v[SB_XSIZE];
+    __shared__ uint8_t raw_x[SB_XSIZE + 8];
+    for (int i = threadIdx.x; i < 256; i += kTableThreads) raw_hbc[i] = a.table[i];
+    for (int i = threadIdx.x; i < a.m; i += kTableThreads) raw_v[i] = (short)a.table[256 + i];
+    stage_pattern_smem(raw_x, a);
+    __syncthreads();
+    const Smem<int> s_hbc(raw_hbc);
+    const Smem<short> s_v(raw_v);
+    const Smem<uint8_t> s_x(raw_x);
+    const int m = a.m;
+    const long long lo = ((long long)blockIdx.x * kTableThreads + threadIdx.x) * a.seg;
+    unsigned cnt = 0;
+    if (lo < a.hi) {
+        const long long own_end = min(lo + a.seg, a.hi);
+        for (long long s = lo; s < own_end;) {  // pbmh.c:53-58
+            int i = 0;
+            while (i < m) {
+                const int v = s_v[i];
+                if (s_x[v] != __ldg(a.text + s + v)) break;
+                i++;
+            }
+            cnt += i == m;
+            s += s_hbc[__ldg(a.text + s + m - 1)];
         }
     }
     table_reduce(a, cnt);

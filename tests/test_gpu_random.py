@@ -52,7 +52,7 @@ def test_random_small_cases(oracle, case):
                   "qf34", "qf62", "aut", "bom", "ebom", "bndm", "br", "tvsbs", "smith", "skip", "fjs", "sbndm2",
                   "ssabs", "fs", "graspm", "tbm", "ac", "zt", "skip3", "skip6", "wfr", "wfrq2", "wfrq4",
                   "bndmq2", "bndmq4", "fndm", "sbndm", "ts", "kmpskip", "bom2", "sebom", "iom", "qlqs", "tsw", "tvsbs-w2",
-                  "wfr3", "twfr", "twfr5", "twfrq2", "bxs", "bxs2", "bxs4", "sbndm-bmh", "lbndm", "bsdm", "bsdm4", "bsdm7", "aoso2", "aoso6", "svm0", "wc", "fs-w1", "fbom", "sfbom"):
+                  "wfr3", "twfr", "twfr5", "twfrq2", "bxs", "bxs2", "bxs4", "sbndm-bmh", "lbndm", "bsdm", "bsdm4", "bsdm7", "aoso2", "aoso6", "svm0", "wc", "fs-w1", "fbom", "sfbom", "wom", "pbmh"):
             assert sb.search(a, t2, x, flags=sb.FLAG_TABLE_SCAN).count == expected(a, x.size, want.size, y.size), (a, x.size)
         # asynchronous tickets give the same answers as the blocking calls
         tickets = [sb.submit(a, t, x) for a in ("bf", "bm", "so", "qf23", "wfr", "sbndm2")]
