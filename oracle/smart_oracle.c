@@ -3,9 +3,9 @@
  *
  * A plain-C CPU restatement of the reference's (ostafen/smart) exact-string-matching path:
  * the brute-force result that defines every algorithm's count, the preprocessing tables of
- * the north-star algorithm families, and each family's sequential scan (54 algorithms, the
- * last fourteen being wfr, wfrq2..8, skip3/5/6/7/8 and zt; a further 88 are covered by result specification +
- * domain rule, see "Tier 2" below).  Only tests/,
+ * the north-star algorithm families, and each family's sequential scan: 113 of the 143 registered algorithms
+ * (round 1: 40; round 2 added wfr, wfrq2..8, skip3/5/6/7/8, zt, aut, bom, ebom, sbndm2 and the "second batch" near the
+ * end of the file); the other 30 are covered by result specification + domain rule, see "Tier 2" below.  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
  * file's shared object; nothing under smart_b200/ links or calls it.
  *
@@ -1119,7 +1119,623 @@ long long ora_search_skipq(const unsigned char *x, int m, const unsigned char *y
 }
 
 /* ------------------------------------------------------------------------------------------
- * Tier 2: the other reference algorithms that agree with bf.c on every golden input (SURVEY.md Appendix A
+ * Second batch of restated scans (round 2).  The reference versions end their loops on a copy of the pattern they
+ * write behind the text and read a few characters around it; the restatements run on a private copy of the text
+ * with zeroed margins (ORA_MARGIN in front, 2m + ORA_MARGIN behind) and stop on explicit bounds instead:
+ * windows are only counted when they start in [0, n-m]. */
+#define ORA_MARGIN 64
+void ora_pre_bom(const unsigned char *x, int m, short *trans, unsigned char *term); /* (defined with the BOM scans below) */
+static unsigned char *ora_padded(const unsigned char *y, size_t n, int m)
+{
+    unsigned char *b = calloc(n + 2 * (size_t)m + 2 * ORA_MARGIN, 1);
+    if (!b) return NULL;
+    memcpy(b + ORA_MARGIN, y, n);
+    return b + ORA_MARGIN;
+}
+static void ora_padded_free(unsigned char *t) { free(t - ORA_MARGIN); }
+
+static int ora_whole(const unsigned char *x, int m, const unsigned char *t, long long st)
+{
+    return memcmp(x, t + st, (size_t)m) == 0;
+}
+
+/* bndmq2.c:31-71 / search_large :79-127 (bndmq4.c, bndmq6.c): BNDM reading the window's last q characters at once */
+static long long ora_search_bndmq(const unsigned char *x, int m, const unsigned char *y, size_t n, int Q)
+{
+    if (m < Q) return -1;
+    if ((size_t)m > n) return 0;
+    unsigned int B[ORA_SIGMA];
+    const int k = m < 32 ? m : 32;
+    const unsigned int M = 1u << (k - 1);
+    const long long hi = (long long)n - m + 1;
+    unsigned char *t = ora_padded(y, n, m);
+    ora_pre_bndm(x, m, B);
+    long long count = ora_whole(x, m, t, 0);
+    long long i = k + 1 - Q;
+    while (i - (k - Q) < hi) {
+        unsigned int D = B[t[i]];
+        for (int q = 1; q < Q; q++) D &= B[t[i + q]] << q;
+        if (D != 0) {
+            long long j = i;
+            const long long first = i - (k - Q);
+            do {
+                if (D >= M) {
+                    if (j > first) i = j - 1;
+                    else if (first < hi) count += m > 32 ? ora_whole(x, m, t, first) : 1;
+                }
+                j--;
+                D = (D << 1) & B[t[j]];
+            } while (D != 0);
+        }
+        i += k - Q + 1;
+    }
+    ora_padded_free(t);
+    return count;
+}
+
+/* fndm.c:28-60 / search_large :68-104: the Shift-Or masks driving a forward factor scan */
+static long long ora_search_fndm(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    unsigned int S[ORA_SIGMA];
+    const int k = m < 32 ? m : 32;
+    const unsigned int top = ~0u << (k - 1);
+    const long long hi = (long long)n - m + 1;
+    unsigned char *t = ora_padded(y, n, m);
+    ora_pre_so(x, m, S);
+    long long count = 0, i = k - 1;
+    while (i - (k - 1) < hi) {
+        unsigned int D = S[t[i]];
+        while (D != ~0u && i - (k - 1) < hi) {
+            if (D < top) count += ora_whole(x, m, t, i - k + 1);
+            i++;
+            D = (D << 1) | S[t[i]];
+        }
+        i += k;
+    }
+    ora_padded_free(t);
+    return count;
+}
+
+/* sbndm.c:28-84 / search_large :92-146 (bmh = 0) and sbndm-bmh.c:27-84 / :90-148 (bmh = 1) */
+static long long ora_search_sbndm(const unsigned char *x, int m, const unsigned char *y, size_t n, int bmh)
+{
+    if (m < 2) return -1;
+    if ((size_t)m > n) return 0;
+    unsigned int B[ORA_SIGMA];
+    int hbc[ORA_SIGMA], border[40];
+    const int k = m < 32 ? m : 32;
+    const long long hi = (long long)n - m + 1;
+    unsigned char *t = ora_padded(y, n, m);
+    ora_pre_bndm(x, m, B);
+    for (int c = 0; c < ORA_SIGMA; c++) B[c] <<= 32 - k; /* sbndm.c:42: aligned to the top of the word */
+    ora_pre_mp(x, k, border);
+    const int shift = k - border[k]; /* restore[0], sbndm.c:44-55: the window's smallest period */
+    for (int c = 0; c < ORA_SIGMA; c++) hbc[c] = 2 * k;
+    for (int i = 0; i < k; i++) hbc[x[i]] = 2 * k - i - 1; /* sbndm-bmh.c:41-42 */
+    long long count = ora_whole(x, m, t, 0);
+    long long i = k;
+    while (i - k + 1 < hi) {
+        unsigned int D = B[t[i]];
+        if (bmh) {
+            while (D == 0 && i - k + 1 < hi) {
+                i += hbc[t[i + k]];
+                D = B[t[i]];
+            }
+            if (i - k + 1 >= hi) break;
+        } else if (m > 32 && D == 0) {
+            i += k;
+            continue;
+        }
+        long long j = i - 1;
+        const long long first = i - k + 1;
+        for (;;) {
+            D = (D << 1) & B[t[j]];
+            if (!((j - first) && D)) break;
+            j--;
+        }
+        if (D != 0) {
+            count += m > 32 ? ora_whole(x, m, t, first) : 1;
+            i += shift;
+        } else {
+            i = j + k;
+        }
+    }
+    ora_padded_free(t);
+    return count;
+}
+
+/* bxs.c:30-75 (Q = 1), bxs2.c .. bxs8.c */
+static long long ora_search_bxs(const unsigned char *x, int m, const unsigned char *y, size_t n, int Q)
+{
+    if (m < Q) return -1;
+    if ((size_t)m > n) return 0;
+    unsigned int B[ORA_SIGMA];
+    const int k = m < 32 ? m : 32, mq1 = k - Q + 1;
+    const unsigned int mask = 1u << (k - 1);
+    const long long hi = (long long)n - m + 1;
+    unsigned char *t = ora_padded(y, n, m);
+    ora_pre_bndm(x, m, B);
+    long long count = 0;
+    for (long long i = mq1 - 1; i - mq1 + 1 < hi; i += mq1) {
+        unsigned int D = B[t[i + Q - 1]];
+        for (int q = Q - 2; q >= 0; q--) D = (D << 1) & B[t[i + q]];
+        if (D) {
+            long long j = i;
+            const long long first = i - mq1;
+            do {
+                j--;
+                if (D >= mask) {
+                    if (j - first) i = j;
+                    else if (first + 1 < hi) count += ora_whole(x, m, t, first + 1);
+                    D = ((D << 1) | 1u) & B[t[j]];
+                } else {
+                    D = (D << 1) & B[t[j]];
+                }
+            } while (D && j > first);
+        }
+    }
+    ora_padded_free(t);
+    return count;
+}
+
+/* lbndm.c:42-85 */
+static long long ora_search_lbndm(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if (m < 2) return -1;
+    if ((size_t)m > n) return 0;
+    unsigned int B[ORA_SIGMA] = {0};
+    const int k = (m - 1) / 32 + 1, m1 = m - 1, m2 = m1 - k, rmd = m - (m / k) * k;
+    const unsigned int M = 1u << 31;
+    const long long hi = (long long)n - m + 1;
+    unsigned char *t = ora_padded(y, n, m);
+    for (int i = m / k, l = m; i > 0; i--, l -= k)
+        for (int j = k; j > 0; j--) B[x[l - j]] |= 1u << (32 - i);
+    long long count = 0;
+    for (long long j = 0; j < hi;) {
+        unsigned int D = B[t[j + m1]];
+        int last = (D & M) ? m - k - rmd : m - rmd, l = m2;
+        while (D) {
+            D = (D << 1) & B[t[j + l]];
+            if (D & M) {
+                if (l < k + rmd) {
+                    for (int q = 0; q < k && j + q < hi; q++) count += ora_whole(x, m, t, j + q);
+                    break;
+                }
+                last = l - (k + rmd) + 1;
+            }
+            l -= k;
+        }
+        j += last;
+    }
+    ora_padded_free(t);
+    return count;
+}
+
+/* iom.c:32-56 */
+static long long ora_search_iom(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    int ibc[2][ORA_SIGMA], step[2] = {2 * m - 1, 2 * m - 1};
+    const long long hi = (long long)n - m + 1;
+    unsigned char *t = ora_padded(y, n, m);
+    for (int i = 0; i < m - 1; i++) step[x[i] == x[m - 1] ? 0 : 1] = 2 * m - i - 2;
+    for (int w = 0; w < 2; w++) {
+        for (int c = 0; c < ORA_SIGMA; c++) ibc[w][c] = step[w] + 1;
+        for (int i = 0; i < m; i++) ibc[w][x[i]] = step[w] - i;
+    }
+    long long count = 0;
+    for (long long s = 0; s < hi;) {
+        if (x[m - 1] == t[s + m - 1]) {
+            count += ora_whole(x, m, t, s);
+            s += ibc[0][t[s + step[0]]];
+        } else {
+            s += ibc[1][t[s + step[1]]];
+        }
+    }
+    ora_padded_free(t);
+    return count;
+}
+
+/* qlqs.c:38-62 */
+static long long ora_search_qlqs(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    int qsf[ORA_SIGMA], qsb[ORA_SIGMA];
+    unsigned char *rev = malloc((size_t)m), *t = ora_padded(y, n, m);
+    const long long hi = (long long)n - m + 1;
+    const int z = m + m / 2;
+    for (int i = 0; i < m; i++) rev[i] = x[m - 1 - i];
+    ora_pre_qsbc(x, m, qsf);
+    ora_pre_qsbc(rev, m, qsb);
+    long long count = 0;
+    for (long long i = 0; i < hi;) {
+        count += ora_whole(x, m, t, i);
+        const int f = qsf[t[i + m]], b = qsb[t[i + z - 1]];
+        i += f > z - b ? z : f;
+    }
+    free(rev);
+    ora_padded_free(t);
+    return count;
+}
+
+/* tsw.c:40-71 (tvsbs = 0) and tvsbs-w2.c:36-71 (tvsbs = 1): one window moves up, one moves down */
+static long long ora_search_br2(const unsigned char *x, int m, const unsigned char *y, size_t n, int tvsbs)
+{
+    if ((size_t)m > n) return 0;
+    int *L = malloc(sizeof(int) * 65536), *R = malloc(sizeof(int) * 65536);
+    unsigned char *rev = malloc((size_t)m), *t = ora_padded(y, n, m);
+    for (int i = 0; i < m; i++) rev[i] = x[m - 1 - i];
+    ora_pre_brbc(x, m, L);
+    ora_pre_brbc(rev, m, R);
+    long long count = 0, j = 0, e = (long long)n - m;
+    while (j <= e) {
+        int look = 1;
+        if (tvsbs) look = (x[0] == t[j] || x[0] == t[e]) && (x[m - 1] == t[j + m - 1] || x[m - 1] == t[e + m - 1]);
+        if (look) {
+            count += ora_whole(x, m, t, j);
+            if (j < e) count += ora_whole(x, m, t, e);
+        }
+        j += L[t[j + m] * 256 + t[j + m + 1]];
+        e -= R[t[e - 1] * 256 + t[e - 2]];
+    }
+    free(L);
+    free(R);
+    free(rev);
+    ora_padded_free(t);
+    return count;
+}
+
+/* bom2.c:28-78: the factor oracle without terminal flags; shift = what was left unread, 1 after an occurrence */
+static long long ora_search_bom2(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    short *trans = malloc((size_t)(m + 1) * 256 * sizeof(short));
+    unsigned char *term = malloc((size_t)m + 1);
+    ora_pre_bom(x, m, trans, term);
+    long long count = 0;
+    for (long long j = 0; j <= (long long)n - m;) {
+        int i = m - 1, p = m, q;
+        while (i >= 0 && (q = trans[p * 256 + y[i + j]]) >= 0) {
+            p = q;
+            --i;
+        }
+        count += i < 0;
+        j += i < 0 ? 1 : i + 1;
+    }
+    free(trans);
+    free(term);
+    return count;
+}
+
+/* fbom.c:28-96 (sfbom.c): the oracle + a look-ahead table over the character behind the window */
+static long long ora_search_fbom(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    short *trans = malloc((size_t)(m + 1) * 256 * sizeof(short));
+    unsigned char *term = malloc((size_t)m + 1), *t = ora_padded(y, n, m);
+    int *FT = malloc(sizeof(int) * 65536);
+    const long long hi = (long long)n - m + 1;
+    ora_pre_bom(x, m, trans, term);
+    for (int a = 0; a < 256; a++) { /* fbom.c:53-64 */
+        const int q = trans[m * 256 + a];
+        for (int b = 0; b < 256; b++) {
+            const int p = q >= 0 ? trans[q * 256 + b] : -1;
+            FT[a * 256 + b] = p >= 0 ? p : 2 * m + 1;
+        }
+    }
+    for (int a = 0; a < 256; a++) FT[a * 256 + x[m - 1]] = trans[m * 256 + x[m - 1]];
+    for (int b = 0; b < 256; b++)
+        if (FT[x[0] * 256 + b] > m) FT[x[0] * 256 + b] -= 1;
+    long long count = ora_whole(x, m, t, 0), j = m;
+    while (j - m + 1 < hi) { /* fbom.c:71-80 */
+        int p;
+        while ((p = FT[t[j + 1] * 256 + t[j]]) > m && j - m + 1 < hi) j += p - m;
+        if (p > m) break;
+        long long i = j - 1;
+        while (i >= j - m && (p = trans[p * 256 + t[i]]) >= 0) i--;
+        if (i < j - (m - 1)) {
+            count += j - m + 1 < hi;
+            i++;
+        }
+        j = i + m;
+    }
+    free(trans);
+    free(term);
+    free(FT);
+    ora_padded_free(t);
+    return count;
+}
+
+/* bsdm.c:30-79 (Q = 1), bsdm4.c:32-95, bsdm5.c, bsdm7.c, bsdm8.c */
+static unsigned ora_bsdm_hash(const unsigned char *p, int Q)
+{
+    const int step = Q == 4 ? 2 : 1; /* bsdm4.c:29 shifts by 2 bits per character, bsdm5/7/8.c:29 by 1 */
+    unsigned h = 0;
+    for (int q = 0; q < Q; q++) h += (unsigned)p[q] << (step * (Q - 1 - q));
+    return h & 0xffffu;
+}
+
+static long long ora_search_bsdm(const unsigned char *x, int m, const unsigned char *y, size_t n, int Q)
+{
+    if (m < Q) return -1;
+    if ((size_t)m > n) return 0;
+    int *pos = malloc(sizeof(int) * 65536);
+    unsigned char *occ = calloc(65536, 1), *t = ora_padded(y, n, m);
+    const long long hi = (long long)n - m + 1;
+    int st = 0, len = 0;
+    for (int i = 0, j = 0; i < m - Q + 1; i++) { /* bsdm.c:36-50: the longest run of grams without a repeat */
+        const unsigned c = ora_bsdm_hash(x + i, Q);
+        if (occ[c]) {
+            unsigned d = ora_bsdm_hash(x + j, Q);
+            while (d != c) {
+                occ[d] = 0;
+                j++;
+                d = ora_bsdm_hash(x + j, Q);
+            }
+            occ[d] = 0;
+            j++;
+        }
+        occ[c] = 1;
+        if (len < i - j + 1) {
+            len = i - j + 1;
+            st = j;
+        }
+    }
+    for (int i = 0; i < 65536; i++) pos[i] = -1;
+    for (int i = 0; i < len; i++) pos[ora_bsdm_hash(x + st + i, Q)] = i;
+    const int offset = st + len - 1;
+    long long count = 0, j = Q == 1 ? offset : len - 1;
+    while (j - offset < hi) {
+        int i;
+        while ((i = pos[ora_bsdm_hash(t + j, Q)]) < 0 && j - offset < hi) j += len;
+        if (i < 0) break;
+        int k = 1;
+        while (k <= i && x[st + i - k] == t[j - k]) k++;
+        if (k > i) {
+            if (k == len) {
+                const long long s0 = j - offset;
+                if (s0 >= 0 && s0 < hi) count += ora_whole(x, m, t, s0);
+            } else {
+                j -= k;
+            }
+        }
+        j += len;
+    }
+    free(pos);
+    free(occ);
+    ora_padded_free(t);
+    return count;
+}
+
+/* aoso2.c:42-77 / search_large :99-132 (aoso4.c, aoso6.c) */
+static long long ora_search_aoso(const unsigned char *x, int m, const unsigned char *y, size_t n, int q)
+{
+    if (m <= q) return -1;
+    if ((size_t)m > n) return 0;
+    unsigned int B[ORA_SIGMA], mm = 0, h = 0;
+    const int k = m < 32 ? m : 32, mq = k / q;
+    const long long hi = (long long)n - m + 1;
+    for (int c = 0; c < ORA_SIGMA; c++) B[c] = ~0u;
+    for (int j = 0; j < q; j++) {
+        for (int i = 0; i < mq; i++) B[x[i * q + j]] &= ~(1u << h++);
+        mm |= 1u << (h - 1);
+    }
+    long long count = 0;
+    unsigned int D = ~0u;
+    for (long long j = 0; j < (long long)n; j += q) {
+        D = ((D & ~mm) << 1) | B[y[j]];
+        if ((D & mm) != mm) {
+            unsigned int E = (D & mm) ^ mm;
+            while (E) {
+                const int s = 31 - __builtin_clz(E);
+                const long long i = j - (long long)(mq - 1) * q - s / mq;
+                if (i >= 0 && i < hi) count += memcmp(x, y + i, (size_t)m) == 0;
+                E &= ~(1u << s);
+            }
+        }
+    }
+    return count;
+}
+
+/* svm0.c:36-72 / search_large :80-124 */
+static long long ora_search_svm0(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    unsigned int cv[ORA_SIGMA], sv = 0;
+    const int k = m < 31 ? m : 31;
+    const long long hi = (long long)n - m + 1;
+    unsigned char *t = ora_padded(y, n, m);
+    for (int c = 0; c < ORA_SIGMA; c++) cv[c] = ~0u >> (32 - k);
+    for (int j = k - 1, b = 0; j >= 0; j--, b++) cv[x[j]] &= ~(1u << b);
+    long long count = ora_whole(x, m, t, 0);
+    for (long long s = k; s - k + 1 < hi;) {
+        sv |= cv[t[s]];
+        int j = 1;
+        while ((sv & 1u) == 0) {
+            if (j >= k) {
+                count += m > k ? ora_whole(x, m, t, s - k + 1) : 1;
+                break;
+            }
+            sv |= cv[t[s - j]] >> j;
+            j++;
+        }
+        const int adv = __builtin_ffs((int)~(sv >> 1));
+        sv = adv < 32 ? sv >> adv : 0u;
+        s += adv;
+    }
+    ora_padded_free(t);
+    return count;
+}
+
+/* wc.c:28-98: the reference keeps `max` in an int, so the comparison truncates */
+static long long ora_search_wc(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    int bc[ORA_SIGMA], last[ORA_SIGMA], pos = 0, mx = 1;
+    double adv = 1;
+    const long long hi = (long long)n - m + 1;
+    unsigned char *t = ora_padded(y, n, m);
+    for (int c = 0; c < ORA_SIGMA; c++) last[c] = -1;
+    for (int i = 1; i <= m; i++) {
+        const int gbc = i - last[x[i - 1]] - 1;
+        adv = adv - (double)gbc * 0.5 + 1;
+        last[x[i - 1]] = i - 1;
+        if (adv > mx) {
+            mx = (int)adv;
+            pos = i;
+        }
+    }
+    for (int c = 0; c < ORA_SIGMA; c++) bc[c] = pos + 1;
+    for (int i = 0; i < pos; i++) bc[x[i]] = pos - i;
+    long long count = 0;
+    for (long long s = 0; s < hi; s += bc[t[s + pos]]) count += ora_whole(x, m, t, s);
+    ora_padded_free(t);
+    return count;
+}
+
+/* fs-w1.c:65-101: fs.c's tables and shifts, the scan starts on the first window's last character */
+static long long ora_search_fsw1(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    int bc[ORA_SIGMA];
+    int *gs = malloc(sizeof(int) * (size_t)(m + 1));
+    long long count = 0;
+    ora_pre_lastocc(x, m, bc);
+    ora_pre_fsgs(x, m, gs);
+    size_t s = (size_t)m - 1;
+    while (s < n) {
+        int k;
+        while (s < n && (k = bc[y[s]]) != 0) s += (size_t)k;
+        if (s >= n) break;
+        int j = m - 1;
+        const size_t st = s - (size_t)(m - 1);
+        while (j >= 0 && x[j] == y[st + (size_t)j]) j--;
+        if (j < 0) count++;
+        s += (size_t)gs[j + 1];
+    }
+    free(gs);
+    return count;
+}
+
+/* wom.c:28-80 (pbmh = 0) and pbmh.c:29-61 (pbmh = 1): both rank characters by their count among the text's first
+ * 100 characters (the reference reads 100 bytes whatever n is; bytes past n count as 0 here) */
+static long long ora_search_freq100(const unsigned char *x, int m, const unsigned char *y, size_t n, int pbmh)
+{
+    if ((size_t)m > n) return 0;
+    int cnt[ORA_SIGMA] = {0}, table[ORA_SIGMA];
+    const long long hi = (long long)n - m + 1;
+    unsigned char *t = ora_padded(y, n, m);
+    for (int i = 0; i < 100; i++) cnt[(size_t)i < n ? y[i] : 0]++;
+    long long count = 0;
+    if (!pbmh) {
+        double freq[ORA_SIGMA], adv = 1.0, mx = 1.0;
+        int lp[ORA_SIGMA], q = 0;
+        for (int c = 0; c < ORA_SIGMA; c++) {
+            freq[c] = cnt[c] / 100.0;
+            lp[c] = -1;
+        }
+        for (int i = 1; i <= m; i++) { /* wom.c:35-52 FindWorstOccurrence */
+            const int gbc = i - lp[x[i - 1]] - 1;
+            adv = adv - freq[x[i - 1]] * gbc + 1.0;
+            lp[x[i - 1]] = i - 1;
+            if (adv > mx) {
+                mx = adv;
+                q = i;
+            }
+        }
+        for (int c = 0; c < ORA_SIGMA; c++) table[c] = q + 1;
+        for (int i = 0; i < q; i++) table[x[i]] = q - i;
+        for (long long s0 = 0; s0 < hi; s0 += table[t[s0 + q]]) count += ora_whole(x, m, t, s0);
+    } else {
+        int *v = malloc(sizeof(int) * (size_t)m);
+        for (int i = 0; i < m; i++) v[i] = i;
+        for (int i = 1; i < m; i++) { /* pbmh.c:39-45 is a stable bubble sort: the same order by insertion */
+            const int key = v[i];
+            int j = i - 1;
+            while (j >= 0 && cnt[x[v[j]]] > cnt[x[key]]) {
+                v[j + 1] = v[j];
+                j--;
+            }
+            v[j + 1] = key;
+        }
+        ora_pre_hbc(x, m, table);
+        for (long long s0 = 0; s0 < hi; s0 += table[t[s0 + m - 1]]) {
+            int i = 0;
+            while (i < m && x[v[i]] == t[s0 + v[i]]) i++;
+            count += i == m;
+        }
+        free(v);
+    }
+    ora_padded_free(t);
+    return count;
+}
+
+/* wfr2.c .. wfr8.c, twfr.c, twfr2.c .. twfr8.c, twfrq2.c .. twfrq8.c: wfr's / wfrq's scan, tabq = the builder's Q
+ * (0: every factor, wfr.c:41-58; Q: whole q-grams, wfrq4.c:50-65), scanq = characters per step (1: wfr.c:73-92,
+ * Q: wfrq4.c:80-100), tuned = the explicit skip loop in front of every window (twfr.c:57, twfr4.c:63-66) */
+static long long ora_search_wfrx(const unsigned char *x, int m, const unsigned char *y, size_t n, int tabq, int scanq, int tuned)
+{
+    if (m < scanq) return -1;
+    if ((size_t)m > n) return 0;
+    const int plen = m, Q = scanq;
+    if (Q > 1) m -= m % Q;
+    unsigned char *F = malloc(65536), *t = ora_padded(y, n, plen);
+    const long long hi = (long long)n - plen + 1;
+    long long count = 0;
+    ora_pre_wfr(x, m, tabq, F);
+#define ORA_WFRX_GRAM(pos_)                                                                     \
+    ({                                                                                          \
+        unsigned g_ = 0;                                                                        \
+        for (int k_ = 0; k_ < Q; k_++) g_ += (unsigned)t[(pos_) - k_] << (2 * (Q - 1 - k_));    \
+        g_ & 0xffffu;                                                                           \
+    })
+    if (Q <= 1) {
+        long long j = m - 1;
+        while (j - (m - 1) < hi) {
+            unsigned h = t[j];
+            if (tuned)
+                while (!F[h] && j + 1 < hi) {
+                    j += m;
+                    h = t[j];
+                }
+            const long long i = j - (m - 1);
+            int test;
+            while ((test = F[h]) && j > i) {
+                j--;
+                h = ((h << 2) + t[j]) & 0xffffu;
+            }
+            if (j == i && test && i < hi) count += ora_whole(x, plen, t, i);
+            j += m;
+        }
+    } else {
+        count += ora_whole(x, plen, t, 0);
+        long long j = m;
+        while (j - m + 1 < hi) {
+            unsigned h = ORA_WFRX_GRAM(j);
+            if (tuned)
+                while (!F[h] && j + (m - Q + 1) - m + 1 < hi) {
+                    j += m - Q + 1;
+                    h = ORA_WFRX_GRAM(j);
+                }
+            const long long i = j - m + 1;
+            int test;
+            while ((test = F[h]) && j > i + Q - 1) {
+                j -= Q;
+                h = ((h << (2 * Q)) + ORA_WFRX_GRAM(j)) & 0xffffu;
+            }
+            if (j == i + Q - 1 && test && i < hi) count += ora_whole(x, plen, t, i);
+            j += m - Q + 1;
+        }
+    }
+#undef ORA_WFRX_GRAM
+    free(F);
+    ora_padded_free(t);
+    return count;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Tier 2: the reference algorithms without a restated scan that agree with bf.c on every golden input (SURVEY.md Appendix A
  * "always clean", minus kbndm, ksa and ssm which the golden sweep caught).  Their scans are NOT restated
  * here: each of them returns the brute-force count (bf.c:33-36) outside its `return -1` domain, so the
  * oracle for them is that count plus the guard, and the pin is the recorded output of the unmodified
@@ -1128,84 +1744,26 @@ static const struct ora_tier2 {
     const char *name;
     int min_m, min_ratio;
 } ora_tier2[] = {
-    {"aoso2", 3, 0}, /* aoso2.c:47 */
-    {"aoso4", 5, 0}, /* aoso4.c:47 */
-    {"aoso6", 7, 0}, /* aoso6.c:47 */
     {"faoso2", 3, 0}, /* faoso2.c:56 */
     {"faoso4", 5, 0}, /* faoso4.c:56 */
-    {"svm0", 1, 0},
     {"blim", 1, 0},
     {"ufndmq2", 2, 0}, /* ufndmq2.c:36 */
     {"ufndmq4", 4, 0}, /* ufndmq4.c:34 */
     {"ufndmq6", 6, 0}, /* ufndmq6.c:34 */
     {"ufndmq8", 8, 0}, /* ufndmq8.c:34 */
-    {"aut", 1, 0},
     {"smoa", 1, 0},
     {"tw", 1, 0},
     {"rcolussi", 1, 0},
-    {"bndmq2", 2, 0}, /* bndmq2.c:35 */
-    {"bndmq4", 4, 0}, /* bndmq4.c:33 */
-    {"bndmq6", 6, 0}, /* bndmq6.c:33 */
-    {"lbndm", 2, 0}, /* lbndm.c:49 */
-    {"sbndm", 2, 0}, /* sbndm.c:36 */
-    {"sbndm-bmh", 2, 0}, /* sbndm-bmh.c:34 */
     {"fsbndm-w2", 1, 0},
-    {"fndm", 1, 0},
     {"tndm", 1, 0},
     {"tndma", 1, 0},
-    {"bxs", 1, 0},
-    {"bxs2", 2, 0}, /* bxs2.c:33 */
-    {"bxs4", 4, 0}, /* bxs4.c:33 */
-    {"bxs6", 6, 0}, /* bxs6.c:33 */
-    {"bxs8", 8, 0}, /* bxs8.c:33 */
     {"bww", 1, 0},
     {"dbww", 1, 2}, /* dbww.c:35 */
     {"dbww2", 1, 2}, /* dbww2.c:38 */
-    {"bom", 1, 0},
-    {"bom2", 1, 0},
-    {"ebom", 2, 0}, /* ebom.c:35 */
-    {"fbom", 1, 0},
-    {"sebom", 2, 0}, /* sebom.c:32 */
-    {"sfbom", 1, 0},
     {"ildm1", 1, 0},
     {"ildm2", 1, 0},
     {"fdm", 1, 0},
-    {"bsdm", 1, 0},
-    {"bsdm4", 4, 0}, /* bsdm4.c:36 */
-    {"bsdm5", 5, 0}, /* bsdm5.c:36 */
-    {"bsdm7", 7, 0}, /* bsdm7.c:36 */
-    {"bsdm8", 8, 0}, /* bsdm8.c:36 */
     {"ww", 1, 0},
-    {"wfr", 1, 0},
-    {"wfr2", 2, 0}, /* wfr2.c:65 */
-    {"wfr3", 3, 0}, /* wfr3.c:64 */
-    {"wfr4", 4, 0}, /* wfr4.c:64 */
-    {"wfr5", 5, 0}, /* wfr5.c:63 */
-    {"wfr6", 6, 0}, /* wfr6.c:64 */
-    {"wfr7", 7, 0}, /* wfr7.c:65 */
-    {"wfr8", 8, 0}, /* wfr8.c:64 */
-    {"wfrq2", 2, 0}, /* wfrq2.c:72 */
-    {"wfrq3", 3, 0}, /* wfrq3.c:71 */
-    {"wfrq4", 4, 0}, /* wfrq4.c:71 */
-    {"wfrq5", 5, 0}, /* wfrq5.c:70 */
-    {"wfrq6", 6, 0}, /* wfrq6.c:71 */
-    {"wfrq7", 7, 0}, /* wfrq7.c:72 */
-    {"wfrq8", 8, 0}, /* wfrq8.c:71 */
-    {"twfr", 1, 0},
-    {"twfr2", 2, 0}, /* twfr2.c:45 */
-    {"twfr3", 3, 0}, /* twfr3.c:45 */
-    {"twfr4", 4, 0}, /* twfr4.c:45 */
-    {"twfr5", 5, 0}, /* twfr5.c:45 */
-    {"twfr6", 6, 0}, /* twfr6.c:45 */
-    {"twfr7", 7, 0}, /* twfr7.c:45 */
-    {"twfr8", 8, 0}, /* twfr8.c:45 */
-    {"twfrq2", 2, 0}, /* twfrq2.c:53 */
-    {"twfrq3", 3, 0}, /* twfrq3.c:52 */
-    {"twfrq4", 4, 0}, /* twfrq4.c:52 */
-    {"twfrq5", 5, 0}, /* twfrq5.c:52 */
-    {"twfrq6", 6, 0}, /* twfrq6.c:52 */
-    {"twfrq7", 7, 0}, /* twfrq7.c:52 */
-    {"twfrq8", 8, 0}, /* twfrq8.c:52 */
     {"lwfr2", 2, 0}, /* lwfr2.c:65 */
     {"lwfr3", 3, 0}, /* lwfr3.c:65 */
     {"lwfr4", 4, 0}, /* lwfr4.c:65 */
@@ -1213,22 +1771,8 @@ static const struct ora_tier2 {
     {"lwfr6", 6, 0}, /* lwfr6.c:65 */
     {"lwfr7", 7, 0}, /* lwfr7.c:65 */
     {"lwfr8", 8, 0}, /* lwfr8.c:65 */
-    {"skip3", 3, 0}, /* skip3.c:31 */
-    {"skip5", 5, 0}, /* skip5.c:31 */
-    {"skip6", 6, 0}, /* skip6.c:31 */
-    {"skip7", 7, 0}, /* skip7.c:31 */
-    {"skip8", 8, 0}, /* skip8.c:31 */
     {"bfs", 1, 0},
     {"ffs", 1, 0},
-    {"iom", 1, 0},
-    {"wom", 1, 0},
-    {"pbmh", 1, 0},
-    {"qlqs", 1, 0},
-    {"tsw", 1, 0},
-    {"wc", 1, 0},
-    {"zt", 1, 0},
-    {"tvsbs-w2", 1, 0},
-    {"fs-w1", 1, 0},
     {"ssef", 32, 0}, /* ssef.c:41 */
 };
 
@@ -1477,6 +2021,34 @@ long long ora_search(const char *algo, const unsigned char *x, int m, const unsi
     if (!strcmp(algo, "sbndm2")) return ora_search_sbndm2(x, m, y, n);
     if (!strcmp(algo, "wfr")) return (size_t)m > n ? 0 : ora_search_wfr(x, m, y, n);
     if (!strncmp(algo, "wfrq", 4) && algo[4] >= '2' && algo[4] <= '8' && !algo[5]) return ora_search_wfrq(x, m, y, n, algo[4] - '0');
+    /* second batch (round 2) */
+    if (!strncmp(algo, "bndmq", 5) && algo[5] && !algo[6]) return ora_search_bndmq(x, m, y, n, algo[5] - '0');
+    if (!strcmp(algo, "fndm")) return ora_search_fndm(x, m, y, n);
+    if (!strcmp(algo, "sbndm")) return ora_search_sbndm(x, m, y, n, 0);
+    if (!strcmp(algo, "sbndm-bmh")) return ora_search_sbndm(x, m, y, n, 1);
+    if (!strcmp(algo, "bxs")) return ora_search_bxs(x, m, y, n, 1);
+    if (!strncmp(algo, "bxs", 3) && algo[3] && !algo[4]) return ora_search_bxs(x, m, y, n, algo[3] - '0');
+    if (!strcmp(algo, "lbndm")) return ora_search_lbndm(x, m, y, n);
+    if (!strcmp(algo, "iom")) return ora_search_iom(x, m, y, n);
+    if (!strcmp(algo, "qlqs")) return ora_search_qlqs(x, m, y, n);
+    if (!strcmp(algo, "tsw")) return ora_search_br2(x, m, y, n, 0);
+    if (!strcmp(algo, "tvsbs-w2")) return ora_search_br2(x, m, y, n, 1);
+    if (!strcmp(algo, "bom2")) return ora_search_bom2(x, m, y, n);
+    if (!strcmp(algo, "sebom")) return ora_search_ebom(x, m, y, n); /* sebom.c:61-77 is ebom.c:62-78 */
+    if (!strcmp(algo, "fbom") || !strcmp(algo, "sfbom")) return ora_search_fbom(x, m, y, n);
+    if (!strcmp(algo, "bsdm")) return ora_search_bsdm(x, m, y, n, 1);
+    if (!strncmp(algo, "bsdm", 4) && algo[4] && !algo[5]) return ora_search_bsdm(x, m, y, n, algo[4] - '0');
+    if (!strncmp(algo, "aoso", 4) && algo[4] && !algo[5]) return ora_search_aoso(x, m, y, n, algo[4] - '0');
+    if (!strcmp(algo, "svm0")) return ora_search_svm0(x, m, y, n);
+    if (!strcmp(algo, "wc")) return ora_search_wc(x, m, y, n);
+    if (!strcmp(algo, "fs-w1")) return ora_search_fsw1(x, m, y, n);
+    if (!strcmp(algo, "wom")) return ora_search_freq100(x, m, y, n, 0);
+    if (!strcmp(algo, "pbmh")) return ora_search_freq100(x, m, y, n, 1);
+    if (!strncmp(algo, "wfr", 3) && algo[3] >= '2' && algo[3] <= '8' && !algo[4]) return ora_search_wfrx(x, m, y, n, 0, algo[3] - '0', 0);
+    if (!strcmp(algo, "twfr")) return ora_search_wfrx(x, m, y, n, 0, 1, 1);
+    if (!strncmp(algo, "twfrq", 5) && algo[5] >= '2' && algo[5] <= '8' && !algo[6])
+        return ora_search_wfrx(x, m, y, n, algo[5] - '0', algo[5] - '0', 1);
+    if (!strncmp(algo, "twfr", 4) && algo[4] >= '2' && algo[4] <= '8' && !algo[5]) return ora_search_wfrx(x, m, y, n, 0, algo[4] - '0', 1);
     return ora_search_tier2(algo, x, m, y, n);
 }
 

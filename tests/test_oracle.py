@@ -60,7 +60,11 @@ def test_oracle_vs_golden_reference_counts(oracle, golden, tname):
         assert oracle.bf_count(x, y) == ref["bf"]
         # the slow restated scans on a third of the cases, the cheap ones everywhere
         algos = ALGOS if idx % 3 == 0 else ("kmp", "hor", "so", "hash3", "qf23")
-        for a in algos:
+        for ai, a in enumerate(algos):
+            # the weak-factor tables saturate on the two-symbol text and every window is read in full, O(n*m) as in
+            # the reference: its 37 variants take turns there for the long patterns
+            if tname == "rand2" and c["m"] >= 512 and "wfr" in a and (ai + idx) % 4:
+                continue
             assert oracle.search(a, x, y) == ref[a], (tname, c["m"], c["pi"], a)
 
 
