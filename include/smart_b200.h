@@ -68,8 +68,11 @@ extern "C" {
                                         (kmpNext / mpNext, hbc, Shift-Or/And masks, HASHq shift table - bit-identical to
                                         the reference's; also bmBc+bmGs, qsBc, the Karp-Rabin hash, the QF bit table) is
                                         uploaded, staged in shared memory and drives the scan loop of kmp.c / mp.c / hor.c /
-                                        bm.c / qs.c / raita.c / tunedbm.c / so.c / sa.c / kr.c / hash3,5,8.c / qf*.c / aut.c / bom.c / ebom.c / sbndm2.c (m <= 32) / bndm.c / br.c / tvsbs.c / smith.c / skip.c / fjs.c / ssabs.c / fs.c / graspm.c / tbm.c / ac.c, one
-                                        thread per text segment.
+                                        bm.c / qs.c / raita.c / tunedbm.c / so.c / sa.c / kr.c / hash3,5,8.c / qf*.c / aut.c /
+                                        bom.c / ebom.c / sbndm2.c (m <= 32) / bndm.c / br.c / tvsbs.c / smith.c / skip.c /
+                                        fjs.c / ssabs.c / fs.c / graspm.c / tbm.c / ac.c and, by the end of round 2, 111 of the
+                                        143 registered algorithms (the list is sb_timing.filter_kind below), one thread per
+                                        text segment.
                                         Same counts as every other mode; slower than the default fingerprint filters
                                         (DESIGN.md section 3.4).  Count only; other algorithms ignore the flag. */
 
