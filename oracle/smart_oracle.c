@@ -1594,6 +1594,233 @@ static long long ora_search_wc(const unsigned char *x, int m, const unsigned cha
     return count;
 }
 
+/* lwfr2.c .. lwfr8.c (lwfr4.c:60-125): the weak-factor scan of wfrQ in front of a KMP automaton that remembers how far
+ * the text has been compared (tp) and in which state (st), which makes the scan linear.  kmpNext is built over the whole
+ * pattern by the bounded variant of lwfr4.c:26-38, the factor table over the pattern cut to a multiple of Q. */
+static long long ora_search_lwfr(const unsigned char *x, int m, const unsigned char *y, size_t n, int Q)
+{
+    if (m < Q) return -1;
+    if ((size_t)m > n) return 0;
+    const int plen = m;
+    int *kmpNext = malloc(sizeof(int) * (size_t)(plen + 1));
+    {
+        int i = 0, j = kmpNext[0] = -1;
+        while (i < plen) {
+            while (j > -1 && x[i] != x[j]) j = kmpNext[j];
+            i++;
+            j++;
+            kmpNext[i] = (i < plen && x[i] == x[j]) ? kmpNext[j] : j;
+        }
+    }
+    m -= m % Q;
+    const int mm1 = m - 1, mq = m - Q + 1;
+    unsigned char *F = malloc(65536), *t = ora_padded(y, n, plen);
+    const long long nn = (long long)n;
+    ora_pre_wfr(x, m, 0, F);
+#define ORA_LWFR_GRAM(pos_)                                                                     \
+    ({                                                                                          \
+        unsigned g_ = 0;                                                                        \
+        for (int k_ = 0; k_ < Q; k_++) g_ += (unsigned)t[(pos_) - k_] << (2 * (Q - 1 - k_));    \
+        g_ & 0xffffu;                                                                           \
+    })
+    long long count = ora_whole(x, plen, t, 0), tp = 0, j = m;
+    int st = 0;
+    while (j < nn) {
+        unsigned h = ORA_LWFR_GRAM(j);
+        while (!F[h] && j < nn) { /* (the reference stops on the pattern copy behind the text) */
+            j += mq;
+            h = ORA_LWFR_GRAM(j);
+        }
+        if (j >= nn) break;
+        long long lf = j - m + Q, b = lf;
+        if (b < tp) b = tp - 1;
+        int test;
+        while ((test = F[h]) && j > b) {
+            j -= Q;
+            h = ((h << (2 * Q)) + ORA_LWFR_GRAM(j)) & 0xffffu;
+        }
+        if (j <= b && test) {
+            lf -= Q - 1;
+            if (lf > tp) { /* restart the automaton at the window */
+                tp = lf;
+                st = 0;
+            }
+            while (st >= tp - lf) {
+                while (st < plen && tp < nn && x[st] == t[tp]) {
+                    st++;
+                    tp++;
+                }
+                if (st == plen) count++;
+                st = kmpNext[st];
+                if (st < 0) {
+                    st++;
+                    tp++;
+                }
+            }
+            j = tp + mm1 - st;
+        } else {
+            j += m - Q + 1;
+        }
+    }
+#undef ORA_LWFR_GRAM
+    free(kmpNext);
+    free(F);
+    ora_padded_free(t);
+    return count;
+}
+
+/* ufndmq2.c:33-78 / search_large :87-137 (ufndmq4.c, ufndmq6.c, ufndmq8.c): Shift-Or reading q characters at a time,
+ * jumping m ahead while the state is all ones.  The loop of the reference has no bound of its own: it returns when
+ * it verifies an occurrence that ends behind the text, which the two pattern copies it writes at y[n..n+2m)
+ * guarantee (:44, :93).  The restatement scans a private copy of the text that carries the same two copies. */
+static long long ora_search_ufndmq(const unsigned char *x, int m, const unsigned char *y, size_t n, int q)
+{
+    if (m < q) return -1;
+    if ((size_t)m > n) return 0;
+    const int plen = m, me = m + q > 32 ? 32 - q : m, mq = me + q - 1;
+    const unsigned int c = (1u << (q - 1)) - 1u, mm = 1u << (me + q - 2), mask = (1u << (me - 1)) - 1u;
+    const long long nn = (long long)n;
+    unsigned char *buf = calloc(n + 4 * (size_t)plen + 2 * ORA_MARGIN, 1), *t = buf + ORA_MARGIN;
+    unsigned int B[ORA_SIGMA];
+    memcpy(t, y, n);
+    memcpy(t + n, x, (size_t)plen);
+    memcpy(t + n + plen, x, (size_t)plen);
+    for (int j = 0; j < ORA_SIGMA; j++) B[j] = ~(c << me);
+    for (int j = 0; j < me; j++) B[x[j]] &= ~(1u << j);
+    long long count = memcmp(x, t, (size_t)plen) == 0, i = 0;
+    unsigned int D = ~0u, F;
+#define ORA_UFNDM_GRAM(i_)                                              \
+    ({                                                                  \
+        unsigned int g_ = 0;                                            \
+        for (int s_ = 0; s_ < q; s_++) g_ |= B[t[(i_) - s_]] << s_;     \
+        g_;                                                             \
+    })
+    for (;;) {
+        while ((D | c) == ~0u && i < nn + 3 * plen) {
+            i += me;
+            D = (D << me) | ORA_UFNDM_GRAM(i);
+        }
+        if (i >= nn + 3 * plen) break; /* (never reached: the copies behind the text end the scan below) */
+        if ((F = ~(D | mask)) != 0) {
+            for (long long k = i - mq + 1; F; F <<= 1, k++)
+                if (F >= mm) {
+                    if (memcmp(t + k, x, (size_t)plen) == 0) {
+                        if (k + plen > nn) goto done;
+                        count++;
+                    }
+                    F -= mm;
+                }
+        }
+        i += q;
+        D = (D << q) | ORA_UFNDM_GRAM(i);
+    }
+done:
+#undef ORA_UFNDM_GRAM
+    free(buf);
+    return count;
+}
+
+/* bww.c:28-95 / search_large :103-177: Bit-parallel Wide Window.  Every m-th text character (k*m - 1) is a window
+ * centre: a forward automaton collects which pattern prefixes end right of it (pre), a backward automaton which
+ * suffixes start left of it, both together an occurrence.  Patterns over 30 characters use their 30-character prefix
+ * and compare the rest.  The tail behind the last centre is compared position by position; the reference compares
+ * only the 30-character prefix there (:170-173) - the restatement compares the whole pattern (the true count). */
+static long long ora_search_bww(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    const int plen = m;
+    if (m > 30) m = 30;
+    unsigned int B[ORA_SIGMA] = {0}, C[ORA_SIGMA] = {0};
+    const unsigned int s = 1u << (m - 1), tt = 1u << (m - 1);
+    const long long nn = (long long)n;
+    unsigned char *t = ora_padded(y, n, plen);
+    for (int i = 0; i < m; i++) {
+        B[x[i]] |= 1u << i;
+        C[x[m - 1 - i]] |= 1u << i;
+    }
+    long long count = 0, end = nn / m + (nn % m > 0);
+    for (long long k = 1; k < end; k++) {
+        const long long c = k * m - 1;
+        int r = 0, left = 0, ell = 0;
+        unsigned int pre = 0, R = ~0u, cur = s, L = ~0u;
+        while (R != 0 && c + r < nn) {
+            R &= B[t[c + r]];
+            ++r;
+            if (R & s) {
+                pre |= cur;
+                if (m + 1 - r > left) left = m + 1 - r;
+            }
+            R <<= 1;
+            cur >>= 1;
+        }
+        cur = 1;
+        while (L != 0 && left > ell) {
+            L &= C[t[c - ell]];
+            if ((L & tt) && (cur & pre)) {
+                const long long first = c - ell;
+                if (first + plen <= nn && memcmp(x + m, t + first + m, (size_t)(plen - m)) == 0) count++;
+            }
+            L <<= 1;
+            cur <<= 1;
+            ++ell;
+        }
+    }
+    for (long long j = (end - 1) * m; j <= nn - plen; j++) count += ora_whole(x, plen, t, j);
+    ora_padded_free(t);
+    return count;
+}
+
+/* dbww.c:28-102 (dbww2.c is the same scan): two window centres at a time, their automata side by side in the two
+ * halves of a word over the pattern's first min(m, 16) characters; n/m < 2 -> -1 (:35, m already cut to 16) */
+static long long ora_search_dbww(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    const int plen = m;
+    if (m > 16) m = 16;
+    if (n / (size_t)m < 2) return -1;
+    if ((size_t)plen > n) return 0;
+    unsigned int B[ORA_SIGMA] = {0}, C[ORA_SIGMA] = {0};
+    const long long nn = (long long)n;
+    unsigned char *t = ora_padded(y, n, plen);
+    for (int i = 0; i < m; i++) {
+        B[x[i]] |= 1u << i;
+        C[x[m - 1 - i]] |= 1u << i;
+    }
+    const unsigned int H1 = 1u << (m - 1), M = (H1 << 16) | H1;
+    long long count = 0, end = nn / m + (nn % m > 0), j2 = -1;
+    for (long long k = 1; k < end - 1; k += 2) {
+        const long long j1 = k * m - 1;
+        j2 = (k + 1) * m - 1;
+        int l = 0, left = 0;
+        unsigned int suf = 0, D = ~0u, H;
+        while (D) { /* left to right, dbww.c:59-69 */
+            D &= (B[t[j1 + l]] << 16) | B[t[j2 + l]];
+            H = D & M;
+            if (H) {
+                suf |= H >> l;
+                if (left == 0) left = m - l;
+            }
+            ++l;
+            D <<= 1;
+        }
+        D = ~0u;
+        l = 0;
+        while (D != 0 && left > l) { /* right to left, dbww.c:71-90 */
+            D &= (C[t[j1 - l]] << 16) | C[t[j2 - l]];
+            H = D & M;
+            if (H) {
+                H &= suf << (m - 1 - l);
+                if (H & 0xffff0000u) count += memcmp(x + m, t + j1 - l + m, (size_t)(plen - m)) == 0;
+                if (H & 0x0000ffffu) count += memcmp(x + m, t + j2 - l + m, (size_t)(plen - m)) == 0;
+            }
+            D <<= 1;
+            ++l;
+        }
+    }
+    for (long long k = j2 + 1; k <= nn - plen; k++) count += ora_whole(x, plen, t, k); /* dbww.c:96-99 */
+    ora_padded_free(t);
+    return count;
+}
+
 /* fs-w1.c:65-101: fs.c's tables and shifts, the scan starts on the first window's last character */
 static long long ora_search_fsw1(const unsigned char *x, int m, const unsigned char *y, size_t n)
 {
@@ -1747,30 +1974,16 @@ static const struct ora_tier2 {
     {"faoso2", 3, 0}, /* faoso2.c:56 */
     {"faoso4", 5, 0}, /* faoso4.c:56 */
     {"blim", 1, 0},
-    {"ufndmq2", 2, 0}, /* ufndmq2.c:36 */
-    {"ufndmq4", 4, 0}, /* ufndmq4.c:34 */
-    {"ufndmq6", 6, 0}, /* ufndmq6.c:34 */
-    {"ufndmq8", 8, 0}, /* ufndmq8.c:34 */
     {"smoa", 1, 0},
     {"tw", 1, 0},
     {"rcolussi", 1, 0},
     {"fsbndm-w2", 1, 0},
     {"tndm", 1, 0},
     {"tndma", 1, 0},
-    {"bww", 1, 0},
-    {"dbww", 1, 2}, /* dbww.c:35 */
-    {"dbww2", 1, 2}, /* dbww2.c:38 */
     {"ildm1", 1, 0},
     {"ildm2", 1, 0},
     {"fdm", 1, 0},
     {"ww", 1, 0},
-    {"lwfr2", 2, 0}, /* lwfr2.c:65 */
-    {"lwfr3", 3, 0}, /* lwfr3.c:65 */
-    {"lwfr4", 4, 0}, /* lwfr4.c:65 */
-    {"lwfr5", 5, 0}, /* lwfr5.c:65 */
-    {"lwfr6", 6, 0}, /* lwfr6.c:65 */
-    {"lwfr7", 7, 0}, /* lwfr7.c:65 */
-    {"lwfr8", 8, 0}, /* lwfr8.c:65 */
     {"bfs", 1, 0},
     {"ffs", 1, 0},
     {"ssef", 32, 0}, /* ssef.c:41 */
@@ -2040,6 +2253,10 @@ long long ora_search(const char *algo, const unsigned char *x, int m, const unsi
     if (!strncmp(algo, "bsdm", 4) && algo[4] && !algo[5]) return ora_search_bsdm(x, m, y, n, algo[4] - '0');
     if (!strncmp(algo, "aoso", 4) && algo[4] && !algo[5]) return ora_search_aoso(x, m, y, n, algo[4] - '0');
     if (!strcmp(algo, "svm0")) return ora_search_svm0(x, m, y, n);
+    if (!strncmp(algo, "lwfr", 4) && algo[4] >= '2' && algo[4] <= '8' && !algo[5]) return ora_search_lwfr(x, m, y, n, algo[4] - '0');
+    if (!strncmp(algo, "ufndmq", 6) && algo[6] && !algo[7]) return ora_search_ufndmq(x, m, y, n, algo[6] - '0');
+    if (!strcmp(algo, "bww")) return ora_search_bww(x, m, y, n);
+    if (!strcmp(algo, "dbww") || !strcmp(algo, "dbww2")) return ora_search_dbww(x, m, y, n);
     if (!strcmp(algo, "wc")) return ora_search_wc(x, m, y, n);
     if (!strcmp(algo, "fs-w1")) return ora_search_fsw1(x, m, y, n);
     if (!strcmp(algo, "wom")) return ora_search_freq100(x, m, y, n, 0);
