@@ -1821,6 +1821,271 @@ static long long ora_search_dbww(const unsigned char *x, int m, const unsigned c
     return count;
 }
 
+/* tndm.c:28-92 / search_large :99-165 (variant = 0) and tndma.c (variant = 1, the extra shift of :67 / :142): Two-way
+ * NDM.  When the window's last character is not the pattern's last, the window is first extended to the RIGHT until
+ * some pattern position fits (or nothing does), then read right to left like BNDM. */
+static long long ora_search_tndm(const unsigned char *x, int m, const unsigned char *y, size_t n, int variant)
+{
+    if ((size_t)m > n) return 0;
+    const int plen = m;
+    if (m > 32) m = 32;
+    unsigned int B[ORA_SIGMA], sv;
+    int *restore = malloc(sizeof(int) * (size_t)(m + 2));
+    const long long nn = (long long)n;
+    unsigned char *t = ora_padded(y, n, plen);
+    ora_pre_bndm(x, m, B);
+    {
+        int last = m;
+        sv = ~0u >> (32 - m);
+        for (int i = m - 1; i >= 0; i--) { /* tndm.c:43-51 */
+            sv &= B[x[i]];
+            if ((sv & (1u << (m - 1))) && i > 0) last = i;
+            restore[m - i] = last;
+            sv <<= 1;
+        }
+    }
+    long long count = 0, j = m - 1;
+    while (j < nn) {
+        int i = 0, last = m;
+        unsigned int d = B[t[j]];
+        if ((d & 1u) == 0) {
+            while (d != 0 && !(d & (1u << i))) {
+                i++;
+                d &= B[t[j + i]] << i;
+            }
+            if (d == 0 || j + i >= nn) {
+                if (variant && B[t[j + i]] == 0) last = i + m;
+                goto over;
+            }
+            j += i;
+            last = restore[i];
+        }
+        do {
+            i++;
+            if (d & (1u << (m - 1))) {
+                if (i < m) {
+                    last = m - i;
+                } else {
+                    const long long first = j - m + 1;
+                    if (first + plen <= nn && memcmp(x + m, t + first + m, (size_t)(plen - m)) == 0) count++;
+                    goto over;
+                }
+            }
+            d <<= 1;
+            d &= B[t[j - i]];
+        } while (d != 0);
+    over:
+        j += last;
+    }
+    free(restore);
+    ora_padded_free(t);
+    return count;
+}
+
+/* faoso2.c:47-106 / search_large :127-179 (faoso4.c): AOSO reading u = 2 sampled characters per step; every
+ * sub-automaton carries one spare bit so that two shifts fit between the tests (masq clears what the spare bits
+ * collect).  The alignments named by the zero top bits are compared in full; only those inside the text count. */
+static long long ora_search_faoso(const unsigned char *x, int m, const unsigned char *y, size_t n, int q)
+{
+    const int u = 2, plen = m;
+    if (m > 32 - u + 1) m = 32 - u + 1;
+    else if (m <= q) return -1;
+    if ((size_t)plen > n) return 0;
+    unsigned int B[ORA_SIGMA], masq = 0, mm = 0, h;
+    const int mq = m / q;
+    const long long nn = (long long)n, hi = nn - plen + 1;
+    unsigned char *t = ora_padded(y, n, plen);
+    h = (unsigned)mq;
+    for (int j = 0; j < q; j++) { /* faoso2.c:62-69 */
+        masq |= 1u << h;
+        h += (unsigned)mq + 1;
+    }
+    for (int c = 0; c < ORA_SIGMA; c++) B[c] = ~0u;
+    h = 0;
+    for (int j = 0; j < q; j++) { /* faoso2.c:72-81 */
+        for (int i = 0; i < mq; i++) B[x[i * q + j]] &= ~(1u << h++);
+        mm |= 1u << (h - 1);
+        ++h;
+        mm |= 1u << (h - 1);
+    }
+    long long count = 0;
+    unsigned int D = ~mm;
+    for (long long j = 0; j < nn; j += u * q) {
+        D = (D << 1) | (B[t[j]] & ~masq);
+        D = (D << 1) | (B[t[j + q]] & ~masq);
+        if ((D & mm) != mm) { /* verify, faoso2.c:28-45, called with j + (u-1)*q */
+            unsigned int E = (D & mm) ^ mm;
+            const int mq1 = mq - 1, v = mq1 + u;
+            while (E) {
+                const int sbit = 31 - __builtin_clz(E), z = sbit % v - mq1;
+                const long long i = j + (u - 1) * q - (long long)mq1 * q - (sbit / v + (long long)z * q);
+                if (i >= 0 && i < hi) count += ora_whole(x, plen, t, i);
+                E &= ~(1u << sbit);
+            }
+        }
+        D &= ~mm;
+    }
+    ora_padded_free(t);
+    return count;
+}
+
+/* bfs.c:28-96 Backward-Fast-Search and ffs.c:28-80 Forward-Fast-Search: Fast-Search with a good-suffix table that
+ * also depends on one text character - the one that broke the comparison (bfs, gs[k][y[j]]) or the one behind the
+ * window (ffs, gs[k][y[s+1]]).  Both end their skip loop on what they write behind the text (bfs.c:76: the pattern;
+ * ffs.c:64-65: m+1 copies of its last character); the restatements scan a private copy carrying the same bytes. */
+static long long ora_search_bfs(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    int bc[ORA_SIGMA], *temp = malloc(sizeof(int) * (size_t)(m + 2));
+    int *gs = malloc(sizeof(int) * (size_t)(m + 1) * ORA_SIGMA);
+    const long long nn = (long long)n;
+    unsigned char *buf = calloc(n + 3 * (size_t)m + 2 * ORA_MARGIN, 1), *t = buf + ORA_MARGIN;
+    memcpy(t, y, n);
+    memcpy(t + n, x, (size_t)m);
+    ora_pre_lastocc(x, m, bc);
+#define GS(i_, c_) gs[(size_t)(i_) * ORA_SIGMA + (c_)]
+    { /* PreBFS, bfs.c:28-62 */
+        int suffix_len = 1, last = m - 1, i;
+        for (i = 0; i <= m; i++)
+            for (int c = 0; c < ORA_SIGMA; c++) GS(i, c) = m;
+        for (i = 0; i <= m; i++) temp[i] = -1;
+        for (i = m - 2; i >= 0; i--)
+            if (x[i] == x[last]) {
+                temp[last] = i;
+                last = i;
+            }
+        for (suffix_len = 2; suffix_len <= m; suffix_len++) {
+            const int row = m - suffix_len + 1;
+            last = m - 1;
+            i = temp[last];
+            while (i >= 0) {
+                const int p = i - suffix_len + 1;
+                if (p >= 0) {
+                    if (x[p] == x[last - suffix_len + 1]) {
+                        temp[last] = i;
+                        last = i;
+                    }
+                    if (GS(row, x[p]) > m - 1 - i) GS(row, x[p]) = m - 1 - i;
+                } else {
+                    temp[last] = i;
+                    last = i;
+                    for (int c = 0; c < ORA_SIGMA; c++)
+                        if (GS(row, c) > m - 1 - i) GS(row, c) = m - 1 - i;
+                }
+                i = temp[i];
+            }
+            temp[last] = -1;
+        }
+    }
+    const int first = GS(1, x[0]);
+    long long count = 0, s0 = m - 1;
+    while (s0 < nn) { /* bfs.c:84-92 */
+        int k;
+        while ((k = bc[t[s0]]) != 0) s0 += k;
+        long long j = s0 - 1;
+        for (k = m - 1; k > 0 && x[k - 1] == t[j]; k--, j--) {}
+        if (k == 0) {
+            if (s0 < nn) count++;
+            s0 += first;
+        } else {
+            s0 += GS(k, t[j]);
+        }
+    }
+#undef GS
+    free(temp);
+    free(gs);
+    free(buf);
+    return count;
+}
+
+static long long ora_search_ffs(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    int bc[ORA_SIGMA], *temx = malloc(sizeof(int) * (size_t)(m + 2));
+    int *gs = malloc(sizeof(int) * (size_t)(m + 1) * ORA_SIGMA);
+    const long long nn = (long long)n;
+    unsigned char *buf = calloc(n + 3 * (size_t)m + 2 * ORA_MARGIN, 1), *t = buf + ORA_MARGIN;
+    memcpy(t, y, n);
+    memset(t + n, x[m - 1], (size_t)m + 1);
+    ora_pre_lastocc(x, m, bc);
+#define GS(i_, c_) gs[(size_t)(i_) * ORA_SIGMA + (c_)]
+    { /* Forward_Suffix_Function, ffs.c:28-50 */
+        for (int i = 0; i <= m; i++)
+            for (int c = 0; c < ORA_SIGMA; c++) GS(i, c) = m + 1;
+        for (int i = 0; i < m; i++) temx[i] = i - 1;
+        for (int suffix_len = 0; suffix_len <= m; suffix_len++) {
+            const int row = m - suffix_len;
+            int last = m - 1, i = temx[last];
+            while (i >= 0) {
+                if (GS(row, x[i + 1]) > m - 1 - i)
+                    if (i - suffix_len < 0 || x[i - suffix_len] != x[m - 1 - suffix_len]) GS(row, x[i + 1]) = m - 1 - i;
+                if (i - suffix_len < 0 || x[i - suffix_len] == x[last - suffix_len]) {
+                    temx[last] = i;
+                    last = i;
+                }
+                i = temx[i];
+            }
+            if (GS(row, x[0]) > m) GS(row, x[0]) = m;
+            temx[last] = -1;
+        }
+    }
+    long long count = memcmp(x, t, (size_t)m) == 0, s0 = m;
+    while (s0 < nn) { /* ffs.c:72-77 */
+        int k;
+        while ((k = bc[t[s0]]) != 0) s0 += k;
+        long long j = s0 - 1;
+        for (k = m - 1; k > 0 && x[k - 1] == t[j]; k--, j--) {}
+        if (!k && s0 < nn) count++;
+        s0 += GS(k, t[s0 + 1]);
+    }
+#undef GS
+    free(temx);
+    free(gs);
+    free(buf);
+    return count;
+}
+
+/* blim.c:30-86 Bit-parallel Length Invariant Matcher: a window of 31 + m characters, one mask per (character, window
+ * position) saying which of the 32 alignments inside the window survive; positions are read in the order m-1, 2m-1,
+ * ..., m-2, ... (ScanOrder, blim.c:53-62) and the window moves by shift[y[i + wsize]].  Reads up to 31 + m characters
+ * behind the text (zero there, as in the driver's page-rounded segment). */
+static long long ora_search_blim(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    const int wsize = 32 - 1 + m;
+    const long long nn = (long long)n;
+    unsigned int *M = malloc(sizeof(unsigned int) * ORA_SIGMA * (size_t)wsize);
+    int *so = malloc(sizeof(int) * (size_t)wsize), shift[ORA_SIGMA], ns = 0;
+    unsigned char *buf = calloc(n + 2 * (size_t)wsize + 2 * ORA_MARGIN, 1), *t = buf + ORA_MARGIN;
+    memcpy(t, y, n);
+    memset(M, 0xff, sizeof(unsigned int) * ORA_SIGMA * (size_t)wsize);
+    for (int i = 0; i < 32; i++) { /* blim.c:44-50 */
+        const unsigned int bit = 1u << i;
+        for (int j = 0; j < m; j++) {
+            for (int c = 0; c < ORA_SIGMA; c++) M[(size_t)(i + j) * ORA_SIGMA + c] &= ~bit;
+            M[(size_t)(i + j) * ORA_SIGMA + x[j]] |= bit;
+        }
+    }
+    for (int c = 0; c < ORA_SIGMA; c++) shift[c] = wsize + 1;
+    for (int i = 0; i < m; i++) shift[x[i]] = wsize - i;
+    for (int i = m - 1; i >= 0; i--)
+        for (int k = i; k < wsize; k += m) so[ns++] = k;
+    long long count = 0, i = 0;
+    while (i < nn) { /* blim.c:67-79 */
+        unsigned int F = M[(size_t)so[0] * ORA_SIGMA + t[i + so[0]]];
+        if (wsize > 1) F &= M[(size_t)so[1] * ORA_SIGMA + t[i + so[1]]];
+        for (int j = 2; F && j < wsize; j++) F &= M[(size_t)so[j] * ORA_SIGMA + t[i + so[j]]];
+        if (F)
+            for (int j = 0; j < 32; j++)
+                if ((F & (1u << j)) && i + j <= nn - m) count++;
+        i += shift[t[i + wsize]];
+    }
+    free(M);
+    free(so);
+    free(buf);
+    return count;
+}
+
 /* fs-w1.c:65-101: fs.c's tables and shifts, the scan starts on the first window's last character */
 static long long ora_search_fsw1(const unsigned char *x, int m, const unsigned char *y, size_t n)
 {
@@ -1971,21 +2236,14 @@ static const struct ora_tier2 {
     const char *name;
     int min_m, min_ratio;
 } ora_tier2[] = {
-    {"faoso2", 3, 0}, /* faoso2.c:56 */
-    {"faoso4", 5, 0}, /* faoso4.c:56 */
-    {"blim", 1, 0},
     {"smoa", 1, 0},
     {"tw", 1, 0},
     {"rcolussi", 1, 0},
     {"fsbndm-w2", 1, 0},
-    {"tndm", 1, 0},
-    {"tndma", 1, 0},
     {"ildm1", 1, 0},
     {"ildm2", 1, 0},
     {"fdm", 1, 0},
     {"ww", 1, 0},
-    {"bfs", 1, 0},
-    {"ffs", 1, 0},
     {"ssef", 32, 0}, /* ssef.c:41 */
 };
 
@@ -2257,6 +2515,12 @@ long long ora_search(const char *algo, const unsigned char *x, int m, const unsi
     if (!strncmp(algo, "ufndmq", 6) && algo[6] && !algo[7]) return ora_search_ufndmq(x, m, y, n, algo[6] - '0');
     if (!strcmp(algo, "bww")) return ora_search_bww(x, m, y, n);
     if (!strcmp(algo, "dbww") || !strcmp(algo, "dbww2")) return ora_search_dbww(x, m, y, n);
+    if (!strcmp(algo, "tndm")) return ora_search_tndm(x, m, y, n, 0);
+    if (!strcmp(algo, "tndma")) return ora_search_tndm(x, m, y, n, 1);
+    if (!strncmp(algo, "faoso", 5) && algo[5] && !algo[6]) return ora_search_faoso(x, m, y, n, algo[5] - '0');
+    if (!strcmp(algo, "bfs")) return ora_search_bfs(x, m, y, n);
+    if (!strcmp(algo, "ffs")) return ora_search_ffs(x, m, y, n);
+    if (!strcmp(algo, "blim")) return ora_search_blim(x, m, y, n);
     if (!strcmp(algo, "wc")) return ora_search_wc(x, m, y, n);
     if (!strcmp(algo, "fs-w1")) return ora_search_fsw1(x, m, y, n);
     if (!strcmp(algo, "wom")) return ora_search_freq100(x, m, y, n, 0);
