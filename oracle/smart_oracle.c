@@ -2086,6 +2086,290 @@ static long long ora_search_blim(const unsigned char *x, int m, const unsigned c
     return count;
 }
 
+/* fsbndm-w2.c:47-98: Forward SBNDM with two windows, one moving up from the start of the text with the masks of the
+ * pattern (B), one moving down from the end with the masks of the reversed pattern (W), their states OR-ed in one
+ * word over the first min(m, 31) characters; both windows are compared in full when the scan returns to where it
+ * started. */
+static long long ora_search_fsbndmw2(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    const int plen = m;
+    if (m > 31) m = 31;
+    unsigned int B[ORA_SIGMA], W[ORA_SIGMA], d = 0;
+    int hbcr[ORA_SIGMA], hbcl[ORA_SIGMA];
+    const int mm1 = m - 1;
+    unsigned char *t = ora_padded(y, n, plen);
+    for (int c = 0; c < ORA_SIGMA; c++) {
+        B[c] = W[c] = 1;
+        hbcr[c] = hbcl[c] = 2 * m;
+    }
+    for (int i = 0; i < m; i++) {
+        B[x[i]] |= 1u << (m - i);
+        W[x[m - 1 - i]] |= 1u << (m - i);
+        hbcr[x[i]] = 2 * m - i - 1;
+        hbcl[x[m - 1 - i]] = 2 * m - i - 1;
+    }
+    long long count = 0, s1 = mm1, s2 = (long long)n - plen;
+    while (s1 <= s2 + mm1) {
+        while (s1 <= s2 + mm1 && (d = (((B[t[s1 + 1]] << 1) & B[t[s1]]) | ((W[t[s2 - 1]] << 1) & W[t[s2]]))) == 0) {
+            s1 += hbcr[t[s1 + m]];
+            s2 -= hbcl[t[s2 - m]];
+        }
+        const long long pos = s1;
+        while ((d = (d + d) & (B[t[s1 - 1]] | W[t[s2 + 1]])) != 0) {
+            --s1;
+            ++s2;
+        }
+        s1 += mm1;
+        s2 -= mm1;
+        if (s1 == pos) {
+            if (ora_whole(x, plen, t, s1 - mm1) && s1 <= s2 + mm1) count++;
+            if (ora_whole(x, plen, t, s2) && s1 < s2 + mm1) count++;
+            ++s1;
+            --s2;
+        }
+    }
+    ora_padded_free(t);
+    return count;
+}
+
+/* smoa.c:25-106 String Matching on Ordered Alphabets: no table; the maximal suffix of what has been matched so far is
+ * maintained incrementally (i', j', k, p) and gives the period to shift by.  The reference orders characters as
+ * plain `char` (signed on the build target, smoa.c:27), and looks one character past the matched prefix - y[n] = 0
+ * at the text end (smart.c:125). */
+static void ora_smoa_next(const unsigned char *w, int len, int *i, int *j, int *k, int *p)
+{
+    while (*j + *k < len) {
+        const signed char a = (signed char)w[*i + *k], b = (signed char)w[*j + *k];
+        if (a == b) {
+            if (*k == *p) {
+                *j += *p;
+                *k = 1;
+            } else {
+                ++*k;
+            }
+        } else if (a > b) {
+            *j += *k;
+            *k = 1;
+            *p = *j - *i;
+        } else {
+            *i = *j;
+            ++*j;
+            *k = *p = 1;
+        }
+    }
+}
+
+static long long ora_search_smoa(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    const long long nn = (long long)n;
+    unsigned char *t = ora_padded(y, n, m);
+    long long count = 0, j = 0;
+    int ip = -1, i = 0, jp = 0, k = 1, p = 1;
+    while (j <= nn - m) {
+        while (i + j < nn && i < m && x[i] == t[i + j]) ++i;
+        if (i == 0) {
+            ++j;
+            ip = -1;
+            jp = 0;
+            k = p = 1;
+        } else {
+            if (i >= m) count++;
+            ora_smoa_next(t + j, i + 1, &ip, &jp, &k, &p);
+            if (ip < 0 || (ip < p && memcmp(t + j, t + j + p, (size_t)ip + 1) == 0)) {
+                j += p;
+                i -= p;
+                if (i < 0) i = 0;
+                if (jp - ip > p) {
+                    jp -= p;
+                } else {
+                    ip = -1;
+                    jp = 0;
+                    k = p = 1;
+                }
+            } else {
+                const int a = ip + 1, b = i - ip - 1 < jp + 1 ? i - ip - 1 : jp + 1;
+                j += (a > b ? a : b) + 1;
+                i = jp = 0;
+                ip = -1;
+                k = p = 1;
+            }
+        }
+    }
+    ora_padded_free(t);
+    return count;
+}
+
+/* tw.c:26-155 Two-Way: critical factorisation from the two maximal suffixes (characters ordered as plain `char`,
+ * tw.c:29), right part left to right, left part right to left, with the memory of the periodic case.  The test
+ * memcmp(x, x + per, ell + 1) of tw.c:101 can look past x[m-1]: the pattern buffer holds 0 there (smart.c:313). */
+static int ora_tw_maxsuf(const unsigned char *x, int m, int *p, int tilde)
+{
+    int ms = -1, j = 0, k = 1;
+    *p = 1;
+    while (j + k < m) {
+        const signed char a = (signed char)x[j + k], b = (signed char)x[ms + k];
+        if (tilde ? a > b : a < b) {
+            j += k;
+            k = 1;
+            *p = j - ms;
+        } else if (a == b) {
+            if (k != *p) {
+                ++k;
+            } else {
+                j += *p;
+                k = 1;
+            }
+        } else {
+            ms = j;
+            j = ms + 1;
+            k = *p = 1;
+        }
+    }
+    return ms;
+}
+
+static long long ora_search_tw(const unsigned char *x0, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    unsigned char *x = calloc(2 * (size_t)m + 8, 1);
+    memcpy(x, x0, (size_t)m);
+    int p, q, ell, per;
+    const int i0 = ora_tw_maxsuf(x, m, &p, 0), j0 = ora_tw_maxsuf(x, m, &q, 1);
+    if (i0 > j0) {
+        ell = i0;
+        per = p;
+    } else {
+        ell = j0;
+        per = q;
+    }
+    const long long nn = (long long)n;
+    long long count = 0, j = 0;
+    if (memcmp(x, x + per, (size_t)ell + 1) == 0) {
+        int memory = -1;
+        while (j <= nn - m) {
+            int i = (ell > memory ? ell : memory) + 1;
+            while (i < m && x[i] == y[i + j]) ++i;
+            if (i >= m) {
+                i = ell;
+                while (i > memory && x[i] == y[i + j]) --i;
+                if (i <= memory) count++;
+                j += per;
+                memory = m - per - 1;
+            } else {
+                j += i - ell;
+                memory = -1;
+            }
+        }
+    } else {
+        per = (ell + 1 > m - ell - 1 ? ell + 1 : m - ell - 1) + 1;
+        while (j <= nn - m) {
+            int i = ell + 1;
+            while (i < m && x[i] == y[i + j]) ++i;
+            if (i >= m) {
+                i = ell;
+                while (i >= 0 && x[i] == y[i + j]) --i;
+                if (i < 0) count++;
+                j += per;
+            } else {
+                j += i - ell;
+            }
+        }
+    }
+    free(x);
+    return count;
+}
+
+/* rcolussi.c:26-123 Reverse Colussi: positions are compared in the order h[1..m-1] that preRc derives from the
+ * pattern's periodicities (hmin, kmin, rmin), the shift after a mismatch at step i is rcGs[i]; while the window's
+ * last character is wrong the shift comes from rcBc[character][previous shift].  The arrays are sized with the same
+ * slack the reference's XSIZE-sized locals give the construction. */
+static long long ora_search_rcolussi(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    const size_t w = (size_t)m + 2, big = 2 * (size_t)m + 8;
+    int *rcBc = calloc(ORA_SIGMA * w, sizeof(int)), *rcGs = calloc(big, sizeof(int)), *h = calloc(big, sizeof(int));
+    int *hmin = calloc(big, sizeof(int)), *kmin = calloc(big, sizeof(int)), *link = calloc(big, sizeof(int)),
+        *rmin = calloc(big, sizeof(int)), locc[ORA_SIGMA];
+    const long long nn = (long long)n;
+    unsigned char *t = ora_padded(y, n, m);
+    { /* preRc, rcolussi.c:26-94 */
+        int i, j, k, q, r = 0;
+        for (int a = 0; a < ORA_SIGMA; a++) locc[a] = -1;
+        link[0] = -1;
+        for (i = 0; i < m - 1; i++) {
+            link[i + 1] = locc[x[i]];
+            locc[x[i]] = i;
+        }
+        for (int a = 0; a < ORA_SIGMA; a++)
+            for (int sft = 1; sft <= m; sft++) {
+                i = locc[a];
+                j = link[m - sft];
+                while (i - j != sft && j >= 0) {
+                    if (i - j > sft) i = link[i + 1];
+                    else j = link[j + 1];
+                }
+                while (i - j > sft) i = link[i + 1];
+                rcBc[(size_t)a * w + sft] = m - i - 1;
+            }
+        k = 1;
+        i = m - 1;
+        while (k <= m) {
+            while (i - k >= 0 && x[i - k] == x[i]) --i;
+            hmin[k] = i;
+            q = k + 1;
+            while (hmin[q - k] - (q - k) > i) {
+                hmin[q] = hmin[q - k];
+                ++q;
+            }
+            i += q - k;
+            k = q;
+            if (i == m) i = m - 1;
+        }
+        for (k = m; k > 0; k--) kmin[hmin[k]] = k;
+        for (i = m - 1; i >= 0; i--) {
+            if (hmin[i + 1] == i) r = i + 1;
+            rmin[i] = r;
+        }
+        i = 1;
+        for (k = 1; k <= m; k++)
+            if (hmin[k] != m - 1 && kmin[hmin[k]] == k) {
+                h[i] = hmin[k];
+                rcGs[i++] = k;
+            }
+        i = m - 1;
+        for (j = m - 2; j >= 0; j--)
+            if (kmin[j] == 0) {
+                h[i] = j;
+                rcGs[i--] = rmin[j];
+            }
+        rcGs[m] = rmin[0];
+    }
+    long long count = 0, j = 0;
+    int sft = m;
+    while (j <= nn - m) { /* rcolussi.c:106-118 */
+        while (j <= nn - m && x[m - 1] != t[j + m - 1]) {
+            sft = rcBc[(size_t)t[j + m - 1] * w + sft];
+            j += sft;
+        }
+        int i = 1;
+        while (i < m && x[h[i]] == t[j + h[i]]) i++;
+        if (i >= m && j <= nn - m) count++;
+        sft = rcGs[i];
+        j += sft;
+    }
+    free(rcBc);
+    free(rcGs);
+    free(h);
+    free(hmin);
+    free(kmin);
+    free(link);
+    free(rmin);
+    ora_padded_free(t);
+    return count;
+}
+
 /* fs-w1.c:65-101: fs.c's tables and shifts, the scan starts on the first window's last character */
 static long long ora_search_fsw1(const unsigned char *x, int m, const unsigned char *y, size_t n)
 {
@@ -2236,10 +2520,6 @@ static const struct ora_tier2 {
     const char *name;
     int min_m, min_ratio;
 } ora_tier2[] = {
-    {"smoa", 1, 0},
-    {"tw", 1, 0},
-    {"rcolussi", 1, 0},
-    {"fsbndm-w2", 1, 0},
     {"ildm1", 1, 0},
     {"ildm2", 1, 0},
     {"fdm", 1, 0},
@@ -2521,6 +2801,10 @@ long long ora_search(const char *algo, const unsigned char *x, int m, const unsi
     if (!strcmp(algo, "bfs")) return ora_search_bfs(x, m, y, n);
     if (!strcmp(algo, "ffs")) return ora_search_ffs(x, m, y, n);
     if (!strcmp(algo, "blim")) return ora_search_blim(x, m, y, n);
+    if (!strcmp(algo, "fsbndm-w2")) return ora_search_fsbndmw2(x, m, y, n);
+    if (!strcmp(algo, "smoa")) return ora_search_smoa(x, m, y, n);
+    if (!strcmp(algo, "tw")) return ora_search_tw(x, m, y, n);
+    if (!strcmp(algo, "rcolussi")) return ora_search_rcolussi(x, m, y, n);
     if (!strcmp(algo, "wc")) return ora_search_wc(x, m, y, n);
     if (!strcmp(algo, "fs-w1")) return ora_search_fsw1(x, m, y, n);
     if (!strcmp(algo, "wom")) return ora_search_freq100(x, m, y, n, 0);
