@@ -2370,6 +2370,172 @@ static long long ora_search_rcolussi(const unsigned char *x, int m, const unsign
     return count;
 }
 
+/* The suffix automaton of include/AUTOMATON.h:135-182 (buildSimpleSuffixAutomaton): state 0 is the initial state,
+ * state 1 the artificial one its suffix link points to; at most 2m + 2 states.  trans is dense, -1 = undefined. */
+typedef struct {
+    int *trans, *length, *suffix;
+    unsigned char *terminal;
+} ora_sam_t;
+
+static void ora_sam_build(const unsigned char *x, int m, ora_sam_t *a)
+{
+    const size_t states = 3 * (size_t)m + 3;
+    a->trans = malloc(states * ORA_SIGMA * sizeof(int));
+    memset(a->trans, -1, states * ORA_SIGMA * sizeof(int));
+    a->length = calloc(states, sizeof(int));
+    a->suffix = calloc(states, sizeof(int));
+    a->terminal = calloc(states, 1);
+    const int init = 0, art = 1;
+    int counter = 2, last = init;
+    a->suffix[init] = art;
+#define T(p_, c_) a->trans[(size_t)(p_) * ORA_SIGMA + (c_)]
+    for (int i = 0; i < m; i++) {
+        const unsigned char c = x[i];
+        int p = last;
+        const int q = counter++;
+        a->length[q] = a->length[p] + 1;
+        while (p != init && T(p, c) == -1) {
+            T(p, c) = q;
+            p = a->suffix[p];
+        }
+        if (T(p, c) == -1) {
+            T(init, c) = q;
+            a->suffix[q] = init;
+        } else if (a->length[p] + 1 == a->length[T(p, c)]) {
+            a->suffix[q] = T(p, c);
+        } else {
+            const int r = counter++, old = T(p, c);
+            memcpy(&T(r, 0), &T(old, 0), ORA_SIGMA * sizeof(int));
+            a->length[r] = a->length[p] + 1;
+            a->suffix[r] = a->suffix[old];
+            a->suffix[old] = r;
+            a->suffix[q] = r;
+            while (p != art && a->length[T(p, c)] >= a->length[r]) {
+                T(p, c) = r;
+                p = a->suffix[p];
+            }
+        }
+        last = q;
+    }
+    a->terminal[last] = 1;
+    while (last != init) {
+        last = a->suffix[last];
+        a->terminal[last] = 1;
+    }
+}
+
+#undef T
+#define T(p_, c_) a.trans[(size_t)(p_) * ORA_SIGMA + (c_)]
+
+static void ora_sam_free(ora_sam_t *a)
+{
+    free(a->trans);
+    free(a->length);
+    free(a->suffix);
+    free(a->terminal);
+}
+
+void ora_pre_aut(const unsigned char *x, int m, int *ttrans); /* (preSMA, defined with the automaton scan below) */
+
+/* fdm.c:27-76 Forward DAWG Matching: the longest pattern factor ending at every text position */
+static long long ora_search_fdm(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    ora_sam_t a;
+    ora_sam_build(x, m, &a);
+    long long count = 0;
+    int ell = 0, state = 0;
+    for (size_t j = 0; j < n; j++) {
+        if (T(state, y[j]) != -1) {
+            ++ell;
+            state = T(state, y[j]);
+        } else {
+            while (state != 0 && T(state, y[j]) == -1) state = a.suffix[state];
+            if (T(state, y[j]) != -1) {
+                ell = a.length[state] + 1;
+                state = T(state, y[j]);
+            } else {
+                ell = 0;
+                state = 0;
+            }
+        }
+        if (ell == m) count++;
+    }
+    ora_sam_free(&a);
+    return count;
+}
+
+/* ildm1.c:28-76 (variant 1) and ildm2.c:40-92 (variant 2): the window is read right to left through the suffix
+ * automaton of the reversed pattern (R = the longest pattern prefix that ends the window), then the string-matching
+ * automaton continues forward from state R while it stays above 0 (ildm1) / above m/2 (ildm2) */
+static long long ora_search_ildm(const unsigned char *x, int m, const unsigned char *y, size_t n, int variant)
+{
+    if ((size_t)m > n) return 0;
+    unsigned char *xr = malloc((size_t)m);
+    for (int i = 0; i < m; i++) xr[i] = x[m - 1 - i];
+    ora_sam_t a;
+    ora_sam_build(xr, m, &a);
+    int *sma = malloc((size_t)(m + 1) * ORA_SIGMA * sizeof(int));
+    ora_pre_aut(x, m, sma);
+    const long long nn = (long long)n;
+    const int floor_r = variant == 2 ? m / 2 : 0;
+    long long count = 0, k = m - 1;
+    while (k < nn) {
+        int L = 0, R = 0, l = 0;
+        while (k - l >= 0 && (L = T(L, y[k - l])) != -1) {
+            l++;
+            if (a.terminal[L]) R = l;
+        }
+        while (R > floor_r) {
+            if (R == m) count++;
+            k++;
+            if (k >= nn) break;
+            R = sma[R * ORA_SIGMA + y[k]];
+        }
+        k += variant == 2 ? m - R : m;
+    }
+    free(sma);
+    free(xr);
+    ora_sam_free(&a);
+    return count;
+}
+
+/* ww.c:26-98 Wide Window: every m-th character is a window centre; the suffix automaton of the pattern reads forward
+ * from it (L = the longest pattern suffix that is a prefix of what follows), then the automaton of the reversed
+ * pattern (preSMARev, ww.c:26-37) reads backward from state L */
+static long long ora_search_ww(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if ((size_t)m > n) return 0;
+    ora_sam_t a;
+    ora_sam_build(x, m, &a);
+    unsigned char *xr = malloc((size_t)m);
+    for (int i = 0; i < m; i++) xr[i] = x[m - 1 - i];
+    int *sma = malloc((size_t)(m + 1) * ORA_SIGMA * sizeof(int));
+    ora_pre_aut(xr, m, sma); /* preSMARev(x) is preSMA of the reversed pattern */
+    const long long nn = (long long)n;
+    long long count = 0, end = nn / m + (nn % m > 0);
+    for (long long k = 1; k < end; k++) {
+        const long long c = k * m - 1;
+        int R = 0, L = 0, r = 0, ell = 0;
+        while (R != -1 && c + r < nn) {
+            R = T(R, y[c + r]);
+            ++r;
+            if (R != -1 && a.terminal[R]) L = r;
+        }
+        while (L > ell) {
+            if (L == m) count++;
+            ++ell;
+            if (ell == m) break;
+            L = sma[L * ORA_SIGMA + y[c - ell]];
+        }
+    }
+    for (long long k = (end - 1) * m; k <= nn - m; k++) count += memcmp(x, y + k, (size_t)m) == 0;
+    free(sma);
+    free(xr);
+    ora_sam_free(&a);
+    return count;
+}
+#undef T
+
 /* fs-w1.c:65-101: fs.c's tables and shifts, the scan starts on the first window's last character */
 static long long ora_search_fsw1(const unsigned char *x, int m, const unsigned char *y, size_t n)
 {
@@ -2520,10 +2686,6 @@ static const struct ora_tier2 {
     const char *name;
     int min_m, min_ratio;
 } ora_tier2[] = {
-    {"ildm1", 1, 0},
-    {"ildm2", 1, 0},
-    {"fdm", 1, 0},
-    {"ww", 1, 0},
     {"ssef", 32, 0}, /* ssef.c:41 */
 };
 
@@ -2805,6 +2967,10 @@ long long ora_search(const char *algo, const unsigned char *x, int m, const unsi
     if (!strcmp(algo, "smoa")) return ora_search_smoa(x, m, y, n);
     if (!strcmp(algo, "tw")) return ora_search_tw(x, m, y, n);
     if (!strcmp(algo, "rcolussi")) return ora_search_rcolussi(x, m, y, n);
+    if (!strcmp(algo, "fdm")) return ora_search_fdm(x, m, y, n);
+    if (!strcmp(algo, "ildm1")) return ora_search_ildm(x, m, y, n, 1);
+    if (!strcmp(algo, "ildm2")) return ora_search_ildm(x, m, y, n, 2);
+    if (!strcmp(algo, "ww")) return ora_search_ww(x, m, y, n);
     if (!strcmp(algo, "wc")) return ora_search_wc(x, m, y, n);
     if (!strcmp(algo, "fs-w1")) return ora_search_fsw1(x, m, y, n);
     if (!strcmp(algo, "wom")) return ora_search_freq100(x, m, y, n, 0);
