@@ -3,9 +3,9 @@
  *
  * A plain-C CPU restatement of the reference's (ostafen/smart) exact-string-matching path:
  * the brute-force result that defines every algorithm's count, the preprocessing tables of
- * the north-star algorithm families, and each family's sequential scan: 113 of the 143 registered algorithms
+ * the north-star algorithm families, and each family's sequential scan: all 143 registered algorithms
  * (round 1: 40; round 2 added wfr, wfrq2..8, skip3/5/6/7/8, zt, aut, bom, ebom, sbndm2 and the "second batch" near the
- * end of the file); the other 30 are covered by result specification + domain rule, see "Tier 2" below.  Only tests/,
+ * end of the file).  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
  * file's shared object; nothing under smart_b200/ links or calls it.
  *
@@ -2536,6 +2536,41 @@ static long long ora_search_ww(const unsigned char *x, int m, const unsigned cha
 }
 #undef T
 
+/* ssef.c:39-118 SSE filtering (m >= 32): the filter value of 16 consecutive characters is the word of their top bits
+ * (_mm_movemask_epi8, ssef.c:97); every alignment i of the pattern over a 16-byte text block that lies wholly inside
+ * it is filed under the filter value of the pattern characters that would cover the block (:61-84); the text is
+ * sampled every (m/16 - 1)-th block and the alignments filed under its value are compared (:93-108).  Scalar here. */
+static long long ora_search_ssef(const unsigned char *x, int m, const unsigned char *y, size_t n)
+{
+    if (m < 32) return -1;
+    if ((size_t)m > n) return 0;
+    const int last = m / 16 - 1, npos = last * 16;
+    int *head = malloc(sizeof(int) * 65536), *tail = malloc(sizeof(int) * 65536), *next = malloc(sizeof(int) * (size_t)(npos + 1));
+    for (int v = 0; v < 65536; v++) head[v] = tail[v] = -1;
+    for (int i = 0; i < npos; i++) { /* lists keep the order of insertion (ssef.c:70-83) */
+        const int j = npos - i;
+        unsigned v = 0;
+        for (int b = 0; b < 16; b++) v |= (unsigned)(x[j + b] >> 7) << b;
+        next[i] = -1;
+        if (head[v] < 0) head[v] = i;
+        else next[tail[v]] = i;
+        tail[v] = i;
+    }
+    const long long nn = (long long)n, blocks = nn / 16;
+    long long count = 0;
+    for (long long c = last; c < blocks; c += last) {
+        unsigned v = 0;
+        for (int b = 0; b < 16; b++) v |= (unsigned)(y[16 * c + b] >> 7) << b;
+        const long long base = (c - last) * 16;
+        for (int e = head[v]; e >= 0; e = next[e])
+            if (base + e + m <= nn && memcmp(x, y + base + e, (size_t)m) == 0) count++;
+    }
+    free(head);
+    free(tail);
+    free(next);
+    return count;
+}
+
 /* fs-w1.c:65-101: fs.c's tables and shifts, the scan starts on the first window's last character */
 static long long ora_search_fsw1(const unsigned char *x, int m, const unsigned char *y, size_t n)
 {
@@ -2677,17 +2712,9 @@ static long long ora_search_wfrx(const unsigned char *x, int m, const unsigned c
 }
 
 /* ------------------------------------------------------------------------------------------
- * Tier 2: the reference algorithms without a restated scan that agree with bf.c on every golden input (SURVEY.md Appendix A
- * "always clean", minus kbndm, ksa and ssm which the golden sweep caught).  Their scans are NOT restated
- * here: each of them returns the brute-force count (bf.c:33-36) outside its `return -1` domain, so the
- * oracle for them is that count plus the guard, and the pin is the recorded output of the unmodified
- * sources (oracle/_ref/<name>.so -> tests/golden/counts.json).  {name, smallest m, smallest n/m}. */
-static const struct ora_tier2 {
-    const char *name;
-    int min_m, min_ratio;
-} ora_tier2[] = {
-    {"ssef", 32, 0}, /* ssef.c:41 */
-};
+ * (Round 1 kept a "tier 2" here: algorithms covered by result specification + `return -1` domain only.  Since the end
+ * of round 2 every registered algorithm has a restated scan above or below, checked against the recorded outputs
+ * of the unmodified sources (tests/golden/counts.json) and against the compiled reference on fresh random inputs.) */
 
 /* aut.c:26-45 with preSMA (include/AUTOMATON.h:185-198): the automaton is grown state by state; the new state's
  * row is a copy of the row of the state the old transition on x[i] led to.  ttrans has (m+1)*256 ints. */
@@ -2879,18 +2906,11 @@ static long long ora_search_sbndm2(const unsigned char *x, int m, const unsigned
     return count;
 }
 
-int ora_tier2_count(void) { return (int)(sizeof ora_tier2 / sizeof ora_tier2[0]); }
-const char *ora_tier2_name(int i) { return i >= 0 && i < ora_tier2_count() ? ora_tier2[i].name : NULL; }
-
-static long long ora_search_tier2(const char *algo, const unsigned char *x, int m, const unsigned char *y, size_t n)
+int ora_tier2_count(void) { return 0; } /* (kept for callers of the round-1 interface) */
+const char *ora_tier2_name(int i)
 {
-    for (int i = 0; i < ora_tier2_count(); i++)
-        if (!strcmp(algo, ora_tier2[i].name)) {
-            if (m < ora_tier2[i].min_m) return -1;
-            if (ora_tier2[i].min_ratio && n / (size_t)m < (size_t)ora_tier2[i].min_ratio) return -1;
-            return (long long)ora_bf_count_fast(x, (size_t)m, y, n);
-        }
-    return -2;
+    (void)i;
+    return NULL;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -2971,6 +2991,7 @@ long long ora_search(const char *algo, const unsigned char *x, int m, const unsi
     if (!strcmp(algo, "ildm1")) return ora_search_ildm(x, m, y, n, 1);
     if (!strcmp(algo, "ildm2")) return ora_search_ildm(x, m, y, n, 2);
     if (!strcmp(algo, "ww")) return ora_search_ww(x, m, y, n);
+    if (!strcmp(algo, "ssef")) return ora_search_ssef(x, m, y, n);
     if (!strcmp(algo, "wc")) return ora_search_wc(x, m, y, n);
     if (!strcmp(algo, "fs-w1")) return ora_search_fsw1(x, m, y, n);
     if (!strcmp(algo, "wom")) return ora_search_freq100(x, m, y, n, 0);
@@ -2980,7 +3001,7 @@ long long ora_search(const char *algo, const unsigned char *x, int m, const unsi
     if (!strncmp(algo, "twfrq", 5) && algo[5] >= '2' && algo[5] <= '8' && !algo[6])
         return ora_search_wfrx(x, m, y, n, algo[5] - '0', algo[5] - '0', 1);
     if (!strncmp(algo, "twfr", 4) && algo[4] >= '2' && algo[4] <= '8' && !algo[5]) return ora_search_wfrx(x, m, y, n, 0, algo[4] - '0', 1);
-    return ora_search_tier2(algo, x, m, y, n);
+    return -2;
 }
 
 /* glibc rand() stream of textgen.c:34-54: srand is never called => seed 1; the stream continues

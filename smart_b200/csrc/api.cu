@@ -1495,10 +1495,12 @@ int sb_set_device(int device)
 int sb_get_device(void) { return host_device(); }
 
 /* the reference's `return -1` guards: m below the algorithm's minimum (hash3.c:31, raita.c:38, qf23.c:44, ...)
- * or, for the double-window searches, a text shorter than two patterns (dbww.c:35) */
+ * or, for the double-window searches, a text shorter than two windows - where the window is the pattern already cut
+ * to 16 characters (dbww.c:33-35: `if (m > 16) m = 16; if ((n/m) < 2) return -1;`) */
 static bool outside_domain(const sb_algo_desc *d, int m, unsigned long long n)
 {
-    return m < d->min_m || (d->min_ratio > 0 && n / (unsigned long long)m < (unsigned long long)d->min_ratio);
+    const unsigned long long window = m > 16 ? 16 : m;
+    return m < d->min_m || (d->min_ratio > 0 && n / window < (unsigned long long)d->min_ratio);
 }
 
 /* ---- asynchronous searches: tickets ------------------------------------------------------------------

@@ -95,8 +95,8 @@ static const sb_algo_desc g_algos[] = {
     {"bxs6", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 6, 0}, /* bxs6.c:30, m<6 -> -1 (:33) */
     {"bxs8", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 8, 0}, /* bxs8.c:30, m<8 -> -1 (:33) */
     {"bww", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* bww.c:28 */
-    {"dbww", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 2}, /* dbww.c:28, n/m<2 -> -1 (:35) */
-    {"dbww2", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 2}, /* dbww2.c:31, n/m<2 -> -1 (:38) */
+    {"dbww", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 2}, /* dbww.c:28, n/min(m,16)<2 -> -1 (:33-35) */
+    {"dbww2", SB_FAM_BNDMX, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 2}, /* dbww2.c:31, n/min(m,16)<2 -> -1 (:36-38) */
     {"bom", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* bom.c:77 */
     {"bom2", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 1, 0}, /* bom2.c:28 */
     {"ebom", SB_FAM_FACTOR, SB_ANCHOR_SUFFIX, 0, 0, 0, 2, 0}, /* ebom.c:28, m<2 -> -1 (:35) */

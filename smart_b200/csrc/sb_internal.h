@@ -58,7 +58,7 @@ typedef struct sb_algo_desc {
     int q;     /* HASHq rank */
     int Q, S;  /* QF parameters; WFR: Q = q-gram length of the wfrq/twfrq variants */
     int min_m; /* smaller m -> -1, as the reference */
-    int min_ratio; /* n / m below this -> -1 (dbww.c:35); 0 = no such rule */
+    int min_ratio; /* n / min(m, 16) below this -> -1 (dbww.c:33-35); 0 = no such rule */
 } sb_algo_desc;
 
 const sb_algo_desc *sb_algo_desc_get(int algo);

@@ -16,9 +16,9 @@ ALGOS = (
     "bndm", "br", "tvsbs", "fjs", "ssabs", "ts",
     "skip", "kmpskip", "fs", "graspm",
 )
-# tier 1: the first batch, scans restated in oracle/smart_oracle.c in round 1.  Tier 2: the second batch - 83 of its
-# scans are restated by now as well, 30 are result specification + -1 domain only (smart_oracle.c "Tier 2"); all are
-# pinned by the recorded outputs of the unmodified reference (counts.json)
+# tier 1: the first batch, scans restated in oracle/smart_oracle.c in round 1.  Tier 2: the second batch, restated in
+# round 2 (until then: result specification + -1 domain only); all are pinned by the recorded outputs of the unmodified
+# reference (counts.json)
 TIER1 = ALGOS
 TIER2 = (
     "aoso2", "aoso4", "aoso6", "faoso2", "faoso4", "svm0", "blim", "ufndmq2", "ufndmq4", "ufndmq6", "ufndmq8", "aut",
@@ -58,7 +58,7 @@ def expected(algo: str, m: int, bf: int, n=None) -> int:
     """what the reference returns for a pattern of length m whose true count is bf"""
     if m < min_m(algo):
         return -1
-    if n is not None and algo in MIN_RATIO and n // m < MIN_RATIO[algo]:
+    if n is not None and algo in MIN_RATIO and n // min(m, 16) < MIN_RATIO[algo]:  # dbww.c:33-35: m is cut to 16 first
         return -1
     return bf
 
