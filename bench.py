@@ -396,10 +396,10 @@ def main_ours(args, algos, ms):
     # ---- the algorithm axis: the same searches with each algorithm's OWN table driving the scan on the device
     # (SB_FLAG_TABLE_SCAN: kmpNext / hbc / Shift-Or masks in shared memory, table_kernels.cuh); bf has no table
     table_scan = {}
-    try:
-        for a in algos:
-            if a == "bf":
-                continue
+    for a in list(algos) + [b for b in ("bm", "kr", "hash3", "qf23") if b not in algos]:  # (+ the other SURVEY 8(a) families)
+        if a == "bf":
+            continue
+        try:
             row = {}
             for m in ms:
                 r = sb.search(a, text, pats[m], flags=sb.FLAG_TABLE_SCAN)
@@ -407,8 +407,8 @@ def main_ours(args, algos, ms):
                 if tm.filter_kind in range(601, 652) and r.count == sb.search(a, text, pats[m]).count:
                     row[str(m)] = own / (tm.kernel_ms * 1e-3) / 1e9
             table_scan[a] = row
-    except Exception as e:  # an extra, never fatal
-        table_scan = {"error": repr(e)}
+        except Exception as e:  # an extra, never fatal
+            table_scan[a] = {"error": repr(e)}
 
     # ---- (f)-3 extra: the driver's real shape, 500 patterns of one length, counted in ONE pass
     multi = None
