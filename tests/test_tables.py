@@ -256,3 +256,57 @@ def test_bom_factor_oracle_equals_the_reference_builder(oracle):
                 for c in set(x.tolist()) | {0, 255}:
                     got = ref.L.getTransition(x.ctypes.data_as(C.c_void_p), C.c_int(p), L, C.c_ubyte(c))
                     assert got == trans[p, c], (m, p, c)
+
+
+def test_round2_bucket_and_run_builders_follow_their_definitions():
+    """sb_prep_skipq (skip3.c:33-42, skip5.c:36-45) and sb_prep_bsdm (bsdm.c:33-55, bsdm4.c:38-66) feed the table-driven
+    kernels only; the GPU tests pin them through counts, this pins them on the CPU by their definitions: every pattern
+    q-gram filed exactly once under its hash, newest first; the first longest run of pairwise distinct q-grams."""
+    import ctypes as C
+
+    L = sb.lib()
+    rng = np.random.default_rng(2026)
+
+    def skip_hash(p, Q):
+        if Q == 3:
+            return (int(p[0]) << 4) + (int(p[1]) << 2) + int(p[2])
+        return sum(int(p[k]) << (Q - 1 - k) for k in range(Q))
+
+    def bsdm_hash(p, Q):
+        step = 2 if Q == 4 else 1
+        return sum(int(p[t]) << (step * (Q - 1 - t)) for t in range(Q)) & 0xFFFF
+
+    for sigma in (2, 4, 20, 256):
+        for m in (8, 9, 31, 64, 257):
+            x = rng.integers(0, sigma, m, dtype=np.uint8)
+            xp = x.ctypes.data_as(C.c_void_p)
+            for Q in (3, 5, 6, 7, 8):
+                head = np.zeros(65536, dtype=np.int32)
+                nxt = np.zeros(m, dtype=np.int32)
+                L.sb_prep_skipq(xp, C.c_int(m), C.c_int(Q), head.ctypes.data_as(C.c_void_p), nxt.ctypes.data_as(C.c_void_p))
+                want = {}
+                for i in range(m - Q + 1):
+                    want.setdefault(skip_hash(x[i:i + Q], Q), []).insert(0, i)
+                assert set(np.nonzero(head >= 0)[0].tolist()) == set(want)
+                for h, offs in want.items():
+                    got, e = [], int(head[h])
+                    while e >= 0:
+                        got.append(e)
+                        e = int(nxt[e])
+                    assert got == offs, (sigma, m, Q, h)
+            for Q in (1, 4, 5, 7, 8):
+                pos = np.zeros(65536, dtype=np.int32)
+                st, ln = C.c_int(-1), C.c_int(-1)
+                L.sb_prep_bsdm(xp, C.c_int(m), C.c_int(Q), pos.ctypes.data_as(C.c_void_p), C.byref(st), C.byref(ln))
+                g = [bsdm_hash(x[i:i + Q], Q) for i in range(m - Q + 1)]
+                best_st, best_len, j = 0, 0, 0
+                for i in range(len(g)):  # the longest window of pairwise distinct grams ending at i starts at j
+                    while g[i] in g[j:i]:
+                        j += 1
+                    if i - j + 1 > best_len:
+                        best_st, best_len = j, i - j + 1
+                assert (st.value, ln.value) == (best_st, best_len), (sigma, m, Q)
+                want_pos = np.full(65536, -1, dtype=np.int32)
+                for i in range(best_len):
+                    want_pos[g[best_st + i]] = i
+                assert np.array_equal(pos, want_pos), (sigma, m, Q)
