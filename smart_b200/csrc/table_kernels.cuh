@@ -80,6 +80,14 @@
  * automata stream 256-bit vectors instead, see stream_segment) - which is why these are a selectable mode and not
  * the default.
  * What they return is bit-identical to everything else: the count of bf.c:33-36.
+ *
+ * Reads behind a window.  Some shift rules look at text behind the window they have just compared (qs, smith, ssabs,
+ * wc, wom, fbom: one character; br, tvsbs, tsw, tvsbs-w2, zt's pair: two; qlqs: m/2; iom: up to m).  A shard keeps
+ * SB_XSIZE-1 bytes of halo behind the start positions it owns, so such a read can land in the zero padding (last shard:
+ * behind the text; other shards, m near the maximum: behind the halo).  That is harmless because every one of these
+ * rules uses the character at a position p only to rule out windows that CONTAIN p: with p >= own + SB_XSIZE-1 those
+ * windows start at p-m+1 >= own or later - not this shard's - and behind the text they are no windows at all.  The
+ * same holds on the left for the two-ended scans (a window containing a position before local byte 0 is not owned).
  */
 #pragma once
 #include "scan_kernels.cuh"
