@@ -82,7 +82,7 @@
  * What they return is bit-identical to everything else: the count of bf.c:33-36.
  *
  * Reads behind a window.  Some shift rules look at text behind the window they have just compared (qs, smith, ssabs,
- * wc, wom, fbom: one character; br, tvsbs, tsw, tvsbs-w2, zt's pair: two; qlqs: m/2; iom: up to m).  A shard keeps
+ * wc, wom, fbom: one character; br, tvsbs, tsw, tvsbs-w2: two; qlqs: m/2; iom: up to m).  A shard keeps
  * SB_XSIZE-1 bytes of halo behind the start positions it owns, so such a read can land in the zero padding (last shard:
  * behind the text; other shards, m near the maximum: behind the halo).  That is harmless because every one of these
  * rules uses the character at a position p only to rule out windows that CONTAIN p: with p >= own + SB_XSIZE-1 those
